@@ -1,0 +1,262 @@
+"""Test infrastructure: generate tests/golden/*.npz by running the UNMODIFIED reference
+(funsor 0.4.8 from /root/reference, imported through oracle/ref_boot.py) on seeded
+inputs.  Run in the build container only:
+
+    python -m oracle.make_golden
+
+The fixtures are committed; the GPU box never runs this script.  Every array is stored
+with its inputs so that tests can replay the same inputs through the oracle
+(tests/test_oracle_golden.py, CPU) and through the CUDA path (tests/test_*_gpu.py).
+"""
+import importlib.util
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def main():
+    sys.path.insert(0, ROOT)
+    from oracle import ref_boot
+
+    funsor = ref_boot.boot("float64")
+    import torch
+
+    import funsor.ops as ops
+    from funsor.adjoint import AdjointTape
+    from funsor.cnf import Contraction
+    from funsor.domains import Bint, Reals
+    from funsor.gaussian import Gaussian
+    from funsor.sum_product import (
+        MarkovProduct,
+        mixed_sequential_sum_product,
+        naive_sequential_sum_product,
+        sequential_sum_product,
+    )
+    from funsor.tensor import Tensor
+    from funsor.terms import Variable
+    from funsor.testing import random_gaussian
+
+    os.makedirs(GOLDEN, exist_ok=True)
+    SEMI = {"log": (ops.logaddexp, ops.add), "max": (ops.max, ops.add)}
+
+    def tfun(data, names):
+        return Tensor(data, OrderedDict((n, Bint[s]) for n, s in zip(names, data.shape)))
+
+    def to_bij(f, names):
+        return _np(f.align(tuple(names)).data)
+
+    # ------------------------------------------------------------------ pair products (a6 / a7)
+    out = {}
+    torch.manual_seed(11)
+    for name, (B, T, S) in {"p0": (1, 1, 2), "p1": (2, 3, 3), "p2": (3, 5, 16), "p3": (2, 2, 33)}.items():
+        x = torch.randn(B, T, S, S)
+        y = torch.randn(B, T, S, S)
+        if name == "p1":  # -inf handling incl. a fully masked row / column (A.2)
+            x[0, 0, 1, :] = -float("inf")
+            y[0, 0, :, 2] = -float("inf")
+            x[1, 1, 0, 1] = -float("inf")
+            y[1, 2, 1, 1] = -float("inf")
+        fx = tfun(x, ["b", "t", "i", "k"])
+        fy = tfun(y, ["b", "t", "k", "j"])
+        out[name + "/x"] = _np(x)
+        out[name + "/y"] = _np(y)
+        for sname, (sop, pop) in SEMI.items():
+            z = Contraction(sop, pop, frozenset({Variable("k", Bint[S])}), fx, fy)
+            assert isinstance(z, Tensor), type(z)
+            out[name + "/" + sname] = to_bij(z, ["b", "t", "i", "j"])
+    # non-square contraction (I,K,J differ) through the same rules
+    x = torch.randn(2, 4, 5)
+    y = torch.randn(2, 5, 3)
+    out["rect/x"], out["rect/y"] = _np(x), _np(y)
+    for sname, (sop, pop) in SEMI.items():
+        z = Contraction(sop, pop, frozenset({Variable("k", Bint[5])}), tfun(x, ["b", "i", "k"]), tfun(y, ["b", "k", "j"]))
+        out["rect/" + sname] = to_bij(z, ["b", "i", "j"])
+    np.savez_compressed(os.path.join(GOLDEN, "pair_product.npz"), **out)
+
+    # ------------------------------------------------------------------ scans (a1-a4)
+    out = {}
+    torch.manual_seed(12)
+    cases = [(B, T, S) for B in (1, 3) for T in (1, 2, 3, 4, 5, 7, 8, 11, 12) for S in (2, 3)]
+    cases += [(2, 37, 5), (1, 100, 16), (2, 64, 8)]
+    for B, T, S in cases:
+        key = "B{}_T{}_S{}".format(B, T, S)
+        trans = torch.randn(B, T, S, S)
+        if (B, T, S) == (3, 7, 3):
+            trans[1, 2, :, 1] = -float("inf")
+            trans[2, 4, 0, :] = -float("inf")
+        f = tfun(trans, ["b", "time", "prev", "curr"])
+        time = Variable("time", Bint[T])
+        out[key + "/trans"] = _np(trans)
+        for sname, (sop, pop) in SEMI.items():
+            r = sequential_sum_product(sop, pop, f, time, {"prev": "curr"})
+            out[key + "/" + sname + "_seq"] = to_bij(r, ["b", "prev", "curr"])
+            if T <= 12:
+                r = naive_sequential_sum_product(sop, pop, f, time, {"prev": "curr"})
+                out[key + "/" + sname + "_naive"] = to_bij(r, ["b", "prev", "curr"])
+                for seg in (2, 3):
+                    r = mixed_sequential_sum_product(sop, pop, f, time, {"prev": "curr"}, num_segments=seg)
+                    out[key + "/" + sname + "_mixed{}".format(seg)] = to_bij(r, ["b", "prev", "curr"])
+                r = MarkovProduct(sop, pop, f, time, {"prev": "curr"})
+                out[key + "/" + sname + "_markov"] = to_bij(r, ["b", "prev", "curr"])
+    np.savez_compressed(os.path.join(GOLDEN, "chain_product.npz"), **out)
+
+    # ------------------------------------------------------------------ HMM log_prob (hmm.py:129-135) incl. C1
+    out = {}
+    torch.manual_seed(0)  # C1 exactly as SURVEY 8(d): seed 0, randn(1,100,16,16), randn(1,16), fp32
+    torch.set_default_dtype(torch.float32)
+    trans = torch.randn(1, 100, 16, 16)
+    init = torch.randn(1, 16)
+    f = tfun(trans, ["b", "time", "state", "state(time=1)"])
+    r = sequential_sum_product(ops.logaddexp, ops.add, f, Variable("time", Bint[100]), {"state": "state(time=1)"})
+    r = tfun(init, ["b", "state"]) + r.reduce(ops.logaddexp, "state(time=1)")
+    r = r.reduce(ops.logaddexp, "state")
+    out["c1/trans"], out["c1/init"], out["c1/logZ_fp32"] = _np(trans), _np(init), _np(r.data)
+    torch.set_default_dtype(torch.float64)
+    f = tfun(trans.double(), ["b", "time", "state", "state(time=1)"])
+    r = sequential_sum_product(ops.logaddexp, ops.add, f, Variable("time", Bint[100]), {"state": "state(time=1)"})
+    r = (tfun(init.double(), ["b", "state"]) + r.reduce(ops.logaddexp, "state(time=1)")).reduce(ops.logaddexp, "state")
+    out["c1/logZ_fp64"] = _np(r.data)
+
+    torch.manual_seed(13)
+    for name, (B, T, S, amode) in {
+        "h0": (2, 9, 4, "shared"),
+        "h1": (3, 16, 7, "batched"),
+        "h2": (2, 6, 3, "timevarying"),
+        "h3": (1, 50, 32, "shared"),
+    }.items():
+        init = torch.randn(B, S).log_softmax(-1)
+        if amode == "shared":
+            A = torch.randn(S, S).log_softmax(-1)
+            fA = tfun(A, ["state", "state(time=1)"])
+        elif amode == "batched":
+            A = torch.randn(B, S, S).log_softmax(-1)
+            fA = tfun(A, ["b", "state", "state(time=1)"])
+        else:
+            A = torch.randn(B, T, S, S).log_softmax(-1)
+            fA = tfun(A, ["b", "time", "state", "state(time=1)"])
+        obs = torch.randn(B, T, S)
+        if name == "h1":
+            A[..., 0, 1] = -float("inf")  # forbidden transition (test_hmm.py:387-396 style)
+            obs[0, 3, 2] = -float("inf")
+        fobs = tfun(obs, ["b", "time", "state(time=1)"])
+        finit = tfun(init, ["b", "state"])
+        out[name + "/init"], out[name + "/A"], out[name + "/obs"] = _np(init), _np(A), _np(obs)
+        for sname, (sop, pop) in SEMI.items():
+            with AdjointTape() as tape:
+                result = fA + fobs
+                result = sequential_sum_product(sop, pop, result, Variable("time", Bint[T]), {"state": "state(time=1)"})
+                result = finit + result.reduce(sop, "state(time=1)")
+                result = result.reduce(sop, "state")
+            out[name + "/" + sname + "_Z"] = to_bij(result, ["b"])
+    np.savez_compressed(os.path.join(GOLDEN, "hmm_logprob.npz"), **out)
+
+    # ------------------------------------------------------------------ adjoint (a11), test_adjoint.py:187-261 body
+    out = {}
+    torch.manual_seed(14)
+    for B, T, S in [(1, 3, 2), (2, 7, 3), (2, 12, 3), (1, 9, 5)]:
+        key = "B{}_T{}_S{}".format(B, T, S)
+        trans = torch.randn(B, T, S, S)
+        f = tfun(trans, ["b", "time", "prev", "curr"])
+        out[key + "/trans"] = _np(trans)
+        for sname, (sop, pop) in SEMI.items():
+            with AdjointTape() as tape:
+                z = sequential_sum_product(sop, pop, f, Variable("time", Bint[T]), {"prev": "curr"})
+                z = z.reduce(sop, frozenset({"prev", "curr"}))
+            adj = tape.adjoint(sop, pop, z, (f,), batch_vars=frozenset({Variable("b", Bint[B])}))[f]
+            out[key + "/" + sname + "_Z"] = to_bij(z, ["b"])
+            out[key + "/" + sname + "_adj"] = to_bij(adj, ["b", "time", "prev", "curr"])
+    np.savez_compressed(os.path.join(GOLDEN, "adjoint.npz"), **out)
+
+    # ------------------------------------------------------------------ Gaussian scans (a10), test_sum_product.py:2427-2493
+    out = {}
+    torch.manual_seed(15)
+
+    def info_of(result, names, D):
+        """(Lam, eta, c) of a `Tensor + Gaussian` funsor over real inputs `names`."""
+        terms = result.terms if isinstance(result, Contraction) else (result,)
+        g = [t for t in terms if isinstance(t, Gaussian)]
+        assert len(g) == 1
+        g = g[0]
+        reals = [k for k, d in g.inputs.items() if d.dtype == "real"]
+        assert sorted(reals) == sorted(names), list(g.inputs)
+        perm = np.concatenate([np.arange(D) + D * reals.index(n) for n in names])  # reorder real blocks
+        zero = {n: funsor.to_funsor(torch.zeros(D), Reals[D]) for n in names}
+        c = result(**zero)
+        assert isinstance(c, Tensor)
+        bnames = [k for k, d in g.inputs.items() if d.dtype != "real"]
+        Lam = _np(g._precision)[..., perm, :][..., :, perm]
+        eta = _np(g._info_vec)[..., perm]
+        return Lam, eta, _np(c.align(tuple(bnames)).data), bnames
+
+    for B, T, D in [(1, 1, 1), (2, 2, 1), (2, 3, 2), (1, 5, 3), (3, 8, 2), (2, 11, 3), (1, 12, 4)]:
+        key = "B{}_T{}_D{}".format(B, T, D)
+        inputs = OrderedDict([("b", Bint[B]), ("time", Bint[T]), ("prev", Reals[D]), ("curr", Reals[D])])
+        g = random_gaussian(inputs)
+        out[key + "/w"], out[key + "/P"] = _np(g.white_vec), _np(g.prec_sqrt)
+        r = sequential_sum_product(ops.logaddexp, ops.add, g, Variable("time", Bint[T]), {"prev": "curr"})
+        Lam, eta, c, bn = info_of(r, ["prev", "curr"], D)
+        assert bn == ["b"], bn
+        out[key + "/Lam"], out[key + "/eta"], out[key + "/c"] = Lam, eta, c
+        if T <= 8:
+            r2 = naive_sequential_sum_product(ops.logaddexp, ops.add, g, Variable("time", Bint[T]), {"prev": "curr"})
+            Lam2, eta2, c2, _ = info_of(r2, ["prev", "curr"], D)
+            out[key + "/Lam_naive"], out[key + "/eta_naive"], out[key + "/c_naive"] = Lam2, eta2, c2
+    # one explicit pair contraction with rank-deficient (Kalman-like) operands
+    np.savez_compressed(os.path.join(GOLDEN, "gaussian_chain.npz"), **out)
+
+    # ------------------------------------------------------------------ Kalman / GaussianHMM element + log_prob
+    out = {}
+    torch.manual_seed(16)
+    spec = importlib.util.spec_from_file_location("_ref_convert", os.path.join(ref_boot.REFERENCE_ROOT, "funsor/pyro/convert.py"))
+    conv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(conv)
+    MVN = torch.distributions.MultivariateNormal
+
+    def spd_tril(*shape):
+        a = torch.randn(*shape, shape[-1])
+        return torch.linalg.cholesky(a @ a.transpose(-1, -2) / shape[-1] + 0.5 * torch.eye(shape[-1]))
+
+    for name, (B, T, D, O) in {"k0": (2, 6, 2, 1), "k1": (2, 9, 4, 2), "k2": (1, 16, 6, 3)}.items():
+        F = 0.9 * torch.linalg.qr(torch.randn(B, D, D))[0]
+        H = torch.randn(B, D, O)
+        q_loc, r_loc = 0.1 * torch.randn(B, D), 0.1 * torch.randn(B, O)
+        q_tril, r_tril = spd_tril(B, D), spd_tril(B, O)
+        m0, p0_tril = torch.randn(B, D), spd_tril(B, D)
+        y = torch.randn(B, T, O)
+        for k, v in dict(F=F, H=H, q_loc=q_loc, r_loc=r_loc, q_tril=q_tril, r_tril=r_tril, m0=m0, p0_tril=p0_tril, y=y).items():
+            out[name + "/" + k] = _np(v)
+        # hmm.py:258-270 with time-homogeneous parameters expanded over a `time` batch dim
+        ex = lambda t: t.unsqueeze(1).expand((B, T) + t.shape[1:])  # noqa: E731
+        trans = conv.matrix_and_mvn_to_funsor(ex(F), MVN(ex(q_loc), scale_tril=ex(q_tril)), ("time",), "state", "state(time=1)")
+        obs = conv.matrix_and_mvn_to_funsor(ex(H), MVN(ex(r_loc), scale_tril=ex(r_tril)), ("time",), "state(time=1)", "value")
+        value = Tensor(y, OrderedDict([("_pyro_dim_-1", Bint[B]), ("time", Bint[T])]))
+        elem = trans + obs(value=value)
+        chain = sequential_sum_product(ops.logaddexp, ops.add, elem, Variable("time", Bint[T]), {"state": "state(time=1)"})
+        Lam, eta, c, bn = info_of(chain, ["state", "state(time=1)"], D)
+        out[name + "/chain_Lam"], out[name + "/chain_eta"], out[name + "/chain_c"] = Lam, eta, c
+        # initial N(m0, L L') as a funsor; dist_to_funsor needs pyro, so build the same density directly
+        P0 = torch.linalg.inv(p0_tril).transpose(-1, -2)
+        w0 = (m0.unsqueeze(-2) @ P0).squeeze(-2)
+        s0 = -0.5 * D * np.log(2 * np.pi) - p0_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1)
+        binp = OrderedDict([("_pyro_dim_-1", Bint[B])])
+        ginp = binp.copy()
+        ginp["state"] = Reals[D]
+        init = Gaussian(white_vec=w0, prec_sqrt=P0, inputs=ginp) + Tensor(s0, binp)
+        lp = (init + chain.reduce(ops.logaddexp, "state(time=1)")).reduce(ops.logaddexp, "state")
+        out[name + "/logprob"] = _np(lp.data)
+    np.savez_compressed(os.path.join(GOLDEN, "kalman.npz"), **out)
+    for fn in sorted(os.listdir(GOLDEN)):
+        print(fn, os.path.getsize(os.path.join(GOLDEN, fn)))
+
+
+if __name__ == "__main__":
+    main()
