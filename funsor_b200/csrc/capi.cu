@@ -1,0 +1,170 @@
+// C-ABI plumbing: status strings, thread-local error text, device check, launch counter,
+// host-buffer entry points (the e2e path of bench.py).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace fb2 {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches += n; }
+
+int check_device() {
+    static thread_local int cached = -1;
+    if (cached == FB2_OK) return cached;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device visible (%s): funsor_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return FB2_ERR_NO_DEVICE;
+    }
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+        set_error("cannot query the current CUDA device");
+        return FB2_ERR_CUDA;
+    }
+    if (major != 10) {
+        set_error("device compute capability %d.x is not sm_100: this library ships sm_100a code only", major);
+        return FB2_ERR_NO_DEVICE;
+    }
+    cached = FB2_OK;
+    return cached;
+}
+
+// ---- per-thread device arena for the *_host entry points
+struct HostArena {
+    void* dev = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+static thread_local HostArena g_arena;
+
+static int arena_reserve(size_t bytes) {
+    if (!g_arena.stream) FB2_CUDA(cudaStreamCreateWithFlags(&g_arena.stream, cudaStreamNonBlocking));
+    if (bytes <= g_arena.bytes) return FB2_OK;
+    if (g_arena.dev) FB2_CUDA(cudaFree(g_arena.dev));
+    g_arena.dev = nullptr;
+    g_arena.bytes = 0;
+    FB2_CUDA(cudaMalloc(&g_arena.dev, bytes));
+    g_arena.bytes = bytes;
+    return FB2_OK;
+}
+
+}  // namespace fb2
+
+using namespace fb2;
+
+extern "C" int fb2_version(void) { return FB2_VERSION; }
+
+extern "C" const char* fb2_status_string(int status) {
+    switch (status) {
+        case FB2_OK: return "ok";
+        case FB2_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case FB2_ERR_UNSUPPORTED: return "unsupported configuration";
+        case FB2_ERR_CUDA: return "CUDA runtime error";
+        case FB2_ERR_WORKSPACE: return "workspace too small or misaligned";
+        case FB2_ERR_NO_DEVICE: return "no sm_100 CUDA device (no CPU fallback)";
+        case FB2_ERR_NUMERIC: return "numerical failure (non-positive pivot)";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char* fb2_last_error(void) { return g_err; }
+
+extern "C" int fb2_device_query(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin_bytes) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device >= count) {
+        cudaGetLastError();
+        set_error("device %d not available", device);
+        return FB2_ERR_NO_DEVICE;
+    }
+    int v = 0;
+    if (sm_count) { FB2_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); *sm_count = v; }
+    if (cc_major) { FB2_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, device)); *cc_major = v; }
+    if (cc_minor) { FB2_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, device)); *cc_minor = v; }
+    if (smem_optin_bytes) {
+        FB2_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        *smem_optin_bytes = (size_t)v;
+    }
+    return FB2_OK;
+}
+
+extern "C" int64_t fb2_launch_count(void) { return g_launches; }
+extern "C" void fb2_launch_count_reset(void) { g_launches = 0; }
+
+extern "C" int fb2_host_arena_release(void) {
+    if (g_arena.dev) FB2_CUDA(cudaFree(g_arena.dev));
+    g_arena.dev = nullptr;
+    g_arena.bytes = 0;
+    if (g_arena.stream) FB2_CUDA(cudaStreamDestroy(g_arena.stream));
+    g_arena.stream = nullptr;
+    return FB2_OK;
+}
+
+extern "C" int fb2_hmm_forward_f32_host(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb,
+                                        int64_t a_st, const float* obs, int64_t B, int64_t T, int32_t S, float* logZ) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(B >= 1 && T >= 1 && S >= 1 && init && A && obs && logZ, "bad arguments");
+    size_t n_init = (size_t)(init_sb ? B : 1) * S;
+    size_t n_A = (size_t)(a_sb ? B : 1) * (a_st ? T : 1) * S * S;
+    FB2_REQUIRE(init_sb == 0 || init_sb == S, "host entry point needs packed init");
+    FB2_REQUIRE((a_sb == 0 || a_sb == (a_st ? T : 1) * (int64_t)S * S) && (a_st == 0 || a_st == (int64_t)S * S),
+                "host entry point needs packed A");
+    size_t n_obs = (size_t)B * T * S;
+    size_t ws = fb2_hmm_workspace_bytes(0, B, T, S);
+    size_t total = align_up(n_init * 4) + align_up(n_A * 4) + align_up(n_obs * 4) + align_up((size_t)B * 4) + ws;
+    st = arena_reserve(total);
+    if (st != FB2_OK) return st;
+    Arena ar(g_arena.dev, g_arena.bytes);
+    float* d_init = ar.take<float>(n_init);
+    float* d_A = ar.take<float>(n_A);
+    float* d_obs = ar.take<float>(n_obs);
+    float* d_out = ar.take<float>((size_t)B);
+    void* d_ws = ar.take<char>(ws);
+    cudaStream_t s = g_arena.stream;
+    FB2_CUDA(cudaMemcpyAsync(d_init, init, n_init * 4, cudaMemcpyHostToDevice, s));
+    FB2_CUDA(cudaMemcpyAsync(d_A, A, n_A * 4, cudaMemcpyHostToDevice, s));
+    FB2_CUDA(cudaMemcpyAsync(d_obs, obs, n_obs * 4, cudaMemcpyHostToDevice, s));
+    st = fb2_hmm_forward_f32(semiring, d_init, init_sb, d_A, a_sb, a_st, d_obs, B, T, S, d_out, nullptr, d_ws, ws, s);
+    if (st != FB2_OK) return st;
+    FB2_CUDA(cudaMemcpyAsync(logZ, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    FB2_CUDA(cudaStreamSynchronize(s));
+    return FB2_OK;
+}
+
+extern "C" int fb2_chain_product_f32_host(int semiring, const float* trans, int64_t B, int64_t T, int32_t S, float* out) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(B >= 1 && T >= 1 && S >= 1 && trans && out, "bad arguments");
+    size_t n_in = (size_t)B * T * S * S, n_out = (size_t)B * S * S;
+    size_t ws = fb2_chain_product_workspace_bytes(B, T, S);
+    st = arena_reserve(align_up(n_in * 4) + align_up(n_out * 4) + ws);
+    if (st != FB2_OK) return st;
+    Arena ar(g_arena.dev, g_arena.bytes);
+    float* d_in = ar.take<float>(n_in);
+    float* d_out = ar.take<float>(n_out);
+    void* d_ws = ar.take<char>(ws);
+    cudaStream_t s = g_arena.stream;
+    FB2_CUDA(cudaMemcpyAsync(d_in, trans, n_in * 4, cudaMemcpyHostToDevice, s));
+    int64_t strides[4] = {T * (int64_t)S * S, (int64_t)S * S, S, 1};
+    st = fb2_chain_product_f32(semiring, d_in, strides, B, T, S, d_out, d_ws, ws, s);
+    if (st != FB2_OK) return st;
+    FB2_CUDA(cudaMemcpyAsync(out, d_out, n_out * 4, cudaMemcpyDeviceToHost, s));
+    FB2_CUDA(cudaStreamSynchronize(s));
+    return FB2_OK;
+}

@@ -1,0 +1,685 @@
+// Factored HMM passes: forward (log / max-plus), Viterbi back-pointers + backtrace, backward.
+//
+// Reference semantics: funsor/pyro/hmm.py:129-135 evaluated as the vector recurrence
+//   alpha_t[j] = (+)_i ( alpha_{t-1}[i] (x) A[i,j] ) (x) obs[t,j],   alpha_{-1} = init
+// instead of materialising trans + obs and calling sequential_sum_product (sum_product.py:652-701).
+//
+// Layout / execution model ("generic" path, any S, both semirings):
+//   * chains are processed in groups of R (R in {1,4,16}); a group is served by Gg co-resident CTAs
+//     (cooperative launch), CTA c owning the W = ceil(S/Gg) output states [c*W, c*W+W).
+//   * the message vector lives in a double-buffered global (L2-resident) array vec[2][B][S]; after
+//     every step the group's CTAs meet at a counter barrier and re-read the full vector with ld.cg.
+//   * the CTA's slice of A is re-read every step: it is served by L1/L2 (S*W*4 bytes per CTA).
+//   * obs[b,t,slice] is prefetched one step ahead into shared memory, so HBM latency is off the
+//     step-to-step critical path.
+#include "common.cuh"
+
+namespace fb2 {
+
+struct HmmArgs {
+    const float* init;  // nullable -> semiring one
+    int64_t init_sb;
+    const float* A;
+    int64_t a_sb, a_st;
+    const float* obs;  // nullable -> 0
+    int64_t B, T;
+    int S;
+    float* vec;          // [2][B][S]
+    unsigned* counters;  // [groups_conc]
+    float* alpha_all;    // nullable [B,T,S]
+    int32_t* backptr;    // nullable [B,T,S]
+    float* out;          // [B]   (+)_j alpha_{T-1}[j]
+    int32_t* last;       // nullable [B] argmax_j alpha_{T-1}[j]
+    const float* final_; // nullable [B,S] folded into out (adjoint use): out = (+)_j alpha[j] (x) final[j]
+    int Gg, W, LW;
+    int groups_total, groups_conc;
+    int cpo;             // chains per obs/A batch entry (1 normally; S for chunk summaries: chain = b*S + row)
+    int init_identity;   // 1: alpha_{-1} of chain c is the semiring identity row (c % cpo)
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All CTAs of one group meet here. `target` is the cumulative arrival count to wait for.
+__device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned target, int Gg) {
+    __syncthreads();
+    if (Gg > 1 && threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while ((int)(ld_acquire_u32(ctr) - target) < 0) {
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward recurrence, generic path
+// smem: s_alpha[R][S] | s_red_a[256*R] | s_red_b[256*R] | s_obs[2][R][W]
+template <int SEMI, int R, bool ARG>
+__global__ void __launch_bounds__(256) hmm_forward_generic(HmmArgs p) {
+    extern __shared__ __align__(16) float smem[];
+    const int S = p.S, W = p.W, LW = p.LW, NSUB = 256 / LW;
+    float* s_alpha = smem;
+    float* s_red_a = s_alpha + (size_t)R * S;
+    float* s_red_b = s_red_a + 256 * R;
+    float* s_obs = s_red_b + 256 * R;
+    const int tid = threadIdx.x;
+    const int gconc = blockIdx.x / p.Gg, slice = blockIdx.x % p.Gg;
+    const int j0 = slice * W;
+    const int jw = max(0, min(W, S - j0));
+    const int lw = tid % LW, isub = tid / LW;
+    unsigned* ctr = p.counters + gconc;
+    unsigned epoch = 0;
+
+    for (int g = gconc; g < p.groups_total; g += p.groups_conc) {
+        const int64_t b0 = (int64_t)g * R;
+        const int nb = (int)min((int64_t)R, p.B - b0);
+        // ---- alpha_{-1} = init  -> vec[0]
+        for (int idx = tid; idx < nb * jw; idx += 256) {
+            int r = idx / jw, j = j0 + idx % jw;
+            float v = p.init ? p.init[(b0 + r) * p.init_sb + j] : 0.f;
+            if (p.init_identity) v = (j == (int)((b0 + r) % p.cpo)) ? 0.f : kNegInf;
+            p.vec[((b0 + r) * S) + j] = v;
+        }
+        // prefetch obs for t = 0
+        if (p.obs)
+            for (int idx = tid; idx < nb * jw; idx += 256) {
+                int r = idx / jw, jj = idx % jw;
+                s_obs[(0 * R + r) * W + jj] = p.obs[((b0 + r) / p.cpo * p.T + 0) * S + j0 + jj];
+            }
+        group_barrier(ctr, (++epoch) * p.Gg, p.Gg);
+
+        for (int64_t t = 0; t < p.T; ++t) {
+            const float* vin = p.vec + (size_t)(t & 1) * p.B * S;
+            float* vout = p.vec + (size_t)((t + 1) & 1) * p.B * S;
+            // ---- stage the full previous vector of every chain of the group
+            for (int idx = tid; idx < R * S; idx += 256) {
+                int r = idx / S, i = idx % S;
+                s_alpha[idx] = (r < nb) ? __ldcg(vin + (b0 + r) * S + i) : kNegInf;
+            }
+            // ---- prefetch obs for t+1 (latency hidden behind this step's compute + barrier)
+            if (p.obs && t + 1 < p.T)
+                for (int idx = tid; idx < nb * jw; idx += 256) {
+                    int r = idx / jw, jj = idx % jw;
+                    s_obs[(((t + 1) & 1) * R + r) * W + jj] = p.obs[((b0 + r) / p.cpo * p.T + t + 1) * S + j0 + jj];
+                }
+            __syncthreads();
+            const float* s_ob = s_obs + (size_t)((t & 1) * R) * W;
+
+            for (int c0 = 0; c0 < jw; c0 += LW) {
+                const int jj = c0 + lw;
+                const bool colok = jj < jw;
+                float acc_a[R], acc_b[R];  // LOG: (max, sum)   MAX: (best, arg as float bits)
+                if (colok) {
+                    float ob[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) ob[r] = (p.obs && r < nb) ? s_ob[r * W + jj] : 0.f;
+                    const bool per_chain = p.a_sb != 0;
+                    const float* Abase = p.A + t * p.a_st + j0 + jj;
+                    int64_t aoff[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) aoff[r] = per_chain ? ((b0 + (r < nb ? r : nb - 1)) / p.cpo) * p.a_sb : 0;
+                    if (SEMI == FB2_SEMIRING_LOG) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            acc_a[r] = -FLT_MAX;
+                            acc_b[r] = 0.f;
+                        }
+                        for (int i = isub; i < S; i += NSUB) {
+                            const float a0 = per_chain ? 0.f : __ldg(Abase + (int64_t)i * S);
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                const float a = per_chain ? __ldg(Abase + aoff[r] + (int64_t)i * S) : a0;
+                                acc_a[r] = fmaxf(acc_a[r], s_alpha[r * S + i] + a);
+                            }
+                        }
+                        for (int i = isub; i < S; i += NSUB) {
+                            const float a0 = per_chain ? 0.f : __ldg(Abase + (int64_t)i * S);
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                const float a = per_chain ? __ldg(Abase + aoff[r] + (int64_t)i * S) : a0;
+                                acc_b[r] += __expf(s_alpha[r * S + i] + a - acc_a[r]);
+                            }
+                        }
+                    } else {
+                        int arg[R];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            acc_a[r] = kNegInf;
+                            arg[r] = isub < S ? isub : 0;
+                        }
+                        for (int i = isub; i < S; i += NSUB) {
+                            const float a0 = per_chain ? 0.f : __ldg(Abase + (int64_t)i * S);
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                const float a = per_chain ? __ldg(Abase + aoff[r] + (int64_t)i * S) : a0;
+                                const float v = s_alpha[r * S + i] + (a + ob[r]);  // (A + obs) first: hmm.py:130
+                                if (v > acc_a[r]) {
+                                    acc_a[r] = v;
+                                    arg[r] = i;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acc_b[r] = __int_as_float(arg[r]);
+                    }
+                }
+                // ---- combine the NSUB partials of every (chain, column) in a fixed order
+                if (colok) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        s_red_a[(isub * R + r) * LW + lw] = acc_a[r];
+                        s_red_b[(isub * R + r) * LW + lw] = acc_b[r];
+                    }
+                }
+                __syncthreads();
+                if (tid < R * LW) {
+                    const int r = tid / LW, l = tid % LW;
+                    const int col = c0 + l;
+                    if (r < nb && col < jw) {
+                        const int64_t b = b0 + r;
+                        float res;
+                        if (SEMI == FB2_SEMIRING_LOG) {
+                            float m = -FLT_MAX;
+                            for (int q = 0; q < NSUB; ++q) m = fmaxf(m, s_red_a[(q * R + r) * LW + l]);
+                            float s = 0.f;
+                            for (int q = 0; q < NSUB; ++q)
+                                s += s_red_b[(q * R + r) * LW + l] * __expf(s_red_a[(q * R + r) * LW + l] - m);
+                            res = m + logf(s) + (p.obs ? s_ob[r * W + col] : 0.f);
+                        } else {
+                            float best = kNegInf;
+                            int arg = 0x7fffffff;
+                            for (int q = 0; q < NSUB; ++q) {
+                                float v = s_red_a[(q * R + r) * LW + l];
+                                int ai = __float_as_int(s_red_b[(q * R + r) * LW + l]);
+                                if (v > best || (v == best && ai < arg)) {
+                                    best = v;
+                                    arg = ai;
+                                }
+                            }
+                            res = best;
+                            if (ARG) p.backptr[(b * p.T + t) * S + j0 + col] = arg;
+                        }
+                        vout[b * S + j0 + col] = res;
+                        if (p.alpha_all) p.alpha_all[(b * p.T + t) * S + j0 + col] = res;
+                    }
+                }
+                __syncthreads();
+            }
+            group_barrier(ctr, (++epoch) * p.Gg, p.Gg);
+        }
+        // ---- out[b] = (+)_j alpha_{T-1}[j] (x) final[j]  (slice 0 of the group does it)
+        if (slice == 0) {
+            const float* vfin = p.vec + (size_t)(p.T & 1) * p.B * S;
+            const int warp = tid / 32, lane = tid % 32;
+            for (int r = warp; r < nb; r += 8) {
+                const int64_t b = b0 + r;
+                float m = (SEMI == FB2_SEMIRING_LOG) ? -FLT_MAX : kNegInf;
+                int arg = 0x7fffffff;
+                for (int j = lane; j < S; j += 32) {
+                    float v = __ldcg(vfin + b * S + j) + (p.final_ ? p.final_[b * S + j] : 0.f);
+                    if (SEMI == FB2_SEMIRING_LOG) {
+                        m = fmaxf(m, v);
+                    } else if (v > m || (v == m && j < arg)) {
+                        m = v;
+                        arg = j;
+                    }
+                }
+                if (SEMI == FB2_SEMIRING_LOG) {
+                    m = warp_max(m);
+                    float s = 0.f;
+                    for (int j = lane; j < S; j += 32)
+                        s += __expf(__ldcg(vfin + b * S + j) + (p.final_ ? p.final_[b * S + j] : 0.f) - m);
+                    s = warp_sum(s);
+                    if (lane == 0) p.out[b] = m + logf(s);
+                } else {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        float om = __shfl_xor_sync(0xffffffffu, m, o);
+                        int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                        if (om > m || (om == m && oa < arg)) {
+                            m = om;
+                            arg = oa;
+                        }
+                    }
+                    if (lane == 0) {
+                        p.out[b] = m;
+                        if (p.last) p.last[b] = arg;
+                    }
+                }
+            }
+        }
+        // the next wave re-uses vec[] of other chains only, but s_obs/s_alpha are re-used: sync
+        group_barrier(ctr, (++epoch) * p.Gg, p.Gg);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward recurrence, generic path (log / max):
+//   beta_{T-1} = final (or one);  beta_{t-1}[i] = (+)_j A_t[i,j] (x) obs[t,j] (x) beta_t[j]
+// CTA c owns rows i in [c*W, c*W+W); one warp per row, lanes stride over j (coalesced rows of A).
+// beta_all[b,t,:] = beta_t.  smem: s_w[R][S] (= obs_t + beta_t)
+template <int SEMI, int R>
+__global__ void __launch_bounds__(256) hmm_backward_generic(HmmArgs p) {
+    extern __shared__ __align__(16) float smem[];
+    const int S = p.S, W = p.W;
+    float* s_w = smem;
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const int gconc = blockIdx.x / p.Gg, slice = blockIdx.x % p.Gg;
+    const int i0 = slice * W;
+    const int iw = max(0, min(W, S - i0));
+    unsigned* ctr = p.counters + gconc;
+    unsigned epoch = 0;
+
+    for (int g = gconc; g < p.groups_total; g += p.groups_conc) {
+        const int64_t b0 = (int64_t)g * R;
+        const int nb = (int)min((int64_t)R, p.B - b0);
+        // beta_{T-1} -> vec[(T-1)&1]... buffer index convention: vec[t&1] holds beta_t
+        for (int idx = tid; idx < nb * iw; idx += 256) {
+            int r = idx / iw, i = i0 + idx % iw;
+            float v = p.final_ ? p.final_[(b0 + r) * S + i] : 0.f;
+            p.vec[(size_t)((p.T - 1) & 1) * p.B * S + (b0 + r) * S + i] = v;
+            if (p.alpha_all) p.alpha_all[((b0 + r) * p.T + p.T - 1) * S + i] = v;
+        }
+        group_barrier(ctr, (++epoch) * p.Gg, p.Gg);
+        for (int64_t t = p.T - 1; t >= 1; --t) {
+            const float* vin = p.vec + (size_t)(t & 1) * p.B * S;
+            float* vout = p.vec + (size_t)((t - 1) & 1) * p.B * S;
+            for (int idx = tid; idx < R * S; idx += 256) {
+                int r = idx / S, j = idx % S;
+                float v = kNegInf;
+                if (r < nb) v = __ldcg(vin + (b0 + r) * S + j) + (p.obs ? p.obs[((b0 + r) * p.T + t) * S + j] : 0.f);
+                s_w[idx] = v;
+            }
+            __syncthreads();
+            for (int ii = warp; ii < iw; ii += 8) {
+                const int i = i0 + ii;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (r >= nb) break;
+                    const float* Ar = p.A + (b0 + r) * p.a_sb + t * p.a_st + (int64_t)i * S;
+                    float m = (SEMI == FB2_SEMIRING_LOG) ? -FLT_MAX : kNegInf;
+                    for (int j = lane; j < S; j += 32) m = fmaxf(m, __ldg(Ar + j) + s_w[r * S + j]);
+                    m = warp_max(m);
+                    float res = m;
+                    if (SEMI == FB2_SEMIRING_LOG) {
+                        float s = 0.f;
+                        for (int j = lane; j < S; j += 32) s += __expf(__ldg(Ar + j) + s_w[r * S + j] - m);
+                        s = warp_sum(s);
+                        res = m + logf(s);
+                    }
+                    if (lane == 0) {
+                        vout[(b0 + r) * S + i] = res;
+                        if (p.alpha_all) p.alpha_all[((b0 + r) * p.T + t - 1) * S + i] = res;
+                    }
+                }
+            }
+            group_barrier(ctr, (++epoch) * p.Gg, p.Gg);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Viterbi backtrace: path[b,T] = last[b]; path[b,t] = backptr[b,t,path[b,t+1]]
+__global__ void viterbi_backtrace(const int32_t* backptr, const int32_t* last, int64_t B, int64_t T, int S,
+                                  int64_t* path) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int s = last[b];
+    path[b * (T + 1) + T] = s;
+    for (int64_t t = T - 1; t >= 0; --t) {
+        s = backptr[(b * T + t) * S + s];
+        path[b * (T + 1) + t] = s;
+    }
+}
+
+// gamma[b,t,j] = alpha[b,t,j] + beta[b,t,j] - logZ[b]   (in place over alpha)
+__global__ void marginals_combine(float* alpha, const float* beta, const float* logZ, int64_t B, int64_t T, int S) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t per = T * (int64_t)S;
+    if (idx >= B * per) return;
+    alpha[idx] = alpha[idx] + beta[idx] - logZ[idx / per];
+}
+
+// xi_sum[b,i,j] = sum_t exp(alpha_{t-1}[i] + A_t[i,j] + obs[t,j] + beta_t[j] - logZ)
+// one thread per (b,i,j); alpha_{-1} = init.  Simple O(T S^2) accumulation (T-serial per thread).
+__global__ void xi_sum_kernel(const float* init, int64_t init_sb, const float* A, int64_t a_sb, int64_t a_st,
+                              const float* obs, const float* alpha, const float* beta, const float* logZ, int64_t B,
+                              int64_t T, int S, float* xi) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t per = (int64_t)S * S;
+    if (idx >= B * per) return;
+    int64_t b = idx / per;
+    int i = (int)((idx % per) / S), j = (int)(idx % S);
+    float z = logZ[b];
+    float acc = 0.f;
+    for (int64_t t = 0; t < T; ++t) {
+        float ap = t == 0 ? (init ? init[b * init_sb + i] : 0.f) : alpha[(b * T + t - 1) * S + i];
+        float v = ap + A[b * a_sb + t * a_st + (int64_t)i * S + j] + obs[(b * T + t) * S + j] + beta[(b * T + t) * S + j] - z;
+        acc += __expf(v);
+    }
+    xi[idx] = acc;
+}
+
+// adj[b,t,i,j] = alphaprev[b,t,i] + beta[b,t,j]  where alphaprev[b,0] = init (or 0) and alphaprev[b,t] = alpha[b,t-1]
+__global__ void adjoint_outer(const float* init, const float* alpha, const float* beta, int64_t B, int64_t T, int S,
+                              float* adj) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t per = (int64_t)S * S;
+    if (idx >= B * T * per) return;
+    int64_t bt = idx / per;
+    int64_t b = bt / T, t = bt % T;
+    int i = (int)((idx % per) / S), j = (int)(idx % S);
+    float ap = t == 0 ? (init ? init[b * S + i] : 0.f) : alpha[(b * T + t - 1) * S + i];
+    adj[idx] = ap + beta[(b * T + t) * S + j];
+}
+
+// ---------------------------------------------------------------------------------------------
+struct PassPlan {
+    int R, Gg, W, LW, groups_total, groups_conc, grid;
+    size_t smem;
+};
+
+static int g_sm_count = 0;
+static size_t g_smem_optin = 0;
+
+static int device_facts() {
+    if (g_sm_count) return FB2_OK;
+    int dev = 0;
+    FB2_CUDA(cudaGetDevice(&dev));
+    int sm = 0, optin = 0;
+    FB2_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    FB2_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    g_sm_count = sm;
+    g_smem_optin = (size_t)optin;
+    return FB2_OK;
+}
+
+static int make_plan(int64_t B, int S, bool backward, PassPlan* pl) {
+    int st = device_facts();
+    if (st != FB2_OK) return st;
+    int R = B >= 16 ? 16 : (B > 1 ? 4 : 1);
+    if (backward && R > 4) R = 4;
+    // shared memory needed independent of W: alpha staging
+    for (;;) {
+        size_t fixed = (size_t)R * S * 4 + (backward ? 0 : 2 * 256 * (size_t)R * 4);
+        if (fixed + 4096 <= g_smem_optin || R == 1) break;
+        R = R == 16 ? 4 : 1;
+    }
+    int groups_total = (int)ceil_div(B, R);
+    int groups_conc = groups_total < g_sm_count ? groups_total : g_sm_count;
+    int Gg = g_sm_count / groups_conc;
+    if (Gg > S) Gg = S;
+    if (Gg < 1) Gg = 1;
+    int W = (int)ceil_div(S, Gg);
+    if (W > 4) W = (W + 7) / 8 * 8;  // whole 32-byte sectors per row segment
+    Gg = (int)ceil_div(S, W);        // drop CTAs that would own nothing
+    int LW = 1;
+    while (LW < W && LW < 32) LW <<= 1;
+    pl->R = R;
+    pl->Gg = Gg;
+    pl->W = W;
+    pl->LW = LW;
+    pl->groups_total = groups_total;
+    pl->groups_conc = groups_conc;
+    pl->grid = groups_conc * Gg;
+    pl->smem = (size_t)R * S * 4 + (backward ? 0 : (2 * 256 * (size_t)R * 4 + 2 * (size_t)R * W * 4));
+    if (pl->smem > g_smem_optin) {
+        set_error("hmm pass: state dimension S=%d needs %zu bytes of shared memory (> %zu)", S, pl->smem, g_smem_optin);
+        return FB2_ERR_UNSUPPORTED;
+    }
+    return FB2_OK;
+}
+
+template <typename K>
+static int coop_launch(K kernel, const PassPlan& pl, HmmArgs& args, cudaStream_t stream) {
+    FB2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    int per_sm = 0;
+    FB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, pl.smem));
+    if (per_sm * g_sm_count < pl.grid) {
+        set_error("hmm pass: grid of %d CTAs cannot be co-resident (%d per SM)", pl.grid, per_sm);
+        return FB2_ERR_UNSUPPORTED;
+    }
+    void* kargs[] = {&args};
+    FB2_CUDA(cudaLaunchCooperativeKernel((void*)kernel, dim3(pl.grid), dim3(256), kargs, pl.smem, stream));
+    count_launch();
+    return FB2_OK;
+}
+
+static int run_forward(int semiring, bool want_arg, const PassPlan& pl, HmmArgs& a, cudaStream_t stream) {
+#define FB2_FWD(SEMI, RR, ARGF) return coop_launch(hmm_forward_generic<SEMI, RR, ARGF>, pl, a, stream)
+    if (semiring == FB2_SEMIRING_LOG) {
+        if (pl.R == 16) FB2_FWD(FB2_SEMIRING_LOG, 16, false);
+        if (pl.R == 4) FB2_FWD(FB2_SEMIRING_LOG, 4, false);
+        FB2_FWD(FB2_SEMIRING_LOG, 1, false);
+    } else if (want_arg) {
+        if (pl.R == 16) FB2_FWD(FB2_SEMIRING_MAX, 16, true);
+        if (pl.R == 4) FB2_FWD(FB2_SEMIRING_MAX, 4, true);
+        FB2_FWD(FB2_SEMIRING_MAX, 1, true);
+    } else {
+        if (pl.R == 16) FB2_FWD(FB2_SEMIRING_MAX, 16, false);
+        if (pl.R == 4) FB2_FWD(FB2_SEMIRING_MAX, 4, false);
+        FB2_FWD(FB2_SEMIRING_MAX, 1, false);
+    }
+#undef FB2_FWD
+}
+
+static int run_backward(int semiring, const PassPlan& pl, HmmArgs& a, cudaStream_t stream) {
+    if (semiring == FB2_SEMIRING_LOG) {
+        if (pl.R == 4) return coop_launch(hmm_backward_generic<FB2_SEMIRING_LOG, 4>, pl, a, stream);
+        return coop_launch(hmm_backward_generic<FB2_SEMIRING_LOG, 1>, pl, a, stream);
+    }
+    if (pl.R == 4) return coop_launch(hmm_backward_generic<FB2_SEMIRING_MAX, 4>, pl, a, stream);
+    return coop_launch(hmm_backward_generic<FB2_SEMIRING_MAX, 1>, pl, a, stream);
+}
+
+static int check_hmm_args(int semiring, const float* A, int64_t B, int64_t T, int S) {
+    FB2_REQUIRE(semiring == FB2_SEMIRING_LOG || semiring == FB2_SEMIRING_MAX, "unknown semiring %d", semiring);
+    FB2_REQUIRE(B >= 0 && T >= 1 && S >= 1, "bad extents B=%lld T=%lld S=%d", (long long)B, (long long)T, S);
+    FB2_REQUIRE(A != nullptr, "A is null");
+    return FB2_OK;
+}
+
+// workspace layout helpers ----------------------------------------------------------------------
+static size_t vec_bytes(int64_t B, int S) { return align_up((size_t)2 * B * S * 4); }
+static size_t ctr_bytes() { return align_up(1024 * sizeof(unsigned)); }
+
+int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb, int64_t a_st,
+                       const float* obs, const float* final_, int64_t B, int64_t T, int S, float* out,
+                       float* alpha_all, int32_t* backptr, int32_t* last, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream, int cpo = 1, float* alpha_last = nullptr) {
+    PassPlan pl;
+    int st = make_plan(B, S, false, &pl);
+    if (st != FB2_OK) return st;
+    Arena arena(workspace, workspace_bytes);
+    float* vec = arena.take<float>((size_t)2 * B * S);
+    unsigned* ctr = arena.take<unsigned>(1024);
+    if (!arena.ok()) {
+        set_error("hmm forward: workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    FB2_CUDA(cudaMemsetAsync(ctr, 0, 1024 * sizeof(unsigned), stream));
+    HmmArgs a{};
+    a.init = init; a.init_sb = init_sb; a.A = A; a.a_sb = a_sb; a.a_st = a_st; a.obs = obs;
+    a.B = B; a.T = T; a.S = S; a.vec = vec; a.counters = ctr; a.alpha_all = alpha_all; a.backptr = backptr;
+    a.out = out; a.last = last; a.final_ = final_;
+    a.Gg = pl.Gg; a.W = pl.W; a.LW = pl.LW; a.groups_total = pl.groups_total; a.groups_conc = pl.groups_conc;
+    a.cpo = cpo; a.init_identity = cpo > 1 ? 1 : 0;
+    st = run_forward(semiring, backptr != nullptr, pl, a, stream);
+    if (st != FB2_OK) return st;
+    if (alpha_last)
+        FB2_CUDA(cudaMemcpyAsync(alpha_last, vec + (size_t)(T & 1) * B * S, (size_t)B * S * 4, cudaMemcpyDeviceToDevice, stream));
+    return FB2_OK;
+}
+
+int hmm_backward_device(int semiring, const float* A, int64_t a_sb, int64_t a_st, const float* obs, const float* final_,
+                        int64_t B, int64_t T, int S, float* beta_all, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream) {
+    PassPlan pl;
+    int st = make_plan(B, S, true, &pl);
+    if (st != FB2_OK) return st;
+    Arena arena(workspace, workspace_bytes);
+    float* vec = arena.take<float>((size_t)2 * B * S);
+    unsigned* ctr = arena.take<unsigned>(1024);
+    if (!arena.ok()) {
+        set_error("hmm backward: workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    FB2_CUDA(cudaMemsetAsync(ctr, 0, 1024 * sizeof(unsigned), stream));
+    HmmArgs a{};
+    a.A = A; a.a_sb = a_sb; a.a_st = a_st; a.obs = obs; a.final_ = final_;
+    a.B = B; a.T = T; a.S = S; a.vec = vec; a.counters = ctr; a.alpha_all = beta_all;
+    a.Gg = pl.Gg; a.W = pl.W; a.LW = pl.LW; a.groups_total = pl.groups_total; a.groups_conc = pl.groups_conc;
+    a.cpo = 1;
+    return run_backward(semiring, pl, a, stream);
+}
+
+}  // namespace fb2
+
+using namespace fb2;
+
+extern "C" size_t fb2_hmm_workspace_bytes(int op, int64_t B, int64_t T, int32_t S) {
+    size_t base = vec_bytes(B, S) + ctr_bytes() + 512;
+    if (op == 1) base += align_up((size_t)B * T * S * sizeof(int32_t)) + align_up((size_t)B * sizeof(int32_t));
+    if (op == 2) base += align_up((size_t)B * T * S * sizeof(float)) + vec_bytes(B, S) + ctr_bytes();
+    return base;
+}
+
+extern "C" int fb2_hmm_forward_f32(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb,
+                                   int64_t a_st, const float* obs, int64_t B, int64_t T, int32_t S, float* logZ,
+                                   float* alpha_all, void* workspace, size_t workspace_bytes, void* stream) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    st = check_hmm_args(semiring, A, B, T, S);
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(logZ != nullptr, "logZ is null");
+    if (B == 0) return FB2_OK;
+    return hmm_forward_device(semiring, init, init_sb, A, a_sb, a_st, obs, nullptr, B, T, S, logZ, alpha_all, nullptr,
+                              nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fb2_hmm_viterbi_f32(const float* init, int64_t init_sb, const float* A, int64_t a_sb, int64_t a_st,
+                                   const float* obs, int64_t B, int64_t T, int32_t S, float* best, int64_t* path,
+                                   void* workspace, size_t workspace_bytes, void* stream_) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    st = check_hmm_args(FB2_SEMIRING_MAX, A, B, T, S);
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(best && path, "null output");
+    if (B == 0) return FB2_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Arena arena(workspace, workspace_bytes);
+    int32_t* bp = arena.take<int32_t>((size_t)B * T * S);
+    int32_t* last = arena.take<int32_t>((size_t)B);
+    if (!arena.ok()) {
+        set_error("viterbi: workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    st = hmm_forward_device(FB2_SEMIRING_MAX, init, init_sb, A, a_sb, a_st, obs, nullptr, B, T, S, best, nullptr, bp, last,
+                            static_cast<char*>(workspace) + arena.used, workspace_bytes - arena.used, stream);
+    if (st != FB2_OK) return st;
+    viterbi_backtrace<<<(unsigned)ceil_div(B, 64), 64, 0, stream>>>(bp, last, B, T, S, path);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
+extern "C" int fb2_hmm_marginals_f32(const float* init, int64_t init_sb, const float* A, int64_t a_sb, int64_t a_st,
+                                     const float* obs, int64_t B, int64_t T, int32_t S, float* logZ, float* gamma,
+                                     float* xi_sum, void* workspace, size_t workspace_bytes, void* stream_) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    st = check_hmm_args(FB2_SEMIRING_LOG, A, B, T, S);
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(logZ && gamma && obs, "null pointer");
+    if (B == 0) return FB2_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Arena arena(workspace, workspace_bytes);
+    float* beta = arena.take<float>((size_t)B * T * S);
+    if (!arena.ok()) {
+        set_error("marginals: workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    char* rest = static_cast<char*>(workspace) + arena.used;
+    size_t rest_bytes = workspace_bytes - arena.used;
+    // alpha goes straight into gamma, then gamma = alpha + beta - logZ in place
+    st = hmm_forward_device(FB2_SEMIRING_LOG, init, init_sb, A, a_sb, a_st, obs, nullptr, B, T, S, logZ, gamma, nullptr,
+                            nullptr, rest, rest_bytes, stream);
+    if (st != FB2_OK) return st;
+    st = hmm_backward_device(FB2_SEMIRING_LOG, A, a_sb, a_st, obs, nullptr, B, T, S, beta, rest, rest_bytes, stream);
+    if (st != FB2_OK) return st;
+    if (xi_sum) {
+        int64_t n = B * (int64_t)S * S;
+        xi_sum_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(init, init_sb, A, a_sb, a_st, obs, gamma, beta, logZ,
+                                                                     B, T, S, xi_sum);
+        FB2_LAUNCH_CHECK();
+    }
+    int64_t n = B * T * (int64_t)S;
+    marginals_combine<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(gamma, beta, logZ, B, T, S);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
+extern "C" size_t fb2_chain_adjoint_workspace_bytes(int64_t B, int64_t T, int32_t S) {
+    return 2 * align_up((size_t)B * T * S * 4) + vec_bytes(B, S) + ctr_bytes() + 512;
+}
+
+extern "C" int fb2_chain_adjoint_f32(int semiring, const float* trans, const int64_t ts[4], const float* init,
+                                     const float* final_, int64_t B, int64_t T, int32_t S, float* Z, float* adj,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    st = check_hmm_args(semiring, trans, B, T, S);
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(Z && adj, "null output");
+    FB2_REQUIRE(ts[2] == S && ts[3] == 1, "chain_adjoint: each trans[b,t] must be a contiguous row-major S x S matrix");
+    if (B == 0) return FB2_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Arena arena(workspace, workspace_bytes);
+    float* alpha = arena.take<float>((size_t)B * T * S);
+    float* beta = arena.take<float>((size_t)B * T * S);
+    if (!arena.ok()) {
+        set_error("chain_adjoint: workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    char* rest = static_cast<char*>(workspace) + arena.used;
+    size_t rest_bytes = workspace_bytes - arena.used;
+    st = hmm_forward_device(semiring, init, S, trans, ts[0], ts[1], nullptr, final_, B, T, S, Z, alpha, nullptr, nullptr,
+                            rest, rest_bytes, stream);
+    if (st != FB2_OK) return st;
+    st = hmm_backward_device(semiring, trans, ts[0], ts[1], nullptr, final_, B, T, S, beta, rest, rest_bytes, stream);
+    if (st != FB2_OK) return st;
+    int64_t n = B * T * (int64_t)S * S;
+    FB2_REQUIRE(ceil_div(n, 256) < (1ll << 31), "chain_adjoint: output too large for one launch");
+    adjoint_outer<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(init, alpha, beta, B, T, S, adj);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
+extern "C" size_t fb2_hmm_chunk_summary_workspace_bytes(int64_t B, int64_t T, int32_t S) {
+    return vec_bytes(B * S, S) + ctr_bytes() + align_up((size_t)B * S * 4) + 512;
+}
+
+extern "C" int fb2_hmm_chunk_summary_f32(int semiring, const float* A, int64_t a_sb, int64_t a_st, const float* obs,
+                                         int64_t B, int64_t T, int32_t S, float* out, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    st = check_hmm_args(semiring, A, B, T, S);
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(out != nullptr, "out is null");
+    if (B == 0) return FB2_OK;
+    Arena arena(workspace, workspace_bytes);
+    float* scratch_out = arena.take<float>((size_t)B * S);  // per-row reductions, unused by the caller
+    if (!arena.ok()) {
+        set_error("chunk_summary: workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    // S chains per batch entry, chain (b, r) starts from the identity row r: the final vectors are the
+    // rows of the chunk's transfer matrix.
+    return hmm_forward_device(semiring, nullptr, 0, A, a_sb, a_st, obs, nullptr, B * S, T, S, scratch_out, nullptr, nullptr,
+                              nullptr, static_cast<char*>(workspace) + arena.used, workspace_bytes - arena.used,
+                              static_cast<cudaStream_t>(stream), S, out);
+}

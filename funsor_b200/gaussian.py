@@ -1,0 +1,137 @@
+"""Host-side mirror of the reference's Gaussian-factor chain path on raw torch CUDA tensors.
+
+Chain elements are carried in information form (Lam[..., 2D, 2D], eta[..., 2D], c[...]) over rows
+(prev; curr): f(x) = c - 1/2 x Lam x' + x eta.  This is the representation-independent content of the
+reference's (white_vec, prec_sqrt, scalar Tensor) triple (funsor/gaussian.py:419-498, 545, 569;
+funsor/testing.py:149-153 compares exactly these).
+
+Mirrors: eager_add_gaussian_gaussian gaussian.py:1117-1132, Gaussian.eager_reduce 841-906,
+_marginalize_after_split 1061-1090, eager_contraction_gaussian cnf.py:385-389,
+sequential_sum_product sum_product.py:652-701, matrix_and_mvn_to_funsor pyro/convert.py:278-298,
+GaussianHMM pyro/hmm.py:258-274.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check
+from .ops import _dev_f32, _ptr, _stream, _workspace
+
+
+def sqrt_to_info(white_vec, prec_sqrt, scalar=None):
+    """(w[..., r], P[..., n, r], s[...]) -> (Lam[..., n, n], eta[..., n], c[...]) with one fused kernel."""
+    _dev_f32(white_vec, "white_vec"), _dev_f32(prec_sqrt, "prec_sqrt")
+    batch = prec_sqrt.shape[:-2]
+    n, r = prec_sqrt.shape[-2:]
+    w = white_vec.expand(batch + (r,)).contiguous()
+    P = prec_sqrt.contiguous()
+    s = None if scalar is None else _dev_f32(scalar, "scalar").expand(batch).contiguous()
+    N = int(torch.Size(batch).numel())
+    Lam = torch.empty(batch + (n, n), dtype=torch.float32, device=P.device)
+    eta = torch.empty(batch + (n,), dtype=torch.float32, device=P.device)
+    c = torch.empty(batch, dtype=torch.float32, device=P.device)
+    lib = _lib.load()
+    with torch.cuda.device(P.device):
+        check(lib.fb2_gaussian_sqrt_to_info_f32(w.data_ptr(), P.data_ptr(), _ptr(s), N, n, r, Lam.data_ptr(), eta.data_ptr(),
+                                                c.data_ptr(), _stream()))
+    return Lam, eta, c
+
+
+def gaussian_pair_combine(x, y):
+    """Contraction[logaddexp, add] of two chain elements x over (a;b) and y over (b;c) (cnf.py:385-389).
+    x, y: tuples (Lam[..., 2D, 2D], eta[..., 2D], c[...]) with identical batch shapes."""
+    Lx, ex, cx = (t.contiguous() for t in x)
+    Ly, ey, cy = (t.contiguous() for t in y)
+    for t in (Lx, ex, cx, Ly, ey, cy):
+        _dev_f32(t, "gaussian element")
+    batch = Lx.shape[:-2]
+    n = Lx.shape[-1]
+    D = n // 2
+    N = int(torch.Size(batch).numel())
+    Lo, eo, co = torch.empty_like(Lx), torch.empty_like(ex), torch.empty_like(cx)
+    flag = torch.zeros(1, dtype=torch.int32, device=Lx.device)
+    lib = _lib.load()
+    with torch.cuda.device(Lx.device):
+        check(lib.fb2_gaussian_pair_combine_f32(Lx.data_ptr(), ex.data_ptr(), cx.data_ptr(), 1, Ly.data_ptr(), ey.data_ptr(),
+                                                cy.data_ptr(), 1, 1, N, 0, 0, D, Lo.data_ptr(), eo.data_ptr(), co.data_ptr(),
+                                                flag.data_ptr(), _stream()))
+    return Lo, eo, co, flag
+
+
+def gaussian_sequential_sum_product(Lam, eta, c, validate=True):
+    """sequential_sum_product(logaddexp, add, ...) over Gaussian chain elements
+    Lam[B, T, 2D, 2D], eta[B, T, 2D], c[B, T] -> (Lam[B, 2D, 2D], eta[B, 2D], c[B])."""
+    for t in (Lam, eta, c):
+        _dev_f32(t, "gaussian element")
+    if Lam.dim() != 4 or Lam.shape[-1] != Lam.shape[-2] or Lam.shape[-1] % 2:
+        raise ValueError("Lam must be [B, T, 2D, 2D], got {}".format(tuple(Lam.shape)))
+    B, T, n, _ = Lam.shape
+    D = n // 2
+    Lam, eta, c = Lam.contiguous(), eta.expand(B, T, n).contiguous(), c.expand(B, T).contiguous()
+    Lo = torch.empty((B, n, n), dtype=torch.float32, device=Lam.device)
+    eo = torch.empty((B, n), dtype=torch.float32, device=Lam.device)
+    co = torch.empty((B,), dtype=torch.float32, device=Lam.device)
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_gaussian_chain_workspace_bytes(B, T, D), Lam.device)
+    with torch.cuda.device(Lam.device):
+        check(lib.fb2_gaussian_chain_f32(Lam.data_ptr(), eta.data_ptr(), c.data_ptr(), B, T, D, Lo.data_ptr(), eo.data_ptr(),
+                                         co.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    if validate and bool(torch.isnan(co).any()):
+        raise ValueError("Too little information to marginalize over the shared state. Consider adding a prior.")
+    return Lo, eo, co
+
+
+def kalman_elements_sqrt(F, q_loc, q_tril, H, r_loc, r_tril, y):
+    """GaussianHMM chain elements (pyro/hmm.py:258-270): trans + obs(value=y_t) in the reference's sqrt
+    form over rows (state; state'), built from time-homogeneous parameters
+    F[B,D,D], q_loc[B,D], q_tril[B,D,D], H[B,D,O], r_loc[B,O], r_tril[B,O,O], y[B,T,O]
+    following matrix_and_mvn_to_funsor (pyro/convert.py:278-298) and the observed-value substitution
+    (gaussian.py:723-744).  Small per-batch linear algebra (triangular inverses) uses torch; the T-sized
+    work is one broadcasted matmul.  Returns w[B,T,D+O], P[B,T,2D,D+O], s[B,T]."""
+    B, T, O = y.shape
+    D = F.shape[-1]
+    eyeD = torch.eye(D, device=F.device, dtype=F.dtype)
+    eyeO = torch.eye(O, device=F.device, dtype=F.dtype)
+    Pq = torch.linalg.solve_triangular(q_tril, eyeD.expand(B, D, D), upper=False).transpose(-1, -2)
+    Pr = torch.linalg.solve_triangular(r_tril, eyeO.expand(B, O, O), upper=False).transpose(-1, -2)
+    P = torch.zeros(B, T, 2 * D, D + O, device=F.device, dtype=F.dtype)
+    P[:, :, :D, :D] = (F @ Pq)[:, None]
+    P[:, :, D:, :D] = (-Pq)[:, None]
+    P[:, :, D:, D:] = (H @ Pr)[:, None]
+    w_t = -(q_loc[:, None, :] @ Pq)[:, 0]  # [B,D]
+    w_o = -(r_loc[:, None, :] @ Pr)[:, 0]  # [B,O]
+    w = torch.cat([w_t[:, None, :].expand(B, T, D), w_o[:, None, :] + y @ Pr], dim=-1)
+    s = (-0.5 * (D + O) * math.log(2 * math.pi) - q_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1)
+         - r_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1))
+    return w.contiguous(), P, s[:, None].expand(B, T).contiguous()
+
+
+def kalman_chain(F, q_loc, q_tril, H, r_loc, r_tril, y):
+    """Parallel-scan Kalman filter: builds the chain elements, converts them to information form and
+    reduces them with the Gaussian scan kernel.  Returns (Lam[B,2D,2D], eta[B,2D], c[B]) over
+    (state_{-1}; state_{T-1}), the value of the reference's MarkovProduct (pyro/hmm.py:269)."""
+    w, P, s = kalman_elements_sqrt(F, q_loc, q_tril, H, r_loc, r_tril, y)
+    Lam, eta, c = sqrt_to_info(w, P, s)
+    return gaussian_sequential_sum_product(Lam, eta, c)
+
+
+def gaussian_hmm_log_prob(m0, p0_tril, chain):
+    """hmm.py:271-272: init + chain.reduce(curr) then reduce(state), for init = N(m0, p0 p0').
+    A [B, 2D, 2D] problem once per call (not T-sized): done with torch.linalg in float64."""
+    Lam, eta, c = (t.double() for t in chain)
+    D = Lam.shape[-1] // 2
+    B = Lam.shape[0]
+    eye = torch.eye(D, device=Lam.device, dtype=torch.float64)
+    Li = torch.linalg.solve_triangular(p0_tril.double(), eye.expand(B, D, D), upper=False)
+    L0 = Li.transpose(-1, -2) @ Li
+    e0 = (L0 @ m0.double()[..., None])[..., 0]
+    c0 = -0.5 * D * math.log(2 * math.pi) - p0_tril.double().diagonal(dim1=-1, dim2=-2).log().sum(-1) - 0.5 * (m0.double() * e0).sum(-1)
+    Lam = Lam.clone()
+    eta = eta.clone()
+    Lam[:, :D, :D] += L0
+    eta[:, :D] += e0
+    Lc = torch.linalg.cholesky(Lam)
+    v = torch.linalg.solve_triangular(Lc, eta[..., None], upper=False)[..., 0]
+    n = 2 * D
+    return c + c0 + 0.5 * n * math.log(2 * math.pi) - Lc.diagonal(dim1=-1, dim2=-2).log().sum(-1) + 0.5 * (v * v).sum(-1)

@@ -1,0 +1,248 @@
+"""Host-side mirror of the reference interface for the Markov-chain sum-product path, on raw
+torch CUDA tensors.  Every function here is a thin marshalling layer over the C ABI in
+include/funsor_b200.h (ctypes, raw device pointers + strides, launch on the current torch stream).
+PyTorch is used for device memory and streams only.  There is no CPU fallback: CPU tensors, non-fp32
+dtypes or a missing shared library raise.
+
+Reference functions mirrored (paths relative to the funsor tree):
+  sequential_sum_product / naive_ / mixed_   funsor/sum_product.py:652-701, 625-649, 704-795
+  Contraction rules (log, max-plus)          funsor/cnf.py:335-379, 312-324
+  DiscreteHMM.log_prob                       funsor/pyro/hmm.py:119-138
+  AdjointTape.adjoint over a scan            funsor/adjoint.py:72-131
+"""
+import torch
+
+from . import _lib
+from ._lib import SEMIRING_LOG, SEMIRING_MAX, check, strides4
+
+
+def semiring_id(sum_op, prod_op="add"):
+    """Map (sum_op, prod_op) -- strings or funsor.ops objects -- to the C-ABI semiring id.
+    Only the two semirings of the path are accepted (funsor/einsum/__init__.py:13-28)."""
+    s = getattr(sum_op, "__name__", None) or str(sum_op)
+    p = getattr(prod_op, "__name__", None) or str(prod_op)
+    s, p = s.replace("ops.", ""), p.replace("ops.", "")
+    if p != "add":
+        raise NotImplementedError("funsor_b200 supports prod_op=add only, got {!r}".format(prod_op))
+    if s in ("logaddexp", "log", "logsumexp"):
+        return SEMIRING_LOG
+    if s in ("max", "amax"):
+        return SEMIRING_MAX
+    raise NotImplementedError("funsor_b200 supports sum_op in {{logaddexp, max}}, got {!r}".format(sum_op))
+
+
+def _dev_f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("{} must be a torch.Tensor".format(name))
+    if not t.is_cuda:
+        raise ValueError("{} must live on a CUDA device: funsor_b200 has no CPU path".format(name))
+    if t.dtype != torch.float32:
+        raise ValueError("{} must be float32, got {}".format(name, t.dtype))
+    return t
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------------------- a6 / a7
+def semiring_matmul(sum_op, prod_op, x, y, want_argmax=False):
+    """out[..., i, j] = (+)_k x[..., i, k] (x) y[..., k, j]  for strided views x, y.
+
+    Mirrors the eager Contraction of two Tensors that one scan level performs (cnf.py:335-379 for
+    (logaddexp, add); cnf.py:312-324 for (max, add)).  With want_argmax (max only) also returns the
+    first maximising k as int32 (approximations.py:115-127)."""
+    semi = semiring_id(sum_op, prod_op)
+    _dev_f32(x, "x"), _dev_f32(y, "y")
+    if x.dim() < 2 or y.dim() < 2 or x.shape[-1] != y.shape[-2]:
+        raise ValueError("shape mismatch: x {} y {}".format(tuple(x.shape), tuple(y.shape)))
+    I, K, J = x.shape[-2], x.shape[-1], y.shape[-1]
+    if K < 1:
+        raise ValueError("contracted dimension must be non-empty")
+    batch = torch.broadcast_shapes(x.shape[:-2], y.shape[:-2])
+    x = x.expand(batch + (I, K))
+    y = y.expand(batch + (K, J))
+    if len(batch) > 2:  # collapse leading dims (may copy for exotic layouts)
+        x = x.reshape((-1, batch[-1], I, K))
+        y = y.reshape((-1, batch[-1], K, J))
+    while x.dim() < 4:
+        x, y = x.unsqueeze(0), y.unsqueeze(0)
+    n0, n1 = x.shape[0], x.shape[1]
+    out = torch.empty((n0, n1, I, J), dtype=torch.float32, device=x.device)
+    arg = torch.empty((n0, n1, I, J), dtype=torch.int32, device=x.device) if want_argmax else None
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        check(lib.fb2_semiring_matmul_f32(semi, x.data_ptr(), strides4(x.stride()), y.data_ptr(), strides4(y.stride()),
+                                          out.data_ptr(), _ptr(arg), n0, n1, I, K, J, _stream()))
+    out = out.reshape(batch + (I, J))
+    return (out, arg.reshape(batch + (I, J))) if want_argmax else out
+
+
+# ----------------------------------------------------------------------------------------- a1 - a4
+def sequential_sum_product(sum_op, prod_op, trans, time=-3):
+    """Chain product over the `time` dim of trans[..., T, S, S] (prev = dim -2, curr = dim -1), in the
+    reference's balanced-tree order (sum_product.py:690-701).  Returns [..., S, S]."""
+    semi = semiring_id(sum_op, prod_op)
+    _dev_f32(trans, "trans")
+    if trans.dim() < 3 or trans.shape[-1] != trans.shape[-2]:
+        raise ValueError("trans must be [..., T, S, S], got {}".format(tuple(trans.shape)))
+    if time not in (-3, trans.dim() - 3):
+        trans = trans.movedim(time, -3)
+    batch = trans.shape[:-3]
+    T, S = trans.shape[-3], trans.shape[-1]
+    if T < 1:
+        raise ValueError("time dimension must be non-empty")
+    t4 = trans.reshape((-1, T, S, S)) if len(batch) != 1 else trans
+    B = t4.shape[0]
+    out = torch.empty((B, S, S), dtype=torch.float32, device=trans.device)
+    lib = _lib.load()
+    nbytes = lib.fb2_chain_product_workspace_bytes(B, T, S)
+    ws = _workspace(nbytes, trans.device)
+    with torch.cuda.device(trans.device):
+        check(lib.fb2_chain_product_f32(semi, t4.data_ptr(), strides4(t4.stride()), B, T, S, out.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _stream()))
+    return out.reshape(batch + (S, S))
+
+
+def naive_sequential_sum_product(sum_op, prod_op, trans, time=-3):
+    """Same value as sequential_sum_product (sum_product.py:625-649 is the serial right fold of the
+    same associative product); on the GPU both run the tree."""
+    return sequential_sum_product(sum_op, prod_op, trans, time)
+
+
+def mixed_sequential_sum_product(sum_op, prod_op, trans, time=-3, num_segments=None):
+    """sum_product.py:704-795: serial scan inside num_segments equal segments, parallel scan across.
+    The segment products are themselves chain products, so this is two calls of the same kernel;
+    a ragged tail is folded on afterwards exactly like the reference's recursion (731-758)."""
+    if time not in (-3, trans.dim() - 3):
+        trans = trans.movedim(time, -3)
+    T = trans.shape[-3]
+    num_segments = T if num_segments is None else num_segments
+    if num_segments <= 1 or num_segments >= T:
+        return sequential_sum_product(sum_op, prod_op, trans)
+    rem = T % num_segments
+    head = trans[..., : T - rem, :, :]
+    L = (T - rem) // num_segments
+    seg = head.reshape(head.shape[:-3] + (num_segments, L) + head.shape[-2:])
+    first = sequential_sum_product(sum_op, prod_op, seg)  # [..., num_segments, S, S]
+    result = sequential_sum_product(sum_op, prod_op, first)
+    if rem:
+        tail = torch.cat([result.unsqueeze(-3), trans[..., T - rem :, :, :]], dim=-3)
+        result = sequential_sum_product(sum_op, prod_op, tail)
+    return result
+
+
+# ----------------------------------------------------------------------------------------- factored HMM
+def _hmm_args(init, A, obs):
+    _dev_f32(obs, "obs"), _dev_f32(A, "A")
+    if obs.dim() != 3:
+        raise ValueError("obs must be [B, T, S], got {}".format(tuple(obs.shape)))
+    B, T, S = obs.shape
+    obs = obs.contiguous()
+    if A.shape[-2:] != (S, S):
+        raise ValueError("A must end in [S, S] with S={}, got {}".format(S, tuple(A.shape)))
+    A = A.contiguous()
+    if A.dim() == 2:
+        a_sb, a_st = 0, 0
+    elif A.dim() == 3 and A.shape[0] == B:
+        a_sb, a_st = S * S, 0
+    elif A.dim() == 4 and A.shape[:2] == (B, T):
+        a_sb, a_st = T * S * S, S * S
+    elif A.dim() == 3 and A.shape[0] == T and B != T:
+        raise ValueError("time-varying A must be given as [B, T, S, S]")
+    else:
+        raise ValueError("A must be [S,S], [B,S,S] or [B,T,S,S]; got {}".format(tuple(A.shape)))
+    if init is None:
+        init_t, init_sb = None, 0
+    else:
+        _dev_f32(init, "init")
+        init_t = init.contiguous()
+        if init_t.shape == (S,):
+            init_sb = 0
+        elif init_t.shape == (B, S):
+            init_sb = S
+        else:
+            raise ValueError("init must be [S] or [B, S]; got {}".format(tuple(init.shape)))
+    return init_t, init_sb, A, a_sb, a_st, obs, B, T, S
+
+
+def hmm_forward(init, A, obs, sum_op="logaddexp", return_alpha=False):
+    """DiscreteHMM.log_prob (hmm.py:129-135) without materialising trans + obs:
+    returns (+)_{paths} init[z0] (x) prod_t (A[z_{t-1}, z_t] (x) obs[t, z_t])  as [B]."""
+    semi = semiring_id(sum_op)
+    init_t, init_sb, A, a_sb, a_st, obs, B, T, S = _hmm_args(init, A, obs)
+    out = torch.empty((B,), dtype=torch.float32, device=obs.device)
+    alpha = torch.empty((B, T, S), dtype=torch.float32, device=obs.device) if return_alpha else None
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_hmm_workspace_bytes(0, B, T, S), obs.device)
+    with torch.cuda.device(obs.device):
+        check(lib.fb2_hmm_forward_f32(semi, _ptr(init_t), init_sb, A.data_ptr(), a_sb, a_st, obs.data_ptr(), B, T, S,
+                                      out.data_ptr(), _ptr(alpha), ws.data_ptr(), ws.numel(), _stream()))
+    return (out, alpha) if return_alpha else out
+
+
+def hmm_viterbi(init, A, obs):
+    """Max-plus forward + back-pointers + backtrace.  Returns (best[B], path[B, T+1] int64) with
+    path[:, 0] the state before the first transition; first-index tie-break."""
+    init_t, init_sb, A, a_sb, a_st, obs, B, T, S = _hmm_args(init, A, obs)
+    best = torch.empty((B,), dtype=torch.float32, device=obs.device)
+    path = torch.empty((B, T + 1), dtype=torch.int64, device=obs.device)
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_hmm_workspace_bytes(1, B, T, S), obs.device)
+    with torch.cuda.device(obs.device):
+        check(lib.fb2_hmm_viterbi_f32(_ptr(init_t), init_sb, A.data_ptr(), a_sb, a_st, obs.data_ptr(), B, T, S,
+                                      best.data_ptr(), path.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return best, path
+
+
+def hmm_marginals(init, A, obs, want_xi=True):
+    """Forward-backward posteriors (examples/forward_backward.py:58-107,162):
+    logZ[B], gamma[B,T,S] = log p(z_t | obs), xi_sum[B,S,S] = sum_t p(z_{t-1}, z_t | obs)."""
+    init_t, init_sb, A, a_sb, a_st, obs, B, T, S = _hmm_args(init, A, obs)
+    logZ = torch.empty((B,), dtype=torch.float32, device=obs.device)
+    gamma = torch.empty((B, T, S), dtype=torch.float32, device=obs.device)
+    xi = torch.empty((B, S, S), dtype=torch.float32, device=obs.device) if want_xi else None
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_hmm_workspace_bytes(2, B, T, S), obs.device)
+    with torch.cuda.device(obs.device):
+        check(lib.fb2_hmm_marginals_f32(_ptr(init_t), init_sb, A.data_ptr(), a_sb, a_st, obs.data_ptr(), B, T, S,
+                                        logZ.data_ptr(), gamma.data_ptr(), _ptr(xi), ws.data_ptr(), ws.numel(), _stream()))
+    return logZ, gamma, xi
+
+
+def chain_adjoint(sum_op, prod_op, trans, init=None, final=None):
+    """Backward pass of the scan (adjoint.py:72-131 specialised to a chain):
+    returns (Z[B], adj[B,T,S,S]) with adj[b,t,i,j] = alpha_{t-1}[i] (x) beta_t[j].
+    Posterior pairwise marginal = adj + trans - Z (examples/forward_backward.py:162)."""
+    semi = semiring_id(sum_op, prod_op)
+    _dev_f32(trans, "trans")
+    if trans.dim() != 4 or trans.shape[-1] != trans.shape[-2]:
+        raise ValueError("trans must be [B, T, S, S]")
+    trans = trans.contiguous()
+    B, T, S, _ = trans.shape
+    init_t = None if init is None else _dev_f32(init, "init").expand(B, S).contiguous()
+    final_t = None if final is None else _dev_f32(final, "final").expand(B, S).contiguous()
+    Z = torch.empty((B,), dtype=torch.float32, device=trans.device)
+    adj = torch.empty((B, T, S, S), dtype=torch.float32, device=trans.device)
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_chain_adjoint_workspace_bytes(B, T, S), trans.device)
+    with torch.cuda.device(trans.device):
+        check(lib.fb2_chain_adjoint_f32(semi, trans.data_ptr(), strides4(trans.stride()), _ptr(init_t), _ptr(final_t), B, T, S,
+                                        Z.data_ptr(), adj.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return Z, adj
+
+
+def launch_count(reset=False):
+    lib = _lib.load()
+    n = int(lib.fb2_launch_count())
+    if reset:
+        lib.fb2_launch_count_reset()
+    return n

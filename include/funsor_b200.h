@@ -1,0 +1,159 @@
+/*
+ * funsor_b200 -- C ABI of the B200-native Markov-chain sum-product path.
+ *
+ * This is the drop-in boundary: plain pointers, sizes and strides, no
+ * torch types.  Every entry point returns an int status (FB2_OK == 0) and never throws; a message
+ * for the last non-zero status of the calling thread is available from fb2_last_error().
+ * All `const float*` / `float*` arguments are DEVICE pointers unless the function name ends in
+ * `_host`.  Strides are in ELEMENTS.  `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream).  Kernels neither allocate nor free: scratch memory is passed in as `workspace`, sized by
+ * the matching *_workspace_bytes() query, and must be 256-byte aligned.  No host synchronisation
+ * happens inside the device-pointer entry points.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the funsor tree).
+ */
+#ifndef FUNSOR_B200_H
+#define FUNSOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB2_VERSION 100
+
+/* status codes */
+#define FB2_OK 0
+#define FB2_ERR_INVALID_ARGUMENT 1 /* -> Python ValueError                                   */
+#define FB2_ERR_UNSUPPORTED 2      /* -> delegate to the captured reference rule / NotImplementedError */
+#define FB2_ERR_CUDA 3             /* -> RuntimeError                                        */
+#define FB2_ERR_WORKSPACE 4        /* workspace too small or misaligned                      */
+#define FB2_ERR_NO_DEVICE 5        /* no sm_100 device: the product path fails loudly, no CPU fallback */
+#define FB2_ERR_NUMERIC 6          /* e.g. non-positive pivot: "Too little information to marginalize" (gaussian.py:897-901) */
+
+/* semirings: (sum_op, prod_op) pairs of funsor/ops/builtin.py:266-292 that the path supports */
+#define FB2_SEMIRING_LOG 0 /* (ops.logaddexp, ops.add) */
+#define FB2_SEMIRING_MAX 1 /* (ops.max, ops.add)       */
+
+int fb2_version(void);
+const char* fb2_status_string(int status);
+const char* fb2_last_error(void);
+/* Device facts the host side needs for grid sizing / roofline arithmetic. */
+int fb2_device_query(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Strided batched semiring matmul -- one level of the scan.
+ * Replaces: Contraction[Logaddexp, Add, Tensor, Tensor] funsor/cnf.py:335-379 (-> einsum/numpy_log.py:24-47)
+ *           Contraction[Max, Add, Tensor, Tensor]       funsor/cnf.py:312-324 (-> tensor.py:700-726, 313-330)
+ *   out[n0,n1,i,j] = (+)_k x[n0,n1,i,k] (x) y[n0,n1,k,j]
+ * x, y are arbitrary strided views (the reference passes even/odd time slices);
+ * out is contiguous [n0,n1,I,J].  LOG uses the reference's clamped row/column max shifts.
+ * argk (nullable, MAX only): int32 [n0,n1,I,J], first maximising k (approximations.py:115-127).
+ */
+int fb2_semiring_matmul_f32(int semiring, const float* x, const int64_t x_strides[4], const float* y,
+                            const int64_t y_strides[4], float* out, int32_t* argk, int64_t n0, int64_t n1,
+                            int32_t I, int32_t K, int32_t J, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Chain product over time -- the whole scan.
+ * Replaces: sequential_sum_product funsor/sum_product.py:652-701, naive_/mixed_ 625-649/704-795,
+ *           eager MarkovProduct 1049-1064 for Tensor factors.
+ *   out[b] = trans[b,0] (x) trans[b,1] (x) ... (x) trans[b,T-1]   (matrix products in the semiring)
+ * Association order is the reference's balanced even/odd tree (sum_product.py:690-701), so MAX
+ * results are bit-identical to the reference evaluated in fp32.  trans is a strided [B,T,S,S] view,
+ * out is contiguous [B,S,S].
+ */
+size_t fb2_chain_product_workspace_bytes(int64_t B, int64_t T, int32_t S);
+int fb2_chain_product_f32(int semiring, const float* trans, const int64_t trans_strides[4], int64_t B,
+                          int64_t T, int32_t S, float* out, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Factored HMM passes: trans[b,t,i,j] = A[b,t,i,j] + obs[b,t,j] is never materialised.
+ * Replaces: DiscreteHMM.log_prob funsor/pyro/hmm.py:129-135 (trans + obs -> sequential_sum_product
+ *           -> init + reduce(curr) -> reduce(state)) evaluated as a vector recurrence.
+ * init  [B,S]   batch stride init_sb (0 = shared)
+ * A     [S,S]   row-major (prev, curr); batch stride a_sb and time stride a_st (0 = shared / homogeneous)
+ * obs   [B,T,S] contiguous
+ * forward : logZ[B] (required); alpha_all (nullable) [B,T,S] log-domain filtered messages.
+ * viterbi : best[B] max-plus value and path[B,T+1] int64 (path[:,0] = state before step 0); first-index
+ *           tie-break; recurrence delta_t[j] = max_i(delta_{t-1}[i] + (A[i,j] + obs[t,j])) evaluated in
+ *           that fp32 order, so values are bit-identical to a serial fp32 evaluation.
+ * marginals (examples/forward_backward.py:58-107,162): logZ[B], gamma[B,T,S] = log p(z_t | obs),
+ *           xi_sum (nullable) [B,S,S] = sum_t p(z_{t-1}=i, z_t=j | obs).
+ */
+size_t fb2_hmm_workspace_bytes(int op /*0 fwd, 1 viterbi, 2 marginals*/, int64_t B, int64_t T, int32_t S);
+int fb2_hmm_forward_f32(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb,
+                        int64_t a_st, const float* obs, int64_t B, int64_t T, int32_t S, float* logZ,
+                        float* alpha_all, void* workspace, size_t workspace_bytes, void* stream);
+int fb2_hmm_viterbi_f32(const float* init, int64_t init_sb, const float* A, int64_t a_sb, int64_t a_st,
+                        const float* obs, int64_t B, int64_t T, int32_t S, float* best, int64_t* path,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int fb2_hmm_marginals_f32(const float* init, int64_t init_sb, const float* A, int64_t a_sb, int64_t a_st,
+                          const float* obs, int64_t B, int64_t T, int32_t S, float* logZ, float* gamma,
+                          float* xi_sum, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Time-sharded pieces: one rank owns obs[:, t0:t1].
+ * chunk_summary: out[b] = (x)_{t in chunk} (A + obs[b,t]) as an S x S matrix (the summary that is
+ *                all-gathered); it is the forward recurrence started from the semiring identity matrix.
+ * The fold of gathered summaries into boundary vectors uses fb2_semiring_matmul_f32 with I = 1. */
+size_t fb2_hmm_chunk_summary_workspace_bytes(int64_t B, int64_t T, int32_t S);
+int fb2_hmm_chunk_summary_f32(int semiring, const float* A, int64_t a_sb, int64_t a_st, const float* obs,
+                              int64_t B, int64_t T, int32_t S, float* out /*[B,S,S]*/, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (4) Dense adjoint of the chain (backward pass).
+ * Replaces: AdjointTape.adjoint over a scan, funsor/adjoint.py:72-131, 231-294 (+ Scatter tensor.py:639-683).
+ *   adj[b,t,i,j] = alpha_{t-1}[b,i] (x) beta_t[b,j];  Z[b] = (+)_j alpha_{T-1}[b,j] (x) final[b,j]
+ * init/final nullable (= semiring unit).  trans strided [B,T,S,S]; adj contiguous [B,T,S,S].
+ */
+size_t fb2_chain_adjoint_workspace_bytes(int64_t B, int64_t T, int32_t S);
+int fb2_chain_adjoint_f32(int semiring, const float* trans, const int64_t trans_strides[4], const float* init,
+                          const float* final_, int64_t B, int64_t T, int32_t S, float* Z, float* adj,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (5) Gaussian factors in information form (Lam[n,n], eta[n], c): f(x) = c - 1/2 x Lam x' + x eta,
+ *     n = 2D over rows (prev; curr).  Lam = P P', eta = P w, c = s - |w|^2/2 of the reference's
+ *     (white_vec w, prec_sqrt P, scalar Tensor s) triple (funsor/gaussian.py:419-498, 545, 569).
+ * sqrt_to_info : that conversion (fused P P' / P w), elements strided over [N].
+ * pair_combine : Contraction[Logaddexp, Add, Gaussian|GaussianMixture x2] funsor/cnf.py:385-389 =
+ *                eager_add_gaussian_gaussian gaussian.py:1117-1132 + Gaussian.eager_reduce 841-906 +
+ *                _marginalize_after_split 1061-1090, as a Schur complement on the shared block.
+ * chain        : sequential_sum_product over Gaussian elements, reference tree order.
+ * Element n of a batch lives at base + n*stride; Lam row-major [2D,2D].  D <= 32.
+ */
+int fb2_gaussian_sqrt_to_info_f32(const float* w, const float* P, const float* s, int64_t N, int32_t dim,
+                                  int32_t rank, float* Lam, float* eta, float* c, void* stream);
+int fb2_gaussian_pair_combine_f32(const float* Lx, const float* ex, const float* cx, int64_t x_stride,
+                                  const float* Ly, const float* ey, const float* cy, int64_t y_stride,
+                                  int64_t n0, int64_t n1, int64_t x_s0, int64_t y_s0, int32_t D, float* Lo,
+                                  float* eo, float* co, int32_t* status_flag, void* stream);
+size_t fb2_gaussian_chain_workspace_bytes(int64_t B, int64_t T, int32_t D);
+int fb2_gaussian_chain_f32(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D,
+                           float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer entry points (what a CPU-side caller of the reference binds): inputs and outputs are
+ * HOST pointers; the call stages them through device memory it owns (one cached arena per thread),
+ * runs the device path on its own stream and synchronises before returning.  These are the `e2e`
+ * numbers of bench.py.
+ */
+int fb2_hmm_forward_f32_host(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb,
+                             int64_t a_st, const float* obs, int64_t B, int64_t T, int32_t S, float* logZ);
+int fb2_chain_product_f32_host(int semiring, const float* trans, int64_t B, int64_t T, int32_t S, float* out);
+int fb2_host_arena_release(void);
+
+/* Counters: kernels launched by this library on the calling thread since the last reset (bench.py's
+ * gpu_launches). */
+int64_t fb2_launch_count(void);
+void fb2_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUNSOR_B200_H */

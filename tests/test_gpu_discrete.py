@@ -1,0 +1,286 @@
+"""GPU parity tests for the discrete path: CUDA kernels (through the C ABI) vs the numpy oracle and the
+golden fixtures produced by the unmodified reference.
+
+Tolerances: the north star asks for 1e-5 relative (fp32) on log-normalisers; we use the reference
+comparator |d| <= rtol * (atol + |expected|) (funsor/testing.py:176-178) with rtol = 1e-5 and atol = 1.
+Max-plus values and all argmax / path indices are compared bit-exactly against an fp32 evaluation of
+the same recurrence."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cases, load_golden, rel_close
+from oracle import semiring_ref as R
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+SEMI = {"log": ("logaddexp", R.LOG), "max": ("max", R.MAX)}
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import funsor_b200
+
+    assert torch.cuda.is_available()
+    return funsor_b200
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("sname", ["log", "max"])
+def test_pair_product_golden(fb, sname):
+    op, _ = SEMI[sname]
+    for case, d in golden_cases(load_golden("pair_product")).items():
+        got = fb.semiring_matmul(op, "add", dev(d["x"]), dev(d["y"]))
+        rel_close(host(got), d[sname], rtol=RTOL, atol=1.0)
+
+
+@pytest.mark.parametrize("sname", ["log", "max"])
+@pytest.mark.parametrize("shape", [(3, 5, 70, 100, 33), (1, 2, 129, 64, 257), (2, 1, 64, 64, 64), (1, 1, 5, 300, 7)])
+def test_pair_product_random_strided(fb, sname, shape):
+    op, sid = SEMI[sname]
+    n0, n1, I, K, J = shape
+    g = torch.Generator().manual_seed(1)
+    xx = torch.randn(n0, 2 * n1, I, K, generator=g) * 3
+    yy = torch.randn(n0, 2 * n1, K, J, generator=g) * 3
+    x, y = xx.cuda()[:, 0::2], yy.cuda()[:, 1::2]  # even/odd views as in sum_product.py:692-693
+    got = fb.semiring_matmul(op, "add", x, y)
+    want = R.pair_product(sid, xx[:, 0::2].double().numpy(), yy[:, 1::2].double().numpy())
+    rel_close(host(got), want, rtol=RTOL, atol=1.0)
+    # transposed (non unit inner stride) and broadcast operands
+    got_t = fb.semiring_matmul(op, "add", yy.cuda()[:, 1::2].transpose(-1, -2), xx.cuda()[:, 0::2].transpose(-1, -2))
+    rel_close(host(got_t), np.swapaxes(want, -1, -2), rtol=RTOL, atol=1.0)
+    got_b = fb.semiring_matmul(op, "add", x[:1, :1], y)
+    want_b = R.pair_product(sid, xx[:1, 0:1].double().numpy(), yy[:, 1::2].double().numpy())
+    rel_close(host(got_b), want_b, rtol=RTOL, atol=1.0)
+
+
+def test_pair_product_max_bit_exact_and_argmax(fb):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 3, 65, 90, generator=g)
+    y = torch.randn(2, 3, 90, 70, generator=g)
+    y[0, 0, 5] = y[0, 0, 3]  # duplicate rows -> exact ties, first index must win
+    x[0, 0, :, 5] = x[0, 0, :, 3]
+    out, arg = fb.semiring_matmul("max", "add", x.cuda(), y.cuda(), want_argmax=True)
+    want, warg = R.max_matmul(x.numpy(), y.numpy(), want_arg=True)
+    assert np.array_equal(host(out), want)
+    assert np.array_equal(host(arg).astype(np.int64), warg)
+    out_s, arg_s = fb.semiring_matmul("max", "add", x[..., :9, :].cuda(), y[..., :7].cuda(), want_argmax=True)
+    want, warg = R.max_matmul(x[..., :9, :].numpy(), y[..., :7].numpy(), want_arg=True)
+    assert np.array_equal(host(out_s), want) and np.array_equal(host(arg_s).astype(np.int64), warg)
+
+
+def test_pair_product_neg_inf(fb):
+    x = torch.randn(1, 1, 40, 40)
+    y = torch.randn(1, 1, 40, 40)
+    x[0, 0, 3, :] = -float("inf")
+    y[0, 0, :, 7] = -float("inf")
+    x[0, 0, 10, 5] = -float("inf")
+    for sname, (op, sid) in SEMI.items():
+        got = host(fb.semiring_matmul(op, "add", x.cuda(), y.cuda()))
+        want = R.pair_product(sid, x.double().numpy(), y.double().numpy())
+        assert np.isneginf(got[0, 0, 3]).all() and np.isneginf(got[0, 0, :, 7]).all()
+        assert not np.isnan(got).any()
+        rel_close(got, want, rtol=RTOL, atol=1.0)
+
+
+@pytest.mark.parametrize("sname", ["log", "max"])
+def test_chain_product_golden(fb, sname):
+    op, sid = SEMI[sname]
+    for case, d in golden_cases(load_golden("chain_product")).items():
+        T = d["trans"].shape[1]
+        got = host(fb.sequential_sum_product(op, "add", dev(d["trans"])))
+        rel_close(got, d[sname + "_seq"], rtol=RTOL, atol=1.0)
+        if sname == "max":  # same association order as the reference -> bit-identical to its fp32 evaluation
+            assert np.array_equal(got, R.chain_product(R.MAX, d["trans"].astype(np.float32))), case
+        if sname + "_mixed2" in d and T >= 2:
+            for seg in (2, 3):
+                got = host(fb.mixed_sequential_sum_product(op, "add", dev(d["trans"]), num_segments=seg))
+                rel_close(got, d[sname + "_mixed%d" % seg], rtol=RTOL, atol=1.0)
+
+
+@pytest.mark.parametrize("sname", ["log", "max"])
+@pytest.mark.parametrize("B,T,S", [(2, 33, 64), (1, 7, 130), (5, 1, 9), (3, 1000, 4), (1, 2, 256)])
+def test_chain_product_random(fb, sname, B, T, S):
+    op, sid = SEMI[sname]
+    g = torch.Generator().manual_seed(3)
+    trans = torch.randn(B, T, S, S, generator=g)
+    got = host(fb.sequential_sum_product(op, "add", trans.cuda()))
+    want = R.chain_product(sid, trans.double().numpy())
+    rel_close(got, want, rtol=RTOL, atol=1.0)
+    # strided input: time in a different position (Cat moves time to dim 0 in the reference, tensor.py:942-962)
+    tt = trans.permute(1, 0, 2, 3).contiguous().cuda()
+    got2 = host(fb.sequential_sum_product(op, "add", tt, time=0))
+    assert np.array_equal(got, got2)
+
+
+def test_c1_config(fb):
+    d = golden_cases(load_golden("hmm_logprob"))["c1"]
+    chain = fb.sequential_sum_product("logaddexp", "add", dev(d["trans"]))
+    z = torch.logsumexp(dev(d["init"])[:, :, None] + chain, dim=(-1, -2))
+    rel_close(host(z), d["logZ_fp64"], rtol=RTOL)
+    z2 = fb.hmm_forward(dev(d["init"]), dev(d["trans"]), torch.zeros(1, 100, 16, device="cuda"))
+    rel_close(host(z2), d["logZ_fp64"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("sname", ["log", "max"])
+def test_hmm_forward_golden(fb, sname):
+    op, sid = SEMI[sname]
+    g = golden_cases(load_golden("hmm_logprob"))
+    g.pop("c1")
+    for case, d in g.items():
+        got = fb.hmm_forward(dev(d["init"]), dev(d["A"]), dev(d["obs"]), sum_op=op)
+        rel_close(host(got), d[sname + "_Z"], rtol=RTOL, atol=1.0)
+
+
+@pytest.mark.parametrize("sname", ["log", "max"])
+@pytest.mark.parametrize("B,T,S,amode", [(5, 200, 64, "shared"), (16, 40, 1024, "shared"), (3, 30, 100, "batched"),
+                                         (2, 12, 37, "timevarying"), (40, 25, 16, "shared"), (1, 64, 700, "shared")])
+def test_hmm_forward_random(fb, sname, B, T, S, amode):
+    op, sid = SEMI[sname]
+    g = torch.Generator().manual_seed(4)
+    init = torch.randn(B, S, generator=g).log_softmax(-1)
+    shape = {"shared": (S, S), "batched": (B, S, S), "timevarying": (B, T, S, S)}[amode]
+    A = torch.randn(*shape, generator=g).log_softmax(-1)
+    obs = torch.randn(B, T, S, generator=g)
+    got, alpha = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda(), sum_op=op, return_alpha=True)
+    want, walpha = R.hmm_forward(sid, init.double().numpy(), A.double().numpy(), obs.double().numpy(), want_alpha=True)
+    rel_close(host(got), want, rtol=RTOL, atol=1.0)
+    rel_close(host(alpha), walpha, rtol=RTOL, atol=1.0)
+
+
+def test_hmm_forward_neg_inf(fb):
+    g = torch.Generator().manual_seed(5)
+    B, T, S = 3, 20, 12
+    init = torch.randn(B, S, generator=g)
+    A = torch.randn(S, S, generator=g)
+    A[0, 1] = -float("inf")
+    A[:, 4] = -float("inf")  # unreachable state
+    obs = torch.randn(B, T, S, generator=g)
+    obs[1, 3, 2] = -float("inf")
+    obs[2, 5, :] = -float("inf")  # impossible observation -> logZ = -inf, not NaN
+    for sname, (op, sid) in SEMI.items():
+        got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda(), sum_op=op))
+        want = R.hmm_forward(sid, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+        assert np.isneginf(got[2]) and not np.isnan(got).any()
+        rel_close(got, want, rtol=RTOL, atol=1.0)
+
+
+@pytest.mark.parametrize("B,T,S,amode", [(2, 50, 16, "shared"), (1, 300, 257, "shared"), (3, 20, 40, "batched"),
+                                         (2, 9, 5, "timevarying"), (17, 11, 8, "shared")])
+def test_viterbi_bit_exact(fb, B, T, S, amode):
+    g = torch.Generator().manual_seed(6)
+    init = torch.randn(B, S, generator=g)
+    shape = {"shared": (S, S), "batched": (B, S, S), "timevarying": (B, T, S, S)}[amode]
+    A = torch.randn(*shape, generator=g)
+    obs = torch.randn(B, T, S, generator=g)
+    best, path = fb.hmm_viterbi(init.cuda(), A.cuda(), obs.cuda())
+    wbest, wpath = R.viterbi(init.numpy(), A.numpy(), obs.numpy())  # fp32, same recurrence
+    assert np.array_equal(host(best), wbest)
+    assert np.array_equal(host(path), wpath)
+    # value parity with the reference's max-plus scan semantics in fp64
+    want = R.hmm_forward(R.MAX, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    rel_close(host(best), want, rtol=RTOL, atol=1.0)
+
+
+def test_viterbi_ties_first_index(fb):
+    B, T, S = 2, 6, 5
+    init = torch.zeros(B, S)
+    A = torch.zeros(S, S)
+    obs = torch.zeros(B, T, S)
+    best, path = fb.hmm_viterbi(init.cuda(), A.cuda(), obs.cuda())
+    wbest, wpath = R.viterbi(init.numpy(), A.numpy(), obs.numpy())
+    assert np.array_equal(host(path), wpath) and (host(path) == 0).all()
+
+
+def test_viterbi_planted_path(fb):
+    # SURVEY 8(d) C3 at reduced size: planted path with a margin must be recovered exactly
+    g = torch.Generator().manual_seed(7)
+    T, S = 400, 512
+    A = torch.randn(S, S, generator=g)
+    obs = torch.randn(1, T, S, generator=g)
+    init = torch.randn(1, S, generator=g)
+    z = torch.randint(0, S, (T + 1,), generator=g)
+    init[0, z[0]] += 30.0
+    obs[0, torch.arange(T), z[1:]] += 30.0
+    best, path = fb.hmm_viterbi(init.cuda(), A.cuda(), obs.cuda())
+    assert np.array_equal(host(path)[0], z.numpy())
+    score = R.path_score(init.numpy(), A.numpy(), obs.numpy(), z.numpy()[None])
+    rel_close(host(best), score, rtol=RTOL, atol=1.0)
+
+
+@pytest.mark.parametrize("B,T,S,amode", [(2, 30, 16, "shared"), (1, 100, 130, "shared"), (3, 12, 20, "batched"), (2, 9, 6, "timevarying")])
+def test_hmm_marginals(fb, B, T, S, amode):
+    g = torch.Generator().manual_seed(8)
+    init = torch.randn(B, S, generator=g).log_softmax(-1)
+    shape = {"shared": (S, S), "batched": (B, S, S), "timevarying": (B, T, S, S)}[amode]
+    A = torch.randn(*shape, generator=g).log_softmax(-1)
+    obs = torch.randn(B, T, S, generator=g)
+    logZ, gamma, xi = fb.hmm_marginals(init.cuda(), A.cuda(), obs.cuda())
+    wZ, wgamma, wxi = R.hmm_marginals(init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    rel_close(host(logZ), wZ, rtol=RTOL, atol=1.0)
+    rel_close(host(gamma), wgamma, rtol=1e-4, atol=1.0)
+    np.testing.assert_allclose(host(xi), wxi, rtol=1e-4, atol=1e-5 * T)
+    np.testing.assert_allclose(np.exp(host(gamma)).sum(-1), 1.0, atol=1e-4)
+
+
+@pytest.mark.parametrize("sname", ["log", "max"])
+def test_chain_adjoint_golden(fb, sname):
+    op, sid = SEMI[sname]
+    for case, d in golden_cases(load_golden("adjoint")).items():
+        Z, adj = fb.chain_adjoint(op, "add", dev(d["trans"]))
+        rel_close(host(Z), d[sname + "_Z"], rtol=RTOL, atol=1.0)
+        rel_close(host(adj), d[sname + "_adj"], rtol=RTOL, atol=1.0)
+
+
+def test_chain_adjoint_viterbi_argmax(fb):
+    # per-step argmax of adj + trans under (max, add) is the Viterbi path when it is unique
+    g = torch.Generator().manual_seed(9)
+    B, T, S = 2, 15, 6
+    trans = torch.randn(B, T, S, S, generator=g)
+    init = torch.randn(B, S, generator=g)
+    Z, adj = fb.chain_adjoint("max", "add", trans.cuda(), init=init.cuda())
+    m = host(adj) + trans.numpy()
+    _, path = R.viterbi(init.numpy(), trans.numpy(), np.zeros((B, T, S), np.float32))
+    for b in range(B):
+        for t in range(T):
+            i, j = np.unravel_index(np.argmax(m[b, t]), (S, S))
+            assert (i, j) == (path[b, t], path[b, t + 1])
+
+
+# ------------------------------------------------------------------ size-independent properties at BASELINE sizes
+def test_c2_full_size_uniform_transition_property(fb):
+    """C2 (T=65536, S=1024, B=16): with a uniform transition matrix the log-likelihood factorises:
+    logZ = lse(init) + sum_t (lse_j obs[t, j] - log S).  Checked in float64 on the device."""
+    B, T, S = 16, 65536, 1024
+    g = torch.Generator(device="cuda").manual_seed(0)
+    obs = torch.randn(B, T, S, device="cuda", generator=g)
+    init = torch.randn(B, S, device="cuda", generator=g).log_softmax(-1)
+    A = torch.full((S, S), -float(np.log(S)), device="cuda")
+    got = fb.hmm_forward(init, A, obs)
+    want = torch.logsumexp(init.double(), -1) + (torch.logsumexp(obs.double(), -1) - np.log(S)).sum(-1)
+    rel_close(host(got), host(want), rtol=RTOL)
+
+
+def test_c2_full_size_shift_and_split_properties(fb):
+    """C2 size, random A: (i) adding a constant per step to obs adds its sum to logZ; (ii) the chain
+    splits: logZ(T) = lse_j(alpha_{T/2}[j] + rest) is checked through alpha hand-over at T/2."""
+    B, T, S = 16, 65536, 1024
+    g = torch.Generator(device="cuda").manual_seed(1)
+    obs = torch.randn(B, T, S, device="cuda", generator=g)
+    init = torch.randn(B, S, device="cuda", generator=g).log_softmax(-1)
+    A = torch.randn(S, S, device="cuda", generator=g).log_softmax(-1)
+    z = fb.hmm_forward(init, A, obs)
+    shift = torch.randn(B, T, 1, device="cuda", generator=g)
+    z_shift = fb.hmm_forward(init, A, obs + shift)
+    rel_close(host(z_shift), host(z.double() + shift.double().sum((1, 2))), rtol=RTOL)
+    half = T // 2
+    z1, alpha = fb.hmm_forward(init, A, obs[:, :half].contiguous(), return_alpha=True)
+    z2 = fb.hmm_forward(alpha[:, -1].contiguous(), A, obs[:, half:].contiguous())
+    rel_close(host(z2), host(z), rtol=RTOL)

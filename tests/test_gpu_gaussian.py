@@ -1,0 +1,121 @@
+"""GPU parity tests for the Gaussian-factor chain path against golden fixtures from the unmodified
+reference and the float64 oracle.
+
+Tolerance (north star): 1e-5 relative on Gaussian natural parameters, measured per tensor against its
+largest entry (the reference's own comparator with atol = max|expected|): entries that are exactly or
+nearly zero by structure (e.g. the prev-curr coupling after many contracting steps) carry no relative
+information."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cases, load_golden
+from oracle import gaussian_ref as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fg():
+    import funsor_b200.gaussian as fg
+
+    assert torch.cuda.is_available()
+    return fg
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def close_norm(actual, expected, rtol):
+    scale = max(np.abs(expected).max(), 1.0)
+    err = np.abs(actual - expected).max()
+    assert err <= rtol * scale, "max err {:.3e} vs {:.3e} (scale {:.3e})".format(err, rtol * scale, scale)
+
+
+def test_sqrt_to_info(fg):
+    rng = np.random.default_rng(0)
+    for batch, n, r in [((3, 5), 4, 4), ((7,), 6, 9), ((2,), 64, 48), ((1,), 64, 192), ((4,), 2, 1)]:
+        w = rng.standard_normal(batch + (r,))
+        P = rng.standard_normal(batch + (n, r))
+        s = rng.standard_normal(batch)
+        got = fg.sqrt_to_info(dev(w), dev(P), dev(s))
+        want = G.sqrt_to_info(w, P, s)
+        for a, b in zip(got, want):
+            close_norm(host(a), b, 2e-6 * max(r, 8))
+
+
+def test_pair_combine_vs_oracle(fg):
+    rng = np.random.default_rng(1)
+    for D in (1, 2, 3, 8, 17, 32):
+        N, n = 6, 2 * D
+
+        def rand_elem():
+            P = rng.standard_normal((N, n, n + 3)) / np.sqrt(n)
+            Lam = P @ np.swapaxes(P, -1, -2) + 0.5 * np.eye(n)
+            return Lam, rng.standard_normal((N, n)), rng.standard_normal(N)
+
+        x, y = rand_elem(), rand_elem()
+        Lo, eo, co, flag = fg.gaussian_pair_combine(tuple(dev(t) for t in x), tuple(dev(t) for t in y))
+        want = G.info_pair_combine(x, y, D)
+        assert int(flag.item()) == 0
+        for a, b in zip((Lo, eo, co), want):
+            close_norm(host(a), b, 1e-5)
+
+
+def test_chain_golden(fg):
+    for case, d in golden_cases(load_golden("gaussian_chain")).items():
+        D = int(case.split("_D")[1])
+        Lam, eta, c = fg.sqrt_to_info(dev(d["w"]), dev(d["P"]))
+        got = fg.gaussian_sequential_sum_product(Lam, eta, c)
+        for a, key in zip(got, ("Lam", "eta", "c")):
+            close_norm(host(a), d[key], 1e-5 * max(1, d["w"].shape[1] // 4))
+
+
+def test_kalman_golden(fg):
+    for case, d in golden_cases(load_golden("kalman")).items():
+        args = [dev(d[k]) for k in ("F", "q_loc", "q_tril", "H", "r_loc", "r_tril", "y")]
+        chain = fg.kalman_chain(*args)
+        for a, key in zip(chain, ("chain_Lam", "chain_eta", "chain_c")):
+            close_norm(host(a), d[key], 1e-5)
+        lp = fg.gaussian_hmm_log_prob(dev(d["m0"]), dev(d["p0_tril"]), chain)
+        close_norm(host(lp), d["logprob"], 1e-5)
+
+
+@pytest.mark.parametrize("B,T,D,O", [(4, 257, 8, 4), (2, 1000, 32, 16), (64, 100, 32, 16), (3, 33, 5, 3)])
+def test_kalman_random_vs_oracle(fg, B, T, D, O):
+    rng = np.random.default_rng(2)
+
+    def spd_tril(n):
+        a = rng.standard_normal((B, n, n))
+        return np.linalg.cholesky(a @ np.swapaxes(a, -1, -2) / n + 0.5 * np.eye(n))
+
+    F = 0.9 * np.linalg.qr(rng.standard_normal((B, D, D)))[0]
+    H = rng.standard_normal((B, D, O)) / np.sqrt(D)
+    q_loc, r_loc = 0.1 * rng.standard_normal((B, D)), 0.1 * rng.standard_normal((B, O))
+    q_tril, r_tril = spd_tril(D), spd_tril(O)
+    m0, p0 = rng.standard_normal((B, D)), spd_tril(D)
+    y = rng.standard_normal((B, T, O))
+    args = (F, q_loc, q_tril, H, r_loc, r_tril, y)
+    chain = fg.kalman_chain(*[dev(a) for a in args])
+    want = G.chain_info(*G.kalman_elements_info(*args), D)
+    for a, b in zip(chain, want):
+        close_norm(host(a), b, 1e-5)
+    lp = fg.gaussian_hmm_log_prob(dev(m0), dev(p0), chain)
+    wlp = G.hmm_logprob_from_chain(G.mvn_info(m0, p0), want, D)
+    close_norm(host(lp), wlp, 1e-5)
+    if T <= 300:
+        close_norm(host(lp), G.kalman_filter_logprob(m0, p0, *args), 1e-5)
+
+
+def test_too_little_information_raises(fg):
+    D = 2
+    Lam = torch.zeros(1, 2, 4, 4, device="cuda")  # no information on the shared block
+    eta = torch.zeros(1, 2, 4, device="cuda")
+    c = torch.zeros(1, 2, device="cuda")
+    with pytest.raises(ValueError, match="Too little information"):
+        fg.gaussian_sequential_sum_product(Lam, eta, c)
