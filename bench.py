@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on the configuration BASELINE.json's metric is quoted on.
+
+Workload (config.workload = "c2"): batched discrete-HMM forward log-likelihood in the log semiring,
+T=65536, S=1024, batch=16 per GPU, fp32, factored inputs A[S,S] + obs[B,T,S] (the
+dense trans[B,T,S,S] of the reference API would be 4.4 TB).  One step = one pass of the hot path over
+the whole batch.  Unit of work = one (t, batch, prev, curr) semiring multiply-add, so
+value = N * T*S^2*B / seconds.  Multi-GPU: batch sharding, no data-path collective ("weak" scaling:
+16 chains per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hmm_forward_logsemiring_TxS2xB_per_s"
+UNIT = "semiring_madd/s"
+WORKLOADS = {
+    "c2": dict(T=65536, S=1024, B=16),
+    "c2_small": dict(T=2048, S=1024, B=16),  # debugging only
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_inputs(T, S, B, device, seed):
+    import torch
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    A = torch.randn(S, S, device=device, generator=g).log_softmax(-1)  # normalised like hmm.py:92
+    init = torch.randn(B, S, device=device, generator=g).log_softmax(-1)
+    obs = torch.randn(B, T, S, device=device, generator=g)
+    return init, A, obs
+
+
+def cpu_reference_sample(S, B, T_sample, repeats=1):
+    """Time the reference's own data flow (oracle/cpu_port.py) on all host threads on a bounded sample."""
+    import torch
+
+    from oracle import cpu_port
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(S, S, generator=g).log_softmax(-1)
+    init = torch.randn(B, S, generator=g).log_softmax(-1)
+    obs = torch.randn(B, T_sample, S, generator=g)
+    cpu_port.hmm_log_prob(init, A, obs[:, :2])  # warm-up (thread pool, allocator)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cpu_port.hmm_log_prob(init, A, obs)
+        best = min(best, time.perf_counter() - t0)
+    return dict(value=T_sample * S * S * B / best, seconds=best, cores=cores,
+                sample="T={} of the workload's S={}, B={} (dense trans+obs, pairwise log-matmul tree, torch CPU fp32, {} threads)".format(T_sample, S, B, cores))
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    T_sample = args.ref_T
+    samples = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_sample(wl["S"], wl["B"], T_sample)
+        if i >= args.warmup:
+            samples.append(r)
+    sec = sum(r["seconds"] for r in samples) / len(samples)
+    value = T_sample * wl["S"] ** 2 * wl["B"] / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "T": wl["T"], "S": wl["S"], "B_per_gpu": wl["B"], "reference_sample_T": T_sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": samples[0]["cores"], "kind": "port", "sample": samples[0]["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-T", type=int, default=16, help="time steps in the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.warmup < 3 and args.impl == "ours" and args.workload == "c2":
+        pass  # allowed for debugging, but the driver always passes W >= 3
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import funsor_b200 as fb
+    from funsor_b200 import _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the product path has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    T, S, B = wl["T"], wl["S"], wl["B"]
+    init, A, obs = make_inputs(T, S, B, device, seed=rank)
+    units_per_step_rank = T * S * S * B
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident timing (value) ----------------
+    for _ in range(args.warmup):
+        z = fb.hmm_forward(init, A, obs)
+    barrier()
+    fb.launch_count(reset=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev[0].record()
+        for i in range(args.steps):
+            z = fb.hmm_forward(init, A, obs)
+            ev[i + 1].record()
+        barrier()
+    launches = fb.launch_count()
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    kernel_ms = sum(step_ms) / len(step_ms)  # the step is one memset + the cooperative forward kernel
+    value = world * units_per_step_rank * args.steps / (total_ms * 1e-3)
+    assert bool(torch.isfinite(z).all()), "non-finite log-likelihood"
+
+    # ---------------- end-to-end through the C ABI with host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        lib = _lib.load()
+        h_init, h_A = init.cpu().pin_memory(), A.cpu().pin_memory()
+        h_obs = torch.empty(obs.shape, dtype=torch.float32, pin_memory=True)
+        h_obs.copy_(obs)
+        h_out = torch.empty(B, dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            _lib.check(lib.fb2_hmm_forward_f32_host(0, h_init.data_ptr(), S, h_A.data_ptr(), 0, 0, h_obs.data_ptr(), B, T, S, h_out.data_ptr()))
+
+        n_e2e = max(2, min(args.steps, 3))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        assert torch.allclose(h_out.to(device), z, rtol=1e-5, atol=1e-2), "e2e result differs from the device-resident result"
+        e2e = {"value": world * units_per_step_rank * n_e2e / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": int(h_obs.numel() * 4 + h_A.numel() * 4 + h_init.numel() * 4), "d2h_bytes_per_step": int(B * 4),
+               "ms_per_step": e2e_s / n_e2e * 1e3, "steps": n_e2e}
+        lib.fb2_host_arena_release()
+        del h_obs
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    flops = 2.0 * units_per_step_rank
+    achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
+    hbm_bytes = (obs.numel() + A.numel() + init.numel()) * 4
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops"],
+                "traffic": None, "kernel": "hmm_forward_generic<LOG,16>", "kernel_ms": kernel_ms, "peak_source": peaks["src"],
+                "algorithmic_flops_per_launch": flops,
+                "hbm": {"achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                        "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": hbm_bytes}}
+    cpu = None
+    if not args.no_cpu:
+        r = cpu_reference_sample(S, B, args.ref_T)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    extra = {}
+    if not args.no_extra:
+        try:
+            extra = extra_measurements(device)
+        except Exception as e:  # extras never invalidate the headline line
+            extra = {"error": repr(e)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "T": T, "S": S, "B_per_gpu": B, "layout": "factored A[S,S] + obs[B,T,S]",
+                   "parallelism": "batch-sharded x{}".format(world), "l2": "inputs (4.3 GB obs) larger than L2, no flush needed"},
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_measurements(device):
+    """Secondary numbers of the same metric family (not the headline): Kalman steps/s and dense chain product."""
+    import torch
+
+    import funsor_b200 as fb
+    import funsor_b200.gaussian as fg
+
+    out = {}
+    g = torch.Generator(device=device).manual_seed(0)
+
+    def timeit(fn, n=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e-3
+
+    # Kalman (C4 shape at reduced T): D=32, O=16, B=64
+    Bk, Tk, D, O = 64, 4096, 32, 16
+    F = 0.9 * torch.linalg.qr(torch.randn(Bk, D, D, device=device, generator=g))[0]
+    H = torch.randn(Bk, D, O, device=device, generator=g) / D ** 0.5
+    eye = lambda n: torch.eye(n, device=device).expand(Bk, n, n).contiguous()  # noqa: E731
+    y = torch.randn(Bk, Tk, O, device=device, generator=g)
+    w, P, s = fg.kalman_elements_sqrt(F, torch.zeros(Bk, D, device=device), eye(D), H, torch.zeros(Bk, O, device=device), eye(O), y)
+    Lam, eta, c = fg.sqrt_to_info(w, P, s)
+    sec = timeit(lambda: fg.gaussian_sequential_sum_product(Lam, eta, c, validate=False))
+    out["kalman_scan"] = {"steps_per_s": Bk * Tk / sec, "D": D, "O": O, "B": Bk, "T": Tk, "ms": sec * 1e3,
+                          "note": "Gaussian scan over dense info-form elements (C4 shape at reduced T)"}
+    del w, P, s, Lam, eta, c
+    # dense chain product (literal sequential_sum_product semantics), S=1024
+    Bd, Td, Sd = 4, 64, 1024
+    trans = torch.randn(Bd, Td, Sd, Sd, device=device, generator=g)
+    sec = timeit(lambda: fb.sequential_sum_product("logaddexp", "add", trans), n=2)
+    out["dense_chain_log"] = {"pair_products_per_s": Bd * (Td - 1) / sec, "tflops_fp32": 2.0 * Bd * (Td - 1) * Sd ** 3 / sec / 1e12,
+                              "B": Bd, "T": Td, "S": Sd, "ms": sec * 1e3}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,9 @@ struct HmmArgs {
     const float* final_; // nullable [B,S] folded into out (adjoint use): out = (+)_j alpha[j] (x) final[j]
     int Gg, W, LW;
     int groups_total, groups_conc;
+    double* ell_all;     // nullable [B,T]: when given, alpha_all holds NORMALISED messages and ell_all their offsets
+    double* out_d;       // nullable [B]: out in double (LOG)
+    float* alpha_last;   // nullable [B,S]: alpha_{T-1} (forward) with its offset folded in
     int cpo;             // chains per obs/A batch entry (1 normally; S for chunk summaries: chain = b*S + row)
     int init_identity;   // 1: alpha_{-1} of chain c is the semiring identity row (c % cpo)
 };
@@ -66,6 +69,9 @@ __global__ void __launch_bounds__(256) hmm_forward_generic(HmmArgs p) {
     float* s_red_a = s_alpha + (size_t)R * S;
     float* s_red_b = s_red_a + 256 * R;
     float* s_obs = s_red_b + 256 * R;
+    // LOG only: messages are kept relative to a running offset ell (double), so fp32 resolution does not
+    // degrade as |alpha| grows with t:  alpha_t = vec_t + ell_t,  ell_t = sum_{tau<=t} max_i vec_{tau-1}[i]
+    __shared__ double s_ell[16];
     const int tid = threadIdx.x;
     const int gconc = blockIdx.x / p.Gg, slice = blockIdx.x % p.Gg;
     const int j0 = slice * W;
@@ -77,6 +83,7 @@ __global__ void __launch_bounds__(256) hmm_forward_generic(HmmArgs p) {
     for (int g = gconc; g < p.groups_total; g += p.groups_conc) {
         const int64_t b0 = (int64_t)g * R;
         const int nb = (int)min((int64_t)R, p.B - b0);
+        if (tid < 16) s_ell[tid] = 0.0;
         // ---- alpha_{-1} = init  -> vec[0]
         for (int idx = tid; idx < nb * jw; idx += 256) {
             int r = idx / jw, j = j0 + idx % jw;
@@ -107,6 +114,17 @@ __global__ void __launch_bounds__(256) hmm_forward_generic(HmmArgs p) {
                     s_obs[(((t + 1) & 1) * R + r) * W + jj] = p.obs[((b0 + r) / p.cpo * p.T + t + 1) * S + j0 + jj];
                 }
             __syncthreads();
+            if (SEMI == FB2_SEMIRING_LOG) {
+                const int warp = tid / 32, lane = tid % 32;
+                for (int r = warp; r < R; r += 8) {
+                    float m = -FLT_MAX;
+                    for (int i = lane; i < S; i += 32) m = fmaxf(m, s_alpha[r * S + i]);
+                    m = warp_max(m);
+                    for (int i = lane; i < S; i += 32) s_alpha[r * S + i] -= m;
+                    if (lane == 0 && r < nb) s_ell[r] += (double)m;
+                }
+                __syncthreads();
+            }
             const float* s_ob = s_obs + (size_t)((t & 1) * R) * W;
 
             for (int c0 = 0; c0 < jw; c0 += LW) {
@@ -204,7 +222,11 @@ __global__ void __launch_bounds__(256) hmm_forward_generic(HmmArgs p) {
                             if (ARG) p.backptr[(b * p.T + t) * S + j0 + col] = arg;
                         }
                         vout[b * S + j0 + col] = res;
-                        if (p.alpha_all) p.alpha_all[(b * p.T + t) * S + j0 + col] = res;
+                        if (p.alpha_all) {
+                            float off = (SEMI == FB2_SEMIRING_LOG && !p.ell_all) ? (float)s_ell[r] : 0.f;
+                            p.alpha_all[(b * p.T + t) * S + j0 + col] = res + off;
+                        }
+                        if (SEMI == FB2_SEMIRING_LOG && p.ell_all && j0 + col == 0) p.ell_all[b * p.T + t] = s_ell[r];
                     }
                 }
                 __syncthreads();
@@ -234,7 +256,11 @@ __global__ void __launch_bounds__(256) hmm_forward_generic(HmmArgs p) {
                     for (int j = lane; j < S; j += 32)
                         s += __expf(__ldcg(vfin + b * S + j) + (p.final_ ? p.final_[b * S + j] : 0.f) - m);
                     s = warp_sum(s);
-                    if (lane == 0) p.out[b] = m + logf(s);
+                    if (lane == 0) {
+                        double z = s_ell[r] + (double)(m + logf(s));
+                        p.out[b] = (float)z;
+                        if (p.out_d) p.out_d[b] = z;
+                    }
                 } else {
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
@@ -252,7 +278,15 @@ __global__ void __launch_bounds__(256) hmm_forward_generic(HmmArgs p) {
                 }
             }
         }
-        // the next wave re-uses vec[] of other chains only, but s_obs/s_alpha are re-used: sync
+        if (p.alpha_last) {
+            const float* vfin = p.vec + (size_t)(p.T & 1) * p.B * S;
+            for (int idx = tid; idx < nb * jw; idx += 256) {
+                int r = idx / jw, j = j0 + idx % jw;
+                float off = (SEMI == FB2_SEMIRING_LOG) ? (float)s_ell[r] : 0.f;
+                p.alpha_last[(b0 + r) * S + j] = __ldcg(vfin + (b0 + r) * S + j) + off;
+            }
+        }
+        // the next wave re-uses vec[] of other chains only, but s_obs/s_alpha/s_ell are re-used: sync
         group_barrier(ctr, (++epoch) * p.Gg, p.Gg);
     }
 }
@@ -267,6 +301,7 @@ __global__ void __launch_bounds__(256) hmm_backward_generic(HmmArgs p) {
     extern __shared__ __align__(16) float smem[];
     const int S = p.S, W = p.W;
     float* s_w = smem;
+    __shared__ double s_ell[16];  // LOG: beta_t = vec_t + ell_t (same scheme as the forward kernel)
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
     const int gconc = blockIdx.x / p.Gg, slice = blockIdx.x % p.Gg;
     const int i0 = slice * W;
@@ -277,12 +312,14 @@ __global__ void __launch_bounds__(256) hmm_backward_generic(HmmArgs p) {
     for (int g = gconc; g < p.groups_total; g += p.groups_conc) {
         const int64_t b0 = (int64_t)g * R;
         const int nb = (int)min((int64_t)R, p.B - b0);
-        // beta_{T-1} -> vec[(T-1)&1]... buffer index convention: vec[t&1] holds beta_t
+        // buffer index convention: vec[t&1] holds beta_t
+        if (tid < 16) s_ell[tid] = 0.0;
         for (int idx = tid; idx < nb * iw; idx += 256) {
             int r = idx / iw, i = i0 + idx % iw;
             float v = p.final_ ? p.final_[(b0 + r) * S + i] : 0.f;
             p.vec[(size_t)((p.T - 1) & 1) * p.B * S + (b0 + r) * S + i] = v;
             if (p.alpha_all) p.alpha_all[((b0 + r) * p.T + p.T - 1) * S + i] = v;
+            if (p.ell_all && i == 0) p.ell_all[(b0 + r) * p.T + p.T - 1] = 0.0;
         }
         group_barrier(ctr, (++epoch) * p.Gg, p.Gg);
         for (int64_t t = p.T - 1; t >= 1; --t) {
@@ -295,6 +332,16 @@ __global__ void __launch_bounds__(256) hmm_backward_generic(HmmArgs p) {
                 s_w[idx] = v;
             }
             __syncthreads();
+            if (SEMI == FB2_SEMIRING_LOG) {
+                for (int r = warp; r < R; r += 8) {
+                    float m = -FLT_MAX;
+                    for (int j = lane; j < S; j += 32) m = fmaxf(m, s_w[r * S + j]);
+                    m = warp_max(m);
+                    for (int j = lane; j < S; j += 32) s_w[r * S + j] -= m;
+                    if (lane == 0 && r < nb) s_ell[r] += (double)m;
+                }
+                __syncthreads();
+            }
             for (int ii = warp; ii < iw; ii += 8) {
                 const int i = i0 + ii;
 #pragma unroll
@@ -313,7 +360,11 @@ __global__ void __launch_bounds__(256) hmm_backward_generic(HmmArgs p) {
                     }
                     if (lane == 0) {
                         vout[(b0 + r) * S + i] = res;
-                        if (p.alpha_all) p.alpha_all[((b0 + r) * p.T + t - 1) * S + i] = res;
+                        if (p.alpha_all) {
+                            float off = (SEMI == FB2_SEMIRING_LOG && !p.ell_all) ? (float)s_ell[r] : 0.f;
+                            p.alpha_all[((b0 + r) * p.T + t - 1) * S + i] = res + off;
+                        }
+                        if (SEMI == FB2_SEMIRING_LOG && p.ell_all && i == 0) p.ell_all[(b0 + r) * p.T + t - 1] = s_ell[r];
                     }
                 }
             }
@@ -336,37 +387,40 @@ __global__ void viterbi_backtrace(const int32_t* backptr, const int32_t* last, i
     }
 }
 
-// gamma[b,t,j] = alpha[b,t,j] + beta[b,t,j] - logZ[b]   (in place over alpha)
-__global__ void marginals_combine(float* alpha, const float* beta, const float* logZ, int64_t B, int64_t T, int S) {
+// gamma[b,t,j] = alpha_hat[b,t,j] + beta_hat[b,t,j] + (ell_a[b,t] + ell_b[b,t] - logZ[b])   (in place over alpha)
+__global__ void marginals_combine(float* alpha, const float* beta, const double* ell_a, const double* ell_b,
+                                  const double* logZ, int64_t B, int64_t T, int S) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t per = T * (int64_t)S;
-    if (idx >= B * per) return;
-    alpha[idx] = alpha[idx] + beta[idx] - logZ[idx / per];
+    if (idx >= B * T * (int64_t)S) return;
+    int64_t bt = idx / S;
+    alpha[idx] = alpha[idx] + beta[idx] + (float)(ell_a[bt] + ell_b[bt] - logZ[bt / T]);
 }
 
 // xi_sum[b,i,j] = sum_t exp(alpha_{t-1}[i] + A_t[i,j] + obs[t,j] + beta_t[j] - logZ)
 // one thread per (b,i,j); alpha_{-1} = init.  Simple O(T S^2) accumulation (T-serial per thread).
 __global__ void xi_sum_kernel(const float* init, int64_t init_sb, const float* A, int64_t a_sb, int64_t a_st,
-                              const float* obs, const float* alpha, const float* beta, const float* logZ, int64_t B,
-                              int64_t T, int S, float* xi) {
+                              const float* obs, const float* alpha, const float* beta, const double* ell_a,
+                              const double* ell_b, const double* logZ, int64_t B, int64_t T, int S, float* xi) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t per = (int64_t)S * S;
     if (idx >= B * per) return;
     int64_t b = idx / per;
     int i = (int)((idx % per) / S), j = (int)(idx % S);
-    float z = logZ[b];
+    double z = logZ[b];
     float acc = 0.f;
     for (int64_t t = 0; t < T; ++t) {
         float ap = t == 0 ? (init ? init[b * init_sb + i] : 0.f) : alpha[(b * T + t - 1) * S + i];
-        float v = ap + A[b * a_sb + t * a_st + (int64_t)i * S + j] + obs[(b * T + t) * S + j] + beta[(b * T + t) * S + j] - z;
+        float off = (float)((t == 0 ? 0.0 : ell_a[b * T + t - 1]) + ell_b[b * T + t] - z);
+        float v = ap + A[b * a_sb + t * a_st + (int64_t)i * S + j] + obs[(b * T + t) * S + j] + beta[(b * T + t) * S + j] + off;
         acc += __expf(v);
     }
     xi[idx] = acc;
 }
 
-// adj[b,t,i,j] = alphaprev[b,t,i] + beta[b,t,j]  where alphaprev[b,0] = init (or 0) and alphaprev[b,t] = alpha[b,t-1]
-__global__ void adjoint_outer(const float* init, const float* alpha, const float* beta, int64_t B, int64_t T, int S,
-                              float* adj) {
+// adj[b,t,i,j] = alphaprev[b,t,i] + beta[b,t,j]  where alphaprev[b,0] = init (or 0) and alphaprev[b,t] = alpha[b,t-1];
+// ell_a / ell_b (nullable) are the offsets of normalised messages (LOG).
+__global__ void adjoint_outer(const float* init, const float* alpha, const float* beta, const double* ell_a,
+                              const double* ell_b, int64_t B, int64_t T, int S, float* adj) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t per = (int64_t)S * S;
     if (idx >= B * T * per) return;
@@ -374,7 +428,9 @@ __global__ void adjoint_outer(const float* init, const float* alpha, const float
     int64_t b = bt / T, t = bt % T;
     int i = (int)((idx % per) / S), j = (int)(idx % S);
     float ap = t == 0 ? (init ? init[b * S + i] : 0.f) : alpha[(b * T + t - 1) * S + i];
-    adj[idx] = ap + beta[(b * T + t) * S + j];
+    float off = 0.f;
+    if (ell_a) off = (float)((t == 0 ? 0.0 : ell_a[bt - 1]) + ell_b[bt]);
+    adj[idx] = (ap + beta[(b * T + t) * S + j]) + off;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -490,7 +546,8 @@ static size_t ctr_bytes() { return align_up(1024 * sizeof(unsigned)); }
 int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb, int64_t a_st,
                        const float* obs, const float* final_, int64_t B, int64_t T, int S, float* out,
                        float* alpha_all, int32_t* backptr, int32_t* last, void* workspace, size_t workspace_bytes,
-                       cudaStream_t stream, int cpo = 1, float* alpha_last = nullptr) {
+                       cudaStream_t stream, int cpo = 1, float* alpha_last = nullptr, double* ell_all = nullptr,
+                       double* out_d = nullptr) {
     PassPlan pl;
     int st = make_plan(B, S, false, &pl);
     if (st != FB2_OK) return st;
@@ -508,16 +565,13 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
     a.out = out; a.last = last; a.final_ = final_;
     a.Gg = pl.Gg; a.W = pl.W; a.LW = pl.LW; a.groups_total = pl.groups_total; a.groups_conc = pl.groups_conc;
     a.cpo = cpo; a.init_identity = cpo > 1 ? 1 : 0;
-    st = run_forward(semiring, backptr != nullptr, pl, a, stream);
-    if (st != FB2_OK) return st;
-    if (alpha_last)
-        FB2_CUDA(cudaMemcpyAsync(alpha_last, vec + (size_t)(T & 1) * B * S, (size_t)B * S * 4, cudaMemcpyDeviceToDevice, stream));
-    return FB2_OK;
+    a.alpha_last = alpha_last; a.ell_all = ell_all; a.out_d = out_d;
+    return run_forward(semiring, backptr != nullptr, pl, a, stream);
 }
 
 int hmm_backward_device(int semiring, const float* A, int64_t a_sb, int64_t a_st, const float* obs, const float* final_,
                         int64_t B, int64_t T, int S, float* beta_all, void* workspace, size_t workspace_bytes,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, double* ell_all = nullptr) {
     PassPlan pl;
     int st = make_plan(B, S, true, &pl);
     if (st != FB2_OK) return st;
@@ -533,7 +587,7 @@ int hmm_backward_device(int semiring, const float* A, int64_t a_sb, int64_t a_st
     a.A = A; a.a_sb = a_sb; a.a_st = a_st; a.obs = obs; a.final_ = final_;
     a.B = B; a.T = T; a.S = S; a.vec = vec; a.counters = ctr; a.alpha_all = beta_all;
     a.Gg = pl.Gg; a.W = pl.W; a.LW = pl.LW; a.groups_total = pl.groups_total; a.groups_conc = pl.groups_conc;
-    a.cpo = 1;
+    a.cpo = 1; a.ell_all = ell_all;
     return run_backward(semiring, pl, a, stream);
 }
 
@@ -544,7 +598,7 @@ using namespace fb2;
 extern "C" size_t fb2_hmm_workspace_bytes(int op, int64_t B, int64_t T, int32_t S) {
     size_t base = vec_bytes(B, S) + ctr_bytes() + 512;
     if (op == 1) base += align_up((size_t)B * T * S * sizeof(int32_t)) + align_up((size_t)B * sizeof(int32_t));
-    if (op == 2) base += align_up((size_t)B * T * S * sizeof(float)) + vec_bytes(B, S) + ctr_bytes();
+    if (op == 2) base += align_up((size_t)B * T * S * sizeof(float)) + 2 * align_up((size_t)B * T * 8) + align_up((size_t)B * 8);
     return base;
 }
 
@@ -598,32 +652,35 @@ extern "C" int fb2_hmm_marginals_f32(const float* init, int64_t init_sb, const f
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     Arena arena(workspace, workspace_bytes);
     float* beta = arena.take<float>((size_t)B * T * S);
+    double* ell_a = arena.take<double>((size_t)B * T);
+    double* ell_b = arena.take<double>((size_t)B * T);
+    double* z_d = arena.take<double>((size_t)B);
     if (!arena.ok()) {
         set_error("marginals: workspace too small (%zu bytes)", workspace_bytes);
         return FB2_ERR_WORKSPACE;
     }
     char* rest = static_cast<char*>(workspace) + arena.used;
     size_t rest_bytes = workspace_bytes - arena.used;
-    // alpha goes straight into gamma, then gamma = alpha + beta - logZ in place
+    // normalised alpha goes straight into gamma, then gamma = alpha + beta + offsets - logZ in place
     st = hmm_forward_device(FB2_SEMIRING_LOG, init, init_sb, A, a_sb, a_st, obs, nullptr, B, T, S, logZ, gamma, nullptr,
-                            nullptr, rest, rest_bytes, stream);
+                            nullptr, rest, rest_bytes, stream, 1, nullptr, ell_a, z_d);
     if (st != FB2_OK) return st;
-    st = hmm_backward_device(FB2_SEMIRING_LOG, A, a_sb, a_st, obs, nullptr, B, T, S, beta, rest, rest_bytes, stream);
+    st = hmm_backward_device(FB2_SEMIRING_LOG, A, a_sb, a_st, obs, nullptr, B, T, S, beta, rest, rest_bytes, stream, ell_b);
     if (st != FB2_OK) return st;
     if (xi_sum) {
         int64_t n = B * (int64_t)S * S;
-        xi_sum_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(init, init_sb, A, a_sb, a_st, obs, gamma, beta, logZ,
-                                                                     B, T, S, xi_sum);
+        xi_sum_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(init, init_sb, A, a_sb, a_st, obs, gamma, beta, ell_a,
+                                                                     ell_b, z_d, B, T, S, xi_sum);
         FB2_LAUNCH_CHECK();
     }
     int64_t n = B * T * (int64_t)S;
-    marginals_combine<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(gamma, beta, logZ, B, T, S);
+    marginals_combine<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(gamma, beta, ell_a, ell_b, z_d, B, T, S);
     FB2_LAUNCH_CHECK();
     return FB2_OK;
 }
 
 extern "C" size_t fb2_chain_adjoint_workspace_bytes(int64_t B, int64_t T, int32_t S) {
-    return 2 * align_up((size_t)B * T * S * 4) + vec_bytes(B, S) + ctr_bytes() + 512;
+    return 2 * align_up((size_t)B * T * S * 4) + 2 * align_up((size_t)B * T * 8) + vec_bytes(B, S) + ctr_bytes() + 512;
 }
 
 extern "C" int fb2_chain_adjoint_f32(int semiring, const float* trans, const int64_t ts[4], const float* init,
@@ -640,6 +697,9 @@ extern "C" int fb2_chain_adjoint_f32(int semiring, const float* trans, const int
     Arena arena(workspace, workspace_bytes);
     float* alpha = arena.take<float>((size_t)B * T * S);
     float* beta = arena.take<float>((size_t)B * T * S);
+    double* ell_a = arena.take<double>((size_t)B * T);
+    double* ell_b = arena.take<double>((size_t)B * T);
+    if (semiring != FB2_SEMIRING_LOG) ell_a = ell_b = nullptr;
     if (!arena.ok()) {
         set_error("chain_adjoint: workspace too small (%zu bytes)", workspace_bytes);
         return FB2_ERR_WORKSPACE;
@@ -647,13 +707,13 @@ extern "C" int fb2_chain_adjoint_f32(int semiring, const float* trans, const int
     char* rest = static_cast<char*>(workspace) + arena.used;
     size_t rest_bytes = workspace_bytes - arena.used;
     st = hmm_forward_device(semiring, init, S, trans, ts[0], ts[1], nullptr, final_, B, T, S, Z, alpha, nullptr, nullptr,
-                            rest, rest_bytes, stream);
+                            rest, rest_bytes, stream, 1, nullptr, ell_a, nullptr);
     if (st != FB2_OK) return st;
-    st = hmm_backward_device(semiring, trans, ts[0], ts[1], nullptr, final_, B, T, S, beta, rest, rest_bytes, stream);
+    st = hmm_backward_device(semiring, trans, ts[0], ts[1], nullptr, final_, B, T, S, beta, rest, rest_bytes, stream, ell_b);
     if (st != FB2_OK) return st;
     int64_t n = B * T * (int64_t)S * S;
     FB2_REQUIRE(ceil_div(n, 256) < (1ll << 31), "chain_adjoint: output too large for one launch");
-    adjoint_outer<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(init, alpha, beta, B, T, S, adj);
+    adjoint_outer<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(init, alpha, beta, ell_a, ell_b, B, T, S, adj);
     FB2_LAUNCH_CHECK();
     return FB2_OK;
 }

@@ -133,3 +133,14 @@ def test_kalman_elements_chain_logprob():
         # independent absolute check: textbook Kalman filter
         kf = G.kalman_filter_logprob(d["m0"], d["p0_tril"], *args)
         rel_close(kf, d["logprob"], rtol=1e-9, atol=1.0)
+
+
+def test_cpu_port_matches_oracle():
+    import torch
+
+    from oracle import cpu_port
+
+    d = golden_cases(load_golden("hmm_logprob"))["h0"]
+    for sname, s in SEMI.items():
+        got = cpu_port.hmm_log_prob(torch.tensor(d["init"]), torch.tensor(d["A"]), torch.tensor(d["obs"]), sname)
+        rel_close(got.numpy(), d[sname + "_Z"], rtol=1e-11, atol=1.0)
