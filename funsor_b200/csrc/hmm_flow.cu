@@ -1,0 +1,701 @@
+// Dataflow forward pass for the log semiring with a time-homogeneous transition matrix.
+//
+// Reference semantics: DiscreteHMM.log_prob funsor/pyro/hmm.py:129-135, i.e.
+// sequential_sum_product(logaddexp, add, A + obs) (sum_product.py:652-701) followed by
+// init + reduce(curr), reduce(state), evaluated as the vector recurrence
+//     alpha_t[j] = logsumexp_i(alpha_{t-1}[i] + A[i,j]) + obs[t,j]
+// with the reference's own max-subtract / exp trick (einsum/numpy_log.py:24-47): the contraction
+// runs in the linear domain on the tensor pipe and only O(S) exp / O(1) log per step remain.
+//
+// The step-to-step dependency chain is T long, so the kernel is built around the latency of one
+// step, not around throughput:
+//   * P = exp(A - colmax(A)) never moves: every CTA keeps its [Ks x 64] block as split-TF32
+//     (hi + lo) mma.sync B-fragments in REGISTERS for the whole pass.
+//   * 2-D split.  A cluster of 8 CTAs owns 64 output columns; inside the cluster the contraction
+//     index is split 8 ways (Ks = Sp/8 rows per CTA).  A CTA therefore reads only its K-slice of the
+//     message (16 chains x Ks values) instead of the whole vector, which keeps the per-step L2
+//     traffic at Sp*16*8 B per cluster instead of per CTA.
+//   * The 8 partial sums of a column group are reduced over distributed shared memory
+//     (st.shared::cluster + a remote mbarrier arrive); CTA q of the cluster is the final owner of
+//     columns [8q, 8q+8) of the cluster's 64.
+//   * Messages travel between clusters through L2 as self-validating 8-byte packets
+//     {fp32 mantissa, step stamp | block exponent}: a consumer polls the data itself, so there is no
+//     grid barrier, no separate flag and no fence on the critical path.
+//   * Block floating point.  Every group of 8 columns carries its own integer exponent, so a
+//     producer normalises with purely local information; consumers align the exponents of their
+//     K-slice (exact power-of-two scaling).  The absolute exponent is tracked by the final owner in
+//     an int, so the log-likelihood keeps fp32 mantissa accuracy no matter how large |log Z| grows.
+//   * 3xTF32 (hi*hi + lo*hi + hi*lo) keeps the contraction at fp32-class accuracy.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace fb2 {
+
+constexpr int FLOW_CLUSTER = 8;
+constexpr int FLOW_THREADS = 256;
+constexpr int FLOW_CHAINS = 16;  // chains per group = M of the mma tile
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int FLOW_PROF_CTAS = 160;
+constexpr int FLOW_OBS_DEPTH = 8;     // observation prefetch distance in steps (HBM latency << 7 steps)
+constexpr long long FLOW_SPIN_LIMIT = 2000000000ll;  // cycles (~1 s) before a wait gives up and aborts the pass
+
+struct FlowArgs {
+    const float* init;  // [B,S] log domain, nullable (= 0)
+    int64_t init_sb;
+    const float* A;     // [S,S] log domain
+    const float* obs;   // [B,T,S], nullable (= 0)
+    const float* cA;    // [Sp] clamped column maxima of A (0 in the padding)
+    int64_t B, T;
+    int S;
+    unsigned long long* pkt;  // [nsets][2][16][Sp] packets
+    float* fin_u;             // [groups*16][Sp] final mantissas
+    int* fin_e;               // [groups*16][Sp/8] final absolute exponents (INT_MIN = zero group)
+    int* abort_flag;
+    long long* prof;  // nullable: [gridDim][8] accumulated cycles per phase (FB2_FLOW_PROF=1)
+    int nsets, groups_total;
+};
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t cvt_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// Remote shared-memory stores that signal the destination CTA's mbarrier by transaction bytes: data and
+// notification travel together, no release/acquire fence at cluster scope on the critical path.
+__device__ __forceinline__ void st_async_v2f(uint32_t addr, float a, float b, uint32_t mbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(addr), "f"(a),
+                 "f"(b), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_u32(uint32_t addr, uint32_t v, uint32_t mbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(addr), "r"(v), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arm(uint32_t addr, uint32_t tx_bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(tx_bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void ld_pkt2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_pkt(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ int sext15(int x) { return (int)((unsigned)x << 17) >> 17; }
+__device__ __forceinline__ float pow2i(int d) {  // 2^d for d <= 0, flushed to 0 below 2^-126
+    return d < -126 ? 0.f : __int_as_float((127 + d) << 23);
+}
+__device__ __forceinline__ float group8_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return v;
+}
+
+// Normalise the 8 values of one column group (one per lane of an aligned 8-lane group): returns the
+// mantissa of this lane and the new wrapped exponent / zero flag of the group.
+//   true value = s * 2^(x) * 2^(e_in)   ->   u * 2^(E)
+__device__ __forceinline__ float flow_normalise(float s, float x, int e_in15, int& E15, bool& zero) {
+    const float xm = group8_max(x);
+    float nf = 0.f, e2 = 0.f;
+    if (xm > -1e30f) {
+        nf = ceilf(xm);
+        e2 = exp2f(x - nf);
+        if (!(fabsf(nf) <= 8000.f)) e2 = __int_as_float(0x7fc00000);  // |obs| beyond the 15-bit block-exponent range
+    }
+    float u = s * e2;
+    float mu = group8_max(u);
+    zero = !(mu > 0.f);
+    if (!(mu <= FLT_MAX)) {  // inf or NaN input: poison the group, the log-likelihood becomes NaN
+        E15 = e_in15 & 0x7FFF;
+        zero = false;
+        return __int_as_float(0x7fc00000);
+    }
+    if (zero) {
+        E15 = e_in15 & 0x7FFF;
+        return 0.f;
+    }
+    int extra = 0;
+    if (mu < 1e-20f) {
+        u *= 0x1p64f;
+        mu *= 0x1p64f;
+        extra = -64;
+    }
+    const int q = ((__float_as_int(mu) >> 23) & 0xFF) - 127;
+    u *= __int_as_float((127 - q) << 23);
+    E15 = (e_in15 + (int)nf + q + extra) & 0x7FFF;
+    return u;
+}
+
+// ------------------------------------------------------------------------------------------ the kernel
+// K16 = k16-steps per CTA (Ks = 16*K16 rows of P per CTA, Sp = 8*Ks = 128*K16 padded states);
+// NT  = 8-column n-tiles per warp (a cluster owns 64*NT columns); grid = nsets * (2*K16/NT) clusters of 8.
+//
+// Contraction arithmetic: 3xTF32.  v = vh + vl and P = Ph + Pl with TF32 halves; vh*Ph + vl*Ph + vh*Pl on
+// mma.sync.m16n8k8 with fp32 accumulation gives fp32-class accuracy over the full fp32 exponent range
+// (a split-fp16 variant was measured and rejected: its 2^40 dynamic range loses the small entries of
+// sparse messages).  Pl is kept as packed fp16 of 2^24*Pl (exactly representable in TF32 after
+// conversion) to halve its register footprint; the 2^-24 is applied to the accumulator.
+constexpr float kScalePl = 16777216.f, kUnscalePl = 1.f / 16777216.f;
+
+template <int K16, int NT>
+__global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) {
+    constexpr int KS = K16 * 16;          // rows of P (= message entries) per CTA
+    constexpr int SP = K16 * 128;         // padded state count
+    constexpr int NG = 2 * K16;           // producer groups (8 columns each) in this CTA's K-slice
+    constexpr int NA = 8 * NG;            // threads that fetch packets: (chain pair ga, producer group pa)
+    constexpr int NCC = 2 * K16 / NT;     // clusters per chain-group set
+    constexpr int CW = 64 * NT;           // columns owned by a cluster
+    constexpr int ROWB = 1024 + 16;       // bytes per k8-step row of A fragments: 32 lanes x (16 B hi + 16 B lo) + pad
+    constexpr int C0 = FLOW_THREADS - 128 * NT;  // first final-owner thread
+    static_assert(K16 >= 1 && K16 <= 16 && (K16 & (K16 - 1)) == 0, "K16 must be a power of two in [1,16]");
+    static_assert(NT == 1 || NT == 2, "NT must be 1 or 2");
+    static_assert(NA <= FLOW_THREADS && NG <= 32, "K-slice too long");
+
+    extern __shared__ __align__(16) unsigned char s_frag_raw[];  // [2][NG][ROWB]
+    unsigned char(*s_frag)[NG][ROWB] = reinterpret_cast<unsigned char(*)[NG][ROWB]>(s_frag_raw);
+    __shared__ __align__(16) float s_part[2][FLOW_CLUSTER][NT][FLOW_CHAINS][8];
+    __shared__ int s_eref[2][FLOW_CLUSTER][FLOW_CHAINS];
+    __shared__ int s_erefloc[2][FLOW_CHAINS];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ int s_abort;
+    __shared__ float s_obs[FLOW_OBS_DEPTH][FLOW_THREADS];  // cp.async ring of obs[b, t, colC], private per thread
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+    const int rank = (int)cluster_ctarank();
+    const int cid = blockIdx.x / FLOW_CLUSTER;
+    const int set = cid / NCC, cc = cid % NCC;
+    const int S = p.S;
+
+    // bytes one step delivers into this CTA: 8 source CTAs x (NT tiles x 16 chains x 8 columns fp32 + 16 exponents)
+    constexpr uint32_t TX_BYTES = FLOW_CLUSTER * (NT * FLOW_CHAINS * 8 * 4 + FLOW_CHAINS * 4);
+    if (tid == 0) {
+        mbar_init(smem_u32(&s_bar[0]), 1);
+        mbar_init(smem_u32(&s_bar[1]), 1);
+        s_abort = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arm(smem_u32(&s_bar[0]), TX_BYTES);  // armed for steps 0 and 1; re-armed two steps ahead in phase C
+        mbar_arm(smem_u32(&s_bar[1]), TX_BYTES);
+    }
+
+    // ---- resident operand: B fragments of P[k, col] = exp(A[k, col] - cA[col]); k-permutation inside a
+    //      k8-step: fragment slot (tig, h) holds k = 2*tig + h
+    uint32_t Ph[NT][NG][2], Pl[NT][NG];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int col = cc * CW + nt * 64 + warp * 8 + g;
+        const float ca = col < S ? p.cA[col] : 0.f;
+#pragma unroll
+        for (int ks = 0; ks < NG; ++ks) {
+            float lo2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = rank * KS + ks * 8 + 2 * tig + h;
+                float v = 0.f;
+                if (k < S && col < S) v = expf(p.A[(int64_t)k * S + col] - ca);
+                const uint32_t hi = cvt_tf32(v);
+                Ph[nt][ks][h] = hi;
+                lo2[h] = (v - __uint_as_float(hi)) * kScalePl;
+            }
+            const __half2 l = __floats2half2_rn(lo2[0], lo2[1]);
+            Pl[nt][ks] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+    }
+
+    // ---- roles
+    // phase A (tid < NA): chain pair (ga, ga+8), producer group pa of this CTA's K-slice
+    const int ga = tid / NG, pa = tid % NG;
+    // phase C (tid >= C0): final owner of column colC for chain bc
+    const int tc = tid - C0;
+    const int ntc = tc >> 7, bc = (tc >> 3) & 15, jc = tc & 7;
+    const int colC = cc * CW + ntc * 64 + rank * 8 + jc;
+    const float caC = (tc >= 0 && colC < S) ? p.cA[colC] : 0.f;
+    const uint32_t bar_addr0 = smem_u32(&s_bar[0]);
+    // remote addresses for the reduce-scatter: warp w sends its partials to cluster rank w
+    const uint32_t r_part = mapa_u32(smem_u32(&s_part[0][rank][0][0][0]), (uint32_t)warp);
+    const uint32_t r_eref = mapa_u32(smem_u32(&s_eref[0][rank][0]), (uint32_t)warp);
+    const uint32_t r_bar0 = mapa_u32(bar_addr0, (uint32_t)warp);
+
+    cluster_sync_all();  // barriers initialised cluster-wide before any remote arrive
+
+    unsigned long long* const pkt_set = p.pkt + (size_t)set * 2 * FLOW_CHAINS * SP;
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned nstep = 0;  // steps executed by this CTA (drives barrier parity and smem buffer choice)
+    unsigned tau = 0;    // packet stamp counter (monotone across chain groups)
+    bool aborted = false;
+
+    for (int grp = set; grp < p.groups_total && !aborted; grp += p.nsets) {
+        const int64_t b0 = (int64_t)grp * FLOW_CHAINS;
+        int E_prev = 0, E_abs = 0;
+        bool zero_last = true;
+        float u_last = 0.f;
+        const bool chain_ok = tc >= 0 && (b0 + bc) < p.B && colC < S;
+        const float* obs_c = (chain_ok && p.obs) ? p.obs + ((b0 + bc) * p.T) * S + colC : nullptr;
+
+        // ---- message before the first step: alpha_{-1} = init
+        if (tc >= 0) {
+            float x = -INFINITY;
+            if (chain_ok) x = (p.init ? p.init[(b0 + bc) * p.init_sb + colC] : 0.f) * kLog2e;
+            int E15;
+            bool zero;
+            const float u = flow_normalise(1.f, x, 0, E15, zero);
+            E_abs = sext15(E15);
+            E_prev = E15;
+            u_last = u;
+            zero_last = zero;
+            const unsigned stamp = ((tau & 0xFFFFu) << 16) | (zero ? 0x8000u : 0u) | (unsigned)E15;
+            st_pkt(pkt_set + ((size_t)(tau & 1) * FLOW_CHAINS + bc) * SP + colC,
+                   ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(u));
+        }
+        // obs prefetch ring: one cp.async group per step, FLOW_OBS_DEPTH-1 steps ahead
+        const uint32_t obs_ring = smem_u32(&s_obs[0][tid]);
+#pragma unroll
+        for (int q = 0; q < FLOW_OBS_DEPTH - 1; ++q) {
+            if (obs_c && q < p.T) cp_async4(obs_ring + (uint32_t)q * (FLOW_THREADS * 4), obs_c + (int64_t)q * S);
+            cp_async_commit();
+        }
+
+        for (int64_t t = 0; t < p.T; ++t) {
+            const int buf = nstep & 1, par = nstep & 1;
+            const unsigned ph = (nstep >> 1) & 1;
+            int timed_out = 0;
+            const long long c_top = p.prof ? clock64() : 0;
+            long long c_pkt = c_top;
+
+            // ================= phase A: fetch this CTA's K-slice of the message =================
+            if (tid < NA) {
+                constexpr unsigned amask = NA >= 32 ? 0xffffffffu : ((1u << (NA & 31)) - 1u);
+                const unsigned long long* src0 = pkt_set + ((size_t)(tau & 1) * FLOW_CHAINS + ga) * SP + rank * KS + pa * 8;
+                const unsigned long long* src1 = src0 + (size_t)8 * SP;
+                unsigned long long q0[8], q1[8];
+                const unsigned want = tau & 0xFFFFu;
+                const long long start = clock64();
+                for (;;) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        ld_pkt2(src0 + 2 * i, q0[2 * i], q0[2 * i + 1]);
+                        ld_pkt2(src1 + 2 * i, q1[2 * i], q1[2 * i + 1]);
+                    }
+                    bool ok = true;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        ok = ok && ((unsigned)(q0[i] >> 48) == want) && ((unsigned)(q1[i] >> 48) == want);
+                    if (ok) break;
+                    if (clock64() - start > FLOW_SPIN_LIMIT) {
+                        timed_out = 1;
+                        if (atomicCAS(p.abort_flag + 1, 0, 1) == 0) {  // first timeout wins: leave a post-mortem record
+                            p.abort_flag[2] = (int)blockIdx.x;
+                            p.abort_flag[3] = tid;
+                            p.abort_flag[4] = (int)t;
+                            p.abort_flag[5] = (int)want;
+                            p.abort_flag[6] = (int)(q0[0] >> 32);
+                            p.abort_flag[7] = (int)(q1[7] >> 32);
+                        }
+                        break;
+                    }
+                }
+                if (p.prof) c_pkt = clock64();
+                // align block exponents across the producer groups of the slice (lanes sharing ga are contiguous)
+                const int e0 = (int)(q0[0] >> 32) & 0xFFFF, e1 = (int)(q1[0] >> 32) & 0xFFFF;
+                const int base_lane = lane & ~(NG - 1);
+                const int ref0 = __shfl_sync(amask, e0, base_lane) & 0x7FFF;
+                const int ref1 = __shfl_sync(amask, e1, base_lane) & 0x7FFF;
+                const int d0 = (e0 & 0x8000) ? -40000 : sext15(e0 - ref0);
+                const int d1 = (e1 & 0x8000) ? -40000 : sext15(e1 - ref1);
+                int m0 = d0, m1 = d1;
+#pragma unroll
+                for (int o = NG / 2; o > 0; o >>= 1) {
+                    m0 = max(m0, __shfl_xor_sync(amask, m0, o));
+                    m1 = max(m1, __shfl_xor_sync(amask, m1, o));
+                }
+                const float sc0 = (d0 == -40000) ? 0.f : pow2i(d0 - m0);
+                const float sc1 = (d1 == -40000) ? 0.f : pow2i(d1 - m1);
+                if (pa == 0) {
+                    s_erefloc[buf][ga] = (m0 == -40000) ? (0x8000 | ref0) : ((ref0 + m0) & 0x7FFF);
+                    s_erefloc[buf][ga + 8] = (m1 == -40000) ? (0x8000 | ref1) : ((ref1 + m1) & 0x7FFF);
+                }
+                // split to TF32 hi/lo and lay out as mma A fragments of k8-step pa: lane (ga, tig') gets
+                // {v0[2tig'], v1[2tig'], v0[2tig'+1], v1[2tig'+1]} (chains ga / ga+8), 16 B hi + 16 B lo per
+                // lane; the two halves are xor-swizzled with bit 2 of the lane so that the writes here and
+                // the reads in phase B are bank-conflict free.
+                unsigned char* row = &s_frag[buf][pa][0];
+                const int swz = (ga & 1) * 16;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float v[4] = {__uint_as_float((unsigned)q0[2 * i]) * sc0, __uint_as_float((unsigned)q1[2 * i]) * sc1,
+                                        __uint_as_float((unsigned)q0[2 * i + 1]) * sc0,
+                                        __uint_as_float((unsigned)q1[2 * i + 1]) * sc1};
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        hi[c] = cvt_tf32(v[c]);
+                        lo[c] = cvt_tf32(v[c] - __uint_as_float(hi[c]));
+                    }
+                    unsigned char* dst = row + (ga * 4 + i) * 32;
+                    *reinterpret_cast<uint4*>(dst + swz) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(dst + (16 ^ swz)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+            if (__syncthreads_or(timed_out | *(volatile int*)&s_abort)) {
+                aborted = true;
+                break;
+            }
+
+            const long long c_sync = p.prof ? clock64() : 0;
+            // ================= phase B: partial contraction + reduce-scatter over DSMEM =================
+            {
+                float acc[NT][3][4];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[nt][q][c] = 0.f;
+                const int swz = ((lane >> 2) & 1) * 16;
+#pragma unroll
+                for (int ks = 0; ks < NG; ++ks) {
+                    const unsigned char* rowp = &s_frag[buf][ks][0] + lane * 32;
+                    const uint4 fh = *reinterpret_cast<const uint4*>(rowp + swz);
+                    const uint4 fl = *reinterpret_cast<const uint4*>(rowp + (16 ^ swz));
+                    const uint32_t ah[4] = {fh.x, fh.y, fh.z, fh.w};
+                    const uint32_t al[4] = {fl.x, fl.y, fl.z, fl.w};
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const float2 pl = __half22float2(*reinterpret_cast<const __half2*>(&Pl[nt][ks]));
+                        mma_tf32(acc[nt][0], ah, Ph[nt][ks][0], Ph[nt][ks][1]);
+                        mma_tf32(acc[nt][1], al, Ph[nt][ks][0], Ph[nt][ks][1]);
+                        mma_tf32(acc[nt][2], ah, __float_as_uint(pl.x), __float_as_uint(pl.y));
+                    }
+                }
+                const uint32_t off = (uint32_t)par * (FLOW_CLUSTER * NT * FLOW_CHAINS * 8 * 4);
+                const uint32_t r_bar = r_bar0 + (uint32_t)par * 8;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const uint32_t o2 = off + (uint32_t)nt * (FLOW_CHAINS * 8 * 4);
+                    st_async_v2f(r_part + o2 + (uint32_t)((g * 8 + 2 * tig) * 4),
+                                 acc[nt][0][0] + (acc[nt][1][0] + kUnscalePl * acc[nt][2][0]),
+                                 acc[nt][0][1] + (acc[nt][1][1] + kUnscalePl * acc[nt][2][1]), r_bar);
+                    st_async_v2f(r_part + o2 + (uint32_t)(((g + 8) * 8 + 2 * tig) * 4),
+                                 acc[nt][0][2] + (acc[nt][1][2] + kUnscalePl * acc[nt][2][2]),
+                                 acc[nt][0][3] + (acc[nt][1][3] + kUnscalePl * acc[nt][2][3]), r_bar);
+                }
+                if (lane < FLOW_CHAINS)
+                    st_async_u32(r_eref + (uint32_t)par * (FLOW_CLUSTER * FLOW_CHAINS * 4) + (uint32_t)lane * 4,
+                                 (uint32_t)s_erefloc[buf][lane], r_bar);
+            }
+            const long long c_sent = p.prof ? clock64() : 0;
+            if (p.prof && tid == 0) {
+                prof_acc[0] += c_pkt - c_top;    // waiting for / loading packets
+                prof_acc[1] += c_sync - c_pkt;   // exponent alignment, split, STS, bar.sync
+                prof_acc[2] += c_sent - c_sync;  // LDS + mma + DSMEM stores + arrive
+            }
+
+            // ================= phase C: final owners finish their columns and publish =================
+            if (tc >= 0) {
+                const long long start = clock64();
+                while (!mbar_try_wait(bar_addr0 + (uint32_t)par * 8, ph)) {
+                    if (clock64() - start > FLOW_SPIN_LIMIT) {
+                        s_abort = 1;
+                        if (atomicCAS(p.abort_flag + 1, 0, 2) == 0) {
+                            p.abort_flag[2] = (int)blockIdx.x;
+                            p.abort_flag[3] = tid;
+                            p.abort_flag[4] = (int)t;
+                        }
+                        break;
+                    }
+                }
+                const long long c_got = p.prof ? clock64() : 0;
+                const int e0 = s_eref[par][0][bc] & 0x7FFF;
+                int dr[FLOW_CLUSTER], dmax = -40000;
+#pragma unroll
+                for (int r = 0; r < FLOW_CLUSTER; ++r) {
+                    const int e = s_eref[par][r][bc];
+                    dr[r] = (e & 0x8000) ? -40000 : sext15(e - e0);
+                    dmax = max(dmax, dr[r]);
+                }
+                float s = 0.f;
+#pragma unroll
+                for (int r = 0; r < FLOW_CLUSTER; ++r)
+                    s += (dr[r] == -40000) ? 0.f : s_part[par][r][ntc][bc][jc] * pow2i(dr[r] - dmax);
+                const int emax = (dmax == -40000) ? e0 : ((e0 + dmax) & 0x7FFF);
+                // this phase is complete (all threads of the CTA that wait on it see the same parity); arm the
+                // barrier for the step after next.  No sender can be two steps ahead of this CTA.
+                if (tc == 0) mbar_arm(bar_addr0 + (uint32_t)par * 8, TX_BYTES);
+                const long long c_red = p.prof ? clock64() : 0;
+                cp_async_wait<FLOW_OBS_DEPTH - 2>();
+                const float ob = obs_c ? s_obs[t % FLOW_OBS_DEPTH][tid] : 0.f;
+                const float x = chain_ok ? (ob + caC) * kLog2e : -INFINITY;
+                int E15;
+                bool zero;
+                const long long c_obs = p.prof ? clock64() : 0;
+                const float u = flow_normalise(s, x, emax, E15, zero);
+                const long long c_nrm = p.prof ? clock64() : 0;
+                E_abs += sext15(E15 - E_prev);
+                E_prev = E15;
+                u_last = u;
+                zero_last = zero;
+                const unsigned tn = tau + 1;
+                const unsigned stamp = ((tn & 0xFFFFu) << 16) | (zero ? 0x8000u : 0u) | (unsigned)E15;
+                st_pkt(pkt_set + ((size_t)(tn & 1) * FLOW_CHAINS + bc) * SP + colC,
+                       ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(u));
+                // refill the slot consumed one step ago
+                {
+                    const int64_t tn2 = t + FLOW_OBS_DEPTH - 1;
+                    if (obs_c && tn2 < p.T)
+                        cp_async4(obs_ring + (uint32_t)(tn2 % FLOW_OBS_DEPTH) * (FLOW_THREADS * 4), obs_c + tn2 * S);
+                    cp_async_commit();
+                }
+                if (p.prof && tid == FLOW_THREADS - 1) {
+                    prof_acc[3] += c_got - c_sent;       // waiting for the 8 partials of my columns
+                    prof_acc[4] += clock64() - c_got;    // reduce, exp2, normalise, publish
+                    prof_acc[5] += c_red - c_got;
+                    prof_acc[6] += c_obs - c_red;
+                    prof_acc[7] += c_nrm - c_obs;
+                }
+            }
+            ++nstep;
+            ++tau;
+        }
+        cp_async_wait<0>();
+        // ---- final message of the group (alpha_{T-1}) for the log-likelihood reduction
+        if (tc >= 0 && (b0 + bc) < p.B) {
+            p.fin_u[(b0 + bc) * SP + colC] = u_last;
+            if (jc == 0) p.fin_e[(b0 + bc) * (SP / 8) + colC / 8] = zero_last ? INT_MIN : E_abs;
+        }
+        // The next group's initial message overwrites this group's last message (same buffer parity, which
+        // nobody reads any more) under a stamp that differs from it.
+        tau += 2;
+    }
+    if (p.prof) {
+        if (tid == 0)
+            for (int q = 0; q < 3; ++q) p.prof[(size_t)blockIdx.x * 8 + q] = prof_acc[q];
+        if (tid == FLOW_THREADS - 1) {
+            p.prof[(size_t)blockIdx.x * 8 + 3] = prof_acc[3];
+            p.prof[(size_t)blockIdx.x * 8 + 4] = prof_acc[4];
+            p.prof[(size_t)blockIdx.x * 8 + 5] = (long long)nstep;
+            p.prof[(size_t)blockIdx.x * 8 + 6] = prof_acc[5];
+            p.prof[(size_t)blockIdx.x * 8 + 7] = prof_acc[6];
+            p.prof[(size_t)blockIdx.x * 8 + 2] += 0;
+            p.prof[(size_t)(FLOW_PROF_CTAS / 2 + blockIdx.x / 2) * 8 + (blockIdx.x & 1)] = prof_acc[7];
+        }
+    }
+    if (aborted && tid == 0) atomicExch(p.abort_flag, 1);
+    cluster_sync_all();  // nobody may exit while a peer can still write into its shared memory
+}
+
+// cA[j] = max(max_i A[i,j], -FLT_MAX) for j < S, 0 in the padding (clamped like numpy_log.py:31-32)
+__global__ void flow_colmax(const float* A, int S, int Sp, float* cA) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Sp) return;
+    float m = -FLT_MAX;
+    if (j < S)
+        for (int i = 0; i < S; ++i) m = fmaxf(m, A[(int64_t)i * S + j]);
+    cA[j] = j < S ? m : 0.f;
+}
+
+// logZ[b] = log sum_j u[b,j] 2^{E[b,j/8]}  (one warp per chain, double accumulation)
+__global__ void flow_finalise(const float* fin_u, const int* fin_e, const int* abort_flag, int64_t B, int S, int Sp,
+                              float* logZ, double* logZ_d) {
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (b >= B) return;
+    const int ngrp = Sp / 8;
+    int emax = INT_MIN;
+    for (int q = lane; q < ngrp; q += 32) emax = max(emax, fin_e[b * ngrp + q]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    double sum = 0.0;
+    if (emax != INT_MIN)
+        for (int j = lane; j < S; j += 32) {
+            const int e = fin_e[b * ngrp + j / 8];
+            if (e != INT_MIN) sum += ldexp((double)fin_u[b * Sp + j], max(e - emax, -2000));
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) {
+        double z = (emax == INT_MIN) ? -INFINITY : (double)emax * 0.69314718055994530942 + log(sum);
+        if (*abort_flag) z = __longlong_as_double(0x7ff8000000000000ll);
+        logZ[b] = (float)z;
+        if (logZ_d) logZ_d[b] = z;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct FlowShape {
+    int k16, nt;
+};
+static FlowShape flow_shape(int S) {
+    if (S <= 64 || S > 1024) return {0, 0};
+    if (S <= 128) return {1, 1};
+    if (S <= 256) return {2, 1};
+    if (S <= 512) return {4, 1};
+    return {8, 2};
+}
+
+bool hmm_flow_supported(int semiring, int64_t a_sb, int64_t a_st, int S, bool wants_alpha) {
+    return semiring == FB2_SEMIRING_LOG && a_sb == 0 && a_st == 0 && !wants_alpha && flow_shape(S).k16 != 0;
+}
+
+constexpr int FLOW_MAX_SETS = 8;
+
+size_t hmm_flow_workspace_bytes(int64_t B, int S) {
+    const FlowShape fs = flow_shape(S);
+    if (!fs.k16) return 0;
+    const size_t Sp = (size_t)fs.k16 * 128;
+    const size_t groups = (size_t)ceil_div(B, FLOW_CHAINS);
+    return align_up(Sp * 4) + align_up((size_t)FLOW_MAX_SETS * 2 * FLOW_CHAINS * Sp * 8) + align_up(groups * FLOW_CHAINS * Sp * 4) +
+           align_up(groups * FLOW_CHAINS * (Sp / 8) * 4) + align_up(32) + align_up((size_t)FLOW_PROF_CTAS * 64) + 256;
+}
+
+template <int K16, int NT>
+static int flow_launch(FlowArgs& a, cudaStream_t stream) {
+    auto kernel = hmm_flow_forward<K16, NT>;
+    constexpr int NCC = 2 * K16 / NT;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(FLOW_THREADS);
+    cfg.dynamicSmemBytes = (size_t)2 * (2 * K16) * (1024 + 16);
+    FB2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = FLOW_CLUSTER;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    // how many clusters of 8 can be co-resident?  (the CTAs of one set wait on each other)
+    cfg.gridDim = dim3(FLOW_CLUSTER * NCC);
+    int max_clusters = 0;
+    FB2_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
+    int nsets = max_clusters / NCC;
+    if (nsets > FLOW_MAX_SETS) nsets = FLOW_MAX_SETS;
+    if (nsets > a.groups_total) nsets = a.groups_total;
+    if (nsets < 1) {
+        set_error("hmm flow: only %d clusters of %d CTAs can be co-resident, %d needed", max_clusters, FLOW_CLUSTER, NCC);
+        return FB2_ERR_UNSUPPORTED;
+    }
+    a.nsets = nsets;
+    cfg.gridDim = dim3(FLOW_CLUSTER * NCC * nsets);
+    // Plain cluster launch.  The occupancy query above proves that every cluster of the grid can be resident at
+    // once, which is what the inter-CTA waits need.  cudaLaunchAttributeCooperative is deliberately NOT added:
+    // measured on B200 / driver 580, a cooperative + cluster launch is not co-scheduled under ncu / CUPTI kernel
+    // serialisation (the first packet wait of every CTA timed out), while the plain cluster launch runs there.
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a);
+    if (getenv("FB2_DEBUG")) fprintf(stderr, "[fb2 flow] launch grid %d max_clusters %d -> %s\n", cfg.gridDim.x, max_clusters, cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        set_error("hmm flow launch failed: %s", cudaGetErrorString(e));
+        return FB2_ERR_CUDA;
+    }
+    count_launch();
+    return FB2_OK;
+}
+
+int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
+                            float* logZ, double* logZ_d, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    const FlowShape fs = flow_shape(S);
+    if (!fs.k16) {
+        set_error("hmm flow: S=%d outside the supported range", S);
+        return FB2_ERR_UNSUPPORTED;
+    }
+    const int Sp = fs.k16 * 128;
+    const int64_t groups = ceil_div(B, FLOW_CHAINS);
+    Arena arena(workspace, workspace_bytes);
+    float* cA = arena.take<float>((size_t)Sp);
+    unsigned long long* pkt = arena.take<unsigned long long>((size_t)FLOW_MAX_SETS * 2 * FLOW_CHAINS * Sp);
+    float* fin_u = arena.take<float>((size_t)groups * FLOW_CHAINS * Sp);
+    int* fin_e = arena.take<int>((size_t)groups * FLOW_CHAINS * (Sp / 8));
+    int* abort_flag = arena.take<int>(8);  // [0] abort, [1..7] post-mortem of the first wait that gave up
+    long long* prof = arena.take<long long>((size_t)FLOW_PROF_CTAS * 8);
+    if (!arena.ok()) {
+        set_error("hmm flow: workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    // stale packets must never carry a valid stamp: 0xFF.. = stamp 0xFFFF, overwritten after two steps
+    FB2_CUDA(cudaMemsetAsync(pkt, 0xFF, (size_t)FLOW_MAX_SETS * 2 * FLOW_CHAINS * Sp * 8, stream));
+    FB2_CUDA(cudaMemsetAsync(abort_flag, 0, 32, stream));
+    flow_colmax<<<(unsigned)ceil_div(Sp, 128), 128, 0, stream>>>(A, S, Sp, cA);
+    FB2_LAUNCH_CHECK();
+    FlowArgs a{};
+    a.init = init; a.init_sb = init_sb; a.A = A; a.obs = obs; a.cA = cA; a.B = B; a.T = T; a.S = S;
+    a.pkt = pkt; a.fin_u = fin_u; a.fin_e = fin_e; a.abort_flag = abort_flag; a.groups_total = (int)groups;
+    const char* prof_env = getenv("FB2_FLOW_PROF");
+    a.prof = (prof_env && prof_env[0] == '1') ? prof : nullptr;
+    if (a.prof) FB2_CUDA(cudaMemsetAsync(prof, 0, (size_t)FLOW_PROF_CTAS * 64, stream));
+    int st;
+    if (fs.k16 == 1) st = flow_launch<1, 1>(a, stream);
+    else if (fs.k16 == 2) st = flow_launch<2, 1>(a, stream);
+    else if (fs.k16 == 4) st = flow_launch<4, 1>(a, stream);
+    else st = flow_launch<8, 2>(a, stream);
+    if (st != FB2_OK) return st;
+    flow_finalise<<<(unsigned)ceil_div(B, 4), 128, 0, stream>>>(fin_u, fin_e, abort_flag, B, S, Sp, logZ, logZ_d);
+    FB2_LAUNCH_CHECK();
+    if (getenv("FB2_DEBUG")) {
+        int h[8];
+        FB2_CUDA(cudaStreamSynchronize(stream));
+        FB2_CUDA(cudaMemcpy(h, abort_flag, sizeof(h), cudaMemcpyDeviceToHost));
+        if (h[0] || h[1])
+            fprintf(stderr, "[fb2 flow] ABORT=%d first timeout: kind %d (1 packets, 2 partials) cta %d tid %d t %d want %#x saw %#x %#x\n",
+                    h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+    }
+    if (a.prof) {  // debugging aid only: synchronises and prints the per-phase cycle averages of a few CTAs
+        static long long h[FLOW_PROF_CTAS * 8];
+        FB2_CUDA(cudaStreamSynchronize(stream));
+        FB2_CUDA(cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int c = 0; c < FLOW_PROF_CTAS / 2; c += 9) {
+            const double n = h[c * 8 + 5] > 0 ? (double)h[c * 8 + 5] : 1.0;
+            if (h[c * 8 + 5] > 0)
+                fprintf(stderr, "[fb2 flow prof] cta %3d steps %lld | pkt-wait %.0f  A-proc+sync %.0f  B(mma+send) %.0f | C-wait %.0f  C-proc %.0f (reduce %.0f obs %.0f normalise %.0f) cycles/step\n",
+                        c, h[c * 8 + 5], h[c * 8 + 0] / n, h[c * 8 + 1] / n, h[c * 8 + 2] / n, h[c * 8 + 3] / n, h[c * 8 + 4] / n,
+                        h[c * 8 + 6] / n, h[c * 8 + 7] / n, h[(FLOW_PROF_CTAS / 2 + c / 2) * 8 + (c & 1)] / n);
+        }
+    }
+    return FB2_OK;
+}
+
+}  // namespace fb2

@@ -14,7 +14,20 @@
 //     step-to-step critical path.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace fb2 {
+
+// hmm_flow.cu
+bool hmm_flow_supported(int semiring, int64_t a_sb, int64_t a_st, int S, bool wants_alpha);
+size_t hmm_flow_workspace_bytes(int64_t B, int S);
+int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
+                            float* logZ, double* logZ_d, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// FB2_DISABLE_FLOW=1 forces the generic kernel (A/B testing of the two GPU paths)
+static bool flow_disabled() {
+    const char* e = getenv("FB2_DISABLE_FLOW");
+    return e && e[0] == '1';
+}
 
 struct HmmArgs {
     const float* init;  // nullable -> semiring one
@@ -597,6 +610,7 @@ using namespace fb2;
 
 extern "C" size_t fb2_hmm_workspace_bytes(int op, int64_t B, int64_t T, int32_t S) {
     size_t base = vec_bytes(B, S) + ctr_bytes() + 512;
+    if (op == 0) base += hmm_flow_workspace_bytes(B, S);
     if (op == 1) base += align_up((size_t)B * T * S * sizeof(int32_t)) + align_up((size_t)B * sizeof(int32_t));
     if (op == 2) base += align_up((size_t)B * T * S * sizeof(float)) + 2 * align_up((size_t)B * T * 8) + align_up((size_t)B * 8);
     return base;
@@ -611,6 +625,17 @@ extern "C" int fb2_hmm_forward_f32(int semiring, const float* init, int64_t init
     if (st != FB2_OK) return st;
     FB2_REQUIRE(logZ != nullptr, "logZ is null");
     if (B == 0) return FB2_OK;
+    // time-homogeneous log-semiring chains take the dataflow kernel (hmm_flow.cu); everything else, and
+    // shapes it declines, run the generic cooperative kernel above.  Both are GPU paths.
+    if (hmm_flow_supported(semiring, a_sb, a_st, S, alpha_all != nullptr) && !flow_disabled()) {
+        const size_t fw = hmm_flow_workspace_bytes(B, S);
+        if (workspace_bytes >= fw) {
+            st = hmm_flow_forward_device(init, init_sb, A, obs, B, T, S, logZ, nullptr, workspace, workspace_bytes,
+                                         static_cast<cudaStream_t>(stream));
+            if (st != FB2_ERR_UNSUPPORTED) return st;
+            if (getenv("FB2_DEBUG")) fprintf(stderr, "[fb2] dataflow kernel declined: %s\n", fb2_last_error());
+        }
+    }
     return hmm_forward_device(semiring, init, init_sb, A, a_sb, a_st, obs, nullptr, B, T, S, logZ, alpha_all, nullptr,
                               nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }

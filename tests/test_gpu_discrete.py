@@ -284,3 +284,101 @@ def test_c2_full_size_shift_and_split_properties(fb):
     z1, alpha = fb.hmm_forward(init, A, obs[:, :half].contiguous(), return_alpha=True)
     z2 = fb.hmm_forward(alpha[:, -1].contiguous(), A, obs[:, half:].contiguous())
     rel_close(host(z2), host(z), rtol=RTOL)
+
+
+# ------------------------------------------------------------------ dataflow forward kernel (hmm_flow.cu)
+def _flow_case(B, T, S, seed, obs_scale=1.0, obs_shift=0.0):
+    g = torch.Generator().manual_seed(seed)
+    init = torch.randn(B, S, generator=g).log_softmax(-1)
+    A = torch.randn(S, S, generator=g).log_softmax(-1)
+    obs = torch.randn(B, T, S, generator=g) * obs_scale + obs_shift
+    return init, A, obs
+
+
+@pytest.mark.parametrize("B,T,S", [(16, 40, 1024), (1, 64, 700), (5, 33, 65), (3, 1, 128), (40, 25, 257), (16, 2, 512),
+                                   (2, 300, 100), (17, 50, 1000), (1, 3, 1024)])
+def test_hmm_forward_flow_random(fb, B, T, S):
+    """Homogeneous log-semiring chains with 64 < S <= 1024 and no alpha output run the dataflow kernel."""
+    init, A, obs = _flow_case(B, T, S, seed=11)
+    n0 = fb.launch_count(reset=True)
+    got = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda())
+    assert fb.launch_count() == 3, "expected colmax + flow + finalise launches, i.e. the dataflow path"
+    want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    rel_close(host(got), want, rtol=RTOL, atol=1.0)
+
+
+def test_hmm_forward_flow_tight_short_chain(fb):
+    """Short chains have small |logZ|: the 3xTF32 contraction must hold fp32-class accuracy (1e-5 of 1 + |logZ|)."""
+    init, A, obs = _flow_case(16, 8, 256, seed=12)
+    got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    assert np.max(np.abs(got - want)) < 2e-5 * (1 + np.max(np.abs(want)))
+
+
+def test_hmm_forward_flow_matches_generic_kernel(fb):
+    import os
+
+    init, A, obs = _flow_case(7, 120, 384, seed=13)
+    z_flow = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    os.environ["FB2_DISABLE_FLOW"] = "1"
+    try:
+        z_gen = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    finally:
+        os.environ.pop("FB2_DISABLE_FLOW")
+    rel_close(z_flow, z_gen, rtol=RTOL, atol=1.0)
+
+
+def test_hmm_forward_flow_extreme_observations(fb):
+    """Observation log-likelihoods of magnitude ~1e3 with a spread of hundreds of nats between states
+    (continuous-emission HMMs): block exponents absorb them; nothing over- or underflows."""
+    init, A, obs = _flow_case(4, 60, 200, seed=14, obs_scale=150.0, obs_shift=-900.0)
+    got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    rel_close(got, want, rtol=RTOL, atol=1.0)
+
+
+def test_hmm_forward_flow_neg_inf(fb):
+    g = torch.Generator().manual_seed(15)
+    B, T, S = 4, 20, 130
+    init = torch.randn(B, S, generator=g)
+    A = torch.randn(S, S, generator=g)
+    A[0, 1] = -float("inf")
+    A[:, 4] = -float("inf")  # unreachable state
+    A[:, 64:72] = -float("inf")  # a whole column group unreachable
+    obs = torch.randn(B, T, S, generator=g)
+    obs[1, 3, 2] = -float("inf")
+    obs[2, 5, :] = -float("inf")  # impossible observation -> logZ = -inf, not NaN
+    init[3, :] = -float("inf")
+    init[3, 7] = 0.0  # deterministic start
+    got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    assert np.isneginf(got[2]) and not np.isnan(got).any()
+    rel_close(got, want, rtol=RTOL, atol=1.0)
+
+
+def test_hmm_forward_flow_sparse_left_to_right(fb):
+    """Banded (left-to-right) transition matrix: most of P is exactly zero and the message is sparse."""
+    B, T, S = 3, 90, 160
+    g = torch.Generator().manual_seed(16)
+    A = torch.full((S, S), -float("inf"))
+    for i in range(S):
+        A[i, i] = np.log(0.6)
+        A[i, (i + 1) % S] = np.log(0.4)
+    init = torch.full((B, S), -float("inf"))
+    init[:, 0] = 0.0
+    obs = torch.randn(B, T, S, generator=g) * 3
+    got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    rel_close(got, want, rtol=RTOL, atol=1.0)
+
+
+def test_hmm_forward_flow_long_chain_stamp_wrap(fb):
+    """T > 65536 wraps the 16-bit packet stamp; uniform transitions give a closed form for logZ."""
+    B, T, S = 2, 70001, 128
+    g = torch.Generator(device="cuda").manual_seed(17)
+    obs = torch.randn(B, T, S, device="cuda", generator=g)
+    init = torch.randn(B, S, device="cuda", generator=g).log_softmax(-1)
+    A = torch.full((S, S), -float(np.log(S)), device="cuda")
+    got = fb.hmm_forward(init, A, obs)
+    want = torch.logsumexp(init.double(), -1) + (torch.logsumexp(obs.double(), -1) - np.log(S)).sum(-1)
+    rel_close(host(got), host(want), rtol=RTOL)
