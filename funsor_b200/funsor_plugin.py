@@ -1,0 +1,202 @@
+"""Eager patterns that route funsor's Markov-chain sum-product path to the sm_100a kernels.
+
+This is the drop-in boundary on the reference side.  `register()` adds three
+more-specific rules to funsor's `eager` interpretation for the torch backend:
+
+  Contraction[Logaddexp, Add, frozenset, Tensor, Tensor]   replaces funsor/cnf.py:335-340
+  Contraction[Max,       Add, frozenset, Tensor, Tensor]   beats the generic funsor/cnf.py:312-324
+  MarkovProduct[Logaddexp|Max, Add, Tensor, Variable, frozenset, frozenset]
+                                                           beats funsor/sum_product.py:1049-1064
+
+A rule takes the CUDA path only when its operands are float32 CUDA tensors with scalar output shape and
+the contraction has matrix-product structure; in every other case it calls the handler that was
+registered BEFORE ours (captured with eager.dispatch, funsor/registry.py:107-108).  It never returns
+None: that would leave a lazy term instead of trying the next rule (probe).
+
+The named-dimension bookkeeping is kept in two pure functions (`contract_named`, `markov_named`) that
+work on raw tensors and name lists and take the kernel entry point as an argument.  That is what lets
+the path be tested on both sides of the gap between the two machines: against the unmodified reference
+with a torch stand-in for the kernel (CPU container, tests/test_funsor_plugin.py) and against torch with
+the real kernels (GPU box, tests/test_gpu_plugin.py).
+
+funsor itself is not a dependency of this package: nothing here imports it until register() is called.
+"""
+from collections import OrderedDict
+
+import torch
+
+_STATE = {"registered": False, "calls": {"contraction_fast": 0, "contraction_delegated": 0,
+                                         "markov_fast": 0, "markov_delegated": 0}}
+
+
+def stats(reset=False):
+    out = dict(_STATE["calls"])
+    if reset:
+        for k in _STATE["calls"]:
+            _STATE["calls"][k] = 0
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# pure named-tensor logic (no funsor types)
+def contract_named(x, x_names, y, y_names, reduced, semiring, matmul):
+    """out[names] = (+)_{reduced} x[x_names] (x) y[y_names] as one batched semiring matmul.
+
+    x, y: tensors whose dims are exactly the named dims (funsor Tensor.data with scalar output,
+    funsor/tensor.py:138-150).  reduced: set of names present in BOTH operands.  Returns
+    (data, names) with names in funsor's output order: first-seen over x then y, minus reduced
+    (funsor/cnf.py:348-375).  Returns None when the contraction is not a matrix product
+    (a reduced name missing from one side)."""
+    x_names, y_names = list(x_names), list(y_names)
+    if not reduced or not all(r in x_names and r in y_names for r in reduced):
+        return None
+    shared = [n for n in x_names if n in y_names and n not in reduced]  # batch dims
+    ks = [n for n in x_names if n in reduced]
+    x_only = [n for n in x_names if n not in y_names]
+    y_only = [n for n in y_names if n not in x_names]
+    size = {n: x.shape[i] for i, n in enumerate(x_names)}
+    size.update({n: y.shape[i] for i, n in enumerate(y_names)})
+
+    def prod(names):
+        p = 1
+        for n in names:
+            p *= size[n]
+        return p
+
+    xb = x.permute([x_names.index(n) for n in shared + x_only + ks])
+    yb = y.permute([y_names.index(n) for n in shared + ks + y_only])
+    bshape = tuple(size[n] for n in shared)
+    I, K, J = prod(x_only), prod(ks), prod(y_only)
+    xb = xb.reshape(bshape + (I, K))  # a view whenever the grouped dims are mergeable, else one copy
+    yb = yb.reshape(bshape + (K, J))
+    out = matmul(semiring, xb, yb)  # [batch..., I, J]
+    out = out.reshape(bshape + tuple(size[n] for n in x_only) + tuple(size[n] for n in y_only))
+    cur = shared + x_only + y_only
+    want = [n for n in OrderedDict.fromkeys(x_names + y_names) if n not in reduced]
+    out = out.permute([cur.index(n) for n in want])
+    return out, want
+
+
+def markov_named(trans, names, time, prev, curr, semiring, chain):
+    """Chain product over `time` of trans[names] with (prev -> curr) steps.
+
+    Returns (data, out_names): out_names = names without `time`, in the original order -- what
+    sequential_sum_product returns (funsor/sum_product.py:652-701) before step_names are substituted."""
+    names = list(names)
+    batch = [n for n in names if n not in (time, prev, curr)]
+    t = trans.permute([names.index(n) for n in batch + [time, prev, curr]])
+    out = chain(semiring, t)  # [batch..., S, S]
+    cur = batch + [prev, curr]
+    want = [n for n in names if n != time]
+    return out.permute([cur.index(n) for n in want]), want
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel entry points used by the rules
+def _kernel_matmul(semiring, x, y):
+    from . import ops
+
+    return ops.semiring_matmul(semiring, "add", x, y)
+
+
+def _kernel_chain(semiring, t):
+    from . import ops
+
+    return ops.sequential_sum_product(semiring, "add", t)
+
+
+def _fast_ok(*datas):
+    return all(isinstance(d, torch.Tensor) and d.is_cuda and d.dtype == torch.float32 for d in datas)
+
+
+# ------------------------------------------------------------------------------------------------
+def register():
+    """Register the rules into the imported funsor (torch backend).  Idempotent."""
+    if _STATE["registered"]:
+        return
+    import funsor
+    import funsor.ops as fops
+    from funsor.cnf import Contraction
+    from funsor.domains import Bint
+    from funsor.interpretations import eager
+    from funsor.sum_product import MarkovProduct
+    from funsor.tensor import Tensor
+    from funsor.terms import Subs, Variable
+
+    if funsor.get_backend() != "torch":
+        raise RuntimeError("funsor_b200 plugs into the torch backend: call funsor.set_backend('torch') first")
+
+    # ---- capture the handlers that are in force now, by dispatching on tiny sample terms
+    sx = Tensor(torch.zeros(2, 2), OrderedDict(a=Bint[2], b=Bint[2]))
+    sy = Tensor(torch.zeros(2, 2), OrderedDict(b=Bint[2], c=Bint[2]))
+    rv = frozenset({Variable("b", Bint[2])})
+    prev_contract = {}
+    for name, op in (("logaddexp", fops.logaddexp), ("max", fops.max)):
+        prev_contract[name] = eager.dispatch(Contraction, op, fops.add, rv, sx, sy)
+    st = Tensor(torch.zeros(2, 2, 2), OrderedDict(time=Bint[2], prev=Bint[2], curr=Bint[2]))
+    tv = Variable("time", Bint[2])
+    step = frozenset({("prev", "curr")})
+    names = frozenset({("curr", "prev")})
+    prev_markov = eager.dispatch(MarkovProduct, fops.logaddexp, fops.add, st, tv, step, names)
+
+    def _semiring(op):
+        return "logaddexp" if op is fops.logaddexp else "max"
+
+    def contraction_rule(red_op, bin_op, reduced_vars, x, y):
+        sname = _semiring(red_op)
+        fast = (
+            x.dtype == "real" and y.dtype == "real" and not x.shape and not y.shape
+            and _fast_ok(x.data, y.data) and len(reduced_vars) >= 1
+        )
+        if fast:
+            reduced = {v.name for v in reduced_vars}
+            res = contract_named(x.data, x.inputs, y.data, y.inputs, reduced, sname, _kernel_matmul)
+            if res is not None:
+                data, out_names = res
+                inputs = OrderedDict()
+                for term in (x, y):
+                    inputs.update(term.inputs)
+                _STATE["calls"]["contraction_fast"] += 1
+                return Tensor(data, OrderedDict((n, inputs[n]) for n in out_names))
+        _STATE["calls"]["contraction_delegated"] += 1
+        return prev_contract[sname](red_op, bin_op, reduced_vars, x, y)
+
+    eager.register(Contraction, fops.LogaddexpOp, fops.AddOp, frozenset, Tensor, Tensor)(contraction_rule)
+    eager.register(Contraction, fops.MaxOp, fops.AddOp, frozenset, Tensor, Tensor)(contraction_rule)
+
+    def markov_rule(sum_op, prod_op, trans, time, step, step_names):
+        fast = (
+            len(step) == 1 and trans.dtype == "real" and not trans.shape and _fast_ok(trans.data)
+            and time.name in trans.inputs
+        )
+        if fast:
+            ((prev, curr),) = tuple(step)
+            if prev in trans.inputs and curr in trans.inputs and trans.inputs[prev] == trans.inputs[curr]:
+                data, out_names = markov_named(trans.data, trans.inputs, time.name, prev, curr, _semiring(sum_op), _kernel_chain)
+                result = Tensor(data, OrderedDict((n, trans.inputs[n]) for n in out_names))
+                _STATE["calls"]["markov_fast"] += 1
+                return Subs(result, step_names)  # funsor/sum_product.py:1064
+        _STATE["calls"]["markov_delegated"] += 1
+        return prev_markov(sum_op, prod_op, trans, time, step, step_names)
+
+    for op_t in (fops.LogaddexpOp, fops.MaxOp):
+        eager.register(MarkovProduct, op_t, fops.AddOp, Tensor, Variable, frozenset, frozenset)(markov_rule)
+
+    _STATE["registered"] = True
+
+
+def sequential_sum_product(sum_op, prod_op, trans, time, step):
+    """Same signature as funsor.sum_product.sequential_sum_product (652-701) for funsor Tensors on the GPU;
+    funsor/pyro/hmm.py:131 calls that function directly (not through MarkovProduct), so callers that want
+    the fused scan import this one."""
+    import funsor.ops as fops
+    from funsor.sum_product import sequential_sum_product as ref_ssp
+    from funsor.tensor import Tensor
+
+    if (isinstance(trans, Tensor) and sum_op in (fops.logaddexp, fops.max) and prod_op is fops.add and len(step) == 1
+            and trans.dtype == "real" and not trans.shape and _fast_ok(trans.data)):
+        ((prev, curr),) = tuple(dict(step).items())
+        data, out_names = markov_named(trans.data, trans.inputs, time.name, prev, curr,
+                                       "logaddexp" if sum_op is fops.logaddexp else "max", _kernel_chain)
+        return Tensor(data, OrderedDict((n, trans.inputs[n]) for n in out_names))
+    return ref_ssp(sum_op, prod_op, trans, time, step)

@@ -218,6 +218,20 @@ def hmm_marginals(init, A, obs, want_xi=True):
     return logZ, gamma, xi
 
 
+def hmm_chunk_summary(A, obs, sum_op="logaddexp"):
+    """Transfer matrix of a chunk of time: out[b] = (x)_{t in chunk} (A + obs[b,t]) as [B,S,S] -- the summary
+    that time-sharded ranks all-gather (mixed_sequential_sum_product sum_product.py:766-795)."""
+    semi = semiring_id(sum_op)
+    _, _, A, a_sb, a_st, obs, B, T, S = _hmm_args(None, A, obs)
+    out = torch.empty((B, S, S), dtype=torch.float32, device=obs.device)
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_hmm_chunk_summary_workspace_bytes(B, T, S), obs.device)
+    with torch.cuda.device(obs.device):
+        check(lib.fb2_hmm_chunk_summary_f32(semi, A.data_ptr(), a_sb, a_st, obs.data_ptr(), B, T, S, out.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), _stream()))
+    return out
+
+
 def chain_adjoint(sum_op, prod_op, trans, init=None, final=None):
     """Backward pass of the scan (adjoint.py:72-131 specialised to a chain):
     returns (Z[B], adj[B,T,S,S]) with adj[b,t,i,j] = alpha_{t-1}[i] (x) beta_t[j].
