@@ -140,13 +140,15 @@ __device__ __forceinline__ float group8_max(float v) {
 // Normalise the 8 values of one column group (one per lane of an aligned 8-lane group): returns the
 // mantissa of this lane and the new wrapped exponent / zero flag of the group.
 //   true value = s * 2^(x) * 2^(e_in)   ->   u * 2^(E)
-__device__ __forceinline__ float flow_normalise(float s, float x, int e_in15, int& E15, bool& zero) {
+__device__ __forceinline__ float flow_normalise(float s, float x, int e_in15, int& E15, bool& zero, int& dE, bool check_range = true) {
+    dE = 0;
     const float xm = group8_max(x);
     float nf = 0.f, e2 = 0.f;
     if (xm > -1e30f) {
         nf = ceilf(xm);
         e2 = exp2f(x - nf);
-        if (!(fabsf(nf) <= 8000.f)) e2 = __int_as_float(0x7fc00000);  // |obs| beyond the 15-bit block-exponent range
+        // a per-step |obs + colmax| beyond the 15-bit wrapped block-exponent range poisons the result (NaN)
+        if (check_range && !(fabsf(nf) <= 8000.f)) e2 = __int_as_float(0x7fc00000);
     }
     float u = s * e2;
     float mu = group8_max(u);
@@ -168,7 +170,8 @@ __device__ __forceinline__ float flow_normalise(float s, float x, int e_in15, in
     }
     const int q = ((__float_as_int(mu) >> 23) & 0xFF) - 127;
     u *= __int_as_float((127 - q) << 23);
-    E15 = (e_in15 + (int)nf + q + extra) & 0x7FFF;
+    dE = (int)nf + q + extra;
+    E15 = (e_in15 + dE) & 0x7FFF;
     return u;
 }
 
@@ -283,8 +286,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
             if (chain_ok) x = (p.init ? p.init[(b0 + bc) * p.init_sb + colC] : 0.f) * kLog2e;
             int E15;
             bool zero;
-            const float u = flow_normalise(1.f, x, 0, E15, zero);
-            E_abs = sext15(E15);
+            int dE;
+            const float u = flow_normalise(1.f, x, 0, E15, zero, dE, false);  // |init| may be large (hand-over of alpha)
+            E_abs = dE;
             E_prev = E15;
             u_last = u;
             zero_last = zero;
@@ -473,7 +477,8 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 int E15;
                 bool zero;
                 const long long c_obs = p.prof ? clock64() : 0;
-                const float u = flow_normalise(s, x, emax, E15, zero);
+                int dE;
+                const float u = flow_normalise(s, x, emax, E15, zero, dE);
                 const long long c_nrm = p.prof ? clock64() : 0;
                 E_abs += sext15(E15 - E_prev);
                 E_prev = E15;
@@ -526,6 +531,533 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
     }
     if (aborted && tid == 0) atomicExch(p.abort_flag, 1);
     cluster_sync_all();  // nobody may exit while a peer can still write into its shared memory
+}
+
+// ------------------------------------------------------------------------------------------ tcgen05 variant
+// Same dataflow, but the per-step contraction runs on the 5th-generation tensor cores:
+//   D[m, n] (TMEM, 128 lanes x 16 columns fp32) += P^T[m, k] (TMEM, resident for the whole pass) * v[n, k] (SMEM)
+// with m = the 128 columns of P owned by the cluster, n = the 16 chains, k = this CTA's K-slice, kind::tf32,
+// M=128, N=16, K=8 per instruction, 3xTF32 (Ph*vh + Ph*vl + Pl*vh accumulate into one D).  One elected thread
+// issues the 3*KSTEPS MMAs and commits to an mbarrier; warps 4-7 read D with tcgen05.ld (one lane = one column of
+// P) and push their 16 chain values straight to the column's final owner with st.async.  The legacy
+// HMMA.1688.TF32 pipe needed ~1900 cycles per step for the same product (measured); this needs a few hundred.
+//
+// KSTEPS = k8-steps per CTA (Ks = 8*KSTEPS rows, Sp = 64*KSTEPS padded states, Sp/128 clusters of 8 per set).
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t mbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr), "r"(a),
+                 "r"(b), "r"(c), "r"(d), "r"(mbar)
+                 : "memory");
+}
+// K-major, no-swizzle shared-memory operand: core matrix = 8 rows x 16 B contiguous; SBO = 128 B between the two
+// 8-row groups of the 16 chains, LBO = 256 B between the two 16-byte k-chunks of one K=8 instruction.
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(256u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+
+// Issue the 3*KSTEPS MMAs of one step.  Everything the instructions need is a compile-time constant or the
+// (warp-uniform) dynamic shared memory base: the tensor-memory allocation is the whole 512 columns, so its base
+// is 0 (checked once after the allocation), and BUF selects the B tiles / accumulators.  That keeps the operands
+// in uniform registers; an earlier version that computed them from per-thread registers inside `if (tid == 0)`
+// paid ~64 cycles per MMA in R2UR / elect loops (measured).
+template <int KSTEPS, int NACC, int BUF>
+__device__ __forceinline__ void tc_issue_step(uint32_t smem_base, uint32_t mma_bar) {
+    constexpr int KS = KSTEPS * 8;
+    constexpr int STEPB = 512 + 16;
+    constexpr int TILEB = KSTEPS * STEPB;
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t D0 = (uint32_t)(2 * KS + NACC * 16 * BUF);
+    const uint32_t bh = smem_base + (uint32_t)((BUF * 2 + 0) * TILEB), bl = smem_base + (uint32_t)((BUF * 2 + 1) * TILEB);
+    uint32_t elected;
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(elected));
+    if (elected) {
+#pragma unroll
+        for (int i = 0; i < 3 * KSTEPS; ++i) {
+            const int pass = i / KSTEPS, ks = i % KSTEPS;
+            const uint32_t a = (uint32_t)((pass == 2 ? KS : 0) + ks * 8);
+            const uint32_t b = (pass == 1 ? bl : bh) + (uint32_t)(ks * STEPB);
+            tc_mma_tf32_ts(D0 + (uint32_t)((i % NACC) * 16), a, tc_smem_desc(b), IDESC, i >= NACC ? 1u : 0u);
+        }
+        tc_commit(mma_bar);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void st_pkt2(unsigned long long* p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// Normalise one column group held by a PAIR of lanes (lane, lane^16), 4 columns each:
+//   true value = s[i] * 2^(x[i]) * 2^(e_in)   ->   u[i] * 2^(E)
+// Split in two so that everything that depends only on the observations (group max of x, exp2) is done
+// BEFORE the thread waits for the partial sums; only a short dependent chain remains after the wait.
+struct FlowObsTerm {
+    float e2[4];  // 2^(x[i] - nf)
+    int nf;       // ceil(group max of x)
+    int bad;      // per-step magnitude outside the wrapped-exponent range
+};
+__device__ __forceinline__ FlowObsTerm flow_obs_term(const float (&x)[4], bool check_range) {
+    FlowObsTerm o;
+    float xm = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3]));
+    xm = fmaxf(xm, __shfl_xor_sync(0xffffffffu, xm, 16));
+    float nf = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.e2[i] = 0.f;
+    if (xm > -1e30f) {
+        nf = ceilf(xm);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o.e2[i] = exp2f(x[i] - nf);
+    }
+    o.bad = (check_range && xm > -1e30f && !(fabsf(nf) <= 8000.f)) ? 1 : 0;
+    o.nf = (int)nf;
+    return o;
+}
+__device__ __forceinline__ void flow_finish4(const float (&s)[4], const FlowObsTerm& o, int e_in15, float (&u)[4], int& E15, bool& zero,
+                                             int& dE) {
+    int bad = o.bad;
+    float mu = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        u[i] = s[i] * o.e2[i];
+        bad |= !(u[i] <= FLT_MAX) ? 1 : 0;  // NaN or +inf
+        mu = fmaxf(mu, u[i]);
+    }
+    mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, 16));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, 16);
+    dE = 0;
+    E15 = e_in15 & 0x7FFF;
+    zero = !(mu > 0.f);
+    if (bad) {  // poison the group: the log-likelihood becomes NaN
+        zero = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = __int_as_float(0x7fc00000);
+        return;
+    }
+    if (zero) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = 0.f;
+        return;
+    }
+    int extra = 0;
+    float pre = 1.f;
+    if (mu < 1e-20f) {
+        pre = 0x1p64f;
+        mu *= 0x1p64f;
+        extra = -64;
+    }
+    const int q = ((__float_as_int(mu) >> 23) & 0xFF) - 127;
+    const float sc = __int_as_float((127 - q) << 23);  // two multiplications: pre * sc can overflow for denormal mu
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = (u[i] * pre) * sc;
+    dE = o.nf + q + extra;
+    E15 = (e_in15 + dE) & 0x7FFF;
+}
+
+template <int KSTEPS>
+__global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs p) {
+    constexpr int KS = KSTEPS * 8;
+    constexpr int SP = KSTEPS * 64;
+    constexpr int NG = KSTEPS;
+    constexpr int NA = 8 * NG;
+    constexpr int NCC = SP / 128;
+    constexpr int CW = 128;
+    constexpr int NT = 2;
+    constexpr int NACC = 4;                // independent TMEM accumulators (2*KS + 2*NACC*16 <= 512 columns)
+    constexpr int STEPB = 512 + 16;        // bytes between consecutive k-steps of a B tile (+16: conflict-free STS)
+    constexpr int TILEB = KSTEPS * STEPB;  // one B tile (hi or lo)
+    constexpr uint32_t TX_BYTES = FLOW_CLUSTER * (NT * FLOW_CHAINS * 8 * 4 + FLOW_CHAINS * 4);
+    static_assert(KSTEPS >= 2 && KSTEPS <= 16 && (KSTEPS & (KSTEPS - 1)) == 0, "KSTEPS must be a power of two in [2,16]");
+
+    extern __shared__ __align__(128) unsigned char s_b[];  // [2 buf][2 (hi, lo)][TILEB]
+    __shared__ __align__(16) float s_part[2][FLOW_CLUSTER][NT][8][FLOW_CHAINS];  // [parity][src][tile][column][chain]
+    __shared__ __align__(16) int s_eref[2][FLOW_CLUSTER][FLOW_CHAINS];
+    __shared__ __align__(16) int s_erefloc[2][FLOW_CHAINS];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ __align__(8) unsigned long long s_mma_bar;
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int s_abort;
+    __shared__ __align__(16) float s_obs[FLOW_OBS_DEPTH][64][4];  // cp.async ring of obs[b, t, 4 columns], private per phase-C thread
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = (int)cluster_ctarank();
+    const int cid = blockIdx.x / FLOW_CLUSTER;
+    const int set = cid / NCC, cc = cid % NCC;
+    const int S = p.S;
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&s_bar[0]), 1);
+        mbar_init(smem_u32(&s_bar[1]), 1);
+        mbar_init(smem_u32(&s_mma_bar), 1);
+        s_abort = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arm(smem_u32(&s_bar[0]), TX_BYTES);
+        mbar_arm(smem_u32(&s_bar[1]), TX_BYTES);
+    }
+    if (warp == 0) {  // tensor memory: P hi [KS cols] | P lo [KS cols] | two D buffers of 32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = 0;  // a 512-column allocation is the whole tensor memory
+    if (s_tmem_base != 0) __trap();
+
+    // ---- resident operand: lane m of TMEM holds column (cc*128 + m) of P for this CTA's K-slice (hi, then lo)
+    if (warp >= 4) {
+        const int m = tid - 128;
+        const int col = cc * CW + m;
+        const float ca = col < S ? p.cA[col] : 0.f;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp - 4) * 32) << 16);
+#pragma unroll 1
+        for (int k0 = 0; k0 < KS; k0 += 16) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = rank * KS + k0 + i;
+                float v = 0.f;
+                if (k < S && col < S) v = expf(p.A[(int64_t)k * S + col] - ca);
+                hi[i] = cvt_tf32(v);
+                lo[i] = cvt_tf32(v - __uint_as_float(hi[i]));
+            }
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+                    lane_base + (uint32_t)k0),
+                "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]), "r"(hi[8]), "r"(hi[9]),
+                "r"(hi[10]), "r"(hi[11]), "r"(hi[12]), "r"(hi[13]), "r"(hi[14]), "r"(hi[15])
+                : "memory");
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+                    lane_base + (uint32_t)(KS + k0)),
+                "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]), "r"(lo[8]), "r"(lo[9]),
+                "r"(lo[10]), "r"(lo[11]), "r"(lo[12]), "r"(lo[13]), "r"(lo[14]), "r"(lo[15])
+                : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- roles
+    const int ga = tid / NG, pa = tid % NG;        // phase A (tid < NA): chain pair (ga, ga+8), k-step pa
+    const int me = tid - 128;                      // epilogue (warps 4-7): TMEM lane = column me of the cluster's 128
+    // phase C (warps 4 and 5): warp = tile, lane = chain + 16*half; a thread finishes 4 of the 8 columns of its group
+    const bool isC = (warp == 4 || warp == 5);
+    const int ntc = warp & 1, bc = lane & 15, jh = lane >> 4;
+    const int tcc = tid - 128;  // 0..63 for the phase-C threads
+    const int colC = cc * CW + ntc * 64 + rank * 8 + 4 * jh;
+    float caC[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) caC[i] = (colC + i) < S ? p.cA[colC + i] : 0.f;
+    const bool vec_obs = (S % 4) == 0 && (reinterpret_cast<uintptr_t>(p.obs) % 16) == 0;
+    const uint32_t bar_addr0 = smem_u32(&s_bar[0]);
+    const uint32_t mma_bar = smem_u32(&s_mma_bar);
+    // epilogue thread me sends its 16 chain values to the final owner of its column
+    uint32_t r_part_t = 0, r_eref_t = 0, r_bar_t = 0;
+    if (me >= 0) {
+        const uint32_t owner = (uint32_t)((me & 63) >> 3);
+        r_part_t = mapa_u32(smem_u32(&s_part[0][rank][me >> 6][me & 7][0]), owner);
+        r_eref_t = mapa_u32(smem_u32(&s_eref[0][rank][0]), owner);
+        r_bar_t = mapa_u32(bar_addr0, owner);
+    }
+
+    cluster_sync_all();
+
+    unsigned long long* const pkt_set = p.pkt + (size_t)set * 2 * FLOW_CHAINS * SP;
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned nstep = 0, tau = 0;
+    bool aborted = false;
+
+    for (int grp = set; grp < p.groups_total && !aborted; grp += p.nsets) {
+        const int64_t b0 = (int64_t)grp * FLOW_CHAINS;
+        int E_prev = 0, E_abs = 0;
+        bool zero_last = true;
+        float u_last[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool chain_ok = isC && (b0 + bc) < p.B;
+        const float* obs_c = (chain_ok && p.obs && colC < S) ? p.obs + ((b0 + bc) * p.T) * S + colC : nullptr;
+        const uint32_t obs_ring = smem_u32(&s_obs[0][isC ? tcc : 0][0]);
+        auto prefetch_obs = [&](int64_t tt) {
+            if (obs_c && tt < p.T) {
+                const uint32_t dst = obs_ring + (uint32_t)(tt % FLOW_OBS_DEPTH) * (64 * 16);
+                const float* src = obs_c + tt * S;
+                if (vec_obs) cp_async16(dst, src);
+                else
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (colC + i < S) cp_async4(dst + 4 * i, src + i);
+            }
+            cp_async_commit();
+        };
+        if (isC) {
+            float x[4], ones[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                x[i] = -INFINITY;
+                if (chain_ok && colC + i < S) x[i] = (p.init ? p.init[(b0 + bc) * p.init_sb + colC + i] : 0.f) * kLog2e;
+            }
+            int E15, dE;
+            bool zero;
+            flow_finish4(ones, flow_obs_term(x, false), 0, u_last, E15, zero, dE);  // |init| may be large (hand-over of alpha)
+            E_abs = dE;
+            E_prev = E15;
+            zero_last = zero;
+            const unsigned long long stamp = (unsigned long long)(((tau & 0xFFFFu) << 16) | (zero ? 0x8000u : 0u) | (unsigned)E15) << 32;
+            unsigned long long* dst = pkt_set + ((size_t)(tau & 1) * FLOW_CHAINS + bc) * SP + colC;
+            st_pkt2(dst, stamp | __float_as_uint(u_last[0]), stamp | __float_as_uint(u_last[1]));
+            st_pkt2(dst + 2, stamp | __float_as_uint(u_last[2]), stamp | __float_as_uint(u_last[3]));
+        }
+#pragma unroll
+        for (int q = 0; q < FLOW_OBS_DEPTH - 1; ++q) prefetch_obs(q);
+
+        for (int64_t t = 0; t < p.T; ++t) {
+            const int buf = nstep & 1, par = nstep & 1;
+            const unsigned ph = (nstep >> 1) & 1;
+            int timed_out = 0;
+            const long long c_top = p.prof ? clock64() : 0;
+            long long c_pkt = c_top;
+            unsigned char* const tile_hi = s_b + (size_t)(buf * 2 + 0) * TILEB;
+            unsigned char* const tile_lo = s_b + (size_t)(buf * 2 + 1) * TILEB;
+
+            // ================= phase A: fetch the K-slice, align exponents, write the B operand =================
+            if (tid < NA) {
+                constexpr unsigned amask = NA >= 32 ? 0xffffffffu : ((1u << (NA & 31)) - 1u);
+                const unsigned long long* src0 = pkt_set + ((size_t)(tau & 1) * FLOW_CHAINS + ga) * SP + rank * KS + pa * 8;
+                const unsigned long long* src1 = src0 + (size_t)8 * SP;
+                unsigned long long q0[8], q1[8];
+                const unsigned want = tau & 0xFFFFu;
+                const long long start = clock64();
+                for (;;) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        ld_pkt2(src0 + 2 * i, q0[2 * i], q0[2 * i + 1]);
+                        ld_pkt2(src1 + 2 * i, q1[2 * i], q1[2 * i + 1]);
+                    }
+                    bool ok = true;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        ok = ok && ((unsigned)(q0[i] >> 48) == want) && ((unsigned)(q1[i] >> 48) == want);
+                    if (ok) break;
+                    if (clock64() - start > FLOW_SPIN_LIMIT) {
+                        timed_out = 1;
+                        if (atomicCAS(p.abort_flag + 1, 0, 1) == 0) {
+                            p.abort_flag[2] = (int)blockIdx.x;
+                            p.abort_flag[3] = tid;
+                            p.abort_flag[4] = (int)t;
+                            p.abort_flag[5] = (int)want;
+                            p.abort_flag[6] = (int)(q0[0] >> 32);
+                            p.abort_flag[7] = (int)(q1[7] >> 32);
+                        }
+                        break;
+                    }
+                }
+                if (p.prof) c_pkt = clock64();
+                const int e0 = (int)(q0[0] >> 32) & 0xFFFF, e1 = (int)(q1[0] >> 32) & 0xFFFF;
+                const int base_lane = lane & ~(NG - 1);
+                const int ref0 = __shfl_sync(amask, e0, base_lane) & 0x7FFF;
+                const int ref1 = __shfl_sync(amask, e1, base_lane) & 0x7FFF;
+                const int d0 = (e0 & 0x8000) ? -40000 : sext15(e0 - ref0);
+                const int d1 = (e1 & 0x8000) ? -40000 : sext15(e1 - ref1);
+                int m0 = d0, m1 = d1;
+#pragma unroll
+                for (int o = NG / 2; o > 0; o >>= 1) {
+                    m0 = max(m0, __shfl_xor_sync(amask, m0, o));
+                    m1 = max(m1, __shfl_xor_sync(amask, m1, o));
+                }
+                const float sc0 = (d0 == -40000) ? 0.f : pow2i(d0 - m0);
+                const float sc1 = (d1 == -40000) ? 0.f : pow2i(d1 - m1);
+                if (pa == 0) {
+                    s_erefloc[buf][ga] = (m0 == -40000) ? (0x8000 | ref0) : ((ref0 + m0) & 0x7FFF);
+                    s_erefloc[buf][ga + 8] = (m1 == -40000) ? (0x8000 | ref1) : ((ref1 + m1) & 0x7FFF);
+                }
+                // B operand, K-major: k-step pa at pa*STEPB; chunk j (4 k's) at +j*256; 8-row group at +128; row at +16*ga
+                const uint32_t off = (uint32_t)pa * STEPB + (uint32_t)ga * 16;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    uint32_t h0[4], l0[4], h1[4], l1[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float v0 = __uint_as_float((unsigned)q0[4 * j + c]) * sc0;
+                        const float v1 = __uint_as_float((unsigned)q1[4 * j + c]) * sc1;
+                        h0[c] = cvt_tf32(v0);
+                        l0[c] = cvt_tf32(v0 - __uint_as_float(h0[c]));
+                        h1[c] = cvt_tf32(v1);
+                        l1[c] = cvt_tf32(v1 - __uint_as_float(h1[c]));
+                    }
+                    *reinterpret_cast<uint4*>(tile_hi + off + j * 256) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+                    *reinterpret_cast<uint4*>(tile_hi + off + j * 256 + 128) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+                    *reinterpret_cast<uint4*>(tile_lo + off + j * 256) = make_uint4(l0[0], l0[1], l0[2], l0[3]);
+                    *reinterpret_cast<uint4*>(tile_lo + off + j * 256 + 128) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+            }
+            if (__syncthreads_or(timed_out | *(volatile int*)&s_abort)) {
+                aborted = true;
+                break;
+            }
+            const long long c_sync = p.prof ? clock64() : 0;
+            const uint32_t d_tmem = tmem + (uint32_t)(2 * KS + NACC * 16 * (int)(nstep & 1));
+
+            // ================= phase B: one thread issues the MMAs =================
+            if (warp == 0) {  // whole warp, warp-uniform operands; one elected lane issues
+                tc_fence_after();
+                if (nstep & 1) tc_issue_step<KSTEPS, NACC, 1>(smem_u32(s_b), mma_bar);
+                else tc_issue_step<KSTEPS, NACC, 0>(smem_u32(s_b), mma_bar);
+            }
+            // ================= epilogue: D -> registers -> final owners (reduce-scatter over DSMEM) =================
+            if (warp >= 4) {
+                const long long start = clock64();
+                while (!mbar_try_wait(mma_bar, nstep & 1)) {
+                    if (clock64() - start > FLOW_SPIN_LIMIT) {
+                        s_abort = 1;
+                        if (atomicCAS(p.abort_flag + 1, 0, 3) == 0) {
+                            p.abort_flag[2] = (int)blockIdx.x;
+                            p.abort_flag[3] = tid;
+                            p.abort_flag[4] = (int)t;
+                        }
+                        break;
+                    }
+                }
+                tc_fence_after();
+                uint32_t d[16];
+                {
+                    const uint32_t taddr = d_tmem + ((uint32_t)((warp - 4) * 32) << 16);
+                    float acc[16];
+#pragma unroll
+                    for (int a = 0; a < NACC; ++a) {
+                        uint32_t r[16];
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                            : "r"(taddr + (uint32_t)(a * 16))
+                            : "memory");
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) acc[q] = a == 0 ? __uint_as_float(r[q]) : acc[q] + __uint_as_float(r[q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) d[q] = __float_as_uint(acc[q]);
+                }
+                tc_fence_before();
+                const uint32_t r_bar = r_bar_t + (uint32_t)par * 8;
+                const uint32_t dst = r_part_t + (uint32_t)par * (FLOW_CLUSTER * NT * 8 * FLOW_CHAINS * 4);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) st_async_v4(dst + q * 16, d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3], r_bar);
+                if ((me & 71) == 0) {  // column 0 of tile 0 of each owner: also deliver the K-slice exponents
+                    const uint32_t de = r_eref_t + (uint32_t)par * (FLOW_CLUSTER * FLOW_CHAINS * 4);
+                    const uint4* src = reinterpret_cast<const uint4*>(&s_erefloc[buf][0]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 e = src[q];
+                        st_async_v4(de + q * 16, e.x, e.y, e.z, e.w, r_bar);
+                    }
+                }
+            }
+            const long long c_sent = p.prof ? clock64() : 0;
+            if (p.prof && tid == FLOW_THREADS - 1) {
+                prof_acc[0] += c_pkt - c_top;
+                prof_acc[1] += c_sync - c_pkt;
+                prof_acc[2] += c_sent - c_sync;  // mma wait + tcgen05.ld + sends
+            }
+
+            // ================= phase C: final owners finish their columns and publish =================
+            if (isC) {
+                // observation-only work first: it overlaps the flight time of the partial sums
+                cp_async_wait<FLOW_OBS_DEPTH - 2>();
+                float x[4];
+                {
+                    const float4 ob = obs_c ? *reinterpret_cast<const float4*>(&s_obs[t % FLOW_OBS_DEPTH][tcc][0]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float obv[4] = {ob.x, ob.y, ob.z, ob.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = (chain_ok && colC + i < S) ? (obv[i] + caC[i]) * kLog2e : -INFINITY;
+                }
+                const FlowObsTerm oterm = flow_obs_term(x, true);
+                prefetch_obs(t + FLOW_OBS_DEPTH - 1);
+                const long long start = clock64();
+                while (!mbar_try_wait(bar_addr0 + (uint32_t)par * 8, ph)) {
+                    if (clock64() - start > FLOW_SPIN_LIMIT) {
+                        s_abort = 1;
+                        if (atomicCAS(p.abort_flag + 1, 0, 2) == 0) {
+                            p.abort_flag[2] = (int)blockIdx.x;
+                            p.abort_flag[3] = tid;
+                            p.abort_flag[4] = (int)t;
+                        }
+                        break;
+                    }
+                }
+                const long long c_got = p.prof ? clock64() : 0;
+                const int e0 = s_eref[par][0][bc] & 0x7FFF;
+                int dr[FLOW_CLUSTER], dmax = -40000;
+#pragma unroll
+                for (int r = 0; r < FLOW_CLUSTER; ++r) {
+                    const int e = s_eref[par][r][bc];
+                    dr[r] = (e & 0x8000) ? -40000 : sext15(e - e0);
+                    dmax = max(dmax, dr[r]);
+                }
+                float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int r = 0; r < FLOW_CLUSTER; ++r) {
+                    const float w = (dr[r] == -40000) ? 0.f : pow2i(dr[r] - dmax);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sacc[i] = fmaf(s_part[par][r][ntc][4 * jh + i][bc], w, sacc[i]);
+                }
+                const int emax = (dmax == -40000) ? e0 : ((e0 + dmax) & 0x7FFF);
+                // this phase is complete; arm the barrier for the step after next (no sender can be two steps ahead)
+                if (tcc == 0) mbar_arm(bar_addr0 + (uint32_t)par * 8, TX_BYTES);
+                int E15, dE;
+                bool zero;
+                flow_finish4(sacc, oterm, emax, u_last, E15, zero, dE);
+                E_abs += sext15(E15 - E_prev);
+                E_prev = E15;
+                zero_last = zero;
+                const unsigned tn = tau + 1;
+                const unsigned long long stamp = (unsigned long long)(((tn & 0xFFFFu) << 16) | (zero ? 0x8000u : 0u) | (unsigned)E15) << 32;
+                unsigned long long* dst = pkt_set + ((size_t)(tn & 1) * FLOW_CHAINS + bc) * SP + colC;
+                st_pkt2(dst, stamp | __float_as_uint(u_last[0]), stamp | __float_as_uint(u_last[1]));
+                st_pkt2(dst + 2, stamp | __float_as_uint(u_last[2]), stamp | __float_as_uint(u_last[3]));
+                if (p.prof && tcc == 63) {
+                    prof_acc[3] += c_got - c_sent;
+                    prof_acc[4] += clock64() - c_got;
+                }
+            }
+            ++nstep;
+            ++tau;
+        }
+        cp_async_wait<0>();
+        if (chain_ok) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) p.fin_u[(b0 + bc) * SP + colC + i] = u_last[i];
+            if (jh == 0) p.fin_e[(b0 + bc) * (SP / 8) + colC / 8] = zero_last ? INT_MIN : E_abs;
+        }
+        tau += 2;
+    }
+    if (p.prof && tid == FLOW_THREADS - 1) {
+        for (int q = 0; q < 3; ++q) p.prof[(size_t)blockIdx.x * 8 + q] = prof_acc[q];
+        p.prof[(size_t)blockIdx.x * 8 + 5] = (long long)nstep;
+    }
+    if (p.prof && tid == 191) {
+        p.prof[(size_t)blockIdx.x * 8 + 3] = prof_acc[3];
+        p.prof[(size_t)blockIdx.x * 8 + 4] = prof_acc[4];
+    }
+    if (aborted && tid == 0) atomicExch(p.abort_flag, 1);
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 // cA[j] = max(max_i A[i,j], -FLT_MAX) for j < S, 0 in the padding (clamped like numpy_log.py:31-32)
@@ -636,6 +1168,44 @@ static int flow_launch(FlowArgs& a, cudaStream_t stream) {
     return FB2_OK;
 }
 
+template <int KSTEPS>
+static int flow_launch_tc(FlowArgs& a, cudaStream_t stream) {
+    auto kernel = hmm_flow_forward_tc<KSTEPS>;
+    constexpr int NCC = KSTEPS / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(FLOW_THREADS);
+    cfg.dynamicSmemBytes = (size_t)4 * KSTEPS * (512 + 16);
+    FB2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = FLOW_CLUSTER;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    cfg.gridDim = dim3(FLOW_CLUSTER * NCC);
+    int max_clusters = 0;
+    FB2_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
+    int nsets = max_clusters / NCC;
+    if (nsets > FLOW_MAX_SETS) nsets = FLOW_MAX_SETS;
+    if (nsets > a.groups_total) nsets = a.groups_total;
+    if (nsets < 1) {
+        set_error("hmm flow (tcgen05): only %d clusters of %d CTAs can be co-resident, %d needed", max_clusters, FLOW_CLUSTER, NCC);
+        return FB2_ERR_UNSUPPORTED;
+    }
+    a.nsets = nsets;
+    cfg.gridDim = dim3(FLOW_CLUSTER * NCC * nsets);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a);
+    if (getenv("FB2_DEBUG")) fprintf(stderr, "[fb2 flow tc] launch grid %d max_clusters %d -> %s\n", cfg.gridDim.x, max_clusters, cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        set_error("hmm flow (tcgen05) launch failed: %s", cudaGetErrorString(e));
+        return FB2_ERR_CUDA;
+    }
+    count_launch();
+    return FB2_OK;
+}
+
 int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
                             float* logZ, double* logZ_d, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     const FlowShape fs = flow_shape(S);
@@ -668,7 +1238,14 @@ int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, 
     a.prof = (prof_env && prof_env[0] == '1') ? prof : nullptr;
     if (a.prof) FB2_CUDA(cudaMemsetAsync(prof, 0, (size_t)FLOW_PROF_CTAS * 64, stream));
     int st;
-    if (fs.k16 == 1) st = flow_launch<1, 1>(a, stream);
+    const char* legacy_env = getenv("FB2_FLOW_LEGACY");  // 1: mma.sync (HMMA) variant, for A/B measurements
+    const bool legacy = legacy_env && legacy_env[0] == '1';
+    if (!legacy) {
+        if (fs.k16 == 1) st = flow_launch_tc<2>(a, stream);
+        else if (fs.k16 == 2) st = flow_launch_tc<4>(a, stream);
+        else if (fs.k16 == 4) st = flow_launch_tc<8>(a, stream);
+        else st = flow_launch_tc<16>(a, stream);
+    } else if (fs.k16 == 1) st = flow_launch<1, 1>(a, stream);
     else if (fs.k16 == 2) st = flow_launch<2, 1>(a, stream);
     else if (fs.k16 == 4) st = flow_launch<4, 1>(a, stream);
     else st = flow_launch<8, 2>(a, stream);

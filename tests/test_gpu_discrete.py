@@ -382,3 +382,20 @@ def test_hmm_forward_flow_long_chain_stamp_wrap(fb):
     got = fb.hmm_forward(init, A, obs)
     want = torch.logsumexp(init.double(), -1) + (torch.logsumexp(obs.double(), -1) - np.log(S)).sum(-1)
     rel_close(host(got), host(want), rtol=RTOL)
+
+
+def test_hmm_forward_flow_large_magnitude_init(fb):
+    """Hand-over of a message from an earlier chunk: |init| ~ 1e4-1e5 must not hit the block-exponent range."""
+    init, A, obs = _flow_case(5, 40, 300, seed=18)
+    init = init - 65000.0 + torch.arange(5)[:, None] * 30000.0
+    got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    rel_close(got, want, rtol=RTOL, atol=1.0)
+
+
+def test_hmm_forward_flow_unaligned_state_count(fb):
+    """S not a multiple of 4 takes the scalar observation prefetch."""
+    init, A, obs = _flow_case(3, 30, 301, seed=19)
+    got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    rel_close(got, want, rtol=RTOL, atol=1.0)
