@@ -56,6 +56,7 @@ struct FlowArgs {
     int* abort_flag;
     long long* prof;  // nullable: [gridDim][8] accumulated cycles per phase (FB2_FLOW_PROF=1)
     int nsets, groups_total;
+    int mode;  // experiment switches (FB2_FLOW_MODE): 1 publish with atom.exch, 2 poll with ld.volatile, 4 nanosleep in the probe loop
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -486,8 +487,12 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 zero_last = zero;
                 const unsigned tn = tau + 1;
                 const unsigned stamp = ((tn & 0xFFFFu) << 16) | (zero ? 0x8000u : 0u) | (unsigned)E15;
-                st_pkt(pkt_set + ((size_t)(tn & 1) * FLOW_CHAINS + bc) * SP + colC,
-                       ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(u));
+                if (p.mode & 1)
+                    atomicExch(pkt_set + ((size_t)(tn & 1) * FLOW_CHAINS + bc) * SP + colC,
+                               ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(u));
+                else
+                    st_pkt(pkt_set + ((size_t)(tn & 1) * FLOW_CHAINS + bc) * SP + colC,
+                           ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(u));
                 // refill the slot consumed one step ago
                 {
                     const int64_t tn2 = t + FLOW_OBS_DEPTH - 1;
@@ -667,7 +672,7 @@ __device__ __forceinline__ void flow_finish4(const float (&s)[4], const FlowObsT
     E15 = (e_in15 + dE) & 0x7FFF;
 }
 
-template <int KSTEPS>
+template <int KSTEPS, int NACC>
 __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs p) {
     constexpr int KS = KSTEPS * 8;
     constexpr int SP = KSTEPS * 64;
@@ -676,7 +681,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
     constexpr int NCC = SP / 128;
     constexpr int CW = 128;
     constexpr int NT = 2;
-    constexpr int NACC = 4;                // independent TMEM accumulators (2*KS + 2*NACC*16 <= 512 columns)
+    // NACC = independent TMEM accumulators, used round-robin (2*KS + 2*NACC*16 <= 512 columns)
     constexpr int STEPB = 512 + 16;        // bytes between consecutive k-steps of a B tile (+16: conflict-free STS)
     constexpr int TILEB = KSTEPS * STEPB;  // one B tile (hi or lo)
     constexpr uint32_t TX_BYTES = FLOW_CLUSTER * (NT * FLOW_CHAINS * 8 * 4 + FLOW_CHAINS * 4);
@@ -690,6 +695,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
     __shared__ __align__(8) unsigned long long s_mma_bar;
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_abort;
+    __shared__ long long s_ts[8], s_ts2[8];  // FB2_FLOW_PROF: event timestamps of the current step (one SM, one clock)
     __shared__ __align__(16) float s_obs[FLOW_OBS_DEPTH][64][4];  // cp.async ring of obs[b, t, 4 columns], private per phase-C thread
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -828,8 +834,18 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
             const int buf = nstep & 1, par = nstep & 1;
             const unsigned ph = (nstep >> 1) & 1;
             int timed_out = 0;
-            const long long c_top = p.prof ? clock64() : 0;
-            long long c_pkt = c_top;
+            if (p.prof && tid == 0) s_ts[0] = clock64();
+            if (false) {
+                if (nstep > 0) {
+                    prof_acc[0] += s_ts[1] - s_ts[0];  // top -> packets valid
+                    prof_acc[1] += s_ts[2] - s_ts[1];  // align, split, STS, proxy fence, bar.sync
+                    prof_acc[2] += s_ts[3] - s_ts[2];  // MMA issue + commit
+                    prof_acc[3] += s_ts[4] - s_ts[2];  // bar.sync -> accumulators ready (epilogue thread)
+                    prof_acc[4] += s_ts[5] - s_ts[4];  // tcgen05.ld + sends
+                    prof_acc[5] += s_ts[6] - s_ts[5];  // sends -> all partials here
+                    prof_acc[6] += s_ts[7] - s_ts[6];  // reduce, normalise, publish
+                }
+            }
             unsigned char* const tile_hi = s_b + (size_t)(buf * 2 + 0) * TILEB;
             unsigned char* const tile_lo = s_b + (size_t)(buf * 2 + 1) * TILEB;
 
@@ -842,6 +858,18 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
                 const unsigned want = tau & 0xFFFFu;
                 const long long start = clock64();
                 for (;;) {
+                    // light probe first: spin on ONE 16-byte load (the last packets this thread needs) so that the
+                    // 8 CTAs x 128 threads polling the same lines do not flood the L2 slices the producers write to
+                    for (;;) {
+                        if (p.mode & 8) break;
+                        if (p.mode & 2) {
+                            q1[7] = *reinterpret_cast<const volatile unsigned long long*>(src1 + 7);
+                        } else {
+                            ld_pkt2(src1 + 6, q1[6], q1[7]);
+                        }
+                        if ((unsigned)(q1[7] >> 48) == want || clock64() - start > FLOW_SPIN_LIMIT) break;
+                        if (p.mode & 4) __nanosleep(40);
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         ld_pkt2(src0 + 2 * i, q0[2 * i], q0[2 * i + 1]);
@@ -865,7 +893,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
                         break;
                     }
                 }
-                if (p.prof) c_pkt = clock64();
+                if (p.prof && tid == 0) {
+                    s_ts[1] = clock64();
+                }
                 const int e0 = (int)(q0[0] >> 32) & 0xFFFF, e1 = (int)(q1[0] >> 32) & 0xFFFF;
                 const int base_lane = lane & ~(NG - 1);
                 const int ref0 = __shfl_sync(amask, e0, base_lane) & 0x7FFF;
@@ -909,7 +939,20 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
                 aborted = true;
                 break;
             }
-            const long long c_sync = p.prof ? clock64() : 0;
+            if (p.prof && tid == 0) {
+                if (nstep > 0) {  // everybody is past the barrier: the previous step's timeline (s_ts2[]) is complete
+                    prof_acc[2] += s_ts2[3] - s_ts2[2];  // MMA issue + commit
+                    prof_acc[3] += s_ts2[4] - s_ts2[2];  // bar.sync -> accumulators ready (epilogue thread)
+                    prof_acc[4] += s_ts2[5] - s_ts2[4];  // tcgen05.ld + sends
+                    prof_acc[5] += s_ts2[6] - s_ts2[5];  // sends -> all partials here
+                    prof_acc[6] += s_ts2[7] - s_ts2[6];  // reduce, normalise, publish
+                    prof_acc[7] += s_ts[1] - s_ts2[7];   // own publish -> next packets valid (exchange + skew)
+                }
+                prof_acc[0] += s_ts[1] - s_ts[0];  // top -> packets valid
+                s_ts[2] = clock64();
+                prof_acc[1] += s_ts[2] - s_ts[1];  // align, split, STS, proxy fence, bar.sync
+                s_ts2[2] = s_ts[2];
+            }
             const uint32_t d_tmem = tmem + (uint32_t)(2 * KS + NACC * 16 * (int)(nstep & 1));
 
             // ================= phase B: one thread issues the MMAs =================
@@ -917,6 +960,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
                 tc_fence_after();
                 if (nstep & 1) tc_issue_step<KSTEPS, NACC, 1>(smem_u32(s_b), mma_bar);
                 else tc_issue_step<KSTEPS, NACC, 0>(smem_u32(s_b), mma_bar);
+                if (p.prof && tid == 0) s_ts2[3] = clock64();
             }
             // ================= epilogue: D -> registers -> final owners (reduce-scatter over DSMEM) =================
             if (warp >= 4) {
@@ -933,6 +977,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
                     }
                 }
                 tc_fence_after();
+                if (p.prof && tid == 128) s_ts2[4] = clock64();
                 uint32_t d[16];
                 {
                     const uint32_t taddr = d_tmem + ((uint32_t)((warp - 4) * 32) << 16);
@@ -968,12 +1013,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
                     }
                 }
             }
-            const long long c_sent = p.prof ? clock64() : 0;
-            if (p.prof && tid == FLOW_THREADS - 1) {
-                prof_acc[0] += c_pkt - c_top;
-                prof_acc[1] += c_sync - c_pkt;
-                prof_acc[2] += c_sent - c_sync;  // mma wait + tcgen05.ld + sends
-            }
+            if (p.prof && tid == 128) s_ts2[5] = clock64();
 
             // ================= phase C: final owners finish their columns and publish =================
             if (isC) {
@@ -1000,7 +1040,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
                         break;
                     }
                 }
-                const long long c_got = p.prof ? clock64() : 0;
+                if (p.prof && tid == 191) s_ts2[6] = clock64();
                 const int e0 = s_eref[par][0][bc] & 0x7FFF;
                 int dr[FLOW_CLUSTER], dmax = -40000;
 #pragma unroll
@@ -1028,12 +1068,14 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
                 const unsigned tn = tau + 1;
                 const unsigned long long stamp = (unsigned long long)(((tn & 0xFFFFu) << 16) | (zero ? 0x8000u : 0u) | (unsigned)E15) << 32;
                 unsigned long long* dst = pkt_set + ((size_t)(tn & 1) * FLOW_CHAINS + bc) * SP + colC;
-                st_pkt2(dst, stamp | __float_as_uint(u_last[0]), stamp | __float_as_uint(u_last[1]));
-                st_pkt2(dst + 2, stamp | __float_as_uint(u_last[2]), stamp | __float_as_uint(u_last[3]));
-                if (p.prof && tcc == 63) {
-                    prof_acc[3] += c_got - c_sent;
-                    prof_acc[4] += clock64() - c_got;
+                if (p.mode & 1) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) atomicExch(dst + i, stamp | __float_as_uint(u_last[i]));
+                } else {
+                    st_pkt2(dst, stamp | __float_as_uint(u_last[0]), stamp | __float_as_uint(u_last[1]));
+                    st_pkt2(dst + 2, stamp | __float_as_uint(u_last[2]), stamp | __float_as_uint(u_last[3]));
                 }
+                if (p.prof && tid == 191) s_ts2[7] = clock64();
             }
             ++nstep;
             ++tau;
@@ -1046,13 +1088,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
         }
         tau += 2;
     }
-    if (p.prof && tid == FLOW_THREADS - 1) {
-        for (int q = 0; q < 3; ++q) p.prof[(size_t)blockIdx.x * 8 + q] = prof_acc[q];
-        p.prof[(size_t)blockIdx.x * 8 + 5] = (long long)nstep;
-    }
-    if (p.prof && tid == 191) {
-        p.prof[(size_t)blockIdx.x * 8 + 3] = prof_acc[3];
-        p.prof[(size_t)blockIdx.x * 8 + 4] = prof_acc[4];
+    if (p.prof && tid == 0) {
+        for (int q = 0; q < 8; ++q) p.prof[(size_t)blockIdx.x * 8 + q] = prof_acc[q];
+        p.prof[(size_t)(FLOW_PROF_CTAS / 2 + blockIdx.x / 2) * 8 + (blockIdx.x & 1)] = (long long)nstep;
     }
     if (aborted && tid == 0) atomicExch(p.abort_flag, 1);
     tc_fence_before();
@@ -1168,9 +1206,9 @@ static int flow_launch(FlowArgs& a, cudaStream_t stream) {
     return FB2_OK;
 }
 
-template <int KSTEPS>
+template <int KSTEPS, int NACC>
 static int flow_launch_tc(FlowArgs& a, cudaStream_t stream) {
-    auto kernel = hmm_flow_forward_tc<KSTEPS>;
+    auto kernel = hmm_flow_forward_tc<KSTEPS, NACC>;
     constexpr int NCC = KSTEPS / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(FLOW_THREADS);
@@ -1234,17 +1272,23 @@ int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, 
     FlowArgs a{};
     a.init = init; a.init_sb = init_sb; a.A = A; a.obs = obs; a.cA = cA; a.B = B; a.T = T; a.S = S;
     a.pkt = pkt; a.fin_u = fin_u; a.fin_e = fin_e; a.abort_flag = abort_flag; a.groups_total = (int)groups;
+    const char* mode_env = getenv("FB2_FLOW_MODE");
+    a.mode = mode_env ? atoi(mode_env) : 1;  // default: publish packets with atom.exch (store->load hand-over measured ~10 % faster)
     const char* prof_env = getenv("FB2_FLOW_PROF");
     a.prof = (prof_env && prof_env[0] == '1') ? prof : nullptr;
     if (a.prof) FB2_CUDA(cudaMemsetAsync(prof, 0, (size_t)FLOW_PROF_CTAS * 64, stream));
     int st;
-    const char* legacy_env = getenv("FB2_FLOW_LEGACY");  // 1: mma.sync (HMMA) variant, for A/B measurements
-    const bool legacy = legacy_env && legacy_env[0] == '1';
+    // Two implementations of the per-step contraction, same dataflow around them: mma.sync 3xTF32 with P in registers
+    // (default: measured 3.4 us/step at S=1024) and tcgen05 kind::tf32 with P in tensor memory (FB2_FLOW_TC=1: 3.7 us/step;
+    // its shorter MMA phase is hidden behind the DSMEM reduce-scatter, which moves the same 8 KB per CTA-step either way).
+    const char* tc_env = getenv("FB2_FLOW_TC");
+    const bool legacy = !(tc_env && tc_env[0] == '1');
     if (!legacy) {
-        if (fs.k16 == 1) st = flow_launch_tc<2>(a, stream);
-        else if (fs.k16 == 2) st = flow_launch_tc<4>(a, stream);
-        else if (fs.k16 == 4) st = flow_launch_tc<8>(a, stream);
-        else st = flow_launch_tc<16>(a, stream);
+        if (fs.k16 == 1) st = flow_launch_tc<2, 1>(a, stream);
+        else if (fs.k16 == 2) st = flow_launch_tc<4, 1>(a, stream);
+        else if (fs.k16 == 4) st = flow_launch_tc<8, 1>(a, stream);
+        else if (a.mode & 16) st = flow_launch_tc<16, 4>(a, stream);
+        else st = flow_launch_tc<16, 1>(a, stream);
     } else if (fs.k16 == 1) st = flow_launch<1, 1>(a, stream);
     else if (fs.k16 == 2) st = flow_launch<2, 1>(a, stream);
     else if (fs.k16 == 4) st = flow_launch<4, 1>(a, stream);
@@ -1260,7 +1304,19 @@ int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, 
             fprintf(stderr, "[fb2 flow] ABORT=%d first timeout: kind %d (1 packets, 2 partials) cta %d tid %d t %d want %#x saw %#x %#x\n",
                     h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
     }
-    if (a.prof) {  // debugging aid only: synchronises and prints the per-phase cycle averages of a few CTAs
+    if (a.prof && !legacy) {  // debugging aid only: per-step timeline of a few CTAs (tcgen05 variant)
+        static long long h[FLOW_PROF_CTAS * 8];
+        FB2_CUDA(cudaStreamSynchronize(stream));
+        FB2_CUDA(cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int c = 0; c < FLOW_PROF_CTAS / 2; c += 9) {
+            const double n = (double)h[(FLOW_PROF_CTAS / 2 + c / 2) * 8 + (c & 1)] - 1.0;
+            if (n > 0)
+                fprintf(stderr, "[fb2 flow tc prof] cta %3d | top->pkts %.0f  A-proc %.0f | issue %.0f  sync->acc-ready %.0f  ld+send %.0f | "
+                        "send->partials %.0f  C-proc %.0f | publish->next pkts %.0f cycles/step\n",
+                        c, h[c * 8 + 0] / n, h[c * 8 + 1] / n, h[c * 8 + 2] / n, h[c * 8 + 3] / n, h[c * 8 + 4] / n, h[c * 8 + 5] / n,
+                        h[c * 8 + 6] / n, h[c * 8 + 7] / n);
+        }
+    } else if (a.prof) {  // debugging aid only: synchronises and prints the per-phase cycle averages of a few CTAs
         static long long h[FLOW_PROF_CTAS * 8];
         FB2_CUDA(cudaStreamSynchronize(stream));
         FB2_CUDA(cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost));

@@ -328,6 +328,33 @@ def test_hmm_forward_flow_matches_generic_kernel(fb):
     rel_close(z_flow, z_gen, rtol=RTOL, atol=1.0)
 
 
+@pytest.mark.parametrize("B,T,S", [(16, 40, 1024), (5, 33, 65), (40, 25, 257), (3, 90, 160), (2, 300, 100), (4, 20, 130)])
+def test_hmm_forward_flow_tcgen05_variant(fb, B, T, S):
+    """The tcgen05 / tensor-memory implementation of the same dataflow (FB2_FLOW_TC=1), incl. a sparse banded chain."""
+    import os
+
+    init, A, obs = _flow_case(B, T, S, seed=21)
+    if S == 160:  # left-to-right chain with a wide dynamic range
+        A = torch.full((S, S), -float("inf"))
+        for i in range(S):
+            A[i, i] = np.log(0.6)
+            A[i, (i + 1) % S] = np.log(0.4)
+        init = torch.full((B, S), -float("inf"))
+        init[:, 0] = 0.0
+        obs = obs * 3
+    if S == 130:
+        A[:, 64:72] = -float("inf")
+        obs[2, 5, :] = -float("inf")
+    os.environ["FB2_FLOW_TC"] = "1"
+    try:
+        got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    finally:
+        os.environ.pop("FB2_FLOW_TC")
+    want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    assert not np.isnan(got).any()
+    rel_close(got, want, rtol=RTOL, atol=1.0)
+
+
 def test_hmm_forward_flow_extreme_observations(fb):
     """Observation log-likelihoods of magnitude ~1e3 with a spread of hundreds of nats between states
     (continuous-emission HMMs): block exponents absorb them; nothing over- or underflows."""
