@@ -24,6 +24,10 @@ size_t hmm_flow_workspace_bytes(int64_t B, int S);
 int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
                             float* logZ, double* logZ_d, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // FB2_DISABLE_FLOW=1 forces the generic kernel (A/B testing of the two GPU paths)
+static bool stream_disabled() {
+    const char* e = getenv("FB2_DISABLE_STREAM");
+    return e && e[0] == '1';
+}
 static bool flow_disabled() {
     const char* e = getenv("FB2_DISABLE_FLOW");
     return e && e[0] == '1';
@@ -305,6 +309,182 @@ __global__ void __launch_bounds__(256) hmm_forward_generic(HmmArgs p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// max-plus forward, streaming path: shared (time-homogeneous) A, few chains, large S (Viterbi, BASELINE config 3).
+//   delta_t[j] = max_i( delta_{t-1}[i] + (A[i,j] + obs[t,j]) ),  first-index argmax, same fp32 order as the generic path.
+// A no longer fits anywhere on chip (64 MB at S=4096) and is re-read every step, so the step is bound by L2 -> SM
+// bandwidth.  Each CTA owns 32 columns = one 128-byte line per row of A; warp w streams rows w, w+8, ... with 16
+// independent line loads in flight per thread, keeps (best, arg) for R chains in registers (A is read once for all of
+// them), and the 8 warps are combined through shared memory.  One grid barrier per step.
+// A[S,S] row-major -> strips[tile][row][32] (columns beyond S padded with -inf): every CTA then streams ONE contiguous
+// 128*S-byte strip per step instead of 128-byte pieces 4*S bytes apart (DRAM page locality; A does not stay in L2 at
+// S=4096: 64 MB against 2 x 63 MB of die-local L2).
+__global__ void stream_retile_A(const float* A, int S, float* strips) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ntiles = (S + 31) / 32;
+    if (idx >= (int64_t)ntiles * S * 32) return;
+    const int l = (int)(idx & 31);
+    const int64_t r = idx >> 5;
+    const int row = (int)(r % S), tile = (int)(r / S);
+    const int col = tile * 32 + l;
+    strips[idx] = col < S ? A[(int64_t)row * S + col] : kNegInf;
+}
+constexpr int STREAM_WARPS = 8;
+constexpr int STREAM_THREADS = STREAM_WARPS * 32;
+template <int R, bool ARG>
+__global__ void __launch_bounds__(STREAM_THREADS) hmm_maxplus_stream(HmmArgs p) {
+    constexpr int NW = STREAM_WARPS, NTH = STREAM_THREADS;
+    extern __shared__ __align__(16) float smem[];
+    const int S = p.S;
+    float* s_delta = smem;                                     // [R][S]
+    float* s_best = s_delta + (((size_t)R * S + 3) & ~(size_t)3);  // [NW][R][32] (16-byte aligned)
+    int* s_arg = reinterpret_cast<int*>(s_best + NW * R * 32);  // [NW][R][32]
+    float* s_strip = reinterpret_cast<float*>(s_arg + NW * R * 32);  // [keep][32]: the first `keep` rows of this CTA's strip
+    // When every CTA owns exactly one strip, the part of it that fits in the remaining shared memory stays on chip for
+    // the whole pass and only the rest is streamed each step.
+    const int keep = p.W;  // rows resident in shared memory (0 if a CTA serves several strips)
+    if (keep > 0 && (int)blockIdx.x < (S + 31) / 32) {
+        const float4* src = reinterpret_cast<const float4*>(p.A + (size_t)blockIdx.x * S * 32);
+        float4* dst = reinterpret_cast<float4*>(s_strip);
+        for (int idx = threadIdx.x; idx < keep * 8; idx += NTH) dst[idx] = __ldg(src + idx);
+    }
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = (S + 31) / 32;
+    unsigned epoch = 0;
+    unsigned* ctr = p.counters;
+
+    for (int64_t b0 = 0; b0 < p.B; b0 += R) {
+        const int nb = (int)min((int64_t)R, p.B - b0);
+        // ---- delta_{-1} = init -> vec[0]
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+            for (int idx = tid; idx < nb * 32; idx += NTH) {
+                const int r = idx >> 5, j = tile * 32 + (idx & 31);
+                if (j < S) p.vec[(b0 + r) * S + j] = p.init ? p.init[(b0 + r) * p.init_sb + j] : 0.f;
+            }
+        group_barrier(ctr, (++epoch) * gridDim.x, gridDim.x);
+
+        for (int64_t t = 0; t < p.T; ++t) {
+            const float* vin = p.vec + (size_t)(t & 1) * p.B * S;
+            float* vout = p.vec + (size_t)((t + 1) & 1) * p.B * S;
+            for (int idx = tid; idx < R * S; idx += NTH) {
+                const int r = idx / S, i = idx - r * S;
+                s_delta[idx] = (r < nb) ? __ldcg(vin + (b0 + r) * S + i) : kNegInf;
+            }
+            __syncthreads();
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int col = tile * 32 + lane;
+                const bool colok = col < S;
+                float ob[R], best[R];
+                int arg[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    ob[r] = (p.obs && colok && r < nb) ? __ldg(p.obs + ((b0 + r) * p.T + t) * S + col) : 0.f;
+                    best[r] = kNegInf;
+                    arg[r] = warp < S ? warp : 0;
+                }
+                const float* Acol = p.A + (size_t)tile * S * 32 + lane;  // strip-major copy of A: [tile][row][32]
+                int i = warp;
+                for (; i < keep; i += NW * 8) {  // resident rows (keep is a multiple of 8*NW)
+                    float a[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a[u] = s_strip[(i + NW * u) * 32 + lane];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const float v = s_delta[r * S + i + NW * u] + (a[u] + ob[r]);
+                            if (v > best[r]) {
+                                best[r] = v;
+                                arg[r] = i + NW * u;
+                            }
+                        }
+                }
+                for (; i + NW * 15 < S; i += NW * 16) {
+                    float a[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) a[u] = __ldg(Acol + (size_t)(i + NW * u) * 32);
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const float v = s_delta[r * S + i + NW * u] + (a[u] + ob[r]);  // (A + obs) first: hmm.py:130
+                            if (v > best[r]) {
+                                best[r] = v;
+                                arg[r] = i + NW * u;
+                            }
+                        }
+                }
+                for (; i < S; i += NW) {
+                    const float a = __ldg(Acol + (size_t)i * 32);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const float v = s_delta[r * S + i] + (a + ob[r]);
+                        if (v > best[r]) {
+                            best[r] = v;
+                            arg[r] = i;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    s_best[(warp * R + r) * 32 + lane] = best[r];
+                    s_arg[(warp * R + r) * 32 + lane] = arg[r];
+                }
+                __syncthreads();
+                if (tid < R * 32) {
+                    const int r = tid >> 5, l = tid & 31, c = tile * 32 + l;
+                    if (r < nb && c < S) {
+                        float bb = kNegInf;
+                        int aa = 0x7fffffff;
+                        for (int w = 0; w < NW; ++w) {
+                            const float v = s_best[(w * R + r) * 32 + l];
+                            const int ai = s_arg[(w * R + r) * 32 + l];
+                            if (v > bb || (v == bb && ai < aa)) {
+                                bb = v;
+                                aa = ai;
+                            }
+                        }
+                        vout[(b0 + r) * S + c] = bb;
+                        if (ARG) p.backptr[((b0 + r) * p.T + t) * S + c] = aa;
+                        if (p.alpha_all) p.alpha_all[((b0 + r) * p.T + t) * S + c] = bb;
+                    }
+                }
+                __syncthreads();
+            }
+            group_barrier(ctr, (++epoch) * gridDim.x, gridDim.x);
+        }
+        // ---- out[b] = max_j delta_{T-1}[j], first-index argmax
+        if (blockIdx.x == 0) {
+            const float* vfin = p.vec + (size_t)(p.T & 1) * p.B * S;
+            for (int r = warp; r < nb; r += NW) {
+                float m = kNegInf;
+                int arg = 0x7fffffff;
+                for (int j = lane; j < S; j += 32) {
+                    const float v = __ldcg(vfin + (b0 + r) * S + j);
+                    if (v > m || (v == m && j < arg)) {
+                        m = v;
+                        arg = j;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+                    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                    if (om > m || (om == m && oa < arg)) {
+                        m = om;
+                        arg = oa;
+                    }
+                }
+                if (lane == 0) {
+                    p.out[b0 + r] = m;
+                    if (p.last) p.last[b0 + r] = arg;
+                }
+            }
+        }
+        group_barrier(ctr, (++epoch) * gridDim.x, gridDim.x);  // vec[] is reused by the next chains
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward recurrence, generic path (log / max):
 //   beta_{T-1} = final (or one);  beta_{t-1}[i] = (+)_j A_t[i,j] (x) obs[t,j] (x) beta_t[j]
 // CTA c owns rows i in [c*W, c*W+W); one warp per row, lanes stride over j (coalesced rows of A).
@@ -504,16 +684,16 @@ static int make_plan(int64_t B, int S, bool backward, PassPlan* pl) {
 }
 
 template <typename K>
-static int coop_launch(K kernel, const PassPlan& pl, HmmArgs& args, cudaStream_t stream) {
+static int coop_launch(K kernel, const PassPlan& pl, HmmArgs& args, cudaStream_t stream, int threads = 256) {
     FB2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     int per_sm = 0;
-    FB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, pl.smem));
+    FB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, pl.smem));
     if (per_sm * g_sm_count < pl.grid) {
         set_error("hmm pass: grid of %d CTAs cannot be co-resident (%d per SM)", pl.grid, per_sm);
         return FB2_ERR_UNSUPPORTED;
     }
     void* kargs[] = {&args};
-    FB2_CUDA(cudaLaunchCooperativeKernel((void*)kernel, dim3(pl.grid), dim3(256), kargs, pl.smem, stream));
+    FB2_CUDA(cudaLaunchCooperativeKernel((void*)kernel, dim3(pl.grid), dim3(threads), kargs, pl.smem, stream));
     count_launch();
     return FB2_OK;
 }
@@ -563,7 +743,9 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
                        double* out_d = nullptr) {
     PassPlan pl;
     int st = make_plan(B, S, false, &pl);
-    if (st != FB2_OK) return st;
+    const bool stream_ok = semiring == FB2_SEMIRING_MAX && a_sb == 0 && a_st == 0 && cpo == 1 && !final_ && !alpha_last &&
+                           !ell_all && S >= 256 && B <= 64 && !stream_disabled();
+    if (st != FB2_OK && !(stream_ok && st == FB2_ERR_UNSUPPORTED)) return st;
     Arena arena(workspace, workspace_bytes);
     float* vec = arena.take<float>((size_t)2 * B * S);
     unsigned* ctr = arena.take<unsigned>(1024);
@@ -572,6 +754,43 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
         return FB2_ERR_WORKSPACE;
     }
     FB2_CUDA(cudaMemsetAsync(ctr, 0, 1024 * sizeof(unsigned), stream));
+    if (stream_ok) {
+        const size_t strip_elems = (size_t)((S + 31) / 32) * S * 32;
+        float* strips = arena.take<float>(strip_elems);
+        if (!arena.ok()) {
+            set_error("hmm forward (max-plus stream): workspace too small (%zu bytes)", workspace_bytes);
+            return FB2_ERR_WORKSPACE;
+        }
+        stream_retile_A<<<(unsigned)ceil_div((int64_t)strip_elems, 256), 256, 0, stream>>>(A, S, strips);
+        FB2_LAUNCH_CHECK();
+        HmmArgs a{};
+        a.init = init; a.init_sb = init_sb; a.A = strips; a.obs = obs; a.B = B; a.T = T; a.S = S; a.vec = vec; a.counters = ctr;
+        a.alpha_all = alpha_all; a.backptr = backptr; a.out = out; a.last = last;
+        const int R = B >= 4 ? 4 : 1;
+        size_t smem = ((((size_t)R * S + 3) & ~(size_t)3) + 2 * STREAM_WARPS * R * 32) * 4;
+        if (smem <= g_smem_optin) {
+            int ntiles = (S + 31) / 32;
+            int grid = ntiles < g_sm_count ? ntiles : g_sm_count;
+            int keep = 0;
+            if (ntiles <= g_sm_count) {  // one strip per CTA: keep as many of its rows on chip as fit
+                keep = (int)((g_smem_optin - smem - 1024) / 128);
+                if (keep > S) keep = S;
+                keep = keep / (8 * STREAM_WARPS) * (8 * STREAM_WARPS);
+                if (keep < 0) keep = 0;
+            }
+            a.W = keep;
+            smem += (size_t)keep * 128;
+            PassPlan sp{};
+            sp.grid = grid;
+            sp.smem = smem;
+            if (R == 4)
+                return backptr ? coop_launch(hmm_maxplus_stream<4, true>, sp, a, stream, STREAM_THREADS)
+                               : coop_launch(hmm_maxplus_stream<4, false>, sp, a, stream, STREAM_THREADS);
+            return backptr ? coop_launch(hmm_maxplus_stream<1, true>, sp, a, stream, STREAM_THREADS)
+                           : coop_launch(hmm_maxplus_stream<1, false>, sp, a, stream, STREAM_THREADS);
+        }
+        if (st != FB2_OK) return st;
+    }
     HmmArgs a{};
     a.init = init; a.init_sb = init_sb; a.A = A; a.a_sb = a_sb; a.a_st = a_st; a.obs = obs;
     a.B = B; a.T = T; a.S = S; a.vec = vec; a.counters = ctr; a.alpha_all = alpha_all; a.backptr = backptr;
@@ -611,6 +830,7 @@ using namespace fb2;
 extern "C" size_t fb2_hmm_workspace_bytes(int op, int64_t B, int64_t T, int32_t S) {
     size_t base = vec_bytes(B, S) + ctr_bytes() + 512;
     if (op == 0) base += hmm_flow_workspace_bytes(B, S);
+    if (op <= 1 && S >= 256) base += align_up((size_t)((S + 31) / 32) * S * 32 * sizeof(float));  // strip-major copy of A
     if (op == 1) base += align_up((size_t)B * T * S * sizeof(int32_t)) + align_up((size_t)B * sizeof(int32_t));
     if (op == 2) base += align_up((size_t)B * T * S * sizeof(float)) + 2 * align_up((size_t)B * T * 8) + align_up((size_t)B * 8);
     return base;

@@ -426,3 +426,39 @@ def test_hmm_forward_flow_unaligned_state_count(fb):
     got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
     want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
     rel_close(got, want, rtol=RTOL, atol=1.0)
+
+
+# ------------------------------------------------------------------ streaming max-plus kernel (Viterbi, S >= 256, shared A)
+@pytest.mark.parametrize("B,T,S", [(1, 60, 4096), (5, 40, 1000), (4, 25, 257), (2, 33, 300), (9, 7, 512)])
+def test_viterbi_stream_bit_exact(fb, B, T, S):
+    g = torch.Generator().manual_seed(22)
+    init = torch.randn(B, S, generator=g)
+    A = torch.randn(S, S, generator=g)
+    obs = torch.randn(B, T, S, generator=g)
+    if S == 300:  # unreachable states, an impossible observation and exact ties
+        A[:, 7] = -float("inf")
+        A[3, :] = -float("inf")
+        obs[1, 5, 17] = -float("inf")
+        A[:, 40:44] = 0.25
+        obs[:, :, 40:44] = 0.5
+    best, path = fb.hmm_viterbi(init.cuda(), A.cuda(), obs.cuda())
+    wbest, wpath = R.viterbi(init.numpy(), A.numpy(), obs.numpy())  # fp32, same recurrence, first-index ties
+    assert np.array_equal(host(best), wbest)
+    assert np.array_equal(host(path), wpath)
+    z, alpha = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda(), sum_op="max", return_alpha=True)
+    assert np.array_equal(host(z), wbest)
+
+
+def test_viterbi_stream_matches_generic_kernel(fb):
+    import os
+
+    g = torch.Generator().manual_seed(23)
+    B, T, S = 3, 50, 640
+    init, A, obs = torch.randn(B, S, generator=g), torch.randn(S, S, generator=g), torch.randn(B, T, S, generator=g)
+    best, path = fb.hmm_viterbi(init.cuda(), A.cuda(), obs.cuda())
+    os.environ["FB2_DISABLE_STREAM"] = "1"
+    try:
+        gbest, gpath = fb.hmm_viterbi(init.cuda(), A.cuda(), obs.cuda())
+    finally:
+        os.environ.pop("FB2_DISABLE_STREAM")
+    assert np.array_equal(host(best), host(gbest)) and np.array_equal(host(path), host(gpath))
