@@ -56,7 +56,7 @@ struct FlowArgs {
     int* abort_flag;
     long long* prof;  // nullable: [gridDim][8] accumulated cycles per phase (FB2_FLOW_PROF=1)
     int nsets, groups_total;
-    int mode;  // experiment switches (FB2_FLOW_MODE): 1 publish with atom.exch, 2 poll with ld.volatile, 4 nanosleep in the probe loop
+    int mode;  // experiment switches (FB2_FLOW_MODE): 1 publish with atom.exch (default), 2/4 sleep 0.5/1 us before polling, 16 four staggered probes
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -126,6 +126,37 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// Wait until the packet pair at `addr` carries stamp `want`.  Four probe loads are kept in flight a quarter of a
+// hand-over apart (one L2 store->load hand-over is ~936 cycles, scripts/microbench/pingpong.cu), so a new packet is
+// seen ~230 cycles after it lands instead of up to a full round trip later.  The step time is the maximum over all
+// polling threads of the chip, so this quantisation was paid in full on every step.
+__device__ __forceinline__ void spin_cycles(int n) {
+    const long long c = clock64();
+    while (clock64() - c < n) {
+    }
+}
+__device__ __forceinline__ bool probe_wait(const unsigned long long* addr, unsigned want, long long start) {
+    unsigned long long a0, b0, a1, b1, a2, b2, a3, b3;
+    ld_pkt2(addr, a0, b0);
+    if ((unsigned)(b0 >> 48) == want) return true;
+    spin_cycles(200);
+    ld_pkt2(addr, a1, b1);
+    spin_cycles(200);
+    ld_pkt2(addr, a2, b2);
+    spin_cycles(200);
+    ld_pkt2(addr, a3, b3);
+    for (;;) {
+        if ((unsigned)(b0 >> 48) == want) return true;
+        ld_pkt2(addr, a0, b0);
+        if ((unsigned)(b1 >> 48) == want) return true;
+        ld_pkt2(addr, a1, b1);
+        if ((unsigned)(b2 >> 48) == want) return true;
+        ld_pkt2(addr, a2, b2);
+        if ((unsigned)(b3 >> 48) == want) return true;
+        ld_pkt2(addr, a3, b3);
+        if (clock64() - start > FLOW_SPIN_LIMIT) return false;
+    }
 }
 __device__ __forceinline__ int sext15(int x) { return (int)((unsigned)x << 17) >> 17; }
 __device__ __forceinline__ float pow2i(int d) {  // 2^d for d <= 0, flushed to 0 below 2^-126
@@ -320,7 +351,10 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 unsigned long long q0[8], q1[8];
                 const unsigned want = tau & 0xFFFFu;
                 const long long start = clock64();
+                if (p.mode & 2) __nanosleep(500);
+                if (p.mode & 4) __nanosleep(1000);
                 for (;;) {
+                    if (p.mode & 16) probe_wait(src1 + 6, want, start);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         ld_pkt2(src0 + 2 * i, q0[2 * i], q0[2 * i + 1]);
@@ -860,16 +894,15 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
                 for (;;) {
                     // light probe first: spin on ONE 16-byte load (the last packets this thread needs) so that the
                     // 8 CTAs x 128 threads polling the same lines do not flood the L2 slices the producers write to
-                    for (;;) {
-                        if (p.mode & 8) break;
-                        if (p.mode & 2) {
-                            q1[7] = *reinterpret_cast<const volatile unsigned long long*>(src1 + 7);
-                        } else {
+                    // light probe first: spin on ONE 16-byte load (the last packets this thread needs); measured faster
+                    // than polling all eight loads and than keeping several staggered probes in flight (mode 16), which
+                    // load the L2 slices the producers are writing to
+                    if (p.mode & 16) probe_wait(src1 + 6, want, start);
+                    else
+                        for (;;) {
                             ld_pkt2(src1 + 6, q1[6], q1[7]);
+                            if ((unsigned)(q1[7] >> 48) == want || clock64() - start > FLOW_SPIN_LIMIT) break;
                         }
-                        if ((unsigned)(q1[7] >> 48) == want || clock64() - start > FLOW_SPIN_LIMIT) break;
-                        if (p.mode & 4) __nanosleep(40);
-                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         ld_pkt2(src0 + 2 * i, q0[2 * i], q0[2 * i + 1]);
