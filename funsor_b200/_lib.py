@@ -30,7 +30,8 @@ SIGNATURES = {
     "fb2_status_string": (c_char_p, [c_int]),
     "fb2_last_error": (c_char_p, []),
     "fb2_device_query": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
-    "fb2_semiring_matmul_f32": (c_int, [c_int, _fp, _i64p, _fp, _i64p, _fp, _fp, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),
+    "fb2_semiring_matmul_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
+    "fb2_semiring_matmul_f32": (c_int, [c_int, _fp, _i64p, _fp, _i64p, _fp, _fp, c_int64, c_int64, c_int32, c_int32, c_int32, _fp, c_size_t, c_void_p]),
     "fb2_chain_product_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "fb2_chain_product_f32": (c_int, [c_int, _fp, _i64p, c_int64, c_int64, c_int32, _fp, _fp, c_size_t, c_void_p]),
     "fb2_hmm_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64, c_int32]),

@@ -1,0 +1,350 @@
+// Log-semiring batched matmul on the 5th-generation tensor cores (tcgen05, accumulators in tensor memory).
+//
+// Reference semantics: Contraction[Logaddexp, Add, Tensor, Tensor] funsor/cnf.py:335-379 ->
+// einsum/numpy_log.py:24-47 for the scan-level equation `abcd,abde->abce`:
+//     out[n,i,j] = (sx[n,i] + sy[n,j]) + log sum_k exp(x[n,i,k] - sx[n,i]) * exp(y[n,k,j] - sy[n,j])
+// with sx / sy the row / column maxima clamped to finfo.min.  The exp is applied while the operands are
+// staged into shared memory, the inner contraction is a plain GEMM and runs as 3xTF32
+// (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM), the log and the shifts are the epilogue.
+//
+// One CTA = one 128 x 128 output tile of one batch element.  K is consumed in chunks of 32:
+//   warps 0-3 stage X (one row per thread: exp, TF32 hi/lo split, K-major canonical layout),
+//   warps 4-7 stage Y (4 x 8 patches, exp, split, register transpose into the same K-major canonical layout),
+//   after a proxy fence + barrier one elected lane issues the 12 MMAs (4 k-steps x 3 products) of the chunk and
+//   commits them to the buffer's mbarrier; staging of the next chunk overlaps the tensor pipe (2 buffers).
+// Epilogue: all 8 warps read their quarter of the accumulator lanes with tcgen05.ld, apply log + shifts, store.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace fb2 {
+
+constexpr int LM_TILE = 128;
+constexpr int LM_KC = 32;                               // K per staged chunk
+constexpr int LM_OPB = LM_TILE * LM_KC * 4;             // bytes of one operand tile (hi or lo): 16 KB
+constexpr int LM_STAGEB = 4 * LM_OPB;                   // A hi, A lo, B hi, B lo
+constexpr int LM_STAGES = 2;
+constexpr int LM_SMEM = LM_STAGES * LM_STAGEB + 1024;   // + alignment slack
+
+struct LogMatmulArgs {
+    const float* x;
+    const float* y;
+    const float* sx;  // [n, I] clamped row maxima of x
+    const float* sy;  // [n, J] clamped column maxima of y
+    float* out;
+    int64_t n1, os0;
+    int64_t xs0, xs1, xsi;  // xsk == 1
+    int64_t ys0, ys1, ysk;  // ysj == 1
+    int I, K, J;
+    int mode;  // FB2_LM_MODE experiments: 1 = stage only the first two chunks, 2 = do not issue MMAs
+};
+
+__device__ __forceinline__ uint32_t lm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// TF32 "hi" part by truncation (a LOP3 on the ALU pipe; cvt.rna.tf32 is a quarter-rate conversion and two of them per
+// element made the staging XU-bound).  lo = x - hi is exact in fp32 and the tensor core itself ignores its low 13 bits,
+// so hi + lo carries 21+ mantissa bits either way.
+__device__ __forceinline__ uint32_t lm_tf32(float x) { return __float_as_uint(x) & 0xffffe000u; }
+// K-major operand tile in the 128-byte-swizzle canonical layout: row r (an output row of X / an output column of Y) at
+// r * 128 B, its eight 16-byte k-chunks XOR-swizzled with (r % 8); 8-row groups 1024 B apart (SBO); one staged chunk of
+// K = 32 TF32 is exactly one swizzle row, and a K = 8 instruction advances the start address by 32 B.  (The no-swizzle
+// "interleave" layout was measured first: ~600 cycles per 128x128x8 MMA, i.e. shared-memory-bound.)
+__device__ __forceinline__ uint64_t lm_desc(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void lm_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t lm_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+
+// sx[n,i] = max(max_k x[n,i,k], -FLT_MAX): one warp per row (k contiguous)
+__global__ void lm_rowmax(const float* x, int64_t n1, int64_t xs0, int64_t xs1, int64_t xsi, int I, int K, int64_t rows, float* sx) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (row >= rows) return;
+    const int lane = threadIdx.x % 32;
+    const int64_t n = row / I;
+    const int i = (int)(row % I);
+    const float* p = x + (n / n1) * xs0 + (n % n1) * xs1 + (int64_t)i * xsi;
+    float m = -FLT_MAX;
+    for (int k = lane; k < K; k += 32) m = fmaxf(m, p[k]);
+    m = warp_max(m);
+    if (lane == 0) sx[row] = m;
+}
+// sy[n,j] = max(max_k y[n,k,j], -FLT_MAX): threads over j (contiguous), 8-way split of k, combined through shared memory
+__global__ void lm_colmax(const float* y, int64_t n1, int64_t ys0, int64_t ys1, int64_t ysk, int K, int J, float* sy) {
+    __shared__ float red[8][32];
+    const int64_t n = blockIdx.y;
+    const int j = blockIdx.x * 32 + threadIdx.x % 32;
+    const int part = threadIdx.x / 32;
+    const float* p = y + (n / n1) * ys0 + (n % n1) * ys1 + j;
+    float m = -FLT_MAX;
+    if (j < J)
+        for (int k = part; k < K; k += 8) m = fmaxf(m, p[(int64_t)k * ysk]);
+    red[part][threadIdx.x % 32] = m;
+    __syncthreads();
+    if (part == 0 && j < J) {
+#pragma unroll
+        for (int q = 1; q < 8; ++q) m = fmaxf(m, red[q][threadIdx.x]);
+        sy[n * J + j] = m;
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
+    extern __shared__ unsigned char lm_smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar[LM_STAGES];
+    __shared__ __align__(8) unsigned long long s_done;
+    __shared__ uint32_t s_tmem;
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(lm_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n = blockIdx.z;
+    const int i0 = blockIdx.y * LM_TILE, j0 = blockIdx.x * LM_TILE;
+    const int64_t b0 = n / a.n1, b1 = n % a.n1;
+    const float* xb = a.x + b0 * a.xs0 + b1 * a.xs1;
+    const float* yb = a.y + b0 * a.ys0 + b1 * a.ys1;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < LM_STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lm_smem_u32(&s_bar[s])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lm_smem_u32(&s_done)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(lm_smem_u32(&s_tmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    // ---- per-thread staging role
+    // X (warps 0-3): thread t owns k-chunk kc = t % 8 of rows t/8 + 16 m (m = 0..7): a warp instruction reads 4 full
+    //   128-byte lines.  Y (warps 4-7): thread t owns k = 4 kq .. 4 kq + 3 (kq = t % 8) of the chunk and columns
+    //   8 jq .. 8 jq + 7 (jq = t / 8): a warp instruction reads 8 full lines; the 4 x 8 patch is transposed in registers.
+    // Global loads for chunk c+1 are issued right after chunk c has been written to shared memory (register prefetch).
+    const bool stage_x = warp < 4;
+    const int t = tid & 127;
+    const int kc = t & 7, rbase = t >> 3;
+    const int kq = t & 7, jq = t >> 3;
+    float shift[8];  // X: sx of the thread's 8 rows;  Y: sy of its 8 columns
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        if (stage_x) {
+            const int row = i0 + rbase + 16 * m;
+            shift[m] = row < a.I ? a.sx[n * a.I + row] : 0.f;
+        } else {
+            const int j = j0 + jq * 8 + m;
+            shift[m] = j < a.J ? a.sy[n * a.J + j] : 0.f;
+        }
+    }
+    const bool x_vec = (a.xsi % 4 == 0) && (reinterpret_cast<uintptr_t>(xb) % 16 == 0);
+    const bool y_vec = (a.ysk % 4 == 0) && (reinterpret_cast<uintptr_t>(yb) % 16 == 0);
+
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);  // A, B K-major
+    const int nchunks = (a.K + LM_KC - 1) / LM_KC;
+
+    float4 pre[8];  // prefetched raw values of the next chunk
+    auto load_chunk = [&](int c) {
+        const int k0 = c * LM_KC;
+        if (stage_x) {
+            const int k = k0 + kc * 4;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int row = i0 + rbase + 16 * m;
+                const float* p = xb + (int64_t)(row < a.I ? row : 0) * a.xsi + k;
+                if (row < a.I && k + 3 < a.K && x_vec) {
+                    pre[m] = __ldg(reinterpret_cast<const float4*>(p));
+                } else {
+                    float v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = (row < a.I && k + q < a.K) ? __ldg(p + q) : -INFINITY;
+                    pre[m] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = k0 + kq * 4 + kk;
+                const float* p = yb + (int64_t)(k < a.K ? k : 0) * a.ysk + j0 + jq * 8;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = j0 + jq * 8 + h * 4;
+                    if (k < a.K && j + 3 < a.J && y_vec) {
+                        pre[kk * 2 + h] = __ldg(reinterpret_cast<const float4*>(p + h * 4));
+                    } else {
+                        float v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) v[q] = (k < a.K && j + q < a.J) ? __ldg(p + h * 4 + q) : -INFINITY;
+                        pre[kk * 2 + h] = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                }
+            }
+        }
+    };
+    load_chunk(0);
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int s = c % LM_STAGES;
+        unsigned char* stage = smem + (size_t)s * LM_STAGEB;
+        // the MMAs that read this buffer LM_STAGES chunks ago must have completed
+        if (c >= LM_STAGES && !(a.mode & 2)) {
+            const uint32_t parity = ((c / LM_STAGES) - 1) & 1;
+            while (!lm_try_wait(lm_smem_u32(&s_bar[s]), parity)) {
+            }
+        }
+        if ((a.mode & 1) && c >= LM_STAGES) {
+        } else if (stage_x) {
+            // A operand: 16-byte k-chunk kc of row r at  r * 128 + ((kc ^ (r % 8)) * 16)
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int r = rbase + 16 * m;
+                const float v[4] = {pre[m].x, pre[m].y, pre[m].z, pre[m].w};
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float e = __expf(v[q] - shift[m]);
+                    hi[q] = lm_tf32(e);
+                    lo[q] = __float_as_uint(e - __uint_as_float(hi[q]));
+                }
+                unsigned char* dst = stage + r * 128 + ((kc ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(dst + LM_OPB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        } else {
+            // B operand (same layout as A with j in the role of the row): column j = 8 jq + q, chunk kq at
+            // j * 128 + ((kq ^ q) * 16); the eight threads of a quarter warp differ in kq, i.e. hit eight different bank groups.
+            unsigned char* Bh = stage + 2 * LM_OPB + jq * 1024;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float4 pv = pre[kk * 2 + (q >> 2)];
+                    const float raw = (q & 3) == 0 ? pv.x : (q & 3) == 1 ? pv.y : (q & 3) == 2 ? pv.z : pv.w;
+                    const float e = __expf(raw - shift[q]);
+                    hi[kk] = lm_tf32(e);
+                    lo[kk] = __float_as_uint(e - __uint_as_float(hi[kk]));
+                }
+                unsigned char* dst = Bh + q * 128 + ((kq ^ q) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(dst + LM_OPB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        if (c + 1 < nchunks) load_chunk(c + 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t elected;
+            asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(elected));
+            if (elected && !((a.mode & 2) && c < nchunks - 1)) {
+                const uint32_t ah = lm_smem_u32(stage), al = ah + LM_OPB, bh = ah + 2 * LM_OPB, bl = ah + 3 * LM_OPB;
+#pragma unroll
+                for (int ks = 0; ks < LM_KC / 8; ++ks) {
+                    const uint64_t dah = lm_desc(ah + ks * 32), dal = lm_desc(al + ks * 32);
+                    const uint64_t dbh = lm_desc(bh + ks * 32), dbl = lm_desc(bl + ks * 32);
+                    lm_mma(tmem, dah, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                    lm_mma(tmem, dal, dbh, IDESC, 1u);
+                    lm_mma(tmem, dah, dbl, IDESC, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(lm_smem_u32(&s_bar[s])) : "memory");
+                if (c == nchunks - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(lm_smem_u32(&s_done)) : "memory");
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- epilogue: warp w reads lanes 32*(w%4).. and columns [64*(w/4), +64)
+    while (!lm_try_wait(lm_smem_u32(&s_done), 0)) {
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        const int row = i0 + (warp & 3) * 32 + lane;
+        const int cbase = (warp >> 2) * 64;
+        const float sxo = row < a.I ? a.sx[n * a.I + row] : 0.f;
+        float* orow = a.out + b0 * a.os0 + b1 * (int64_t)a.I * a.J + (int64_t)row * a.J;
+#pragma unroll
+        for (int cc = 0; cc < 64; cc += 16) {
+            uint32_t d[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]),
+                  "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
+                : "r"(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cbase + cc))
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < a.I) {
+                const int jb = j0 + cbase + cc;
+                float o[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) o[q] = (sxo + ((jb + q) < a.J ? __ldg(a.sy + n * a.J + jb + q) : 0.f)) + __logf(__uint_as_float(d[q]));
+                if (jb + 15 < a.J && (a.J % 4 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 16 == 0)) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(orow + jb + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        if (jb + q < a.J) orow[jb + q] = o[q];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+}
+
+// Returns FB2_ERR_UNSUPPORTED when the shapes / strides do not fit this kernel (caller falls back to the SIMT tile kernel).
+int launch_log_matmul_tc(const float* x, const int64_t* xs, const float* y, const int64_t* ys, float* out, int64_t n0, int64_t n1, int I,
+                         int K, int J, int64_t out_s0, float* sx_sy_workspace, cudaStream_t stream) {
+    if (xs[3] != 1 || ys[3] != 1 || I < 64 || J < 64 || K < 32 || sx_sy_workspace == nullptr) return FB2_ERR_UNSUPPORTED;
+    const int64_t n = n0 * n1;
+    if (n <= 0 || n > 65535) return FB2_ERR_UNSUPPORTED;
+    float* sx = sx_sy_workspace;
+    float* sy = sx + n * I;
+    const int64_t rows = n * I;
+    lm_rowmax<<<(unsigned)ceil_div(rows, 8), 256, 0, stream>>>(x, n1, xs[0], xs[1], xs[2], I, K, rows, sx);
+    FB2_LAUNCH_CHECK();
+    lm_colmax<<<dim3((unsigned)ceil_div(J, 32), (unsigned)n), 256, 0, stream>>>(y, n1, ys[0], ys[1], ys[2], K, J, sy);
+    FB2_LAUNCH_CHECK();
+    LogMatmulArgs a;
+    a.x = x; a.y = y; a.sx = sx; a.sy = sy; a.out = out; a.n1 = n1;
+    a.os0 = out_s0 >= 0 ? out_s0 : n1 * (int64_t)I * J;
+    a.xs0 = xs[0]; a.xs1 = xs[1]; a.xsi = xs[2];
+    a.ys0 = ys[0]; a.ys1 = ys[1]; a.ysk = ys[2];
+    a.I = I; a.K = K; a.J = J;
+    {
+        const char* m = getenv("FB2_LM_MODE");
+        a.mode = m ? atoi(m) : 0;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)ceil_div(J, LM_TILE), (unsigned)ceil_div(I, LM_TILE), (unsigned)n);
+    log_matmul_tc<<<grid, 256, LM_SMEM, stream>>>(a);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
+size_t log_matmul_tc_workspace_floats(int64_t n, int I, int J) { return (size_t)n * ((size_t)I + (size_t)J); }
+
+}  // namespace fb2

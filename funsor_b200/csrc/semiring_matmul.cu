@@ -1,6 +1,8 @@
 // Strided batched semiring matmul (one scan level) and the chain product built from it.
 // Reference semantics: funsor/cnf.py:335-379 -> einsum/numpy_log.py:24-47 (LOG),
 // cnf.py:312-324 -> tensor.py:700-726,313-330 (MAX), sum_product.py:690-701 (tree order).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fb2 {
@@ -192,10 +194,23 @@ __global__ void __launch_bounds__(256) semiring_matmul_tiled(MatmulArgs a) {
     }
 }
 
+// log_matmul_tc.cu: tcgen05 path for the log semiring (needs (n0*n1)*(I+J) floats of scratch for the shifts)
+int launch_log_matmul_tc(const float* x, const int64_t* xs, const float* y, const int64_t* ys, float* out, int64_t n0, int64_t n1, int I,
+                         int K, int J, int64_t out_s0, float* sx_sy_workspace, cudaStream_t stream);
+size_t log_matmul_tc_workspace_floats(int64_t n, int I, int J);
+static bool tc_matmul_disabled() {
+    const char* e = getenv("FB2_DISABLE_TC_MATMUL");
+    return e && e[0] == '1';
+}
+
 int launch_semiring_matmul(int semiring, const float* x, const int64_t* xs, const float* y, const int64_t* ys,
                            float* out, int32_t* argk, int64_t n0, int64_t n1, int I, int K, int J,
-                           cudaStream_t stream, int64_t out_s0 = -1) {
+                           cudaStream_t stream, int64_t out_s0 = -1, float* shift_ws = nullptr) {
     if (n0 * n1 == 0 || I == 0 || J == 0) return FB2_OK;
+    if (semiring == FB2_SEMIRING_LOG && shift_ws != nullptr && !tc_matmul_disabled()) {
+        int st = launch_log_matmul_tc(x, xs, y, ys, out, n0, n1, I, K, J, out_s0, shift_ws, stream);
+        if (st != FB2_ERR_UNSUPPORTED) return st;
+    }
     MatmulArgs a;
     a.x = x; a.y = y; a.out = out; a.argk = argk; a.n1 = n1;
     a.os0 = out_s0 >= 0 ? out_s0 : n1 * (int64_t)I * J;
@@ -254,9 +269,15 @@ int launch_copy_matrices(const float* src, int64_t sb, int64_t si, int64_t sj, f
 
 using namespace fb2;
 
+extern "C" size_t fb2_semiring_matmul_workspace_bytes(int64_t n0, int64_t n1, int32_t I, int32_t K, int32_t J) {
+    (void)K;
+    return align_up(log_matmul_tc_workspace_floats(n0 * n1, I, J) * sizeof(float)) + 256;
+}
+
 extern "C" int fb2_semiring_matmul_f32(int semiring, const float* x, const int64_t x_strides[4], const float* y,
                                        const int64_t y_strides[4], float* out, int32_t* argk, int64_t n0,
-                                       int64_t n1, int32_t I, int32_t K, int32_t J, void* stream) {
+                                       int64_t n1, int32_t I, int32_t K, int32_t J, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
     int st = check_device();
     if (st != FB2_OK) return st;
     FB2_REQUIRE(semiring == FB2_SEMIRING_LOG || semiring == FB2_SEMIRING_MAX, "unknown semiring %d", semiring);
@@ -264,8 +285,11 @@ extern "C" int fb2_semiring_matmul_f32(int semiring, const float* x, const int64
                 (long long)n0, (long long)n1, I, K, J);
     FB2_REQUIRE(x && y && out, "null pointer");
     FB2_REQUIRE(!(argk && semiring != FB2_SEMIRING_MAX), "argk is only defined for the max-plus semiring");
+    float* shift_ws = nullptr;
+    if (workspace != nullptr && workspace_bytes >= log_matmul_tc_workspace_floats(n0 * n1, I, J) * sizeof(float))
+        shift_ws = static_cast<float*>(workspace);
     return launch_semiring_matmul(semiring, x, x_strides, y, y_strides, out, argk, n0, n1, I, K, J,
-                                  static_cast<cudaStream_t>(stream));
+                                  static_cast<cudaStream_t>(stream), -1, shift_ws);
 }
 
 static void level_sizes(int64_t T, int64_t* t1, int64_t* t2) {
@@ -277,7 +301,8 @@ extern "C" size_t fb2_chain_product_workspace_bytes(int64_t B, int64_t T, int32_
     int64_t t1, t2;
     level_sizes(T, &t1, &t2);
     size_t per = (size_t)S * S * sizeof(float);
-    return align_up((size_t)B * t1 * per) + align_up((size_t)B * t2 * per) + 256;
+    return align_up((size_t)B * t1 * per) + align_up((size_t)B * t2 * per) +
+           align_up(log_matmul_tc_workspace_floats(B * (T / 2 > 0 ? T / 2 : 1), S, S) * sizeof(float)) + 256;
 }
 
 extern "C" int fb2_chain_product_f32(int semiring, const float* trans, const int64_t ts[4], int64_t B, int64_t T,
@@ -297,6 +322,7 @@ extern "C" int fb2_chain_product_f32(int semiring, const float* trans, const int
     float* buf[2];
     buf[0] = arena.take<float>((size_t)B * t1 * per);
     buf[1] = arena.take<float>((size_t)B * t2 * per);
+    float* shift_ws = arena.take<float>(log_matmul_tc_workspace_floats(B * (T / 2 > 0 ? T / 2 : 1), S, S));
     if (!arena.ok()) {
         set_error("chain_product: workspace too small (%zu bytes given)", workspace_bytes);
         return FB2_ERR_WORKSPACE;
@@ -314,7 +340,7 @@ extern "C" int fb2_chain_product_f32(int semiring, const float* trans, const int
         int64_t xs[4] = {cs[0], 2 * cs[1], cs[2], cs[3]};
         int64_t ys[4] = {cs[0], 2 * cs[1], cs[2], cs[3]};
         // products go to dst[b, 0:half]; an odd leftover cur[b, d-1] goes to dst[b, half] (sum_product.py:696-698)
-        st = launch_semiring_matmul(semiring, cur, xs, cur + cs[1], ys, dst, nullptr, B, half, S, S, S, stream, dst_sb);
+        st = launch_semiring_matmul(semiring, cur, xs, cur + cs[1], ys, dst, nullptr, B, half, S, S, S, stream, dst_sb, shift_ws);
         if (st != FB2_OK) return st;
         if (nd != half) {
             st = launch_copy_matrices(cur + (d - 1) * cs[1], cs[0], cs[2], cs[3], dst + half * per, dst_sb, B, S, stream);

@@ -79,9 +79,10 @@ def semiring_matmul(sum_op, prod_op, x, y, want_argmax=False):
     out = torch.empty((n0, n1, I, J), dtype=torch.float32, device=x.device)
     arg = torch.empty((n0, n1, I, J), dtype=torch.int32, device=x.device) if want_argmax else None
     lib = _lib.load()
+    ws = _workspace(lib.fb2_semiring_matmul_workspace_bytes(n0, n1, I, K, J), x.device)
     with torch.cuda.device(x.device):
         check(lib.fb2_semiring_matmul_f32(semi, x.data_ptr(), strides4(x.stride()), y.data_ptr(), strides4(y.stride()),
-                                          out.data_ptr(), _ptr(arg), n0, n1, I, K, J, _stream()))
+                                          out.data_ptr(), _ptr(arg), n0, n1, I, K, J, ws.data_ptr(), ws.numel(), _stream()))
     out = out.reshape(batch + (I, J))
     return (out, arg.reshape(batch + (I, J))) if want_argmax else out
 

@@ -51,10 +51,13 @@ int fb2_device_query(int device, int* sm_count, int* cc_major, int* cc_minor, si
  * x, y are arbitrary strided views (the reference passes even/odd time slices);
  * out is contiguous [n0,n1,I,J].  LOG uses the reference's clamped row/column max shifts.
  * argk (nullable, MAX only): int32 [n0,n1,I,J], first maximising k (approximations.py:115-127).
+ * workspace (nullable): scratch for the LOG shifts; when given, contiguous-k / contiguous-j operands with
+ * I, J >= 64 and K >= 32 run on the tcgen05 tensor cores (3xTF32, fp32-class accuracy), otherwise on CUDA cores.
  */
+size_t fb2_semiring_matmul_workspace_bytes(int64_t n0, int64_t n1, int32_t I, int32_t K, int32_t J);
 int fb2_semiring_matmul_f32(int semiring, const float* x, const int64_t x_strides[4], const float* y,
                             const int64_t y_strides[4], float* out, int32_t* argk, int64_t n0, int64_t n1,
-                            int32_t I, int32_t K, int32_t J, void* stream);
+                            int32_t I, int32_t K, int32_t J, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (2) Chain product over time -- the whole scan.

@@ -60,7 +60,7 @@ def test_device_entry_points_fail_loudly_without_gpu(lib):
     from funsor_b200 import _lib
 
     arr = (ctypes.c_int64 * 4)(1, 1, 1, 1)
-    st = lib.fb2_semiring_matmul_f32(0, 8, arr, 8, arr, 8, None, 1, 1, 1, 1, 1, None)
+    st = lib.fb2_semiring_matmul_f32(0, 8, arr, 8, arr, 8, None, 1, 1, 1, 1, 1, None, 0, None)
     assert st == _lib.ERR_NO_DEVICE
     with pytest.raises(_lib.Fb2Error):
         _lib.check(st)

@@ -462,3 +462,36 @@ def test_viterbi_stream_matches_generic_kernel(fb):
     finally:
         os.environ.pop("FB2_DISABLE_STREAM")
     assert np.array_equal(host(best), host(gbest)) and np.array_equal(host(path), host(gpath))
+
+
+# ------------------------------------------------------------------ tcgen05 log-semiring matmul (log_matmul_tc.cu)
+@pytest.mark.parametrize("shape", [(1, 1, 128, 128, 128), (2, 3, 128, 64, 128), (1, 2, 200, 100, 130), (3, 1, 64, 33, 64),
+                                   (1, 1, 257, 260, 129), (1, 1, 512, 1000, 384)])
+def test_log_matmul_tensor_core_path(fb, shape):
+    """Contiguous operands with I, J >= 64 and K >= 32 take the tcgen05 kernel (3 launches: row max, column max, GEMM);
+    values must hold the fp32 tolerance, including -inf rows / columns."""
+    n0, n1, I, K, J = shape
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(n0, n1, I, K, generator=g) * 3
+    y = torch.randn(n0, n1, K, J, generator=g) * 3
+    x[0, 0, 3, :] = -float("inf")  # a row that contributes nothing
+    y[0, 0, :, 5] = -float("inf")
+    x[0, 0, 7, ::2] = -float("inf")
+    fb.launch_count(reset=True)
+    got = fb.semiring_matmul("logaddexp", "add", x.cuda(), y.cuda())
+    assert fb.launch_count() == 3
+    want = R.pair_product(R.LOG, x.double().numpy(), y.double().numpy())
+    assert not np.isnan(host(got)).any()
+    rel_close(host(got), want, rtol=RTOL, atol=1.0)
+
+
+def test_log_matmul_tensor_core_strided_views(fb):
+    """Even/odd time views (what one scan level passes, sum_product.py:692-694) stay zero-copy on the tcgen05 path."""
+    g = torch.Generator().manual_seed(32)
+    trans = torch.randn(2, 9, 128, 128, generator=g).cuda()
+    x, y = trans[:, 0:8:2], trans[:, 1:8:2]
+    fb.launch_count(reset=True)
+    got = fb.semiring_matmul("logaddexp", "add", x, y)
+    assert fb.launch_count() == 3
+    want = R.pair_product(R.LOG, host(x).astype(np.float64), host(y).astype(np.float64))
+    rel_close(host(got), want, rtol=RTOL, atol=1.0)
