@@ -244,7 +244,9 @@ def main():
     hbm_bytes = (obs.numel() + A.numel() + init.numel()) * 4
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops"],
                 "traffic": None, "kernel": "hmm_flow_forward<8,2>", "kernel_ms": kernel_ms, "peak_source": peaks["src"],
-                "algorithmic_flops_per_launch": flops,
+                "algorithmic_flops_per_launch": flops, "us_per_time_step": kernel_ms * 1e3 / T,
+                "note": "T dependent steps of a [16x1024]x[1024x1024] product: latency-bound (one L2 hand-over is 936 cycles "
+                        "measured, plus a DSMEM reduce per step), DESIGN.md section 3; dram traffic = algorithmic (profiles/)",
                 "hbm": {"achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
                         "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": hbm_bytes}}
     cpu = None
@@ -305,13 +307,52 @@ def extra_measurements(device):
     out["kalman_scan"] = {"steps_per_s": Bk * Tk / sec, "D": D, "O": O, "B": Bk, "T": Tk, "ms": sec * 1e3,
                           "note": "Gaussian scan over dense info-form elements (C4 shape at reduced T)"}
     del w, P, s, Lam, eta, c
-    # dense chain product (literal sequential_sum_product semantics), S=1024
+    # dense chain product (literal sequential_sum_product semantics), S=1024: tcgen05 3xTF32 log-matmul per level
     Bd, Td, Sd = 4, 64, 1024
     trans = torch.randn(Bd, Td, Sd, Sd, device=device, generator=g)
     sec = timeit(lambda: fb.sequential_sum_product("logaddexp", "add", trans), n=2)
-    out["dense_chain_log"] = {"pair_products_per_s": Bd * (Td - 1) / sec, "tflops_fp32": 2.0 * Bd * (Td - 1) * Sd ** 3 / sec / 1e12,
-                              "B": Bd, "T": Td, "S": Sd, "ms": sec * 1e3}
+    tf = 2.0 * Bd * (Td - 1) * Sd ** 3 / sec / 1e12
+    out["dense_chain_log"] = {"pair_products_per_s": Bd * (Td - 1) / sec, "useful_tflops": tf, "B": Bd, "T": Td, "S": Sd, "ms": sec * 1e3,
+                              "kernel": "log_matmul_tc (tcgen05 kind::tf32, 3 products per useful flop)",
+                              "roofline": {"bound": "tensor", "achieved": 3 * tf, "peak": peaks_tf32(), "unit": "TFLOP/s (tf32 issued)",
+                                           "frac": 3 * tf / peaks_tf32()}}
+    sec = timeit(lambda: fb.sequential_sum_product("max", "add", trans), n=1)
+    out["dense_chain_max"] = {"pair_products_per_s": Bd * (Td - 1) / sec, "fp32_tflops": 2.0 * Bd * (Td - 1) * Sd ** 3 / sec / 1e12,
+                              "ms": sec * 1e3, "kernel": "semiring_matmul_tiled<MAX> (CUDA cores: max-plus has no tensor-core form)"}
+    del trans
+    # Viterbi (C3 shape at reduced T): S=4096, B=1, bit-exact max-plus forward + back-pointers + backtrace
+    Sv, Tv = 4096, 2048
+    Av = torch.randn(Sv, Sv, device=device, generator=g)
+    ov = torch.randn(1, Tv, Sv, device=device, generator=g)
+    iv = torch.randn(1, Sv, device=device, generator=g)
+    sec = timeit(lambda: fb.hmm_viterbi(iv, Av, ov), n=2)
+    out["viterbi"] = {"units_per_s": Tv * Sv * Sv / sec, "us_per_step": sec * 1e6 / Tv, "S": Sv, "B": 1, "T": Tv, "ms": sec * 1e3,
+                      "kernel": "hmm_maxplus_stream<1,true>",
+                      "roofline": {"bound": "hbm", "achieved": 4.0 * Sv * Sv * Tv / sec / 1e9, "peak": hbm_peak(), "unit": "GB/s",
+                                   "frac": 4.0 * Sv * Sv * Tv / sec / 1e9 / hbm_peak(),
+                                   "note": "algorithmic bytes = A re-read every step (64 MB does not stay in the die-local L2); "
+                                           "achieved can exceed DRAM traffic because ~40 % of each strip stays in shared memory"}}
+    del Av, ov, iv
+    # forward-backward marginals (C5 shape at reduced T): S=512, B=1
+    Sm, Tm = 512, 8192
+    Am = torch.randn(Sm, Sm, device=device, generator=g).log_softmax(-1)
+    om = torch.randn(1, Tm, Sm, device=device, generator=g)
+    im = torch.randn(1, Sm, device=device, generator=g).log_softmax(-1)
+    sec = timeit(lambda: fb.hmm_marginals(im, Am, om, want_xi=False), n=2)
+    out["marginals"] = {"units_per_s": 2.0 * Tm * Sm * Sm / sec, "us_per_step": sec * 1e6 / Tm, "S": Sm, "B": 1, "T": Tm, "ms": sec * 1e3,
+                        "note": "forward + backward + gamma (xi_sum off), generic cooperative kernels"}
+    sec = timeit(lambda: fb.hmm_forward(im, Am, om), n=2)
+    out["forward_S512_B1"] = {"units_per_s": Tm * Sm * Sm / sec, "us_per_step": sec * 1e6 / Tm, "ms": sec * 1e3, "kernel": "hmm_flow_forward<4,1>"}
     return out
+
+
+def peaks_tf32():
+    # no measured TF32 figure in MEASURED_PEAKS.json: half of the measured sustained bf16 rate (TF32 is half-rate on B200)
+    return measured_peaks()["tflops"] / 2.0
+
+
+def hbm_peak():
+    return measured_peaks()["hbm_gbs"]
 
 
 if __name__ == "__main__":
