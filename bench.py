@@ -127,7 +127,8 @@ def run_reference(args, wl, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "T": wl["T"], "S": wl["S"], "B_per_gpu": wl["B"], "reference_sample_T": T_sample},
+        "config": {"workload": args.workload, "T": wl["T"], "S": wl["S"], "B_per_gpu": wl["B"], "layout": "factored A[S,S] + obs[B,T,S]",
+                   "parallelism": "host threads", "reference_sample_T": T_sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": samples[0]["cores"], "kind": "port", "sample": samples[0]["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
