@@ -1,12 +1,16 @@
 """Eager patterns that route funsor's Markov-chain sum-product path to the sm_100a kernels.
 
-This is the drop-in boundary on the reference side.  `register()` adds three
+This is the drop-in boundary on the reference side.  `register()` adds these
 more-specific rules to funsor's `eager` interpretation for the torch backend:
 
   Contraction[Logaddexp, Add, frozenset, Tensor, Tensor]   replaces funsor/cnf.py:335-340
   Contraction[Max,       Add, frozenset, Tensor, Tensor]   beats the generic funsor/cnf.py:312-324
   MarkovProduct[Logaddexp|Max, Add, Tensor, Variable, frozenset, frozenset]
                                                            beats funsor/sum_product.py:1049-1064
+  MarkovProduct[Logaddexp, Add, Gaussian | GaussianMixture, Variable, frozenset, frozenset]
+                                                           the Gaussian scan (gaussian.py:841-1132 per level) as ONE
+                                                           information-form chain kernel; the result is converted back
+                                                           to the reference's (white_vec, prec_sqrt) + Tensor form
 
 A rule takes the CUDA path only when its operands are float32 CUDA tensors with scalar output shape and
 the contraction has matrix-product structure; in every other case it calls the handler that was
@@ -91,6 +95,57 @@ def markov_named(trans, names, time, prev, curr, semiring, chain):
     return out.permute([cur.index(n) for n in want]), want
 
 
+def gaussian_markov_named(white_vec, prec_sqrt, scalar, bint_names, real_blocks, time, prev, curr, chain):
+    """Scan of Gaussian chain elements in the reference's sqrt form (funsor/gaussian.py:419-498).
+
+    white_vec[bints..., rank], prec_sqrt[bints..., dim, rank]; the leading dims are the bint inputs `bint_names`
+    (one of them `time`), the rows of prec_sqrt are the real inputs concatenated in `real_blocks` order
+    [(name, size), ...] (gaussian.py:133-151), which must be exactly {prev, curr} with equal sizes D.
+    scalar: None or a tensor over the same bint dims (the Tensor half of a `Tensor + Gaussian` element).
+    chain(w[B,T,r], P[B,T,2D,r], s[B,T]) -> (Lam[B,2D,2D], eta[B,2D], c[B]) over rows (prev; curr).
+    Returns (Lam, eta, c, batch_names) with the batch dims in their original order."""
+    bint_names = list(bint_names)
+    names = [n for n, _ in real_blocks]
+    sizes = dict(real_blocks)
+    if sorted(names) != sorted([prev, curr]) or sizes[prev] != sizes[curr]:
+        return None
+    D = sizes[prev]
+    batch = [n for n in bint_names if n != time]
+    perm = [bint_names.index(n) for n in batch + [time]]
+    nb = len(bint_names)
+    w = white_vec.permute(perm + [nb])
+    P = prec_sqrt.permute(perm + [nb, nb + 1])
+    if names[0] != prev:  # rows are (curr; prev): swap the two blocks
+        P = torch.cat([P[..., D:, :], P[..., :D, :]], dim=-2)
+    bshape = tuple(w.shape[:-2])
+    T, r = w.shape[-2], w.shape[-1]
+    if scalar is None:
+        s = w.new_zeros(bshape + (T,))
+    else:
+        s = scalar.permute(perm).expand(bshape + (T,))
+    Bflat = 1
+    for d in bshape:
+        Bflat *= d
+    Lam, eta, c = chain(w.reshape(Bflat, T, r), P.reshape(Bflat, T, 2 * D, r), s.reshape(Bflat, T))
+    return Lam.reshape(bshape + (2 * D, 2 * D)), eta.reshape(bshape + (2 * D,)), c.reshape(bshape), batch
+
+
+def info_to_sqrt(Lam, eta, c):
+    """(Lam, eta, c) -> the reference's (white_vec, prec_sqrt, scalar) triple.  The precision of a chain product is
+    positive SEMI-definite in general (transition factors are rank deficient), so the square root
+    is taken through an eigendecomposition rather than a Cholesky factor: P = V sqrt(l), w = sqrt(l)^-1 V' eta on the
+    range of Lam.  A [B, 2D, 2D] problem once per scan (not T-sized); float64 on whatever device the inputs live on."""
+    lam, V = torch.linalg.eigh(Lam.double())
+    tol = lam.amax(-1, keepdim=True).clamp(min=0) * (Lam.shape[-1] * 1e-7 if Lam.dtype == torch.float32 else 1e-13)
+    keep = lam > tol
+    root = torch.where(keep, lam.clamp(min=0).sqrt(), torch.zeros_like(lam))
+    P = V * root[..., None, :]
+    proj = (V.transpose(-1, -2) @ eta.double()[..., None])[..., 0]
+    w = torch.where(keep, proj / torch.where(keep, root, torch.ones_like(root)), torch.zeros_like(proj))
+    s = c.double() + 0.5 * (w * w).sum(-1)
+    return w.to(Lam.dtype), P.to(Lam.dtype), s.to(Lam.dtype)
+
+
 # ------------------------------------------------------------------------------------------------
 # kernel entry points used by the rules
 def _kernel_matmul(semiring, x, y):
@@ -103,6 +158,13 @@ def _kernel_chain(semiring, t):
     from . import ops
 
     return ops.sequential_sum_product(semiring, "add", t)
+
+
+def _kernel_gaussian_chain(w, P, s):
+    from . import gaussian as fg
+
+    Lam, eta, c = fg.sqrt_to_info(w.contiguous(), P.contiguous(), s.contiguous())
+    return fg.gaussian_sequential_sum_product(Lam, eta, c)
 
 
 def _fast_ok(*datas):
@@ -181,6 +243,61 @@ def register():
 
     for op_t in (fops.LogaddexpOp, fops.MaxOp):
         eager.register(MarkovProduct, op_t, fops.AddOp, Tensor, Variable, frozenset, frozenset)(markov_rule)
+
+    # ---- Gaussian chain elements: MarkovProduct[Logaddexp, Add, Gaussian | Tensor + Gaussian, ...]
+    from funsor.cnf import GaussianMixture
+    from funsor.domains import Reals
+    from funsor.gaussian import Gaussian
+
+    def _split_gaussian(trans):
+        """(scalar Tensor or None, Gaussian) of a chain element, or None if it is neither form."""
+        if isinstance(trans, Gaussian):
+            return None, trans
+        if isinstance(trans, Contraction) and len(trans.terms) == 2 and not trans.reduced_vars:
+            t, g = trans.terms
+            if isinstance(t, Tensor) and isinstance(g, Gaussian) and t.dtype == "real" and not t.shape:
+                return t, g
+        return None
+
+    def gaussian_markov_rule(sum_op, prod_op, trans, time, step, step_names):
+        parts = _split_gaussian(trans)
+        if parts is not None and len(step) == 1:
+            t, g = parts
+            ((prev, curr),) = tuple(step)
+            bints = [(k, d) for k, d in g.inputs.items() if d.dtype != "real"]
+            reals = [(k, d.num_elements) for k, d in g.inputs.items() if d.dtype == "real"]
+            ok = (_fast_ok(g.white_vec, g.prec_sqrt) and time.name in dict(bints)
+                  and all(len(g.inputs[k].shape) == 1 for k, _ in reals) and max(n for _, n in reals) <= 32)
+            scalar = None
+            if ok and t is not None:
+                ok = _fast_ok(t.data) and set(t.inputs) <= set(k for k, _ in bints)
+                if ok:  # broadcast the Tensor half over the Gaussian's bint dims
+                    tdims = list(t.inputs)
+                    data = t.data.permute([tdims.index(k) for k, _ in bints if k in tdims])
+                    shape = [d.size if k in tdims else 1 for k, d in bints]
+                    scalar = data.reshape(shape).expand([d.size for _, d in bints])
+            if ok:
+                res = gaussian_markov_named(g.white_vec, g.prec_sqrt, scalar, [k for k, _ in bints], reals, time.name, prev, curr,
+                                            _kernel_gaussian_chain)
+                if res is not None:
+                    Lam, eta, c, batch = res
+                    w, P, s = info_to_sqrt(Lam, eta, c)
+                    D = dict(reals)[prev]
+                    binputs = OrderedDict((k, g.inputs[k]) for k in batch)
+                    ginputs = binputs.copy()
+                    ginputs[prev] = Reals[D]
+                    ginputs[curr] = Reals[D]
+                    result = Tensor(s, binputs) + Gaussian(white_vec=w, prec_sqrt=P, inputs=ginputs)
+                    _STATE["calls"]["markov_fast"] += 1
+                    return Subs(result, step_names)
+        _STATE["calls"]["markov_delegated"] += 1
+        return prev_markov_gauss(sum_op, prod_op, trans, time, step, step_names)
+
+    sg = Gaussian(white_vec=torch.zeros(2, 2), prec_sqrt=torch.eye(2).expand(2, 2, 2).contiguous(),
+                  inputs=OrderedDict(time=Bint[2], prev=Reals[1], curr=Reals[1]))
+    prev_markov_gauss = eager.dispatch(MarkovProduct, fops.logaddexp, fops.add, sg, tv, step, names)
+    eager.register(MarkovProduct, fops.LogaddexpOp, fops.AddOp, Gaussian, Variable, frozenset, frozenset)(gaussian_markov_rule)
+    eager.register(MarkovProduct, fops.LogaddexpOp, fops.AddOp, GaussianMixture, Variable, frozenset, frozenset)(gaussian_markov_rule)
 
     _STATE["registered"] = True
 

@@ -144,3 +144,103 @@ def test_rules_register_and_delegate_on_cpu_tensors(funsor):
         assert isinstance(after[k], Tensor), (k, type(after[k]))
         assert tuple(after[k].inputs) == tuple(before[k].inputs)
         assert torch.allclose(after[k].data, before[k].data, rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------ Gaussian chain elements
+def _oracle_gaussian_chain(w, P, s):
+    from oracle import gaussian_ref as G
+
+    Lam, eta, c = G.sqrt_to_info(w.double().numpy(), P.double().numpy(), s.double().numpy())
+    D = P.shape[-2] // 2
+    Lo, eo, co = G.chain_info(Lam, eta, c, D)
+    return torch.from_numpy(Lo), torch.from_numpy(eo), torch.from_numpy(co)
+
+
+def _info_of(funsor, result, names, D):
+    """(Lam, eta, c) of a `Tensor + Gaussian` funsor over real inputs `names` (as oracle/make_golden.py does)."""
+    from funsor.cnf import Contraction
+    from funsor.domains import Reals
+    from funsor.gaussian import Gaussian
+    from funsor.tensor import Tensor
+
+    terms = result.terms if isinstance(result, Contraction) else (result,)
+    (g,) = [t for t in terms if isinstance(t, Gaussian)]
+    reals = [k for k, d in g.inputs.items() if d.dtype == "real"]
+    assert sorted(reals) == sorted(names)
+    perm = torch.cat([torch.arange(D) + D * reals.index(n) for n in names])
+    zero = {n: funsor.to_funsor(torch.zeros(D), Reals[D]) for n in names}
+    c = result(**zero)
+    assert isinstance(c, Tensor)
+    bnames = [k for k, d in g.inputs.items() if d.dtype != "real"]
+    Lam = g._precision[..., perm, :][..., :, perm]
+    eta = g._info_vec[..., perm]
+    return Lam, eta, c.align(tuple(bnames)).data
+
+
+@pytest.mark.parametrize("order", [("b", "time", "prev", "curr"), ("time", "b", "curr", "prev"), ("time", "prev", "curr")])
+@pytest.mark.parametrize("T,D", [(1, 1), (3, 2), (8, 2), (11, 3)])
+def test_gaussian_markov_named_matches_reference_scan(funsor, order, T, D):
+    import funsor.ops as ops
+    from funsor.domains import Bint, Reals
+    from funsor.sum_product import sequential_sum_product
+    from funsor.terms import Variable
+    from funsor.testing import random_gaussian
+
+    from funsor_b200.funsor_plugin import gaussian_markov_named, info_to_sqrt
+
+    torch.manual_seed(3)
+    doms = dict(b=Bint[2], time=Bint[T], prev=Reals[D], curr=Reals[D])
+    g = random_gaussian(OrderedDict((n, doms[n]) for n in order))
+    want = sequential_sum_product(ops.logaddexp, ops.add, g, Variable("time", Bint[T]), {"prev": "curr"})
+    wLam, weta, wc = _info_of(funsor, want, ["prev", "curr"], D)
+    bints = [n for n in order if n in ("b", "time")]
+    reals = [(n, D) for n in order if n in ("prev", "curr")]
+    Lam, eta, c, batch = gaussian_markov_named(g.white_vec, g.prec_sqrt, None, bints, reals, "time", "prev", "curr", _oracle_gaussian_chain)
+    assert batch == [n for n in bints if n != "time"]
+    assert torch.allclose(Lam, wLam, rtol=1e-8, atol=1e-8)
+    assert torch.allclose(eta, weta, rtol=1e-8, atol=1e-8)
+    assert torch.allclose(c, wc, rtol=1e-8, atol=1e-8)
+    # and back to the reference's representation: the (w, P, s) triple must describe the same function
+    w, P, s = info_to_sqrt(Lam, eta, c)
+    assert torch.allclose(P @ P.transpose(-1, -2), wLam, rtol=1e-7, atol=1e-7)
+    assert torch.allclose((P @ w[..., None])[..., 0], weta, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(s - 0.5 * (w * w).sum(-1), wc, rtol=1e-7, atol=1e-7)
+
+
+def test_info_to_sqrt_handles_singular_precision(funsor):
+    from funsor_b200.funsor_plugin import info_to_sqrt
+
+    torch.manual_seed(4)
+    A = torch.randn(3, 6, 2, dtype=torch.float64)  # rank 2 of 6
+    Lam = A @ A.transpose(-1, -2)
+    eta = (A @ torch.randn(3, 2, 1, dtype=torch.float64))[..., 0]  # in the range of Lam
+    c = torch.randn(3, dtype=torch.float64)
+    w, P, s = info_to_sqrt(Lam, eta, c)
+    assert torch.allclose(P @ P.transpose(-1, -2), Lam, atol=1e-10)
+    assert torch.allclose((P @ w[..., None])[..., 0], eta, atol=1e-9)
+    assert torch.allclose(s - 0.5 * (w * w).sum(-1), c, atol=1e-10)
+
+
+def test_gaussian_rule_delegates_on_cpu(funsor):
+    import funsor.ops as ops
+    from funsor.domains import Bint, Reals
+    from funsor.sum_product import MarkovProduct
+    from funsor.terms import Variable
+    from funsor.testing import random_gaussian
+
+    from funsor_b200 import funsor_plugin
+
+    torch.manual_seed(5)
+    inputs = OrderedDict(b=Bint[2], time=Bint[5], prev=Reals[2], curr=Reals[2])
+    g1, g2 = random_gaussian(inputs), None
+    tv = Variable("time", Bint[5])
+    before = MarkovProduct(ops.logaddexp, ops.add, g1, tv, {"prev": "curr"})
+    funsor_plugin.register()
+    funsor_plugin.stats(reset=True)
+    from funsor.gaussian import Gaussian
+
+    g2 = Gaussian(white_vec=g1.white_vec.clone(), prec_sqrt=g1.prec_sqrt.clone(), inputs=g1.inputs)
+    after = MarkovProduct(ops.logaddexp, ops.add, g2, tv, {"prev": "curr"})
+    assert funsor_plugin.stats()["markov_delegated"] >= 1 and funsor_plugin.stats()["markov_fast"] == 0
+    for x, y in zip(_info_of(funsor, before, ["prev", "curr"], 2), _info_of(funsor, after, ["prev", "curr"], 2)):
+        assert torch.allclose(x, y, rtol=1e-10, atol=1e-10)

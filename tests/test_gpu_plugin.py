@@ -59,3 +59,39 @@ def test_markov_named_kernel(sname, order):
     want = R.chain_product(R.LOG if sname == "logaddexp" else R.MAX, canon)
     got = got.permute([names.index(n) for n in batch + ["prev", "curr"]])
     rel_close(got.cpu().numpy(), want, rtol=1e-5, atol=1.0)
+
+
+@pytest.mark.parametrize("order", [("b", "time", "prev", "curr"), ("time", "b", "curr", "prev"), ("time", "prev", "curr")])
+@pytest.mark.parametrize("T,D", [(1, 2), (9, 3), (40, 8), (17, 32)])
+def test_gaussian_markov_named_kernel(order, T, D):
+    """The Gaussian MarkovProduct rule's tensor logic with the real kernels (sqrt->info, scan) against the numpy oracle,
+    then back to the reference's sqrt representation."""
+    from funsor_b200.funsor_plugin import _kernel_gaussian_chain, gaussian_markov_named, info_to_sqrt
+    from oracle import gaussian_ref as G
+
+    g = torch.Generator().manual_seed(7)
+    sizes = dict(b=3, time=T)
+    bints = [n for n in order if n in sizes]
+    reals = [(n, D) for n in order if n in ("prev", "curr")]
+    bshape = [sizes[n] for n in bints]
+    n = 2 * D
+    P = torch.randn(*bshape, n, n, generator=g) / n ** 0.5 + 0.7 * torch.eye(n)
+    w = torch.randn(*bshape, n, generator=g)
+    s = torch.randn(*bshape, generator=g)
+    Lam, eta, c, batch = gaussian_markov_named(w.cuda(), P.cuda(), s.cuda(), bints, reals, "time", "prev", "curr", _kernel_gaussian_chain)
+    # oracle on canonical layout [B, T, ...], rows (prev; curr)
+    perm = [bints.index(x) for x in batch + ["time"]]
+    wc = w.permute(perm + [len(bints)]).double().numpy()
+    Pc = P.permute(perm + [len(bints), len(bints) + 1]).double()
+    if reals[0][0] != "prev":
+        Pc = torch.cat([Pc[..., D:, :], Pc[..., :D, :]], dim=-2)
+    sc = s.permute(perm).double().numpy()
+    wL, we, wcc = G.sqrt_to_info(wc, Pc.numpy(), sc)
+    wL, we, wcc = G.chain_info(wL.reshape(-1, T, n, n), we.reshape(-1, T, n), wcc.reshape(-1, T), D)
+    shape = tuple(sizes[x] for x in batch)
+    rel_close(Lam.cpu().numpy(), wL.reshape(shape + (n, n)), rtol=2e-4, atol=1.0)
+    rel_close(eta.cpu().numpy(), we.reshape(shape + (n,)), rtol=2e-4, atol=1.0)
+    rel_close(c.cpu().numpy(), wcc.reshape(shape), rtol=1e-5, atol=1.0)
+    w2, P2, s2 = info_to_sqrt(Lam, eta, c)
+    assert torch.allclose(P2 @ P2.transpose(-1, -2), Lam, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(s2 - 0.5 * (w2 * w2).sum(-1), c, rtol=1e-5, atol=1e-3)
