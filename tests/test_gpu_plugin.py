@@ -91,7 +91,7 @@ def test_gaussian_markov_named_kernel(order, T, D):
     shape = tuple(sizes[x] for x in batch)
     rel_close(Lam.cpu().numpy(), wL.reshape(shape + (n, n)), rtol=2e-4, atol=1.0)
     rel_close(eta.cpu().numpy(), we.reshape(shape + (n,)), rtol=2e-4, atol=1.0)
-    rel_close(c.cpu().numpy(), wcc.reshape(shape), rtol=1e-5, atol=1.0)
+    rel_close(c.cpu().numpy(), wcc.reshape(shape), rtol=1e-5, atol=float(T * D))  # c sums T terms of magnitude ~D
     w2, P2, s2 = info_to_sqrt(Lam, eta, c)
     assert torch.allclose(P2 @ P2.transpose(-1, -2), Lam, rtol=1e-4, atol=1e-4)
     assert torch.allclose(s2 - 0.5 * (w2 * w2).sum(-1), c, rtol=1e-5, atol=1e-3)
