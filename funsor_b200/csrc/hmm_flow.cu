@@ -54,6 +54,14 @@ struct FlowArgs {
     float* fin_u;             // [groups*16][Sp] final mantissas
     int* fin_e;               // [groups*16][Sp/8] final absolute exponents (INT_MIN = zero group)
     int* abort_flag;
+    // optional history of the messages after every step (forward-backward): mantissas [B][hist_T][Sp] and absolute block
+    // exponents [B][hist_T][Sp/8] (INT_MIN = zero group)
+    float* hist_u;
+    int* hist_e;
+    int64_t hist_T;
+    int64_t obs_T;   // time extent of the obs array (rows per chain); the pass runs p.T steps over obs rows [0, p.T)
+    int transpose;   // 1: contract with A^T (backward pass)
+    int reverse;     // 1: step t consumes obs row p.T-1-t and writes history slot p.T-1-t
     long long* prof;  // nullable: [gridDim][8] accumulated cycles per phase (FB2_FLOW_PROF=1)
     int nsets, groups_total;
     int mode;  // experiment switches (FB2_FLOW_MODE): 1 publish with atom.exch (default), 2/4 sleep 0.5/1 us before polling, 16 four staggered probes
@@ -272,7 +280,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
             for (int h = 0; h < 2; ++h) {
                 const int k = rank * KS + ks * 8 + 2 * tig + h;
                 float v = 0.f;
-                if (k < S && col < S) v = expf(p.A[(int64_t)k * S + col] - ca);
+                if (k < S && col < S) v = expf((p.transpose ? p.A[(int64_t)col * S + k] : p.A[(int64_t)k * S + col]) - ca);
                 const uint32_t hi = cvt_tf32(v);
                 Ph[nt][ks][h] = hi;
                 lo2[h] = (v - __uint_as_float(hi)) * kScalePl;
@@ -310,7 +318,8 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
         bool zero_last = true;
         float u_last = 0.f;
         const bool chain_ok = tc >= 0 && (b0 + bc) < p.B && colC < S;
-        const float* obs_c = (chain_ok && p.obs) ? p.obs + ((b0 + bc) * p.T) * S + colC : nullptr;
+        const float* obs_c = (chain_ok && p.obs) ? p.obs + ((b0 + bc) * p.obs_T) * S + colC : nullptr;
+        auto obs_row = [&](int64_t step) { return p.reverse ? (p.T - 1 - step) : step; };
 
         // ---- message before the first step: alpha_{-1} = init
         if (tc >= 0) {
@@ -332,7 +341,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
         const uint32_t obs_ring = smem_u32(&s_obs[0][tid]);
 #pragma unroll
         for (int q = 0; q < FLOW_OBS_DEPTH - 1; ++q) {
-            if (obs_c && q < p.T) cp_async4(obs_ring + (uint32_t)q * (FLOW_THREADS * 4), obs_c + (int64_t)q * S);
+            if (obs_c && q < p.T) cp_async4(obs_ring + (uint32_t)q * (FLOW_THREADS * 4), obs_c + obs_row(q) * S);
             cp_async_commit();
         }
 
@@ -527,11 +536,16 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 else
                     st_pkt(pkt_set + ((size_t)(tn & 1) * FLOW_CHAINS + bc) * SP + colC,
                            ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(u));
+                if (p.hist_u && (b0 + bc) < p.B) {
+                    const int64_t slot = (b0 + bc) * p.hist_T + obs_row(t);
+                    p.hist_u[slot * SP + colC] = u;
+                    if (jc == 0) p.hist_e[slot * (SP / 8) + colC / 8] = zero ? INT_MIN : E_abs;
+                }
                 // refill the slot consumed one step ago
                 {
                     const int64_t tn2 = t + FLOW_OBS_DEPTH - 1;
                     if (obs_c && tn2 < p.T)
-                        cp_async4(obs_ring + (uint32_t)(tn2 % FLOW_OBS_DEPTH) * (FLOW_THREADS * 4), obs_c + tn2 * S);
+                        cp_async4(obs_ring + (uint32_t)(tn2 % FLOW_OBS_DEPTH) * (FLOW_THREADS * 4), obs_c + obs_row(tn2) * S);
                     cp_async_commit();
                 }
                 if (p.prof && tid == FLOW_THREADS - 1) {
@@ -829,7 +843,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
         bool zero_last = true;
         float u_last[4] = {0.f, 0.f, 0.f, 0.f};
         const bool chain_ok = isC && (b0 + bc) < p.B;
-        const float* obs_c = (chain_ok && p.obs && colC < S) ? p.obs + ((b0 + bc) * p.T) * S + colC : nullptr;
+        const float* obs_c = (chain_ok && p.obs && colC < S) ? p.obs + ((b0 + bc) * p.obs_T) * S + colC : nullptr;
         const uint32_t obs_ring = smem_u32(&s_obs[0][isC ? tcc : 0][0]);
         auto prefetch_obs = [&](int64_t tt) {
             if (obs_c && tt < p.T) {
@@ -1132,12 +1146,12 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward_tc(FlowArgs 
 }
 
 // cA[j] = max(max_i A[i,j], -FLT_MAX) for j < S, 0 in the padding (clamped like numpy_log.py:31-32)
-__global__ void flow_colmax(const float* A, int S, int Sp, float* cA) {
+__global__ void flow_colmax(const float* A, int S, int Sp, float* cA, int transpose) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Sp) return;
     float m = -FLT_MAX;
     if (j < S)
-        for (int i = 0; i < S; ++i) m = fmaxf(m, A[(int64_t)i * S + j]);
+        for (int i = 0; i < S; ++i) m = fmaxf(m, transpose ? A[(int64_t)j * S + i] : A[(int64_t)i * S + j]);
     cA[j] = j < S ? m : 0.f;
 }
 
@@ -1168,6 +1182,34 @@ __global__ void flow_finalise(const float* fin_u, const int* fin_e, const int* a
     }
 }
 
+// gamma[b,t,j] = log alpha_t[j] + log beta_t[j] - logZ from the two recorded passes.  The backward pass records
+// w_t = obs_t (.) beta_t (for t < T-1; w_{T-1} = obs_{T-1}), so log beta_t = log w_t - obs_t.  The large parts
+// (block exponents, logZ) are combined in double; everything else is O(1).
+__global__ void flow_gamma(const float* ua, const int* ea, const float* uw, const int* ew, const float* obs, const double* logZ,
+                           int64_t B, int64_t T, int S, int Sp, float* gamma) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * T * (int64_t)S) return;
+    const int j = (int)(idx % S);
+    const int64_t bt = idx / S, t = bt % T, b = bt / T;
+    const int G = Sp / 8;
+    const float a = ua[bt * Sp + j];
+    const int e1 = ea[bt * G + j / 8];
+    float out = -INFINITY;
+    if (e1 != INT_MIN && a > 0.f) {
+        if (t == T - 1) {
+            out = (float)((double)e1 * 0.69314718055994530942 - logZ[b]) + logf(a);
+        } else {
+            const float w = uw[bt * Sp + j];
+            const int e2 = ew[bt * G + j / 8];
+            if (e2 != INT_MIN && w > 0.f)
+                out = (float)(((double)e1 + (double)e2) * 0.69314718055994530942 - logZ[b]) + (logf(a) + logf(w) - obs[idx]);
+        }
+    }
+    gamma[idx] = out;
+}
+
+int flow_padded_states(int S);
+
 // ------------------------------------------------------------------------------------------ host side
 struct FlowShape {
     int k16, nt;
@@ -1179,6 +1221,8 @@ static FlowShape flow_shape(int S) {
     if (S <= 512) return {4, 1};
     return {8, 2};
 }
+
+int flow_padded_states(int S) { return flow_shape(S).k16 * 128; }
 
 bool hmm_flow_supported(int semiring, int64_t a_sb, int64_t a_st, int S, bool wants_alpha) {
     return semiring == FB2_SEMIRING_LOG && a_sb == 0 && a_st == 0 && !wants_alpha && flow_shape(S).k16 != 0;
@@ -1277,8 +1321,22 @@ static int flow_launch_tc(FlowArgs& a, cudaStream_t stream) {
     return FB2_OK;
 }
 
+int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t obs_T, int64_t B, int64_t T, int S,
+                         float* logZ, double* logZ_d, float* hist_u, int* hist_e, int64_t hist_T, int transpose, int reverse,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
                             float* logZ, double* logZ_d, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    return hmm_flow_pass_device(init, init_sb, A, obs, T, B, T, S, logZ, logZ_d, nullptr, nullptr, 0, 0, 0, workspace, workspace_bytes,
+                                stream);
+}
+
+// General pass: T steps over obs rows [0, T) of an array with obs_T rows per chain, optionally with A transposed and
+// time reversed (the backward recursion is the forward recursion on (A^T, reversed obs), see fb2_hmm_marginals_f32),
+// optionally recording every message (mantissas + block exponents).
+int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t obs_T, int64_t B, int64_t T, int S,
+                         float* logZ, double* logZ_d, float* hist_u, int* hist_e, int64_t hist_T, int transpose, int reverse,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     const FlowShape fs = flow_shape(S);
     if (!fs.k16) {
         set_error("hmm flow: S=%d outside the supported range", S);
@@ -1300,11 +1358,12 @@ int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, 
     // stale packets must never carry a valid stamp: 0xFF.. = stamp 0xFFFF, overwritten after two steps
     FB2_CUDA(cudaMemsetAsync(pkt, 0xFF, (size_t)FLOW_MAX_SETS * 2 * FLOW_CHAINS * Sp * 8, stream));
     FB2_CUDA(cudaMemsetAsync(abort_flag, 0, 32, stream));
-    flow_colmax<<<(unsigned)ceil_div(Sp, 128), 128, 0, stream>>>(A, S, Sp, cA);
+    flow_colmax<<<(unsigned)ceil_div(Sp, 128), 128, 0, stream>>>(A, S, Sp, cA, transpose);
     FB2_LAUNCH_CHECK();
     FlowArgs a{};
     a.init = init; a.init_sb = init_sb; a.A = A; a.obs = obs; a.cA = cA; a.B = B; a.T = T; a.S = S;
     a.pkt = pkt; a.fin_u = fin_u; a.fin_e = fin_e; a.abort_flag = abort_flag; a.groups_total = (int)groups;
+    a.hist_u = hist_u; a.hist_e = hist_e; a.hist_T = hist_T; a.obs_T = obs_T; a.transpose = transpose; a.reverse = reverse;
     const char* mode_env = getenv("FB2_FLOW_MODE");
     a.mode = mode_env ? atoi(mode_env) : 1;  // default: publish packets with atom.exch (store->load hand-over measured ~10 % faster)
     const char* prof_env = getenv("FB2_FLOW_PROF");
@@ -1315,7 +1374,7 @@ int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, 
     // (default: measured 3.4 us/step at S=1024) and tcgen05 kind::tf32 with P in tensor memory (FB2_FLOW_TC=1: 3.7 us/step;
     // its shorter MMA phase is hidden behind the DSMEM reduce-scatter, which moves the same 8 KB per CTA-step either way).
     const char* tc_env = getenv("FB2_FLOW_TC");
-    const bool legacy = !(tc_env && tc_env[0] == '1');
+    const bool legacy = !(tc_env && tc_env[0] == '1') || hist_u != nullptr || transpose || reverse;
     if (!legacy) {
         if (fs.k16 == 1) st = flow_launch_tc<2, 1>(a, stream);
         else if (fs.k16 == 2) st = flow_launch_tc<4, 1>(a, stream);
@@ -1361,6 +1420,46 @@ int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, 
                         h[c * 8 + 6] / n, h[c * 8 + 7] / n, h[(FLOW_PROF_CTAS / 2 + c / 2) * 8 + (c & 1)] / n);
         }
     }
+    return FB2_OK;
+}
+
+
+size_t hmm_flow_marginals_workspace_bytes(int64_t B, int64_t T, int S) {
+    const size_t Sp = (size_t)flow_padded_states(S);
+    if (!Sp) return 0;
+    return 2 * (align_up((size_t)B * T * Sp * 4) + align_up((size_t)B * T * (Sp / 8) * 4)) + 2 * align_up((size_t)B * 8) +
+           align_up((size_t)B * 4) + hmm_flow_workspace_bytes(B, S) + 512;
+}
+
+// Forward-backward posteriors on the dataflow kernel: a forward pass and a backward pass (= the same kernel on A^T and
+// time-reversed observations, started from obs_{T-1}) record their messages; flow_gamma combines them.
+int hmm_flow_marginals_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
+                              float* logZ, float* gamma, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    const int Sp = flow_padded_states(S);
+    if (!Sp) return FB2_ERR_UNSUPPORTED;
+    Arena arena(workspace, workspace_bytes);
+    float* ua = arena.take<float>((size_t)B * T * Sp);
+    int* ea = arena.take<int>((size_t)B * T * (Sp / 8));
+    float* uw = arena.take<float>((size_t)B * T * Sp);
+    int* ew = arena.take<int>((size_t)B * T * (Sp / 8));
+    double* z_d = arena.take<double>((size_t)B);
+    double* zb_d = arena.take<double>((size_t)B);
+    float* zb = arena.take<float>((size_t)B);
+    if (!arena.ok()) {
+        set_error("hmm flow marginals: workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    char* rest = static_cast<char*>(workspace) + arena.used;
+    const size_t rest_bytes = workspace_bytes - arena.used;
+    int st = hmm_flow_pass_device(init, init_sb, A, obs, T, B, T, S, logZ, z_d, ua, ea, T, 0, 0, rest, rest_bytes, stream);
+    if (st != FB2_OK) return st;
+    // backward: w_{T-1} = obs_{T-1}; w_{t-1}[i] = obs_{t-1}[i] * sum_j A[i,j] w_t[j]  ->  T-1 steps over obs rows T-2 .. 0
+    st = hmm_flow_pass_device(obs + (T - 1) * (int64_t)S, T * (int64_t)S, A, obs, T, B, T - 1, S, zb, zb_d, uw, ew, T, 1, 1, rest, rest_bytes,
+                              stream);
+    if (st != FB2_OK) return st;
+    const int64_t n = B * T * (int64_t)S;
+    flow_gamma<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(ua, ea, uw, ew, obs, z_d, B, T, S, Sp, gamma);
+    FB2_LAUNCH_CHECK();
     return FB2_OK;
 }
 

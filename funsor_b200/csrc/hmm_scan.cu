@@ -23,6 +23,9 @@ bool hmm_flow_supported(int semiring, int64_t a_sb, int64_t a_st, int S, bool wa
 size_t hmm_flow_workspace_bytes(int64_t B, int S);
 int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
                             float* logZ, double* logZ_d, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t hmm_flow_marginals_workspace_bytes(int64_t B, int64_t T, int S);
+int hmm_flow_marginals_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
+                              float* logZ, float* gamma, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // FB2_DISABLE_FLOW=1 forces the generic kernel (A/B testing of the two GPU paths)
 static bool stream_disabled() {
     const char* e = getenv("FB2_DISABLE_STREAM");
@@ -832,7 +835,11 @@ extern "C" size_t fb2_hmm_workspace_bytes(int op, int64_t B, int64_t T, int32_t 
     if (op == 0) base += hmm_flow_workspace_bytes(B, S);
     if (op <= 1 && S >= 256) base += align_up((size_t)((S + 31) / 32) * S * 32 * sizeof(float));  // strip-major copy of A
     if (op == 1) base += align_up((size_t)B * T * S * sizeof(int32_t)) + align_up((size_t)B * sizeof(int32_t));
-    if (op == 2) base += align_up((size_t)B * T * S * sizeof(float)) + 2 * align_up((size_t)B * T * 8) + align_up((size_t)B * 8);
+    if (op == 2) {
+        base += align_up((size_t)B * T * S * sizeof(float)) + 2 * align_up((size_t)B * T * 8) + align_up((size_t)B * 8);
+        const size_t fm = hmm_flow_marginals_workspace_bytes(B, T, S);
+        if (fm > base) base = fm;
+    }
     return base;
 }
 
@@ -895,6 +902,12 @@ extern "C" int fb2_hmm_marginals_f32(const float* init, int64_t init_sb, const f
     FB2_REQUIRE(logZ && gamma && obs, "null pointer");
     if (B == 0) return FB2_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    // homogeneous chains without the pairwise sum run both passes on the dataflow kernel
+    if (!xi_sum && T >= 2 && hmm_flow_supported(FB2_SEMIRING_LOG, a_sb, a_st, S, false) && !flow_disabled() &&
+        workspace_bytes >= hmm_flow_marginals_workspace_bytes(B, T, S)) {
+        st = hmm_flow_marginals_device(init, init_sb, A, obs, B, T, S, logZ, gamma, workspace, workspace_bytes, stream);
+        if (st != FB2_ERR_UNSUPPORTED) return st;
+    }
     Arena arena(workspace, workspace_bytes);
     float* beta = arena.take<float>((size_t)B * T * S);
     double* ell_a = arena.take<double>((size_t)B * T);

@@ -495,3 +495,42 @@ def test_log_matmul_tensor_core_strided_views(fb):
     assert fb.launch_count() == 3
     want = R.pair_product(R.LOG, host(x).astype(np.float64), host(y).astype(np.float64))
     rel_close(host(got), want, rtol=RTOL, atol=1.0)
+
+
+# ------------------------------------------------------------------ forward-backward on the dataflow kernel
+@pytest.mark.parametrize("B,T,S", [(1, 100, 130), (3, 40, 512), (17, 12, 65), (2, 2, 300), (16, 25, 1024), (2, 300, 96)])
+def test_hmm_marginals_flow(fb, B, T, S):
+    """want_xi=False + homogeneous A + 64 < S <= 1024: both passes run on hmm_flow_forward (the backward pass is the same
+    kernel on A^T and time-reversed observations)."""
+    g = torch.Generator().manual_seed(41)
+    init = torch.randn(B, S, generator=g).log_softmax(-1)
+    A = torch.randn(S, S, generator=g).log_softmax(-1)
+    obs = torch.randn(B, T, S, generator=g) * 2
+    if S == 300:
+        A[:, 7] = -float("inf")
+        obs[1, 1, 17] = -float("inf")
+    fb.launch_count(reset=True)
+    logZ, gamma, xi = fb.hmm_marginals(init.cuda(), A.cuda(), obs.cuda(), want_xi=False)
+    assert xi is None and fb.launch_count() == 7  # 2 x (colmax, flow, finalise) + gamma
+    wZ, wgamma, _ = R.hmm_marginals(init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    rel_close(host(logZ), wZ, rtol=RTOL, atol=1.0)
+    rel_close(host(gamma), wgamma, rtol=1e-4, atol=1.0)
+    np.testing.assert_allclose(np.exp(host(gamma)).sum(-1), 1.0, atol=1e-4)
+
+
+def test_hmm_marginals_flow_matches_generic(fb):
+    import os
+
+    g = torch.Generator().manual_seed(42)
+    B, T, S = 2, 60, 200
+    init = torch.randn(B, S, generator=g).log_softmax(-1)
+    A = torch.randn(S, S, generator=g).log_softmax(-1)
+    obs = torch.randn(B, T, S, generator=g)
+    z1, g1, _ = fb.hmm_marginals(init.cuda(), A.cuda(), obs.cuda(), want_xi=False)
+    os.environ["FB2_DISABLE_FLOW"] = "1"
+    try:
+        z2, g2, _ = fb.hmm_marginals(init.cuda(), A.cuda(), obs.cuda(), want_xi=False)
+    finally:
+        os.environ.pop("FB2_DISABLE_FLOW")
+    rel_close(host(z1), host(z2), rtol=RTOL, atol=1.0)
+    rel_close(host(g1), host(g2), rtol=1e-4, atol=1.0)
