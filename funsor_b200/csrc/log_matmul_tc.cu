@@ -20,12 +20,16 @@
 
 namespace fb2 {
 
-constexpr int LM_TILE = 128;
+constexpr int LM_TILE = 128;                            // output rows per CTA (MMA M)
 constexpr int LM_KC = 32;                               // K per staged chunk
-constexpr int LM_OPB = LM_TILE * LM_KC * 4;             // bytes of one operand tile (hi or lo): 16 KB
-constexpr int LM_STAGEB = 4 * LM_OPB;                   // A hi, A lo, B hi, B lo
 constexpr int LM_STAGES = 2;
-constexpr int LM_SMEM = LM_STAGES * LM_STAGEB + 1024;   // + alignment slack
+template <int BN>
+struct LmCfg {
+    static constexpr int A_OPB = LM_TILE * LM_KC * 4;   // bytes of one A tile (hi or lo): 16 KB
+    static constexpr int B_OPB = BN * LM_KC * 4;        // bytes of one B tile (hi or lo): 16 / 32 KB
+    static constexpr int STAGEB = 2 * A_OPB + 2 * B_OPB;
+    static constexpr int SMEM = LM_STAGES * STAGEB + 1024;  // + alignment slack
+};
 
 struct LogMatmulArgs {
     const float* x;
@@ -104,7 +108,11 @@ __global__ void lm_colmax(const float* y, int64_t n1, int64_t ys0, int64_t ys1, 
     }
 }
 
+// BN = output columns per CTA (MMA N): 256 when J > 128 (each staged x row then feeds 256 columns, halving the L2 -> SM
+// traffic per flop, which is what bounded the 128 x 128 version), else 128.
+template <int BN>
 __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
+    using Cfg = LmCfg<BN>;
     extern __shared__ unsigned char lm_smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[LM_STAGES];
     __shared__ __align__(8) unsigned long long s_done;
@@ -112,7 +120,7 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(lm_smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n = blockIdx.z;
-    const int i0 = blockIdx.y * LM_TILE, j0 = blockIdx.x * LM_TILE;
+    const int i0 = blockIdx.y * LM_TILE, j0 = blockIdx.x * BN;
     const int64_t b0 = n / a.n1, b1 = n % a.n1;
     const float* xb = a.x + b0 * a.xs0 + b1 * a.xs1;
     const float* yb = a.y + b0 * a.ys0 + b1 * a.ys1;
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(lm_smem_u32(&s_tmem)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lm_smem_u32(&s_tmem)), "n"(BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -133,51 +141,51 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
 
-    // ---- per-thread staging role
-    // X (warps 0-3): thread t owns k-chunk kc = t % 8 of rows t/8 + 16 m (m = 0..7): a warp instruction reads 4 full
-    //   128-byte lines.  Y (warps 4-7): thread t owns k = 4 kq .. 4 kq + 3 (kq = t % 8) of the chunk and columns
-    //   8 jq .. 8 jq + 7 (jq = t / 8): a warp instruction reads 8 full lines; the 4 x 8 patch is transposed in registers.
+    // ---- staging roles (every thread stages a part of X and a part of Y)
+    // X: thread t owns k-chunk kc = t % 8 of rows t/8 + 32 m (m = 0..3): a warp instruction reads 4 full 128-byte lines.
+    // Y: thread t (t < BN) owns k = 4 kq .. 4 kq + 3 (kq = t % 8) of the chunk and columns 8 jq .. 8 jq + 7 (jq = t / 8): a warp
+    //    instruction reads 8 full lines; the 4 x 8 patch is transposed in registers.
     // Global loads for chunk c+1 are issued right after chunk c has been written to shared memory (register prefetch).
-    const bool stage_x = warp < 4;
-    const int t = tid & 127;
-    const int kc = t & 7, rbase = t >> 3;
-    const int kq = t & 7, jq = t >> 3;
-    float shift[8];  // X: sx of the thread's 8 rows;  Y: sy of its 8 columns
+    const int kc = tid & 7, rbase = tid >> 3;
+    const int kq = tid & 7, jq = tid >> 3;
+    const bool has_y = tid < BN;
+    float sxr[4], syr[8];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        if (stage_x) {
-            const int row = i0 + rbase + 16 * m;
-            shift[m] = row < a.I ? a.sx[n * a.I + row] : 0.f;
-        } else {
-            const int j = j0 + jq * 8 + m;
-            shift[m] = j < a.J ? a.sy[n * a.J + j] : 0.f;
-        }
+    for (int m = 0; m < 4; ++m) {
+        const int row = i0 + rbase + 32 * m;
+        sxr[m] = row < a.I ? a.sx[n * a.I + row] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int j = j0 + jq * 8 + q;
+        syr[q] = (has_y && j < a.J) ? a.sy[n * a.J + j] : 0.f;
     }
     const bool x_vec = (a.xsi % 4 == 0) && (reinterpret_cast<uintptr_t>(xb) % 16 == 0);
     const bool y_vec = (a.ysk % 4 == 0) && (reinterpret_cast<uintptr_t>(yb) % 16 == 0);
 
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);  // A, B K-major
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);  // A, B K-major
     const int nchunks = (a.K + LM_KC - 1) / LM_KC;
 
-    float4 pre[8];  // prefetched raw values of the next chunk
+    float4 prex[4], prey[8];  // prefetched raw values of the next chunk
     auto load_chunk = [&](int c) {
         const int k0 = c * LM_KC;
-        if (stage_x) {
+        {
             const int k = k0 + kc * 4;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int row = i0 + rbase + 16 * m;
+            for (int m = 0; m < 4; ++m) {
+                const int row = i0 + rbase + 32 * m;
                 const float* p = xb + (int64_t)(row < a.I ? row : 0) * a.xsi + k;
                 if (row < a.I && k + 3 < a.K && x_vec) {
-                    pre[m] = __ldg(reinterpret_cast<const float4*>(p));
+                    prex[m] = __ldg(reinterpret_cast<const float4*>(p));
                 } else {
                     float v[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) v[q] = (row < a.I && k + q < a.K) ? __ldg(p + q) : -INFINITY;
-                    pre[m] = make_float4(v[0], v[1], v[2], v[3]);
+                    prex[m] = make_float4(v[0], v[1], v[2], v[3]);
                 }
             }
-        } else {
+        }
+        if (has_y) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 const int k = k0 + kq * 4 + kk;
@@ -186,12 +194,12 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
                 for (int h = 0; h < 2; ++h) {
                     const int j = j0 + jq * 8 + h * 4;
                     if (k < a.K && j + 3 < a.J && y_vec) {
-                        pre[kk * 2 + h] = __ldg(reinterpret_cast<const float4*>(p + h * 4));
+                        prey[kk * 2 + h] = __ldg(reinterpret_cast<const float4*>(p + h * 4));
                     } else {
                         float v[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) v[q] = (k < a.K && j + q < a.J) ? __ldg(p + h * 4 + q) : -INFINITY;
-                        pre[kk * 2 + h] = make_float4(v[0], v[1], v[2], v[3]);
+                        prey[kk * 2 + h] = make_float4(v[0], v[1], v[2], v[3]);
                     }
                 }
             }
@@ -201,49 +209,49 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
 
     for (int c = 0; c < nchunks; ++c) {
         const int s = c % LM_STAGES;
-        unsigned char* stage = smem + (size_t)s * LM_STAGEB;
+        unsigned char* stage = smem + (size_t)s * Cfg::STAGEB;
         // the MMAs that read this buffer LM_STAGES chunks ago must have completed
         if (c >= LM_STAGES && !(a.mode & 2)) {
             const uint32_t parity = ((c / LM_STAGES) - 1) & 1;
             while (!lm_try_wait(lm_smem_u32(&s_bar[s]), parity)) {
             }
         }
-        if ((a.mode & 1) && c >= LM_STAGES) {
-        } else if (stage_x) {
+        if (!((a.mode & 1) && c >= LM_STAGES)) {
             // A operand: 16-byte k-chunk kc of row r at  r * 128 + ((kc ^ (r % 8)) * 16)
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int r = rbase + 16 * m;
-                const float v[4] = {pre[m].x, pre[m].y, pre[m].z, pre[m].w};
+            for (int m = 0; m < 4; ++m) {
+                const int r = rbase + 32 * m;
+                const float v[4] = {prex[m].x, prex[m].y, prex[m].z, prex[m].w};
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float e = __expf(v[q] - shift[m]);
+                    const float e = __expf(v[q] - sxr[m]);
                     hi[q] = lm_tf32(e);
                     lo[q] = __float_as_uint(e - __uint_as_float(hi[q]));
                 }
                 unsigned char* dst = stage + r * 128 + ((kc ^ (r & 7)) << 4);
                 *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(dst + LM_OPB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4*>(dst + Cfg::A_OPB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-        } else {
-            // B operand (same layout as A with j in the role of the row): column j = 8 jq + q, chunk kq at
-            // j * 128 + ((kq ^ q) * 16); the eight threads of a quarter warp differ in kq, i.e. hit eight different bank groups.
-            unsigned char* Bh = stage + 2 * LM_OPB + jq * 1024;
+            // B operand (same layout with j in the role of the row): column j = 8 jq + q, chunk kq at j * 128 + ((kq ^ q) * 16);
+            // the eight threads of a quarter warp differ in kq, i.e. hit eight different bank groups.
+            if (has_y) {
+                unsigned char* Bh = stage + 2 * Cfg::A_OPB + jq * 1024;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                uint32_t hi[4], lo[4];
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const float4 pv = pre[kk * 2 + (q >> 2)];
-                    const float raw = (q & 3) == 0 ? pv.x : (q & 3) == 1 ? pv.y : (q & 3) == 2 ? pv.z : pv.w;
-                    const float e = __expf(raw - shift[q]);
-                    hi[kk] = lm_tf32(e);
-                    lo[kk] = __float_as_uint(e - __uint_as_float(hi[kk]));
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const float4 pv = prey[kk * 2 + (q >> 2)];
+                        const float raw = (q & 3) == 0 ? pv.x : (q & 3) == 1 ? pv.y : (q & 3) == 2 ? pv.z : pv.w;
+                        const float e = __expf(raw - syr[q]);
+                        hi[kk] = lm_tf32(e);
+                        lo[kk] = __float_as_uint(e - __uint_as_float(hi[kk]));
+                    }
+                    unsigned char* dst = Bh + q * 128 + ((kq ^ q) << 4);
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(dst + Cfg::B_OPB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
-                unsigned char* dst = Bh + q * 128 + ((kq ^ q) << 4);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(dst + LM_OPB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
         }
         if (c + 1 < nchunks) load_chunk(c + 1);
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
             uint32_t elected;
             asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(elected));
             if (elected && !((a.mode & 2) && c < nchunks - 1)) {
-                const uint32_t ah = lm_smem_u32(stage), al = ah + LM_OPB, bh = ah + 2 * LM_OPB, bl = ah + 3 * LM_OPB;
+                const uint32_t ah = lm_smem_u32(stage), al = ah + Cfg::A_OPB, bh = ah + 2 * Cfg::A_OPB, bl = bh + Cfg::B_OPB;
 #pragma unroll
                 for (int ks = 0; ks < LM_KC / 8; ++ks) {
                     const uint64_t dah = lm_desc(ah + ks * 32), dal = lm_desc(al + ks * 32);
@@ -271,17 +279,18 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
         }
     }
 
-    // ---- epilogue: warp w reads lanes 32*(w%4).. and columns [64*(w/4), +64)
+    // ---- epilogue: warp w reads lanes 32*(w%4).. and columns [BN/2*(w/4), +BN/2)
     while (!lm_try_wait(lm_smem_u32(&s_done), 0)) {
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
         const int row = i0 + (warp & 3) * 32 + lane;
-        const int cbase = (warp >> 2) * 64;
+        const int cbase = (warp >> 2) * (BN / 2);
         const float sxo = row < a.I ? a.sx[n * a.I + row] : 0.f;
         float* orow = a.out + b0 * a.os0 + b1 * (int64_t)a.I * a.J + (int64_t)row * a.J;
-#pragma unroll
-        for (int cc = 0; cc < 64; cc += 16) {
+        const bool vec_out = (a.J % 4 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 2; cc += 16) {
             uint32_t d[16];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -295,7 +304,7 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
                 float o[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) o[q] = (sxo + ((jb + q) < a.J ? __ldg(a.sy + n * a.J + jb + q) : 0.f)) + __logf(__uint_as_float(d[q]));
-                if (jb + 15 < a.J && (a.J % 4 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 16 == 0)) {
+                if (jb + 15 < a.J && vec_out) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(orow + jb + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
                 } else {
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
 }
 
 // Returns FB2_ERR_UNSUPPORTED when the shapes / strides do not fit this kernel (caller falls back to the SIMT tile kernel).
@@ -336,11 +345,18 @@ int launch_log_matmul_tc(const float* x, const int64_t* xs, const float* y, cons
     }
     static bool attr_set = false;
     if (!attr_set) {
-        FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM));
+        FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<128>::SMEM));
+        FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<256>::SMEM));
         attr_set = true;
     }
-    dim3 grid((unsigned)ceil_div(J, LM_TILE), (unsigned)ceil_div(I, LM_TILE), (unsigned)n);
-    log_matmul_tc<<<grid, 256, LM_SMEM, stream>>>(a);
+    const char* bn_env = getenv("FB2_LM_BN");  // A/B switch: force the 128-column tile
+    if (J > 128 && !(bn_env && atoi(bn_env) == 128)) {
+        dim3 grid((unsigned)ceil_div(J, 256), (unsigned)ceil_div(I, LM_TILE), (unsigned)n);
+        log_matmul_tc<256><<<grid, 256, LmCfg<256>::SMEM, stream>>>(a);
+    } else {
+        dim3 grid((unsigned)ceil_div(J, 128), (unsigned)ceil_div(I, LM_TILE), (unsigned)n);
+        log_matmul_tc<128><<<grid, 256, LmCfg<128>::SMEM, stream>>>(a);
+    }
     FB2_LAUNCH_CHECK();
     return FB2_OK;
 }
