@@ -10,6 +10,8 @@
 //     Lam' = diag(Lx_aa, Ly_bb) - U'U,  eta' = [ex_a ; ey_b] - U'v,
 //     c'   = cx + cy + D/2 log 2pi - sum log diag L + |v|^2/2
 // One CTA of 256 threads per pair; everything between the loads and the stores stays in shared memory.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fb2 {
@@ -120,6 +122,196 @@ __global__ void __launch_bounds__(256) gaussian_pair_combine(GaussPairArgs a) {
     (void)s_red;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-per-pair version of the same contraction.  The CTA-per-pair kernel above spends its time in ~100 block
+// barriers around a 32-step Cholesky (measured: 1.07e7 pairs/s, ~5 % of the fp32 roofline of the arithmetic);
+// here one warp owns a pair, nothing but __syncwarp separates the phases, and 8 warps per CTA (2 CTAs per SM) keep
+// 16 pairs in flight per SM.
+//   phase 1  lane i holds row i of M = Lx_bb + Ly_aa in registers; right-looking Cholesky with shuffles
+//   phase 2  L goes to the warp's shared-memory slot; lane l forward-substitutes right-hand-side columns l, l+32 (, 64)
+//            of [G' | e_b] reading L as broadcast loads -> U columns in registers and in shared memory
+//   phase 3  lane l produces output rows l and l+32:  Lam'[r, :] = base[r, :] - U[:, r]' U,  eta'[r] likewise
+constexpr int GW_WARPS = 4;
+template <int DT>
+struct GaussWarpSmem {
+    float L[DT][DT + 1];
+    float U[DT][(2 * DT + 4) < 20 ? 20 : (2 * DT + 4)];  // column 2*DT holds v; rows are 16-byte aligned and at least 16 + 4 wide
+};
+
+// DT = compile-time padded state dimension (D <= DT): the shared block is padded with an identity and zero right-hand
+// sides, so every loop has static bounds, every array stays in registers and the shuffles are unconditional (a first
+// version with run-time bounds put the row array in local memory and wrapped each shuffle in divergence handling).
+template <int DT>
+__global__ void __launch_bounds__(GW_WARPS * 32, 3) gaussian_pair_combine_warp(GaussPairArgs a, int64_t npairs) {
+    extern __shared__ __align__(16) unsigned char gw_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    GaussWarpSmem<DT>& sm = reinterpret_cast<GaussWarpSmem<DT>*>(gw_raw)[warp];
+    const int D = a.D, n = 2 * D;
+    constexpr int NCOL = (2 * DT + 31) / 32;  // right-hand-side columns / output rows per lane
+    for (int64_t pair = (int64_t)blockIdx.x * GW_WARPS + warp; pair < npairs; pair += (int64_t)gridDim.x * GW_WARPS) {
+        const int64_t q0 = pair / a.n1, q1 = pair % a.n1;
+        const int64_t xe = q0 * a.x_s0 + q1 * a.x_s1, ye = q0 * a.y_s0 + q1 * a.y_s1, oe = q0 * a.o_s0 + q1;
+        const float* Lx = a.Lx + xe * n * n;
+        const float* Ly = a.Ly + ye * n * n;
+        const float* ex = a.ex + xe * n;
+        const float* ey = a.ey + ye * n;
+
+        // ---- phase 1: Cholesky of M = Lx_bb + Ly_aa, lane = row (M is symmetric: column `lane` is read, coalesced, as row `lane`)
+        float m[DT];
+#pragma unroll
+        for (int k = 0; k < DT; ++k)
+            m[k] = (lane < D && k < D) ? __ldg(Lx + (D + k) * n + D + lane) + __ldg(Ly + k * n + lane) : (k == lane ? 1.f : 0.f);
+        float logdet = 0.f;
+        int bad = 0;
+#pragma unroll
+        for (int j = 0; j < DT; ++j) {
+            float d = __shfl_sync(0xffffffffu, m[j], j);
+            if (!(d > 0.f)) {
+                bad = 1;
+                d = 1.f;
+            }
+            const float ljj = sqrtf(d), inv = 1.f / ljj;
+            logdet += __logf(ljj);
+            const float lij = lane > j ? m[j] * inv : (lane == j ? ljj : 0.f);
+            m[j] = lij;
+#pragma unroll
+            for (int k = j + 1; k < DT; ++k) m[k] = fmaf(-lij, __shfl_sync(0xffffffffu, lij, k), m[k]);
+        }
+        // v = L^-1 (ex_b + ey_a), still lane = row: lane k ends up with v[k]
+        float val = lane < D ? ex[D + lane] + ey[lane] : 0.f;
+#pragma unroll
+        for (int j = 0; j < DT; ++j) {
+            const float vj = __shfl_sync(0xffffffffu, val, j) / __shfl_sync(0xffffffffu, m[j], j);
+            val = lane == j ? vj : (lane > j ? fmaf(-m[j], vj, val) : val);
+        }
+        if (lane < DT) {
+#pragma unroll
+            for (int k = 0; k < DT; ++k) sm.L[lane][k] = m[k];
+            sm.U[lane][2 * DT] = val;
+        }
+        __syncwarp();
+
+        // ---- phase 2: forward substitution, lane = right-hand-side columns c = lane + 32 q of G' (padded layout: the a-block
+        // occupies columns [0, DT), the c-block columns [DT, 2 DT)); G'[k, c] is read through its symmetric counterpart so
+        // that the lanes coalesce: Lx_ab[c, k] = Lx_ba[k, c], Ly_ba[c, k] = Ly_ab[k, c]
+        float u[NCOL][DT];
+#pragma unroll
+        for (int q = 0; q < NCOL; ++q) {
+            const int c = lane + 32 * q;
+            const int blk = c / DT, cc = c % DT;  // 0: a-block, 1: c-block
+#pragma unroll
+            for (int k = 0; k < DT; ++k) {
+                float g = 0.f;
+                if (c < 2 * DT && cc < D && k < D) g = blk == 0 ? __ldg(Lx + (D + k) * n + cc) : __ldg(Ly + k * n + D + cc);
+                u[q][k] = g;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            float acc[NCOL];
+#pragma unroll
+            for (int q = 0; q < NCOL; ++q) acc[q] = u[q][k];
+#pragma unroll
+            for (int mm = 0; mm < k; ++mm) {
+                const float l = sm.L[k][mm];
+#pragma unroll
+                for (int q = 0; q < NCOL; ++q) acc[q] = fmaf(-l, u[q][mm], acc[q]);
+            }
+            const float inv = 1.f / sm.L[k][k];
+#pragma unroll
+            for (int q = 0; q < NCOL; ++q) {
+                u[q][k] = acc[q] * inv;
+                const int c = lane + 32 * q;
+                if (c < 2 * DT) sm.U[k][c] = u[q][k];
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 3: outputs, lane = output rows (padded index) r = lane + 32 q; inputs and output are symmetric, so element
+        // (r, s) is read from / written to (s, r) and the lanes coalesce
+        float* Lo = a.Lo + oe * n * n;
+        float* eo = a.eo + oe * n;
+#pragma unroll 1
+        for (int s0 = 0; s0 < 2 * DT; s0 += 16) {
+            float acc[NCOL][16];
+#pragma unroll
+            for (int q = 0; q < NCOL; ++q)
+#pragma unroll
+                for (int t = 0; t < 16; ++t) acc[q][t] = 0.f;
+#pragma unroll
+            for (int k = 0; k < DT; ++k) {
+                const float4* up = reinterpret_cast<const float4*>(&sm.U[k][s0]);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 uv = up[q4];
+#pragma unroll
+                    for (int q = 0; q < NCOL; ++q) {
+                        acc[q][4 * q4 + 0] = fmaf(u[q][k], uv.x, acc[q][4 * q4 + 0]);
+                        acc[q][4 * q4 + 1] = fmaf(u[q][k], uv.y, acc[q][4 * q4 + 1]);
+                        acc[q][4 * q4 + 2] = fmaf(u[q][k], uv.z, acc[q][4 * q4 + 2]);
+                        acc[q][4 * q4 + 3] = fmaf(u[q][k], uv.w, acc[q][4 * q4 + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int sp = s0 + t;  // padded column index
+                const int sblk = sp / DT, sc = sp % DT;
+                if (sp < 2 * DT && sc < D) {
+                    const int s = sblk * D + sc;  // real column index
+#pragma unroll
+                    for (int q = 0; q < NCOL; ++q) {
+                        const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
+                        if (rp < 2 * DT && rc < D) {
+                            const int r = rblk * D + rc;
+                            float base = 0.f;
+                            if (rblk == 0 && sblk == 0) base = __ldg(Lx + s * n + r);
+                            else if (rblk == 1 && sblk == 1) base = __ldg(Ly + s * n + r);
+                            Lo[s * n + r] = base - acc[q][t];
+                        }
+                    }
+                }
+            }
+        }
+        // eta' and the scalar need column v of U
+        float e[NCOL], vv = 0.f;
+#pragma unroll
+        for (int q = 0; q < NCOL; ++q) e[q] = 0.f;
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            const float v = sm.U[k][2 * DT];
+#pragma unroll
+            for (int q = 0; q < NCOL; ++q) e[q] = fmaf(u[q][k], v, e[q]);
+            vv = fmaf(v, v, vv);
+        }
+#pragma unroll
+        for (int q = 0; q < NCOL; ++q) {
+            const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
+            if (rp < 2 * DT && rc < D) {
+                const int r = rblk * D + rc;
+                eo[r] = (rblk == 0 ? ex[r] : ey[r]) - e[q];
+            }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            a.co[oe] = a.cx[xe] + a.cy[ye] + D * kHalfLog2Pi - logdet + 0.5f * vv;
+            if (bad && a.flag) atomicExch(a.flag, 1);
+        }
+        __syncwarp();  // the shared-memory slot is reused by the next pair
+    }
+}
+
+template <int DT>
+static int launch_pair_warp(const GaussPairArgs& a, int64_t npairs, cudaStream_t stream) {
+    const size_t smem = GW_WARPS * sizeof(GaussWarpSmem<DT>);
+    FB2_CUDA(cudaFuncSetAttribute(gaussian_pair_combine_warp<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = ceil_div(npairs, GW_WARPS);
+    if (blocks > 148 * 3 * 8) blocks = 148 * 3 * 8;  // persistent-ish: a few waves of 3 CTAs per SM
+    gaussian_pair_combine_warp<DT><<<(unsigned)blocks, GW_WARPS * 32, smem, stream>>>(a, npairs);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
 // (w, P, s) -> (Lam, eta, c): one CTA per element, P staged in shared memory in chunks of rank.
 __global__ void __launch_bounds__(256) gaussian_sqrt_to_info(const float* w, const float* P, const float* s, int dim,
                                                              int rank, float* Lam, float* eta, float* c) {
@@ -199,9 +391,17 @@ static int launch_pair(const float* Lx, const float* ex, const float* cx, int64_
     GaussPairArgs a;
     a.Lx = Lx; a.ex = ex; a.cx = cx; a.Ly = Ly; a.ey = ey; a.cy = cy; a.Lo = Lo; a.eo = eo; a.co = co; a.flag = flag;
     a.n1 = n1; a.x_s0 = x_s0; a.x_s1 = x_s1; a.y_s0 = y_s0; a.y_s1 = y_s1; a.o_s0 = o_s0; a.D = D;
-    gaussian_pair_combine<<<(unsigned)(n0 * n1), 256, 0, stream>>>(a);
-    FB2_LAUNCH_CHECK();
-    return FB2_OK;
+    const char* old_env = getenv("FB2_GAUSS_CTA");  // A/B switch: the CTA-per-pair kernel
+    if (old_env && old_env[0] == '1') {
+        gaussian_pair_combine<<<(unsigned)(n0 * n1), 256, 0, stream>>>(a);
+        FB2_LAUNCH_CHECK();
+        return FB2_OK;
+    }
+    const int64_t npairs = n0 * n1;
+    if (D <= 4) return launch_pair_warp<4>(a, npairs, stream);
+    if (D <= 8) return launch_pair_warp<8>(a, npairs, stream);
+    if (D <= 16) return launch_pair_warp<16>(a, npairs, stream);
+    return launch_pair_warp<32>(a, npairs, stream);
 }
 
 }  // namespace fb2
