@@ -296,18 +296,18 @@ def extra_measurements(device):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n * 1e-3
 
-    # Kalman (C4 shape at reduced T): D=32, O=16, B=64
-    Bk, Tk, D, O = 64, 4096, 32, 16
+    # Kalman (C4 shape, T reduced 100000 -> 16384): D=32, O=16, B=64, homogeneous dynamics; elements + eta + parallel scan
+    Bk, Tk, D, O = 64, 16384, 32, 16
     F = 0.9 * torch.linalg.qr(torch.randn(Bk, D, D, device=device, generator=g))[0]
     H = torch.randn(Bk, D, O, device=device, generator=g) / D ** 0.5
     eye = lambda n: torch.eye(n, device=device).expand(Bk, n, n).contiguous()  # noqa: E731
     y = torch.randn(Bk, Tk, O, device=device, generator=g)
-    w, P, s = fg.kalman_elements_sqrt(F, torch.zeros(Bk, D, device=device), eye(D), H, torch.zeros(Bk, O, device=device), eye(O), y)
-    Lam, eta, c = fg.sqrt_to_info(w, P, s)
-    sec = timeit(lambda: fg.gaussian_sequential_sum_product(Lam, eta, c, validate=False))
+    kargs = (F, torch.zeros(Bk, D, device=device), eye(D), H, torch.zeros(Bk, O, device=device), eye(O), y)
+    sec = timeit(lambda: fg.kalman_chain(*kargs, validate=False))
     out["kalman_scan"] = {"steps_per_s": Bk * Tk / sec, "D": D, "O": O, "B": Bk, "T": Tk, "ms": sec * 1e3,
-                          "note": "Gaussian scan over dense info-form elements (C4 shape at reduced T)"}
-    del w, P, s, Lam, eta, c
+                          "kernel": "gaussian_pair_combine_warp<32> (one warp per pair contraction, fp32 CUDA cores)",
+                          "note": "C4 shape at reduced T; full size (T=100000): profiles/r01_full_configs.jsonl"}
+    del y, kargs
     # dense chain product (literal sequential_sum_product semantics), S=1024: tcgen05 3xTF32 log-matmul per level
     Bd, Td, Sd = 4, 64, 1024
     trans = torch.randn(Bd, Td, Sd, Sd, device=device, generator=g)

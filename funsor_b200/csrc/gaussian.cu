@@ -24,7 +24,8 @@ struct GaussPairArgs {
     float *Lo, *eo, *co;
     int32_t* flag;
     int64_t n1;                     // pairs per outer batch index
-    int64_t x_s0, x_s1, y_s0, y_s1; // element strides (units of one element) for (outer, inner)
+    int64_t x_s0, x_s1, y_s0, y_s1; // element strides (units of one element) for (outer, inner) of eta / c
+    int64_t lx_s0, lx_s1, ly_s0, ly_s1;  // the same for the Lam arrays (stride 0 over time = time-invariant precision)
     int64_t o_s0;                   // output element stride of the outer index (inner contiguous)
     int D;
 };
@@ -39,8 +40,8 @@ __global__ void __launch_bounds__(256) gaussian_pair_combine(GaussPairArgs a) {
     const int64_t pair = blockIdx.x;
     const int64_t q0 = pair / a.n1, q1 = pair % a.n1;
     const int64_t xe = q0 * a.x_s0 + q1 * a.x_s1, ye = q0 * a.y_s0 + q1 * a.y_s1, oe = q0 * a.o_s0 + q1;
-    const float* Lx = a.Lx + xe * n * n;
-    const float* Ly = a.Ly + ye * n * n;
+    const float* Lx = a.Lx + (q0 * a.lx_s0 + q1 * a.lx_s1) * n * n;
+    const float* Ly = a.Ly + (q0 * a.ly_s0 + q1 * a.ly_s1) * n * n;
     const float* ex = a.ex + xe * n;
     const float* ey = a.ey + ye * n;
     if (tid == 0) s_bad = 0;
@@ -151,8 +152,8 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) gaussian_pair_combine_warp(G
     for (int64_t pair = (int64_t)blockIdx.x * GW_WARPS + warp; pair < npairs; pair += (int64_t)gridDim.x * GW_WARPS) {
         const int64_t q0 = pair / a.n1, q1 = pair % a.n1;
         const int64_t xe = q0 * a.x_s0 + q1 * a.x_s1, ye = q0 * a.y_s0 + q1 * a.y_s1, oe = q0 * a.o_s0 + q1;
-        const float* Lx = a.Lx + xe * n * n;
-        const float* Ly = a.Ly + ye * n * n;
+        const float* Lx = a.Lx + (q0 * a.lx_s0 + q1 * a.lx_s1) * n * n;
+        const float* Ly = a.Ly + (q0 * a.ly_s0 + q1 * a.ly_s1) * n * n;
         const float* ex = a.ex + xe * n;
         const float* ey = a.ey + ye * n;
 
@@ -364,16 +365,37 @@ __global__ void __launch_bounds__(256) gaussian_sqrt_to_info(const float* w, con
     }
 }
 
+// eta[b,t,:] = P[b] w[b,t,:],  c[b,t] = s[b,t] - |w[b,t]|^2 / 2   for a time-invariant prec_sqrt P[b] (n x r): one warp per (b,t)
+__global__ void gaussian_eta_c(const float* w, const float* P, const float* s, int64_t B, int64_t T, int n, int r, float* eta, float* c) {
+    const int64_t e = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (e >= B * T) return;
+    const int lane = threadIdx.x % 32;
+    const int64_t b = e / T;
+    const float* we = w + e * r;
+    const float* Pb = P + b * (int64_t)n * r;
+    float ww = 0.f;
+    for (int k = lane; k < r; k += 32) ww = fmaf(we[k], we[k], ww);
+    ww = warp_sum(ww);
+    for (int i = lane; i < n; i += 32) {
+        float acc = 0.f;
+        for (int k = 0; k < r; ++k) acc = fmaf(__ldg(Pb + (int64_t)i * r + k), __ldg(we + k), acc);
+        eta[e * n + i] = acc;
+    }
+    if (lane == 0) c[e] = (s ? s[e] : 0.f) - 0.5f * ww;
+}
+
 // copy one strided element per outer index: dst[q0*o_s0 + slot] = src[q0*s_s0 + which]
 __global__ void gaussian_copy_elements(const float* L, const float* e, const float* c, int64_t s_s0, int64_t which, float* Lo,
-                                       float* eo, float* co, int64_t o_s0, int64_t slot, int64_t B, int n) {
+                                       float* eo, float* co, int64_t o_s0, int64_t slot, int64_t B, int n, int64_t l_s0 = -1,
+                                       int64_t l_which = 0) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int per = n * n + n + 1;
     if (idx >= B * per) return;
     int64_t b = idx / per;
     int o = (int)(idx % per);
     int64_t se = b * s_s0 + which, de = b * o_s0 + slot;
-    if (o < n * n) Lo[de * n * n + o] = L[se * n * n + o];
+    const int64_t le = l_s0 < 0 ? se : b * l_s0 + l_which;
+    if (o < n * n) Lo[de * n * n + o] = L[le * n * n + o];
     else if (o < n * n + n) eo[de * n + (o - n * n)] = e[se * n + (o - n * n)];
     else co[de] = c[se];
 }
@@ -385,12 +407,17 @@ __global__ void gaussian_poison_if_flag(const int32_t* flag, float* co, int64_t 
 
 static int launch_pair(const float* Lx, const float* ex, const float* cx, int64_t x_s0, int64_t x_s1, const float* Ly,
                        const float* ey, const float* cy, int64_t y_s0, int64_t y_s1, int64_t n0, int64_t n1, int D,
-                       float* Lo, float* eo, float* co, int64_t o_s0, int32_t* flag, cudaStream_t stream) {
+                       float* Lo, float* eo, float* co, int64_t o_s0, int32_t* flag, cudaStream_t stream, bool lam_time_invariant = false) {
     if (n0 * n1 == 0) return FB2_OK;
     FB2_REQUIRE(n0 * n1 < (1ll << 31), "gaussian_pair_combine: too many pairs for one launch");
     GaussPairArgs a;
     a.Lx = Lx; a.ex = ex; a.cx = cx; a.Ly = Ly; a.ey = ey; a.cy = cy; a.Lo = Lo; a.eo = eo; a.co = co; a.flag = flag;
     a.n1 = n1; a.x_s0 = x_s0; a.x_s1 = x_s1; a.y_s0 = y_s0; a.y_s1 = y_s1; a.o_s0 = o_s0; a.D = D;
+    a.lx_s0 = x_s0; a.lx_s1 = x_s1; a.ly_s0 = y_s0; a.ly_s1 = y_s1;
+    if (lam_time_invariant) {  // Lam[b] shared by every time step of chain b: both operands read the same matrix
+        a.lx_s0 = a.ly_s0 = 1;
+        a.lx_s1 = a.ly_s1 = 0;
+    }
     const char* old_env = getenv("FB2_GAUSS_CTA");  // A/B switch: the CTA-per-pair kernel
     if (old_env && old_env[0] == '1') {
         gaussian_pair_combine<<<(unsigned)(n0 * n1), 256, 0, stream>>>(a);
@@ -438,6 +465,18 @@ extern "C" int fb2_gaussian_pair_combine_f32(const float* Lx, const float* ex, c
 
 static size_t gauss_elem_floats(int n) { return (size_t)n * n + n + 1; }
 
+extern "C" int fb2_gaussian_eta_f32(const float* w, const float* P, const float* s, int64_t B, int64_t T, int32_t dim, int32_t rank,
+                                    float* eta, float* c, void* stream) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(w && P && eta && c, "null pointer");
+    FB2_REQUIRE(B >= 0 && T >= 0 && dim >= 1 && rank >= 0, "bad extents");
+    if (B * T == 0) return FB2_OK;
+    gaussian_eta_c<<<(unsigned)ceil_div(B * T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, P, s, B, T, dim, rank, eta, c);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
 extern "C" size_t fb2_gaussian_chain_workspace_bytes(int64_t B, int64_t T, int32_t D) {
     int n = 2 * D;
     int64_t t1 = (T + 1) / 2, t2 = (t1 + 1) / 2;
@@ -448,9 +487,23 @@ extern "C" size_t fb2_gaussian_chain_workspace_bytes(int64_t B, int64_t T, int32
     return per + align_up(4) + 256;
 }
 
+static int gaussian_chain_impl(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D, float* Lo, float* eo,
+                               float* co, void* workspace, size_t workspace_bytes, void* stream_, bool homog);
+
 extern "C" int fb2_gaussian_chain_f32(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D,
                                       float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes,
                                       void* stream_) {
+    return gaussian_chain_impl(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream_, false);
+}
+
+extern "C" int fb2_gaussian_chain_homog_f32(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D,
+                                            float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes,
+                                            void* stream_) {
+    return gaussian_chain_impl(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream_, true);
+}
+
+static int gaussian_chain_impl(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D, float* Lo, float* eo,
+                               float* co, void* workspace, size_t workspace_bytes, void* stream_, bool homog) {
     int st = check_device();
     if (st != FB2_OK) return st;
     FB2_REQUIRE(Lam && eta && c && Lo && eo && co, "null pointer");
@@ -465,6 +518,7 @@ extern "C" int fb2_gaussian_chain_f32(const float* Lam, const float* eta, const 
         FB2_LAUNCH_CHECK();
         return FB2_OK;
     }
+    bool first_level = true;
     int64_t t1 = (T + 1) / 2, t2 = (t1 + 1) / 2;
     Arena arena(workspace, workspace_bytes);
     float *bL[2], *be[2], *bc[2];
@@ -490,14 +544,21 @@ extern "C" int fb2_gaussian_chain_f32(const float* Lam, const float* eta, const 
         float* de = nd == 1 ? eo : be[which];
         float* dc = nd == 1 ? co : bc[which];
         int64_t o_s0 = nd;  // when nd == 1 outputs are [B] contiguous: stride 1 == nd
-        st = launch_pair(cL, ce, cc, cur_s0, 2, cL + (size_t)n * n, ce + n, cc + 1, cur_s0, 2, B, half, D, dL, de, dc, o_s0,
-                         flag, stream);
+        const bool inv = homog && first_level;  // level 1 of a homogeneous chain: Lam[b] is shared by all time steps
+        st = launch_pair(cL, ce, cc, cur_s0, 2, inv ? cL : cL + (size_t)n * n, ce + n, cc + 1, cur_s0, 2, B, half, D, dL, de, dc, o_s0,
+                         flag, stream, inv);
         if (st != FB2_OK) return st;
         if (nd != half) {
-            gaussian_copy_elements<<<(unsigned)ceil_div(B * per, 256), 256, 0, stream>>>(cL, ce, cc, cur_s0, d - 1, dL, de, dc,
-                                                                                       o_s0, half, B, n);
+            if (inv) {  // odd leftover: Lam from [b], eta / c from [b, d-1]
+                gaussian_copy_elements<<<(unsigned)ceil_div(B * per, 256), 256, 0, stream>>>(cL, ce, cc, cur_s0, d - 1, dL, de, dc, o_s0,
+                                                                                           half, B, n, 1, 0);
+            } else {
+                gaussian_copy_elements<<<(unsigned)ceil_div(B * per, 256), 256, 0, stream>>>(cL, ce, cc, cur_s0, d - 1, dL, de, dc, o_s0,
+                                                                                           half, B, n, cur_s0, d - 1);
+            }
             FB2_LAUNCH_CHECK();
         }
+        first_level = false;
         cL = dL; ce = de; cc = dc;
         cur_s0 = nd;
         d = nd;

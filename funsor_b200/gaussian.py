@@ -107,13 +107,60 @@ def kalman_elements_sqrt(F, q_loc, q_tril, H, r_loc, r_tril, y):
     return w.contiguous(), P, s[:, None].expand(B, T).contiguous()
 
 
-def kalman_chain(F, q_loc, q_tril, H, r_loc, r_tril, y):
-    """Parallel-scan Kalman filter: builds the chain elements, converts them to information form and
-    reduces them with the Gaussian scan kernel.  Returns (Lam[B,2D,2D], eta[B,2D], c[B]) over
-    (state_{-1}; state_{T-1}), the value of the reference's MarkovProduct (pyro/hmm.py:269)."""
-    w, P, s = kalman_elements_sqrt(F, q_loc, q_tril, H, r_loc, r_tril, y)
-    Lam, eta, c = sqrt_to_info(w, P, s)
-    return gaussian_sequential_sum_product(Lam, eta, c)
+def kalman_elements_homog(F, q_loc, q_tril, H, r_loc, r_tril, y):
+    """The same chain elements for time-homogeneous parameters without the T-sized prec_sqrt: only white_vec depends on
+    t (pyro/hmm.py:258-270), so P is built once per chain.  Returns w[B,T,D+O], P[B,2D,D+O], s[B,T]."""
+    B, T, O = y.shape
+    D = F.shape[-1]
+    eyeD = torch.eye(D, device=F.device, dtype=F.dtype)
+    eyeO = torch.eye(O, device=F.device, dtype=F.dtype)
+    Pq = torch.linalg.solve_triangular(q_tril, eyeD.expand(B, D, D), upper=False).transpose(-1, -2)
+    Pr = torch.linalg.solve_triangular(r_tril, eyeO.expand(B, O, O), upper=False).transpose(-1, -2)
+    P = torch.zeros(B, 2 * D, D + O, device=F.device, dtype=F.dtype)
+    P[:, :D, :D] = F @ Pq
+    P[:, D:, :D] = -Pq
+    P[:, D:, D:] = H @ Pr
+    w_t = -(q_loc[:, None, :] @ Pq)[:, 0]
+    w_o = -(r_loc[:, None, :] @ Pr)[:, 0]
+    w = torch.cat([w_t[:, None, :].expand(B, T, D), w_o[:, None, :] + y @ Pr], dim=-1)
+    s = (-0.5 * (D + O) * math.log(2 * math.pi) - q_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1)
+         - r_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1))
+    return w.contiguous(), P, s[:, None].expand(B, T).contiguous()
+
+
+def gaussian_chain_homog(white_vec, prec_sqrt, scalar, validate=True):
+    """Scan over chain elements that share one prec_sqrt per chain: white_vec[B,T,r], prec_sqrt[B,2D,r], scalar[B,T].
+    Lam[B] = P P' once per chain, eta / c per step; the T-sized precision array is never formed."""
+    _dev_f32(white_vec, "white_vec"), _dev_f32(prec_sqrt, "prec_sqrt")
+    B, T, r = white_vec.shape
+    n = prec_sqrt.shape[-2]
+    D = n // 2
+    w = white_vec.contiguous()
+    P = prec_sqrt.contiguous()
+    s = None if scalar is None else _dev_f32(scalar, "scalar").expand(B, T).contiguous()
+    Lam, _, _ = sqrt_to_info(torch.zeros(B, r, device=P.device), P)
+    eta = torch.empty((B, T, n), dtype=torch.float32, device=P.device)
+    c = torch.empty((B, T), dtype=torch.float32, device=P.device)
+    Lo = torch.empty((B, n, n), dtype=torch.float32, device=P.device)
+    eo = torch.empty((B, n), dtype=torch.float32, device=P.device)
+    co = torch.empty((B,), dtype=torch.float32, device=P.device)
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_gaussian_chain_workspace_bytes(B, T, D), P.device)
+    with torch.cuda.device(P.device):
+        check(lib.fb2_gaussian_eta_f32(w.data_ptr(), P.data_ptr(), _ptr(s), B, T, n, r, eta.data_ptr(), c.data_ptr(), _stream()))
+        check(lib.fb2_gaussian_chain_homog_f32(Lam.data_ptr(), eta.data_ptr(), c.data_ptr(), B, T, D, Lo.data_ptr(), eo.data_ptr(),
+                                               co.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    if validate and bool(torch.isnan(co).any()):
+        raise ValueError("Too little information to marginalize over the shared state. Consider adding a prior.")
+    return Lo, eo, co
+
+
+def kalman_chain(F, q_loc, q_tril, H, r_loc, r_tril, y, validate=True):
+    """Parallel-scan Kalman filter for time-homogeneous parameters (examples/kalman_filter.py, GaussianHMM pyro/hmm.py:258-274):
+    Returns (Lam[B,2D,2D], eta[B,2D], c[B]) over (state_{-1}; state_{T-1}), the value of the reference's MarkovProduct
+    (pyro/hmm.py:269).  Time-varying elements go through kalman_elements_sqrt + sqrt_to_info + gaussian_sequential_sum_product."""
+    w, P, s = kalman_elements_homog(F, q_loc, q_tril, H, r_loc, r_tril, y)
+    return gaussian_chain_homog(w, P, s, validate=validate)
 
 
 def gaussian_hmm_log_prob(m0, p0_tril, chain):

@@ -135,6 +135,15 @@ int fb2_gaussian_pair_combine_f32(const float* Lx, const float* ex, const float*
                                   const float* Ly, const float* ey, const float* cy, int64_t y_stride,
                                   int64_t n0, int64_t n1, int64_t x_s0, int64_t y_s0, int32_t D, float* Lo,
                                   float* eo, float* co, int32_t* status_flag, void* stream);
+/* eta          : eta[b,t] = P[b] w[b,t], c[b,t] = s[b,t] - |w[b,t]|^2/2 for a TIME-INVARIANT prec_sqrt P[b] (GaussianHMM with
+ *                homogeneous dynamics, pyro/hmm.py:258-270: only white_vec depends on t).
+ * chain_homog  : the same scan for Lam[B,2D,2D] shared by all time steps of a chain (eta[B,T,2D], c[B,T] per step): the
+ *                T-sized precision array is never materialised and level 1 reads Lam[b] for both operands.
+ */
+int fb2_gaussian_eta_f32(const float* w, const float* P, const float* s, int64_t B, int64_t T, int32_t dim, int32_t rank,
+                         float* eta, float* c, void* stream);
+int fb2_gaussian_chain_homog_f32(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D,
+                                 float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes, void* stream);
 size_t fb2_gaussian_chain_workspace_bytes(int64_t B, int64_t T, int32_t D);
 int fb2_gaussian_chain_f32(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D,
                            float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes,

@@ -34,3 +34,7 @@ ms0 = timeit(lambda: fg.sqrt_to_info(w, P, s))
 Lam, eta, c = fg.sqrt_to_info(w, P, s)
 ms = timeit(lambda: fg.gaussian_sequential_sum_product(Lam, eta, c, validate=False))
 print("kalman D=32 B=64 T=%d: sqrt_to_info %.2f ms, scan %.2f ms -> %.3g steps/s" % (Tk, ms0, ms, Bk * Tk / (ms * 1e-3)), flush=True)
+
+kargs = (F, torch.zeros(Bk, D, device=dev), eye(D), H, torch.zeros(Bk, O, device=dev), eye(O), y)
+ms = timeit(lambda: fg.kalman_chain(*kargs, validate=False))
+print("kalman homogeneous path (elements + eta + scan) D=32 B=64 T=%d: %.2f ms -> %.3g steps/s" % (Tk, ms, Bk * Tk / (ms * 1e-3)), flush=True)

@@ -34,20 +34,25 @@ fb.hmm_viterbi(init, A, obs[:, :32].contiguous())
 ok = bool((path[0] == zpath).all())
 print(json.dumps({"config": "C3", "T": T, "S": S, "B": 1, "ms": ms, "units_per_s": T * S * S / ms * 1e3, "us_per_step": ms * 1e3 / T, "planted_path_recovered": ok}), flush=True)
 del A, obs
-# C4: Kalman D=32, O=16, B=64, T as large as fits (dense info-form elements are 16.6 KB each)
-Bk, Tk, D, O = 64, 50000, 32, 16
+# C4: Kalman D=32, O=16, B=64, T=100000, homogeneous dynamics (examples/kalman_filter.py shape): full size
+Bk, Tk, D, O = 64, 100000, 32, 16
 F = 0.9 * torch.linalg.qr(torch.randn(Bk, D, D, device=dev, generator=g))[0]
 H = torch.randn(Bk, D, O, device=dev, generator=g) / D ** 0.5
 eye = lambda n: torch.eye(n, device=dev).expand(Bk, n, n).contiguous()
 y = torch.randn(Bk, Tk, O, device=dev, generator=g)
-w, P, s = fg.kalman_elements_sqrt(F, torch.zeros(Bk, D, device=dev), eye(D), H, torch.zeros(Bk, O, device=dev), eye(O), y)
-(Lam, eta, c), ms0 = timed(lambda: fg.sqrt_to_info(w, P, s))
-del w, P, s
-out, ms = timed(lambda: fg.gaussian_sequential_sum_product(Lam, eta, c, validate=False))
+kargs = (F, torch.zeros(Bk, D, device=dev), eye(D), H, torch.zeros(Bk, O, device=dev), eye(O), y)
+fg.kalman_chain(*[a[:, :64].contiguous() if a.dim() == 3 and a.shape[1] == Tk else a for a in kargs])
+out, ms = timed(lambda: fg.kalman_chain(*kargs, validate=False))
 lp = fg.gaussian_hmm_log_prob(torch.zeros(Bk, D, device=dev), eye(D), out)
-print(json.dumps({"config": "C4", "T": Tk, "B": Bk, "D": D, "O": O, "ms_scan": ms, "ms_sqrt_to_info": ms0, "kalman_steps_per_s": Bk * Tk / ms * 1e3,
-                  "log_prob0": float(lp[0]), "finite": bool(torch.isfinite(lp).all())}), flush=True)
-del Lam, eta, c, out
+# split-and-recombine property: the chain over [0,T) equals the pair contraction of the chains over [0,T/2) and [T/2,T)
+h1 = fg.kalman_chain(*[a[:, :Tk // 2].contiguous() if a.dim() == 3 and a.shape[1] == Tk else a for a in kargs])
+h2 = fg.kalman_chain(*[a[:, Tk // 2:].contiguous() if a.dim() == 3 and a.shape[1] == Tk else a for a in kargs])
+comb = fg.gaussian_pair_combine(h1, h2)
+lp2 = fg.gaussian_hmm_log_prob(torch.zeros(Bk, D, device=dev), eye(D), comb[:3])
+print(json.dumps({"config": "C4", "T": Tk, "B": Bk, "D": D, "O": O, "ms": ms, "kalman_steps_per_s": Bk * Tk / ms * 1e3,
+                  "log_prob0": float(lp[0]), "finite": bool(torch.isfinite(lp).all()),
+                  "split_recombine_rel_err": float(((lp - lp2).abs() / lp.abs()).max())}), flush=True)
+del out, y
 # C5: forward-backward T=1,048,576, S=512, B=1 (single GPU)
 S, T = 512, 1048576
 A = torch.randn(S, S, device=dev, generator=g).log_softmax(-1); obs = torch.randn(1, T, S, device=dev, generator=g); init = torch.randn(1, S, device=dev, generator=g).log_softmax(-1)

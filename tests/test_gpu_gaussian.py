@@ -119,3 +119,26 @@ def test_too_little_information_raises(fg):
     c = torch.zeros(1, 2, device="cuda")
     with pytest.raises(ValueError, match="Too little information"):
         fg.gaussian_sequential_sum_product(Lam, eta, c)
+
+
+@pytest.mark.parametrize("B,T,D,O", [(3, 37, 4, 2), (2, 64, 32, 16), (5, 1, 3, 2), (1, 9, 8, 8)])
+def test_kalman_homogeneous_path_matches_general_path(B, T, D, O):
+    """kalman_chain (time-invariant prec_sqrt, Lam formed once per chain, level 1 reads it with stride 0) against the general
+    path that materialises every element."""
+    import funsor_b200.gaussian as fg
+
+    g = torch.Generator().manual_seed(51)
+    F = 0.9 * torch.linalg.qr(torch.randn(B, D, D, generator=g))[0]
+    H = torch.randn(B, D, O, generator=g) / D ** 0.5
+
+    def tril(n):
+        a = torch.randn(B, n, n, generator=g) * 0.2
+        return torch.tril(a, -1) + torch.diag_embed(0.5 + torch.rand(B, n, generator=g))
+
+    args = [F, torch.randn(B, D, generator=g) * 0.1, tril(D), H, torch.randn(B, O, generator=g) * 0.1, tril(O), torch.randn(B, T, O, generator=g)]
+    args = [a.cuda() for a in args]
+    got = fg.kalman_chain(*args)
+    w, P, s = fg.kalman_elements_sqrt(*args)
+    want = fg.gaussian_sequential_sum_product(*fg.sqrt_to_info(w, P, s))
+    for a, b in zip(got, want):
+        close_norm(host(a), host(b).astype(np.float64), 2e-5)
