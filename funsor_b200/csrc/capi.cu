@@ -3,9 +3,20 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fb2 {
+
+// hmm_flow.cu
+bool hmm_flow_supported(int semiring, int64_t a_sb, int64_t a_st, int S, bool wants_alpha);
+size_t hmm_flow_workspace_bytes(int64_t B, int S);
+int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t obs_T, int64_t B, int64_t T, int S,
+                         float* logZ, double* logZ_d, float* hist_u, int* hist_e, int64_t hist_T, int transpose, int reverse,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream, const unsigned* ready_flags,
+                         int64_t rows_per_chunk);
 
 static thread_local char g_err[512] = "";
 static thread_local int64_t g_launches = 0;
@@ -49,6 +60,8 @@ struct HostArena {
     void* dev = nullptr;
     size_t bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev = nullptr;
 };
 static thread_local HostArena g_arena;
 
@@ -112,6 +125,10 @@ extern "C" int fb2_host_arena_release(void) {
     g_arena.bytes = 0;
     if (g_arena.stream) FB2_CUDA(cudaStreamDestroy(g_arena.stream));
     g_arena.stream = nullptr;
+    if (g_arena.copy_stream) FB2_CUDA(cudaStreamDestroy(g_arena.copy_stream));
+    g_arena.copy_stream = nullptr;
+    if (g_arena.ev) FB2_CUDA(cudaEventDestroy(g_arena.ev));
+    g_arena.ev = nullptr;
     return FB2_OK;
 }
 
@@ -127,19 +144,66 @@ extern "C" int fb2_hmm_forward_f32_host(int semiring, const float* init, int64_t
                 "host entry point needs packed A");
     size_t n_obs = (size_t)B * T * S;
     size_t ws = fb2_hmm_workspace_bytes(0, B, T, S);
-    size_t total = align_up(n_init * 4) + align_up(n_A * 4) + align_up(n_obs * 4) + align_up((size_t)B * 4) + ws;
+    size_t total = align_up(n_init * 4) + align_up(n_A * 4) + align_up(n_obs * 4) + align_up((size_t)B * 4 + 1024) + ws;
     st = arena_reserve(total);
     if (st != FB2_OK) return st;
     Arena ar(g_arena.dev, g_arena.bytes);
     float* d_init = ar.take<float>(n_init);
     float* d_A = ar.take<float>(n_A);
     float* d_obs = ar.take<float>(n_obs);
-    float* d_out = ar.take<float>((size_t)B);
+    float* d_out = ar.take<float>((size_t)B + 256);  // + room for the chunk-ready flags of the overlapped path
     void* d_ws = ar.take<char>(ws);
     cudaStream_t s = g_arena.stream;
     FB2_CUDA(cudaMemcpyAsync(d_init, init, n_init * 4, cudaMemcpyHostToDevice, s));
     FB2_CUDA(cudaMemcpyAsync(d_A, A, n_A * 4, cudaMemcpyHostToDevice, s));
-    FB2_CUDA(cudaMemcpyAsync(d_obs, obs, n_obs * 4, cudaMemcpyHostToDevice, s));
+    const char* ov = getenv("FB2_HOST_OVERLAP");
+    // the driver entry point is resolved through the runtime, so the library itself does not link against libcuda
+    typedef CUresult (*WriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static WriteValue32Fn write_value32 = nullptr;
+    if (!write_value32) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            write_value32 = reinterpret_cast<WriteValue32Fn>(fn);
+        else
+            cudaGetLastError();
+    }
+    const bool overlap = write_value32 != nullptr && hmm_flow_supported(semiring, a_sb, a_st, S, false) && T >= 4096 && !(ov && ov[0] == '0');
+    if (overlap) {
+        // The observations are by far the largest input (4.3 GB at the headline shape) and the pass consumes them in time
+        // order, so their H2D copy is cut into time chunks on a second stream and overlapped with the pass: after each chunk
+        // a stream memory operation (no kernel, so nothing here depends on SM scheduling) raises that chunk's flag, and the
+        // kernel's observation prefetch waits on the flag of the chunk it is about to read.
+        constexpr int NCHUNK = 32;
+        if (!g_arena.copy_stream) FB2_CUDA(cudaStreamCreateWithFlags(&g_arena.copy_stream, cudaStreamNonBlocking));
+        if (!g_arena.ev) FB2_CUDA(cudaEventCreateWithFlags(&g_arena.ev, cudaEventDisableTiming));
+        unsigned* d_flags = reinterpret_cast<unsigned*>(d_out + ((B + 63) / 64) * 64);  // tail of the d_out slot (see reservation)
+        const int64_t rows = (T + NCHUNK - 1) / NCHUNK;
+        FB2_CUDA(cudaMemsetAsync(d_flags, 0, NCHUNK * sizeof(unsigned), s));
+        FB2_CUDA(cudaEventRecord(g_arena.ev, s));
+        FB2_CUDA(cudaStreamWaitEvent(g_arena.copy_stream, g_arena.ev, 0));
+        for (int c = 0; c < NCHUNK; ++c) {
+            const int64_t t0 = c * rows, t1 = (t0 + rows < T) ? t0 + rows : T;
+            if (t0 >= T) break;
+            FB2_CUDA(cudaMemcpy2DAsync(d_obs + t0 * S, (size_t)T * S * 4, obs + t0 * S, (size_t)T * S * 4, (size_t)(t1 - t0) * S * 4, (size_t)B,
+                                       cudaMemcpyHostToDevice, g_arena.copy_stream));
+            if (write_value32((CUstream)g_arena.copy_stream, (CUdeviceptr)(d_flags + c), 1u, 0) != CUDA_SUCCESS) {
+                set_error("cuStreamWriteValue32 failed");
+                return FB2_ERR_CUDA;
+            }
+        }
+        st = hmm_flow_pass_device(d_init, init_sb, d_A, d_obs, T, B, T, S, d_out, nullptr, nullptr, nullptr, 0, 0, 0, d_ws, ws, s, d_flags, rows);
+        if (st == FB2_OK) {
+            FB2_CUDA(cudaMemcpyAsync(logZ, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+            FB2_CUDA(cudaStreamSynchronize(s));
+            FB2_CUDA(cudaStreamSynchronize(g_arena.copy_stream));
+            return FB2_OK;
+        }
+        FB2_CUDA(cudaStreamSynchronize(g_arena.copy_stream));  // declined: obs is resident now, fall through to the plain call
+        if (st != FB2_ERR_UNSUPPORTED) return st;
+    } else {
+        FB2_CUDA(cudaMemcpyAsync(d_obs, obs, n_obs * 4, cudaMemcpyHostToDevice, s));
+    }
     st = fb2_hmm_forward_f32(semiring, d_init, init_sb, d_A, a_sb, a_st, d_obs, B, T, S, d_out, nullptr, d_ws, ws, s);
     if (st != FB2_OK) return st;
     FB2_CUDA(cudaMemcpyAsync(logZ, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, s));

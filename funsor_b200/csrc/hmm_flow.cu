@@ -60,6 +60,8 @@ struct FlowArgs {
     int* hist_e;
     int64_t hist_T;
     int64_t obs_T;   // time extent of the obs array (rows per chain); the pass runs p.T steps over obs rows [0, p.T)
+    const unsigned* ready_flags;  // nullable: obs rows [c*rows_per_chunk, ...) of every chain are resident once ready_flags[c] != 0
+    int64_t rows_per_chunk;       //   (host-buffer entry point: the H2D copy of obs is overlapped with the pass)
     int transpose;   // 1: contract with A^T (backward pass)
     int reverse;     // 1: step t consumes obs row p.T-1-t and writes history slot p.T-1-t
     long long* prof;  // nullable: [gridDim][8] accumulated cycles per phase (FB2_FLOW_PROF=1)
@@ -320,6 +322,18 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
         const bool chain_ok = tc >= 0 && (b0 + bc) < p.B && colC < S;
         const float* obs_c = (chain_ok && p.obs) ? p.obs + ((b0 + bc) * p.obs_T) * S + colC : nullptr;
         auto obs_row = [&](int64_t step) { return p.reverse ? (p.T - 1 - step) : step; };
+        int64_t chunk_seen = -1;
+        auto wait_rows = [&](int64_t row) {  // overlapped H2D: block until the chunk holding `row` has landed
+            if (!p.ready_flags) return;
+            const int64_t c = row / p.rows_per_chunk;
+            if (c == chunk_seen) return;
+            const long long start = clock64();
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ready_flags + c) : "memory");
+            } while (v == 0 && clock64() - start < 20 * FLOW_SPIN_LIMIT);
+            chunk_seen = c;
+        };
 
         // ---- message before the first step: alpha_{-1} = init
         if (tc >= 0) {
@@ -341,7 +355,10 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
         const uint32_t obs_ring = smem_u32(&s_obs[0][tid]);
 #pragma unroll
         for (int q = 0; q < FLOW_OBS_DEPTH - 1; ++q) {
-            if (obs_c && q < p.T) cp_async4(obs_ring + (uint32_t)q * (FLOW_THREADS * 4), obs_c + obs_row(q) * S);
+            if (obs_c && q < p.T) {
+                wait_rows(obs_row(q));
+                cp_async4(obs_ring + (uint32_t)q * (FLOW_THREADS * 4), obs_c + obs_row(q) * S);
+            }
             cp_async_commit();
         }
 
@@ -544,8 +561,10 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 // refill the slot consumed one step ago
                 {
                     const int64_t tn2 = t + FLOW_OBS_DEPTH - 1;
-                    if (obs_c && tn2 < p.T)
+                    if (obs_c && tn2 < p.T) {
+                        wait_rows(obs_row(tn2));
                         cp_async4(obs_ring + (uint32_t)(tn2 % FLOW_OBS_DEPTH) * (FLOW_THREADS * 4), obs_c + obs_row(tn2) * S);
+                    }
                     cp_async_commit();
                 }
                 if (p.prof && tid == FLOW_THREADS - 1) {
@@ -1323,7 +1342,8 @@ static int flow_launch_tc(FlowArgs& a, cudaStream_t stream) {
 
 int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t obs_T, int64_t B, int64_t T, int S,
                          float* logZ, double* logZ_d, float* hist_u, int* hist_e, int64_t hist_T, int transpose, int reverse,
-                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream, const unsigned* ready_flags = nullptr,
+                         int64_t rows_per_chunk = 0);
 
 int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
                             float* logZ, double* logZ_d, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -1336,7 +1356,8 @@ int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, 
 // optionally recording every message (mantissas + block exponents).
 int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t obs_T, int64_t B, int64_t T, int S,
                          float* logZ, double* logZ_d, float* hist_u, int* hist_e, int64_t hist_T, int transpose, int reverse,
-                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream, const unsigned* ready_flags,
+                         int64_t rows_per_chunk) {
     const FlowShape fs = flow_shape(S);
     if (!fs.k16) {
         set_error("hmm flow: S=%d outside the supported range", S);
@@ -1364,6 +1385,7 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
     a.init = init; a.init_sb = init_sb; a.A = A; a.obs = obs; a.cA = cA; a.B = B; a.T = T; a.S = S;
     a.pkt = pkt; a.fin_u = fin_u; a.fin_e = fin_e; a.abort_flag = abort_flag; a.groups_total = (int)groups;
     a.hist_u = hist_u; a.hist_e = hist_e; a.hist_T = hist_T; a.obs_T = obs_T; a.transpose = transpose; a.reverse = reverse;
+    a.ready_flags = ready_flags; a.rows_per_chunk = rows_per_chunk > 0 ? rows_per_chunk : 1;
     const char* mode_env = getenv("FB2_FLOW_MODE");
     a.mode = mode_env ? atoi(mode_env) : 1;  // default: publish packets with atom.exch (store->load hand-over measured ~10 % faster)
     const char* prof_env = getenv("FB2_FLOW_PROF");
@@ -1374,7 +1396,7 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
     // (default: measured 3.4 us/step at S=1024) and tcgen05 kind::tf32 with P in tensor memory (FB2_FLOW_TC=1: 3.7 us/step;
     // its shorter MMA phase is hidden behind the DSMEM reduce-scatter, which moves the same 8 KB per CTA-step either way).
     const char* tc_env = getenv("FB2_FLOW_TC");
-    const bool legacy = !(tc_env && tc_env[0] == '1') || hist_u != nullptr || transpose || reverse;
+    const bool legacy = !(tc_env && tc_env[0] == '1') || hist_u != nullptr || transpose || reverse || ready_flags != nullptr;
     if (!legacy) {
         if (fs.k16 == 1) st = flow_launch_tc<2, 1>(a, stream);
         else if (fs.k16 == 2) st = flow_launch_tc<4, 1>(a, stream);

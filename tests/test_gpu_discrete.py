@@ -534,3 +534,24 @@ def test_hmm_marginals_flow_matches_generic(fb):
         os.environ.pop("FB2_DISABLE_FLOW")
     rel_close(host(z1), host(z2), rtol=RTOL, atol=1.0)
     rel_close(host(g1), host(g2), rtol=1e-4, atol=1.0)
+
+
+def test_host_entry_point_overlapped_copy(fb):
+    """fb2_hmm_forward_f32_host with T >= 4096 cuts the observation upload into time chunks and overlaps it with the pass
+    (chunk-ready flags raised by stream memory operations); the result must equal the device-resident call, also for
+    pageable host memory and for a T that is not a multiple of the chunk count."""
+    from funsor_b200 import _lib
+
+    lib = _lib.load()
+    for B, T, S, pin in [(3, 5003, 128, True), (16, 4096, 256, False)]:
+        g = torch.Generator().manual_seed(61)
+        init = torch.randn(B, S, generator=g).log_softmax(-1)
+        A = torch.randn(S, S, generator=g).log_softmax(-1)
+        obs = torch.randn(B, T, S, generator=g)
+        if pin:
+            obs = obs.pin_memory()
+        out = torch.empty(B)
+        _lib.check(lib.fb2_hmm_forward_f32_host(0, init.data_ptr(), S, A.data_ptr(), 0, 0, obs.data_ptr(), B, T, S, out.data_ptr()))
+        want = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+        np.testing.assert_allclose(out.numpy(), want, rtol=1e-6)
+    lib.fb2_host_arena_release()
