@@ -217,6 +217,55 @@ __device__ __forceinline__ float flow_normalise(float s, float x, int e_in15, in
     return u;
 }
 
+// The same normalisation split in two, so that the observation-only half (group max of x, exp2) runs BEFORE the thread
+// waits for the partial sums and only a short dependent chain remains after the wait.
+struct FlowObs1 {
+    float e2;
+    int nf;
+    int bad;
+};
+__device__ __forceinline__ FlowObs1 flow_obs1(float x, bool check_range) {
+    FlowObs1 o;
+    const float xm = group8_max(x);
+    float nf = 0.f;
+    o.e2 = 0.f;
+    if (xm > -1e30f) {
+        nf = ceilf(xm);
+        o.e2 = exp2f(x - nf);
+    }
+    o.bad = (check_range && xm > -1e30f && !(fabsf(nf) <= 8000.f)) ? 1 : 0;
+    o.nf = (int)nf;
+    return o;
+}
+__device__ __forceinline__ float flow_finish1(float s, const FlowObs1& o, int e_in15, int& E15, bool& zero, int& dE) {
+    float u = s * o.e2;
+    int bad = o.bad | (!(u <= FLT_MAX) ? 1 : 0);
+    float mu = group8_max(u);
+    {
+        unsigned b = __ballot_sync(0xffffffffu, bad);
+        bad = (b >> ((threadIdx.x & 31) & ~7)) & 0xFF ? 1 : 0;  // any lane of this 8-lane group
+    }
+    dE = 0;
+    E15 = e_in15 & 0x7FFF;
+    zero = !(mu > 0.f);
+    if (bad) {
+        zero = false;
+        return __int_as_float(0x7fc00000);
+    }
+    if (zero) return 0.f;
+    int extra = 0;
+    if (mu < 1e-20f) {
+        u *= 0x1p64f;
+        mu *= 0x1p64f;
+        extra = -64;
+    }
+    const int q = ((__float_as_int(mu) >> 23) & 0xFF) - 127;
+    u *= __int_as_float((127 - q) << 23);
+    dE = o.nf + q + extra;
+    E15 = (e_in15 + dE) & 0x7FFF;
+    return u;
+}
+
 // ------------------------------------------------------------------------------------------ the kernel
 // K16 = k16-steps per CTA (Ks = 16*K16 rows of P per CTA, Sp = 8*Ks = 128*K16 padded states);
 // NT  = 8-column n-tiles per warp (a cluster owns 64*NT columns); grid = nsets * (2*K16/NT) clusters of 8.
@@ -502,6 +551,10 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
 
             // ================= phase C: final owners finish their columns and publish =================
             if (tc >= 0) {
+                // observation-only work first: it overlaps the flight time of the partial sums
+                cp_async_wait<FLOW_OBS_DEPTH - 2>();
+                const float ob = obs_c ? s_obs[t % FLOW_OBS_DEPTH][tid] : 0.f;
+                const FlowObs1 oterm = flow_obs1(chain_ok ? (ob + caC) * kLog2e : -INFINITY, true);
                 const long long start = clock64();
                 while (!mbar_try_wait(bar_addr0 + (uint32_t)par * 8, ph)) {
                     if (clock64() - start > FLOW_SPIN_LIMIT) {
@@ -532,14 +585,11 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 // barrier for the step after next.  No sender can be two steps ahead of this CTA.
                 if (tc == 0) mbar_arm(bar_addr0 + (uint32_t)par * 8, TX_BYTES);
                 const long long c_red = p.prof ? clock64() : 0;
-                cp_async_wait<FLOW_OBS_DEPTH - 2>();
-                const float ob = obs_c ? s_obs[t % FLOW_OBS_DEPTH][tid] : 0.f;
-                const float x = chain_ok ? (ob + caC) * kLog2e : -INFINITY;
                 int E15;
                 bool zero;
                 const long long c_obs = p.prof ? clock64() : 0;
                 int dE;
-                const float u = flow_normalise(s, x, emax, E15, zero, dE);
+                const float u = flow_finish1(s, oterm, emax, E15, zero, dE);
                 const long long c_nrm = p.prof ? clock64() : 0;
                 E_abs += sext15(E15 - E_prev);
                 E_prev = E15;
