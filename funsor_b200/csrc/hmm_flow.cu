@@ -1277,6 +1277,134 @@ __global__ void flow_gamma(const float* ua, const int* ea, const float* uw, cons
     gamma[idx] = out;
 }
 
+// ---- summed pairwise posteriors  xi_sum[i,j] = sum_t alpha_{t-1}[i] A[i,j] w_t[j] / Z  from the two recorded passes.
+// Steps 1 .. T-2 are an outer-product accumulation over time (a [S x T] . [T x S] GEMM, 2 T S^2 flops) whose rows are
+// rescaled on the fly: per step t the alpha side is aligned to its largest block exponent Ma_t, the w side to Mw_t, and
+// the scalar 2^(Ma_t + Mw_t - log2 Z) (a probability-sized number) multiplies the alpha side.  The two end steps
+// (alpha_{-1} = init, w_{T-1} = obs_{T-1}) are added by the finalising kernel.
+constexpr int XI_TILE = 64, XI_KC = 16;
+
+__global__ void xi_prep(const int* ea, const int* ew, const double* logZ, int64_t B, int64_t T, int G, int* Ma, int* Mw, float* st) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * T) return;
+    const int64_t t = idx % T, b = idx / T;
+    int ma = INT_MIN, mw = INT_MIN;
+    float sc = 0.f;
+    if (t >= 1 && t <= T - 2) {
+        for (int g = 0; g < G; ++g) {
+            ma = max(ma, ea[(idx - 1) * G + g]);
+            mw = max(mw, ew[idx * G + g]);
+        }
+        if (ma != INT_MIN && mw != INT_MIN) {
+            const double l2 = (double)ma + (double)mw - logZ[b] * 1.4426950408889634074;
+            sc = (float)exp2(fmin(l2, 100.0));
+        }
+    }
+    Ma[idx] = ma;
+    Mw[idx] = mw;
+    st[idx] = sc;
+}
+
+__global__ void __launch_bounds__(256) xi_gemm(const float* ua, const int* ea, const float* uw, const int* ew, const int* Ma, const int* Mw,
+                                               const float* st, int64_t T, int S, int Sp, int ksplit, float* partial) {
+    __shared__ __align__(16) float sa[XI_KC][XI_TILE + 4];
+    __shared__ __align__(16) float sb[XI_KC][XI_TILE + 4];
+    const int G = Sp / 8;
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int i0 = blockIdx.y * XI_TILE, j0 = blockIdx.x * XI_TILE;
+    const int64_t b = blockIdx.z / ksplit;
+    const int ks = blockIdx.z % ksplit;
+    const int64_t span = (T - 2 + ksplit - 1) / ksplit;  // steps 1 .. T-2
+    const int64_t t_lo = 1 + ks * span, t_hi = min(t_lo + span, T - 1);
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    const int lt = tid / 16, lq = (tid % 16) * 4;  // staging: time row lt of the chunk, 4 consecutive states from lq
+    for (int64_t t0 = t_lo; t0 < t_hi; t0 += XI_KC) {
+        const int64_t t = t0 + lt;
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+        if (t < t_hi) {
+            const int64_t ra = b * T + t - 1, rb = b * T + t;
+            const float sc = st[rb];
+            if (sc > 0.f) {
+                if (i0 + lq < Sp) {
+                    const int e = ea[ra * G + (i0 + lq) / 8];
+                    const float f = (e == INT_MIN) ? 0.f : sc * pow2i(e - Ma[rb]);
+                    const float4 v = *reinterpret_cast<const float4*>(ua + ra * Sp + i0 + lq);
+                    av = make_float4(v.x * f, v.y * f, v.z * f, v.w * f);
+                }
+                if (j0 + lq < Sp) {
+                    const int e = ew[rb * G + (j0 + lq) / 8];
+                    const float f = (e == INT_MIN) ? 0.f : pow2i(e - Mw[rb]);
+                    const float4 v = *reinterpret_cast<const float4*>(uw + rb * Sp + j0 + lq);
+                    bv = make_float4(v.x * f, v.y * f, v.z * f, v.w * f);
+                }
+            }
+        }
+        *reinterpret_cast<float4*>(&sa[lt][lq]) = av;
+        *reinterpret_cast<float4*>(&sb[lt][lq]) = bv;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < XI_KC; ++k) {
+            const float4 xv = *reinterpret_cast<const float4*>(&sa[k][ty * 4]);
+            const float4 yv = *reinterpret_cast<const float4*>(&sb[k][tx * 4]);
+            const float xr[4] = {xv.x, xv.y, xv.z, xv.w}, yr[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(xr[r], yr[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+    float* out = partial + ((size_t)blockIdx.z * S) * S;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty * 4 + r;
+        if (i >= S) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = j0 + tx * 4 + c;
+            if (j < S) out[(size_t)i * S + j] = acc[r][c];
+        }
+    }
+}
+
+__global__ void xi_final(const float* init, int64_t init_sb, const float* A, const float* obs, const float* ua, const int* ea, const float* uw,
+                         const int* ew, const double* logZ, const float* partial, int ksplit, int64_t B, int64_t T, int S, int Sp,
+                         float* xi) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)S * S;
+    if (idx >= B * per) return;
+    const int64_t b = idx / per;
+    const int i = (int)((idx % per) / S), j = (int)(idx % S);
+    const int G = Sp / 8;
+    const float a = A[(int64_t)i * S + j];
+    const double z = logZ[b];
+    const double LN2 = 0.69314718055994530942;
+    float sum = 0.f;
+    if (T >= 3) {
+        float m = 0.f;
+        for (int k = 0; k < ksplit; ++k) m += partial[((size_t)(b * ksplit + k) * S + i) * S + j];
+        sum = __expf(a) * m;
+    }
+    const float in_i = init ? init[b * init_sb + i] : 0.f;
+    if (T == 1) {
+        sum += __expf(in_i + a + obs[(b * T) * S + j] - (float)z);
+    } else {
+        // t = 0: alpha_{-1} = init, w_0 from the backward history
+        const int e0 = ew[(b * T) * G + j / 8];
+        const float w0 = uw[(b * T) * Sp + j];
+        if (e0 != INT_MIN && w0 > 0.f) sum += __expf(in_i + a + logf(w0) + (float)((double)e0 * LN2 - z));
+        // t = T-1: alpha_{T-2} from the forward history, w_{T-1} = obs_{T-1}
+        const int e1 = ea[(b * T + T - 2) * G + i / 8];
+        const float a1 = ua[(b * T + T - 2) * Sp + i];
+        if (e1 != INT_MIN && a1 > 0.f) sum += __expf(logf(a1) + a + obs[(b * T + T - 1) * S + j] + (float)((double)e1 * LN2 - z));
+    }
+    xi[idx] = sum;
+}
+
 int flow_padded_states(int S);
 
 // ------------------------------------------------------------------------------------------ host side
@@ -1496,17 +1624,23 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
 }
 
 
+static int xi_ksplit(int64_t T) {
+    int64_t k = (T + 2047) / 2048;
+    return (int)(k < 1 ? 1 : (k > 64 ? 64 : k));
+}
+
 size_t hmm_flow_marginals_workspace_bytes(int64_t B, int64_t T, int S) {
     const size_t Sp = (size_t)flow_padded_states(S);
     if (!Sp) return 0;
     return 2 * (align_up((size_t)B * T * Sp * 4) + align_up((size_t)B * T * (Sp / 8) * 4)) + 2 * align_up((size_t)B * 8) +
-           align_up((size_t)B * 4) + hmm_flow_workspace_bytes(B, S) + 512;
+           align_up((size_t)B * 4) + 3 * align_up((size_t)B * T * 4) + align_up((size_t)B * xi_ksplit(T) * S * S * 4) +
+           hmm_flow_workspace_bytes(B, S) + 512;
 }
 
 // Forward-backward posteriors on the dataflow kernel: a forward pass and a backward pass (= the same kernel on A^T and
 // time-reversed observations, started from obs_{T-1}) record their messages; flow_gamma combines them.
 int hmm_flow_marginals_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
-                              float* logZ, float* gamma, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                              float* logZ, float* gamma, float* xi_sum, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     const int Sp = flow_padded_states(S);
     if (!Sp) return FB2_ERR_UNSUPPORTED;
     Arena arena(workspace, workspace_bytes);
@@ -1517,6 +1651,11 @@ int hmm_flow_marginals_device(const float* init, int64_t init_sb, const float* A
     double* z_d = arena.take<double>((size_t)B);
     double* zb_d = arena.take<double>((size_t)B);
     float* zb = arena.take<float>((size_t)B);
+    const int ksplit = xi_ksplit(T);
+    int* Ma = arena.take<int>((size_t)B * T);
+    int* Mw = arena.take<int>((size_t)B * T);
+    float* stt = arena.take<float>((size_t)B * T);
+    float* partial = arena.take<float>((size_t)B * ksplit * S * S);
     if (!arena.ok()) {
         set_error("hmm flow marginals: workspace too small (%zu bytes)", workspace_bytes);
         return FB2_ERR_WORKSPACE;
@@ -1532,6 +1671,18 @@ int hmm_flow_marginals_device(const float* init, int64_t init_sb, const float* A
     const int64_t n = B * T * (int64_t)S;
     flow_gamma<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(ua, ea, uw, ew, obs, z_d, B, T, S, Sp, gamma);
     FB2_LAUNCH_CHECK();
+    if (xi_sum) {
+        if (T >= 3) {
+            xi_prep<<<(unsigned)ceil_div(B * T, 256), 256, 0, stream>>>(ea, ew, z_d, B, T, Sp / 8, Ma, Mw, stt);
+            FB2_LAUNCH_CHECK();
+            dim3 grid((unsigned)ceil_div(S, XI_TILE), (unsigned)ceil_div(S, XI_TILE), (unsigned)(B * ksplit));
+            xi_gemm<<<grid, 256, 0, stream>>>(ua, ea, uw, ew, Ma, Mw, stt, T, S, Sp, ksplit, partial);
+            FB2_LAUNCH_CHECK();
+        }
+        const int64_t m = B * (int64_t)S * S;
+        xi_final<<<(unsigned)ceil_div(m, 256), 256, 0, stream>>>(init, init_sb, A, obs, ua, ea, uw, ew, z_d, partial, ksplit, B, T, S, Sp, xi_sum);
+        FB2_LAUNCH_CHECK();
+    }
     return FB2_OK;
 }
 

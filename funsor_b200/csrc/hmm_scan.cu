@@ -25,7 +25,7 @@ int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, 
                             float* logZ, double* logZ_d, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t hmm_flow_marginals_workspace_bytes(int64_t B, int64_t T, int S);
 int hmm_flow_marginals_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
-                              float* logZ, float* gamma, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                              float* logZ, float* gamma, float* xi_sum, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // FB2_DISABLE_FLOW=1 forces the generic kernel (A/B testing of the two GPU paths)
 static bool stream_disabled() {
     const char* e = getenv("FB2_DISABLE_STREAM");
@@ -902,10 +902,10 @@ extern "C" int fb2_hmm_marginals_f32(const float* init, int64_t init_sb, const f
     FB2_REQUIRE(logZ && gamma && obs, "null pointer");
     if (B == 0) return FB2_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    // homogeneous chains without the pairwise sum run both passes on the dataflow kernel
-    if (!xi_sum && T >= 2 && hmm_flow_supported(FB2_SEMIRING_LOG, a_sb, a_st, S, false) && !flow_disabled() &&
+    // homogeneous chains run both passes on the dataflow kernel (gamma from the recorded messages, xi_sum as a GEMM over time)
+    if (T >= 2 && hmm_flow_supported(FB2_SEMIRING_LOG, a_sb, a_st, S, false) && !flow_disabled() &&
         workspace_bytes >= hmm_flow_marginals_workspace_bytes(B, T, S)) {
-        st = hmm_flow_marginals_device(init, init_sb, A, obs, B, T, S, logZ, gamma, workspace, workspace_bytes, stream);
+        st = hmm_flow_marginals_device(init, init_sb, A, obs, B, T, S, logZ, gamma, xi_sum, workspace, workspace_bytes, stream);
         if (st != FB2_ERR_UNSUPPORTED) return st;
     }
     Arena arena(workspace, workspace_bytes);

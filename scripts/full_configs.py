@@ -56,9 +56,10 @@ del out, y
 # C5: forward-backward T=1,048,576, S=512, B=1 (single GPU)
 S, T = 512, 1048576
 A = torch.randn(S, S, device=dev, generator=g).log_softmax(-1); obs = torch.randn(1, T, S, device=dev, generator=g); init = torch.randn(1, S, device=dev, generator=g).log_softmax(-1)
-fb.hmm_marginals(init, A, obs[:, :64].contiguous(), want_xi=False)
-(logZ, gamma, _), ms = timed(lambda: fb.hmm_marginals(init, A, obs, want_xi=False))
+fb.hmm_marginals(init, A, obs[:, :64].contiguous(), want_xi=True)
+(logZ, gamma, xi), ms = timed(lambda: fb.hmm_marginals(init, A, obs, want_xi=True))
 norm_err = float((torch.logsumexp(gamma[0, ::4096], -1)).abs().max())
 zf = fb.hmm_forward(init, A, obs)
 print(json.dumps({"config": "C5", "T": T, "S": S, "B": 1, "ms": ms, "units_per_s": 2 * T * S * S / ms * 1e3, "us_per_step": ms * 1e3 / T,
-                  "logZ": float(logZ[0]), "logZ_forward_only": float(zf[0]), "max_abs_log_sum_gamma": norm_err}), flush=True)
+                  "logZ": float(logZ[0]), "logZ_forward_only": float(zf[0]), "max_abs_log_sum_gamma": norm_err,
+                  "xi_sum_total_over_T": float(xi.double().sum() / T)}), flush=True)

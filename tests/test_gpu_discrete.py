@@ -555,3 +555,21 @@ def test_host_entry_point_overlapped_copy(fb):
         want = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
         np.testing.assert_allclose(out.numpy(), want, rtol=1e-6)
     lib.fb2_host_arena_release()
+
+
+@pytest.mark.parametrize("B,T,S", [(1, 100, 130), (3, 40, 512), (2, 2, 300), (2, 3, 96), (1, 5000, 128), (17, 9, 65)])
+def test_hmm_marginals_flow_with_pairwise_sum(fb, B, T, S):
+    """xi_sum on the dataflow path: a rescaled outer-product accumulation over time (split-K GEMM) plus the two end steps."""
+    g = torch.Generator().manual_seed(43)
+    init = torch.randn(B, S, generator=g).log_softmax(-1)
+    A = torch.randn(S, S, generator=g).log_softmax(-1)
+    obs = torch.randn(B, T, S, generator=g) * 2
+    if S == 300:
+        A[:, 7] = -float("inf")
+        obs[1, 1, 17] = -float("inf")
+    logZ, gamma, xi = fb.hmm_marginals(init.cuda(), A.cuda(), obs.cuda(), want_xi=True)
+    wZ, wgamma, wxi = R.hmm_marginals(init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    rel_close(host(logZ), wZ, rtol=RTOL, atol=1.0)
+    rel_close(host(gamma), wgamma, rtol=1e-4, atol=1.0)
+    np.testing.assert_allclose(host(xi), wxi, rtol=2e-4, atol=1e-5 * T)
+    np.testing.assert_allclose(host(xi).sum((-1, -2)), float(T), rtol=1e-4)  # T pairwise distributions, each sums to one
