@@ -343,12 +343,9 @@ int launch_log_matmul_tc(const float* x, const int64_t* xs, const float* y, cons
         const char* m = getenv("FB2_LM_MODE");
         a.mode = m ? atoi(m) : 0;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<128>::SMEM));
-        FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<256>::SMEM));
-        attr_set = true;
-    }
+    // per call, not cached in a static: the attribute is per device and a process may drive more than one
+    FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<128>::SMEM));
+    FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<256>::SMEM));
     const char* bn_env = getenv("FB2_LM_BN");  // A/B switch: force the 128-column tile
     if (J > 128 && !(bn_env && atoi(bn_env) == 128)) {
         dim3 grid((unsigned)ceil_div(J, 256), (unsigned)ceil_div(I, LM_TILE), (unsigned)n);

@@ -303,17 +303,14 @@ def register():
 
 
 def sequential_sum_product(sum_op, prod_op, trans, time, step):
-    """Same signature as funsor.sum_product.sequential_sum_product (652-701) for funsor Tensors on the GPU;
-    funsor/pyro/hmm.py:131 calls that function directly (not through MarkovProduct), so callers that want
-    the fused scan import this one."""
-    import funsor.ops as fops
+    """Same signature as funsor.sum_product.sequential_sum_product (652-701).  funsor/pyro/hmm.py:131, 269, 537 call that
+    function directly (not through MarkovProduct), so callers that want the fused scan import this one: it builds the
+    MarkovProduct term, which the rules registered above evaluate on the GPU (Tensor and Gaussian chain elements alike) or
+    hand to the stock rule; the step renaming of MarkovProduct is undone so that the result has the scan's own inputs."""
+    from funsor.sum_product import MarkovProduct
     from funsor.sum_product import sequential_sum_product as ref_ssp
-    from funsor.tensor import Tensor
 
-    if (isinstance(trans, Tensor) and sum_op in (fops.logaddexp, fops.max) and prod_op is fops.add and len(step) == 1
-            and trans.dtype == "real" and not trans.shape and _fast_ok(trans.data)):
-        ((prev, curr),) = tuple(dict(step).items())
-        data, out_names = markov_named(trans.data, trans.inputs, time.name, prev, curr,
-                                       "logaddexp" if sum_op is fops.logaddexp else "max", _kernel_chain)
-        return Tensor(data, OrderedDict((n, trans.inputs[n]) for n in out_names))
-    return ref_ssp(sum_op, prod_op, trans, time, step)
+    if not _STATE["registered"] or len(step) != 1:
+        return ref_ssp(sum_op, prod_op, trans, time, step)
+    # MarkovProduct with identity step_names == the raw scan (sum_product.py:1052-1064 with no renaming)
+    return MarkovProduct(sum_op, prod_op, trans, time, dict(step))

@@ -244,3 +244,31 @@ def test_gaussian_rule_delegates_on_cpu(funsor):
     assert funsor_plugin.stats()["markov_delegated"] >= 1 and funsor_plugin.stats()["markov_fast"] == 0
     for x, y in zip(_info_of(funsor, before, ["prev", "curr"], 2), _info_of(funsor, after, ["prev", "curr"], 2)):
         assert torch.allclose(x, y, rtol=1e-10, atol=1e-10)
+
+
+def test_plugin_sequential_sum_product_function(funsor):
+    """funsor_plugin.sequential_sum_product (what hmm.py-style direct callers would import) == the reference function, for
+    Tensor and Gaussian chain elements (CPU tensors here, so the rules delegate)."""
+    import funsor.ops as ops
+    from funsor.domains import Bint, Reals
+    from funsor.sum_product import sequential_sum_product as ref_ssp
+    from funsor.tensor import Tensor
+    from funsor.terms import Variable
+    from funsor.testing import random_gaussian
+
+    from funsor_b200 import funsor_plugin
+
+    funsor_plugin.register()
+    torch.manual_seed(6)
+    tv = Variable("time", Bint[6])
+    trans = Tensor(torch.randn(2, 6, 3, 3), OrderedDict(b=Bint[2], time=Bint[6], prev=Bint[3], curr=Bint[3]))
+    for op in (ops.logaddexp, ops.max):
+        want = ref_ssp(op, ops.add, trans, tv, {"prev": "curr"})
+        got = funsor_plugin.sequential_sum_product(op, ops.add, trans, tv, {"prev": "curr"})
+        assert isinstance(got, Tensor) and set(got.inputs) == set(want.inputs)
+        assert torch.allclose(got.align(tuple(want.inputs)).data, want.data, rtol=1e-10, atol=1e-10)
+    g = random_gaussian(OrderedDict(b=Bint[2], time=Bint[6], prev=Reals[2], curr=Reals[2]))
+    want = ref_ssp(ops.logaddexp, ops.add, g, tv, {"prev": "curr"})
+    got = funsor_plugin.sequential_sum_product(ops.logaddexp, ops.add, g, tv, {"prev": "curr"})
+    for x, y in zip(_info_of(funsor, want, ["prev", "curr"], 2), _info_of(funsor, got, ["prev", "curr"], 2)):
+        assert torch.allclose(x, y, rtol=1e-9, atol=1e-9)

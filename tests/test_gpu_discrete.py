@@ -573,3 +573,43 @@ def test_hmm_marginals_flow_with_pairwise_sum(fb, B, T, S):
     rel_close(host(gamma), wgamma, rtol=1e-4, atol=1.0)
     np.testing.assert_allclose(host(xi), wxi, rtol=2e-4, atol=1e-5 * T)
     np.testing.assert_allclose(host(xi).sum((-1, -2)), float(T), rtol=1e-4)  # T pairwise distributions, each sums to one
+
+
+# ------------------------------------------------------------------ edge cases across the ABI
+def test_edge_cases_empty_batch_and_single_step(fb):
+    S = 130
+    g = torch.Generator().manual_seed(71)
+    A = torch.randn(S, S, generator=g).log_softmax(-1).cuda()
+    # empty batch: every entry point returns an empty result without launching
+    z = fb.hmm_forward(torch.empty(0, S).cuda(), A, torch.empty(0, 5, S).cuda())
+    assert z.shape == (0,)
+    best, path = fb.hmm_viterbi(torch.empty(0, S).cuda(), A, torch.empty(0, 5, S).cuda())
+    assert best.shape == (0,) and path.shape == (0, 6)
+    out = fb.sequential_sum_product("logaddexp", "add", torch.empty(0, 4, 8, 8).cuda())
+    assert out.shape == (0, 8, 8)
+    # a single time step on every path
+    init = torch.randn(2, S, generator=g).log_softmax(-1)
+    obs = torch.randn(2, 1, S, generator=g)
+    for op, sid in (("logaddexp", R.LOG), ("max", R.MAX)):
+        got = host(fb.hmm_forward(init.cuda(), A, obs.cuda(), sum_op=op))
+        want = R.hmm_forward(sid, init.double().numpy(), host(A).astype(np.float64), obs.double().numpy())
+        rel_close(got, want, rtol=RTOL, atol=1.0)
+    logZ, gamma, xi = fb.hmm_marginals(init.cuda(), A, obs.cuda())
+    wZ, wgamma, wxi = R.hmm_marginals(init.double().numpy(), host(A).astype(np.float64), obs.double().numpy())
+    rel_close(host(logZ), wZ, rtol=RTOL, atol=1.0)
+    rel_close(host(gamma), wgamma, rtol=1e-4, atol=1.0)
+    np.testing.assert_allclose(host(xi), wxi, rtol=1e-4, atol=1e-5)
+    best, path = fb.hmm_viterbi(init.cuda(), A, obs.cuda())
+    wbest, wpath = R.viterbi(init.numpy(), host(A), obs.numpy())
+    assert np.array_equal(host(best), wbest) and np.array_equal(host(path), wpath)
+
+
+def test_rejects_cpu_tensors_and_wrong_dtype(fb):
+    """No CPU fallback: CPU tensors and non-fp32 dtypes raise instead of computing somewhere else."""
+    A = torch.zeros(8, 8)
+    with pytest.raises(ValueError):
+        fb.hmm_forward(torch.zeros(1, 8), A, torch.zeros(1, 3, 8))
+    with pytest.raises(ValueError):
+        fb.hmm_forward(torch.zeros(1, 8).cuda(), A.cuda().double(), torch.zeros(1, 3, 8).cuda())
+    with pytest.raises(NotImplementedError):
+        fb.sequential_sum_product("add", "mul", torch.zeros(1, 2, 4, 4).cuda())
