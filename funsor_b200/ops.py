@@ -104,6 +104,8 @@ def sequential_sum_product(sum_op, prod_op, trans, time=-3):
     t4 = trans.reshape((-1, T, S, S)) if len(batch) != 1 else trans
     B = t4.shape[0]
     out = torch.empty((B, S, S), dtype=torch.float32, device=trans.device)
+    if B == 0:  # empty batch (torch hands out a null data pointer for empty tensors)
+        return out.reshape(batch + (S, S))
     lib = _lib.load()
     nbytes = lib.fb2_chain_product_workspace_bytes(B, T, S)
     ws = _workspace(nbytes, trans.device)
@@ -182,6 +184,8 @@ def hmm_forward(init, A, obs, sum_op="logaddexp", return_alpha=False):
     init_t, init_sb, A, a_sb, a_st, obs, B, T, S = _hmm_args(init, A, obs)
     out = torch.empty((B,), dtype=torch.float32, device=obs.device)
     alpha = torch.empty((B, T, S), dtype=torch.float32, device=obs.device) if return_alpha else None
+    if B == 0:
+        return (out, alpha) if return_alpha else out
     lib = _lib.load()
     ws = _workspace(lib.fb2_hmm_workspace_bytes(0, B, T, S), obs.device)
     with torch.cuda.device(obs.device):
@@ -196,6 +200,8 @@ def hmm_viterbi(init, A, obs):
     init_t, init_sb, A, a_sb, a_st, obs, B, T, S = _hmm_args(init, A, obs)
     best = torch.empty((B,), dtype=torch.float32, device=obs.device)
     path = torch.empty((B, T + 1), dtype=torch.int64, device=obs.device)
+    if B == 0:
+        return best, path
     lib = _lib.load()
     ws = _workspace(lib.fb2_hmm_workspace_bytes(1, B, T, S), obs.device)
     with torch.cuda.device(obs.device):
@@ -211,6 +217,8 @@ def hmm_marginals(init, A, obs, want_xi=True):
     logZ = torch.empty((B,), dtype=torch.float32, device=obs.device)
     gamma = torch.empty((B, T, S), dtype=torch.float32, device=obs.device)
     xi = torch.empty((B, S, S), dtype=torch.float32, device=obs.device) if want_xi else None
+    if B == 0:
+        return logZ, gamma, xi
     lib = _lib.load()
     ws = _workspace(lib.fb2_hmm_workspace_bytes(2, B, T, S), obs.device)
     with torch.cuda.device(obs.device):
