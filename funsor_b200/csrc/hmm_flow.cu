@@ -1405,6 +1405,17 @@ __global__ void xi_final(const float* init, int64_t init_sb, const float* A, con
     xi[idx] = sum;
 }
 
+// alpha[b,t,j] = log of the recorded message (mantissa, block exponent) as fp32
+__global__ void flow_alpha_from_history(const float* u, const int* e, int64_t BT, int S, int Sp, float* alpha) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= BT * (int64_t)S) return;
+    const int j = (int)(idx % S);
+    const int64_t bt = idx / S;
+    const float m = u[bt * Sp + j];
+    const int ex = e[bt * (Sp / 8) + j / 8];
+    alpha[idx] = (ex == INT_MIN || !(m > 0.f)) ? -INFINITY : (float)((double)ex * 0.69314718055994530942 + (double)logf(m));
+}
+
 int flow_padded_states(int S);
 
 // ------------------------------------------------------------------------------------------ host side
@@ -1683,6 +1694,34 @@ int hmm_flow_marginals_device(const float* init, int64_t init_sb, const float* A
         xi_final<<<(unsigned)ceil_div(m, 256), 256, 0, stream>>>(init, init_sb, A, obs, ua, ea, uw, ew, z_d, partial, ksplit, B, T, S, Sp, xi_sum);
         FB2_LAUNCH_CHECK();
     }
+    return FB2_OK;
+}
+
+
+size_t hmm_flow_alpha_workspace_bytes(int64_t B, int64_t T, int S) {
+    const size_t Sp = (size_t)flow_padded_states(S);
+    if (!Sp) return 0;
+    return align_up((size_t)B * T * Sp * 4) + align_up((size_t)B * T * (Sp / 8) * 4) + hmm_flow_workspace_bytes(B, S) + 512;
+}
+
+// forward pass that also returns every filtered message alpha[B,T,S] (log domain)
+int hmm_flow_forward_alpha_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
+                                  float* logZ, float* alpha, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    const int Sp = flow_padded_states(S);
+    if (!Sp) return FB2_ERR_UNSUPPORTED;
+    Arena arena(workspace, workspace_bytes);
+    float* ua = arena.take<float>((size_t)B * T * Sp);
+    int* ea = arena.take<int>((size_t)B * T * (Sp / 8));
+    if (!arena.ok()) {
+        set_error("hmm flow forward+alpha: workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    char* rest = static_cast<char*>(workspace) + arena.used;
+    int st = hmm_flow_pass_device(init, init_sb, A, obs, T, B, T, S, logZ, nullptr, ua, ea, T, 0, 0, rest, workspace_bytes - arena.used, stream);
+    if (st != FB2_OK) return st;
+    const int64_t n = B * T * (int64_t)S;
+    flow_alpha_from_history<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(ua, ea, B * T, S, Sp, alpha);
+    FB2_LAUNCH_CHECK();
     return FB2_OK;
 }
 

@@ -26,6 +26,9 @@ int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, 
 size_t hmm_flow_marginals_workspace_bytes(int64_t B, int64_t T, int S);
 int hmm_flow_marginals_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
                               float* logZ, float* gamma, float* xi_sum, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t hmm_flow_alpha_workspace_bytes(int64_t B, int64_t T, int S);
+int hmm_flow_forward_alpha_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
+                                  float* logZ, float* alpha, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // FB2_DISABLE_FLOW=1 forces the generic kernel (A/B testing of the two GPU paths)
 static bool stream_disabled() {
     const char* e = getenv("FB2_DISABLE_STREAM");
@@ -833,6 +836,11 @@ using namespace fb2;
 extern "C" size_t fb2_hmm_workspace_bytes(int op, int64_t B, int64_t T, int32_t S) {
     size_t base = vec_bytes(B, S) + ctr_bytes() + 512;
     if (op == 0) base += hmm_flow_workspace_bytes(B, S);
+    if (op == 3) {  // forward with the alpha history
+        const size_t fa = hmm_flow_alpha_workspace_bytes(B, T, S);
+        base += hmm_flow_workspace_bytes(B, S);
+        if (fa > base) base = fa;
+    }
     if (op <= 1 && S >= 256) base += align_up((size_t)((S + 31) / 32) * S * 32 * sizeof(float));  // strip-major copy of A
     if (op == 1) base += align_up((size_t)B * T * S * sizeof(int32_t)) + align_up((size_t)B * sizeof(int32_t));
     if (op == 2) {
@@ -854,6 +862,12 @@ extern "C" int fb2_hmm_forward_f32(int semiring, const float* init, int64_t init
     if (B == 0) return FB2_OK;
     // time-homogeneous log-semiring chains take the dataflow kernel (hmm_flow.cu); everything else, and
     // shapes it declines, run the generic cooperative kernel above.  Both are GPU paths.
+    if (alpha_all != nullptr && hmm_flow_supported(semiring, a_sb, a_st, S, false) && !flow_disabled() &&
+        workspace_bytes >= hmm_flow_alpha_workspace_bytes(B, T, S)) {
+        st = hmm_flow_forward_alpha_device(init, init_sb, A, obs, B, T, S, logZ, alpha_all, workspace, workspace_bytes,
+                                           static_cast<cudaStream_t>(stream));
+        if (st != FB2_ERR_UNSUPPORTED) return st;
+    }
     if (hmm_flow_supported(semiring, a_sb, a_st, S, alpha_all != nullptr) && !flow_disabled()) {
         const size_t fw = hmm_flow_workspace_bytes(B, S);
         if (workspace_bytes >= fw) {

@@ -187,7 +187,7 @@ def hmm_forward(init, A, obs, sum_op="logaddexp", return_alpha=False):
     if B == 0:
         return (out, alpha) if return_alpha else out
     lib = _lib.load()
-    ws = _workspace(lib.fb2_hmm_workspace_bytes(0, B, T, S), obs.device)
+    ws = _workspace(lib.fb2_hmm_workspace_bytes(3 if return_alpha else 0, B, T, S), obs.device)
     with torch.cuda.device(obs.device):
         check(lib.fb2_hmm_forward_f32(semi, _ptr(init_t), init_sb, A.data_ptr(), a_sb, a_st, obs.data_ptr(), B, T, S,
                                       out.data_ptr(), _ptr(alpha), ws.data_ptr(), ws.numel(), _stream()))

@@ -87,7 +87,7 @@ int fb2_chain_product_f32(int semiring, const float* trans, const int64_t trans_
  * marginals (examples/forward_backward.py:58-107,162): logZ[B], gamma[B,T,S] = log p(z_t | obs),
  *           xi_sum (nullable) [B,S,S] = sum_t p(z_{t-1}=i, z_t=j | obs).
  */
-size_t fb2_hmm_workspace_bytes(int op /*0 fwd, 1 viterbi, 2 marginals*/, int64_t B, int64_t T, int32_t S);
+size_t fb2_hmm_workspace_bytes(int op /*0 fwd, 1 viterbi, 2 marginals, 3 fwd with alpha_all*/, int64_t B, int64_t T, int32_t S);
 int fb2_hmm_forward_f32(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb,
                         int64_t a_st, const float* obs, int64_t B, int64_t T, int32_t S, float* logZ,
                         float* alpha_all, void* workspace, size_t workspace_bytes, void* stream);
