@@ -29,6 +29,10 @@ int hmm_flow_marginals_device(const float* init, int64_t init_sb, const float* A
 size_t hmm_flow_alpha_workspace_bytes(int64_t B, int64_t T, int S);
 int hmm_flow_forward_alpha_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
                                   float* logZ, float* alpha, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// hmm_small.cu
+bool hmm_small_supported(int semiring, int64_t a_st, int S);
+int hmm_small_forward_device(const float* init, int64_t init_sb, const float* A, int64_t a_sb, const float* obs, int64_t B, int64_t T, int S,
+                             float* logZ, float* alpha_all, cudaStream_t stream);
 // FB2_DISABLE_FLOW=1 forces the generic kernel (A/B testing of the two GPU paths)
 static bool stream_disabled() {
     const char* e = getenv("FB2_DISABLE_STREAM");
@@ -862,6 +866,9 @@ extern "C" int fb2_hmm_forward_f32(int semiring, const float* init, int64_t init
     if (B == 0) return FB2_OK;
     // time-homogeneous log-semiring chains take the dataflow kernel (hmm_flow.cu); everything else, and
     // shapes it declines, run the generic cooperative kernel above.  Both are GPU paths.
+    // small state spaces: one warp per chain, no inter-CTA traffic
+    if (hmm_small_supported(semiring, a_st, S) && !flow_disabled())
+        return hmm_small_forward_device(init, init_sb, A, a_sb, obs, B, T, S, logZ, alpha_all, static_cast<cudaStream_t>(stream));
     if (alpha_all != nullptr && hmm_flow_supported(semiring, a_sb, a_st, S, false) && !flow_disabled() &&
         workspace_bytes >= hmm_flow_alpha_workspace_bytes(B, T, S)) {
         st = hmm_flow_forward_alpha_device(init, init_sb, A, obs, B, T, S, logZ, alpha_all, workspace, workspace_bytes,

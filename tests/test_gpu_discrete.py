@@ -615,3 +615,35 @@ def test_rejects_cpu_tensors_and_wrong_dtype(fb):
         fb.hmm_forward(torch.zeros(1, 8).cuda(), A.cuda().double(), torch.zeros(1, 3, 8).cuda())
     with pytest.raises(NotImplementedError):
         fb.sequential_sum_product("add", "mul", torch.zeros(1, 2, 4, 4).cuda())
+
+
+# ------------------------------------------------------------------ small state spaces: one warp per chain (hmm_small.cu)
+@pytest.mark.parametrize("B,T,S,amode", [(1, 100, 16, "shared"), (40, 25, 16, "shared"), (7, 300, 5, "shared"), (3, 50, 33, "shared"),
+                                         (9, 40, 64, "shared"), (5, 30, 12, "batched"), (2, 1, 8, "shared"), (130, 17, 32, "batched")])
+def test_hmm_forward_small_state_space(fb, B, T, S, amode):
+    g = torch.Generator().manual_seed(81)
+    init = torch.randn(B, S, generator=g).log_softmax(-1)
+    A = torch.randn(*((S, S) if amode == "shared" else (B, S, S)), generator=g).log_softmax(-1)
+    obs = torch.randn(B, T, S, generator=g) * 2
+    if S == 12:
+        A[:, :, 3] = -float("inf")
+        obs[1, 2, 5] = -float("inf")
+    fb.launch_count(reset=True)
+    got, alpha = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda(), return_alpha=True)
+    assert fb.launch_count() == 1  # a single kernel, no barrier / packet machinery
+    want, walpha = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy(), want_alpha=True)
+    rel_close(host(got), want, rtol=RTOL, atol=1.0)
+    rel_close(host(alpha), walpha, rtol=RTOL, atol=max(1.0, T / 10.0))
+
+
+def test_hmm_forward_small_long_chain_and_dead_chain(fb):
+    B, T, S = 3, 20000, 16
+    g = torch.Generator(device="cuda").manual_seed(82)
+    obs = torch.randn(B, T, S, device="cuda", generator=g) - 40.0  # log Z ~ -8e5: the integer exponent carries it
+    init = torch.randn(B, S, device="cuda", generator=g).log_softmax(-1)
+    A = torch.full((S, S), -float(np.log(S)), device="cuda")
+    obs[2, 7, :] = -float("inf")  # impossible observation: -inf, not NaN
+    got = host(fb.hmm_forward(init, A, obs))
+    want = host(torch.logsumexp(init.double(), -1) + (torch.logsumexp(obs.double(), -1) - np.log(S)).sum(-1))
+    assert np.isneginf(got[2])
+    rel_close(got[:2], want[:2], rtol=RTOL)
