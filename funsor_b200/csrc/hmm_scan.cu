@@ -31,8 +31,8 @@ int hmm_flow_forward_alpha_device(const float* init, int64_t init_sb, const floa
                                   float* logZ, float* alpha, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // hmm_small.cu
 bool hmm_small_supported(int semiring, int64_t a_st, int S);
-int hmm_small_forward_device(const float* init, int64_t init_sb, const float* A, int64_t a_sb, const float* obs, int64_t B, int64_t T, int S,
-                             float* logZ, float* alpha_all, cudaStream_t stream);
+int hmm_small_forward_device(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb, const float* obs, int64_t B,
+                             int64_t T, int S, float* logZ, float* alpha_all, int32_t* backptr, int32_t* last, cudaStream_t stream);
 // FB2_DISABLE_FLOW=1 forces the generic kernel (A/B testing of the two GPU paths)
 static bool stream_disabled() {
     const char* e = getenv("FB2_DISABLE_STREAM");
@@ -845,7 +845,7 @@ extern "C" size_t fb2_hmm_workspace_bytes(int op, int64_t B, int64_t T, int32_t 
         base += hmm_flow_workspace_bytes(B, S);
         if (fa > base) base = fa;
     }
-    if (op <= 1 && S >= 256) base += align_up((size_t)((S + 31) / 32) * S * 32 * sizeof(float));  // strip-major copy of A
+    if ((op <= 1 || op == 3) && S >= 256) base += align_up((size_t)((S + 31) / 32) * S * 32 * sizeof(float));  // strip-major copy of A
     if (op == 1) base += align_up((size_t)B * T * S * sizeof(int32_t)) + align_up((size_t)B * sizeof(int32_t));
     if (op == 2) {
         base += align_up((size_t)B * T * S * sizeof(float)) + 2 * align_up((size_t)B * T * 8) + align_up((size_t)B * 8);
@@ -868,7 +868,8 @@ extern "C" int fb2_hmm_forward_f32(int semiring, const float* init, int64_t init
     // shapes it declines, run the generic cooperative kernel above.  Both are GPU paths.
     // small state spaces: one warp per chain, no inter-CTA traffic
     if (hmm_small_supported(semiring, a_st, S) && !flow_disabled())
-        return hmm_small_forward_device(init, init_sb, A, a_sb, obs, B, T, S, logZ, alpha_all, static_cast<cudaStream_t>(stream));
+        return hmm_small_forward_device(semiring, init, init_sb, A, a_sb, obs, B, T, S, logZ, alpha_all, nullptr, nullptr,
+                                        static_cast<cudaStream_t>(stream));
     if (alpha_all != nullptr && hmm_flow_supported(semiring, a_sb, a_st, S, false) && !flow_disabled() &&
         workspace_bytes >= hmm_flow_alpha_workspace_bytes(B, T, S)) {
         st = hmm_flow_forward_alpha_device(init, init_sb, A, obs, B, T, S, logZ, alpha_all, workspace, workspace_bytes,
@@ -905,8 +906,11 @@ extern "C" int fb2_hmm_viterbi_f32(const float* init, int64_t init_sb, const flo
         set_error("viterbi: workspace too small (%zu bytes)", workspace_bytes);
         return FB2_ERR_WORKSPACE;
     }
-    st = hmm_forward_device(FB2_SEMIRING_MAX, init, init_sb, A, a_sb, a_st, obs, nullptr, B, T, S, best, nullptr, bp, last,
-                            static_cast<char*>(workspace) + arena.used, workspace_bytes - arena.used, stream);
+    if (hmm_small_supported(FB2_SEMIRING_MAX, a_st, S) && !flow_disabled())
+        st = hmm_small_forward_device(FB2_SEMIRING_MAX, init, init_sb, A, a_sb, obs, B, T, S, best, nullptr, bp, last, stream);
+    else
+        st = hmm_forward_device(FB2_SEMIRING_MAX, init, init_sb, A, a_sb, a_st, obs, nullptr, B, T, S, best, nullptr, bp, last,
+                                static_cast<char*>(workspace) + arena.used, workspace_bytes - arena.used, stream);
     if (st != FB2_OK) return st;
     viterbi_backtrace<<<(unsigned)ceil_div(B, 64), 64, 0, stream>>>(bp, last, B, T, S, path);
     FB2_LAUNCH_CHECK();

@@ -169,10 +169,105 @@ __global__ void __launch_bounds__(SM_WARPS * 32) hmm_small_forward(SmallArgs p) 
     if (lane == 0) p.logZ[b] = tot > 0.f ? (float)((double)E * 0.69314718055994530942 + log((double)tot)) : (tot == tot ? -INFINITY : tot);
 }
 
-bool hmm_small_supported(int semiring, int64_t a_st, int S) { return semiring == FB2_SEMIRING_LOG && a_st == 0 && S >= 1 && S <= 64; }
+// Max-plus twin (Viterbi for small state spaces): lane j scans the predecessors i in ascending order with a strict '>' on
+//   delta[i] + (A[i,j] + obs[t,j])      (the reference's evaluation order, hmm.py:130; first maximiser wins)
+// so values and back-pointers are bit-identical to the serial fp32 recurrence.  A is kept in shared memory untransformed.
+template <int NJ, int NL>
+__global__ void __launch_bounds__(SM_WARPS * 32) hmm_small_maxplus(SmallArgs p, int32_t* backptr, int32_t* last) {
+    extern __shared__ __align__(16) float sm_raw[];
+    constexpr int SP = NJ * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.S;
+    const bool shared_A = p.a_sb == 0;
+    float* sA = sm_raw + (shared_A ? 0 : (size_t)warp * SP * SP);
+    const int64_t b = (int64_t)blockIdx.x * SM_WARPS + warp;
+    const bool live = b < p.B;
+    {
+        const float* Ab = p.A + (shared_A ? 0 : (live ? b : 0) * p.a_sb);
+        const int nthreads = shared_A ? SM_WARPS * 32 : 32;
+        const int t0 = shared_A ? threadIdx.x : lane;
+        for (int idx = t0; idx < SP * SP; idx += nthreads) {
+            const int i = idx / SP, j = idx % SP;
+            sA[idx] = (i < S && j < S) ? Ab[(int64_t)i * S + j] : kNegInf;
+        }
+        if (shared_A) __syncthreads();
+        else __syncwarp();
+    }
+    if (!live) return;
+    float d[NJ];
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) {
+        const int j = lane + 32 * q;
+        d[q] = j < S ? (p.init ? p.init[b * p.init_sb + j] : 0.f) : kNegInf;
+    }
+    const float* obs_b = p.obs ? p.obs + b * p.T * S : nullptr;
+    for (int64_t t = 0; t < p.T; ++t) {
+        float ob[NJ], best[NJ];
+        int arg[NJ];
+#pragma unroll
+        for (int q = 0; q < NJ; ++q) {
+            const int j = lane + 32 * q;
+            ob[q] = (obs_b && j < S) ? __ldg(obs_b + t * S + j) : 0.f;
+            best[q] = kNegInf;
+            arg[q] = 0;
+        }
+#pragma unroll
+        for (int qi = 0; qi < NJ; ++qi)
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                const int i = l + 32 * qi;
+                const float di = __shfl_sync(0xffffffffu, d[qi], l);
+#pragma unroll
+                for (int q = 0; q < NJ; ++q) {
+                    const float v = di + (sA[i * SP + lane + 32 * q] + ob[q]);
+                    if (v > best[q]) {
+                        best[q] = v;
+                        arg[q] = i;
+                    }
+                }
+            }
+#pragma unroll
+        for (int q = 0; q < NJ; ++q) {
+            const int j = lane + 32 * q;
+            d[q] = j < S ? best[q] : kNegInf;
+            if (j < S) {
+                if (backptr) backptr[(b * p.T + t) * S + j] = arg[q];
+                if (p.alpha_all) p.alpha_all[(b * p.T + t) * S + j] = best[q];
+            }
+        }
+    }
+    // best final state, first index on ties
+    float m = kNegInf;
+    int am = 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) {
+        const int j = lane + 32 * q;
+        if (j < S && (d[q] > m || (d[q] == m && j < am))) {
+            m = d[q];
+            am = j;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+        if (om > m || (om == m && oa < am)) {
+            m = om;
+            am = oa;
+        }
+    }
+    if (lane == 0) {
+        p.logZ[b] = m;
+        if (last) last[b] = am == 0x7fffffff ? 0 : am;
+    }
+}
 
-int hmm_small_forward_device(const float* init, int64_t init_sb, const float* A, int64_t a_sb, const float* obs, int64_t B, int64_t T, int S,
-                             float* logZ, float* alpha_all, cudaStream_t stream) {
+bool hmm_small_supported(int semiring, int64_t a_st, int S) {
+    return (semiring == FB2_SEMIRING_LOG || semiring == FB2_SEMIRING_MAX) && a_st == 0 && S >= 1 && S <= 64;
+}
+
+int hmm_small_forward_device(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb, const float* obs, int64_t B,
+                             int64_t T, int S, float* logZ, float* alpha_all, int32_t* backptr, int32_t* last, cudaStream_t stream) {
     SmallArgs a;
     a.init = init; a.init_sb = init_sb; a.A = A; a.a_sb = a_sb; a.obs = obs; a.B = B; a.T = T; a.S = S; a.logZ = logZ; a.alpha_all = alpha_all;
     const int NJ = S <= 32 ? 1 : 2;
@@ -184,11 +279,22 @@ int hmm_small_forward_device(const float* init, int64_t init_sb, const float* A,
         FB2_CUDA(cudaFuncSetAttribute(hmm_small_forward<NJv, NLv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         hmm_small_forward<NJv, NLv><<<grid, SM_WARPS * 32, smem, stream>>>(a);                                                  \
     } while (0)
-    if (S <= 8) FB2_SMALL(1, 8);
+#define FB2_SMALLMAX(NJv, NLv)                                                                                                 \
+    do {                                                                                                                        \
+        FB2_CUDA(cudaFuncSetAttribute(hmm_small_maxplus<NJv, NLv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        hmm_small_maxplus<NJv, NLv><<<grid, SM_WARPS * 32, smem, stream>>>(a, backptr, last);                                   \
+    } while (0)
+    if (semiring == FB2_SEMIRING_MAX) {
+        if (S <= 8) FB2_SMALLMAX(1, 8);
+        else if (S <= 16) FB2_SMALLMAX(1, 16);
+        else if (S <= 32) FB2_SMALLMAX(1, 32);
+        else FB2_SMALLMAX(2, 32);
+    } else if (S <= 8) FB2_SMALL(1, 8);
     else if (S <= 16) FB2_SMALL(1, 16);
     else if (S <= 32) FB2_SMALL(1, 32);
     else FB2_SMALL(2, 32);
 #undef FB2_SMALL
+#undef FB2_SMALLMAX
     FB2_LAUNCH_CHECK();
     return FB2_OK;
 }

@@ -647,3 +647,23 @@ def test_hmm_forward_small_long_chain_and_dead_chain(fb):
     want = host(torch.logsumexp(init.double(), -1) + (torch.logsumexp(obs.double(), -1) - np.log(S)).sum(-1))
     assert np.isneginf(got[2])
     rel_close(got[:2], want[:2], rtol=RTOL)
+
+
+@pytest.mark.parametrize("B,T,S,amode", [(2, 50, 16, "shared"), (40, 25, 5, "shared"), (3, 60, 33, "batched"), (130, 17, 64, "shared"), (1, 1, 8, "shared")])
+def test_viterbi_small_state_space_bit_exact(fb, B, T, S, amode):
+    g = torch.Generator().manual_seed(83)
+    init = torch.randn(B, S, generator=g)
+    A = torch.randn(*((S, S) if amode == "shared" else (B, S, S)), generator=g)
+    obs = torch.randn(B, T, S, generator=g)
+    if S == 5:  # ties and unreachable states
+        A[:, 2] = -float("inf")
+        A[:, 3:] = 0.5
+        obs[:, :, 3:] = 0.25
+    fb.launch_count(reset=True)
+    best, path = fb.hmm_viterbi(init.cuda(), A.cuda(), obs.cuda())
+    assert fb.launch_count() == 2  # warp-per-chain forward + backtrace
+    wbest, wpath = R.viterbi(init.numpy(), A.numpy(), obs.numpy())
+    assert np.array_equal(host(best), wbest)
+    assert np.array_equal(host(path), wpath)
+    z, delta = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda(), sum_op="max", return_alpha=True)
+    assert np.array_equal(host(z), wbest)
