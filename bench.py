@@ -243,8 +243,13 @@ def main():
     flops = 2.0 * units_per_step_rank
     achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
     hbm_bytes = (obs.numel() + A.numel() + init.numel()) * 4
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if args.workload == "c2" and os.path.exists(tpath):  # dram bytes of one launch of the dominant kernel, from the committed ncu capture
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops"],
-                "traffic": None, "kernel": "hmm_flow_forward<8,2>", "kernel_ms": kernel_ms, "peak_source": peaks["src"],
+                "traffic": traffic, "kernel": "hmm_flow_forward<8,2>", "kernel_ms": kernel_ms, "peak_source": peaks["src"],
                 "algorithmic_flops_per_launch": flops, "us_per_time_step": kernel_ms * 1e3 / T,
                 "note": "T dependent steps of a [16x1024]x[1024x1024] product: latency-bound (one L2 hand-over is 936 cycles "
                         "measured, plus a DSMEM reduce per step), DESIGN.md section 3; dram traffic = algorithmic (profiles/)",
