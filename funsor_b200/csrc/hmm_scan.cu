@@ -62,7 +62,8 @@ struct HmmArgs {
     int groups_total, groups_conc;
     double* ell_all;     // nullable [B,T]: when given, alpha_all holds NORMALISED messages and ell_all their offsets
     double* out_d;       // nullable [B]: out in double (LOG)
-    float* alpha_last;   // nullable [B,S]: alpha_{T-1} (forward) with its offset folded in
+    float* alpha_last;   // nullable [B,S]: alpha_{T-1} (forward) with its offset folded in (or relative to ell_last)
+    double* ell_last;    // nullable [B]: when given, alpha_last is written WITHOUT the running offset and the offset goes here
     int cpo;             // chains per obs/A batch entry (1 normally; S for chunk summaries: chain = b*S + row)
     int init_identity;   // 1: alpha_{-1} of chain c is the semiring identity row (c % cpo)
 };
@@ -309,9 +310,10 @@ __global__ void __launch_bounds__(256) hmm_forward_generic(HmmArgs p) {
             const float* vfin = p.vec + (size_t)(p.T & 1) * p.B * S;
             for (int idx = tid; idx < nb * jw; idx += 256) {
                 int r = idx / jw, j = j0 + idx % jw;
-                float off = (SEMI == FB2_SEMIRING_LOG) ? (float)s_ell[r] : 0.f;
+                float off = (SEMI == FB2_SEMIRING_LOG && !p.ell_last) ? (float)s_ell[r] : 0.f;
                 p.alpha_last[(b0 + r) * S + j] = __ldcg(vfin + (b0 + r) * S + j) + off;
             }
+            if (p.ell_last && slice == 0 && tid < nb) p.ell_last[b0 + tid] = (SEMI == FB2_SEMIRING_LOG) ? s_ell[tid] : 0.0;
         }
         // the next wave re-uses vec[] of other chains only, but s_obs/s_alpha/s_ell are re-used: sync
         group_barrier(ctr, (++epoch) * p.Gg, p.Gg);
@@ -750,7 +752,7 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
                        const float* obs, const float* final_, int64_t B, int64_t T, int S, float* out,
                        float* alpha_all, int32_t* backptr, int32_t* last, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream, int cpo = 1, float* alpha_last = nullptr, double* ell_all = nullptr,
-                       double* out_d = nullptr) {
+                       double* out_d = nullptr, double* ell_last = nullptr) {
     PassPlan pl;
     int st = make_plan(B, S, false, &pl);
     const bool stream_ok = semiring == FB2_SEMIRING_MAX && a_sb == 0 && a_st == 0 && cpo == 1 && !final_ && !alpha_last &&
@@ -807,7 +809,7 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
     a.out = out; a.last = last; a.final_ = final_;
     a.Gg = pl.Gg; a.W = pl.W; a.LW = pl.LW; a.groups_total = pl.groups_total; a.groups_conc = pl.groups_conc;
     a.cpo = cpo; a.init_identity = cpo > 1 ? 1 : 0;
-    a.alpha_last = alpha_last; a.ell_all = ell_all; a.out_d = out_d;
+    a.alpha_last = alpha_last; a.ell_all = ell_all; a.out_d = out_d; a.ell_last = ell_last;
     return run_forward(semiring, backptr != nullptr, pl, a, stream);
 }
 
@@ -1006,7 +1008,7 @@ extern "C" size_t fb2_hmm_chunk_summary_workspace_bytes(int64_t B, int64_t T, in
 }
 
 extern "C" int fb2_hmm_chunk_summary_f32(int semiring, const float* A, int64_t a_sb, int64_t a_st, const float* obs,
-                                         int64_t B, int64_t T, int32_t S, float* out, void* workspace,
+                                         int64_t B, int64_t T, int32_t S, float* out, double* row_offset, void* workspace,
                                          size_t workspace_bytes, void* stream) {
     int st = check_device();
     if (st != FB2_OK) return st;
@@ -1024,5 +1026,5 @@ extern "C" int fb2_hmm_chunk_summary_f32(int semiring, const float* A, int64_t a
     // rows of the chunk's transfer matrix.
     return hmm_forward_device(semiring, nullptr, 0, A, a_sb, a_st, obs, nullptr, B * S, T, S, scratch_out, nullptr, nullptr,
                               nullptr, static_cast<char*>(workspace) + arena.used, workspace_bytes - arena.used,
-                              static_cast<cudaStream_t>(stream), S, out);
+                              static_cast<cudaStream_t>(stream), S, out, nullptr, nullptr, row_offset);
 }

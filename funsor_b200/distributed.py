@@ -61,15 +61,27 @@ def hmm_forward_batch_sharded(init, A, obs, sum_op="logaddexp", group=None, forw
 
 
 # ------------------------------------------------------------------------------------------------ time
-def _default_matmul(sum_op):
-    from .ops import semiring_matmul
+# The folds below are G-1 vector-matrix products of size S on every rank: they run in float64 with torch (device of the
+# inputs).  Summaries and boundary messages carry log-magnitudes of ~1e5 for long chunks; in fp32 that would leave ~1e-2
+# of absolute resolution on quantities whose differences matter, hence (i) summaries travel as fp32 rows + float64 row
+# offsets, (ii) the folds are float64, (iii) boundary messages are re-centred before they are handed to the fp32 kernels.
+def _reduce_op(sum_op):
+    if sum_op in ("logaddexp", "log", "logsumexp"):
+        return lambda z, dim: torch.logsumexp(z, dim)
+    return lambda z, dim: z.amax(dim)
 
-    return lambda x, y: semiring_matmul(sum_op, "add", x, y)
+
+def _as_double_summary(summary):
+    """summary: tensor [B,S,S] (absolute) or (rows[B,S,S], row_offset[B,S]) -> float64 [B,S,S]"""
+    if isinstance(summary, (tuple, list)):
+        rows, off = summary
+        return rows.double() + off.double().unsqueeze(-1)
+    return summary.double()
 
 
 def exchange_summaries(summary, group=None):
     """The one collective of the time-sharded path: all-gather of the per-chunk summaries.
-    summary [B,S,S] -> [G,B,S,S] (chunk order = rank order)."""
+    summary [B,S,S] float64 -> [G,B,S,S] (chunk order = rank order)."""
     rank, world = _world(group)
     if world == 1:
         return summary.unsqueeze(0)
@@ -78,40 +90,64 @@ def exchange_summaries(summary, group=None):
     return flat.reshape((world,) + tuple(summary.shape))
 
 
-def fold_left(init, summaries, upto, matmul):
-    """Boundary message entering chunk `upto`: init (x) M_0 (x) ... (x) M_{upto-1}.  init [B,S] -> [B,S]."""
-    v = init.unsqueeze(-2)  # [B,1,S]
+def fold_left(init, summaries, upto, sum_op="logaddexp"):
+    """Boundary message entering chunk `upto`: init (x) M_0 (x) ... (x) M_{upto-1}.  init [B,S] -> float64 [B,S]."""
+    red = _reduce_op(sum_op)
+    v = init.double()
     for r in range(upto):
-        v = matmul(v, summaries[r])
-    return v.squeeze(-2)
+        v = red(v.unsqueeze(-1) + summaries[r], -2)
+    return v
 
 
-def fold_right(final, summaries, after, matmul):
-    """Backward boundary message leaving chunk `after`: M_{after+1} (x) ... (x) M_{G-1} (x) final.  [B,S]."""
-    v = final.unsqueeze(-1)  # [B,S,1]
+def fold_right(final, summaries, after, sum_op="logaddexp"):
+    """Backward boundary message leaving chunk `after`: M_{after+1} (x) ... (x) M_{G-1} (x) final.  float64 [B,S]."""
+    red = _reduce_op(sum_op)
+    v = final.double()
     for r in range(summaries.shape[0] - 1, after, -1):
-        v = matmul(summaries[r], v)
-    return v.squeeze(-1)
+        v = red(summaries[r] + v.unsqueeze(-2), -1)
+    return v
 
 
-def hmm_forward_time_sharded(init, A, obs_chunk, sum_op="logaddexp", group=None, summary_fn=None, matmul=None,
-                             reduce_fn=None):
+def _default_summary_fn(sum_op):
+    from .ops import hmm_chunk_summary
+
+    return lambda A_, obs_: hmm_chunk_summary(A_, obs_, sum_op=sum_op, return_offsets=True)
+
+
+def hmm_forward_time_sharded(init, A, obs_chunk, sum_op="logaddexp", group=None, summary_fn=None):
     """Log-likelihood (or max-plus value) of chains whose TIME axis is split over the ranks.
 
     init [B,S] (used by every rank), A [S,S] | [B,S,S], obs_chunk [B,T_r,S] = this rank's contiguous slice of
-    time, rank order = time order.  Returns (value[B], boundary[B,S]): value on every rank, and the message
+    time, rank order = time order.  Returns (value[B] float64, boundary[B,S] float64): value on every rank, and the message
     entering this rank's chunk (the hand-over a local alpha / marginals pass starts from)."""
-    if summary_fn is None:
-        from .ops import hmm_chunk_summary
-
-        summary_fn = lambda A_, obs_: hmm_chunk_summary(A_, obs_, sum_op=sum_op)  # noqa: E731
-    if matmul is None:
-        matmul = _default_matmul(sum_op)
-    if reduce_fn is None:
-        reduce_fn = (lambda v: torch.logsumexp(v, -1)) if sum_op in ("logaddexp", "log") else (lambda v: v.amax(-1))
+    summary_fn = summary_fn or _default_summary_fn(sum_op)
     rank, world = _world(group)
-    mine = summary_fn(A, obs_chunk)  # [B,S,S]
-    allm = exchange_summaries(mine, group)  # [G,B,S,S]
-    boundary = fold_left(init, allm, rank, matmul)
-    last = fold_left(boundary, allm[rank:], allm.shape[0] - rank, matmul)
-    return reduce_fn(last), boundary
+    allm = exchange_summaries(_as_double_summary(summary_fn(A, obs_chunk)), group)  # [G,B,S,S]
+    boundary = fold_left(init, allm, rank, sum_op)
+    last = fold_left(boundary, allm[rank:], allm.shape[0] - rank, sum_op)
+    return _reduce_op(sum_op)(last, -1), boundary
+
+
+def hmm_marginals_time_sharded(init, A, obs_chunk, group=None, summary_fn=None, marginals_fn=None):
+    """Forward-backward posteriors with the time axis split over the ranks (BASELINE config 5).
+
+    Each rank reduces its chunk to a summary, ONE all-gather moves the summaries, every rank folds the ones on its left
+    into the message entering its chunk and the ones on its right into the backward message leaving it, then runs the
+    ordinary local forward-backward on its chunk: the left boundary is the (re-centred) `init`, the right boundary is
+    folded into the last observation row (obs[T_r-1] + log beta_out is exactly what the backward recursion starts from).
+    Returns (logZ[B] float64 -- the GLOBAL log-likelihood, identical on all ranks -- and gamma[B,T_r,S] for this chunk)."""
+    summary_fn = summary_fn or _default_summary_fn("logaddexp")
+    if marginals_fn is None:
+        from .ops import hmm_marginals
+
+        marginals_fn = lambda i_, A_, o_: hmm_marginals(i_, A_, o_, want_xi=False)[:2]  # noqa: E731
+    rank, world = _world(group)
+    allm = exchange_summaries(_as_double_summary(summary_fn(A, obs_chunk)), group)
+    alpha_in = fold_left(init, allm, rank)
+    beta_out = fold_right(torch.zeros_like(init, dtype=torch.float64), allm, rank)
+    a_off = alpha_in.amax(-1, keepdim=True)
+    b_off = beta_out.amax(-1, keepdim=True)
+    obs2 = obs_chunk.clone()
+    obs2[:, -1, :] += (beta_out - b_off).to(obs_chunk.dtype)
+    logZ_local, gamma = marginals_fn((alpha_in - a_off).to(obs_chunk.dtype), A, obs2)
+    return logZ_local.double() + a_off[:, 0] + b_off[:, 0], gamma

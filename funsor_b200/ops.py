@@ -227,18 +227,21 @@ def hmm_marginals(init, A, obs, want_xi=True):
     return logZ, gamma, xi
 
 
-def hmm_chunk_summary(A, obs, sum_op="logaddexp"):
+def hmm_chunk_summary(A, obs, sum_op="logaddexp", return_offsets=False):
     """Transfer matrix of a chunk of time: out[b] = (x)_{t in chunk} (A + obs[b,t]) as [B,S,S] -- the summary
-    that time-sharded ranks all-gather (mixed_sequential_sum_product sum_product.py:766-795)."""
+    that time-sharded ranks all-gather (mixed_sequential_sum_product sum_product.py:766-795).
+    With return_offsets the rows come back relative to a float64 offset [B,S] (true entry = out + offset[..., None]):
+    the log-magnitude of a long chunk (~1e5) would otherwise eat the fp32 resolution of the entries."""
     semi = semiring_id(sum_op)
     _, _, A, a_sb, a_st, obs, B, T, S = _hmm_args(None, A, obs)
     out = torch.empty((B, S, S), dtype=torch.float32, device=obs.device)
+    off = torch.zeros((B, S), dtype=torch.float64, device=obs.device) if return_offsets else None
     lib = _lib.load()
     ws = _workspace(lib.fb2_hmm_chunk_summary_workspace_bytes(B, T, S), obs.device)
     with torch.cuda.device(obs.device):
-        check(lib.fb2_hmm_chunk_summary_f32(semi, A.data_ptr(), a_sb, a_st, obs.data_ptr(), B, T, S, out.data_ptr(),
+        check(lib.fb2_hmm_chunk_summary_f32(semi, A.data_ptr(), a_sb, a_st, obs.data_ptr(), B, T, S, out.data_ptr(), _ptr(off),
                                             ws.data_ptr(), ws.numel(), _stream()))
-    return out
+    return (out, off) if return_offsets else out
 
 
 def chain_adjoint(sum_op, prod_op, trans, init=None, final=None):

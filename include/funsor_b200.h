@@ -103,8 +103,10 @@ int fb2_hmm_marginals_f32(const float* init, int64_t init_sb, const float* A, in
  *                all-gathered); it is the forward recurrence started from the semiring identity matrix.
  * The fold of gathered summaries into boundary vectors uses fb2_semiring_matmul_f32 with I = 1. */
 size_t fb2_hmm_chunk_summary_workspace_bytes(int64_t B, int64_t T, int32_t S);
+/* row_offset (nullable) [B,S] double: when given, row i of out[b] is stored RELATIVE to row_offset[b,i] (entries O(1)), so
+ * that summaries of long chunks (log-magnitudes ~1e5) keep their fp32 resolution; the true entry is out + row_offset. */
 int fb2_hmm_chunk_summary_f32(int semiring, const float* A, int64_t a_sb, int64_t a_st, const float* obs,
-                              int64_t B, int64_t T, int32_t S, float* out /*[B,S,S]*/, void* workspace,
+                              int64_t B, int64_t T, int32_t S, float* out /*[B,S,S]*/, double* row_offset, void* workspace,
                               size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

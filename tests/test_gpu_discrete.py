@@ -667,3 +667,29 @@ def test_viterbi_small_state_space_bit_exact(fb, B, T, S, amode):
     assert np.array_equal(host(path), wpath)
     z, delta = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda(), sum_op="max", return_alpha=True)
     assert np.array_equal(host(z), wbest)
+
+
+def test_time_sharded_marginals_emulated_on_one_gpu(fb):
+    """The time-sharded forward-backward (funsor_b200/distributed.py) with the real kernels, the G ranks emulated as G
+    consecutive chunks on one GPU: chunk summaries (fp32 rows + float64 offsets) -> folds -> local passes with boundaries.
+    The collective itself is covered by tests/test_distributed_cpu.py (gloo, world size 2)."""
+    from funsor_b200 import distributed as D
+
+    g = torch.Generator().manual_seed(91)
+    B, T, S, G = 2, 1200, 96, 3
+    init = torch.randn(B, S, generator=g).log_softmax(-1).cuda()
+    A = torch.randn(S, S, generator=g).log_softmax(-1).cuda()
+    obs = (torch.randn(B, T, S, generator=g) - 50.0).cuda()  # log Z ~ -6e4: offsets and re-centring matter
+    bounds = [D.shard_bounds(T, r, G) for r in range(G)]
+    summaries = torch.stack([D._as_double_summary(fb.hmm_chunk_summary(A, obs[:, lo:hi].contiguous(), return_offsets=True)) for lo, hi in bounds])
+    wZ, wgamma, _ = R.hmm_marginals(init.double().cpu().numpy(), A.double().cpu().numpy(), obs.double().cpu().numpy())
+    for r, (lo, hi) in enumerate(bounds):
+        alpha_in = D.fold_left(init, summaries, r)
+        beta_out = D.fold_right(torch.zeros_like(init, dtype=torch.float64), summaries, r)
+        a_off, b_off = alpha_in.amax(-1, keepdim=True), beta_out.amax(-1, keepdim=True)
+        obs2 = obs[:, lo:hi].clone()
+        obs2[:, -1, :] += (beta_out - b_off).float()
+        z_loc, gamma, _ = fb.hmm_marginals((alpha_in - a_off).float(), A, obs2, want_xi=False)
+        zg = z_loc.double() + a_off[:, 0] + b_off[:, 0]
+        rel_close(host(zg), wZ, rtol=RTOL)
+        rel_close(host(gamma), wgamma[:, lo:hi], rtol=1e-4, atol=1.0)
