@@ -16,7 +16,7 @@ size_t hmm_flow_workspace_bytes(int64_t B, int S);
 int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t obs_T, int64_t B, int64_t T, int S,
                          float* logZ, double* logZ_d, float* hist_u, int* hist_e, int64_t hist_T, int transpose, int reverse,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream, const unsigned* ready_flags,
-                         int64_t rows_per_chunk);
+                         int64_t rows_per_chunk, int cpo, float* rows_out, double* row_offset);
 
 static thread_local char g_err[512] = "";
 static thread_local int64_t g_launches = 0;
@@ -192,7 +192,7 @@ extern "C" int fb2_hmm_forward_f32_host(int semiring, const float* init, int64_t
                 return FB2_ERR_CUDA;
             }
         }
-        st = hmm_flow_pass_device(d_init, init_sb, d_A, d_obs, T, B, T, S, d_out, nullptr, nullptr, nullptr, 0, 0, 0, d_ws, ws, s, d_flags, rows);
+        st = hmm_flow_pass_device(d_init, init_sb, d_A, d_obs, T, B, T, S, d_out, nullptr, nullptr, nullptr, 0, 0, 0, d_ws, ws, s, d_flags, rows, 1, nullptr, nullptr);
         if (st == FB2_OK) {
             FB2_CUDA(cudaMemcpyAsync(logZ, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
             FB2_CUDA(cudaStreamSynchronize(s));

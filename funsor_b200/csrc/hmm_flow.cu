@@ -62,6 +62,8 @@ struct FlowArgs {
     int64_t obs_T;   // time extent of the obs array (rows per chain); the pass runs p.T steps over obs rows [0, p.T)
     const unsigned* ready_flags;  // nullable: obs rows [c*rows_per_chunk, ...) of every chain are resident once ready_flags[c] != 0
     int64_t rows_per_chunk;       //   (host-buffer entry point: the H2D copy of obs is overlapped with the pass)
+    int cpo;         // chains per obs entry: 1 normally; S for chunk summaries (chain c = b*S + row reads obs[b] and starts from
+                     // the semiring identity row `row` instead of init)
     int transpose;   // 1: contract with A^T (backward pass)
     int reverse;     // 1: step t consumes obs row p.T-1-t and writes history slot p.T-1-t
     long long* prof;  // nullable: [gridDim][8] accumulated cycles per phase (FB2_FLOW_PROF=1)
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
         bool zero_last = true;
         float u_last = 0.f;
         const bool chain_ok = tc >= 0 && (b0 + bc) < p.B && colC < S;
-        const float* obs_c = (chain_ok && p.obs) ? p.obs + ((b0 + bc) * p.obs_T) * S + colC : nullptr;
+        const float* obs_c = (chain_ok && p.obs) ? p.obs + (((b0 + bc) / p.cpo) * p.obs_T) * S + colC : nullptr;
         auto obs_row = [&](int64_t step) { return p.reverse ? (p.T - 1 - step) : step; };
         int64_t chunk_seen = -1;
         auto wait_rows = [&](int64_t row) {  // overlapped H2D: block until the chunk holding `row` has landed
@@ -388,6 +390,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
         if (tc >= 0) {
             float x = -INFINITY;
             if (chain_ok) x = (p.init ? p.init[(b0 + bc) * p.init_sb + colC] : 0.f) * kLog2e;
+            if (chain_ok && p.cpo > 1) x = (colC == (int)((b0 + bc) % p.cpo)) ? 0.f : -INFINITY;  // identity row
             int E15;
             bool zero;
             int dE;
@@ -1418,6 +1421,28 @@ __global__ void flow_alpha_from_history(const float* u, const int* e, int64_t BT
 
 int flow_padded_states(int S);
 
+// rows_out[c, j] = log(final message of chain c)[j] - row_offset[c],  row_offset[c] = ln2 * (largest block exponent of chain c)
+__global__ void flow_rows_out(const float* fin_u, const int* fin_e, const int* abort_flag, int64_t C, int S, int Sp, float* rows,
+                              double* row_offset) {
+    const int64_t c = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (c >= C) return;
+    const int ngrp = Sp / 8;
+    int emax = INT_MIN;
+    for (int q = lane; q < ngrp; q += 32) emax = max(emax, fin_e[c * ngrp + q]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    const bool bad = *abort_flag != 0;
+    for (int j = lane; j < S; j += 32) {
+        const int e = fin_e[c * ngrp + j / 8];
+        const float u = fin_u[c * Sp + j];
+        float v = -INFINITY;
+        if (e != INT_MIN && u > 0.f) v = logf(u) + (float)(e - emax) * 0.69314718055994530942f;
+        rows[c * S + j] = bad ? __int_as_float(0x7fc00000) : v;
+    }
+    if (lane == 0) row_offset[c] = emax == INT_MIN ? 0.0 : (double)emax * 0.69314718055994530942;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 struct FlowShape {
     int k16, nt;
@@ -1532,7 +1557,7 @@ static int flow_launch_tc(FlowArgs& a, cudaStream_t stream) {
 int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t obs_T, int64_t B, int64_t T, int S,
                          float* logZ, double* logZ_d, float* hist_u, int* hist_e, int64_t hist_T, int transpose, int reverse,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream, const unsigned* ready_flags = nullptr,
-                         int64_t rows_per_chunk = 0);
+                         int64_t rows_per_chunk = 0, int cpo = 1, float* rows_out = nullptr, double* row_offset = nullptr);
 
 int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
                             float* logZ, double* logZ_d, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -1546,7 +1571,7 @@ int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, 
 int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t obs_T, int64_t B, int64_t T, int S,
                          float* logZ, double* logZ_d, float* hist_u, int* hist_e, int64_t hist_T, int transpose, int reverse,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream, const unsigned* ready_flags,
-                         int64_t rows_per_chunk) {
+                         int64_t rows_per_chunk, int cpo, float* rows_out, double* row_offset) {
     const FlowShape fs = flow_shape(S);
     if (!fs.k16) {
         set_error("hmm flow: S=%d outside the supported range", S);
@@ -1575,6 +1600,7 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
     a.pkt = pkt; a.fin_u = fin_u; a.fin_e = fin_e; a.abort_flag = abort_flag; a.groups_total = (int)groups;
     a.hist_u = hist_u; a.hist_e = hist_e; a.hist_T = hist_T; a.obs_T = obs_T; a.transpose = transpose; a.reverse = reverse;
     a.ready_flags = ready_flags; a.rows_per_chunk = rows_per_chunk > 0 ? rows_per_chunk : 1;
+    a.cpo = cpo > 1 ? cpo : 1;
     const char* mode_env = getenv("FB2_FLOW_MODE");
     a.mode = mode_env ? atoi(mode_env) : 1;  // default: publish packets with atom.exch (store->load hand-over measured ~10 % faster)
     const char* prof_env = getenv("FB2_FLOW_PROF");
@@ -1585,20 +1611,31 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
     // (default: measured 3.4 us/step at S=1024) and tcgen05 kind::tf32 with P in tensor memory (FB2_FLOW_TC=1: 3.7 us/step;
     // its shorter MMA phase is hidden behind the DSMEM reduce-scatter, which moves the same 8 KB per CTA-step either way).
     const char* tc_env = getenv("FB2_FLOW_TC");
-    const bool legacy = !(tc_env && tc_env[0] == '1') || hist_u != nullptr || transpose || reverse || ready_flags != nullptr;
+    const bool legacy = !(tc_env && tc_env[0] == '1') || hist_u != nullptr || transpose || reverse || ready_flags != nullptr || cpo > 1;
     if (!legacy) {
         if (fs.k16 == 1) st = flow_launch_tc<2, 1>(a, stream);
         else if (fs.k16 == 2) st = flow_launch_tc<4, 1>(a, stream);
         else if (fs.k16 == 4) st = flow_launch_tc<8, 1>(a, stream);
         else if (a.mode & 16) st = flow_launch_tc<16, 4>(a, stream);
         else st = flow_launch_tc<16, 1>(a, stream);
-    } else if (fs.k16 == 1) st = flow_launch<1, 1>(a, stream);
-    else if (fs.k16 == 2) st = flow_launch<2, 1>(a, stream);
-    else if (fs.k16 == 4) st = flow_launch<4, 1>(a, stream);
-    else st = flow_launch<8, 2>(a, stream);
+    } else {
+        // Many chain groups (B > 16, chunk summaries): two n-tiles per warp halve the clusters a set needs, so two to
+        // three times as many groups run side by side (at most 15 clusters of 8 are co-resident); a single group is
+        // faster with one tile per warp (less tensor work on its critical path).
+        const bool wide = groups > 1;
+        if (fs.k16 == 1) st = wide ? flow_launch<1, 2>(a, stream) : flow_launch<1, 1>(a, stream);
+        else if (fs.k16 == 2) st = wide ? flow_launch<2, 2>(a, stream) : flow_launch<2, 1>(a, stream);
+        else if (fs.k16 == 4) st = wide ? flow_launch<4, 2>(a, stream) : flow_launch<4, 1>(a, stream);
+        else st = flow_launch<8, 2>(a, stream);
+    }
     if (st != FB2_OK) return st;
-    flow_finalise<<<(unsigned)ceil_div(B, 4), 128, 0, stream>>>(fin_u, fin_e, abort_flag, B, S, Sp, logZ, logZ_d);
-    FB2_LAUNCH_CHECK();
+    if (rows_out) {  // chunk summary: the final messages themselves, as rows relative to a float64 offset
+        flow_rows_out<<<(unsigned)ceil_div(B, 4), 128, 0, stream>>>(fin_u, fin_e, abort_flag, B, S, Sp, rows_out, row_offset);
+        FB2_LAUNCH_CHECK();
+    } else {
+        flow_finalise<<<(unsigned)ceil_div(B, 4), 128, 0, stream>>>(fin_u, fin_e, abort_flag, B, S, Sp, logZ, logZ_d);
+        FB2_LAUNCH_CHECK();
+    }
     if (getenv("FB2_DEBUG")) {
         int h[8];
         FB2_CUDA(cudaStreamSynchronize(stream));
@@ -1723,6 +1760,15 @@ int hmm_flow_forward_alpha_device(const float* init, int64_t init_sb, const floa
     flow_alpha_from_history<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(ua, ea, B * T, S, Sp, alpha);
     FB2_LAUNCH_CHECK();
     return FB2_OK;
+}
+
+
+// chunk summary on the dataflow kernel: S chains per batch entry, started from the identity rows, all reading obs[b]
+size_t hmm_flow_summary_workspace_bytes(int64_t B, int S) { return hmm_flow_workspace_bytes(B * S, S); }
+int hmm_flow_summary_device(const float* A, const float* obs, int64_t B, int64_t T, int S, float* rows_out, double* row_offset, void* workspace,
+                            size_t workspace_bytes, cudaStream_t stream) {
+    return hmm_flow_pass_device(nullptr, 0, A, obs, T, B * S, T, S, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, workspace, workspace_bytes, stream,
+                                nullptr, 0, S, rows_out, row_offset);
 }
 
 }  // namespace fb2

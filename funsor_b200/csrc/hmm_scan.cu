@@ -29,6 +29,9 @@ int hmm_flow_marginals_device(const float* init, int64_t init_sb, const float* A
 size_t hmm_flow_alpha_workspace_bytes(int64_t B, int64_t T, int S);
 int hmm_flow_forward_alpha_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t B, int64_t T, int S,
                                   float* logZ, float* alpha, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t hmm_flow_summary_workspace_bytes(int64_t B, int S);
+int hmm_flow_summary_device(const float* A, const float* obs, int64_t B, int64_t T, int S, float* rows_out, double* row_offset, void* workspace,
+                            size_t workspace_bytes, cudaStream_t stream);
 // hmm_small.cu
 bool hmm_small_supported(int semiring, int64_t a_st, int S);
 int hmm_small_forward_device(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb, const float* obs, int64_t B,
@@ -1004,7 +1007,9 @@ extern "C" int fb2_chain_adjoint_f32(int semiring, const float* trans, const int
 }
 
 extern "C" size_t fb2_hmm_chunk_summary_workspace_bytes(int64_t B, int64_t T, int32_t S) {
-    return vec_bytes(B * S, S) + ctr_bytes() + align_up((size_t)B * S * 4) + 512;
+    const size_t generic = vec_bytes(B * S, S) + ctr_bytes() + align_up((size_t)B * S * 4) + 512;
+    const size_t flow = hmm_flow_summary_workspace_bytes(B, S);
+    return generic > flow ? generic : flow;
 }
 
 extern "C" int fb2_hmm_chunk_summary_f32(int semiring, const float* A, int64_t a_sb, int64_t a_st, const float* obs,
@@ -1016,6 +1021,12 @@ extern "C" int fb2_hmm_chunk_summary_f32(int semiring, const float* A, int64_t a
     if (st != FB2_OK) return st;
     FB2_REQUIRE(out != nullptr, "out is null");
     if (B == 0) return FB2_OK;
+    // log-semiring, homogeneous A, offsets requested: the S identity-started chains of every batch entry run on the dataflow kernel
+    if (row_offset && obs && hmm_flow_supported(semiring, a_sb, a_st, S, false) && !flow_disabled() &&
+        workspace_bytes >= hmm_flow_summary_workspace_bytes(B, S)) {
+        st = hmm_flow_summary_device(A, obs, B, T, S, out, row_offset, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+        if (st != FB2_ERR_UNSUPPORTED) return st;
+    }
     Arena arena(workspace, workspace_bytes);
     float* scratch_out = arena.take<float>((size_t)B * S);  // per-row reductions, unused by the caller
     if (!arena.ok()) {

@@ -693,3 +693,20 @@ def test_time_sharded_marginals_emulated_on_one_gpu(fb):
         zg = z_loc.double() + a_off[:, 0] + b_off[:, 0]
         rel_close(host(zg), wZ, rtol=RTOL)
         rel_close(host(gamma), wgamma[:, lo:hi], rtol=1e-4, atol=1.0)
+
+
+@pytest.mark.parametrize("B,T,S", [(2, 37, 96), (1, 200, 130), (3, 5, 65)])
+def test_chunk_summary_on_dataflow_kernel(fb, B, T, S):
+    """hmm_chunk_summary(return_offsets=True) = the chain product of (A + obs[t]) over the chunk, computed as S chains per
+    batch entry started from the identity rows (dataflow kernel), returned as fp32 rows + float64 row offsets."""
+    g = torch.Generator().manual_seed(92)
+    A = torch.randn(S, S, generator=g).log_softmax(-1)
+    obs = torch.randn(B, T, S, generator=g) - 20.0
+    rows, off = fb.hmm_chunk_summary(A.cuda(), obs.cuda(), return_offsets=True)
+    got = rows.double() + off[..., None]
+    trans = A.double().numpy()[None, None] + obs.double().numpy()[:, :, None, :]
+    want = R.chain_product(R.LOG, trans)
+    rel_close(host(got), want, rtol=RTOL, atol=1.0)
+    assert float(rows.abs().max()) < 200.0  # entries stay O(1)-O(100): the magnitude lives in the offsets
+    plain = fb.hmm_chunk_summary(A.cuda(), obs.cuda())  # generic kernel, absolute fp32
+    rel_close(host(plain), want, rtol=RTOL, atol=1.0)
