@@ -14,6 +14,7 @@ from . import _lib  # noqa: F401
 from .ops import (  # noqa: F401
     chain_adjoint,
     hmm_chunk_summary,
+    hmm_chunk_summary_tree,
     hmm_forward,
     hmm_marginals,
     hmm_viterbi,

@@ -227,11 +227,77 @@ def hmm_marginals(init, A, obs, want_xi=True):
     return logZ, gamma, xi
 
 
-def hmm_chunk_summary(A, obs, sum_op="logaddexp", return_offsets=False):
+def _recentre(M):
+    """M[..., S, S] -> (M - max entry, max entry as float64): keeps the fp32 entries O(1)-O(100) whatever the chain length."""
+    m = M.amax((-1, -2))
+    return M - m[..., None, None], m.double()
+
+
+def hmm_chunk_summary_tree(A, obs, sum_op="logaddexp", block_bytes=2 << 30, leaf_steps=128):
+    """The same summary as a blocked balanced tree of dense semiring matmuls -- literally sequential_sum_product
+    (sum_product.py:652-701) over trans[t] = A + obs[t] (hmm.py:130).  Every level is a batch of independent [S x S]
+    products, which for the log semiring run on the tcgen05 tensor cores (log_matmul_tc): ~2 S^3 useful flops per time step at
+    ~100 TFLOP/s instead of a latency-bound recurrence with S chains.
+
+    fp32 log-domain entries lose absolute resolution as their magnitude grows with the number of multiplied steps, so the
+    tree is re-centred: observations are shifted by their per-step maximum, leaves of `leaf_steps` steps are reduced by the
+    chain-product kernel, and from there on every product is followed by subtracting its largest entry; all removed shifts
+    accumulate in float64.  Time is processed in super-blocks whose dense factor tensor fits in `block_bytes`.
+    Returns (rows[B,S,S] fp32 with max entry 0, row_offset[B,S] float64)."""
+    _dev_f32(obs, "obs"), _dev_f32(A, "A")
+    B, T, S = obs.shape
+    if A.dim() != 2:
+        raise ValueError("hmm_chunk_summary_tree needs a shared transition matrix A[S,S]")
+    shift = obs.amax(-1)  # [B,T]
+    shift = torch.where(torch.isfinite(shift), shift, torch.zeros_like(shift))
+    off = shift.double().sum(-1)
+    L = max(1, min(leaf_steps, T))
+    steps_per_block = max(L, int(block_bytes // (B * S * S * 4)) // L * L)
+    acc = None
+    t0 = 0
+    while t0 < T:
+        tb = min(steps_per_block, T - t0)
+        if tb >= L:
+            tb = tb // L * L
+            leaf = L
+        else:
+            leaf = tb  # ragged tail shorter than a leaf
+        nb = tb // leaf
+        ob = (obs[:, t0 : t0 + tb] - shift[:, t0 : t0 + tb, None]).reshape(B * nb, leaf, 1, S)
+        trans = A[None, None] + ob  # [B*nb, leaf, S, S]: the reference's own materialisation, one block at a time
+        M = sequential_sum_product(sum_op, "add", trans).reshape(B, nb, S, S)
+        del trans, ob
+        M, m = _recentre(M)
+        off += m.sum(-1)
+        while nb > 1:  # balanced tree over the leaves of this block, re-centred after every level
+            half = nb // 2
+            P2 = semiring_matmul(sum_op, "add", M[:, 0 : 2 * half : 2], M[:, 1 : 2 * half : 2])
+            P2, m = _recentre(P2)
+            off += m.sum(-1)
+            M = P2 if nb == 2 * half else torch.cat([P2, M[:, nb - 1 :]], 1)
+            nb = half + (nb - 2 * half)
+        M = M[:, 0]
+        if acc is None:
+            acc = M
+        else:
+            acc, m = _recentre(semiring_matmul(sum_op, "add", acc, M))
+            off += m
+        t0 += tb
+    return acc.contiguous(), off[:, None].expand(B, S).contiguous()
+
+
+def hmm_chunk_summary(A, obs, sum_op="logaddexp", return_offsets=False, method="auto"):
     """Transfer matrix of a chunk of time: out[b] = (x)_{t in chunk} (A + obs[b,t]) as [B,S,S] -- the summary
     that time-sharded ranks all-gather (mixed_sequential_sum_product sum_product.py:766-795).
     With return_offsets the rows come back relative to a float64 offset [B,S] (true entry = out + offset[..., None]):
-    the log-magnitude of a long chunk (~1e5) would otherwise eat the fp32 resolution of the entries."""
+    the log-magnitude of a long chunk (~1e5) would otherwise eat the fp32 resolution of the entries.
+    method: "tree" = blocked dense tree on the tensor cores (default with offsets, shared A, S >= 64), "scan" = S chains per
+    batch entry on the recurrence kernels (dataflow kernel with offsets, generic cooperative kernel without)."""
+    if method == "auto":
+        method = "tree" if (return_offsets and A.dim() == 2 and obs.shape[-1] >= 64) else "scan"
+    if method == "tree":
+        rows, off = hmm_chunk_summary_tree(A, obs, sum_op)
+        return (rows, off) if return_offsets else (rows.double() + off[..., None]).float()
     semi = semiring_id(sum_op)
     _, _, A, a_sb, a_st, obs, B, T, S = _hmm_args(None, A, obs)
     out = torch.empty((B, S, S), dtype=torch.float32, device=obs.device)

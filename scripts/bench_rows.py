@@ -25,7 +25,8 @@ ms = timeit(lambda: fb.hmm_forward(init, A, obs, return_alpha=True)); print("log
 Tc = 256
 ms = timeit(lambda: fb.hmm_chunk_summary(A, obs[:, :Tc].contiguous())); print("chunk summary (generic) S=512 T=%d: %.2f ms, %.2f us/step" % (Tc, ms, ms * 1e3 / Tc), flush=True)
 Tc2 = 2048
-ms = timeit(lambda: fb.hmm_chunk_summary(A, obs[:, :Tc2].contiguous(), return_offsets=True)); print("chunk summary (dataflow, offsets) S=512 T=%d: %.2f ms, %.2f us/step" % (Tc2, ms, ms * 1e3 / Tc2), flush=True)
+ms = timeit(lambda: fb.hmm_chunk_summary(A, obs[:, :Tc2].contiguous(), return_offsets=True, method="scan")); print("chunk summary (dataflow scan) S=512 T=%d: %.2f ms, %.2f us/step" % (Tc2, ms, ms * 1e3 / Tc2), flush=True)
+ms = timeit(lambda: fb.hmm_chunk_summary(A, obs, return_offsets=True, method="tree")); print("chunk summary (tcgen05 tree) S=512 T=%d: %.2f ms, %.2f us/step" % (T, ms, ms * 1e3 / T), flush=True)
 Bk, Tk, D, O = 64, 8192, 32, 16
 F = 0.9 * torch.linalg.qr(torch.randn(Bk, D, D, device=dev, generator=g))[0]
 H = torch.randn(Bk, D, O, device=dev, generator=g) / D ** 0.5

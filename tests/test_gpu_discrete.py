@@ -702,11 +702,15 @@ def test_chunk_summary_on_dataflow_kernel(fb, B, T, S):
     g = torch.Generator().manual_seed(92)
     A = torch.randn(S, S, generator=g).log_softmax(-1)
     obs = torch.randn(B, T, S, generator=g) - 20.0
-    rows, off = fb.hmm_chunk_summary(A.cuda(), obs.cuda(), return_offsets=True)
-    got = rows.double() + off[..., None]
     trans = A.double().numpy()[None, None] + obs.double().numpy()[:, :, None, :]
     want = R.chain_product(R.LOG, trans)
-    rel_close(host(got), want, rtol=RTOL, atol=1.0)
-    assert float(rows.abs().max()) < 200.0  # entries stay O(1)-O(100): the magnitude lives in the offsets
+    for method in ("scan", "tree"):
+        rows, off = fb.hmm_chunk_summary(A.cuda(), obs.cuda(), return_offsets=True, method=method)
+        got = rows.double() + off[..., None]
+        rel_close(host(got), want, rtol=RTOL, atol=1.0)
+        assert float(rows.abs().max()) < 200.0  # entries stay O(1)-O(100): the magnitude lives in the offsets
+    # the blocked tree with blocks much shorter than the chunk (several re-centred block products chained)
+    rows, off = fb.hmm_chunk_summary_tree(A.cuda(), obs.cuda(), block_bytes=7 * B * S * S * 4)
+    rel_close(host(rows.double() + off[..., None]), want, rtol=RTOL, atol=1.0)
     plain = fb.hmm_chunk_summary(A.cuda(), obs.cuda())  # generic kernel, absolute fp32
     rel_close(host(plain), want, rtol=RTOL, atol=1.0)
