@@ -41,6 +41,7 @@ struct LogMatmulArgs {
     int64_t xs0, xs1, xsi;  // xsk == 1
     int64_t ys0, ys1, ysk;  // ysj == 1
     int I, K, J;
+    float comp;  // expected relative truncation loss per accumulating MMA (0 = no compensation)
     int mode;  // FB2_LM_MODE experiments: 1 = stage only the first two chunks, 2 = do not issue MMAs
 };
 
@@ -63,6 +64,15 @@ __device__ __forceinline__ void lm_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void lm_tmem_ld16(uint32_t taddr, uint32_t (&d)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]),
+          "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t lm_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -110,8 +120,20 @@ __global__ void lm_colmax(const float* y, int64_t n1, int64_t ys0, int64_t ys1, 
 
 // BN = output columns per CTA (MMA N): 256 when J > 128 (each staged x row then feeds 256 columns, halving the L2 -> SM
 // traffic per flop, which is what bounded the 128 x 128 version), else 128.
-template <int BN>
+//
+// NMAIN + 1 accumulators in tensor memory.  Measured on B200 (scripts/matmul_bias.py): every tcgen05.mma accumulation
+// TRUNCATES the fp32 accumulator toward zero, a one-sided loss of ~2^-24 of the running sum per instruction; with all
+// 3 K/8 instructions of a tile chained into one accumulator the result was low by 2.2e-8 K (relative) -- 1.1e-5 at K = 512,
+// nearly deterministic, and it adds up along a chain of products.  Hence: the two correction products (lo*hi, hi*lo, 2^-11 of the
+// magnitude) go to their own accumulator, where their truncation is negligible, and the hi*hi products of successive K chunks
+// rotate over NMAIN accumulators; the NMAIN + 1 partial sums are added with round-to-nearest in the epilogue.  That divides
+// the loss by 3 NMAIN.  What remains is one-sided and, with >= 8 accumulations, close to its mean (rms error ~ |mean error|
+// in the measurement), so the epilogue multiplies every hi*hi partial sum by 1 + 5.82e-8 * (its number of accumulations):
+// that centres the error (residual in scripts/matmul_bias.py / DESIGN.md 4.4).  BN * (NMAIN + 1) = 512 columns = all of the SM's tensor memory (one CTA per SM anyway).
+template <int BN, int NMAIN>
 __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
+    constexpr uint32_t NCOLS = BN * (NMAIN + 1);
+    static_assert(NCOLS == 512 || NCOLS == 256 || NCOLS == 128, "tensor memory allocation must be a power of two <= 512");
     using Cfg = LmCfg<BN>;
     extern __shared__ unsigned char lm_smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[LM_STAGES];
@@ -133,7 +155,7 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lm_smem_u32(&s_tmem)), "n"(BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lm_smem_u32(&s_tmem)), "n"(NCOLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -267,9 +289,9 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
                 for (int ks = 0; ks < LM_KC / 8; ++ks) {
                     const uint64_t dah = lm_desc(ah + ks * 32), dal = lm_desc(al + ks * 32);
                     const uint64_t dbh = lm_desc(bh + ks * 32), dbl = lm_desc(bl + ks * 32);
-                    lm_mma(tmem, dah, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
-                    lm_mma(tmem, dal, dbh, IDESC, 1u);
-                    lm_mma(tmem, dah, dbl, IDESC, 1u);
+                    lm_mma(tmem + (uint32_t)(c % NMAIN) * BN, dah, dbh, IDESC, (c >= NMAIN || ks > 0) ? 1u : 0u);
+                    lm_mma(tmem + NMAIN * BN, dal, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                    lm_mma(tmem + NMAIN * BN, dah, dbl, IDESC, 1u);
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(lm_smem_u32(&s_bar[s])) : "memory");
                 if (c == nchunks - 1)
@@ -291,19 +313,30 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
         const bool vec_out = (a.J % 4 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
 #pragma unroll 1
         for (int cc = 0; cc < BN / 2; cc += 16) {
-            uint32_t d[16];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]),
-                  "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
-                : "r"(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cbase + cc))
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float d[16];
+            {
+                // the correction accumulator first, then the hi*hi partial sums that were actually written
+                uint32_t r[16];
+                lm_tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(NMAIN * BN + cbase + cc), r);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) d[q] = __uint_as_float(r[q]);
+#pragma unroll
+                for (int mi = 0; mi < NMAIN; ++mi) {
+                    if (mi < nchunks) {
+                        lm_tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mi * BN + cbase + cc), r);
+                        // expected-loss compensation: this accumulator took (LM_KC / 8) * ceil((nchunks - mi) / NMAIN) truncating
+                        // accumulations, each losing on average 0.976 * 2^-24 of the sum (calibrated, see above)
+                        const float f = 1.f + a.comp * (float)((LM_KC / 8) * ((nchunks - mi + NMAIN - 1) / NMAIN));
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) d[q] = fmaf(__uint_as_float(r[q]), f, d[q]);
+                    }
+                }
+            }
             if (row < a.I) {
                 const int jb = j0 + cbase + cc;
                 float o[16];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) o[q] = (sxo + ((jb + q) < a.J ? __ldg(a.sy + n * a.J + jb + q) : 0.f)) + __logf(__uint_as_float(d[q]));
+                for (int q = 0; q < 16; ++q) o[q] = (sxo + ((jb + q) < a.J ? __ldg(a.sy + n * a.J + jb + q) : 0.f)) + __logf(d[q]);
                 if (jb + 15 < a.J && vec_out) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(orow + jb + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
@@ -317,7 +350,7 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NCOLS) : "memory");
 }
 
 // Returns FB2_ERR_UNSUPPORTED when the shapes / strides do not fit this kernel (caller falls back to the SIMT tile kernel).
@@ -342,17 +375,24 @@ int launch_log_matmul_tc(const float* x, const int64_t* xs, const float* y, cons
     {
         const char* m = getenv("FB2_LM_MODE");
         a.mode = m ? atoi(m) : 0;
+        const char* c = getenv("FB2_LM_COMP");  // A/B switch: 0 disables the expected-loss compensation
+        a.comp = (c && atoi(c) == 0) ? 0.f : 5.82e-8f;
     }
     // per call, not cached in a static: the attribute is per device and a process may drive more than one
-    FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<128>::SMEM));
-    FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<256>::SMEM));
-    const char* bn_env = getenv("FB2_LM_BN");  // A/B switch: force the 128-column tile
-    if (J > 128 && !(bn_env && atoi(bn_env) == 128)) {
+    FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<128>::SMEM));
+    FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<256>::SMEM));
+    // Tile choice: 128 x 256 (one hi*hi accumulator, 110 TFLOP/s) is the faster tile, 128 x 128 (three, 78 TFLOP/s) has a third
+    // of the accumulation loss to compensate; measured rms error after compensation 5.5e-7 vs 2.9e-7 at K = 1024, so only
+    // longer contractions take the 128-column tile.  FB2_LM_BN=128|256 forces one.
+    const char* bn_env = getenv("FB2_LM_BN");
+    const int forced = bn_env ? atoi(bn_env) : 0;
+    const bool wide = forced == 256 ? J > 128 : forced == 128 ? false : (J > 128 && K <= 1024);
+    if (wide) {
         dim3 grid((unsigned)ceil_div(J, 256), (unsigned)ceil_div(I, LM_TILE), (unsigned)n);
-        log_matmul_tc<256><<<grid, 256, LmCfg<256>::SMEM, stream>>>(a);
+        log_matmul_tc<256, 1><<<grid, 256, LmCfg<256>::SMEM, stream>>>(a);
     } else {
         dim3 grid((unsigned)ceil_div(J, 128), (unsigned)ceil_div(I, LM_TILE), (unsigned)n);
-        log_matmul_tc<128><<<grid, 256, LmCfg<128>::SMEM, stream>>>(a);
+        log_matmul_tc<128, 3><<<grid, 256, LmCfg<128>::SMEM, stream>>>(a);
     }
     FB2_LAUNCH_CHECK();
     return FB2_OK;

@@ -714,3 +714,42 @@ def test_chunk_summary_on_dataflow_kernel(fb, B, T, S):
     rel_close(host(rows.double() + off[..., None]), want, rtol=RTOL, atol=1.0)
     plain = fb.hmm_chunk_summary(A.cuda(), obs.cuda())  # generic kernel, absolute fp32
     rel_close(host(plain), want, rtol=RTOL, atol=1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [64, 512, 1024, 2048])
+def test_log_matmul_tensor_core_has_no_accumulation_bias(fb, K):
+    # tcgen05 accumulation truncates toward zero (one-sided loss ~2^-24 per MMA, -2.2e-8 K before the fix); the kernel splits the
+    # accumulators and compensates the expected loss.  Signed mean error against float64 must stay at the fp32 noise level.
+    g = torch.Generator(device="cuda").manual_seed(K)
+    x = torch.randn(2, 256, K, device="cuda", generator=g)
+    y = torch.randn(2, K, 256, device="cuda", generator=g)
+    ref = torch.logsumexp(x.double().unsqueeze(-1) + y.double().unsqueeze(-3), -2)
+    d = fb.semiring_matmul("logaddexp", "add", x, y).double() - ref
+    assert abs(d.mean().item()) < 4e-7, d.mean().item()
+    assert d.abs().max().item() < 1e-5
+
+
+@pytest.mark.gpu
+def test_long_chain_log_normaliser_drift_against_float64(fb):
+    # a systematic per-step error adds up linearly along a chain: compare both fp32 routes (dataflow recurrence, tensor-core
+    # summary tree) with a float64 recurrence.  Bound: 1e-6 relative on logZ (north_star tolerance is 1e-5).
+    from funsor_b200 import distributed as fd
+
+    T, S = 16384, 256
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.log_softmax(torch.randn(S, S, device="cuda", generator=g), -1)
+    init = torch.log_softmax(torch.randn(1, S, device="cuda", generator=g), -1)
+    obs = torch.randn(1, T, S, device="cuda", generator=g)
+    P, E, v = A.double().exp(), obs[0].double().exp(), init[0].double().exp()
+    acc = torch.zeros((), dtype=torch.float64, device="cuda")
+    for t in range(T):
+        v = (v @ P) * E[t]
+        s = v.sum()
+        v, acc = v / s, acc + s.log()
+    ref = acc.item()
+    z = fb.hmm_forward(init, A, obs).item()
+    assert abs(z - ref) < 1e-6 * abs(ref) + 4e-3, (z, ref)  # + half an fp32 ulp of the returned value
+    summ = fb.hmm_chunk_summary(A, obs, return_offsets=True, method="tree")
+    val, _ = fd.hmm_forward_time_sharded(init, A, obs, summary_fn=lambda a, o: summ)
+    assert abs(val.item() - ref) < 1e-6 * abs(ref), (val.item(), ref)
