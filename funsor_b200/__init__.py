@@ -5,6 +5,7 @@ The package holds only what the path needs:
   _lib.py          ctypes binding of that ABI (no torch types cross it)
   ops.py           host-side mirror of the reference functions on raw torch CUDA tensors
   gaussian.py      Gaussian-factor (Kalman) mirror
+  hmm.py           DiscreteHMM / GaussianHMM / GaussianMRF with the reference's constructor arguments (pyro/hmm.py)
   distributed.py   batch- and time-sharding across the GPUs of one box
   funsor_plugin.py eager patterns registered into funsor's torch backend (when funsor is importable)
 There is no CPU fallback: without the shared library or without an sm_100 device every compute

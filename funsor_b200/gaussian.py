@@ -128,6 +128,47 @@ def kalman_elements_homog(F, q_loc, q_tril, H, r_loc, r_tril, y):
     return w.contiguous(), P, s[:, None].expand(B, T).contiguous()
 
 
+def kalman_elements_timevarying(F, q_loc, q_tril, H, r_loc, r_tril, y):
+    """Chain elements when any parameter depends on time (pyro/hmm.py:258-270 with heterogeneous inputs): every parameter is
+    [B, T|1, ...] and is broadcast over the time axis.  Returns w[B,T,D+O], P[B,T,2D,D+O], s[B,T] (sqrt form)."""
+    B, T, O = y.shape
+    D = F.shape[-1]
+    eyeD = torch.eye(D, device=F.device, dtype=F.dtype)
+    eyeO = torch.eye(O, device=F.device, dtype=F.dtype)
+    Pq = torch.linalg.solve_triangular(q_tril, eyeD.expand(q_tril.shape), upper=False).transpose(-1, -2)  # [B,Tq,D,D]
+    Pr = torch.linalg.solve_triangular(r_tril, eyeO.expand(r_tril.shape), upper=False).transpose(-1, -2)  # [B,Tr,O,O]
+    P = torch.zeros(B, T, 2 * D, D + O, device=F.device, dtype=F.dtype)
+    P[:, :, :D, :D] = F @ Pq
+    P[:, :, D:, :D] = -Pq
+    P[:, :, D:, D:] = H @ Pr
+    w_t = -(q_loc[..., None, :] @ Pq)[..., 0, :]  # [B,T|1,D]
+    w_o = -(r_loc[..., None, :] @ Pr)[..., 0, :] + (y[..., None, :] @ Pr)[..., 0, :]  # [B,T,O]
+    w = torch.cat([w_t.expand(B, T, D), w_o.expand(B, T, O)], dim=-1)
+    s = (-0.5 * (D + O) * math.log(2 * math.pi) - q_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1)
+         - r_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1))
+    return w.contiguous(), P, s.expand(B, T).contiguous()
+
+
+def gaussian_chain_info_homog(Lam, eta, c, validate=True):
+    """Scan over info-form chain elements that share one precision per chain: Lam[B,2D,2D], eta[B,T,2D], c[B,T]."""
+    for t in (Lam, eta, c):
+        _dev_f32(t, "gaussian element")
+    B, T, n = eta.shape
+    D = n // 2
+    Lam, eta, c = Lam.contiguous(), eta.contiguous(), c.expand(B, T).contiguous()
+    Lo = torch.empty((B, n, n), dtype=torch.float32, device=Lam.device)
+    eo = torch.empty((B, n), dtype=torch.float32, device=Lam.device)
+    co = torch.empty((B,), dtype=torch.float32, device=Lam.device)
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_gaussian_chain_workspace_bytes(B, T, D), Lam.device)
+    with torch.cuda.device(Lam.device):
+        check(lib.fb2_gaussian_chain_homog_f32(Lam.data_ptr(), eta.data_ptr(), c.data_ptr(), B, T, D, Lo.data_ptr(), eo.data_ptr(),
+                                               co.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    if validate and bool(torch.isnan(co).any()):
+        raise ValueError("Too little information to marginalize over the shared state. Consider adding a prior.")
+    return Lo, eo, co
+
+
 def gaussian_chain_homog(white_vec, prec_sqrt, scalar, validate=True):
     """Scan over chain elements that share one prec_sqrt per chain: white_vec[B,T,r], prec_sqrt[B,2D,r], scalar[B,T].
     Lam[B] = P P' once per chain, eta / c per step; the T-sized precision array is never formed."""

@@ -254,6 +254,116 @@ def main():
         lp = (init + chain.reduce(ops.logaddexp, "state(time=1)")).reduce(ops.logaddexp, "state")
         out[name + "/logprob"] = _np(lp.data)
     np.savez_compressed(os.path.join(GOLDEN, "kalman.npz"), **out)
+    # ------------------------------------------------------------------ the chain distributions of funsor/pyro/hmm.py
+    # The classes themselves subclass pyro's TorchDistribution and convert torch distributions through
+    # funsor.torch.distributions (both need pyro, absent here), so their log_prob EXPRESSIONS (hmm.py:117-138, 258-274,
+    # 339-378) are evaluated below with the reference's own funsor machinery and converters (tensor_to_funsor,
+    # funsor_to_tensor, matrix_and_mvn_to_funsor); the one converter that needs pyro (dist_to_funsor / mvn_to_funsor for
+    # an MVN) is restated by `mvn_funsor`.
+    out = {}
+    torch.manual_seed(17)
+    from funsor.util import broadcast_shape
+
+    def rand_mvn(shape, dim):
+        loc = torch.randn(shape + (dim,))
+        a = torch.randn(shape + (dim, 2 * dim))
+        return MVN(loc, scale_tril=torch.linalg.cholesky(a @ a.transpose(-1, -2)))
+
+    def mvn_funsor(d, event_dims, real_inputs):
+        n = d.event_shape[0]
+        Psq = torch.linalg.inv(d.scale_tril).transpose(-1, -2)
+        wv = (d.loc[..., None, :] @ Psq)[..., 0, :]
+        lp = -0.5 * n * np.log(2 * np.pi) - d.scale_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1)
+        lp = conv.tensor_to_funsor(lp, event_dims)
+        wv_f = conv.tensor_to_funsor(wv.expand(Psq.shape[:-2] + (-1,)), event_dims, 1)
+        Ps_f = conv.tensor_to_funsor(Psq, event_dims, 2)
+        inputs = Ps_f.inputs.copy()
+        for k, v in wv_f.inputs.items():
+            inputs.setdefault(k, v)
+        inputs.update(real_inputs)
+        bshape = tuple(v.size for v in inputs.values() if v.dtype != "real")
+        names = [k for k, v in inputs.items() if v.dtype != "real"]
+        wv_d = wv_f.align(tuple(k for k in names if k in wv_f.inputs)).data
+        Ps_d = Ps_f.align(tuple(k for k in names if k in Ps_f.inputs)).data
+        assert wv_d.shape[:-1] == bshape and Ps_d.shape[:-2] == bshape, (wv_d.shape, Ps_d.shape, bshape)
+        return Gaussian(white_vec=wv_d, prec_sqrt=Ps_d, inputs=inputs) + lp
+
+    S = 3
+    DISCRETE = {"d0": ((), (1,), ()), "d1": ((), (), (7,)), "d2": ((), (7,), (5, 7)), "d3": ((5,), (5, 7), (7,)),
+                "d4": ((4, 1, 1), (3, 1, 7), (2, 7)), "d5": ((2,), (6,), (2, 6))}
+    for name, (ish, tsh, osh) in DISCRETE.items():
+        init_logits = torch.randn(ish + (S,))
+        trans_logits = torch.randn(tsh + (S, S))
+        loc, scale = torch.randn(osh + (S,)), torch.randn(osh + (S,)).exp()
+        obs_dist = torch.distributions.Normal(loc, scale)
+        shape = broadcast_shape(ish + (1,), tsh, osh)
+        batch_shape, T = shape[:-1], shape[-1]
+        data = obs_dist.expand(shape + (S,)).sample()[..., 0]
+        # hmm.py:91-99
+        il = init_logits - init_logits.logsumexp(-1, True)
+        tl = trans_logits - trans_logits.logsumexp(-1, True)
+        init = conv.tensor_to_funsor(il, ("state",))
+        trans = conv.tensor_to_funsor(tl, ("time", "state", "state(time=1)"))
+        obs = conv.tensor_to_funsor(obs_dist.log_prob(data.unsqueeze(-1)), ("time", "state(time=1)"))  # = self._obs(value=value)
+        # hmm.py:128-137
+        result = trans + obs
+        result = sequential_sum_product(ops.logaddexp, ops.add, result, Variable("time", Bint[T]), {"state": "state(time=1)"})
+        result = init + result.reduce(ops.logaddexp, "state(time=1)")
+        result = result.reduce(ops.logaddexp, "state")
+        lp = conv.funsor_to_tensor(result, ndims=max(len(batch_shape), data.dim() - 1))
+        for k, v in dict(init_logits=init_logits, trans_logits=trans_logits, loc=loc, scale=scale, data=data, log_prob=lp).items():
+            out["discrete/" + name + "/" + k] = _np(v)
+
+    GH = {"g0": ((), (), (), (), (), 4), "g1": ((), (6,), (), (), (), 6), "g2": ((), (), (), (), (6,), 6),
+          "g3": ((5,), (6,), (), (), (), 6), "g4": ((), (), (5, 1), (6,), (), 6), "g5": ((5,), (5, 6), (5, 6), (5, 6), (5, 6), 6)}
+    for name, (ish, tmsh, tvsh, omsh, ovsh, Tdata) in GH.items():
+        D, O = (2, 3) if name != "g5" else (3, 2)
+        init_dist, trans_dist, obs_dist = rand_mvn(ish, D), rand_mvn(tvsh, D), rand_mvn(ovsh, O)
+        trans_mat, obs_mat = 0.7 * torch.randn(tmsh + (D, D)), torch.randn(omsh + (D, O))
+        shape = broadcast_shape(ish + (1,), tmsh, tvsh, omsh, ovsh)
+        T = shape[-1]
+        if T == 1:  # homogeneous: the reference's event_shape has num_steps = 1 (hmm.py:181-186); use T = 1 data here
+            Tdata = 1
+        data = obs_dist.expand(shape).sample()
+        assert data.shape[-2] == Tdata
+        init = mvn_funsor(init_dist, (), OrderedDict(state=Reals[D]))
+        trans = conv.matrix_and_mvn_to_funsor(trans_mat, trans_dist, ("time",), "state", "state(time=1)")
+        obs = conv.matrix_and_mvn_to_funsor(obs_mat, obs_dist, ("time",), "state(time=1)", "value")
+        value = conv.tensor_to_funsor(data, ("time",), 1)
+        result = trans + obs(value=value)
+        result = sequential_sum_product(ops.logaddexp, ops.add, result, Variable("time", Bint[T]), {"state": "state(time=1)"})
+        result = init + result.reduce(ops.logaddexp, "state(time=1)")
+        result = result.reduce(ops.logaddexp, "state")
+        lp = conv.funsor_to_tensor(result, ndims=len(shape) - 1)
+        for k, v in dict(init_loc=init_dist.loc, init_tril=init_dist.scale_tril, trans_mat=trans_mat, trans_loc=trans_dist.loc,
+                         trans_tril=trans_dist.scale_tril, obs_mat=obs_mat, obs_loc=obs_dist.loc, obs_tril=obs_dist.scale_tril,
+                         data=data, log_prob=lp).items():
+            out["ghmm/" + name + "/" + k] = _np(v)
+
+    MRF = {"m0": ((), (1,), ()), "m1": ((), (7,), ()), "m2": ((), (), (7,)), "m3": ((5,), (7,), (5, 7)), "m4": ((2, 1, 1), (3, 1, 7), (2, 7))}
+    for name, (ish, tsh, osh) in MRF.items():
+        D, O = 2, 2
+        init_dist, trans_dist, obs_dist = rand_mvn(ish, D), rand_mvn(tsh, 2 * D), rand_mvn(osh, D + O)
+        shape = broadcast_shape(ish + (1,), tsh, osh)
+        T = shape[-1]
+        data = obs_dist.expand(shape).sample()[..., D:]
+        init = mvn_funsor(init_dist, (), OrderedDict(state=Reals[D]))
+        trans = mvn_funsor(trans_dist, ("time",), OrderedDict([("state", Reals[D]), ("state(time=1)", Reals[D])]))
+        obs = mvn_funsor(obs_dist, ("time",), OrderedDict([("state(time=1)", Reals[D]), ("value", Reals[O])]))
+        time = Variable("time", Bint[T])
+        value = conv.tensor_to_funsor(data, ("time",), 1)
+        both = frozenset({"state", "state(time=1)"})
+        logp_oh = trans + obs(value=value)
+        logp_oh = sequential_sum_product(ops.logaddexp, ops.add, logp_oh, time, {"state": "state(time=1)"})
+        logp_oh = (logp_oh + init).reduce(ops.logaddexp, both)
+        logp_h = trans + obs.reduce(ops.logaddexp, "value")
+        logp_h = sequential_sum_product(ops.logaddexp, ops.add, logp_h, time, {"state": "state(time=1)"})
+        logp_h = (logp_h + init).reduce(ops.logaddexp, both)
+        lp = conv.funsor_to_tensor(logp_oh - logp_h, ndims=len(shape) - 1)
+        for k, v in dict(init_loc=init_dist.loc, init_tril=init_dist.scale_tril, trans_loc=trans_dist.loc, trans_tril=trans_dist.scale_tril,
+                         obs_loc=obs_dist.loc, obs_tril=obs_dist.scale_tril, data=data, log_prob=lp).items():
+            out["mrf/" + name + "/" + k] = _np(v)
+    np.savez_compressed(os.path.join(GOLDEN, "distributions.npz"), **out)
     for fn in sorted(os.listdir(GOLDEN)):
         print(fn, os.path.getsize(os.path.join(GOLDEN, fn)))
 

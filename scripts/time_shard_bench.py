@@ -93,7 +93,7 @@ def main():
         out["logZ_one_gpu"] = z1[0].item()
         out["logZ_rel_err"] = abs(z1[0].item() - logZ[0].item()) / abs(z1[0].item())
         out["gamma_max_abs_err_chunk0"] = (g1[:, :Tr] - gamma).abs().max().item()
-        out["gamma_rowsum_err"] = (gamma.sum(-1) - 1).abs().max().item()
+        out["gamma_rowsum_err"] = (gamma.exp().sum(-1) - 1).abs().max().item()  # gamma is log p(z_t | obs)
     if world > 1:
         dist.barrier()
     if rank == 0:

@@ -144,3 +144,41 @@ def test_cpu_port_matches_oracle():
     for sname, s in SEMI.items():
         got = cpu_port.hmm_log_prob(torch.tensor(d["init"]), torch.tensor(d["A"]), torch.tensor(d["obs"]), sname)
         rel_close(got.numpy(), d[sname + "_Z"], rtol=1e-11, atol=1.0)
+
+
+# ---------------------------------------------------------------------- chain distributions (funsor/pyro/hmm.py)
+def _normal_logp(x, loc, scale):
+    return -0.5 * ((x - loc) / scale) ** 2 - np.log(scale) - 0.5 * np.log(2 * np.pi)
+
+
+def test_discrete_hmm_oracle_matches_reference():
+    from conftest import dist_cases
+    from oracle import hmm_ref as H
+
+    cases = dist_cases("discrete")
+    assert len(cases) >= 6
+    for name, d in cases.items():
+        obs = _normal_logp(d["data"][..., None].astype(np.float64), d["loc"], d["scale"])
+        got = H.discrete_hmm_log_prob(d["init_logits"], d["trans_logits"], obs)
+        want = d["log_prob"]
+        rel_close(np.broadcast_to(got, want.shape) if got.size == want.size else got, want.reshape(np.shape(got)), rtol=1e-10, atol=1.0)
+
+
+def test_gaussian_hmm_oracle_matches_reference():
+    from conftest import dist_cases, ghmm_oracle
+
+    cases = dist_cases("ghmm")
+    assert len(cases) >= 6
+    for name, d in cases.items():
+        got = ghmm_oracle(d)
+        rel_close(got, d["log_prob"].reshape(got.shape), rtol=1e-8, atol=1.0)
+
+
+def test_gaussian_mrf_oracle_matches_reference():
+    from conftest import dist_cases, mrf_oracle
+
+    cases = dist_cases("mrf")
+    assert len(cases) >= 5
+    for name, d in cases.items():
+        got = mrf_oracle(d)
+        rel_close(got, d["log_prob"].reshape(got.shape), rtol=1e-8, atol=1.0)
