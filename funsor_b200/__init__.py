@@ -18,6 +18,7 @@ from .ops import (  # noqa: F401
     hmm_chunk_summary_tree,
     hmm_forward,
     hmm_marginals,
+    hmm_posterior_sample,
     hmm_viterbi,
     launch_count,
     mixed_sequential_sum_product,

@@ -105,6 +105,12 @@ class DiscreteHMM:
         best, path = ops.hmm_viterbi(init, A, obs)
         return best.reshape(batch), path.reshape(tuple(batch) + (path.shape[-1],))
 
+    def sample_posterior(self, value, num_samples=1, uniforms=None, generator=None):
+        """Forward-filter backward-sample: (paths[batch, N, T+1] int64, log p(path | value)[batch, N])."""
+        init, A, obs, batch = self._factors(value)
+        paths, log_q, _ = ops.hmm_posterior_sample(init, A, obs, num_samples, uniforms, generator)
+        return paths.reshape(tuple(batch) + tuple(paths.shape[-2:])), log_q.reshape(tuple(batch) + (paths.shape[-2],))
+
     def marginals(self, value):
         """Forward-backward: (log_prob[batch], log p(z_t | value)[batch, T, S])."""
         init, A, obs, batch = self._factors(value)

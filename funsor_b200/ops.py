@@ -227,6 +227,32 @@ def hmm_marginals(init, A, obs, want_xi=True):
     return logZ, gamma, xi
 
 
+def hmm_posterior_sample(init, A, obs, num_samples=1, uniforms=None, generator=None):
+    """Forward-filter backward-sample: exact draws of state paths from p(z | obs) (recipes.py:16-90 specialised to a chain;
+    the discrete draw is Tensor._sample tensor.py:332-427).  `uniforms[B,N,T+1]` in [0,1) may be given to make the draws a
+    deterministic function of the inputs.  Returns (paths[B,N,T+1] int64, log_q[B,N] float64 = log p(path | obs), logZ[B])."""
+    init_t, init_sb, A, a_sb, a_st, obs, B, T, S = _hmm_args(init, A, obs)
+    if uniforms is None:
+        uniforms = torch.rand((B, num_samples, T + 1), dtype=torch.float32, device=obs.device, generator=generator)
+    _dev_f32(uniforms, "uniforms")
+    if uniforms.dim() != 3 or uniforms.shape[0] != B or uniforms.shape[2] != T + 1:
+        raise ValueError("uniforms must be [B, N, T+1], got {}".format(tuple(uniforms.shape)))
+    uniforms = uniforms.contiguous()
+    N = uniforms.shape[1]
+    paths = torch.empty((B, N, T + 1), dtype=torch.int64, device=obs.device)
+    score = torch.empty((B, N), dtype=torch.float64, device=obs.device)
+    if B == 0 or N == 0:
+        return paths, score, torch.empty((B,), dtype=torch.float32, device=obs.device)
+    logZ, alpha = hmm_forward(init, A, obs, return_alpha=True)
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_hmm_backward_sample_workspace_bytes(B, T, S, a_sb, a_st), obs.device)
+    with torch.cuda.device(obs.device):
+        check(lib.fb2_hmm_backward_sample_f32(_ptr(init_t), init_sb, A.data_ptr(), a_sb, a_st, obs.data_ptr(), alpha.data_ptr(),
+                                              uniforms.data_ptr(), B, T, S, N, paths.data_ptr(), score.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), _stream()))
+    return paths, score - logZ.double()[:, None], logZ
+
+
 def _recentre(M):
     """M[..., S, S] -> (M - max entry, max entry as float64): keeps the fp32 entries O(1)-O(100) whatever the chain length."""
     m = M.amax((-1, -2))

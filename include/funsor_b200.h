@@ -152,6 +152,22 @@ int fb2_gaussian_chain_f32(const float* Lam, const float* eta, const float* c, i
                            void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (7) Backward sampling of state paths (forward-filter backward-sample).
+ * Replaces: recipes.forward_filter_backward_rsample funsor/recipes.py:16-90 specialised to a discrete chain
+ *           (sum_product + adjoint.forward_backward under MonteCarlo, montecarlo.py:48-61; Tensor._sample tensor.py:332-427).
+ * alpha    [B,T,S] log-domain forward messages (fb2_hmm_forward_f32, alpha_all)
+ * uniforms [B,N,T+1] in [0,1): one per draw; draw t uses inverse-CDF lookup in state order, so the result is a
+ *          deterministic function of (inputs, uniforms).
+ * paths    [B,N,T+1] int64, paths[..,0] = state before the first transition (as fb2_hmm_viterbi_f32)
+ * score    [B,N] float64: init[z0] + sum_t A_t[z_t,z_{t+1}] + obs[t,z_{t+1}]  (log q(path) = score - logZ)
+ */
+size_t fb2_hmm_backward_sample_workspace_bytes(int64_t B, int64_t T, int32_t S, int64_t a_sb, int64_t a_st);
+int fb2_hmm_backward_sample_f32(const float* init, int64_t init_sb, const float* A, int64_t a_sb, int64_t a_st,
+                                const float* obs, const float* alpha, const float* uniforms, int64_t B, int64_t T,
+                                int32_t S, int64_t N, int64_t* paths, double* score, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a CPU-side caller of the reference binds): inputs and outputs are
  * HOST pointers; the call stages them through device memory it owns (one cached arena per thread),
  * runs the device path on its own stream and synchronises before returning.  These are the `e2e`

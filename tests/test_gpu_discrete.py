@@ -753,3 +753,53 @@ def test_long_chain_log_normaliser_drift_against_float64(fb):
     summ = fb.hmm_chunk_summary(A, obs, return_offsets=True, method="tree")
     val, _ = fd.hmm_forward_time_sharded(init, A, obs, summary_fn=lambda a, o: summ)
     assert abs(val.item() - ref) < 1e-6 * abs(ref), (val.item(), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,S,N,amode", [(3, 40, 70, 5, "shared"), (2, 25, 33, 9, "batched"), (2, 12, 6, 4, "timevarying"),
+                                            (1, 300, 257, 3, "shared"), (2, 1, 5, 17, "shared")])
+def test_posterior_sampling_every_conditional_draw(fb, B, T, S, N, amode):
+    # forward-filter backward-sample (recipes.py:16-90 on a chain): every draw of every path is checked against the exact
+    # float64 conditional CDF given the path's own next state; forbidden (-inf) states must never be chosen
+    rng = np.random.default_rng(B * 1000 + T + S)
+    init = torch.log_softmax(torch.tensor(rng.standard_normal((B, S)), dtype=torch.float32), -1)
+    shape = {"shared": (S, S), "batched": (B, S, S), "timevarying": (B, T, S, S)}[amode]
+    A = torch.tensor(rng.standard_normal(shape), dtype=torch.float32)
+    A[..., 0, 1] = -float("inf")
+    A = torch.log_softmax(A, -1)
+    obs = torch.tensor(rng.standard_normal((B, T, S)), dtype=torch.float32)
+    obs[0, T // 2, 2] = -float("inf")
+    u = torch.tensor(rng.random((B, N, T + 1)), dtype=torch.float32)
+    paths, log_q, logZ = fb.hmm_posterior_sample(init.cuda(), A.cuda(), obs.cuda(), uniforms=u.cuda())
+    assert paths.shape == (B, N, T + 1) and paths.dtype == torch.int64
+    checked, want_q = R.backward_sample_check(init.numpy(), A.numpy(), obs.numpy(), u.numpy(), paths.cpu().numpy())
+    assert checked == B * N * (T + 1)
+    rel_close(log_q.cpu().numpy(), want_q, rtol=1e-5, atol=max(1.0, T / 10))
+    # same uniforms -> same paths (deterministic), different uniforms -> different paths
+    paths2, _, _ = fb.hmm_posterior_sample(init.cuda(), A.cuda(), obs.cuda(), uniforms=u.cuda())
+    assert torch.equal(paths, paths2)
+
+
+@pytest.mark.gpu
+def test_posterior_sampling_matches_exact_path_distribution(fb):
+    # small chain: enumerate all S^(T+1) paths, compare the empirical path frequencies of 40000 draws with the exact posterior
+    import itertools
+
+    S, T, N = 3, 4, 40000
+    g = torch.Generator().manual_seed(21)
+    init = torch.log_softmax(torch.randn(1, S, generator=g), -1)
+    A = torch.log_softmax(torch.randn(S, S, generator=g), -1)
+    obs = torch.randn(1, T, S, generator=g)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    paths, log_q, logZ = fb.hmm_posterior_sample(init.cuda(), A.cuda(), obs.cuda(), num_samples=N, generator=gen)
+    i64, A64, o64 = init.double().numpy()[0], A.double().numpy(), obs.double().numpy()[0]
+    allp = list(itertools.product(range(S), repeat=T + 1))
+    score = np.array([i64[p[0]] + sum(A64[p[t], p[t + 1]] + o64[t, p[t + 1]] for t in range(T)) for p in allp])
+    post = np.exp(score - np.log(np.exp(score).sum()))
+    code = (paths[0].cpu().numpy() * (S ** np.arange(T, -1, -1))).sum(-1)
+    freq = np.bincount(code, minlength=len(allp)) / N
+    sigma = np.sqrt(post * (1 - post) / N)
+    assert (np.abs(freq - post) <= 5 * sigma + 1e-4).all(), np.abs(freq - post).max()
+    # reported log-probabilities are the exact posterior log-probabilities of the drawn paths
+    rel_close(log_q[0].cpu().numpy(), np.log(post[code]), rtol=1e-5, atol=1.0)
+    assert abs(logZ.item() - np.log(np.exp(score).sum())) < 1e-5
