@@ -30,6 +30,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace fb2 {
@@ -1568,6 +1570,10 @@ int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, 
 // General pass: T steps over obs rows [0, T) of an array with obs_T rows per chain, optionally with A transposed and
 // time reversed (the backward recursion is the forward recursion on (A^T, reversed obs), see fb2_hmm_marginals_f32),
 // optionally recording every message (mantissas + block exponents).
+// set by hmm_flow_marginals_device around its two passes: take the two-tiles-per-warp variant (half the clusters) even for a
+// single chain group, so that the forward and the backward pass fit on the GPU side by side
+static thread_local int tl_force_wide = 0;
+
 int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t obs_T, int64_t B, int64_t T, int S,
                          float* logZ, double* logZ_d, float* hist_u, int* hist_e, int64_t hist_T, int transpose, int reverse,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream, const unsigned* ready_flags,
@@ -1622,7 +1628,7 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
         // Many chain groups (B > 16, chunk summaries): two n-tiles per warp halve the clusters a set needs, so two to
         // three times as many groups run side by side (at most 15 clusters of 8 are co-resident); a single group is
         // faster with one tile per warp (less tensor work on its critical path).
-        const bool wide = groups > 1;
+        const bool wide = groups > 1 || tl_force_wide;
         if (fs.k16 == 1) st = wide ? flow_launch<1, 2>(a, stream) : flow_launch<1, 1>(a, stream);
         else if (fs.k16 == 2) st = wide ? flow_launch<2, 2>(a, stream) : flow_launch<2, 1>(a, stream);
         else if (fs.k16 == 4) st = wide ? flow_launch<4, 2>(a, stream) : flow_launch<4, 1>(a, stream);
@@ -1682,7 +1688,29 @@ size_t hmm_flow_marginals_workspace_bytes(int64_t B, int64_t T, int S) {
     if (!Sp) return 0;
     return 2 * (align_up((size_t)B * T * Sp * 4) + align_up((size_t)B * T * (Sp / 8) * 4)) + 2 * align_up((size_t)B * 8) +
            align_up((size_t)B * 4) + 3 * align_up((size_t)B * T * 4) + align_up((size_t)B * xi_ksplit(T) * S * S * 4) +
-           hmm_flow_workspace_bytes(B, S) + 512;
+           2 * hmm_flow_workspace_bytes(B, S) + 512;
+}
+
+// A side stream per device for the backward pass of small-batch forward-backward (see below).
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int side_stream_for_current_device(SideStream** out) {
+    static SideStream table[64];
+    static std::mutex mu;
+    int dev = 0;
+    FB2_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return FB2_ERR_UNSUPPORTED;
+    std::lock_guard<std::mutex> lock(mu);
+    SideStream& s = table[dev];
+    if (!s.stream) {
+        FB2_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        FB2_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+        FB2_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    }
+    *out = &s;
+    return FB2_OK;
 }
 
 // Forward-backward posteriors on the dataflow kernel: a forward pass and a backward pass (= the same kernel on A^T and
@@ -1710,12 +1738,38 @@ int hmm_flow_marginals_device(const float* init, int64_t init_sb, const float* A
     }
     char* rest = static_cast<char*>(workspace) + arena.used;
     const size_t rest_bytes = workspace_bytes - arena.used;
-    int st = hmm_flow_pass_device(init, init_sb, A, obs, T, B, T, S, logZ, z_d, ua, ea, T, 0, 0, rest, rest_bytes, stream);
-    if (st != FB2_OK) return st;
-    // backward: w_{T-1} = obs_{T-1}; w_{t-1}[i] = obs_{t-1}[i] * sum_j A[i,j] w_t[j]  ->  T-1 steps over obs rows T-2 .. 0
-    st = hmm_flow_pass_device(obs + (T - 1) * (int64_t)S, T * (int64_t)S, A, obs, T, B, T - 1, S, zb, zb_d, uw, ew, T, 1, 1, rest, rest_bytes,
-                              stream);
-    if (st != FB2_OK) return st;
+    // One chain group (B <= 16) occupies 2 K16 / NT clusters of the 15 a B200 can hold, and the two passes are independent:
+    // run the backward pass on a side stream next to the forward pass.  Each pass needs all its clusters resident, so this
+    // is only done when both fit together with room to spare (S <= 512: 4 + 4 clusters, using the two-tiles-per-warp variant at
+    // K16 = 4); S = 1024 needs 8 clusters per pass and stays sequential.  FB2_FLOW_DUAL=0 switches it off.
+    const FlowShape fs = flow_shape(S);
+    const char* dual_env = getenv("FB2_FLOW_DUAL");
+    const size_t per_pass = hmm_flow_workspace_bytes(B, S);
+    const bool dual = B <= FLOW_CHAINS && fs.k16 <= 4 && T >= 64 && rest_bytes >= 2 * per_pass && !(dual_env && dual_env[0] == '0');
+    int st;
+    if (dual) {
+        SideStream* side = nullptr;
+        st = side_stream_for_current_device(&side);
+        if (st != FB2_OK) return st;
+        FB2_CUDA(cudaEventRecord(side->fork, stream));
+        FB2_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        tl_force_wide = fs.k16 == 4;
+        st = hmm_flow_pass_device(obs + (T - 1) * (int64_t)S, T * (int64_t)S, A, obs, T, B, T - 1, S, zb, zb_d, uw, ew, T, 1, 1, rest + per_pass,
+                                  rest_bytes - per_pass, side->stream);
+        if (st == FB2_OK) st = hmm_flow_pass_device(init, init_sb, A, obs, T, B, T, S, logZ, z_d, ua, ea, T, 0, 0, rest, per_pass, stream);
+        tl_force_wide = 0;
+        // join even on failure so that the caller's stream never runs ahead of the side stream
+        cudaEventRecord(side->join, side->stream);
+        cudaStreamWaitEvent(stream, side->join, 0);
+        if (st != FB2_OK) return st;
+    } else {
+        st = hmm_flow_pass_device(init, init_sb, A, obs, T, B, T, S, logZ, z_d, ua, ea, T, 0, 0, rest, rest_bytes, stream);
+        if (st != FB2_OK) return st;
+        // backward: w_{T-1} = obs_{T-1}; w_{t-1}[i] = obs_{t-1}[i] * sum_j A[i,j] w_t[j]  ->  T-1 steps over obs rows T-2 .. 0
+        st = hmm_flow_pass_device(obs + (T - 1) * (int64_t)S, T * (int64_t)S, A, obs, T, B, T - 1, S, zb, zb_d, uw, ew, T, 1, 1, rest, rest_bytes,
+                                  stream);
+        if (st != FB2_OK) return st;
+    }
     const int64_t n = B * T * (int64_t)S;
     flow_gamma<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(ua, ea, uw, ew, obs, z_d, B, T, S, Sp, gamma);
     FB2_LAUNCH_CHECK();
