@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(256) gaussian_pair_combine(GaussPairArgs a) {
 //   phase 2  L goes to the warp's shared-memory slot; lane l forward-substitutes right-hand-side columns l, l+32 (, 64)
 //            of [G' | e_b] reading L as broadcast loads -> U columns in registers and in shared memory
 //   phase 3  lane l produces output rows l and l+32:  Lam'[r, :] = base[r, :] - U[:, r]' U,  eta'[r] likewise
-constexpr int GW_WARPS = 4;
+// warps per CTA: D = 32 runs one 12-warp CTA per SM (168 registers per thread) with all warps in step, smaller D three 4-warp CTAs
+template <int DT>
+__host__ __device__ constexpr int gw_warps() { return DT >= 32 ? 12 : 4; }
 template <int DT>
 struct GaussWarpSmem {
     float L[DT][DT + 1];
@@ -143,13 +145,21 @@ struct GaussWarpSmem {
 // sides, so every loop has static bounds, every array stays in registers and the shuffles are unconditional (a first
 // version with run-time bounds put the row array in local memory and wrapped each shuffle in divergence handling).
 template <int DT>
-__global__ void __launch_bounds__(GW_WARPS * 32, 3) gaussian_pair_combine_warp(GaussPairArgs a, int64_t npairs) {
+__global__ void __launch_bounds__(gw_warps<DT>() * 32, DT >= 32 ? 1 : 3) gaussian_pair_combine_warp(GaussPairArgs a, int64_t npairs) {
+    constexpr int GW_WARPS = gw_warps<DT>();
     extern __shared__ __align__(16) unsigned char gw_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     GaussWarpSmem<DT>& sm = reinterpret_cast<GaussWarpSmem<DT>*>(gw_raw)[warp];
     const int D = a.D, n = 2 * D;
     constexpr int NCOL = (2 * DT + 31) / 32;  // right-hand-side columns / output rows per lane
-    for (int64_t pair = (int64_t)blockIdx.x * GW_WARPS + warp; pair < npairs; pair += (int64_t)gridDim.x * GW_WARPS) {
+    // The loop is CTA-uniform and the warps of a CTA meet at a barrier per pair: the body is ~150 KB of straight-line code
+    // (everything is unrolled so that the register arrays are statically indexed), and warps drifting apart through it made
+    // instruction fetch the top stall reason (ncu: no_instructions 31 %).  In step, the four warps share each fetched line.
+    for (int64_t pair0 = (int64_t)blockIdx.x * GW_WARPS; pair0 < npairs; pair0 += (int64_t)gridDim.x * GW_WARPS) {
+        __syncthreads();
+        // warps past the end redo the last pair (identical values to identical addresses) so that every warp reaches
+        // the barriers inside the body
+        const int64_t pair = pair0 + warp < npairs ? pair0 + warp : npairs - 1;
         const int64_t q0 = pair / a.n1, q1 = pair % a.n1;
         const int64_t xe = q0 * a.x_s0 + q1 * a.x_s1, ye = q0 * a.y_s0 + q1 * a.y_s1, oe = q0 * a.o_s0 + q1;
         const float* Lx = a.Lx + (q0 * a.lx_s0 + q1 * a.lx_s1) * n * n;
@@ -162,7 +172,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) gaussian_pair_combine_warp(G
 #pragma unroll
         for (int k = 0; k < DT; ++k)
             m[k] = (lane < D && k < D) ? __ldg(Lx + (D + k) * n + D + lane) + __ldg(Ly + k * n + lane) : (k == lane ? 1.f : 0.f);
-        float logdet = 0.f;
+        float logdet = 0.f, dinv = 1.f;  // dinv: 1 / L[lane][lane]
         int bad = 0;
 #pragma unroll
         for (int j = 0; j < DT; ++j) {
@@ -171,8 +181,13 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) gaussian_pair_combine_warp(G
                 bad = 1;
                 d = 1.f;
             }
-            const float ljj = sqrtf(d), inv = 1.f / ljj;
+            // 1/sqrt(d): MUFU.RSQ + one Newton step (full fp32 accuracy, no slow-path call; sqrtf and the divisions below
+            // cost ~25 instructions each and the kernel is instruction-fetch bound)
+            float inv = rsqrtf(d);
+            inv = inv * fmaf(-0.5f * d * inv, inv, 1.5f);
+            const float ljj = d * inv;
             logdet += __logf(ljj);
+            if (lane == j) dinv = inv;
             const float lij = lane > j ? m[j] * inv : (lane == j ? ljj : 0.f);
             m[j] = lij;
 #pragma unroll
@@ -182,16 +197,18 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) gaussian_pair_combine_warp(G
         float val = lane < D ? ex[D + lane] + ey[lane] : 0.f;
 #pragma unroll
         for (int j = 0; j < DT; ++j) {
-            const float vj = __shfl_sync(0xffffffffu, val, j) / __shfl_sync(0xffffffffu, m[j], j);
+            const float vj = __shfl_sync(0xffffffffu, val, j) * __shfl_sync(0xffffffffu, dinv, j);
             val = lane == j ? vj : (lane > j ? fmaf(-m[j], vj, val) : val);
         }
         if (lane < DT) {
 #pragma unroll
             for (int k = 0; k < DT; ++k) sm.L[lane][k] = m[k];
+            sm.L[lane][lane] = dinv;  // phase 2 only needs the inverse of the diagonal
             sm.U[lane][2 * DT] = val;
         }
         __syncwarp();
 
+        __syncthreads();
         // ---- phase 2: forward substitution, lane = right-hand-side columns c = lane + 32 q of G' (padded layout: the a-block
         // occupies columns [0, DT), the c-block columns [DT, 2 DT)); G'[k, c] is read through its symmetric counterpart so
         // that the lanes coalesce: Lx_ab[c, k] = Lx_ba[k, c], Ly_ba[c, k] = Ly_ab[k, c]
@@ -218,7 +235,7 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) gaussian_pair_combine_warp(G
 #pragma unroll
                 for (int q = 0; q < NCOL; ++q) acc[q] = fmaf(-l, u[q][mm], acc[q]);
             }
-            const float inv = 1.f / sm.L[k][k];
+            const float inv = sm.L[k][k];  // holds 1 / L[k][k]
 #pragma unroll
             for (int q = 0; q < NCOL; ++q) {
                 u[q][k] = acc[q] * inv;
@@ -228,17 +245,40 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) gaussian_pair_combine_warp(G
         }
         __syncwarp();
 
+        __syncthreads();
         // ---- phase 3: outputs, lane = output rows (padded index) r = lane + 32 q; inputs and output are symmetric, so element
         // (r, s) is read from / written to (s, r) and the lanes coalesce
         float* Lo = a.Lo + oe * n * n;
         float* eo = a.eo + oe * n;
+        // The diagonal blocks of the result start from the operands' own blocks (Lx_aa, Ly_cc).  Those reads are issued one
+        // 16-column strip AHEAD of the strip being accumulated: measured with ncu (source page), reading them next to the
+        // store that consumes them serialised 128 global-load latencies per pair and was 55 % of all stall samples.
+        auto load_base = [&](int s0, float (&dst)[NCOL][16]) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int sp = s0 + t, sblk = sp / DT, sc = sp % DT;
+#pragma unroll
+                for (int q = 0; q < NCOL; ++q) {
+                    const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
+                    float base = 0.f;
+                    if (sp < 2 * DT && sc < D && rp < 2 * DT && rc < D && rblk == sblk) {
+                        const int sidx = sblk * D + sc, r = rblk * D + rc;
+                        base = __ldg((rblk == 0 ? Lx : Ly) + sidx * n + r);
+                    }
+                    dst[q][t] = base;
+                }
+            }
+        };
+        float nb[NCOL][16];
+        load_base(0, nb);
 #pragma unroll 1
         for (int s0 = 0; s0 < 2 * DT; s0 += 16) {
             float acc[NCOL][16];
 #pragma unroll
             for (int q = 0; q < NCOL; ++q)
 #pragma unroll
-                for (int t = 0; t < 16; ++t) acc[q][t] = 0.f;
+                for (int t = 0; t < 16; ++t) acc[q][t] = nb[q][t];
+            if (s0 + 16 < 2 * DT) load_base(s0 + 16, nb);
 #pragma unroll
             for (int k = 0; k < DT; ++k) {
                 const float4* up = reinterpret_cast<const float4*>(&sm.U[k][s0]);
@@ -247,10 +287,10 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) gaussian_pair_combine_warp(G
                     const float4 uv = up[q4];
 #pragma unroll
                     for (int q = 0; q < NCOL; ++q) {
-                        acc[q][4 * q4 + 0] = fmaf(u[q][k], uv.x, acc[q][4 * q4 + 0]);
-                        acc[q][4 * q4 + 1] = fmaf(u[q][k], uv.y, acc[q][4 * q4 + 1]);
-                        acc[q][4 * q4 + 2] = fmaf(u[q][k], uv.z, acc[q][4 * q4 + 2]);
-                        acc[q][4 * q4 + 3] = fmaf(u[q][k], uv.w, acc[q][4 * q4 + 3]);
+                        acc[q][4 * q4 + 0] = fmaf(-u[q][k], uv.x, acc[q][4 * q4 + 0]);
+                        acc[q][4 * q4 + 1] = fmaf(-u[q][k], uv.y, acc[q][4 * q4 + 1]);
+                        acc[q][4 * q4 + 2] = fmaf(-u[q][k], uv.z, acc[q][4 * q4 + 2]);
+                        acc[q][4 * q4 + 3] = fmaf(-u[q][k], uv.w, acc[q][4 * q4 + 3]);
                     }
                 }
             }
@@ -259,17 +299,11 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) gaussian_pair_combine_warp(G
                 const int sp = s0 + t;  // padded column index
                 const int sblk = sp / DT, sc = sp % DT;
                 if (sp < 2 * DT && sc < D) {
-                    const int s = sblk * D + sc;  // real column index
+                    const int sidx = sblk * D + sc;  // real column index
 #pragma unroll
                     for (int q = 0; q < NCOL; ++q) {
                         const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
-                        if (rp < 2 * DT && rc < D) {
-                            const int r = rblk * D + rc;
-                            float base = 0.f;
-                            if (rblk == 0 && sblk == 0) base = __ldg(Lx + s * n + r);
-                            else if (rblk == 1 && sblk == 1) base = __ldg(Ly + s * n + r);
-                            Lo[s * n + r] = base - acc[q][t];
-                        }
+                        if (rp < 2 * DT && rc < D) Lo[sidx * n + rblk * D + rc] = acc[q][t];
                     }
                 }
             }
@@ -304,10 +338,11 @@ __global__ void __launch_bounds__(GW_WARPS * 32, 3) gaussian_pair_combine_warp(G
 
 template <int DT>
 static int launch_pair_warp(const GaussPairArgs& a, int64_t npairs, cudaStream_t stream) {
+    constexpr int GW_WARPS = gw_warps<DT>();
     const size_t smem = GW_WARPS * sizeof(GaussWarpSmem<DT>);
     FB2_CUDA(cudaFuncSetAttribute(gaussian_pair_combine_warp<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = ceil_div(npairs, GW_WARPS);
-    if (blocks > 148 * 3 * 8) blocks = 148 * 3 * 8;  // persistent-ish: a few waves of 3 CTAs per SM
+    if (blocks > 148 * 96 / GW_WARPS) blocks = 148 * 96 / GW_WARPS;  // persistent-ish: 8 waves of 12 warps per SM
     gaussian_pair_combine_warp<DT><<<(unsigned)blocks, GW_WARPS * 32, smem, stream>>>(a, npairs);
     FB2_LAUNCH_CHECK();
     return FB2_OK;
