@@ -12,6 +12,8 @@
 // One CTA of 256 threads per pair; everything between the loads and the stores stays in shared memory.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace fb2 {
@@ -144,6 +146,208 @@ struct GaussWarpSmem {
 // DT = compile-time padded state dimension (D <= DT): the shared block is padded with an identity and zero right-hand
 // sides, so every loop has static bounds, every array stays in registers and the shuffles are unconditional (a first
 // version with run-time bounds put the row array in local memory and wrapped each shuffle in divergence handling).
+// One pair contraction by one warp (see the phases above).  SYNC: the warps of the CTA step through the phases together;
+// EXPORT: also write the operators (U and L^-1) that update eta and c of any other pair with the same two precision matrices.
+template <int DT, bool SYNC, bool EXPORT>
+__device__ __forceinline__ void gauss_pair_body(const float* Lx, const float* Ly, const float* ex, const float* ey, float cxv, float cyv, int D,
+                                                float* Lo, float* eo, float* co, int32_t* flag, GaussWarpSmem<DT>& sm, int lane,
+                                                float* opU, float* opLinv) {
+    const int n = 2 * D;
+    constexpr int NCOL = (2 * DT + 31) / 32;  // right-hand-side columns / output rows per lane
+    // right-hand sides of phase 2 (G' columns, lane = column).  For D <= 16 they are requested before the Cholesky, whose
+    // serial chain hides the latency; at D = 32 the 64 extra live registers spill, so they are loaded at phase 2.
+    float u[NCOL][DT];
+    auto load_rhs = [&]() {
+#pragma unroll
+        for (int q = 0; q < NCOL; ++q) {
+            const int c = lane + 32 * q;
+            const int blk = c / DT, cc = c % DT;  // 0: a-block, 1: c-block
+#pragma unroll
+            for (int k = 0; k < DT; ++k) {
+                float g = 0.f;
+                if (c < 2 * DT && cc < D && k < D) g = blk == 0 ? __ldg(Lx + (D + k) * n + cc) : __ldg(Ly + k * n + D + cc);
+                u[q][k] = g;
+            }
+        }
+    };
+    if (DT <= 16) load_rhs();
+
+    // ---- phase 1: Cholesky of M = Lx_bb + Ly_aa, lane = row (M is symmetric: column `lane` is read, coalesced, as row `lane`)
+    float m[DT];
+#pragma unroll
+    for (int k = 0; k < DT; ++k)
+        m[k] = (lane < D && k < D) ? __ldg(Lx + (D + k) * n + D + lane) + __ldg(Ly + k * n + lane) : (k == lane ? 1.f : 0.f);
+    float logdet = 0.f, dinv = 1.f;  // dinv: 1 / L[lane][lane]
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < DT; ++j) {
+        float d = __shfl_sync(0xffffffffu, m[j], j);
+        if (!(d > 0.f)) {
+            bad = 1;
+            d = 1.f;
+        }
+        // 1/sqrt(d): MUFU.RSQ + one Newton step (full fp32 accuracy, no slow-path call; sqrtf and the divisions below
+        // cost ~25 instructions each and the kernel is instruction-fetch bound)
+        float inv = rsqrtf(d);
+        inv = inv * fmaf(-0.5f * d * inv, inv, 1.5f);
+        const float ljj = d * inv;
+        logdet += __logf(ljj);
+        if (lane == j) dinv = inv;
+        const float lij = lane > j ? m[j] * inv : (lane == j ? ljj : 0.f);
+        m[j] = lij;
+#pragma unroll
+        for (int k = j + 1; k < DT; ++k) m[k] = fmaf(-lij, __shfl_sync(0xffffffffu, lij, k), m[k]);
+    }
+    // v = L^-1 (ex_b + ey_a), still lane = row: lane k ends up with v[k]
+    float val = lane < D ? ex[D + lane] + ey[lane] : 0.f;
+#pragma unroll
+    for (int j = 0; j < DT; ++j) {
+        const float vj = __shfl_sync(0xffffffffu, val, j) * __shfl_sync(0xffffffffu, dinv, j);
+        val = lane == j ? vj : (lane > j ? fmaf(-m[j], vj, val) : val);
+    }
+    if (lane < DT) {
+#pragma unroll
+        for (int k = 0; k < DT; ++k) sm.L[lane][k] = m[k];
+        sm.L[lane][lane] = dinv;  // phase 2 only needs the inverse of the diagonal
+        sm.U[lane][2 * DT] = val;
+    }
+    __syncwarp();
+
+    if (SYNC) __syncthreads();
+    // ---- phase 2: forward substitution, lane = right-hand-side columns c = lane + 32 q of G' (padded layout: the a-block
+    // occupies columns [0, DT), the c-block columns [DT, 2 DT)); G'[k, c] is read through its symmetric counterpart so
+    // that the lanes coalesce: Lx_ab[c, k] = Lx_ba[k, c], Ly_ba[c, k] = Ly_ab[k, c]
+    if (DT > 16) load_rhs();
+#pragma unroll
+    for (int k = 0; k < DT; ++k) {
+        float acc[NCOL];
+#pragma unroll
+        for (int q = 0; q < NCOL; ++q) acc[q] = u[q][k];
+#pragma unroll
+        for (int mm = 0; mm < k; ++mm) {
+            const float l = sm.L[k][mm];
+#pragma unroll
+            for (int q = 0; q < NCOL; ++q) acc[q] = fmaf(-l, u[q][mm], acc[q]);
+        }
+        const float inv = sm.L[k][k];  // holds 1 / L[k][k]
+#pragma unroll
+        for (int q = 0; q < NCOL; ++q) {
+            u[q][k] = acc[q] * inv;
+            const int c = lane + 32 * q;
+            if (c < 2 * DT) sm.U[k][c] = u[q][k];
+        }
+    }
+    __syncwarp();
+
+    if (EXPORT) {
+        // operators for the eta-only update of a time-homogeneous chain: U (padded layout, DT x 2DT) and Linv = L^-1, obtained
+        // by forward substitution on the identity with lane = column
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+#pragma unroll
+            for (int q = 0; q < NCOL; ++q)
+                if (lane + 32 * q < 2 * DT) opU[k * 2 * DT + lane + 32 * q] = u[q][k];
+        }
+        float x[DT];
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            float acc = k == lane ? 1.f : 0.f;
+#pragma unroll
+            for (int mm = 0; mm < k; ++mm) acc = fmaf(-sm.L[k][mm], x[mm], acc);
+            x[k] = acc * sm.L[k][k];
+        }
+        if (lane < DT) {
+#pragma unroll
+            for (int k = 0; k < DT; ++k) opLinv[k * DT + lane] = x[k];
+        }
+    }
+    if (SYNC) __syncthreads();
+    // ---- phase 3: outputs, lane = output rows (padded index) r = lane + 32 q; inputs and output are symmetric, so element
+    // (r, s) is read from / written to (s, r) and the lanes coalesce
+    // The diagonal blocks of the result start from the operands' own blocks (Lx_aa, Ly_cc).  Those reads are issued one
+    // 16-column strip AHEAD of the strip being accumulated: measured with ncu (source page), reading them next to the
+    // store that consumes them serialised 128 global-load latencies per pair and was 55 % of all stall samples.
+    auto load_base = [&](int s0, float (&dst)[NCOL][16]) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int sp = s0 + t, sblk = sp / DT, sc = sp % DT;
+#pragma unroll
+            for (int q = 0; q < NCOL; ++q) {
+                const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
+                float base = 0.f;
+                if (sp < 2 * DT && sc < D && rp < 2 * DT && rc < D && rblk == sblk) {
+                    const int sidx = sblk * D + sc, r = rblk * D + rc;
+                    base = __ldg((rblk == 0 ? Lx : Ly) + sidx * n + r);
+                }
+                dst[q][t] = base;
+            }
+        }
+    };
+    float nb[NCOL][16];
+    load_base(0, nb);
+#pragma unroll 1
+    for (int s0 = 0; s0 < 2 * DT; s0 += 16) {
+        float acc[NCOL][16];
+#pragma unroll
+        for (int q = 0; q < NCOL; ++q)
+#pragma unroll
+            for (int t = 0; t < 16; ++t) acc[q][t] = nb[q][t];
+        if (s0 + 16 < 2 * DT) load_base(s0 + 16, nb);
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            const float4* up = reinterpret_cast<const float4*>(&sm.U[k][s0]);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 uv = up[q4];
+#pragma unroll
+                for (int q = 0; q < NCOL; ++q) {
+                    acc[q][4 * q4 + 0] = fmaf(-u[q][k], uv.x, acc[q][4 * q4 + 0]);
+                    acc[q][4 * q4 + 1] = fmaf(-u[q][k], uv.y, acc[q][4 * q4 + 1]);
+                    acc[q][4 * q4 + 2] = fmaf(-u[q][k], uv.z, acc[q][4 * q4 + 2]);
+                    acc[q][4 * q4 + 3] = fmaf(-u[q][k], uv.w, acc[q][4 * q4 + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int sp = s0 + t;  // padded column index
+            const int sblk = sp / DT, sc = sp % DT;
+            if (sp < 2 * DT && sc < D) {
+                const int sidx = sblk * D + sc;  // real column index
+#pragma unroll
+                for (int q = 0; q < NCOL; ++q) {
+                    const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
+                    if (rp < 2 * DT && rc < D) Lo[sidx * n + rblk * D + rc] = acc[q][t];
+                }
+            }
+        }
+    }
+    // eta' and the scalar need column v of U
+    float e[NCOL], vv = 0.f;
+#pragma unroll
+    for (int q = 0; q < NCOL; ++q) e[q] = 0.f;
+#pragma unroll
+    for (int k = 0; k < DT; ++k) {
+        const float v = sm.U[k][2 * DT];
+#pragma unroll
+        for (int q = 0; q < NCOL; ++q) e[q] = fmaf(u[q][k], v, e[q]);
+        vv = fmaf(v, v, vv);
+    }
+#pragma unroll
+    for (int q = 0; q < NCOL; ++q) {
+        const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
+        if (rp < 2 * DT && rc < D) {
+            const int r = rblk * D + rc;
+            eo[r] = (rblk == 0 ? ex[r] : ey[r]) - e[q];
+        }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        *co = cxv + cyv + D * kHalfLog2Pi - logdet + 0.5f * vv;
+        if (bad && flag) atomicExch(flag, 1);
+    }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(gw_warps<DT>() * 32, DT >= 32 ? 1 : 3) gaussian_pair_combine_warp(GaussPairArgs a, int64_t npairs) {
     constexpr int GW_WARPS = gw_warps<DT>();
@@ -151,7 +355,6 @@ __global__ void __launch_bounds__(gw_warps<DT>() * 32, DT >= 32 ? 1 : 3) gaussia
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     GaussWarpSmem<DT>& sm = reinterpret_cast<GaussWarpSmem<DT>*>(gw_raw)[warp];
     const int D = a.D, n = 2 * D;
-    constexpr int NCOL = (2 * DT + 31) / 32;  // right-hand-side columns / output rows per lane
     // The loop is CTA-uniform and the warps of a CTA meet at a barrier per pair: the body is ~150 KB of straight-line code
     // (everything is unrolled so that the register arrays are statically indexed), and warps drifting apart through it made
     // instruction fetch the top stall reason (ncu: no_instructions 31 %).  In step, the four warps share each fetched line.
@@ -182,178 +385,8 @@ __global__ void __launch_bounds__(gw_warps<DT>() * 32, DT >= 32 ? 1 : 3) gaussia
                 }
             }
         }
-        // right-hand sides of phase 2 (G' columns, lane = column).  For D <= 16 they are requested before the Cholesky, whose
-        // serial chain hides the latency; at D = 32 the 64 extra live registers spill, so they are loaded at phase 2.
-        float u[NCOL][DT];
-        auto load_rhs = [&]() {
-#pragma unroll
-            for (int q = 0; q < NCOL; ++q) {
-                const int c = lane + 32 * q;
-                const int blk = c / DT, cc = c % DT;  // 0: a-block, 1: c-block
-#pragma unroll
-                for (int k = 0; k < DT; ++k) {
-                    float g = 0.f;
-                    if (c < 2 * DT && cc < D && k < D) g = blk == 0 ? __ldg(Lx + (D + k) * n + cc) : __ldg(Ly + k * n + D + cc);
-                    u[q][k] = g;
-                }
-            }
-        };
-        if (DT <= 16) load_rhs();
-
-        // ---- phase 1: Cholesky of M = Lx_bb + Ly_aa, lane = row (M is symmetric: column `lane` is read, coalesced, as row `lane`)
-        float m[DT];
-#pragma unroll
-        for (int k = 0; k < DT; ++k)
-            m[k] = (lane < D && k < D) ? __ldg(Lx + (D + k) * n + D + lane) + __ldg(Ly + k * n + lane) : (k == lane ? 1.f : 0.f);
-        float logdet = 0.f, dinv = 1.f;  // dinv: 1 / L[lane][lane]
-        int bad = 0;
-#pragma unroll
-        for (int j = 0; j < DT; ++j) {
-            float d = __shfl_sync(0xffffffffu, m[j], j);
-            if (!(d > 0.f)) {
-                bad = 1;
-                d = 1.f;
-            }
-            // 1/sqrt(d): MUFU.RSQ + one Newton step (full fp32 accuracy, no slow-path call; sqrtf and the divisions below
-            // cost ~25 instructions each and the kernel is instruction-fetch bound)
-            float inv = rsqrtf(d);
-            inv = inv * fmaf(-0.5f * d * inv, inv, 1.5f);
-            const float ljj = d * inv;
-            logdet += __logf(ljj);
-            if (lane == j) dinv = inv;
-            const float lij = lane > j ? m[j] * inv : (lane == j ? ljj : 0.f);
-            m[j] = lij;
-#pragma unroll
-            for (int k = j + 1; k < DT; ++k) m[k] = fmaf(-lij, __shfl_sync(0xffffffffu, lij, k), m[k]);
-        }
-        // v = L^-1 (ex_b + ey_a), still lane = row: lane k ends up with v[k]
-        float val = lane < D ? ex[D + lane] + ey[lane] : 0.f;
-#pragma unroll
-        for (int j = 0; j < DT; ++j) {
-            const float vj = __shfl_sync(0xffffffffu, val, j) * __shfl_sync(0xffffffffu, dinv, j);
-            val = lane == j ? vj : (lane > j ? fmaf(-m[j], vj, val) : val);
-        }
-        if (lane < DT) {
-#pragma unroll
-            for (int k = 0; k < DT; ++k) sm.L[lane][k] = m[k];
-            sm.L[lane][lane] = dinv;  // phase 2 only needs the inverse of the diagonal
-            sm.U[lane][2 * DT] = val;
-        }
-        __syncwarp();
-
-        __syncthreads();
-        // ---- phase 2: forward substitution, lane = right-hand-side columns c = lane + 32 q of G' (padded layout: the a-block
-        // occupies columns [0, DT), the c-block columns [DT, 2 DT)); G'[k, c] is read through its symmetric counterpart so
-        // that the lanes coalesce: Lx_ab[c, k] = Lx_ba[k, c], Ly_ba[c, k] = Ly_ab[k, c]
-        if (DT > 16) load_rhs();
-#pragma unroll
-        for (int k = 0; k < DT; ++k) {
-            float acc[NCOL];
-#pragma unroll
-            for (int q = 0; q < NCOL; ++q) acc[q] = u[q][k];
-#pragma unroll
-            for (int mm = 0; mm < k; ++mm) {
-                const float l = sm.L[k][mm];
-#pragma unroll
-                for (int q = 0; q < NCOL; ++q) acc[q] = fmaf(-l, u[q][mm], acc[q]);
-            }
-            const float inv = sm.L[k][k];  // holds 1 / L[k][k]
-#pragma unroll
-            for (int q = 0; q < NCOL; ++q) {
-                u[q][k] = acc[q] * inv;
-                const int c = lane + 32 * q;
-                if (c < 2 * DT) sm.U[k][c] = u[q][k];
-            }
-        }
-        __syncwarp();
-
-        __syncthreads();
-        // ---- phase 3: outputs, lane = output rows (padded index) r = lane + 32 q; inputs and output are symmetric, so element
-        // (r, s) is read from / written to (s, r) and the lanes coalesce
-        float* Lo = a.Lo + oe * n * n;
-        float* eo = a.eo + oe * n;
-        // The diagonal blocks of the result start from the operands' own blocks (Lx_aa, Ly_cc).  Those reads are issued one
-        // 16-column strip AHEAD of the strip being accumulated: measured with ncu (source page), reading them next to the
-        // store that consumes them serialised 128 global-load latencies per pair and was 55 % of all stall samples.
-        auto load_base = [&](int s0, float (&dst)[NCOL][16]) {
-#pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const int sp = s0 + t, sblk = sp / DT, sc = sp % DT;
-#pragma unroll
-                for (int q = 0; q < NCOL; ++q) {
-                    const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
-                    float base = 0.f;
-                    if (sp < 2 * DT && sc < D && rp < 2 * DT && rc < D && rblk == sblk) {
-                        const int sidx = sblk * D + sc, r = rblk * D + rc;
-                        base = __ldg((rblk == 0 ? Lx : Ly) + sidx * n + r);
-                    }
-                    dst[q][t] = base;
-                }
-            }
-        };
-        float nb[NCOL][16];
-        load_base(0, nb);
-#pragma unroll 1
-        for (int s0 = 0; s0 < 2 * DT; s0 += 16) {
-            float acc[NCOL][16];
-#pragma unroll
-            for (int q = 0; q < NCOL; ++q)
-#pragma unroll
-                for (int t = 0; t < 16; ++t) acc[q][t] = nb[q][t];
-            if (s0 + 16 < 2 * DT) load_base(s0 + 16, nb);
-#pragma unroll
-            for (int k = 0; k < DT; ++k) {
-                const float4* up = reinterpret_cast<const float4*>(&sm.U[k][s0]);
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const float4 uv = up[q4];
-#pragma unroll
-                    for (int q = 0; q < NCOL; ++q) {
-                        acc[q][4 * q4 + 0] = fmaf(-u[q][k], uv.x, acc[q][4 * q4 + 0]);
-                        acc[q][4 * q4 + 1] = fmaf(-u[q][k], uv.y, acc[q][4 * q4 + 1]);
-                        acc[q][4 * q4 + 2] = fmaf(-u[q][k], uv.z, acc[q][4 * q4 + 2]);
-                        acc[q][4 * q4 + 3] = fmaf(-u[q][k], uv.w, acc[q][4 * q4 + 3]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const int sp = s0 + t;  // padded column index
-                const int sblk = sp / DT, sc = sp % DT;
-                if (sp < 2 * DT && sc < D) {
-                    const int sidx = sblk * D + sc;  // real column index
-#pragma unroll
-                    for (int q = 0; q < NCOL; ++q) {
-                        const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
-                        if (rp < 2 * DT && rc < D) Lo[sidx * n + rblk * D + rc] = acc[q][t];
-                    }
-                }
-            }
-        }
-        // eta' and the scalar need column v of U
-        float e[NCOL], vv = 0.f;
-#pragma unroll
-        for (int q = 0; q < NCOL; ++q) e[q] = 0.f;
-#pragma unroll
-        for (int k = 0; k < DT; ++k) {
-            const float v = sm.U[k][2 * DT];
-#pragma unroll
-            for (int q = 0; q < NCOL; ++q) e[q] = fmaf(u[q][k], v, e[q]);
-            vv = fmaf(v, v, vv);
-        }
-#pragma unroll
-        for (int q = 0; q < NCOL; ++q) {
-            const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
-            if (rp < 2 * DT && rc < D) {
-                const int r = rblk * D + rc;
-                eo[r] = (rblk == 0 ? ex[r] : ey[r]) - e[q];
-            }
-        }
-        bad = __any_sync(0xffffffffu, bad);
-        if (lane == 0) {
-            a.co[oe] = a.cx[xe] + a.cy[ye] + D * kHalfLog2Pi - logdet + 0.5f * vv;
-            if (bad && a.flag) atomicExch(a.flag, 1);
-        }
+        gauss_pair_body<DT, true, false>(Lx, Ly, ex, ey, a.cx[xe], a.cy[ye], D, a.Lo + oe * n * n, a.eo + oe * n, a.co + oe, a.flag, sm, lane,
+                                         nullptr, nullptr);
         __syncwarp();  // the shared-memory slot is reused by the next pair
     }
 }
@@ -488,6 +521,239 @@ static int launch_pair(const float* Lx, const float* ex, const float* cx, int64_
     return launch_pair_warp<32>(a, npairs, stream);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Time-homogeneous chains (GaussianHMM with fixed dynamics, pyro/hmm.py:258-270: only white_vec depends on t).
+// Every element of a level carries the SAME precision matrix per chain -- except the odd leftover of the reference's tree
+// (sum_product.py:696-698), which travels at the end of the sequence as a "tail" with an older precision.  So the O(D^3) part of
+// a pair contraction (Cholesky of M, U = L^-1 G', Lam' = base - U'U) is needed once per level for the (regular, regular) pair
+// and at most once for the (regular, tail) pair; for all other pairs only eta and c change:
+//     z = eta_x[b] + eta_y[a],  v = L^-1 z,  eta' = [eta_x[a]; eta_y[c]] - U' v,  c' = c_x + c_y + const + |v|^2 / 2
+// which is O(D^2) flops and ~12 D bytes per pair.  At C4 (T=100000, B=64, D=32) this replaces 6.4e6 Schur complements by
+// 17 + <=17 of them per chain plus a bandwidth-bound sweep over eta.
+//
+// gaussian_homog_levels: one CTA per chain, warp 0 = the regular pair of each level, warp 1 = the tail pair; writes the
+// per-level operators (U, L^-1, const) and the level precisions (every buffer is written once and read afterwards, so the
+// non-coherent loads of the pair body never see a stale line).
+struct HomogLevelsArgs {
+    const float* Lam;  // [B, n, n]
+    float* Lreg;       // [B, NL, n, n]
+    float* Ltail;      // [B, NL, n, n]
+    float* opU;        // [B, NL, 2, DT, 2 DT]
+    float* opLinv;     // [B, NL, 2, DT, DT]
+    float* konst;      // [B, NL, 2]
+    const float* zeros;  // [n]
+    float* scratch;      // [B, 2, n] unused eta outputs
+    float* Lo;           // [B, n, n] precision of the result
+    int32_t* flag;
+    int64_t T;
+    int D, NL;
+};
+
+template <int DT>
+__global__ void __launch_bounds__(64) gaussian_homog_levels(HomogLevelsArgs a) {
+    __shared__ __align__(16) GaussWarpSmem<DT> sm2[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b = blockIdx.x;
+    const int D = a.D, n = 2 * D;
+    const size_t nn = (size_t)n * n;
+    const float* cur_reg = a.Lam + b * nn;
+    const float* cur_tail = nullptr;
+    bool has_tail = false;
+    int64_t d = a.T;
+    for (int l = 0; d > 1; ++l) {
+        const int64_t npairs = d / 2;
+        const bool odd = d & 1;
+        const bool tail_pair = has_tail && !odd;
+        const int64_t reg_pairs = npairs - (tail_pair ? 1 : 0);
+        float* next_reg = a.Lreg + (b * a.NL + l) * nn;
+        float* next_tail = a.Ltail + (b * a.NL + l) * nn;
+        const size_t op = ((size_t)b * a.NL + l) * 2 + warp;
+        if ((warp == 0 && reg_pairs > 0) || (warp == 1 && tail_pair)) {
+            gauss_pair_body<DT, false, true>(cur_reg, warp == 0 ? cur_reg : cur_tail, a.zeros, a.zeros, 0.f, 0.f, D, warp == 0 ? next_reg : next_tail,
+                                             a.scratch + (b * 2 + warp) * n, a.konst + op, a.flag, sm2[warp], lane, a.opU + op * DT * 2 * DT,
+                                             a.opLinv + op * DT * DT);
+        }
+        __syncthreads();
+        if (tail_pair) {
+            cur_tail = next_tail;
+        } else if (!has_tail && odd) {
+            cur_tail = cur_reg;
+            has_tail = true;
+        }
+        cur_reg = next_reg;
+        d = (d + 1) / 2;
+    }
+    const float* res = has_tail ? cur_tail : cur_reg;
+    for (size_t i = threadIdx.x; i < nn; i += blockDim.x) a.Lo[b * nn + i] = res[i];
+}
+
+// eta / c update of `count` pairs per chain starting at pair index p0, all with the operator (opU, opLinv, konst) of their
+// chain; one warp per pair, the operator lives in registers.  `leftover`: also copy input element d-1 to output slot `lslot`.
+struct HomogEtaArgs {
+    const float* ein;  // [B, in_T, n]
+    const float* cin;  // [B, in_T]
+    float* eout;       // [B, out_T, n]
+    float* cout;       // [B, out_T]
+    const float* opU;  // + b * op_stride * DT * 2 DT
+    const float* opLinv;
+    const float* konst;
+    int64_t op_stride;  // operators per chain (= 2 NL)
+    int64_t in_T, out_T, p0, count;
+    int64_t leftover_src, leftover_dst;  // -1: none
+    int D;
+};
+constexpr int HE_WARPS = 8;
+
+template <int DT>
+__global__ void __launch_bounds__(HE_WARPS * 32) gaussian_homog_eta(HomogEtaArgs a) {
+    constexpr int NCOL = (2 * DT + 31) / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b = blockIdx.y;
+    const int D = a.D, n = 2 * D;
+    const float* U = a.opU + b * a.op_stride * DT * 2 * DT;
+    const float* Li = a.opLinv + b * a.op_stride * DT * DT;
+    const float konst = a.konst[b * a.op_stride];
+    float linv[DT], uu[NCOL][DT];
+#pragma unroll
+    for (int c = 0; c < DT; ++c) linv[c] = lane < DT ? __ldg(Li + lane * DT + c) : 0.f;
+#pragma unroll
+    for (int q = 0; q < NCOL; ++q)
+#pragma unroll
+        for (int k = 0; k < DT; ++k) uu[q][k] = lane + 32 * q < 2 * DT ? __ldg(U + k * 2 * DT + lane + 32 * q) : 0.f;
+    const float* ein = a.ein + b * a.in_T * n;
+    const float* cin = a.cin + b * a.in_T;
+    float* eout = a.eout + b * a.out_T * n;
+    float* cout = a.cout + b * a.out_T;
+    for (int64_t i = (int64_t)blockIdx.x * HE_WARPS + warp; i < a.count; i += (int64_t)gridDim.x * HE_WARPS) {
+        const int64_t p = a.p0 + i;
+        const float* ex = ein + 2 * p * n;
+        const float* ey = ex + n;
+        const float z = lane < D ? ex[D + lane] + ey[lane] : 0.f;
+        float bse[NCOL];
+#pragma unroll
+        for (int q = 0; q < NCOL; ++q) {
+            const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
+            bse[q] = (rp < 2 * DT && rc < D) ? (rblk == 0 ? ex[rc] : ey[D + rc]) : 0.f;
+        }
+        const float cxy = cin[2 * p] + cin[2 * p + 1];
+        float v = 0.f;
+#pragma unroll
+        for (int c = 0; c < DT; ++c) v = fmaf(linv[c], __shfl_sync(0xffffffffu, z, c), v);
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            const float vk = __shfl_sync(0xffffffffu, v, k);
+#pragma unroll
+            for (int q = 0; q < NCOL; ++q) bse[q] = fmaf(-uu[q][k], vk, bse[q]);
+        }
+        const float vv = warp_sum(v * v);
+#pragma unroll
+        for (int q = 0; q < NCOL; ++q) {
+            const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
+            if (rp < 2 * DT && rc < D) eout[p * n + rblk * D + rc] = bse[q];
+        }
+        if (lane == 0) cout[p] = cxy + konst + 0.5f * vv;
+    }
+    if (a.leftover_src >= 0 && blockIdx.x == 0 && warp == 0) {
+        for (int i = lane; i < n; i += 32) eout[a.leftover_dst * n + i] = ein[a.leftover_src * n + i];
+        if (lane == 0) cout[a.leftover_dst] = cin[a.leftover_src];
+    }
+}
+
+static int homog_levels_count(int64_t T) {
+    int nl = 0;
+    for (int64_t d = T; d > 1; d = (d + 1) / 2) ++nl;
+    return nl;
+}
+static size_t homog_workspace_bytes(int64_t B, int64_t T, int D) {
+    const int n = 2 * D, NL = homog_levels_count(T);
+    const int DT = D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 32;
+    const int64_t t1 = (T + 1) / 2, t2 = (t1 + 1) / 2;
+    size_t w = 2 * align_up((size_t)B * NL * n * n * 4) + align_up((size_t)B * NL * 2 * DT * 2 * DT * 4) + align_up((size_t)B * NL * 2 * DT * DT * 4) +
+               align_up((size_t)B * NL * 2 * 4) + align_up((size_t)n * 4) + align_up((size_t)B * 2 * n * 4) + align_up(4);
+    for (int64_t tt : {t1, t2}) w += align_up((size_t)B * tt * n * 4) + align_up((size_t)B * tt * 4);
+    return w + 256;
+}
+
+template <int DT>
+static int homog_chain_run(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int D, float* Lo, float* eo, float* co,
+                           void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    const int n = 2 * D, NL = homog_levels_count(T);
+    const int64_t t1 = (T + 1) / 2, t2 = (t1 + 1) / 2;
+    Arena arena(workspace, workspace_bytes);
+    HomogLevelsArgs la;
+    la.Lam = Lam; la.T = T; la.D = D; la.NL = NL; la.Lo = Lo;
+    la.Lreg = arena.take<float>((size_t)B * NL * n * n);
+    la.Ltail = arena.take<float>((size_t)B * NL * n * n);
+    la.opU = arena.take<float>((size_t)B * NL * 2 * DT * 2 * DT);
+    la.opLinv = arena.take<float>((size_t)B * NL * 2 * DT * DT);
+    la.konst = arena.take<float>((size_t)B * NL * 2);
+    float* zeros = arena.take<float>((size_t)n);
+    la.zeros = zeros;
+    la.scratch = arena.take<float>((size_t)B * 2 * n);
+    la.flag = arena.take<int32_t>(1);
+    float *be[2], *bc[2];
+    const int64_t tt[2] = {t1, t2};
+    for (int q = 0; q < 2; ++q) {
+        be[q] = arena.take<float>((size_t)B * tt[q] * n);
+        bc[q] = arena.take<float>((size_t)B * tt[q]);
+    }
+    if (!arena.ok()) {
+        set_error("gaussian_chain (homogeneous): workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    FB2_REQUIRE(B <= 65535, "gaussian_chain (homogeneous): at most 65535 chains per call");
+    FB2_CUDA(cudaMemsetAsync(la.flag, 0, sizeof(int32_t), stream));
+    FB2_CUDA(cudaMemsetAsync(zeros, 0, (size_t)n * 4, stream));
+    gaussian_homog_levels<DT><<<(unsigned)B, 64, 0, stream>>>(la);
+    FB2_LAUNCH_CHECK();
+    const float *ce = eta, *cc = c;
+    int64_t d = T, in_T = T;
+    bool has_tail = false;
+    int which = 0;
+    for (int l = 0; d > 1; ++l) {
+        const int64_t npairs = d / 2, nd = (d + 1) / 2;
+        const bool odd = d & 1;
+        const bool tail_pair = has_tail && !odd;
+        const int64_t reg_pairs = npairs - (tail_pair ? 1 : 0);
+        float* de = nd == 1 ? eo : be[which];
+        float* dc = nd == 1 ? co : bc[which];
+        HomogEtaArgs ea;
+        ea.ein = ce; ea.cin = cc; ea.eout = de; ea.cout = dc; ea.in_T = in_T; ea.out_T = nd; ea.D = D; ea.op_stride = (int64_t)NL * 2;
+        ea.leftover_src = -1; ea.leftover_dst = -1;
+        if (reg_pairs > 0) {
+            ea.opU = la.opU + (size_t)(l * 2 + 0) * DT * 2 * DT;
+            ea.opLinv = la.opLinv + (size_t)(l * 2 + 0) * DT * DT;
+            ea.konst = la.konst + (size_t)(l * 2 + 0);
+            ea.p0 = 0; ea.count = reg_pairs;
+            if (odd) {
+                ea.leftover_src = d - 1;
+                ea.leftover_dst = nd - 1;
+            }
+            int64_t blocks = ceil_div(reg_pairs, HE_WARPS * 4);
+            if (blocks > 65535) blocks = 65535;
+            if (blocks * B > 148 * 32) blocks = std::max<int64_t>(1, 148 * 32 / B);
+            gaussian_homog_eta<DT><<<dim3((unsigned)blocks, (unsigned)B), HE_WARPS * 32, 0, stream>>>(ea);
+            FB2_LAUNCH_CHECK();
+        }
+        if (tail_pair) {
+            ea.opU = la.opU + (size_t)(l * 2 + 1) * DT * 2 * DT;
+            ea.opLinv = la.opLinv + (size_t)(l * 2 + 1) * DT * DT;
+            ea.konst = la.konst + (size_t)(l * 2 + 1);
+            ea.p0 = npairs - 1; ea.count = 1;
+            ea.leftover_src = -1; ea.leftover_dst = -1;
+            gaussian_homog_eta<DT><<<dim3(1, (unsigned)B), HE_WARPS * 32, 0, stream>>>(ea);
+            FB2_LAUNCH_CHECK();
+        }
+        if (!tail_pair && !has_tail && odd) has_tail = true;
+        ce = de; cc = dc; in_T = nd; d = nd;
+        which ^= 1;
+    }
+    gaussian_poison_if_flag<<<(unsigned)ceil_div(B, 256), 256, 0, stream>>>(la.flag, co, B);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
 }  // namespace fb2
 
 using namespace fb2;
@@ -541,7 +807,9 @@ extern "C" size_t fb2_gaussian_chain_workspace_bytes(int64_t B, int64_t T, int32
     for (int64_t tt : {t1, t2})
         per += align_up((size_t)B * tt * n * n * 4) + align_up((size_t)B * tt * n * 4) + align_up((size_t)B * tt * 4);
     (void)gauss_elem_floats;
-    return per + align_up(4) + 256;
+    const size_t tree = per + align_up(4) + 256;
+    const size_t homog = T >= 2 ? homog_workspace_bytes(B, T, D) : 0;
+    return tree > homog ? tree : homog;
 }
 
 static int gaussian_chain_impl(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D, float* Lo, float* eo,
@@ -574,6 +842,16 @@ static int gaussian_chain_impl(const float* Lam, const float* eta, const float* 
         gaussian_copy_elements<<<(unsigned)ceil_div(B * per, 256), 256, 0, stream>>>(Lam, eta, c, 1, 0, Lo, eo, co, 1, 0, B, n);
         FB2_LAUNCH_CHECK();
         return FB2_OK;
+    }
+    // time-homogeneous chains: per-level precision operators + eta-only sweeps (FB2_GAUSS_HOMOG_TREE=1 keeps the full tree)
+    {
+        const char* tree_env = getenv("FB2_GAUSS_HOMOG_TREE");
+        if (homog && T >= 4 && B <= 65535 && !(tree_env && tree_env[0] == '1')) {
+            if (D <= 4) return homog_chain_run<4>(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream);
+            if (D <= 8) return homog_chain_run<8>(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream);
+            if (D <= 16) return homog_chain_run<16>(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream);
+            return homog_chain_run<32>(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream);
+        }
     }
     bool first_level = true;
     int64_t t1 = (T + 1) / 2, t2 = (t1 + 1) / 2;

@@ -121,7 +121,8 @@ def test_too_little_information_raises(fg):
         fg.gaussian_sequential_sum_product(Lam, eta, c)
 
 
-@pytest.mark.parametrize("B,T,D,O", [(3, 37, 4, 2), (2, 64, 32, 16), (5, 1, 3, 2), (1, 9, 8, 8)])
+@pytest.mark.parametrize("B,T,D,O", [(3, 37, 4, 2), (2, 64, 32, 16), (5, 1, 3, 2), (1, 9, 8, 8)] + [(2, T, 3, 2) for T in range(2, 36)]
+                         + [(2, 100, 16, 8), (1, 1023, 32, 16), (3, 1000, 5, 3), (2, 77, 32, 20)])
 def test_kalman_homogeneous_path_matches_general_path(B, T, D, O):
     """kalman_chain (time-invariant prec_sqrt, Lam formed once per chain, level 1 reads it with stride 0) against the general
     path that materialises every element."""
@@ -142,3 +143,27 @@ def test_kalman_homogeneous_path_matches_general_path(B, T, D, O):
     want = fg.gaussian_sequential_sum_product(*fg.sqrt_to_info(w, P, s))
     for a, b in zip(got, want):
         close_norm(host(a), host(b).astype(np.float64), 2e-5)
+
+
+@pytest.mark.parametrize("T", [4, 5, 6, 7, 11, 12, 13, 29, 64, 65, 1000, 4097])
+@pytest.mark.parametrize("D,O", [(2, 1), (32, 16)])
+def test_kalman_homogeneous_operator_path_against_float64_filter(fg, T, D, O):
+    """The per-level-operator path for time-homogeneous chains (eta-only sweeps; every tail / odd-leftover combination of the
+    reference's tree, sum_product.py:690-701) against the float64 oracle: chain elements and, through them, the log-likelihood."""
+    rng = np.random.default_rng(T * 100 + D)
+    B = 2
+    F = 0.9 * np.linalg.qr(rng.standard_normal((B, D, D)))[0]
+    H = rng.standard_normal((B, D, O)) / np.sqrt(D)
+
+    def spd_tril(n):
+        a = rng.standard_normal((B, n, n))
+        return np.linalg.cholesky(a @ a.transpose(0, 2, 1) / n + 0.5 * np.eye(n))
+
+    args = (F, 0.1 * rng.standard_normal((B, D)), spd_tril(D), H, 0.1 * rng.standard_normal((B, O)), spd_tril(O), rng.standard_normal((B, T, O)))
+    chain = fg.kalman_chain(*[dev(a) for a in args])
+    want = G.chain_info(*G.kalman_elements_info(*args), D)
+    for a, b in zip(chain, want):
+        close_norm(host(a), b, 1e-5)
+    m0, p0 = rng.standard_normal((B, D)), spd_tril(D)
+    lp = fg.gaussian_hmm_log_prob(dev(m0), dev(p0), chain)
+    close_norm(host(lp), G.hmm_logprob_from_chain(G.mvn_info(m0, p0), want, D), 1e-5)
