@@ -455,23 +455,63 @@ __global__ void __launch_bounds__(256) gaussian_sqrt_to_info(const float* w, con
     }
 }
 
-// eta[b,t,:] = P[b] w[b,t,:],  c[b,t] = s[b,t] - |w[b,t]|^2 / 2   for a time-invariant prec_sqrt P[b] (n x r): one warp per (b,t)
-__global__ void gaussian_eta_c(const float* w, const float* P, const float* s, int64_t B, int64_t T, int n, int r, float* eta, float* c) {
-    const int64_t e = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
-    if (e >= B * T) return;
-    const int lane = threadIdx.x % 32;
-    const int64_t b = e / T;
-    const float* we = w + e * r;
+// eta[b,t,:] = P[b] w[b,t,:],  c[b,t] = s[b,t] - |w[b,t]|^2 / 2   for a time-invariant prec_sqrt P[b] (n x r).
+// One thread per (b,t): P[b] sits in shared memory (rows padded to a multiple of 4, read as broadcast LDS.128), the thread
+// streams its w row four entries at a time and keeps all n outputs in registers; a warp reads / writes contiguous
+// 32 r / 32 n floats.  (The first version -- one warp per element with per-lane strided reads of P -- took 38.6 ms of the
+// 47 ms of C4; this one is bandwidth-bound.)
+constexpr int ETA_THREADS = 128;
+template <int NMAX>
+__global__ void __launch_bounds__(ETA_THREADS) gaussian_eta_c(const float* w, const float* P, const float* s, int64_t B, int64_t T, int n, int r,
+                                                              float* eta, float* c) {
+    extern __shared__ __align__(16) float eta_sP[];  // [n][r4]
+    const int r4 = (r + 3) / 4 * 4;
+    const int64_t b = blockIdx.y;
     const float* Pb = P + b * (int64_t)n * r;
-    float ww = 0.f;
-    for (int k = lane; k < r; k += 32) ww = fmaf(we[k], we[k], ww);
-    ww = warp_sum(ww);
-    for (int i = lane; i < n; i += 32) {
-        float acc = 0.f;
-        for (int k = 0; k < r; ++k) acc = fmaf(__ldg(Pb + (int64_t)i * r + k), __ldg(we + k), acc);
-        eta[e * n + i] = acc;
+    for (int idx = threadIdx.x; idx < n * r4; idx += ETA_THREADS) {
+        const int i = idx / r4, k = idx % r4;
+        eta_sP[idx] = k < r ? Pb[(int64_t)i * r + k] : 0.f;
     }
-    if (lane == 0) c[e] = (s ? s[e] : 0.f) - 0.5f * ww;
+    __syncthreads();
+    const int64_t t = (int64_t)blockIdx.x * ETA_THREADS + threadIdx.x;
+    if (t >= T) return;
+    const int64_t e = b * T + t;
+    const float* we = w + e * r;
+    const bool vec = (r % 4 == 0) && (reinterpret_cast<uintptr_t>(w) % 16 == 0);
+    float acc[NMAX];
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) acc[i] = 0.f;
+    float ww = 0.f;
+    for (int k0 = 0; k0 < r4; k0 += 4) {
+        float4 wv;
+        if (vec) {
+            wv = __ldg(reinterpret_cast<const float4*>(we + k0));
+        } else {
+            wv.x = k0 + 0 < r ? __ldg(we + k0 + 0) : 0.f;
+            wv.y = k0 + 1 < r ? __ldg(we + k0 + 1) : 0.f;
+            wv.z = k0 + 2 < r ? __ldg(we + k0 + 2) : 0.f;
+            wv.w = k0 + 3 < r ? __ldg(we + k0 + 3) : 0.f;
+        }
+        ww = fmaf(wv.x, wv.x, fmaf(wv.y, wv.y, fmaf(wv.z, wv.z, fmaf(wv.w, wv.w, ww))));
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i) {
+            if (i < n) {
+                const float4 p = *reinterpret_cast<const float4*>(&eta_sP[i * r4 + k0]);
+                acc[i] = fmaf(p.x, wv.x, fmaf(p.y, wv.y, fmaf(p.z, wv.z, fmaf(p.w, wv.w, acc[i]))));
+            }
+        }
+    }
+    float* eo = eta + e * n;
+    if (n % 4 == 0 && reinterpret_cast<uintptr_t>(eta) % 16 == 0) {
+#pragma unroll
+        for (int i = 0; i < NMAX; i += 4)
+            if (i < n) *reinterpret_cast<float4*>(eo + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i)
+            if (i < n) eo[i] = acc[i];
+    }
+    c[e] = (s ? s[e] : 0.f) - 0.5f * ww;
 }
 
 // copy one strided element per outer index: dst[q0*o_s0 + slot] = src[q0*s_s0 + which]
@@ -795,7 +835,21 @@ extern "C" int fb2_gaussian_eta_f32(const float* w, const float* P, const float*
     FB2_REQUIRE(w && P && eta && c, "null pointer");
     FB2_REQUIRE(B >= 0 && T >= 0 && dim >= 1 && rank >= 0, "bad extents");
     if (B * T == 0) return FB2_OK;
-    gaussian_eta_c<<<(unsigned)ceil_div(B * T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, P, s, B, T, dim, rank, eta, c);
+    FB2_REQUIRE(dim <= 2 * GMAXD && B <= 65535, "gaussian_eta: dim=%d or B=%lld out of range", dim, (long long)B);
+    const size_t smem = (size_t)dim * ((rank + 3) / 4 * 4) * sizeof(float);
+    FB2_REQUIRE(smem <= 200 * 1024, "gaussian_eta: prec_sqrt of %d x %d does not fit in shared memory", dim, rank);
+    const dim3 grid((unsigned)ceil_div(T, ETA_THREADS), (unsigned)B);
+    cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+#define FB2_ETA_LAUNCH(NMAXv)                                                                                                   \
+    do {                                                                                                                        \
+        FB2_CUDA(cudaFuncSetAttribute(gaussian_eta_c<NMAXv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        gaussian_eta_c<NMAXv><<<grid, ETA_THREADS, smem, st_>>>(w, P, s, B, T, dim, rank, eta, c);                             \
+    } while (0)
+    if (dim <= 8) FB2_ETA_LAUNCH(8);
+    else if (dim <= 16) FB2_ETA_LAUNCH(16);
+    else if (dim <= 32) FB2_ETA_LAUNCH(32);
+    else FB2_ETA_LAUNCH(64);
+#undef FB2_ETA_LAUNCH
     FB2_LAUNCH_CHECK();
     return FB2_OK;
 }
