@@ -288,6 +288,7 @@ def extra_measurements(device):
     import funsor_b200.gaussian as fg
 
     out = {}
+    peaks = measured_peaks()
     g = torch.Generator(device=device).manual_seed(0)
 
     def timeit(fn, n=3):
@@ -301,8 +302,8 @@ def extra_measurements(device):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n * 1e-3
 
-    # Kalman (C4 shape, T reduced 100000 -> 16384): D=32, O=16, B=64, homogeneous dynamics; elements + eta + parallel scan
-    Bk, Tk, D, O = 64, 16384, 32, 16
+    # Kalman (C4 at full size): D=32, O=16, B=64, T=100000, homogeneous dynamics; factor construction + eta + parallel scan
+    Bk, Tk, D, O = 64, 100000, 32, 16
     F = 0.9 * torch.linalg.qr(torch.randn(Bk, D, D, device=device, generator=g))[0]
     H = torch.randn(Bk, D, O, device=device, generator=g) / D ** 0.5
     eye = lambda n: torch.eye(n, device=device).expand(Bk, n, n).contiguous()  # noqa: E731
@@ -310,8 +311,11 @@ def extra_measurements(device):
     kargs = (F, torch.zeros(Bk, D, device=device), eye(D), H, torch.zeros(Bk, O, device=device), eye(O), y)
     sec = timeit(lambda: fg.kalman_chain(*kargs, validate=False))
     out["kalman_scan"] = {"steps_per_s": Bk * Tk / sec, "D": D, "O": O, "B": Bk, "T": Tk, "ms": sec * 1e3,
-                          "kernel": "gaussian_pair_combine_warp<32> (one warp per pair contraction, fp32 CUDA cores)",
-                          "note": "C4 shape at reduced T; full size (T=100000): profiles/r01_full_configs.jsonl"}
+                          "kernel": "gaussian_homog_levels<32> (precision operators per tree level) + gaussian_homog_eta<32> (eta-only sweeps) + gaussian_eta_c<64>",
+                          "roofline": {"bound": "hbm", "achieved": Bk * Tk * (16 + 48 + 64 + 3 * 64 + 6) * 4 / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                       "frac": Bk * Tk * (16 + 48 + 64 + 3 * 64 + 6) * 4 / sec / 1e9 / peaks["hbm_gbs"],
+                                       "note": "algorithmic bytes per step: read y (O) + write/read w (D+O) + write eta (2D) + ~3x2D+6 for the eta sweeps of all levels"},
+                          "note": "BASELINE config C4 at full size; the general (time-varying) scan runs gaussian_pair_combine_warp<32> at 3.6e7 pair contractions/s"}
     del y, kargs
     # dense chain product (literal sequential_sum_product semantics), S=1024: tcgen05 3xTF32 log-matmul per level
     Bd, Td, Sd = 4, 64, 1024
