@@ -643,58 +643,104 @@ struct HomogEtaArgs {
     int64_t leftover_src, leftover_dst;  // -1: none
     int D;
 };
-constexpr int HE_WARPS = 8;
+constexpr int HE_THREADS = 128;
 
+// One THREAD per pair: the operator of the chain (L^-1: DT x DT, U: DT x 2DT) sits in shared memory and is read as broadcast
+// LDS.128; z, v and the 2 DT outputs live in registers.  3 DT^2 FMAs and 3 DT^2 / 4 shared loads per pair, no shuffles (a
+// warp-per-pair version with the operator in registers spent 64 shuffles per pair and took 6.7 ms over the levels of C4).
+// A thread reads the 2 n contiguous floats of its pair; neighbouring threads are 2 n floats apart, the lines are shared through L1.
 template <int DT>
-__global__ void __launch_bounds__(HE_WARPS * 32) gaussian_homog_eta(HomogEtaArgs a) {
-    constexpr int NCOL = (2 * DT + 31) / 32;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(HE_THREADS) gaussian_homog_eta(HomogEtaArgs a) {
+    __shared__ __align__(16) float sLi[DT * DT];
+    __shared__ __align__(16) float sU[DT * 2 * DT];
     const int64_t b = blockIdx.y;
     const int D = a.D, n = 2 * D;
-    const float* U = a.opU + b * a.op_stride * DT * 2 * DT;
-    const float* Li = a.opLinv + b * a.op_stride * DT * DT;
+    {
+        const float* U = a.opU + b * a.op_stride * DT * 2 * DT;
+        const float* Li = a.opLinv + b * a.op_stride * DT * DT;
+        for (int i = threadIdx.x; i < DT * DT; i += HE_THREADS) sLi[i] = __ldg(Li + i);
+        for (int i = threadIdx.x; i < DT * 2 * DT; i += HE_THREADS) sU[i] = __ldg(U + i);
+    }
+    __syncthreads();
     const float konst = a.konst[b * a.op_stride];
-    float linv[DT], uu[NCOL][DT];
-#pragma unroll
-    for (int c = 0; c < DT; ++c) linv[c] = lane < DT ? __ldg(Li + lane * DT + c) : 0.f;
-#pragma unroll
-    for (int q = 0; q < NCOL; ++q)
-#pragma unroll
-        for (int k = 0; k < DT; ++k) uu[q][k] = lane + 32 * q < 2 * DT ? __ldg(U + k * 2 * DT + lane + 32 * q) : 0.f;
     const float* ein = a.ein + b * a.in_T * n;
     const float* cin = a.cin + b * a.in_T;
     float* eout = a.eout + b * a.out_T * n;
     float* cout = a.cout + b * a.out_T;
-    for (int64_t i = (int64_t)blockIdx.x * HE_WARPS + warp; i < a.count; i += (int64_t)gridDim.x * HE_WARPS) {
+    const bool vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(a.ein) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.eout) % 16 == 0);
+    for (int64_t i = (int64_t)blockIdx.x * HE_THREADS + threadIdx.x; i < a.count; i += (int64_t)gridDim.x * HE_THREADS) {
         const int64_t p = a.p0 + i;
         const float* ex = ein + 2 * p * n;
         const float* ey = ex + n;
-        const float z = lane < D ? ex[D + lane] + ey[lane] : 0.f;
-        float bse[NCOL];
+        float z[DT], out[2 * DT];
+        if (vec) {
 #pragma unroll
-        for (int q = 0; q < NCOL; ++q) {
-            const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
-            bse[q] = (rp < 2 * DT && rc < D) ? (rblk == 0 ? ex[rc] : ey[D + rc]) : 0.f;
+            for (int k = 0; k < DT; k += 4) {
+                if (k < D) {
+                    const float4 xa = __ldg(reinterpret_cast<const float4*>(ex + k)), xb = __ldg(reinterpret_cast<const float4*>(ex + D + k));
+                    const float4 ya = __ldg(reinterpret_cast<const float4*>(ey + k)), yc = __ldg(reinterpret_cast<const float4*>(ey + D + k));
+                    z[k] = xb.x + ya.x; z[k + 1] = xb.y + ya.y; z[k + 2] = xb.z + ya.z; z[k + 3] = xb.w + ya.w;
+                    out[k] = xa.x; out[k + 1] = xa.y; out[k + 2] = xa.z; out[k + 3] = xa.w;
+                    out[DT + k] = yc.x; out[DT + k + 1] = yc.y; out[DT + k + 2] = yc.z; out[DT + k + 3] = yc.w;
+                } else {
+                    z[k] = z[k + 1] = z[k + 2] = z[k + 3] = 0.f;
+                    out[k] = out[k + 1] = out[k + 2] = out[k + 3] = 0.f;
+                    out[DT + k] = out[DT + k + 1] = out[DT + k + 2] = out[DT + k + 3] = 0.f;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < DT; ++k) {
+                z[k] = k < D ? __ldg(ex + D + k) + __ldg(ey + k) : 0.f;
+                out[k] = k < D ? __ldg(ex + k) : 0.f;
+                out[DT + k] = k < D ? __ldg(ey + D + k) : 0.f;
+            }
         }
         const float cxy = cin[2 * p] + cin[2 * p + 1];
-        float v = 0.f;
+        float vv = 0.f;
 #pragma unroll
-        for (int c = 0; c < DT; ++c) v = fmaf(linv[c], __shfl_sync(0xffffffffu, z, c), v);
+        for (int r = 0; r < DT; ++r) {
+            // v_r = (L^-1 z)_r; L^-1 is lower triangular: columns beyond r are zero (and beyond D the padding is the identity)
+            float v = 0.f;
 #pragma unroll
-        for (int k = 0; k < DT; ++k) {
-            const float vk = __shfl_sync(0xffffffffu, v, k);
+            for (int k = 0; k < DT; k += 4) {
+                if (k <= r) {
+                    const float4 l = *reinterpret_cast<const float4*>(&sLi[r * DT + k]);
+                    v = fmaf(l.x, z[k], fmaf(l.y, z[k + 1], fmaf(l.z, z[k + 2], fmaf(l.w, z[k + 3], v))));
+                }
+            }
+            vv = fmaf(v, v, vv);
 #pragma unroll
-            for (int q = 0; q < NCOL; ++q) bse[q] = fmaf(-uu[q][k], vk, bse[q]);
+            for (int c = 0; c < 2 * DT; c += 4) {
+                const float4 u = *reinterpret_cast<const float4*>(&sU[r * 2 * DT + c]);
+                out[c] = fmaf(-u.x, v, out[c]);
+                out[c + 1] = fmaf(-u.y, v, out[c + 1]);
+                out[c + 2] = fmaf(-u.z, v, out[c + 2]);
+                out[c + 3] = fmaf(-u.w, v, out[c + 3]);
+            }
         }
-        const float vv = warp_sum(v * v);
+        float* eo = eout + p * n;
+        if (vec) {
 #pragma unroll
-        for (int q = 0; q < NCOL; ++q) {
-            const int rp = lane + 32 * q, rblk = rp / DT, rc = rp % DT;
-            if (rp < 2 * DT && rc < D) eout[p * n + rblk * D + rc] = bse[q];
+            for (int k = 0; k < DT; k += 4) {
+                if (k < D) {
+                    *reinterpret_cast<float4*>(eo + k) = make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]);
+                    *reinterpret_cast<float4*>(eo + D + k) = make_float4(out[DT + k], out[DT + k + 1], out[DT + k + 2], out[DT + k + 3]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < DT; ++k) {
+                if (k < D) {
+                    eo[k] = out[k];
+                    eo[D + k] = out[DT + k];
+                }
+            }
         }
-        if (lane == 0) cout[p] = cxy + konst + 0.5f * vv;
+        cout[p] = cxy + konst + 0.5f * vv;
     }
-    if (a.leftover_src >= 0 && blockIdx.x == 0 && warp == 0) {
+    if (a.leftover_src >= 0 && blockIdx.x == 0 && threadIdx.x < 32) {
+        const int lane = threadIdx.x;
         for (int i = lane; i < n; i += 32) eout[a.leftover_dst * n + i] = ein[a.leftover_src * n + i];
         if (lane == 0) cout[a.leftover_dst] = cin[a.leftover_src];
     }
@@ -770,10 +816,9 @@ static int homog_chain_run(const float* Lam, const float* eta, const float* c, i
                 ea.leftover_src = d - 1;
                 ea.leftover_dst = nd - 1;
             }
-            int64_t blocks = ceil_div(reg_pairs, HE_WARPS * 4);
+            int64_t blocks = ceil_div(reg_pairs, HE_THREADS);
             if (blocks > 65535) blocks = 65535;
-            if (blocks * B > 148 * 32) blocks = std::max<int64_t>(1, 148 * 32 / B);
-            gaussian_homog_eta<DT><<<dim3((unsigned)blocks, (unsigned)B), HE_WARPS * 32, 0, stream>>>(ea);
+            gaussian_homog_eta<DT><<<dim3((unsigned)blocks, (unsigned)B), HE_THREADS, 0, stream>>>(ea);
             FB2_LAUNCH_CHECK();
         }
         if (tail_pair) {
@@ -782,7 +827,7 @@ static int homog_chain_run(const float* Lam, const float* eta, const float* c, i
             ea.konst = la.konst + (size_t)(l * 2 + 1);
             ea.p0 = npairs - 1; ea.count = 1;
             ea.leftover_src = -1; ea.leftover_dst = -1;
-            gaussian_homog_eta<DT><<<dim3(1, (unsigned)B), HE_WARPS * 32, 0, stream>>>(ea);
+            gaussian_homog_eta<DT><<<dim3(1, (unsigned)B), HE_THREADS, 0, stream>>>(ea);
             FB2_LAUNCH_CHECK();
         }
         if (!tail_pair && !has_tail && odd) has_tail = true;
