@@ -292,6 +292,141 @@ extern "C" int fb2_semiring_matmul_f32(int semiring, const float* x, const int64
                                   static_cast<cudaStream_t>(stream), -1, shift_ws);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused tail of the scan: once the elements of a chain fit in shared memory (d S^2 fp32 x 1.5), ONE CTA per chain finishes
+// all remaining levels of the reference's tree (sum_product.py:690-701) without leaving the SM.  Small problems -- BASELINE C1
+// (T=100, S=16: 102 KB) is one -- are launch-latency bound on the level-by-level path (~3 launches x 7 levels); here they are a
+// single launch.  Arithmetic per pair as einsum/numpy_log.py:24-47: row / column maxima clamped to finfo.min, exp applied in
+// place (an element plays exactly one role per level), plain dot products, log + shifts.  Max-plus: max_k (x + y), exact.
+constexpr size_t TAIL_SMEM_LIMIT = 200 * 1024;
+constexpr int TAIL_THREADS = 1024;
+static size_t tail_smem_bytes(int64_t d, int S) {
+    const size_t per = (size_t)S * S;
+    return ((size_t)d * per + (size_t)((d + 1) / 2) * per + 2 * (size_t)(d / 2) * S) * sizeof(float);
+}
+
+// index helper: walks idx = tid, tid + NT, ... as (p, i, j) with idx = (p * S + i) * S + j without a division per step
+struct TailIdx {
+    int p, i, j, di, dj;
+    __device__ TailIdx(int tid, int S, int nt) {
+        const int r = tid / S;
+        j = tid % S;
+        i = r % S;
+        p = r / S;
+        di = nt / S;
+        dj = nt % S;
+    }
+    __device__ void next(int S) {
+        j += dj;
+        i += di;
+        if (j >= S) {
+            j -= S;
+            ++i;
+        }
+        while (i >= S) {
+            i -= S;
+            ++p;
+        }
+    }
+};
+
+template <int SEMI>
+__global__ void __launch_bounds__(TAIL_THREADS) chain_product_tail(const float* cur, int64_t s_b, int64_t s_t, int64_t s_i, int64_t s_j, int d0, int S,
+                                                                   float* out) {
+    extern __shared__ __align__(16) float tail_smem[];
+    const int per = S * S;
+    float* A = tail_smem;
+    float* Bf = A + (size_t)d0 * per;
+    float* sx = Bf + (size_t)((d0 + 1) / 2) * per;
+    float* sy = sx + (size_t)(d0 / 2) * S;
+    const int tid = threadIdx.x;
+    const float* src = cur + blockIdx.x * s_b;
+    {
+        // gather the level into shared memory; four independent loads in flight per thread
+        const int total = d0 * per;
+        TailIdx w(tid, S, TAIL_THREADS);
+        int idx = tid;
+        for (; idx + 3 * TAIL_THREADS < total; idx += 4 * TAIL_THREADS) {
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[q] = __ldg(src + (int64_t)w.p * s_t + (int64_t)w.i * s_i + (int64_t)w.j * s_j);
+                w.next(S);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) A[idx + q * TAIL_THREADS] = v[q];
+        }
+        for (; idx < total; idx += TAIL_THREADS) {
+            A[idx] = __ldg(src + (int64_t)w.p * s_t + (int64_t)w.i * s_i + (int64_t)w.j * s_j);
+            w.next(S);
+        }
+    }
+    __syncthreads();
+    int d = d0;
+    while (d > 1) {
+        const int half = d / 2, nd = (d + 1) / 2;
+        if (SEMI == FB2_SEMIRING_LOG) {
+            // shifts: sx[p][i] = max_k x[i][k], sy[p][j] = max_k y[k][j], clamped to finfo.min
+            for (int r = tid; r < half * S; r += TAIL_THREADS) {
+                const int p = r / S, q = r % S;
+                const float* x = A + (size_t)(2 * p) * per + q * S;
+                const float* y = A + (size_t)(2 * p + 1) * per + q;
+                float mx = -FLT_MAX, my = -FLT_MAX;
+                for (int k = 0; k < S; ++k) {
+                    mx = fmaxf(mx, x[k]);
+                    my = fmaxf(my, y[k * S]);
+                }
+                sx[r] = mx;
+                sy[r] = my;
+            }
+            __syncthreads();
+            TailIdx w(tid, S, TAIL_THREADS);  // here p counts elements: even = x (row shift), odd = y (column shift)
+            for (int idx = tid; idx < 2 * half * per; idx += TAIL_THREADS) {
+                const float shift = (w.p & 1) ? sy[(w.p >> 1) * S + w.j] : sx[(w.p >> 1) * S + w.i];
+                A[idx] = __expf(A[idx] - shift);
+                w.next(S);
+            }
+            __syncthreads();
+        }
+        {
+            TailIdx w(tid, S, TAIL_THREADS);
+            for (int idx = tid; idx < half * per; idx += TAIL_THREADS) {
+                const float* x = A + (size_t)(2 * w.p) * per + w.i * S;
+                const float* y = A + (size_t)(2 * w.p + 1) * per + w.j;
+                float v;
+                if (SEMI == FB2_SEMIRING_LOG) {
+                    float acc0 = 0.f, acc1 = 0.f;
+                    int k = 0;
+                    for (; k + 1 < S; k += 2) {
+                        acc0 = fmaf(x[k], y[k * S], acc0);
+                        acc1 = fmaf(x[k + 1], y[(k + 1) * S], acc1);
+                    }
+                    if (k < S) acc0 = fmaf(x[k], y[k * S], acc0);
+                    v = (sx[w.p * S + w.i] + sy[w.p * S + w.j]) + __logf(acc0 + acc1);
+                } else {
+                    v = kNegInf;
+                    for (int k = 0; k < S; ++k) v = fmaxf(v, x[k] + y[k * S]);
+                }
+                Bf[idx] = v;
+                w.next(S);
+            }
+        }
+        if (nd != half)
+            for (int r = tid; r < per; r += TAIL_THREADS) Bf[(size_t)half * per + r] = A[(size_t)(d - 1) * per + r];
+        __syncthreads();
+        float* t = A;
+        A = Bf;
+        Bf = t;  // capacities alternate between d0 and (d0 + 1) / 2 elements; level sizes halve, so they always fit
+        d = nd;
+    }
+    for (int r = tid; r < per; r += TAIL_THREADS) out[(int64_t)blockIdx.x * per + r] = A[r];
+}
+
+static bool chain_tail_disabled() {
+    const char* e = getenv("FB2_DISABLE_CHAIN_TAIL");
+    return e && e[0] == '1';
+}
+
 static void level_sizes(int64_t T, int64_t* t1, int64_t* t2) {
     *t1 = (T + 1) / 2;
     *t2 = (*t1 + 1) / 2;
@@ -333,6 +468,19 @@ extern "C" int fb2_chain_product_f32(int semiring, const float* trans, const int
     int64_t d = T;
     int which = 0;
     while (d > 1) {
+        // (d <= 128: beyond that a level still has enough independent pairs to fill the GPU and one CTA per chain is slower)
+        if (S <= 32 && d <= 128 && B <= 65535 && !chain_tail_disabled() && tail_smem_bytes(d, S) <= TAIL_SMEM_LIMIT) {
+            const size_t smem = tail_smem_bytes(d, S);
+            if (semiring == FB2_SEMIRING_LOG) {
+                FB2_CUDA(cudaFuncSetAttribute(chain_product_tail<FB2_SEMIRING_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                chain_product_tail<FB2_SEMIRING_LOG><<<(unsigned)B, TAIL_THREADS, smem, stream>>>(cur, cs[0], cs[1], cs[2], cs[3], (int)d, S, out);
+            } else {
+                FB2_CUDA(cudaFuncSetAttribute(chain_product_tail<FB2_SEMIRING_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                chain_product_tail<FB2_SEMIRING_MAX><<<(unsigned)B, TAIL_THREADS, smem, stream>>>(cur, cs[0], cs[1], cs[2], cs[3], (int)d, S, out);
+            }
+            FB2_LAUNCH_CHECK();
+            return FB2_OK;
+        }
         int64_t half = d / 2, nd = (d + 1) / 2;
         float* dst = (nd == 1) ? out : buf[which];
         int64_t dst_sb = (nd == 1) ? per : nd * per;  // batch stride of dst in elements
