@@ -30,7 +30,7 @@ from collections import OrderedDict
 import torch
 
 _STATE = {"registered": False, "calls": {"contraction_fast": 0, "contraction_delegated": 0,
-                                         "markov_fast": 0, "markov_delegated": 0}}
+                                         "markov_fast": 0, "markov_delegated": 0, "gaussian_homogeneous": 0}}
 
 
 def stats(reset=False):
@@ -163,6 +163,13 @@ def _kernel_chain(semiring, t):
 def _kernel_gaussian_chain(w, P, s):
     from . import gaussian as fg
 
+    T = w.shape[1]
+    # GaussianHMM with fixed dynamics reaches this rule with a dense prec_sqrt[B, T, 2D, r] whose time slices are all equal
+    # (pyro/hmm.py:258-270: only white_vec depends on t; the Gaussian product materialises the broadcast).  One comparison
+    # pass detects it and the scan then runs on per-level operators + eta-only sweeps (gaussian.gaussian_chain_homog).
+    if T >= 8 and bool((P[:, 1:] == P[:, :1]).all()):
+        _STATE["calls"]["gaussian_homogeneous"] += 1
+        return fg.gaussian_chain_homog(w.contiguous(), P[:, 0].contiguous(), s.contiguous())
     Lam, eta, c = fg.sqrt_to_info(w.contiguous(), P.contiguous(), s.contiguous())
     return fg.gaussian_sequential_sum_product(Lam, eta, c)
 

@@ -95,3 +95,30 @@ def test_gaussian_markov_named_kernel(order, T, D):
     w2, P2, s2 = info_to_sqrt(Lam, eta, c)
     assert torch.allclose(P2 @ P2.transpose(-1, -2), Lam, rtol=1e-4, atol=1e-4)
     assert torch.allclose(s2 - 0.5 * (w2 * w2).sum(-1), c, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("T,D,r", [(8, 2, 3), (37, 4, 6), (200, 16, 24)])
+def test_gaussian_markov_rule_detects_time_invariant_prec_sqrt(T, D, r):
+    """GaussianHMM with fixed dynamics hands the rule a dense prec_sqrt whose time slices are equal: the kernel entry detects
+    it and takes the per-level-operator path; the result must match the general scan of the same (materialised) elements."""
+    import funsor_b200.gaussian as fg
+    from funsor_b200 import funsor_plugin as fp
+
+    g = torch.Generator().manual_seed(T + D)
+    B, n = 3, 2 * D
+    P1 = torch.randn(B, 1, n, r, generator=g) / n ** 0.5
+    P1[:, 0, :D, :D] += torch.eye(D)  # enough information on the shared block
+    P1[:, 0, D:, :D] -= torch.eye(D)
+    P = P1.expand(B, T, n, r).contiguous().cuda()
+    w = torch.randn(B, T, r, generator=g).cuda()
+    s = torch.randn(B, T, generator=g).cuda()
+    fp.stats(reset=True)
+    got = fp._kernel_gaussian_chain(w, P, s)
+    assert fp.stats()["gaussian_homogeneous"] == 1
+    want = fg.gaussian_sequential_sum_product(*fg.sqrt_to_info(w, P, s))
+    for a, b in zip(got, want):
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-5 * float(b.abs().max())), (a - b).abs().max()
+    P[:, T // 2] += 0.01  # one deviating step -> general path
+    fp.stats(reset=True)
+    fp._kernel_gaussian_chain(w, P, s)
+    assert fp.stats().get("gaussian_homogeneous", 0) == 0
