@@ -28,6 +28,7 @@
 //   * 3xTF32 (hi*hi + lo*hi + hi*lo) keeps the contraction at fp32-class accuracy.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include <mutex>
@@ -658,6 +659,315 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
     }
     if (aborted && tid == 0) atomicExch(p.abort_flag, 1);
     cluster_sync_all();  // nobody may exit while a peer can still write into its shared memory
+}
+
+// ------------------------------------------------------------------------------------------ single-hop variant
+// hmm_direct_forward<KW>: the same recurrence with ONE chip-wide hand-over per step instead of two.
+//
+// CTA c of a set owns the 8 columns [8c, 8c+8) and keeps the FULL-K block P[:, 8c:8c+8] resident (K = Sp rows split over
+// its 8 warps, KW = Sp/64 k8-steps each: 3 KW registers per thread).  The 8 columns a CTA produces are exactly one k8-step
+// of every consumer's contraction, so the producer writes them straight in mma A-fragment order (32 lanes x 16 B) and every
+// consumer warp loads its KW fragments with 16-byte loads: no shared-memory staging, no DSMEM reduce-scatter; the K-reduction
+// happens between the 8 warps of a CTA through shared memory.  L2 read traffic rises to 16 Sp 4 B per CTA-step (8 MB per
+// step chip-wide at S = 1024, all hits), which is what buys the removal of the second hop (measured step budget of the
+// two-hop kernel: packet wait 1450 + DSMEM partial wait 1100 of 6400 cycles).
+//
+// Self-validating words: every fp32 mantissa carries a 1-bit step stamp in its LSB (the value is first rounded to even at
+// that bit, the consumer clears it: <= 1 ulp, unbiased); block exponents travel as {stamp16 | zero | E15} words.  Stale
+// content of a slot is always two steps old, whose stamp bit differs.  Each 4-byte word validates itself, so no 16-byte
+// atomicity is assumed.  Chain groups beyond the first are separated by a grid-wide barrier (cooperative launch).
+template <int KW>
+__global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_direct_forward(FlowArgs p) {
+    constexpr int SP = KW * 64;
+    constexpr int NC = SP / 8;  // CTAs per set = k8-steps of the contraction
+    constexpr int NW = 8;       // warps
+    __shared__ __align__(16) float s_part[2][NW][FLOW_CHAINS][8];
+    __shared__ int s_eref[2][NW][FLOW_CHAINS];
+    __shared__ float s_obs[FLOW_OBS_DEPTH][128];
+    __shared__ int s_abort;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+    const int set = blockIdx.x / NC, c = blockIdx.x % NC;
+    const int S = p.S;
+    uint32_t* const data_set = reinterpret_cast<uint32_t*>(p.pkt) + (size_t)set * (2 * NC * 128 + 2 * NC * 16);
+    uint32_t* const expo_set = data_set + 2 * NC * 128;
+    if (tid == 0) s_abort = 0;
+
+    // resident operand: B fragments of P[k, col] = exp(A[k, col] - cA[col]), col = 8c + g, k8-step (warp, ks); slot (tig, h) <-> k = 2 tig + h
+    uint32_t Ph[KW][2], Pl[KW];
+    {
+        const int col = c * 8 + g;
+        const float ca = col < S ? p.cA[col] : 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KW; ++ks) {
+            float lo2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = (warp * KW + ks) * 8 + 2 * tig + h;
+                float v = 0.f;
+                if (k < S && col < S) v = expf((p.transpose ? p.A[(int64_t)col * S + k] : p.A[(int64_t)k * S + col]) - ca);
+                const uint32_t hi = cvt_tf32(v);
+                Ph[ks][h] = hi;
+                lo2[h] = (v - __uint_as_float(hi)) * kScalePl;
+            }
+            const __half2 l = __floats2half2_rn(lo2[0], lo2[1]);
+            Pl[ks] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+    }
+    // final-owner role (tid < 128): chain bc, column jc of this CTA
+    const bool owner = tid < 128;
+    const int bc = (tid >> 3) & 15, jc = tid & 7;
+    const int colC = c * 8 + jc;
+    const float caC = (owner && colC < S) ? p.cA[colC] : 0.f;
+    // where this thread's value goes in the consumers' fragment: lane (bc & 7, jc >> 1), slot (bc >> 3) + 2 (jc & 1)
+    const int pub_word = (((bc & 7) * 4 + (jc >> 1)) * 4) + (bc >> 3) + 2 * (jc & 1);
+    __syncthreads();
+
+    unsigned tau = 0;
+    unsigned nstep = 0;
+    bool aborted = false;
+    const int ngroups_iter = (p.groups_total + p.nsets - 1) / p.nsets;
+    for (int it = 0; it < ngroups_iter; ++it) {
+        const int grp = it * p.nsets + set;
+        const bool grp_ok = grp < p.groups_total;
+        if (grp_ok && !aborted) {
+            const int64_t b0 = (int64_t)grp * FLOW_CHAINS;
+            int E_prev = 0, E_abs = 0;
+            bool zero_last = true;
+            float u_last = 0.f;
+            const bool chain_ok = owner && (b0 + bc) < p.B && colC < S;
+            const float* obs_c = (chain_ok && p.obs) ? p.obs + (((b0 + bc) / p.cpo) * p.obs_T) * S + colC : nullptr;
+            auto obs_row = [&](int64_t step) { return p.reverse ? (p.T - 1 - step) : step; };
+            int64_t chunk_seen = -1;
+            auto wait_rows = [&](int64_t row) {
+                if (!p.ready_flags) return;
+                const int64_t ch = row / p.rows_per_chunk;
+                if (ch == chunk_seen) return;
+                const long long start = clock64();
+                unsigned v;
+                do {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ready_flags + ch) : "memory");
+                } while (v == 0 && clock64() - start < 20 * FLOW_SPIN_LIMIT);
+                chunk_seen = ch;
+            };
+            auto publish = [&](unsigned t_stamp, float u, int E15, bool zero) {
+                uint32_t bits = __float_as_uint(u);
+                bits = ((bits & 3u) == 3u) ? bits + 1u : (bits & ~1u);  // round to even at bit 1: bit 0 is free for the stamp
+                bits |= (t_stamp >> 1) & 1u;
+                uint32_t* dst = data_set + ((size_t)(t_stamp & 1) * NC + c) * 128 + pub_word;
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(dst), "r"(bits) : "memory");
+                if (jc == 0) {
+                    const uint32_t w = ((t_stamp & 0xFFFFu) << 16) | (zero ? 0x8000u : 0u) | (unsigned)E15;
+                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(expo_set + ((size_t)(t_stamp & 1) * NC + c) * 16 + bc), "r"(w)
+                                 : "memory");
+                }
+            };
+            // ---- message before the first step: alpha_{-1} = init
+            if (owner) {
+                float x = -INFINITY;
+                if (chain_ok) x = (p.init ? p.init[(b0 + bc) * p.init_sb + colC] : 0.f) * kLog2e;
+                if (chain_ok && p.cpo > 1) x = (colC == (int)((b0 + bc) % p.cpo)) ? 0.f : -INFINITY;
+                int E15, dE;
+                bool zero;
+                const float u = flow_normalise(1.f, x, 0, E15, zero, dE, false);
+                E_abs = dE;
+                E_prev = E15;
+                u_last = u;
+                zero_last = zero;
+                publish(tau, u, E15, zero);
+            }
+            const uint32_t obs_ring = smem_u32(&s_obs[0][tid & 127]);
+            if (owner) {
+#pragma unroll
+                for (int q = 0; q < FLOW_OBS_DEPTH - 1; ++q) {
+                    if (obs_c && q < p.T) {
+                        wait_rows(obs_row(q));
+                        cp_async4(obs_ring + (uint32_t)q * (128 * 4), obs_c + obs_row(q) * S);
+                    }
+                    cp_async_commit();
+                }
+            }
+
+            for (int64_t t = 0; t < p.T; ++t) {
+                const int par = nstep & 1;
+                int timed_out = 0;
+                // ================= fetch the KW fragments of this warp's K-range =================
+                uint4 q[KW];
+                uint32_t ew[KW];
+                {
+                    const uint32_t* dsrc = data_set + ((size_t)(tau & 1) * NC + warp * KW) * 128 + lane * 4;
+                    const uint32_t* esrc = expo_set + ((size_t)(tau & 1) * NC + warp * KW) * 16 + ((tig & 1) ? g + 8 : g);
+                    const uint32_t want_bit = (tau >> 1) & 1u, want16 = tau & 0xFFFFu;
+                    const long long start = clock64();
+                    // Spin on the (small) exponent words only; the 16-byte fragments are requested once all KW producer groups
+                    // of this warp's K-range have published (polling the fragments themselves multiplied the L2 traffic).
+                    // KW <= 4: the fragments are polled together with the exponent words (one round trip; measured 1.32 vs
+                    // 1.58 us/step at S = 128).
+                    for (;;) {
+                        bool ok = true;
+                        if constexpr (KW >= 8) {
+#pragma unroll
+                            for (int ks = 0; ks < KW; ++ks)
+                                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ew[ks]) : "l"(esrc + ks * 16) : "memory");
+#pragma unroll
+                            for (int ks = 0; ks < KW; ++ks) ok = ok && ((ew[ks] >> 16) == want16);
+                            if (__all_sync(0xffffffffu, ok)) {
+#pragma unroll
+                                for (int ks = 0; ks < KW; ++ks)
+                                    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                                 : "=r"(q[ks].x), "=r"(q[ks].y), "=r"(q[ks].z), "=r"(q[ks].w)
+                                                 : "l"(dsrc + ks * 128)
+                                                 : "memory");
+#pragma unroll
+                                for (int ks = 0; ks < KW; ++ks) {
+                                    const uint32_t all_and = q[ks].x & q[ks].y & q[ks].z & q[ks].w, all_or = q[ks].x | q[ks].y | q[ks].z | q[ks].w;
+                                    ok = ok && ((want_bit ? all_and : ~all_or) & 1u);
+                                }
+                                if (__all_sync(0xffffffffu, ok)) break;
+                            }
+                        } else {
+#pragma unroll
+                            for (int ks = 0; ks < KW; ++ks) {
+                                asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                             : "=r"(q[ks].x), "=r"(q[ks].y), "=r"(q[ks].z), "=r"(q[ks].w)
+                                             : "l"(dsrc + ks * 128)
+                                             : "memory");
+                                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ew[ks]) : "l"(esrc + ks * 16) : "memory");
+                            }
+#pragma unroll
+                            for (int ks = 0; ks < KW; ++ks) {
+                                const uint32_t all_and = q[ks].x & q[ks].y & q[ks].z & q[ks].w, all_or = q[ks].x | q[ks].y | q[ks].z | q[ks].w;
+                                ok = ok && ((want_bit ? all_and : ~all_or) & 1u) && ((ew[ks] >> 16) == want16);
+                            }
+                            if (__all_sync(0xffffffffu, ok)) break;
+                        }
+                        if (clock64() - start > FLOW_SPIN_LIMIT) {
+                            timed_out = 1;
+                            if (lane == 0 && atomicCAS(p.abort_flag + 1, 0, 3) == 0) {
+                                p.abort_flag[2] = (int)blockIdx.x;
+                                p.abort_flag[3] = tid;
+                                p.abort_flag[4] = (int)t;
+                                p.abort_flag[5] = (int)want16;
+                                p.abort_flag[6] = (int)q[0].x;
+                                p.abort_flag[7] = (int)ew[0];
+                            }
+                            break;
+                        }
+                    }
+                }
+                // ================= align block exponents over the K-range, contract =================
+                {
+                    int e0[KW], e1[KW];  // exponent words of chains g and g+8
+#pragma unroll
+                    for (int ks = 0; ks < KW; ++ks) {
+                        const uint32_t other = __shfl_xor_sync(0xffffffffu, ew[ks], 1);
+                        e0[ks] = (int)(((tig & 1) ? other : ew[ks]) & 0xFFFFu);
+                        e1[ks] = (int)(((tig & 1) ? ew[ks] : other) & 0xFFFFu);
+                    }
+                    const int ref0 = e0[0] & 0x7FFF, ref1 = e1[0] & 0x7FFF;
+                    int m0 = -40000, m1 = -40000;
+#pragma unroll
+                    for (int ks = 0; ks < KW; ++ks) {
+                        e0[ks] = (e0[ks] & 0x8000) ? -40000 : sext15(e0[ks] - ref0);
+                        e1[ks] = (e1[ks] & 0x8000) ? -40000 : sext15(e1[ks] - ref1);
+                        m0 = max(m0, e0[ks]);
+                        m1 = max(m1, e1[ks]);
+                    }
+                    float acc[3][4];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll
+                    for (int ks = 0; ks < KW; ++ks) {
+                        const float sc0 = (e0[ks] == -40000) ? 0.f : pow2i(e0[ks] - m0);
+                        const float sc1 = (e1[ks] == -40000) ? 0.f : pow2i(e1[ks] - m1);
+                        const float v[4] = {__uint_as_float(q[ks].x & ~1u) * sc0, __uint_as_float(q[ks].y & ~1u) * sc1,
+                                            __uint_as_float(q[ks].z & ~1u) * sc0, __uint_as_float(q[ks].w & ~1u) * sc1};
+                        uint32_t ah[4], al[4];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            ah[b] = cvt_tf32(v[b]);
+                            al[b] = __float_as_uint(v[b] - __uint_as_float(ah[b]));  // exact, signed; the tensor core drops its low 13 bits (unbiased)
+                        }
+                        const float2 pl = __half22float2(*reinterpret_cast<const __half2*>(&Pl[ks]));
+                        mma_tf32(acc[0], ah, Ph[ks][0], Ph[ks][1]);
+                        mma_tf32(acc[1], al, Ph[ks][0], Ph[ks][1]);
+                        mma_tf32(acc[2], ah, __float_as_uint(pl.x), __float_as_uint(pl.y));
+                    }
+                    float* dst = &s_part[par][warp][0][0];
+                    *reinterpret_cast<float2*>(dst + g * 8 + 2 * tig) =
+                        make_float2(acc[0][0] + (acc[1][0] + kUnscalePl * acc[2][0]), acc[0][1] + (acc[1][1] + kUnscalePl * acc[2][1]));
+                    *reinterpret_cast<float2*>(dst + (g + 8) * 8 + 2 * tig) =
+                        make_float2(acc[0][2] + (acc[1][2] + kUnscalePl * acc[2][2]), acc[0][3] + (acc[1][3] + kUnscalePl * acc[2][3]));
+                    if (tig == 0) {
+                        s_eref[par][warp][g] = (m0 == -40000) ? (0x8000 | ref0) : ((ref0 + m0) & 0x7FFF);
+                        s_eref[par][warp][g + 8] = (m1 == -40000) ? (0x8000 | ref1) : ((ref1 + m1) & 0x7FFF);
+                    }
+                }
+                // observation-only work before the barrier (owners)
+                FlowObs1 oterm;
+                if (owner) {
+                    cp_async_wait<FLOW_OBS_DEPTH - 2>();
+                    const float ob = obs_c ? s_obs[t % FLOW_OBS_DEPTH][tid] : 0.f;
+                    oterm = flow_obs1(chain_ok ? (ob + caC) * kLog2e : -INFINITY, true);
+                }
+                if (__syncthreads_or(timed_out | *(volatile int*)&s_abort)) {
+                    aborted = true;
+                    break;
+                }
+                // ================= owners: reduce the 8 warp partials, finish, publish =================
+                if (owner) {
+                    const int er0 = s_eref[par][0][bc] & 0x7FFF;
+                    int dr[NW], dmax = -40000;
+#pragma unroll
+                    for (int r = 0; r < NW; ++r) {
+                        const int e = s_eref[par][r][bc];
+                        dr[r] = (e & 0x8000) ? -40000 : sext15(e - er0);
+                        dmax = max(dmax, dr[r]);
+                    }
+                    float s = 0.f;
+#pragma unroll
+                    for (int r = 0; r < NW; ++r) s += (dr[r] == -40000) ? 0.f : s_part[par][r][bc][jc] * pow2i(dr[r] - dmax);
+                    const int emax = (dmax == -40000) ? er0 : ((er0 + dmax) & 0x7FFF);
+                    int E15, dE;
+                    bool zero;
+                    const float u = flow_finish1(s, oterm, emax, E15, zero, dE);
+                    E_abs += sext15(E15 - E_prev);
+                    E_prev = E15;
+                    u_last = u;
+                    zero_last = zero;
+                    publish(tau + 1, u, E15, zero);
+                    if (p.hist_u && (b0 + bc) < p.B) {
+                        const int64_t slot = (b0 + bc) * p.hist_T + obs_row(t);
+                        p.hist_u[slot * SP + colC] = u;
+                        if (jc == 0) p.hist_e[slot * (SP / 8) + colC / 8] = zero ? INT_MIN : E_abs;
+                    }
+                    const int64_t tn2 = t + FLOW_OBS_DEPTH - 1;
+                    if (obs_c && tn2 < p.T) {
+                        wait_rows(obs_row(tn2));
+                        cp_async4(obs_ring + (uint32_t)(tn2 % FLOW_OBS_DEPTH) * (128 * 4), obs_c + obs_row(tn2) * S);
+                    }
+                    cp_async_commit();
+                }
+                ++nstep;
+                ++tau;
+            }
+            cp_async_wait<0>();
+            if (owner && (b0 + bc) < p.B && !aborted) {
+                p.fin_u[(b0 + bc) * SP + colC] = u_last;
+                if (jc == 0) p.fin_e[(b0 + bc) * (SP / 8) + colC / 8] = zero_last ? INT_MIN : E_abs;
+            }
+        }
+        if (ngroups_iter > 1) {
+            // every CTA of the grid is done with this group's packets before the next group's initial message may overwrite them
+            __syncthreads();
+            cooperative_groups::this_grid().sync();
+            // slots now hold stamps tau (unread) and tau - 1; continuing with tau + 1 keeps every overwrite two stamps apart
+            if (grp_ok && !aborted) tau += 1;
+            else tau = 0;
+        }
+    }
+    if (aborted && tid == 0) atomicExch(p.abort_flag, 1);
 }
 
 // ------------------------------------------------------------------------------------------ tcgen05 variant
@@ -1518,6 +1828,34 @@ static int flow_launch(FlowArgs& a, cudaStream_t stream) {
     return FB2_OK;
 }
 
+template <int KW>
+static int direct_launch(FlowArgs& a, cudaStream_t stream) {
+    auto kernel = hmm_direct_forward<KW>;
+    constexpr int NC = KW * 8;
+    int per_sm = 0, sms = 0, dev = 0;
+    FB2_CUDA(cudaGetDevice(&dev));
+    FB2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, FLOW_THREADS, 0));
+    int nsets = per_sm * sms / NC;
+    if (nsets > FLOW_MAX_SETS) nsets = FLOW_MAX_SETS;
+    if (nsets > a.groups_total) nsets = a.groups_total;
+    if (nsets < 1) {
+        set_error("hmm direct: %d CTAs cannot be co-resident (%d per SM x %d SMs)", NC, per_sm, sms);
+        return FB2_ERR_UNSUPPORTED;
+    }
+    a.nsets = nsets;
+    void* args[] = {&a};
+    // cooperative launch: all CTAs of the grid are resident together (they wait on each other's packets)
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3((unsigned)(nsets * NC)), dim3(FLOW_THREADS), args, 0, stream);
+    if (getenv("FB2_DEBUG")) fprintf(stderr, "[fb2 direct] launch grid %d (nsets %d) -> %s\n", nsets * NC, nsets, cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        set_error("hmm direct launch failed: %s", cudaGetErrorString(e));
+        return FB2_ERR_CUDA;
+    }
+    count_launch();
+    return FB2_OK;
+}
+
 template <int KSTEPS, int NACC>
 static int flow_launch_tc(FlowArgs& a, cudaStream_t stream) {
     auto kernel = hmm_flow_forward_tc<KSTEPS, NACC>;
@@ -1618,7 +1956,16 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
     // its shorter MMA phase is hidden behind the DSMEM reduce-scatter, which moves the same 8 KB per CTA-step either way).
     const char* tc_env = getenv("FB2_FLOW_TC");
     const bool legacy = !(tc_env && tc_env[0] == '1') || hist_u != nullptr || transpose || reverse || ready_flags != nullptr || cpo > 1;
-    if (!legacy) {
+    // single-hop variant (hmm_direct_forward): measured faster than the two-hop kernel for S <= 512 (1.32 / 1.86 / 2.35 vs 2.08 / 2.42 /
+    // 2.66 us per step at S = 128 / 256 / 512) and slower at S = 1024 (3.68 vs 3.37: 8 MB of L2 reads per step).  FB2_FLOW_DIRECT=0|1 forces.
+    const char* direct_env = getenv("FB2_FLOW_DIRECT");
+    const bool direct = direct_env ? direct_env[0] == '1' : fs.k16 <= 4;
+    if (direct) {
+        if (fs.k16 == 1) st = direct_launch<2>(a, stream);
+        else if (fs.k16 == 2) st = direct_launch<4>(a, stream);
+        else if (fs.k16 == 4) st = direct_launch<8>(a, stream);
+        else st = direct_launch<16>(a, stream);
+    } else if (!legacy) {
         if (fs.k16 == 1) st = flow_launch_tc<2, 1>(a, stream);
         else if (fs.k16 == 2) st = flow_launch_tc<4, 1>(a, stream);
         else if (fs.k16 == 4) st = flow_launch_tc<8, 1>(a, stream);

@@ -348,10 +348,12 @@ def test_hmm_forward_flow_tcgen05_variant(fb, B, T, S):
         A[:, 64:72] = -float("inf")
         obs[2, 5, :] = -float("inf")
     os.environ["FB2_FLOW_TC"] = "1"
+    os.environ["FB2_FLOW_DIRECT"] = "0"
     try:
         got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
     finally:
         os.environ.pop("FB2_FLOW_TC")
+        os.environ.pop("FB2_FLOW_DIRECT")
     want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
     assert not np.isnan(got).any()
     rel_close(got, want, rtol=RTOL, atol=1.0)
@@ -803,3 +805,75 @@ def test_posterior_sampling_matches_exact_path_distribution(fb):
     # reported log-probabilities are the exact posterior log-probabilities of the drawn paths
     rel_close(log_q[0].cpu().numpy(), np.log(post[code]), rtol=1e-5, atol=1.0)
     assert abs(logZ.item() - np.log(np.exp(score).sum())) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("direct", ["0", "1"])
+@pytest.mark.parametrize("B,T,S", [(16, 40, 1024), (5, 33, 65), (40, 25, 257), (3, 90, 160), (2, 300, 100), (4, 20, 130), (1, 64, 700),
+                                   (33, 17, 512), (130, 9, 128)])
+def test_hmm_forward_both_dataflow_kernels(fb, B, T, S, direct):
+    """The two-hop kernel (DSMEM reduce-scatter + L2 packets) and the single-hop kernel (full-K column owners, fragments through
+    L2 with the step stamp in the mantissa LSB) forced at every size, incl. a sparse left-to-right chain, -inf blocks, several
+    chain groups per set and more groups than sets."""
+    import os
+
+    init, A, obs = _flow_case(B, T, S, seed=33)
+    if S == 160:
+        A = torch.full((S, S), -float("inf"))
+        for i in range(S):
+            A[i, i] = np.log(0.6)
+            A[i, (i + 1) % S] = np.log(0.4)
+        init = torch.full((B, S), -float("inf"))
+        init[:, 0] = 0.0
+        obs = obs * 3
+    if S == 130:
+        A[:, 64:72] = -float("inf")
+        obs[2, 5, :] = -float("inf")
+    os.environ["FB2_FLOW_DIRECT"] = direct
+    try:
+        got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+        z2, alpha = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda(), return_alpha=True)
+        zm, gamma, _ = fb.hmm_marginals(init.cuda(), A.cuda(), obs.cuda(), want_xi=False)
+    finally:
+        os.environ.pop("FB2_FLOW_DIRECT")
+    want, walpha = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy(), want_alpha=True)
+    assert not np.isnan(got).any()
+    rel_close(got, want, rtol=RTOL, atol=1.0)
+    rel_close(host(z2), want, rtol=RTOL, atol=1.0)
+    rel_close(host(zm), want, rtol=RTOL, atol=1.0)
+    # Filtered messages travel in the linear domain with one exponent per block of 8 states, and a contraction aligns the blocks
+    # of a K-range to their largest exponent: entries more than ~87 nats (2^-126) below the largest entry of their K-range are
+    # flushed to zero (log = -inf) where the reference's log-space arithmetic keeps e.g. -120.  Such states carry < 1e-37 of the
+    # mass; compare the log-messages wherever they are within 60 nats of the step's maximum; the rest may only be smaller (up to -inf; +0.7 nat of denormal rounding).
+    a = host(alpha)
+    near = walpha >= walpha.max(-1, keepdims=True) - 60.0
+    rel_close(np.where(near, a, 0.0), np.where(near, walpha, 0.0), rtol=RTOL, atol=max(1.0, T / 10))
+    far, afar = walpha[~near], a[~near]
+    # flushed entirely (-inf), partially (too small), or sitting in the denormal range of its block (few mantissa bits, +-0.7 nat)
+    assert not np.isnan(afar).any() and not np.isposinf(afar).any()
+    fin = np.isfinite(far)
+    assert (afar[fin] <= far[fin] + 1.0).all() and np.isneginf(afar[~fin]).all()
+    if S != 160 and S != 130:
+        assert np.abs(np.exp(host(gamma)).sum(-1) - 1).max() < 1e-3
+
+
+@pytest.mark.gpu
+def test_single_hop_kernel_dead_chain_and_exact_zeros(fb):
+    """Stamp bits in the mantissa LSB must not leak mass into forbidden states: a chain whose probability is exactly zero stays
+    at -inf, next to live chains in the same group."""
+    import os
+
+    B, T, S = 3, 50, 96
+    init, A, obs = _flow_case(B, T, S, seed=5)
+    A[:, :48] = -float("inf")  # states 0..47 unreachable
+    obs[1, 20, 48:] = -float("inf")  # chain 1 dies at t = 20
+    os.environ["FB2_FLOW_DIRECT"] = "1"
+    try:
+        got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+        _, alpha = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda(), return_alpha=True)
+    finally:
+        os.environ.pop("FB2_FLOW_DIRECT")
+    want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    assert got[1] == -np.inf and np.isfinite(got[[0, 2]]).all()
+    rel_close(got, want, rtol=RTOL, atol=1.0)
+    assert (host(alpha)[:, :, :48] == -np.inf).all()
