@@ -352,7 +352,7 @@ def extra_measurements(device):
     out["marginals"] = {"units_per_s": 3.0 * Tm * Sm * Sm / sec, "us_per_step": sec * 1e6 / Tm, "S": Sm, "B": 1, "T": Tm, "ms": sec * 1e3,
                         "note": "forward + backward dataflow passes + gamma + xi_sum (outer-product GEMM over time); 3 T S^2 units"}
     sec = timeit(lambda: fb.hmm_forward(im, Am, om), n=2)
-    out["forward_S512_B1"] = {"units_per_s": Tm * Sm * Sm / sec, "us_per_step": sec * 1e6 / Tm, "ms": sec * 1e3, "kernel": "hmm_flow_forward<4,1>"}
+    out["forward_S512_B1"] = {"units_per_s": Tm * Sm * Sm / sec, "us_per_step": sec * 1e6 / Tm, "ms": sec * 1e3, "kernel": "hmm_direct_forward<8> (single-hop dataflow kernel)"}
     return out
 
 
