@@ -42,6 +42,7 @@ eye = lambda n: torch.eye(n, device=dev).expand(Bk, n, n).contiguous()
 y = torch.randn(Bk, Tk, O, device=dev, generator=g)
 kargs = (F, torch.zeros(Bk, D, device=dev), eye(D), H, torch.zeros(Bk, O, device=dev), eye(O), y)
 fg.kalman_chain(*[a[:, :64].contiguous() if a.dim() == 3 and a.shape[1] == Tk else a for a in kargs])
+fg.kalman_chain(*kargs, validate=False)  # first full-size call pays the workspace allocation
 out, ms = timed(lambda: fg.kalman_chain(*kargs, validate=False))
 lp = fg.gaussian_hmm_log_prob(torch.zeros(Bk, D, device=dev), eye(D), out)
 # split-and-recombine property: the chain over [0,T) equals the pair contraction of the chains over [0,T/2) and [T/2,T)
