@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         hi[c] = cvt_tf32(v[c]);
-                        lo[c] = cvt_tf32(v[c] - __uint_as_float(hi[c]));
+                        lo[c] = __float_as_uint(v[c] - __uint_as_float(hi[c]));  // exact and signed; the tensor core drops its low 13 bits (unbiased), one quarter-rate cvt less
                     }
                     unsigned char* dst = row + (ga * 4 + i) * 32;
                     *reinterpret_cast<uint4*>(dst + swz) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
