@@ -740,6 +740,185 @@ static int run_backward(int semiring, const PassPlan& pl, HmmArgs& a, cudaStream
     return coop_launch(hmm_backward_generic<FB2_SEMIRING_MAX, 1>, pl, a, stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Log-semiring forward, streaming path: the same shape class as hmm_maxplus_stream (shared A, S >= 256, few chains) -- in
+// particular S > 1024, where the dataflow kernels do not apply and the generic kernel needs S^2 exp per chain-step (222 us per
+// step at S = 4096).  Exp trick: P = exp(A - colmax A) is formed ONCE, strip-major, and a step is a GEMV in the linear domain
+//     w = v_{t-1} / max v_{t-1},   u_j = (sum_i w_i P_ij) * exp(obs_j + cA_j - m_t),   m_t = max_j (obs_j + cA_j)
+// with the log of every removed scale accumulated in double: L_t = L_{t-1} + log max v_{t-1} + m_t.  Both maxima are computed
+// redundantly (and identically: max is order-independent) by every CTA, so no extra exchange is needed; one grid barrier per
+// step.  Dynamic range per step is that of fp32 (entries ~87 nats below the step maximum flush to zero).
+__global__ void stream_retile_P(const float* A, const float* cA, int S, float* strips) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ntiles = (S + 31) / 32;
+    if (idx >= (int64_t)ntiles * S * 32) return;
+    const int l = (int)(idx & 31);
+    const int64_t r = idx >> 5;
+    const int row = (int)(r % S), tile = (int)(r / S);
+    const int col = tile * 32 + l;
+    strips[idx] = col < S ? expf(A[(int64_t)row * S + col] - cA[col]) : 0.f;
+}
+__global__ void stream_colmax(const float* A, int S, float* cA) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= S) return;
+    float m = -FLT_MAX;
+    for (int i = 0; i < S; ++i) m = fmaxf(m, A[(int64_t)i * S + j]);
+    cA[j] = m;
+}
+
+template <int R>
+__global__ void __launch_bounds__(STREAM_THREADS) hmm_logsum_stream(HmmArgs p, const float* cA) {
+    constexpr int NW = STREAM_WARPS, NTH = STREAM_THREADS;
+    extern __shared__ __align__(16) float smem[];
+    const int S = p.S;
+    float* s_w = smem;                                        // [R][S] scaled previous message
+    float* s_part = s_w + (((size_t)R * S + 3) & ~(size_t)3);  // [NW][R][32]
+    float* s_strip = s_part + NW * R * 32;                     // [keep][32]
+    __shared__ float s_red[2][R][NW];
+    __shared__ double s_L[R];
+    __shared__ float s_vm[R], s_mt[R];
+    const int keep = p.W;
+    if (keep > 0 && (int)blockIdx.x < (S + 31) / 32) {
+        const float4* src = reinterpret_cast<const float4*>(p.A + (size_t)blockIdx.x * S * 32);
+        float4* dst = reinterpret_cast<float4*>(s_strip);
+        for (int idx = threadIdx.x; idx < keep * 8; idx += NTH) dst[idx] = __ldg(src + idx);
+    }
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = (S + 31) / 32;
+    unsigned epoch = 0;
+    unsigned* ctr = p.counters;
+
+    for (int64_t b0 = 0; b0 < p.B; b0 += R) {
+        const int nb = (int)min((int64_t)R, p.B - b0);
+        // ---- v_{-1} = exp(init - max init), L_{-1} = max init (every CTA computes the maxima itself)
+        for (int r = 0; r < R; ++r) {
+            float m = -INFINITY;
+            if (r < nb)
+                for (int j = tid; j < S; j += NTH) m = fmaxf(m, p.init ? p.init[(b0 + r) * p.init_sb + j] : 0.f);
+            m = warp_max(m);
+            if (lane == 0) s_red[0][r][warp] = m;
+        }
+        __syncthreads();
+        if (tid < R) {
+            float m = -INFINITY;
+            for (int w = 0; w < NW; ++w) m = fmaxf(m, s_red[0][tid][w]);
+            s_L[tid] = (double)m;  // -inf for a dead chain, NaN/+inf propagate
+            s_vm[tid] = m;
+        }
+        __syncthreads();
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+            for (int idx = tid; idx < nb * 32; idx += NTH) {
+                const int r = idx >> 5, j = tile * 32 + (idx & 31);
+                if (j < S) {
+                    const float x = p.init ? p.init[(b0 + r) * p.init_sb + j] : 0.f;
+                    p.vec[(b0 + r) * S + j] = (s_vm[r] == -INFINITY) ? 0.f : __expf(x - s_vm[r]);
+                }
+            }
+        group_barrier(ctr, (++epoch) * gridDim.x, gridDim.x);
+
+        for (int64_t t = 0; t < p.T; ++t) {
+            const float* vin = p.vec + (size_t)(t & 1) * p.B * S;
+            float* vout = p.vec + (size_t)((t + 1) & 1) * p.B * S;
+            // ---- stage v_{t-1}, its maximum, and m_t = max_j (obs_j + cA_j)
+            for (int r = 0; r < R; ++r) {
+                float vm = 0.f, mt = -INFINITY;
+                if (r < nb)
+                    for (int i = tid; i < S; i += NTH) {
+                        const float v = __ldcg(vin + (b0 + r) * S + i);
+                        s_w[r * S + i] = v;
+                        vm = fmaxf(vm, v);
+                        mt = fmaxf(mt, (p.obs ? __ldg(p.obs + ((b0 + r) * p.T + t) * S + i) : 0.f) + __ldg(cA + i));
+                    }
+                else
+                    for (int i = tid; i < S; i += NTH) s_w[r * S + i] = 0.f;
+                vm = warp_max(vm);
+                mt = warp_max(mt);
+                if (lane == 0) {
+                    s_red[0][r][warp] = vm;
+                    s_red[1][r][warp] = mt;
+                }
+            }
+            __syncthreads();
+            if (tid < R) {
+                float vm = 0.f, mt = -INFINITY;
+                for (int w = 0; w < NW; ++w) {
+                    vm = fmaxf(vm, s_red[0][tid][w]);
+                    mt = fmaxf(mt, s_red[1][tid][w]);
+                }
+                s_vm[tid] = vm;
+                s_mt[tid] = mt;
+                if (tid < nb) s_L[tid] += (vm > 0.f ? (double)logf(vm) : -INFINITY) + (double)mt;
+            }
+            __syncthreads();
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                float acc[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] = 0.f;
+                const float* Pcol = p.A + (size_t)tile * S * 32 + lane;  // strip-major P: [tile][row][32]
+                int i = warp;
+                for (; i < keep; i += NW * 8) {
+                    float a[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a[u] = s_strip[(i + NW * u) * 32 + lane];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acc[r] = fmaf(s_w[r * S + i + NW * u], a[u], acc[r]);
+                }
+                for (; i + NW * 15 < S; i += NW * 16) {
+                    float a[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) a[u] = __ldg(Pcol + (size_t)(i + NW * u) * 32);
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acc[r] = fmaf(s_w[r * S + i + NW * u], a[u], acc[r]);
+                }
+                for (; i < S; i += NW) {
+                    const float a = __ldg(Pcol + (size_t)i * 32);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = fmaf(s_w[r * S + i], a, acc[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) s_part[(warp * R + r) * 32 + lane] = acc[r];
+                __syncthreads();
+                if (tid < R * 32) {
+                    const int r = tid >> 5, l = tid & 31, c = tile * 32 + l;
+                    if (r < nb && c < S) {
+                        float sum = 0.f;
+                        for (int w = 0; w < NW; ++w) sum += s_part[(w * R + r) * 32 + l];
+                        const float vm = s_vm[r], mt = s_mt[r];
+                        const float ob = (p.obs ? __ldg(p.obs + ((b0 + r) * p.T + t) * S + c) : 0.f) + __ldg(cA + c);
+                        float u = 0.f;
+                        if (vm > 0.f && mt > -INFINITY) u = (sum / vm) * __expf(ob - mt);
+                        if (!(mt < INFINITY) || !(vm < INFINITY)) u = __int_as_float(0x7fc00000);  // inf / NaN input poisons the chain
+                        vout[(b0 + r) * S + c] = u;
+                        if (p.alpha_all) p.alpha_all[((b0 + r) * p.T + t) * S + c] = (float)(s_L[r] + (double)__logf(u));
+                    }
+                }
+                __syncthreads();
+            }
+            group_barrier(ctr, (++epoch) * gridDim.x, gridDim.x);
+        }
+        // ---- out[b] = L_{T-1} + log sum_j v_{T-1}[j]
+        if (blockIdx.x == 0) {
+            const float* vfin = p.vec + (size_t)(p.T & 1) * p.B * S;
+            for (int r = warp; r < nb; r += NW) {
+                double sum = 0.0;
+                for (int j = lane; j < S; j += 32) sum += (double)__ldcg(vfin + (b0 + r) * S + j);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0) {
+                    const double z = s_L[r] + log(sum);
+                    p.out[b0 + r] = (float)z;
+                    if (p.out_d) p.out_d[b0 + r] = z;
+                }
+            }
+        }
+        group_barrier(ctr, (++epoch) * gridDim.x, gridDim.x);  // vec[] and s_L are reused by the next chains
+    }
+}
+
 static int check_hmm_args(int semiring, const float* A, int64_t B, int64_t T, int S) {
     FB2_REQUIRE(semiring == FB2_SEMIRING_LOG || semiring == FB2_SEMIRING_MAX, "unknown semiring %d", semiring);
     FB2_REQUIRE(B >= 0 && T >= 1 && S >= 1, "bad extents B=%lld T=%lld S=%d", (long long)B, (long long)T, S);
@@ -760,6 +939,49 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
     int st = make_plan(B, S, false, &pl);
     const bool stream_ok = semiring == FB2_SEMIRING_MAX && a_sb == 0 && a_st == 0 && cpo == 1 && !final_ && !alpha_last &&
                            !ell_all && S >= 256 && B <= 64 && !stream_disabled();
+    const bool log_stream_ok = semiring == FB2_SEMIRING_LOG && a_sb == 0 && a_st == 0 && cpo == 1 && !final_ && !alpha_last && !ell_all &&
+                               !ell_last && !backptr && !last && S >= 256 && B <= 64 && !stream_disabled();
+    if (log_stream_ok) {
+        Arena arena(workspace, workspace_bytes);
+        float* vec = arena.take<float>((size_t)2 * B * S);
+        unsigned* ctr = arena.take<unsigned>(1024);
+        const size_t strip_elems = (size_t)((S + 31) / 32) * S * 32;
+        float* strips = arena.take<float>(strip_elems);
+        float* cA = arena.take<float>((size_t)S);
+        const int R = B >= 4 ? 4 : 1;
+        size_t smem = ((((size_t)R * S + 3) & ~(size_t)3) + STREAM_WARPS * R * 32) * 4;
+        if (arena.ok() && smem <= g_smem_optin) {
+            FB2_CUDA(cudaMemsetAsync(ctr, 0, 1024 * sizeof(unsigned), stream));
+            stream_colmax<<<(unsigned)ceil_div(S, 128), 128, 0, stream>>>(A, S, cA);
+            FB2_LAUNCH_CHECK();
+            stream_retile_P<<<(unsigned)ceil_div((int64_t)strip_elems, 256), 256, 0, stream>>>(A, cA, S, strips);
+            FB2_LAUNCH_CHECK();
+            HmmArgs a{};
+            a.init = init; a.init_sb = init_sb; a.A = strips; a.obs = obs; a.B = B; a.T = T; a.S = S; a.vec = vec; a.counters = ctr;
+            a.alpha_all = alpha_all; a.out = out; a.out_d = out_d;
+            const int ntiles = (S + 31) / 32;
+            const int grid = ntiles < g_sm_count ? ntiles : g_sm_count;
+            int keep = 0;
+            if (ntiles <= g_sm_count) {
+                keep = (int)((g_smem_optin - smem - 2048) / 128);
+                if (keep > S) keep = S;
+                keep = keep / (8 * STREAM_WARPS) * (8 * STREAM_WARPS);
+                if (keep < 0) keep = 0;
+            }
+            a.W = keep;
+            smem += (size_t)keep * 128;
+            void* args[] = {&a, &cA};
+            const void* fn = R == 4 ? reinterpret_cast<const void*>(hmm_logsum_stream<4>) : reinterpret_cast<const void*>(hmm_logsum_stream<1>);
+            FB2_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(STREAM_THREADS), args, smem, stream);
+            if (e != cudaSuccess) {
+                set_error("hmm_logsum_stream launch failed: %s", cudaGetErrorString(e));
+                return FB2_ERR_CUDA;
+            }
+            count_launch();
+            return FB2_OK;
+        }
+    }
     if (st != FB2_OK && !(stream_ok && st == FB2_ERR_UNSUPPORTED)) return st;
     Arena arena(workspace, workspace_bytes);
     float* vec = arena.take<float>((size_t)2 * B * S);
@@ -850,7 +1072,7 @@ extern "C" size_t fb2_hmm_workspace_bytes(int op, int64_t B, int64_t T, int32_t 
         base += hmm_flow_workspace_bytes(B, S);
         if (fa > base) base = fa;
     }
-    if ((op <= 1 || op == 3) && S >= 256) base += align_up((size_t)((S + 31) / 32) * S * 32 * sizeof(float));  // strip-major copy of A
+    if ((op <= 1 || op == 3) && S >= 256) base += align_up((size_t)((S + 31) / 32) * S * 32 * sizeof(float)) + align_up((size_t)S * 4);  // strip-major copy of A (+ column maxima)
     if (op == 1) base += align_up((size_t)B * T * S * sizeof(int32_t)) + align_up((size_t)B * sizeof(int32_t));
     if (op == 2) {
         base += align_up((size_t)B * T * S * sizeof(float)) + 2 * align_up((size_t)B * T * 8) + align_up((size_t)B * 8);

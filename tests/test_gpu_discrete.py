@@ -877,3 +877,41 @@ def test_single_hop_kernel_dead_chain_and_exact_zeros(fb):
     assert got[1] == -np.inf and np.isfinite(got[[0, 2]]).all()
     rel_close(got, want, rtol=RTOL, atol=1.0)
     assert (host(alpha)[:, :, :48] == -np.inf).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,S", [(1, 40, 1500), (5, 30, 2048), (2, 20, 4096), (4, 25, 1100), (64, 6, 1030)])
+def test_hmm_forward_log_stream_kernel_large_state_space(fb, B, T, S):
+    """S > 1024 (beyond the dataflow kernels): linear-domain streaming GEMV with P = exp(A - colmax) formed once.  logZ and the
+    filtered messages against the float64 oracle, with forbidden transitions, a -inf observation and a chain that dies."""
+    init, A, obs = _flow_case(B, T, S, seed=S + B)
+    A[:, 100:140] = -float("inf")
+    A = torch.log_softmax(A, -1)
+    obs[0, T // 2, 7] = -float("inf")
+    if B >= 4:
+        obs[3, T // 3, :] = -float("inf")  # chain 3 dies
+    z, alpha = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda(), return_alpha=True)
+    z0 = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda())
+    want, walpha = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy(), want_alpha=True)
+    rel_close(host(z), want, rtol=RTOL, atol=1.0)
+    rel_close(host(z0), want, rtol=RTOL, atol=1.0)
+    a = host(alpha)
+    assert (a[:, :, 100:140] == -np.inf).all()
+    near = walpha >= walpha.max(-1, keepdims=True) - 60.0
+    rel_close(np.where(near, a, 0.0), np.where(near, walpha, 0.0), rtol=RTOL, atol=max(1.0, T / 10))
+    if B >= 4:
+        assert host(z)[3] == -np.inf
+
+
+@pytest.mark.gpu
+def test_hmm_forward_log_stream_matches_generic_kernel(fb):
+    import os
+
+    init, A, obs = _flow_case(3, 40, 1200, seed=77, obs_scale=4.0, obs_shift=-20.0)
+    got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    os.environ["FB2_DISABLE_STREAM"] = "1"
+    try:
+        ref = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    finally:
+        os.environ.pop("FB2_DISABLE_STREAM")
+    rel_close(got, ref, rtol=RTOL, atol=1.0)
