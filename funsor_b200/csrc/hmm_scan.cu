@@ -69,6 +69,8 @@ struct HmmArgs {
     double* ell_last;    // nullable [B]: when given, alpha_last is written WITHOUT the running offset and the offset goes here
     int cpo;             // chains per obs/A batch entry (1 normally; S for chunk summaries: chain = b*S + row)
     int init_identity;   // 1: alpha_{-1} of chain c is the semiring identity row (c % cpo)
+    int64_t obs_T;       // hmm_logsum_stream: rows per chain of obs / alpha_all / ell_all (0 = T)
+    int reverse;         // hmm_logsum_stream: step t consumes row T-1-t (backward pass run as a forward pass on A^T)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -748,7 +750,7 @@ static int run_backward(int semiring, const PassPlan& pl, HmmArgs& a, cudaStream
 // with the log of every removed scale accumulated in double: L_t = L_{t-1} + log max v_{t-1} + m_t.  Both maxima are computed
 // redundantly (and identically: max is order-independent) by every CTA, so no extra exchange is needed; one grid barrier per
 // step.  Dynamic range per step is that of fp32 (entries ~87 nats below the step maximum flush to zero).
-__global__ void stream_retile_P(const float* A, const float* cA, int S, float* strips) {
+__global__ void stream_retile_P(const float* A, const float* cA, int S, float* strips, int transpose) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int ntiles = (S + 31) / 32;
     if (idx >= (int64_t)ntiles * S * 32) return;
@@ -756,13 +758,13 @@ __global__ void stream_retile_P(const float* A, const float* cA, int S, float* s
     const int64_t r = idx >> 5;
     const int row = (int)(r % S), tile = (int)(r / S);
     const int col = tile * 32 + l;
-    strips[idx] = col < S ? expf(A[(int64_t)row * S + col] - cA[col]) : 0.f;
+    strips[idx] = col < S ? expf((transpose ? A[(int64_t)col * S + row] : A[(int64_t)row * S + col]) - cA[col]) : 0.f;
 }
-__global__ void stream_colmax(const float* A, int S, float* cA) {
+__global__ void stream_colmax(const float* A, int S, float* cA, int transpose) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= S) return;
     float m = -FLT_MAX;
-    for (int i = 0; i < S; ++i) m = fmaxf(m, A[(int64_t)i * S + j]);
+    for (int i = 0; i < S; ++i) m = fmaxf(m, transpose ? A[(int64_t)j * S + i] : A[(int64_t)i * S + j]);
     cA[j] = m;
 }
 
@@ -785,6 +787,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) hmm_logsum_stream(HmmArgs p, c
     }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (S + 31) / 32;
+    const int64_t OT = p.obs_T ? p.obs_T : p.T;  // rows per chain of obs / alpha_all / ell_all
     unsigned epoch = 0;
     unsigned* ctr = p.counters;
 
@@ -817,6 +820,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) hmm_logsum_stream(HmmArgs p, c
         group_barrier(ctr, (++epoch) * gridDim.x, gridDim.x);
 
         for (int64_t t = 0; t < p.T; ++t) {
+            const int64_t row = p.reverse ? (p.T - 1 - t) : t;
             const float* vin = p.vec + (size_t)(t & 1) * p.B * S;
             float* vout = p.vec + (size_t)((t + 1) & 1) * p.B * S;
             // ---- stage v_{t-1}, its maximum, and m_t = max_j (obs_j + cA_j)
@@ -827,7 +831,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) hmm_logsum_stream(HmmArgs p, c
                         const float v = __ldcg(vin + (b0 + r) * S + i);
                         s_w[r * S + i] = v;
                         vm = fmaxf(vm, v);
-                        mt = fmaxf(mt, (p.obs ? __ldg(p.obs + ((b0 + r) * p.T + t) * S + i) : 0.f) + __ldg(cA + i));
+                        mt = fmaxf(mt, (p.obs ? __ldg(p.obs + ((b0 + r) * OT + row) * S + i) : 0.f) + __ldg(cA + i));
                     }
                 else
                     for (int i = tid; i < S; i += NTH) s_w[r * S + i] = 0.f;
@@ -847,7 +851,10 @@ __global__ void __launch_bounds__(STREAM_THREADS) hmm_logsum_stream(HmmArgs p, c
                 }
                 s_vm[tid] = vm;
                 s_mt[tid] = mt;
-                if (tid < nb) s_L[tid] += (vm > 0.f ? (double)logf(vm) : -INFINITY) + (double)mt;
+                if (tid < nb) {
+                    s_L[tid] += (vm > 0.f ? (double)logf(vm) : -INFINITY) + (double)mt;
+                    if (p.ell_all && blockIdx.x == 0) p.ell_all[(b0 + tid) * OT + row] = s_L[tid];
+                }
             }
             __syncthreads();
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -888,12 +895,20 @@ __global__ void __launch_bounds__(STREAM_THREADS) hmm_logsum_stream(HmmArgs p, c
                         float sum = 0.f;
                         for (int w = 0; w < NW; ++w) sum += s_part[(w * R + r) * 32 + l];
                         const float vm = s_vm[r], mt = s_mt[r];
-                        const float ob = (p.obs ? __ldg(p.obs + ((b0 + r) * p.T + t) * S + c) : 0.f) + __ldg(cA + c);
+                        const float ob = (p.obs ? __ldg(p.obs + ((b0 + r) * OT + row) * S + c) : 0.f) + __ldg(cA + c);
                         float u = 0.f;
                         if (vm > 0.f && mt > -INFINITY) u = (sum / vm) * __expf(ob - mt);
                         if (!(mt < INFINITY) || !(vm < INFINITY)) u = __int_as_float(0x7fc00000);  // inf / NaN input poisons the chain
                         vout[(b0 + r) * S + c] = u;
-                        if (p.alpha_all) p.alpha_all[((b0 + r) * p.T + t) * S + c] = (float)(s_L[r] + (double)__logf(u));
+                        if (p.alpha_all) {
+                            float* dst = p.alpha_all + ((b0 + r) * OT + row) * S + c;
+                            if (p.reverse)  // beta_row = (A exp-contracted with the message) without the observation of this row
+                                *dst = (vm > 0.f ? __logf(sum / vm) : -INFINITY) + __ldg(cA + c) - mt;
+                            else if (p.ell_all)
+                                *dst = __logf(u);  // normalised: the offset goes to ell_all
+                            else
+                                *dst = (float)(s_L[r] + (double)__logf(u));
+                        }
                     }
                 }
                 __syncthreads();
@@ -930,6 +945,63 @@ static int check_hmm_args(int semiring, const float* A, int64_t B, int64_t T, in
 static size_t vec_bytes(int64_t B, int S) { return align_up((size_t)2 * B * S * 4); }
 static size_t ctr_bytes() { return align_up(1024 * sizeof(unsigned)); }
 
+// beta_{T-1} = 1 (log 0) with offset 0
+__global__ void stream_fill_last_row(float* beta_all, double* ell_all, int64_t B, int64_t T, int S) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * S) return;
+    const int64_t b = idx / S;
+    beta_all[(b * T + T - 1) * S + idx % S] = 0.f;
+    if (idx % S == 0) ell_all[b * T + T - 1] = 0.0;
+}
+
+// Runs hmm_logsum_stream if the shape qualifies and the workspace holds its buffers; FB2_ERR_UNSUPPORTED otherwise.
+// reverse = 1: the backward recursion as a forward pass on A^T over rows T_steps-1 .. 0 (beta_hat into alpha_all, offsets into ell_all).
+static int log_stream_pass(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t obs_T, int64_t B, int64_t T_steps, int S,
+                           float* out, double* out_d, float* alpha_all, double* ell_all, int reverse, void* workspace, size_t workspace_bytes,
+                           cudaStream_t stream) {
+    if (S < 256 || B > 64 || stream_disabled() || !g_sm_count) return FB2_ERR_UNSUPPORTED;
+    Arena arena(workspace, workspace_bytes);
+    float* vec = arena.take<float>((size_t)2 * B * S);
+    unsigned* ctr = arena.take<unsigned>(1024);
+    const size_t strip_elems = (size_t)((S + 31) / 32) * S * 32;
+    float* strips = arena.take<float>(strip_elems);
+    float* cA = arena.take<float>((size_t)S);
+    float* out_scratch = arena.take<float>((size_t)B);
+    const int R = B >= 4 ? 4 : 1;
+    size_t smem = ((((size_t)R * S + 3) & ~(size_t)3) + STREAM_WARPS * R * 32) * 4;
+    if (!arena.ok() || smem > g_smem_optin) return FB2_ERR_UNSUPPORTED;
+    FB2_CUDA(cudaMemsetAsync(ctr, 0, 1024 * sizeof(unsigned), stream));
+    stream_colmax<<<(unsigned)ceil_div(S, 128), 128, 0, stream>>>(A, S, cA, reverse);
+    FB2_LAUNCH_CHECK();
+    stream_retile_P<<<(unsigned)ceil_div((int64_t)strip_elems, 256), 256, 0, stream>>>(A, cA, S, strips, reverse);
+    FB2_LAUNCH_CHECK();
+    HmmArgs a{};
+    a.init = init; a.init_sb = init_sb; a.A = strips; a.obs = obs; a.B = B; a.T = T_steps; a.S = S; a.vec = vec; a.counters = ctr;
+    a.alpha_all = alpha_all; a.ell_all = ell_all; a.out = out ? out : out_scratch; a.out_d = out_d; a.obs_T = obs_T; a.reverse = reverse;
+    const int ntiles = (S + 31) / 32;
+    const int grid = ntiles < g_sm_count ? ntiles : g_sm_count;
+    int keep = 0;
+    if (ntiles <= g_sm_count) {
+        keep = (int)((g_smem_optin - smem - 2048) / 128);
+        if (keep > S) keep = S;
+        keep = keep / (8 * STREAM_WARPS) * (8 * STREAM_WARPS);
+        if (keep < 0) keep = 0;
+    }
+    a.W = keep;
+    smem += (size_t)keep * 128;
+    const float* cAc = cA;
+    void* args[] = {&a, &cAc};
+    const void* fn = R == 4 ? reinterpret_cast<const void*>(hmm_logsum_stream<4>) : reinterpret_cast<const void*>(hmm_logsum_stream<1>);
+    FB2_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(STREAM_THREADS), args, smem, stream);
+    if (e != cudaSuccess) {
+        set_error("hmm_logsum_stream launch failed: %s", cudaGetErrorString(e));
+        return FB2_ERR_CUDA;
+    }
+    count_launch();
+    return FB2_OK;
+}
+
 int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb, int64_t a_st,
                        const float* obs, const float* final_, int64_t B, int64_t T, int S, float* out,
                        float* alpha_all, int32_t* backptr, int32_t* last, void* workspace, size_t workspace_bytes,
@@ -939,48 +1011,9 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
     int st = make_plan(B, S, false, &pl);
     const bool stream_ok = semiring == FB2_SEMIRING_MAX && a_sb == 0 && a_st == 0 && cpo == 1 && !final_ && !alpha_last &&
                            !ell_all && S >= 256 && B <= 64 && !stream_disabled();
-    const bool log_stream_ok = semiring == FB2_SEMIRING_LOG && a_sb == 0 && a_st == 0 && cpo == 1 && !final_ && !alpha_last && !ell_all &&
-                               !ell_last && !backptr && !last && S >= 256 && B <= 64 && !stream_disabled();
-    if (log_stream_ok) {
-        Arena arena(workspace, workspace_bytes);
-        float* vec = arena.take<float>((size_t)2 * B * S);
-        unsigned* ctr = arena.take<unsigned>(1024);
-        const size_t strip_elems = (size_t)((S + 31) / 32) * S * 32;
-        float* strips = arena.take<float>(strip_elems);
-        float* cA = arena.take<float>((size_t)S);
-        const int R = B >= 4 ? 4 : 1;
-        size_t smem = ((((size_t)R * S + 3) & ~(size_t)3) + STREAM_WARPS * R * 32) * 4;
-        if (arena.ok() && smem <= g_smem_optin) {
-            FB2_CUDA(cudaMemsetAsync(ctr, 0, 1024 * sizeof(unsigned), stream));
-            stream_colmax<<<(unsigned)ceil_div(S, 128), 128, 0, stream>>>(A, S, cA);
-            FB2_LAUNCH_CHECK();
-            stream_retile_P<<<(unsigned)ceil_div((int64_t)strip_elems, 256), 256, 0, stream>>>(A, cA, S, strips);
-            FB2_LAUNCH_CHECK();
-            HmmArgs a{};
-            a.init = init; a.init_sb = init_sb; a.A = strips; a.obs = obs; a.B = B; a.T = T; a.S = S; a.vec = vec; a.counters = ctr;
-            a.alpha_all = alpha_all; a.out = out; a.out_d = out_d;
-            const int ntiles = (S + 31) / 32;
-            const int grid = ntiles < g_sm_count ? ntiles : g_sm_count;
-            int keep = 0;
-            if (ntiles <= g_sm_count) {
-                keep = (int)((g_smem_optin - smem - 2048) / 128);
-                if (keep > S) keep = S;
-                keep = keep / (8 * STREAM_WARPS) * (8 * STREAM_WARPS);
-                if (keep < 0) keep = 0;
-            }
-            a.W = keep;
-            smem += (size_t)keep * 128;
-            void* args[] = {&a, &cA};
-            const void* fn = R == 4 ? reinterpret_cast<const void*>(hmm_logsum_stream<4>) : reinterpret_cast<const void*>(hmm_logsum_stream<1>);
-            FB2_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(STREAM_THREADS), args, smem, stream);
-            if (e != cudaSuccess) {
-                set_error("hmm_logsum_stream launch failed: %s", cudaGetErrorString(e));
-                return FB2_ERR_CUDA;
-            }
-            count_launch();
-            return FB2_OK;
-        }
+    if (semiring == FB2_SEMIRING_LOG && a_sb == 0 && a_st == 0 && cpo == 1 && !final_ && !alpha_last && !ell_last && !backptr && !last) {
+        const int ls = log_stream_pass(init, init_sb, A, obs, T, B, T, S, out, out_d, alpha_all, ell_all, 0, workspace, workspace_bytes, stream);
+        if (ls != FB2_ERR_UNSUPPORTED) return ls;
     }
     if (st != FB2_OK && !(stream_ok && st == FB2_ERR_UNSUPPORTED)) return st;
     Arena arena(workspace, workspace_bytes);
@@ -1043,6 +1076,17 @@ int hmm_backward_device(int semiring, const float* A, int64_t a_sb, int64_t a_st
                         cudaStream_t stream, double* ell_all = nullptr) {
     PassPlan pl;
     int st = make_plan(B, S, true, &pl);
+    // large shared-A chains: the backward recursion as a streaming forward pass on A^T (beta_hat + offsets), see hmm_logsum_stream
+    if (semiring == FB2_SEMIRING_LOG && a_sb == 0 && a_st == 0 && !final_ && ell_all && obs && T >= 2) {
+        const int ls = log_stream_pass(obs + (T - 1) * (int64_t)S, T * (int64_t)S, A, obs, T, B, T - 1, S, nullptr, nullptr, beta_all, ell_all, 1,
+                                       workspace, workspace_bytes, stream);
+        if (ls == FB2_OK) {
+            stream_fill_last_row<<<(unsigned)ceil_div(B * (int64_t)S, 256), 256, 0, stream>>>(beta_all, ell_all, B, T, S);
+            FB2_LAUNCH_CHECK();
+            return FB2_OK;
+        }
+        if (ls != FB2_ERR_UNSUPPORTED) return ls;
+    }
     if (st != FB2_OK) return st;
     Arena arena(workspace, workspace_bytes);
     float* vec = arena.take<float>((size_t)2 * B * S);
@@ -1072,10 +1116,12 @@ extern "C" size_t fb2_hmm_workspace_bytes(int op, int64_t B, int64_t T, int32_t 
         base += hmm_flow_workspace_bytes(B, S);
         if (fa > base) base = fa;
     }
-    if ((op <= 1 || op == 3) && S >= 256) base += align_up((size_t)((S + 31) / 32) * S * 32 * sizeof(float)) + align_up((size_t)S * 4);  // strip-major copy of A (+ column maxima)
+    if ((op <= 1 || op == 3) && S >= 256)  // strip-major copy of A (+ column maxima, scratch)
+        base += align_up((size_t)((S + 31) / 32) * S * 32 * sizeof(float)) + align_up((size_t)S * 4) + align_up((size_t)B * 4);
     if (op == 1) base += align_up((size_t)B * T * S * sizeof(int32_t)) + align_up((size_t)B * sizeof(int32_t));
     if (op == 2) {
         base += align_up((size_t)B * T * S * sizeof(float)) + 2 * align_up((size_t)B * T * 8) + align_up((size_t)B * 8);
+        if (S >= 256) base += align_up((size_t)((S + 31) / 32) * S * 32 * sizeof(float)) + align_up((size_t)S * 4) + align_up((size_t)B * 4);  // log stream passes
         const size_t fm = hmm_flow_marginals_workspace_bytes(B, T, S);
         if (fm > base) base = fm;
     }

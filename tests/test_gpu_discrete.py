@@ -915,3 +915,23 @@ def test_hmm_forward_log_stream_matches_generic_kernel(fb):
     finally:
         os.environ.pop("FB2_DISABLE_STREAM")
     rel_close(got, ref, rtol=RTOL, atol=1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,S", [(1, 30, 1500), (5, 12, 2048), (2, 40, 1100)])
+def test_hmm_marginals_large_state_space_on_stream_kernels(fb, B, T, S):
+    """Forward-backward for S > 1024: both recursions on the streaming log kernel (backward = forward on A^T over reversed rows)."""
+    init, A, obs = _flow_case(B, T, S, seed=S + T)
+    A[:, 40:60] = -float("inf")
+    A = torch.log_softmax(A, -1)
+    obs[0, T // 2, 7] = -float("inf")
+    logZ, gamma, xi = fb.hmm_marginals(init.cuda(), A.cuda(), obs.cuda(), want_xi=(S <= 1500))
+    wZ, wgamma, wxi = R.hmm_marginals(init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    rel_close(host(logZ), wZ, rtol=RTOL, atol=1.0)
+    g = host(gamma)
+    assert (g[:, :, 40:60] == -np.inf).all() and g[0, T // 2, 7] == -np.inf
+    near = wgamma >= -60.0
+    assert np.abs(np.where(near, g - wgamma, 0.0)).max() < 2e-4
+    assert np.abs(np.exp(g).sum(-1) - 1).max() < 1e-4
+    if xi is not None:
+        assert np.abs(host(xi) - wxi).max() < 1e-3 * max(1.0, np.abs(wxi).max())
