@@ -353,6 +353,23 @@ def extra_measurements(device):
                         "note": "forward + backward dataflow passes + gamma + xi_sum (outer-product GEMM over time); 3 T S^2 units"}
     sec = timeit(lambda: fb.hmm_forward(im, Am, om), n=2)
     out["forward_S512_B1"] = {"units_per_s": Tm * Sm * Sm / sec, "us_per_step": sec * 1e6 / Tm, "ms": sec * 1e3, "kernel": "hmm_direct_forward<8> (single-hop dataflow kernel)"}
+    # forward-filter backward-sample on the same chain: 64 posterior paths
+    Ns = 64
+    us = torch.rand(1, Ns, Tm + 1, device=device, generator=g)
+    sec = timeit(lambda: fb.hmm_posterior_sample(im, Am, om, uniforms=us), n=2)
+    out["posterior_sampling"] = {"path_steps_per_s": Ns * Tm / sec, "samples": Ns, "S": Sm, "T": Tm, "ms": sec * 1e3,
+                                 "kernel": "hmm_direct_forward<8> (alpha history) + hmm_backward_sample (warp per path)"}
+    del Am, om, im, us
+    # log-semiring forward beyond the dataflow kernels: S = 4096 (linear-domain streaming GEMV over strip-major P)
+    Sl, Tl = 4096, 512
+    Al = torch.randn(Sl, Sl, device=device, generator=g).log_softmax(-1)
+    ol = torch.randn(1, Tl, Sl, device=device, generator=g)
+    il = torch.randn(1, Sl, device=device, generator=g).log_softmax(-1)
+    sec = timeit(lambda: fb.hmm_forward(il, Al, ol), n=2)
+    out["forward_S4096_B1"] = {"units_per_s": Tl * Sl * Sl / sec, "us_per_step": sec * 1e6 / Tl, "ms": sec * 1e3, "kernel": "hmm_logsum_stream<1>",
+                               "roofline": {"bound": "hbm", "achieved": 4.0 * Sl * Sl * Tl / sec / 1e9, "peak": hbm_peak(), "unit": "GB/s",
+                                            "frac": 4.0 * Sl * Sl * Tl / sec / 1e9 / hbm_peak(),
+                                            "note": "algorithmic bytes = P (64 MB) re-read every step"}}
     return out
 
 

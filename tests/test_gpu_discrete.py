@@ -931,7 +931,8 @@ def test_hmm_marginals_large_state_space_on_stream_kernels(fb, B, T, S):
     g = host(gamma)
     assert (g[:, :, 40:60] == -np.inf).all() and g[0, T // 2, 7] == -np.inf
     near = wgamma >= -60.0
-    assert np.abs(np.where(near, g - wgamma, 0.0)).max() < 2e-4
+    with np.errstate(invalid="ignore"):
+        assert np.abs(np.where(near, g - wgamma, 0.0)).max() < 2e-4
     assert np.abs(np.exp(g).sum(-1) - 1).max() < 1e-4
     if xi is not None:
         assert np.abs(host(xi) - wxi).max() < 1e-3 * max(1.0, np.abs(wxi).max())
