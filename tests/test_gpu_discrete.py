@@ -547,7 +547,7 @@ def test_host_entry_point_overlapped_copy(fb):
     from funsor_b200 import _lib
 
     lib = _lib.load()
-    for B, T, S, pin in [(3, 5003, 128, True), (16, 4096, 256, False)]:
+    for B, T, S, pin in [(3, 5003, 128, True), (16, 4096, 256, False), (4, 4100, 1024, True)]:
         g = torch.Generator().manual_seed(61)
         init = torch.randn(B, S, generator=g).log_softmax(-1)
         A = torch.randn(S, S, generator=g).log_softmax(-1)
