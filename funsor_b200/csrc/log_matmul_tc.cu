@@ -50,6 +50,13 @@ __device__ __forceinline__ uint32_t lm_smem_u32(const void* p) { return (uint32_
 // element made the staging XU-bound).  lo = x - hi is exact in fp32 and the tensor core itself ignores its low 13 bits,
 // so hi + lo carries 21+ mantissa bits either way.
 __device__ __forceinline__ uint32_t lm_tf32(float x) { return __float_as_uint(x) & 0xffffe000u; }
+// exp(d) for d <= 0 as one FMUL + MUFU.EX2 (flush-to-zero).  __expf without fast-math wraps the same MUFU in denormal
+// handling (FSETP + two more FMULs per element: a quarter of all instructions the kernel issued).
+__device__ __forceinline__ float lm_exp(float d) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d * 1.4426950408889634f));
+    return r;
+}
 // K-major operand tile in the 128-byte-swizzle canonical layout: row r (an output row of X / an output column of Y) at
 // r * 128 B, its eight 16-byte k-chunks XOR-swizzled with (r % 8); 8-row groups 1024 B apart (SBO); one staged chunk of
 // K = 32 TF32 is exactly one swizzle row, and a K = 8 instruction advances the start address by 32 B.  (The no-swizzle
@@ -130,8 +137,16 @@ __global__ void lm_colmax(const float* y, int64_t n1, int64_t ys0, int64_t ys1, 
 // the loss by 3 NMAIN.  What remains is one-sided and, with >= 8 accumulations, close to its mean (rms error ~ |mean error|
 // in the measurement), so the epilogue multiplies every hi*hi partial sum by 1 + 5.82e-8 * (its number of accumulations):
 // that centres the error (residual in scripts/matmul_bias.py / DESIGN.md 4.4).  BN * (NMAIN + 1) = 512 columns = all of the SM's tensor memory (one CTA per SM anyway).
-template <int BN, int NMAIN>
-__global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
+//
+// NTH threads per CTA: the staging work (loads, exp, split, swizzled stores) is what limits the kernel (ncu: tensor pipe 34 %
+// busy, long-scoreboard stalls with 8 warps per SM), so the wide tile runs 16 warps that each stage half as much.
+template <int BN, int NMAIN, int NTH>
+__global__ void __launch_bounds__(NTH, 1) log_matmul_tc(LogMatmulArgs a) {
+    constexpr int XM = 128 / (NTH / 8);      // X rows per thread (rows rbase + (NTH/8) m)
+    constexpr int RP = NTH / 8;              // X rows staged per pass
+    constexpr int YC = BN >= NTH / 8 * 8 ? 8 : BN / (NTH / 8);  // Y columns per thread (8, or 4 with 512 threads on the 256-column tile)
+    constexpr int YV = YC / 4;               // float4 loads per k row
+    static_assert(YC == 8 || YC == 4, "unsupported thread count for this tile");
     constexpr uint32_t NCOLS = BN * (NMAIN + 1);
     static_assert(NCOLS == 512 || NCOLS == 256 || NCOLS == 128, "tensor memory allocation must be a power of two <= 512");
     using Cfg = LmCfg<BN>;
@@ -170,16 +185,16 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
     // Global loads for chunk c+1 are issued right after chunk c has been written to shared memory (register prefetch).
     const int kc = tid & 7, rbase = tid >> 3;
     const int kq = tid & 7, jq = tid >> 3;
-    const bool has_y = tid < BN;
-    float sxr[4], syr[8];
+    const bool has_y = jq * YC < BN;
+    float sxr[XM], syr[YC];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        const int row = i0 + rbase + 32 * m;
+    for (int m = 0; m < XM; ++m) {
+        const int row = i0 + rbase + RP * m;
         sxr[m] = row < a.I ? a.sx[n * a.I + row] : 0.f;
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int j = j0 + jq * 8 + q;
+    for (int q = 0; q < YC; ++q) {
+        const int j = j0 + jq * YC + q;
         syr[q] = (has_y && j < a.J) ? a.sy[n * a.J + j] : 0.f;
     }
     const bool x_vec = (a.xsi % 4 == 0) && (reinterpret_cast<uintptr_t>(xb) % 16 == 0);
@@ -188,14 +203,14 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);  // A, B K-major
     const int nchunks = (a.K + LM_KC - 1) / LM_KC;
 
-    float4 prex[4], prey[8];  // prefetched raw values of the next chunk
+    float4 prex[XM], prey[4 * YV];  // prefetched raw values of the next chunk
     auto load_chunk = [&](int c) {
         const int k0 = c * LM_KC;
         {
             const int k = k0 + kc * 4;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int row = i0 + rbase + 32 * m;
+            for (int m = 0; m < XM; ++m) {
+                const int row = i0 + rbase + RP * m;
                 const float* p = xb + (int64_t)(row < a.I ? row : 0) * a.xsi + k;
                 if (row < a.I && k + 3 < a.K && x_vec) {
                     prex[m] = __ldg(reinterpret_cast<const float4*>(p));
@@ -211,23 +226,54 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 const int k = k0 + kq * 4 + kk;
-                const float* p = yb + (int64_t)(k < a.K ? k : 0) * a.ysk + j0 + jq * 8;
+                const float* p = yb + (int64_t)(k < a.K ? k : 0) * a.ysk + j0 + jq * YC;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = j0 + jq * 8 + h * 4;
+                for (int h = 0; h < YV; ++h) {
+                    const int j = j0 + jq * YC + h * 4;
                     if (k < a.K && j + 3 < a.J && y_vec) {
-                        prey[kk * 2 + h] = __ldg(reinterpret_cast<const float4*>(p + h * 4));
+                        prey[kk * YV + h] = __ldg(reinterpret_cast<const float4*>(p + h * 4));
                     } else {
                         float v[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) v[q] = (k < a.K && j + q < a.J) ? __ldg(p + h * 4 + q) : -INFINITY;
-                        prey[kk * 2 + h] = make_float4(v[0], v[1], v[2], v[3]);
+                        prey[kk * YV + h] = make_float4(v[0], v[1], v[2], v[3]);
                     }
                 }
             }
         }
     };
-    load_chunk(0);
+    // Fast path (interior of the problem: vectorisable strides, all of this thread's rows / columns in range, chunk fully
+    // inside K): running pointers and unpredicated 16-byte loads.  The generic lambda above cost ~2x the instructions of the
+    // arithmetic itself (ncu: 5600 warp instructions per CTA-chunk against ~2800 for load + exp + split + store).
+    const float* xp[XM];
+    bool xrow[XM];
+#pragma unroll
+    for (int m = 0; m < XM; ++m) {
+        const int row = i0 + rbase + RP * m;
+        xrow[m] = row < a.I;
+        xp[m] = xb + (int64_t)(xrow[m] ? row : 0) * a.xsi + kc * 4;
+    }
+    const float* yp = yb + (int64_t)(kq * 4) * a.ysk + j0 + jq * YC;
+    const bool thread_fast = x_vec && y_vec && (!has_y || j0 + jq * YC + YC <= a.J);
+    const int64_t ystep = a.ysk;
+    auto load_chunk_fast = [&](int c) {
+        const int k0 = c * LM_KC;
+#pragma unroll
+        for (int m = 0; m < XM; ++m)
+            prex[m] = xrow[m] ? __ldg(reinterpret_cast<const float4*>(xp[m] + k0)) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (has_y) {
+            const float* p = yp + (int64_t)k0 * ystep;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int h = 0; h < YV; ++h) prey[kk * YV + h] = __ldg(reinterpret_cast<const float4*>(p + kk * ystep + h * 4));
+        }
+    };
+    auto load_any = [&](int c) {
+        if (thread_fast && (c + 1) * LM_KC <= a.K) load_chunk_fast(c);
+        else load_chunk(c);
+    };
+    load_any(0);
 
     for (int c = 0; c < nchunks; ++c) {
         const int s = c % LM_STAGES;
@@ -241,13 +287,13 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
         if (!((a.mode & 1) && c >= LM_STAGES)) {
             // A operand: 16-byte k-chunk kc of row r at  r * 128 + ((kc ^ (r % 8)) * 16)
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int r = rbase + 32 * m;
+            for (int m = 0; m < XM; ++m) {
+                const int r = rbase + RP * m;
                 const float v[4] = {prex[m].x, prex[m].y, prex[m].z, prex[m].w};
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float e = __expf(v[q] - sxr[m]);
+                    const float e = lm_exp(v[q] - sxr[m]);
                     hi[q] = lm_tf32(e);
                     lo[q] = __float_as_uint(e - __uint_as_float(hi[q]));
                 }
@@ -258,25 +304,26 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
             // B operand (same layout with j in the role of the row): column j = 8 jq + q, chunk kq at j * 128 + ((kq ^ q) * 16);
             // the eight threads of a quarter warp differ in kq, i.e. hit eight different bank groups.
             if (has_y) {
-                unsigned char* Bh = stage + 2 * Cfg::A_OPB + jq * 1024;
+                unsigned char* Bh = stage + 2 * Cfg::A_OPB;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < YC; ++q) {
                     uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        const float4 pv = prey[kk * 2 + (q >> 2)];
+                        const float4 pv = prey[kk * YV + (q >> 2)];
                         const float raw = (q & 3) == 0 ? pv.x : (q & 3) == 1 ? pv.y : (q & 3) == 2 ? pv.z : pv.w;
-                        const float e = __expf(raw - syr[q]);
+                        const float e = lm_exp(raw - syr[q]);
                         hi[kk] = lm_tf32(e);
                         lo[kk] = __float_as_uint(e - __uint_as_float(hi[kk]));
                     }
-                    unsigned char* dst = Bh + q * 128 + ((kq ^ q) << 4);
+                    const int rr = jq * YC + q;  // row of the B tile = output column
+                    unsigned char* dst = Bh + rr * 128 + ((kq ^ (rr & 7)) << 4);
                     *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4*>(dst + Cfg::B_OPB) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
             }
         }
-        if (c + 1 < nchunks) load_chunk(c + 1);
+        if (c + 1 < nchunks) load_any(c + 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (warp == 0) {
@@ -306,13 +353,14 @@ __global__ void __launch_bounds__(256, 1) log_matmul_tc(LogMatmulArgs a) {
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
+        constexpr int CW = BN / (NTH / 128);  // columns per warp: the NTH / 32 warps are 4 lane quarters x NTH / 128 column ranges
         const int row = i0 + (warp & 3) * 32 + lane;
-        const int cbase = (warp >> 2) * (BN / 2);
+        const int cbase = (warp >> 2) * CW;
         const float sxo = row < a.I ? a.sx[n * a.I + row] : 0.f;
         float* orow = a.out + b0 * a.os0 + b1 * (int64_t)a.I * a.J + (int64_t)row * a.J;
         const bool vec_out = (a.J % 4 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 2; cc += 16) {
+        for (int cc = 0; cc < CW; cc += 16) {
             float d[16];
             {
                 // the correction accumulator first, then the hi*hi partial sums that were actually written
@@ -379,8 +427,9 @@ int launch_log_matmul_tc(const float* x, const int64_t* xs, const float* y, cons
         a.comp = (c && atoi(c) == 0) ? 0.f : 5.82e-8f;
     }
     // per call, not cached in a static: the attribute is per device and a process may drive more than one
-    FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<128>::SMEM));
-    FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<256>::SMEM));
+    FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<128, 3, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<128>::SMEM));
+    FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<256, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<256>::SMEM));
+    FB2_CUDA(cudaFuncSetAttribute(log_matmul_tc<256, 1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, LmCfg<256>::SMEM));
     // Tile choice: 128 x 256 (one hi*hi accumulator, 110 TFLOP/s) is the faster tile, 128 x 128 (three, 78 TFLOP/s) has a third
     // of the accumulation loss to compensate; measured rms error after compensation 5.5e-7 vs 2.9e-7 at K = 1024, so only
     // longer contractions take the 128-column tile.  FB2_LM_BN=128|256 forces one.
@@ -389,10 +438,12 @@ int launch_log_matmul_tc(const float* x, const int64_t* xs, const float* y, cons
     const bool wide = forced == 256 ? J > 128 : forced == 128 ? false : (J > 128 && K <= 1024);
     if (wide) {
         dim3 grid((unsigned)ceil_div(J, 256), (unsigned)ceil_div(I, LM_TILE), (unsigned)n);
-        log_matmul_tc<256, 1><<<grid, 256, LmCfg<256>::SMEM, stream>>>(a);
+        const char* th_env = getenv("FB2_LM_THREADS");  // A/B switch: 256 = eight staging warps
+        if (th_env && atoi(th_env) == 256) log_matmul_tc<256, 1, 256><<<grid, 256, LmCfg<256>::SMEM, stream>>>(a);
+        else log_matmul_tc<256, 1, 512><<<grid, 512, LmCfg<256>::SMEM, stream>>>(a);
     } else {
         dim3 grid((unsigned)ceil_div(J, 128), (unsigned)ceil_div(I, LM_TILE), (unsigned)n);
-        log_matmul_tc<128, 3><<<grid, 256, LmCfg<128>::SMEM, stream>>>(a);
+        log_matmul_tc<128, 3, 256><<<grid, 256, LmCfg<128>::SMEM, stream>>>(a);
     }
     FB2_LAUNCH_CHECK();
     return FB2_OK;
