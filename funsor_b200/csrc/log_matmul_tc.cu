@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(NTH, 1) log_matmul_tc(LogMatmulArgs a) {
                 }
             }
         }
-        if (c + 1 < nchunks) load_any(c + 1);
+        if (c + 1 < nchunks && !((a.mode & 8) && c >= 1)) load_any(c + 1);  // (mode 8: experiment, no operand loads after the second chunk)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (warp == 0) {
@@ -337,8 +337,10 @@ __global__ void __launch_bounds__(NTH, 1) log_matmul_tc(LogMatmulArgs a) {
                     const uint64_t dah = lm_desc(ah + ks * 32), dal = lm_desc(al + ks * 32);
                     const uint64_t dbh = lm_desc(bh + ks * 32), dbl = lm_desc(bl + ks * 32);
                     lm_mma(tmem + (uint32_t)(c % NMAIN) * BN, dah, dbh, IDESC, (c >= NMAIN || ks > 0) ? 1u : 0u);
-                    lm_mma(tmem + NMAIN * BN, dal, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
-                    lm_mma(tmem + NMAIN * BN, dah, dbl, IDESC, 1u);
+                    if (!(a.mode & 4)) {  // (mode 4: experiment, hi*hi products only)
+                        lm_mma(tmem + NMAIN * BN, dal, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                        lm_mma(tmem + NMAIN * BN, dah, dbl, IDESC, 1u);
+                    }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(lm_smem_u32(&s_bar[s])) : "memory");
                 if (c == nchunks - 1)
