@@ -317,19 +317,27 @@ def extra_measurements(device):
                                        "note": "algorithmic bytes per step: read y (O) + write/read w (D+O) + write eta (2D) + ~3x2D+6 for the eta sweeps of all levels"},
                           "note": "BASELINE config C4 at full size; the general (time-varying) scan runs gaussian_pair_combine_warp<32> at 3.6e7 pair contractions/s"}
     del y, kargs
-    # dense chain product (literal sequential_sum_product semantics), S=1024: tcgen05 3xTF32 log-matmul per level
-    Bd, Td, Sd = 4, 64, 1024
+    # dense chain product (literal sequential_sum_product semantics at the C2 state count): trans[16,256,1024,1024] = 17 GB,
+    # tcgen05 3xTF32 log-matmul per tree level
+    Bd, Td, Sd = 16, 256, 1024
     trans = torch.randn(Bd, Td, Sd, Sd, device=device, generator=g)
     sec = timeit(lambda: fb.sequential_sum_product("logaddexp", "add", trans), n=2)
     tf = 2.0 * Bd * (Td - 1) * Sd ** 3 / sec / 1e12
+    dense_bytes = 4.0 * Bd * Td * Sd * Sd
     out["dense_chain_log"] = {"pair_products_per_s": Bd * (Td - 1) / sec, "useful_tflops": tf, "B": Bd, "T": Td, "S": Sd, "ms": sec * 1e3,
+                              "units_per_s": Bd * Td * Sd * Sd / sec,
                               "kernel": "log_matmul_tc (tcgen05 kind::tf32, 3 products per useful flop)",
                               "roofline": {"bound": "tensor", "achieved": 3 * tf, "peak": peaks_tf32(), "unit": "TFLOP/s (tf32 issued)",
-                                           "frac": 3 * tf / peaks_tf32()}}
-    sec = timeit(lambda: fb.sequential_sum_product("max", "add", trans), n=1)
-    out["dense_chain_max"] = {"pair_products_per_s": Bd * (Td - 1) / sec, "fp32_tflops": 2.0 * Bd * (Td - 1) * Sd ** 3 / sec / 1e12,
-                              "ms": sec * 1e3, "kernel": "semiring_matmul_tiled<MAX> (CUDA cores: max-plus has no tensor-core form)"}
+                                           "frac": 3 * tf / peaks_tf32(),
+                                           "hbm": {"achieved_gbs": dense_bytes / sec / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                                                   "frac": dense_bytes / sec / 1e9 / peaks["hbm_gbs"],
+                                                   "note": "dense input read once; the matrix-chain product is tensor-bound at S=1024 (S/2 flop per byte)"}}}
+    trans_small = trans[:4, :64].contiguous()
     del trans
+    sec = timeit(lambda: fb.sequential_sum_product("max", "add", trans_small), n=1)
+    out["dense_chain_max"] = {"pair_products_per_s": 4 * 63 / sec, "fp32_tflops": 2.0 * 4 * 63 * Sd ** 3 / sec / 1e12, "B": 4, "T": 64, "S": Sd,
+                              "ms": sec * 1e3, "kernel": "semiring_matmul_tiled<MAX> (CUDA cores: max-plus has no tensor-core form)"}
+    del trans_small
     # Viterbi (C3 shape at reduced T): S=4096, B=1, bit-exact max-plus forward + back-pointers + backtrace
     Sv, Tv = 4096, 2048
     Av = torch.randn(Sv, Sv, device=device, generator=g)
