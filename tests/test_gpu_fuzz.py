@@ -1,0 +1,62 @@
+"""Randomised parity sweep over shapes (fixed seeds): every discrete entry point against the float64 / fp32 oracle at shapes
+chosen to cross the dispatch boundaries (small-S warp kernel <= 64 < dataflow kernels <= 512 < 1024 < streaming kernels;
+chain groups of 16; odd T; batched and time-varying transitions)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_close
+from oracle import semiring_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import funsor_b200 as fb
+
+    assert torch.cuda.is_available()
+    return fb
+
+
+def _case(seed):
+    rng = np.random.default_rng(seed)
+    S = int(rng.choice([3, 17, 64, 65, 100, 128, 129, 200, 256, 257, 384, 512, 513, 700, 1024, 1025, 1300]))
+    B = int(rng.choice([1, 2, 5, 16, 17, 33]))
+    T = int(rng.choice([1, 2, 3, 7, 31, 64, 65, 130]))
+    if S * S * T * B > 6e8:
+        T = max(1, int(6e8 // (S * S * B)))
+    amode = rng.choice(["shared", "shared", "shared", "batched", "timevarying"]) if S <= 200 else "shared"
+    shape = {"shared": (S, S), "batched": (B, S, S), "timevarying": (B, T, S, S)}[amode]
+    A = torch.tensor(rng.standard_normal(shape), dtype=torch.float32)
+    if rng.random() < 0.5:
+        A[..., rng.integers(0, S), :] = -float("inf")
+        A[..., rng.integers(0, S), rng.integers(0, S)] = 0.0  # keep every row alive somewhere
+    A = torch.log_softmax(torch.nan_to_num(A, neginf=-1e30), -1)
+    A = torch.where(A < -1e20, torch.full_like(A, -float("inf")), A)
+    init = torch.log_softmax(torch.tensor(rng.standard_normal((B, S)), dtype=torch.float32), -1)
+    obs = torch.tensor(rng.standard_normal((B, T, S)) * rng.choice([0.5, 1.0, 5.0]) + rng.choice([0.0, -30.0, 20.0]), dtype=torch.float32)
+    if rng.random() < 0.3:
+        obs[rng.integers(0, B), rng.integers(0, T), rng.integers(0, S)] = -float("inf")
+    return B, T, S, amode, init, A, obs
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_forward_viterbi_marginals(fb, seed):
+    B, T, S, amode, init, A, obs = _case(seed)
+    i64, A64, o64 = init.double().numpy(), A.double().numpy(), obs.double().numpy()
+    want = R.hmm_forward(R.LOG, i64, A64, o64)
+    got = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()).cpu().numpy()
+    rel_close(got, want, rtol=1e-5, atol=1.0)
+    # Viterbi: bit-exact value and path against the fp32 evaluation of the same recurrence
+    best, path = fb.hmm_viterbi(init.cuda(), A.cuda(), obs.cuda())
+    wbest, wpath = R.viterbi(init.numpy(), A.numpy(), obs.numpy())
+    assert np.array_equal(best.cpu().numpy(), wbest.astype(np.float32)), (B, T, S, amode)
+    assert np.array_equal(path.cpu().numpy(), wpath), (B, T, S, amode)
+    # posteriors: log-likelihood and normalisation of the marginals
+    logZ, gamma, _ = fb.hmm_marginals(init.cuda(), A.cuda(), obs.cuda(), want_xi=False)
+    rel_close(logZ.cpu().numpy(), want, rtol=1e-5, atol=1.0)
+    live = np.isfinite(want)
+    if live.any():
+        tot = np.exp(gamma.cpu().numpy().astype(np.float64)).sum(-1)[live]
+        assert np.abs(tot - 1).max() < 2e-3, (B, T, S, amode, np.abs(tot - 1).max())
