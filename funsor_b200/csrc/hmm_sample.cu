@@ -54,10 +54,19 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) hmm_backward_sample(SampleA
     const int S = a.S;
     const float* u = a.u + (b * a.N + n) * (a.T + 1);
     int64_t* path = a.paths + (b * a.N + n) * (a.T + 1);
-    double score = 0.0;
+    bool dead = false;
     int z = -1;  // state already drawn at path index t + 1
+    float u_next = u[a.T];
     for (int64_t t = a.T; t >= 0; --t) {
         const float* base = t > 0 ? a.alpha + (b * a.T + (t - 1)) * S : (a.init ? a.init + b * a.init_sb : nullptr);
+        const float ut = u_next;
+        if (t > 0) {
+            u_next = u[t - 1];
+            // the alpha row of the NEXT draw does not depend on this one: pull its lines towards the SM now (one 128-byte line per lane)
+            const float* nb = t > 1 ? a.alpha + (b * a.T + (t - 2)) * S : (a.init ? a.init + b * a.init_sb : nullptr);
+            if (nb)
+                for (int off = lane * 32; off < S; off += 32 * 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(nb + off));
+        }
         // column z of the transition used between path[t] and path[t+1] (time index t)
         const float* col = nullptr;
         int64_t col_stride = 1;
@@ -87,7 +96,7 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) hmm_backward_sample(SampleA
             }
             tot = warp_sum(tot);
             __syncwarp();
-            const float target = u[t] * tot;
+            const float target = ut * tot;
             float run = 0.f;
             int found = -1, last_pos = 0;
             for (int i0 = 0; i0 < S && found < 0; i0 += 32) {
@@ -108,16 +117,24 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) hmm_backward_sample(SampleA
             }
             chosen = found >= 0 ? found : last_pos;  // rounding left the target above the final running sum
         } else {
-            score = -INFINITY;  // no path has positive mass
+            dead = true;  // no path has positive mass
         }
         __syncwarp();
-        if (lane == 0) {
-            path[t] = chosen;
-            if (z >= 0) score += (double)a.A[b * a.a_sb + t * a.a_st + (int64_t)chosen * S + z] + (double)a.obs[(b * a.T + t) * S + z];
-            if (t == 0 && a.init) score += (double)a.init[b * a.init_sb + chosen];
-        }
+        if (lane == 0) path[t] = chosen;
         z = chosen;
     }
+    // score of the drawn path, after the fact and in parallel over t (the gathers would otherwise sit on every step's critical
+    // path): init[z0] + sum_t A_t[z_t, z_{t+1}] + obs[t, z_{t+1}]
+    __syncwarp();
+    double score = 0.0;
+    for (int64_t t = lane; t < a.T; t += 32) {
+        const int64_t z0 = path[t], z1 = path[t + 1];
+        score += (double)a.A[b * a.a_sb + t * a.a_st + z0 * S + z1] + (double)a.obs[(b * a.T + t) * S + z1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) score += __shfl_xor_sync(0xffffffffu, score, o);
+    if (a.init) score += (double)a.init[b * a.init_sb + path[0]];
+    if (dead) score = -INFINITY;
     if (lane == 0) a.score[b * a.N + n] = score;
 }
 
