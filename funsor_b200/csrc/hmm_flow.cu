@@ -282,14 +282,20 @@ __device__ __forceinline__ float flow_finish1(float s, const FlowObs1& o, int e_
 // conversion) to halve its register footprint; the 2^-24 is applied to the accumulator.
 constexpr float kScalePl = 16777216.f, kUnscalePl = 1.f / 16777216.f;
 
-template <int K16, int NT>
+// CL = CTAs per cluster: 8 (each warp contracts the whole K-slice for its n-tile(s)) or 4 ("half-K": the K-slice is twice as
+// long, a cluster owns 32 columns, warp w contracts n-tile w & 3 over K-half w >> 2, so a warp issues half the MMAs and a CTA
+// ships 1.5 KB instead of 7 KB of partials per step; 2 x 4 = 8 partial sources per column group either way).
+template <int K16, int NT, int CL = 8>
 __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) {
-    constexpr int KS = K16 * 16;          // rows of P (= message entries) per CTA
+    constexpr bool HALFK = CL == 4;
     constexpr int SP = K16 * 128;         // padded state count
-    constexpr int NG = 2 * K16;           // producer groups (8 columns each) in this CTA's K-slice
+    constexpr int KS = SP / CL;           // rows of P (= message entries) per CTA
+    constexpr int NG = KS / 8;            // producer groups (8 columns each) in this CTA's K-slice
+    constexpr int NKS = HALFK ? NG / 2 : NG;  // k8-steps contracted by one warp
     constexpr int NA = 8 * NG;            // threads that fetch packets: (chain pair ga, producer group pa)
-    constexpr int NCC = 2 * K16 / NT;     // clusters per chain-group set
-    constexpr int CW = 64 * NT;           // columns owned by a cluster
+    constexpr int CW = CL * 8 * NT;       // columns owned by a cluster
+    constexpr int NCC = SP / CW;          // clusters per chain-group set
+    static_assert(CL == 8 || (CL == 4 && NT == 1), "cluster of 8, or cluster of 4 with one n-tile per warp");
     constexpr int ROWB = 1024 + 16;       // bytes per k8-step row of A fragments: 32 lanes x (16 B hi + 16 B lo) + pad
     constexpr int C0 = FLOW_THREADS - 128 * NT;  // first final-owner thread
     static_assert(K16 >= 1 && K16 <= 16 && (K16 & (K16 - 1)) == 0, "K16 must be a power of two in [1,16]");
@@ -307,9 +313,12 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
     const int rank = (int)cluster_ctarank();
-    const int cid = blockIdx.x / FLOW_CLUSTER;
+    const int cid = blockIdx.x / CL;
     const int set = cid / NCC, cc = cid % NCC;
     const int S = p.S;
+    const int khalf = HALFK ? warp >> 2 : 0;            // which half of the K-slice this warp contracts
+    const int wtile = HALFK ? (warp & 3) : warp;        // n-tile of this warp = cluster rank that finally owns its columns
+    const int src_slot = HALFK ? rank * 2 + khalf : rank;  // this warp's slot among the 8 partial sources of a column group
 
     // bytes one step delivers into this CTA: 8 source CTAs x (NT tiles x 16 chains x 8 columns fp32 + 16 exponents)
     constexpr uint32_t TX_BYTES = FLOW_CLUSTER * (NT * FLOW_CHAINS * 8 * 4 + FLOW_CHAINS * 4);
@@ -324,17 +333,17 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
 
     // ---- resident operand: B fragments of P[k, col] = exp(A[k, col] - cA[col]); k-permutation inside a
     //      k8-step: fragment slot (tig, h) holds k = 2*tig + h
-    uint32_t Ph[NT][NG][2], Pl[NT][NG];
+    uint32_t Ph[NT][NKS][2], Pl[NT][NKS];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-        const int col = cc * CW + nt * 64 + warp * 8 + g;
+        const int col = cc * CW + (HALFK ? 0 : nt * 64) + wtile * 8 + g;
         const float ca = col < S ? p.cA[col] : 0.f;
 #pragma unroll
-        for (int ks = 0; ks < NG; ++ks) {
+        for (int ks = 0; ks < NKS; ++ks) {
             float lo2[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int k = rank * KS + ks * 8 + 2 * tig + h;
+                const int k = rank * KS + (khalf * NKS + ks) * 8 + 2 * tig + h;
                 float v = 0.f;
                 if (k < S && col < S) v = expf((p.transpose ? p.A[(int64_t)col * S + k] : p.A[(int64_t)k * S + col]) - ca);
                 const uint32_t hi = cvt_tf32(v);
@@ -356,9 +365,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
     const float caC = (tc >= 0 && colC < S) ? p.cA[colC] : 0.f;
     const uint32_t bar_addr0 = smem_u32(&s_bar[0]);
     // remote addresses for the reduce-scatter: warp w sends its partials to cluster rank w
-    const uint32_t r_part = mapa_u32(smem_u32(&s_part[0][rank][0][0][0]), (uint32_t)warp);
-    const uint32_t r_eref = mapa_u32(smem_u32(&s_eref[0][rank][0]), (uint32_t)warp);
-    const uint32_t r_bar0 = mapa_u32(bar_addr0, (uint32_t)warp);
+    const uint32_t r_part = mapa_u32(smem_u32(&s_part[0][src_slot][0][0][0]), (uint32_t)wtile);
+    const uint32_t r_eref = mapa_u32(smem_u32(&s_eref[0][src_slot][0]), (uint32_t)wtile);
+    const uint32_t r_bar0 = mapa_u32(bar_addr0, (uint32_t)wtile);
 
     cluster_sync_all();  // barriers initialised cluster-wide before any remote arrive
 
@@ -518,8 +527,8 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                         for (int c = 0; c < 4; ++c) acc[nt][q][c] = 0.f;
                 const int swz = ((lane >> 2) & 1) * 16;
 #pragma unroll
-                for (int ks = 0; ks < NG; ++ks) {
-                    const unsigned char* rowp = &s_frag[buf][ks][0] + lane * 32;
+                for (int ks = 0; ks < NKS; ++ks) {
+                    const unsigned char* rowp = &s_frag[buf][khalf * NKS + ks][0] + lane * 32;
                     const uint4 fh = *reinterpret_cast<const uint4*>(rowp + swz);
                     const uint4 fl = *reinterpret_cast<const uint4*>(rowp + (16 ^ swz));
                     const uint32_t ah[4] = {fh.x, fh.y, fh.z, fh.w};
@@ -1784,35 +1793,35 @@ size_t hmm_flow_workspace_bytes(int64_t B, int S) {
            align_up(groups * FLOW_CHAINS * (Sp / 8) * 4) + align_up(32) + align_up((size_t)FLOW_PROF_CTAS * 64) + 256;
 }
 
-template <int K16, int NT>
+template <int K16, int NT, int CL = 8>
 static int flow_launch(FlowArgs& a, cudaStream_t stream) {
-    auto kernel = hmm_flow_forward<K16, NT>;
-    constexpr int NCC = 2 * K16 / NT;
+    auto kernel = hmm_flow_forward<K16, NT, CL>;
+    constexpr int NCC = K16 * 128 / (CL * 8 * NT);
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(FLOW_THREADS);
-    cfg.dynamicSmemBytes = (size_t)2 * (2 * K16) * (1024 + 16);
+    cfg.dynamicSmemBytes = (size_t)2 * (K16 * 128 / CL / 8) * (1024 + 16);
     FB2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
     cfg.stream = stream;
     cudaLaunchAttribute attrs[1];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = FLOW_CLUSTER;
+    attrs[0].val.clusterDim.x = CL;
     attrs[0].val.clusterDim.y = 1;
     attrs[0].val.clusterDim.z = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
     // how many clusters of 8 can be co-resident?  (the CTAs of one set wait on each other)
-    cfg.gridDim = dim3(FLOW_CLUSTER * NCC);
+    cfg.gridDim = dim3(CL * NCC);
     int max_clusters = 0;
     FB2_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
     int nsets = max_clusters / NCC;
     if (nsets > FLOW_MAX_SETS) nsets = FLOW_MAX_SETS;
     if (nsets > a.groups_total) nsets = a.groups_total;
     if (nsets < 1) {
-        set_error("hmm flow: only %d clusters of %d CTAs can be co-resident, %d needed", max_clusters, FLOW_CLUSTER, NCC);
+        set_error("hmm flow: only %d clusters of %d CTAs can be co-resident, %d needed", max_clusters, CL, NCC);
         return FB2_ERR_UNSUPPORTED;
     }
     a.nsets = nsets;
-    cfg.gridDim = dim3(FLOW_CLUSTER * NCC * nsets);
+    cfg.gridDim = dim3(CL * NCC * nsets);
     // Plain cluster launch.  The occupancy query above proves that every cluster of the grid can be resident at
     // once, which is what the inter-CTA waits need.  cudaLaunchAttributeCooperative is deliberately NOT added:
     // measured on B200 / driver 580, a cooperative + cluster launch is not co-scheduled under ncu / CUPTI kernel
@@ -1979,7 +1988,10 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
         if (fs.k16 == 1) st = wide ? flow_launch<1, 2>(a, stream) : flow_launch<1, 1>(a, stream);
         else if (fs.k16 == 2) st = wide ? flow_launch<2, 2>(a, stream) : flow_launch<2, 1>(a, stream);
         else if (fs.k16 == 4) st = wide ? flow_launch<4, 2>(a, stream) : flow_launch<4, 1>(a, stream);
-        else st = flow_launch<8, 2>(a, stream);
+        else {
+            const char* cl4 = getenv("FB2_FLOW_CL4");  // experiment: clusters of 4 with half-K warps
+            st = (cl4 && cl4[0] == '1') ? flow_launch<8, 1, 4>(a, stream) : flow_launch<8, 2>(a, stream);
+        }
     }
     if (st != FB2_OK) return st;
     if (rows_out) {  // chunk summary: the final messages themselves, as rows relative to a float64 offset

@@ -936,3 +936,23 @@ def test_hmm_marginals_large_state_space_on_stream_kernels(fb, B, T, S):
     assert np.abs(np.exp(g).sum(-1) - 1).max() < 1e-4
     if xi is not None:
         assert np.abs(host(xi) - wxi).max() < 1e-3 * max(1.0, np.abs(wxi).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,S", [(16, 40, 1024), (3, 33, 700), (33, 9, 1000)])
+def test_hmm_forward_two_hop_clusters_of_four(fb, B, T, S):
+    """The experimental cluster-of-4 / half-K variant of the two-hop kernel (FB2_FLOW_CL4=1) must agree with the oracle too."""
+    import os
+
+    init, A, obs = _flow_case(B, T, S, seed=91)
+    os.environ["FB2_FLOW_CL4"] = "1"
+    os.environ["FB2_FLOW_DIRECT"] = "0"
+    try:
+        got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+        z2, alpha = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda(), return_alpha=True)
+    finally:
+        os.environ.pop("FB2_FLOW_CL4")
+        os.environ.pop("FB2_FLOW_DIRECT")
+    want, walpha = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy(), want_alpha=True)
+    rel_close(got, want, rtol=RTOL, atol=1.0)
+    rel_close(host(alpha), walpha, rtol=RTOL, atol=max(1.0, T / 10))
