@@ -227,8 +227,10 @@ __global__ void __launch_bounds__(256) hmm_forward_generic(HmmArgs p) {
                     }
                 }
                 __syncthreads();
-                if (tid < R * LW) {
-                    const int r = tid / LW, l = tid % LW;
+                // (R * LW can exceed the 256 threads -- 16 chains x 32 columns when many groups share the GPU -- hence the loop:
+                //  a plain `if (tid < R * LW)` left chains 8..15 of every group without a result for S * B > ~38000)
+                for (int fin = tid; fin < R * LW; fin += 256) {
+                    const int r = fin / LW, l = fin % LW;
                     const int col = c0 + l;
                     if (r < nb && col < jw) {
                         const int64_t b = b0 + r;

@@ -956,3 +956,28 @@ def test_hmm_forward_two_hop_clusters_of_four(fb, B, T, S):
     want, walpha = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy(), want_alpha=True)
     rel_close(got, want, rtol=RTOL, atol=1.0)
     rel_close(host(alpha), walpha, rtol=RTOL, atol=max(1.0, T / 10))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,S,amode", [(256, 12, 200, "shared"), (320, 8, 130, "batched"), (200, 6, 260, "batched"), (100, 5, 600, "batched")])
+def test_generic_kernel_many_groups_wide_slices(fb, B, T, S, amode):
+    """Generic cooperative kernel with 16 chains per group AND more than 16 columns per CTA (S * B > ~38000): the per-column
+    finalisation has to cover 16 x 32 (chain, column) pairs with 256 threads.  (A plain `if (tid < R * LW)` left half of the
+    chains of every group without results; found by the dispatch-boundary scan, scripts/cliff_time.py.)"""
+    rng = np.random.default_rng(B + S)
+    init = torch.log_softmax(torch.tensor(rng.standard_normal((B, S)), dtype=torch.float32), -1)
+    shape = (S, S) if amode == "shared" else (B, S, S)
+    A = torch.log_softmax(torch.tensor(rng.standard_normal(shape), dtype=torch.float32), -1)
+    obs = torch.tensor(rng.standard_normal((B, T, S)), dtype=torch.float32)
+    best, path = fb.hmm_viterbi(init.cuda(), A.cuda(), obs.cuda())
+    wbest, wpath = R.viterbi(init.numpy(), A.numpy(), obs.numpy())
+    assert np.array_equal(path.cpu().numpy(), wpath)
+    assert np.array_equal(best.cpu().numpy(), wbest.astype(np.float32))
+    if amode == "batched":  # per-chain transition matrices: the log-semiring forward runs on the generic kernel as well
+        want, walpha = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy(), want_alpha=True)
+        z, alpha = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda(), return_alpha=True)
+        rel_close(host(z), want, rtol=RTOL, atol=1.0)
+        rel_close(host(alpha), walpha, rtol=RTOL, atol=1.0)
+        zm, gamma, _ = fb.hmm_marginals(init.cuda(), A.cuda(), obs.cuda(), want_xi=False)
+        rel_close(host(zm), want, rtol=RTOL, atol=1.0)
+        assert np.abs(np.exp(host(gamma)).sum(-1) - 1).max() < 1e-3
