@@ -449,8 +449,8 @@ __global__ void __launch_bounds__(STREAM_THREADS) hmm_maxplus_stream(HmmArgs p) 
                     s_arg[(warp * R + r) * 32 + lane] = arg[r];
                 }
                 __syncthreads();
-                if (tid < R * 32) {
-                    const int r = tid >> 5, l = tid & 31, c = tile * 32 + l;
+                for (int fin = tid; fin < R * 32; fin += NTH) {  // R * 32 may exceed the thread count (R = 16)
+                    const int r = fin >> 5, l = fin & 31, c = tile * 32 + l;
                     if (r < nb && c < S) {
                         float bb = kNegInf;
                         int aa = 0x7fffffff;
@@ -891,8 +891,8 @@ __global__ void __launch_bounds__(STREAM_THREADS) hmm_logsum_stream(HmmArgs p, c
 #pragma unroll
                 for (int r = 0; r < R; ++r) s_part[(warp * R + r) * 32 + lane] = acc[r];
                 __syncthreads();
-                if (tid < R * 32) {
-                    const int r = tid >> 5, l = tid & 31, c = tile * 32 + l;
+                for (int fin = tid; fin < R * 32; fin += NTH) {  // R * 32 may exceed the thread count (R = 16)
+                    const int r = fin >> 5, l = fin & 31, c = tile * 32 + l;
                     if (r < nb && c < S) {
                         float sum = 0.f;
                         for (int w = 0; w < NW; ++w) sum += s_part[(w * R + r) * 32 + l];
@@ -969,8 +969,11 @@ static int log_stream_pass(const float* init, int64_t init_sb, const float* A, c
     float* strips = arena.take<float>(strip_elems);
     float* cA = arena.take<float>((size_t)S);
     float* out_scratch = arena.take<float>((size_t)B);
-    const int R = B >= 4 ? 4 : 1;
-    size_t smem = ((((size_t)R * S + 3) & ~(size_t)3) + STREAM_WARPS * R * 32) * 4;
+    // chains per pass: the strips are re-read for every pass, so as many chains as shared memory (R * S staged entries) allows
+    int R = B >= 16 ? 16 : (B >= 4 ? 4 : 1);
+    auto stream_smem = [&](int r) { return ((((size_t)r * S + 3) & ~(size_t)3) + STREAM_WARPS * r * 32) * 4; };
+    if (R == 16 && stream_smem(16) > 96 * 1024) R = 4;
+    size_t smem = stream_smem(R);
     if (!arena.ok() || smem > g_smem_optin) return FB2_ERR_UNSUPPORTED;
     FB2_CUDA(cudaMemsetAsync(ctr, 0, 1024 * sizeof(unsigned), stream));
     stream_colmax<<<(unsigned)ceil_div(S, 128), 128, 0, stream>>>(A, S, cA, reverse);
@@ -993,7 +996,8 @@ static int log_stream_pass(const float* init, int64_t init_sb, const float* A, c
     smem += (size_t)keep * 128;
     const float* cAc = cA;
     void* args[] = {&a, &cAc};
-    const void* fn = R == 4 ? reinterpret_cast<const void*>(hmm_logsum_stream<4>) : reinterpret_cast<const void*>(hmm_logsum_stream<1>);
+    const void* fn = R == 16 ? reinterpret_cast<const void*>(hmm_logsum_stream<16>)
+                             : (R == 4 ? reinterpret_cast<const void*>(hmm_logsum_stream<4>) : reinterpret_cast<const void*>(hmm_logsum_stream<1>));
     FB2_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(STREAM_THREADS), args, smem, stream);
     if (e != cudaSuccess) {
@@ -1038,8 +1042,10 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
         HmmArgs a{};
         a.init = init; a.init_sb = init_sb; a.A = strips; a.obs = obs; a.B = B; a.T = T; a.S = S; a.vec = vec; a.counters = ctr;
         a.alpha_all = alpha_all; a.backptr = backptr; a.out = out; a.last = last;
-        const int R = B >= 4 ? 4 : 1;
-        size_t smem = ((((size_t)R * S + 3) & ~(size_t)3) + 2 * STREAM_WARPS * R * 32) * 4;
+        int R = B >= 16 ? 16 : (B >= 4 ? 4 : 1);  // chains per pass (A is re-read for every pass)
+        auto mp_smem = [&](int r) { return ((((size_t)r * S + 3) & ~(size_t)3) + 2 * STREAM_WARPS * r * 32) * 4; };
+        if (R == 16 && mp_smem(16) > 96 * 1024) R = 4;
+        size_t smem = mp_smem(R);
         if (smem <= g_smem_optin) {
             int ntiles = (S + 31) / 32;
             int grid = ntiles < g_sm_count ? ntiles : g_sm_count;
@@ -1055,6 +1061,9 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
             PassPlan sp{};
             sp.grid = grid;
             sp.smem = smem;
+            if (R == 16)
+                return backptr ? coop_launch(hmm_maxplus_stream<16, true>, sp, a, stream, STREAM_THREADS)
+                               : coop_launch(hmm_maxplus_stream<16, false>, sp, a, stream, STREAM_THREADS);
             if (R == 4)
                 return backptr ? coop_launch(hmm_maxplus_stream<4, true>, sp, a, stream, STREAM_THREADS)
                                : coop_launch(hmm_maxplus_stream<4, false>, sp, a, stream, STREAM_THREADS);
