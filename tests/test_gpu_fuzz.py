@@ -60,3 +60,38 @@ def test_fuzz_forward_viterbi_marginals(fb, seed):
     if live.any():
         tot = np.exp(gamma.cpu().numpy().astype(np.float64)).sum(-1)[live]
         assert np.abs(tot - 1).max() < 2e-3, (B, T, S, amode, np.abs(tot - 1).max())
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_gaussian_chain(seed):
+    """Random (B, T, D): general scan and homogeneous operator path against each other and against the float64 oracle."""
+    import funsor_b200.gaussian as fg
+    from oracle import gaussian_ref as G
+
+    rng = np.random.default_rng(1000 + seed)
+    D = int(rng.choice([1, 2, 3, 4, 5, 8, 9, 16, 17, 32]))
+    O = int(rng.integers(max(1, D // 2), D + 1))
+    B = int(rng.choice([1, 2, 7, 64, 300]))
+    T = int(rng.choice([1, 2, 3, 4, 5, 9, 33, 64, 100, 257]))
+    if B * T * D * D > 4e6:
+        B = max(1, int(4e6 // (T * D * D)))
+    F = 0.9 * np.linalg.qr(rng.standard_normal((B, D, D)))[0]
+    H = rng.standard_normal((B, D, O)) / np.sqrt(D)
+
+    def spd_tril(n):
+        a = rng.standard_normal((B, n, n))
+        return np.linalg.cholesky(a @ a.transpose(0, 2, 1) / n + 0.5 * np.eye(n))
+
+    args = (F, 0.1 * rng.standard_normal((B, D)), spd_tril(D), H, 0.1 * rng.standard_normal((B, O)), spd_tril(O), rng.standard_normal((B, T, O)))
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()  # noqa: E731
+    dargs = [dev(a) for a in args]
+    want = G.chain_info(*G.kalman_elements_info(*args), D)
+    homog = fg.kalman_chain(*dargs)
+    w, P, s = fg.kalman_elements_sqrt(*dargs)
+    general = fg.gaussian_sequential_sum_product(*fg.sqrt_to_info(w, P, s))
+    for got in (homog, general):
+        for a, b in zip(got, want):
+            a = a.cpu().numpy().astype(np.float64)
+            scale = max(np.abs(b).max(), 1.0)
+            tol = 1e-5 * scale * (T * D if a.ndim == 1 else 1)  # the scalar sums T terms of magnitude ~D
+            assert np.abs(a - b).max() <= max(tol, 2e-5 * scale), (B, T, D, O, np.abs(a - b).max(), scale)
