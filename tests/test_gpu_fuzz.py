@@ -95,3 +95,42 @@ def test_fuzz_gaussian_chain(seed):
             scale = max(np.abs(b).max(), 1.0)
             tol = 1e-5 * scale * (T * D if a.ndim == 1 else 1)  # the scalar sums T terms of magnitude ~D
             assert np.abs(a - b).max() <= max(tol, 2e-5 * scale), (B, T, D, O, np.abs(a - b).max(), scale)
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_fuzz_dense_products(fb, seed):
+    """Random shapes for the dense operators: pair products (incl. strided even/odd time views, the tcgen05 size classes and
+    their edges) and whole chain products (fused tail, level-by-level, tensor-core levels), both semirings."""
+    rng = np.random.default_rng(2000 + seed)
+    # pair product on even/odd views of a [B, T, I, K] / [B, T, K, J] pair
+    B, T = int(rng.integers(1, 4)), int(rng.integers(2, 7))
+    I, K, J = (int(rng.choice([1, 5, 31, 32, 63, 64, 65, 127, 128, 129, 200, 257])) for _ in range(3))
+    x = torch.tensor(rng.standard_normal((B, T, I, K)) * 3, dtype=torch.float32)
+    y = torch.tensor(rng.standard_normal((B, T, K, J)) * 3, dtype=torch.float32)
+    if rng.random() < 0.4:
+        x[:, :, rng.integers(0, I), :] = -float("inf")
+        y[:, :, :, rng.integers(0, J)] = -float("inf")
+    xv, yv = x[:, 0::2][:, : T // 2], y[:, 1::2][:, : T // 2]
+    for op, sem in (("logaddexp", R.LOG), ("max", R.MAX)):
+        got = fb.semiring_matmul(op, "add", xv.cuda(), yv.cuda()).cpu().numpy()
+        want = R.pair_product(sem, xv.double().numpy(), yv.double().numpy())
+        if op == "max":
+            want32 = R.pair_product(sem, xv.numpy(), yv.numpy())
+            assert np.array_equal(got, want32.astype(np.float32)), (B, T, I, K, J)
+        else:
+            rel_close(got, want, rtol=1e-5, atol=1.0)
+    # chain product
+    S = int(rng.choice([2, 3, 7, 16, 33, 64, 96, 130, 200]))
+    Tc = int(rng.choice([1, 2, 3, 5, 8, 13, 31, 64, 100, 257]))
+    Bc = int(rng.choice([1, 2, 5]))
+    if Bc * Tc * S ** 3 > 3e9:
+        Tc = max(1, int(3e9 // (Bc * S ** 3)))
+    trans = torch.tensor(rng.standard_normal((Bc, Tc, S, S)), dtype=torch.float32)
+    for op, sem in (("logaddexp", R.LOG), ("max", R.MAX)):
+        got = fb.sequential_sum_product(op, "add", trans.cuda()).cpu().numpy()
+        if op == "max":
+            want32 = R.chain_product(sem, trans.numpy())
+            assert np.array_equal(got, want32.astype(np.float32)), (Bc, Tc, S)
+        else:
+            want = R.chain_product(sem, trans.double().numpy())
+            rel_close(got, want, rtol=1e-5, atol=1.0)
