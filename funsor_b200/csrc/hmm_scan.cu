@@ -35,7 +35,8 @@ int hmm_flow_summary_device(const float* A, const float* obs, int64_t B, int64_t
 // hmm_small.cu
 bool hmm_small_supported(int semiring, int64_t a_st, int S);
 int hmm_small_forward_device(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb, const float* obs, int64_t B,
-                             int64_t T, int S, float* logZ, float* alpha_all, int32_t* backptr, int32_t* last, cudaStream_t stream);
+                             int64_t T, int S, float* logZ, float* alpha_all, int32_t* backptr, int32_t* last, cudaStream_t stream,
+                             double* ell_all = nullptr, double* logZ_d = nullptr, int64_t obs_T = 0, int transpose = 0, int reverse = 0);
 // FB2_DISABLE_FLOW=1 forces the generic kernel (A/B testing of the two GPU paths)
 static bool stream_disabled() {
     const char* e = getenv("FB2_DISABLE_STREAM");
@@ -1228,6 +1229,28 @@ extern "C" int fb2_hmm_marginals_f32(const float* init, int64_t init_sb, const f
     }
     char* rest = static_cast<char*>(workspace) + arena.used;
     size_t rest_bytes = workspace_bytes - arena.used;
+    // small state spaces: both recursions on the warp-per-chain kernel (backward = forward on A^T over reversed rows)
+    if (hmm_small_supported(FB2_SEMIRING_LOG, a_st, S) && !flow_disabled()) {
+        st = hmm_small_forward_device(FB2_SEMIRING_LOG, init, init_sb, A, a_sb, obs, B, T, S, logZ, gamma, nullptr, nullptr, stream, ell_a, z_d);
+        if (st != FB2_OK) return st;
+        if (T >= 2) {
+            st = hmm_small_forward_device(FB2_SEMIRING_LOG, obs + (T - 1) * (int64_t)S, T * (int64_t)S, A, a_sb, obs, B, T - 1, S, nullptr, beta,
+                                          nullptr, nullptr, stream, ell_b, nullptr, T, 1, 1);
+            if (st != FB2_OK) return st;
+        }
+        stream_fill_last_row<<<(unsigned)ceil_div(B * (int64_t)S, 256), 256, 0, stream>>>(beta, ell_b, B, T, S);
+        FB2_LAUNCH_CHECK();
+        if (xi_sum) {
+            const int64_t nx = B * (int64_t)S * S;
+            xi_sum_kernel<<<(unsigned)ceil_div(nx, 256), 256, 0, stream>>>(init, init_sb, A, a_sb, a_st, obs, gamma, beta, ell_a, ell_b, z_d, B, T, S,
+                                                                         xi_sum);
+            FB2_LAUNCH_CHECK();
+        }
+        const int64_t ng = B * T * (int64_t)S;
+        marginals_combine<<<(unsigned)ceil_div(ng, 256), 256, 0, stream>>>(gamma, beta, ell_a, ell_b, z_d, B, T, S);
+        FB2_LAUNCH_CHECK();
+        return FB2_OK;
+    }
     // normalised alpha goes straight into gamma, then gamma = alpha + beta + offsets - logZ in place
     st = hmm_forward_device(FB2_SEMIRING_LOG, init, init_sb, A, a_sb, a_st, obs, nullptr, B, T, S, logZ, gamma, nullptr,
                             nullptr, rest, rest_bytes, stream, 1, nullptr, ell_a, z_d);

@@ -22,8 +22,15 @@ struct SmallArgs {
     const float* obs;   // nullable
     int64_t B, T;
     int S;
-    float* logZ;
-    float* alpha_all;   // nullable [B,T,S]
+    float* logZ;        // nullable
+    float* alpha_all;   // nullable [B,OT,S]
+    // forward-backward support: with ell_all the messages are written NORMALISED (log of the mantissa) and their offsets go to
+    // ell_all[B,OT]; reverse = 1 runs the backward recursion as a forward pass on A^T (transpose = 1) over rows T-1 .. 0 and
+    // writes beta_hat (the contraction WITHOUT the row's observation) with the offset of the incoming message
+    double* ell_all;
+    double* logZ_d;     // nullable
+    int64_t obs_T;      // rows per chain of obs / alpha_all / ell_all (0 = T)
+    int transpose, reverse;
 };
 
 // NJ = columns per lane: 1 (S <= 32) or 2 (S <= 64); NL = source lanes visited per column block (8, 16 or 32 >= S when NJ == 1).
@@ -48,14 +55,14 @@ __global__ void __launch_bounds__(SM_WARPS * 32) hmm_small_forward(SmallArgs p) 
         for (int j = t0; j < SP; j += nthreads) {
             float m = -FLT_MAX;
             if (j < S)
-                for (int i = 0; i < S; ++i) m = fmaxf(m, Ab[(int64_t)i * S + j]);
+                for (int i = 0; i < S; ++i) m = fmaxf(m, p.transpose ? Ab[(int64_t)j * S + i] : Ab[(int64_t)i * S + j]);
             sCA[j] = j < S ? m : 0.f;
         }
         if (shared_A) __syncthreads();
         else __syncwarp();
         for (int idx = t0; idx < SP * SP; idx += nthreads) {
             const int i = idx / SP, j = idx % SP;
-            sP[idx] = (i < S && j < S) ? expf(Ab[(int64_t)i * S + j] - sCA[j]) : 0.f;
+            sP[idx] = (i < S && j < S) ? expf((p.transpose ? Ab[(int64_t)j * S + i] : Ab[(int64_t)i * S + j]) - sCA[j]) : 0.f;
         }
         if (shared_A) __syncthreads();
         else __syncwarp();
@@ -64,7 +71,9 @@ __global__ void __launch_bounds__(SM_WARPS * 32) hmm_small_forward(SmallArgs p) 
 
     float ca[NJ], v[NJ];
     long long E = 0;  // alpha_t[j] = ln2 * E + log v[j]
-    const float* obs_b = p.obs ? p.obs + b * p.T * S : nullptr;
+    const int64_t OT = p.obs_T ? p.obs_T : p.T;
+    const float* obs_b = p.obs ? p.obs + b * OT * S : nullptr;
+    auto row_of = [&](int64_t t) { return p.reverse ? (p.T - 1 - t) : t; };
     // normalise the lane values x (log2 domain) into v = 2^(x - n), n = ceil(max x); returns n (0 if everything is -inf)
     auto renorm_pow2 = [&](float (&val)[NJ]) -> int {  // scale the warp's message by 2^-q so that its max lies in [1, 2)
         float m = val[0];
@@ -110,7 +119,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) hmm_small_forward(SmallArgs p) 
 #pragma unroll
             for (int q = 0; q < NJ; ++q) {
                 const int j = lane + 32 * q;
-                ob_next[u][q] = (obs_b && t0 + u < p.T && j < S) ? __ldg(obs_b + (t0 + u) * S + j) : 0.f;
+                ob_next[u][q] = (obs_b && t0 + u < p.T && j < S) ? __ldg(obs_b + row_of(t0 + u) * S + j) : 0.f;
             }
     };
     load_block(0);
@@ -151,14 +160,27 @@ __global__ void __launch_bounds__(SM_WARPS * 32) hmm_small_forward(SmallArgs p) 
             const float nf = xm > -1e30f ? ceilf(xm) : 0.f;
 #pragma unroll
             for (int q = 0; q < NJ; ++q) v[q] = (acc[q][0] + acc[q][1]) * (xm > -1e30f ? exp2f(x[q] - nf) : 0.f);
+            const long long E_in = E;
             E += (long long)nf + renorm_pow2(v);
             if (p.alpha_all) {
+                const int64_t slot = b * OT + row_of(t);
 #pragma unroll
                 for (int q = 0; q < NJ; ++q) {
                     const int j = lane + 32 * q;
-                    if (j < S)
-                        p.alpha_all[(b * p.T + t) * S + j] = v[q] > 0.f ? (float)((double)E * 0.69314718055994530942 + (double)logf(v[q])) : -INFINITY;
+                    if (j < S) {
+                        float outv;
+                        if (p.reverse) {
+                            const float sacc = acc[q][0] + acc[q][1];
+                            outv = sacc > 0.f ? logf(sacc) + ca[q] : -INFINITY;  // beta_hat: no observation of this row, offset E_in
+                        } else if (p.ell_all) {
+                            outv = v[q] > 0.f ? logf(v[q]) : -INFINITY;
+                        } else {
+                            outv = v[q] > 0.f ? (float)((double)E * 0.69314718055994530942 + (double)logf(v[q])) : -INFINITY;
+                        }
+                        p.alpha_all[slot * S + j] = outv;
+                    }
                 }
+                if (p.ell_all && lane == 0) p.ell_all[slot] = (double)(p.reverse ? E_in : E) * 0.69314718055994530942;
             }
         }
     }
@@ -166,7 +188,11 @@ __global__ void __launch_bounds__(SM_WARPS * 32) hmm_small_forward(SmallArgs p) 
 #pragma unroll
     for (int q = 0; q < NJ; ++q) tot += v[q];
     tot = warp_sum(tot);
-    if (lane == 0) p.logZ[b] = tot > 0.f ? (float)((double)E * 0.69314718055994530942 + log((double)tot)) : (tot == tot ? -INFINITY : tot);
+    if (lane == 0) {
+        const double z = tot > 0.f ? (double)E * 0.69314718055994530942 + log((double)tot) : (tot == tot ? -INFINITY : (double)tot);
+        if (p.logZ) p.logZ[b] = (float)z;
+        if (p.logZ_d) p.logZ_d[b] = z;
+    }
 }
 
 // Max-plus twin (Viterbi for small state spaces): lane j scans the predecessors i in ascending order with a strict '>' on
@@ -200,7 +226,9 @@ __global__ void __launch_bounds__(SM_WARPS * 32) hmm_small_maxplus(SmallArgs p, 
         const int j = lane + 32 * q;
         d[q] = j < S ? (p.init ? p.init[b * p.init_sb + j] : 0.f) : kNegInf;
     }
-    const float* obs_b = p.obs ? p.obs + b * p.T * S : nullptr;
+    const int64_t OT = p.obs_T ? p.obs_T : p.T;
+    const float* obs_b = p.obs ? p.obs + b * OT * S : nullptr;
+    auto row_of = [&](int64_t t) { return p.reverse ? (p.T - 1 - t) : t; };
     for (int64_t t = 0; t < p.T; ++t) {
         float ob[NJ], best[NJ];
         int arg[NJ];
@@ -267,9 +295,11 @@ bool hmm_small_supported(int semiring, int64_t a_st, int S) {
 }
 
 int hmm_small_forward_device(int semiring, const float* init, int64_t init_sb, const float* A, int64_t a_sb, const float* obs, int64_t B,
-                             int64_t T, int S, float* logZ, float* alpha_all, int32_t* backptr, int32_t* last, cudaStream_t stream) {
+                             int64_t T, int S, float* logZ, float* alpha_all, int32_t* backptr, int32_t* last, cudaStream_t stream,
+                             double* ell_all, double* logZ_d, int64_t obs_T, int transpose, int reverse) {
     SmallArgs a;
     a.init = init; a.init_sb = init_sb; a.A = A; a.a_sb = a_sb; a.obs = obs; a.B = B; a.T = T; a.S = S; a.logZ = logZ; a.alpha_all = alpha_all;
+    a.ell_all = ell_all; a.logZ_d = logZ_d; a.obs_T = obs_T; a.transpose = transpose; a.reverse = reverse;
     const int NJ = S <= 32 ? 1 : 2;
     const int SP = NJ * 32;
     const size_t smem = ((size_t)(a_sb == 0 ? 1 : SM_WARPS) * (SP * SP + SP)) * sizeof(float);
