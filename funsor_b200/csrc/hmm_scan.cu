@@ -1017,7 +1017,9 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
     PassPlan pl;
     int st = make_plan(B, S, false, &pl);
     const bool stream_ok = semiring == FB2_SEMIRING_MAX && a_sb == 0 && a_st == 0 && cpo == 1 && !final_ && !alpha_last &&
-                           !ell_all && S >= 256 && B <= 64 && !stream_disabled();
+                           !ell_all && S > 64 && (B <= 16 || (S > 1024 && B <= 64)) && !stream_disabled();
+    // (S <= 64: warp-per-chain kernel.  The streaming kernel runs on S/32 SMs only; measured, the generic kernel is faster per chain
+    //  once there is more than one 16-chain pass at S <= 1024: e.g. S=512 B=64: 92 vs ~18 us/step, scripts/cliff_time.py)
     if (semiring == FB2_SEMIRING_LOG && a_sb == 0 && a_st == 0 && cpo == 1 && !final_ && !alpha_last && !ell_last && !backptr && !last) {
         const int ls = log_stream_pass(init, init_sb, A, obs, T, B, T, S, out, out_d, alpha_all, ell_all, 0, workspace, workspace_bytes, stream);
         if (ls != FB2_ERR_UNSUPPORTED) return ls;
@@ -1128,7 +1130,7 @@ extern "C" size_t fb2_hmm_workspace_bytes(int op, int64_t B, int64_t T, int32_t 
         base += hmm_flow_workspace_bytes(B, S);
         if (fa > base) base = fa;
     }
-    if ((op <= 1 || op == 3) && S >= 256)  // strip-major copy of A (+ column maxima, scratch)
+    if ((op <= 1 || op == 3) && S > 64)  // strip-major copy of A (+ column maxima, scratch)
         base += align_up((size_t)((S + 31) / 32) * S * 32 * sizeof(float)) + align_up((size_t)S * 4) + align_up((size_t)B * 4);
     if (op == 1) base += align_up((size_t)B * T * S * sizeof(int32_t)) + align_up((size_t)B * sizeof(int32_t));
     if (op == 2) {
