@@ -64,3 +64,34 @@ def test_device_entry_points_fail_loudly_without_gpu(lib):
     assert st == _lib.ERR_NO_DEVICE
     with pytest.raises(_lib.Fb2Error):
         _lib.check(st)
+
+
+def test_chain_distribution_shapes_on_cpu():
+    """Constructor-side logic of the funsor.pyro.hmm mirrors needs no GPU: batch_shape / event_shape follow the reference's
+    broadcasting rules (pyro/hmm.py:82-88, 240-248, 335-341) for its own shape lists (test/pyro/test_hmm.py:26-44, 157-173)."""
+    import numpy as np
+
+    from funsor_b200.hmm import DiscreteHMM, GaussianHMM, GaussianMRF
+
+    MVN = torch.distributions.MultivariateNormal
+    S = 3
+    for ish, tsh, osh in [((), (1,), ()), ((), (), (1,)), ((), (2,), ()), ((), (7,), (1,)), ((), (7,), (5, 7)), ((5,), (5, 7), (7,)),
+                          ((4, 1, 1), (3, 1, 7), (2, 7))]:
+        d = DiscreteHMM(torch.randn(ish + (S,)), torch.randn(tsh + (S, S)), torch.distributions.Normal(torch.randn(osh + (S,)), torch.ones(osh + (S,))))
+        shape = np.broadcast_shapes(ish + (1,), tsh, osh)
+        assert tuple(d.batch_shape) == tuple(shape[:-1]) and tuple(d.event_shape) == (shape[-1],)
+        assert torch.allclose(d.initial_logits.logsumexp(-1), torch.zeros(ish), atol=1e-6)
+        assert torch.allclose(d.transition_logits.logsumexp(-1), torch.zeros(tsh + (S,)), atol=1e-6)
+        with pytest.raises(ValueError, match="CUDA"):
+            d.log_prob(torch.randn(tuple(shape[:-1]) + (max(shape[-1], 2),)))
+    D, O = 2, 3
+    eye = lambda sh, n: torch.eye(n).expand(sh + (n, n))  # noqa: E731
+    for ish, tmsh, tvsh, omsh, ovsh in [((), (), (), (), ()), ((), (6,), (), (), ()), ((5,), (6,), (), (), ()), ((), (5, 1), (6,), (), ()),
+                                        ((5,), (5, 6), (5, 6), (5, 6), (5, 6))]:
+        g = GaussianHMM(MVN(torch.zeros(ish + (D,)), scale_tril=eye(ish, D)), torch.randn(tmsh + (D, D)), MVN(torch.zeros(tvsh + (D,)), scale_tril=eye(tvsh, D)),
+                        torch.randn(omsh + (D, O)), MVN(torch.zeros(ovsh + (O,)), scale_tril=eye(ovsh, O)))
+        shape = np.broadcast_shapes(ish + (1,), tmsh, tvsh, omsh, ovsh)
+        assert tuple(g.batch_shape) == tuple(shape[:-1]) and tuple(g.event_shape) == (shape[-1], O)
+    m = GaussianMRF(MVN(torch.zeros(5, D), scale_tril=eye((5,), D)), MVN(torch.zeros(7, 2 * D), scale_tril=eye((7,), 2 * D)),
+                    MVN(torch.zeros(5, 7, D + O), scale_tril=eye((5, 7), D + O)))
+    assert tuple(m.batch_shape) == (5,) and tuple(m.event_shape) == (7, O) and m.hidden_dim == D and m.obs_dim == O
