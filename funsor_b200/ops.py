@@ -10,6 +10,8 @@ Reference functions mirrored (paths relative to the funsor tree):
   DiscreteHMM.log_prob                       funsor/pyro/hmm.py:119-138
   AdjointTape.adjoint over a scan            funsor/adjoint.py:72-131
 """
+import os
+
 import torch
 
 from . import _lib
@@ -45,8 +47,32 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_GUARD = os.environ.get("FB2_GUARD") == "1"  # debugging aid: a sentinel band behind every workspace, verified by check_guards()
+_GUARD_BYTES = 1 << 16
+_guards = []
+
+
 def _workspace(nbytes, device):
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    n = max(int(nbytes), 256)
+    if not _GUARD:
+        return torch.empty(n, dtype=torch.uint8, device=device)
+    buf = torch.empty(n + _GUARD_BYTES, dtype=torch.uint8, device=device)
+    buf[n:] = 0xA5
+    _guards.append((buf, n))
+    return buf[:n]
+
+
+def check_guards():
+    """With FB2_GUARD=1: synchronise and verify that no kernel wrote past the end of a workspace handed out since the last check."""
+    bad = 0
+    for buf, n in _guards:
+        if not bool((buf[n:] == 0xA5).all()):
+            bad += 1
+    checked = len(_guards)
+    _guards.clear()
+    if bad:
+        raise RuntimeError("{} of {} workspaces were written past their end".format(bad, checked))
+    return checked
 
 
 def _ptr(t):

@@ -11,6 +11,15 @@ from oracle import semiring_ref as R
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _workspace_guards():
+    """FB2_GUARD=1 puts a sentinel band behind every workspace; any kernel writing past the size the library asked for fails here."""
+    yield
+    from funsor_b200 import ops
+
+    ops.check_guards()
+
+
 @pytest.fixture(scope="module")
 def fb():
     import funsor_b200 as fb
