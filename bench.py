@@ -256,12 +256,12 @@ def main():
                 "hbm": {"achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
                         "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": hbm_bytes}}
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # the CPU baseline and the secondary rows are N=1 items
         r = cpu_reference_sample(S, B, args.ref_T)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     extra = {}
-    if not args.no_extra:
+    if not args.no_extra and world == 1:
         try:
             extra = extra_measurements(device)
         except Exception as e:  # extras never invalidate the headline line
