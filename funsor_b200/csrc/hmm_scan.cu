@@ -338,37 +338,45 @@ __global__ void __launch_bounds__(256) hmm_forward_generic(HmmArgs p) {
 // A[S,S] row-major -> strips[tile][row][32] (columns beyond S padded with -inf): every CTA then streams ONE contiguous
 // 128*S-byte strip per step instead of 128-byte pieces 4*S bytes apart (DRAM page locality; A does not stay in L2 at
 // S=4096: 64 MB against 2 x 63 MB of die-local L2).
-__global__ void stream_retile_A(const float* A, int S, float* strips) {
+// With RP > 1 a tile is TW = 32 / RP columns wide and a warp instruction covers RP consecutive rows of it (lane = rp * TW + cl), so
+// that S / TW CTAs share the work instead of S / 32: strips[tile][row][TW], rows padded with -inf to a multiple of RP.
+__global__ void stream_retile_A(const float* A, int S, float* strips, int RP) {
+    const int TW = 32 / RP;
+    const int SR = (S + RP - 1) / RP * RP;  // padded rows
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int ntiles = (S + 31) / 32;
-    if (idx >= (int64_t)ntiles * S * 32) return;
-    const int l = (int)(idx & 31);
-    const int64_t r = idx >> 5;
-    const int row = (int)(r % S), tile = (int)(r / S);
-    const int col = tile * 32 + l;
-    strips[idx] = col < S ? A[(int64_t)row * S + col] : kNegInf;
+    const int ntiles = (S + TW - 1) / TW;
+    if (idx >= (int64_t)ntiles * SR * TW) return;
+    const int l = (int)(idx % TW);
+    const int64_t r = idx / TW;
+    const int row = (int)(r % SR), tile = (int)(r / SR);
+    const int col = tile * TW + l;
+    strips[idx] = (col < S && row < S) ? A[(int64_t)row * S + col] : kNegInf;
 }
 constexpr int STREAM_WARPS = 8;
 constexpr int STREAM_THREADS = STREAM_WARPS * 32;
-template <int R, bool ARG>
+template <int R, bool ARG, int RP>
 __global__ void __launch_bounds__(STREAM_THREADS) hmm_maxplus_stream(HmmArgs p) {
     constexpr int NW = STREAM_WARPS, NTH = STREAM_THREADS;
+    constexpr int TW = 32 / RP;  // columns per tile; lane = rp * TW + cl scans rows rp, rp + RP, ... of column cl
     extern __shared__ __align__(16) float smem[];
     const int S = p.S;
-    float* s_delta = smem;                                     // [R][S]
-    float* s_best = s_delta + (((size_t)R * S + 3) & ~(size_t)3);  // [NW][R][32] (16-byte aligned)
-    int* s_arg = reinterpret_cast<int*>(s_best + NW * R * 32);  // [NW][R][32]
-    float* s_strip = reinterpret_cast<float*>(s_arg + NW * R * 32);  // [keep][32]: the first `keep` rows of this CTA's strip
+    const int SR = (S + RP - 1) / RP * RP;  // rows incl. padding
+    const int NS = SR / RP;                 // row slots (one 128-byte line of the strip each)
+    float* s_delta = smem;                                      // [R][SR]
+    float* s_best = s_delta + (((size_t)R * SR + 3) & ~(size_t)3);  // [NW][R][TW] (16-byte aligned)
+    int* s_arg = reinterpret_cast<int*>(s_best + NW * R * TW);   // [NW][R][TW]
+    float* s_strip = reinterpret_cast<float*>(s_arg + NW * R * TW);  // [keep][32]: the first `keep` row slots of this CTA's strip
+    const int ntiles = (S + TW - 1) / TW;
     // When every CTA owns exactly one strip, the part of it that fits in the remaining shared memory stays on chip for
     // the whole pass and only the rest is streamed each step.
-    const int keep = p.W;  // rows resident in shared memory (0 if a CTA serves several strips)
-    if (keep > 0 && (int)blockIdx.x < (S + 31) / 32) {
-        const float4* src = reinterpret_cast<const float4*>(p.A + (size_t)blockIdx.x * S * 32);
+    const int keep = p.W;  // row slots resident in shared memory (0 if a CTA serves several strips)
+    if (keep > 0 && (int)blockIdx.x < ntiles) {
+        const float4* src = reinterpret_cast<const float4*>(p.A + (size_t)blockIdx.x * SR * TW);
         float4* dst = reinterpret_cast<float4*>(s_strip);
         for (int idx = threadIdx.x; idx < keep * 8; idx += NTH) dst[idx] = __ldg(src + idx);
     }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ntiles = (S + 31) / 32;
+    const int rp = lane / TW, cl = lane % TW;
     unsigned epoch = 0;
     unsigned* ctr = p.counters;
 
@@ -376,8 +384,8 @@ __global__ void __launch_bounds__(STREAM_THREADS) hmm_maxplus_stream(HmmArgs p) 
         const int nb = (int)min((int64_t)R, p.B - b0);
         // ---- delta_{-1} = init -> vec[0]
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-            for (int idx = tid; idx < nb * 32; idx += NTH) {
-                const int r = idx >> 5, j = tile * 32 + (idx & 31);
+            for (int idx = tid; idx < nb * TW; idx += NTH) {
+                const int r = idx / TW, j = tile * TW + (idx % TW);
                 if (j < S) p.vec[(b0 + r) * S + j] = p.init ? p.init[(b0 + r) * p.init_sb + j] : 0.f;
             }
         group_barrier(ctr, (++epoch) * gridDim.x, gridDim.x);
@@ -385,13 +393,13 @@ __global__ void __launch_bounds__(STREAM_THREADS) hmm_maxplus_stream(HmmArgs p) 
         for (int64_t t = 0; t < p.T; ++t) {
             const float* vin = p.vec + (size_t)(t & 1) * p.B * S;
             float* vout = p.vec + (size_t)((t + 1) & 1) * p.B * S;
-            for (int idx = tid; idx < R * S; idx += NTH) {
-                const int r = idx / S, i = idx - r * S;
-                s_delta[idx] = (r < nb) ? __ldcg(vin + (b0 + r) * S + i) : kNegInf;
+            for (int idx = tid; idx < R * SR; idx += NTH) {
+                const int r = idx / SR, i = idx - r * SR;
+                s_delta[idx] = (r < nb && i < S) ? __ldcg(vin + (b0 + r) * S + i) : kNegInf;
             }
             __syncthreads();
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int col = tile * 32 + lane;
+                const int col = tile * TW + cl;
                 const bool colok = col < S;
                 float ob[R], best[R];
                 int arg[R];
@@ -399,65 +407,83 @@ __global__ void __launch_bounds__(STREAM_THREADS) hmm_maxplus_stream(HmmArgs p) 
                 for (int r = 0; r < R; ++r) {
                     ob[r] = (p.obs && colok && r < nb) ? __ldg(p.obs + ((b0 + r) * p.T + t) * S + col) : 0.f;
                     best[r] = kNegInf;
-                    arg[r] = warp < S ? warp : 0;
+                    arg[r] = warp * RP + rp < S ? warp * RP + rp : 0;
                 }
-                const float* Acol = p.A + (size_t)tile * S * 32 + lane;  // strip-major copy of A: [tile][row][32]
-                int i = warp;
-                for (; i < keep; i += NW * 8) {  // resident rows (keep is a multiple of 8*NW)
+                const float* Acol = p.A + (size_t)tile * SR * TW + lane;  // strip-major copy of A: slot sl at + sl * 32
+                int sl = warp;
+                for (; sl < keep; sl += NW * 8) {  // resident slots (keep is a multiple of 8*NW)
                     float a[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) a[u] = s_strip[(i + NW * u) * 32 + lane];
+                    for (int u = 0; u < 8; ++u) a[u] = s_strip[(sl + NW * u) * 32 + lane];
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const float v = s_delta[r * S + i + NW * u] + (a[u] + ob[r]);
+                            const int i = (sl + NW * u) * RP + rp;
+                            const float v = s_delta[r * SR + i] + (a[u] + ob[r]);
                             if (v > best[r]) {
                                 best[r] = v;
-                                arg[r] = i + NW * u;
+                                arg[r] = i;
                             }
                         }
                 }
-                for (; i + NW * 15 < S; i += NW * 16) {
+                for (; sl + NW * 15 < NS; sl += NW * 16) {
                     float a[16];
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) a[u] = __ldg(Acol + (size_t)(i + NW * u) * 32);
+                    for (int u = 0; u < 16; ++u) a[u] = __ldg(Acol + (size_t)(sl + NW * u) * 32);
 #pragma unroll
                     for (int u = 0; u < 16; ++u)
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const float v = s_delta[r * S + i + NW * u] + (a[u] + ob[r]);  // (A + obs) first: hmm.py:130
+                            const int i = (sl + NW * u) * RP + rp;
+                            const float v = s_delta[r * SR + i] + (a[u] + ob[r]);  // (A + obs) first: hmm.py:130
                             if (v > best[r]) {
                                 best[r] = v;
-                                arg[r] = i + NW * u;
+                                arg[r] = i;
                             }
                         }
                 }
-                for (; i < S; i += NW) {
-                    const float a = __ldg(Acol + (size_t)i * 32);
+                for (; sl < NS; sl += NW) {
+                    const float a = __ldg(Acol + (size_t)sl * 32);
+                    const int i = sl * RP + rp;
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const float v = s_delta[r * S + i] + (a + ob[r]);
+                        const float v = s_delta[r * SR + i] + (a + ob[r]);
                         if (v > best[r]) {
                             best[r] = v;
                             arg[r] = i;
                         }
                     }
                 }
+                // combine the RP row phases of a column (lanes cl, cl + TW, ...): larger value, on ties the smaller row
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    s_best[(warp * R + r) * 32 + lane] = best[r];
-                    s_arg[(warp * R + r) * 32 + lane] = arg[r];
+                for (int o = TW; o < 32; o <<= 1) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, best[r], o);
+                        const int oa = __shfl_xor_sync(0xffffffffu, arg[r], o);
+                        if (ov > best[r] || (ov == best[r] && oa < arg[r])) {
+                            best[r] = ov;
+                            arg[r] = oa;
+                        }
+                    }
+                }
+                if (rp == 0) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        s_best[(warp * R + r) * TW + cl] = best[r];
+                        s_arg[(warp * R + r) * TW + cl] = arg[r];
+                    }
                 }
                 __syncthreads();
-                for (int fin = tid; fin < R * 32; fin += NTH) {  // R * 32 may exceed the thread count (R = 16)
-                    const int r = fin >> 5, l = fin & 31, c = tile * 32 + l;
+                for (int fin = tid; fin < R * TW; fin += NTH) {
+                    const int r = fin / TW, l = fin % TW, c = tile * TW + l;
                     if (r < nb && c < S) {
                         float bb = kNegInf;
                         int aa = 0x7fffffff;
                         for (int w = 0; w < NW; ++w) {
-                            const float v = s_best[(w * R + r) * 32 + l];
-                            const int ai = s_arg[(w * R + r) * 32 + l];
+                            const float v = s_best[(w * R + r) * TW + l];
+                            const int ai = s_arg[(w * R + r) * TW + l];
                             if (v > bb || (v == bb && ai < aa)) {
                                 bb = v;
                                 aa = ai;
@@ -1034,28 +1060,33 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
     }
     FB2_CUDA(cudaMemsetAsync(ctr, 0, 1024 * sizeof(unsigned), stream));
     if (stream_ok) {
-        const size_t strip_elems = (size_t)((S + 31) / 32) * S * 32;
+        // row phases: as many as keep the number of tiles (= CTAs) within the SM count
+        int RP = 1;
+        while (RP < 8 && (S + (32 / (2 * RP)) - 1) / (32 / (2 * RP)) <= g_sm_count) RP *= 2;
+        const int TW = 32 / RP, SR = (S + RP - 1) / RP * RP;
+        const int ntiles = (S + TW - 1) / TW;
+        const size_t strip_elems = (size_t)ntiles * SR * TW;
         float* strips = arena.take<float>(strip_elems);
         if (!arena.ok()) {
             set_error("hmm forward (max-plus stream): workspace too small (%zu bytes)", workspace_bytes);
             return FB2_ERR_WORKSPACE;
         }
-        stream_retile_A<<<(unsigned)ceil_div((int64_t)strip_elems, 256), 256, 0, stream>>>(A, S, strips);
+        stream_retile_A<<<(unsigned)ceil_div((int64_t)strip_elems, 256), 256, 0, stream>>>(A, S, strips, RP);
         FB2_LAUNCH_CHECK();
         HmmArgs a{};
         a.init = init; a.init_sb = init_sb; a.A = strips; a.obs = obs; a.B = B; a.T = T; a.S = S; a.vec = vec; a.counters = ctr;
         a.alpha_all = alpha_all; a.backptr = backptr; a.out = out; a.last = last;
         int R = B >= 16 ? 16 : (B >= 4 ? 4 : 1);  // chains per pass (A is re-read for every pass)
-        auto mp_smem = [&](int r) { return ((((size_t)r * S + 3) & ~(size_t)3) + 2 * STREAM_WARPS * r * 32) * 4; };
+        auto mp_smem = [&](int r) { return ((((size_t)r * SR + 3) & ~(size_t)3) + 2 * STREAM_WARPS * r * TW) * 4; };
         if (R == 16 && mp_smem(16) > 96 * 1024) R = 4;
         size_t smem = mp_smem(R);
         if (smem <= g_smem_optin) {
-            int ntiles = (S + 31) / 32;
             int grid = ntiles < g_sm_count ? ntiles : g_sm_count;
             int keep = 0;
-            if (ntiles <= g_sm_count) {  // one strip per CTA: keep as many of its rows on chip as fit
+            const int NS = SR / RP;
+            if (ntiles <= g_sm_count) {  // one strip per CTA: keep as many of its row slots on chip as fit
                 keep = (int)((g_smem_optin - smem - 1024) / 128);
-                if (keep > S) keep = S;
+                if (keep > NS) keep = NS;
                 keep = keep / (8 * STREAM_WARPS) * (8 * STREAM_WARPS);
                 if (keep < 0) keep = 0;
             }
@@ -1064,14 +1095,21 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
             PassPlan sp{};
             sp.grid = grid;
             sp.smem = smem;
-            if (R == 16)
-                return backptr ? coop_launch(hmm_maxplus_stream<16, true>, sp, a, stream, STREAM_THREADS)
-                               : coop_launch(hmm_maxplus_stream<16, false>, sp, a, stream, STREAM_THREADS);
-            if (R == 4)
-                return backptr ? coop_launch(hmm_maxplus_stream<4, true>, sp, a, stream, STREAM_THREADS)
-                               : coop_launch(hmm_maxplus_stream<4, false>, sp, a, stream, STREAM_THREADS);
-            return backptr ? coop_launch(hmm_maxplus_stream<1, true>, sp, a, stream, STREAM_THREADS)
-                           : coop_launch(hmm_maxplus_stream<1, false>, sp, a, stream, STREAM_THREADS);
+#define FB2_MPS(Rv, RPv)                                                                                           \
+    return backptr ? coop_launch(hmm_maxplus_stream<Rv, true, RPv>, sp, a, stream, STREAM_THREADS)                  \
+                   : coop_launch(hmm_maxplus_stream<Rv, false, RPv>, sp, a, stream, STREAM_THREADS)
+#define FB2_MPS_R(RPv)                 \
+    do {                               \
+        if (R == 16) { FB2_MPS(16, RPv); } \
+        if (R == 4) { FB2_MPS(4, RPv); }   \
+        FB2_MPS(1, RPv);               \
+    } while (0)
+            if (RP == 8) FB2_MPS_R(8);
+            if (RP == 4) FB2_MPS_R(4);
+            if (RP == 2) FB2_MPS_R(2);
+            FB2_MPS_R(1);
+#undef FB2_MPS_R
+#undef FB2_MPS
         }
         if (st != FB2_OK) return st;
     }
@@ -1131,7 +1169,7 @@ extern "C" size_t fb2_hmm_workspace_bytes(int op, int64_t B, int64_t T, int32_t 
         if (fa > base) base = fa;
     }
     if ((op <= 1 || op == 3) && S > 64)  // strip-major copy of A (+ column maxima, scratch)
-        base += align_up((size_t)((S + 31) / 32) * S * 32 * sizeof(float)) + align_up((size_t)S * 4) + align_up((size_t)B * 4);
+        base += align_up((size_t)((S + 31) / 32) * (S + 8) * 32 * sizeof(float)) + align_up((size_t)S * 4) + align_up((size_t)B * 4);
     if (op == 1) base += align_up((size_t)B * T * S * sizeof(int32_t)) + align_up((size_t)B * sizeof(int32_t));
     if (op == 2) {
         base += align_up((size_t)B * T * S * sizeof(float)) + 2 * align_up((size_t)B * T * 8) + align_up((size_t)B * 8);
