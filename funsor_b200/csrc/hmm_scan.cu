@@ -391,9 +391,9 @@ __global__ void __launch_bounds__(STREAM_THREADS) hmm_maxplus_stream32(HmmArgs p
         for (int64_t t = 0; t < p.T; ++t) {
             const float* vin = p.vec + (size_t)(t & 1) * p.B * S;
             float* vout = p.vec + (size_t)((t + 1) & 1) * p.B * S;
-            for (int idx = tid; idx < R * S; idx += NTH) {
-                const int r = idx / S, i = idx - r * S;
-                s_delta[idx] = (r < nb) ? __ldcg(vin + (b0 + r) * S + i) : kNegInf;
+            for (int i = tid; i < S; i += NTH) {  // R independent loads per iteration, no division
+#pragma unroll
+                for (int r = 0; r < R; ++r) s_delta[r * S + i] = (r < nb) ? __ldcg(vin + (b0 + r) * S + i) : kNegInf;
             }
             __syncthreads();
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -549,9 +549,10 @@ __global__ void __launch_bounds__(STREAM_THREADS) hmm_maxplus_stream(HmmArgs p) 
         for (int64_t t = 0; t < p.T; ++t) {
             const float* vin = p.vec + (size_t)(t & 1) * p.B * S;
             float* vout = p.vec + (size_t)((t + 1) & 1) * p.B * S;
-            for (int idx = tid; idx < R * SR; idx += NTH) {
-                const int r = idx / SR, i = idx - r * SR;
-                s_delta[idx] = (r < nb && i < S) ? __ldcg(vin + (b0 + r) * S + i) : kNegInf;
+            // R independent loads per iteration and no division (the flat loop with idx / SR cost ~17 us per step at R = 16, S = 1024)
+            for (int i = tid; i < SR; i += NTH) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) s_delta[r * SR + i] = (r < nb && i < S) ? __ldcg(vin + (b0 + r) * S + i) : kNegInf;
             }
             __syncthreads();
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
