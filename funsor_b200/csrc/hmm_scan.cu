@@ -1200,9 +1200,9 @@ int hmm_forward_device(int semiring, const float* init, int64_t init_sb, const f
     PassPlan pl;
     int st = make_plan(B, S, false, &pl);
     const bool stream_ok = semiring == FB2_SEMIRING_MAX && a_sb == 0 && a_st == 0 && cpo == 1 && !final_ && !alpha_last &&
-                           !ell_all && S > 64 && (B <= 16 || (S > 1024 && B <= 64)) && !stream_disabled();
+                           !ell_all && S > 64 && (B <= 16 || (S >= 512 && B <= 64)) && !stream_disabled();
     // (S <= 64: warp-per-chain kernel.  The streaming kernel runs on S/32 SMs only; measured, the generic kernel is faster per chain
-    //  once there is more than one 16-chain pass at S <= 1024: e.g. S=512 B=64: 92 vs ~18 us/step, scripts/cliff_time.py)
+    //  once there is more than one 16-chain pass at S < 512: e.g. S=256 B=64: 19 vs 13.5 us/step, scripts/cliff_time.py)
     if (semiring == FB2_SEMIRING_LOG && a_sb == 0 && a_st == 0 && cpo == 1 && !final_ && !alpha_last && !ell_last && !backptr && !last) {
         const int ls = log_stream_pass(init, init_sb, A, obs, T, B, T, S, out, out_d, alpha_all, ell_all, 0, workspace, workspace_bytes, stream);
         if (ls != FB2_ERR_UNSUPPORTED) return ls;
