@@ -21,6 +21,16 @@ from . import ops
 from ._lib import check  # noqa: F401
 
 
+def _check(cond, what):
+    """Argument validation in the reference's style: a failed check is an AssertionError (pyro/hmm.py:75-80, 233-243, 331-336)."""
+    if not cond:
+        raise AssertionError(what)
+
+
+def _is_mvn(d):
+    return isinstance(d, torch.distributions.MultivariateNormal)
+
+
 def _broadcast_shape(*shapes):
     return tuple(torch.broadcast_shapes(*[tuple(s) for s in shapes]))
 
@@ -41,12 +51,10 @@ class DiscreteHMM:
     """
 
     def __init__(self, initial_logits, transition_logits, observation_dist, validate_args=None):
-        assert isinstance(initial_logits, torch.Tensor)
-        assert isinstance(transition_logits, torch.Tensor)
-        assert isinstance(observation_dist, torch.distributions.Distribution)
-        assert initial_logits.dim() >= 1
-        assert transition_logits.dim() >= 2
-        assert len(observation_dist.batch_shape) >= 1
+        _check(torch.is_tensor(initial_logits) and torch.is_tensor(transition_logits), "logits must be torch tensors")
+        _check(isinstance(observation_dist, torch.distributions.Distribution), "observation_dist must be a torch distribution")
+        _check(initial_logits.dim() >= 1 and transition_logits.dim() >= 2, "logits need a state dim (init) / two state dims (trans)")
+        _check(len(observation_dist.batch_shape) >= 1, "observation_dist needs a state dim in its batch_shape")
         shape = _broadcast_shape(initial_logits.shape[:-1] + (1,), transition_logits.shape[:-2], observation_dist.batch_shape[:-1])
         self.batch_shape, time_shape = torch.Size(shape[:-1]), shape[-1:]
         self.event_shape = torch.Size(time_shape + tuple(observation_dist.event_shape))
@@ -152,17 +160,17 @@ class GaussianHMM:
     has_rsample = True
 
     def __init__(self, initial_dist, transition_matrix, transition_dist, observation_matrix, observation_dist, validate_args=None):
-        assert isinstance(initial_dist, torch.distributions.MultivariateNormal)
-        assert isinstance(transition_matrix, torch.Tensor)
-        assert isinstance(transition_dist, torch.distributions.MultivariateNormal)
-        assert isinstance(observation_matrix, torch.Tensor)
-        assert isinstance(observation_dist, (torch.distributions.MultivariateNormal, torch.distributions.Independent))
-        hidden_dim, obs_dim = observation_matrix.shape[-2:]
-        assert obs_dim >= hidden_dim // 2, "obs_dim must be at least half of hidden_dim"
-        assert initial_dist.event_shape == (hidden_dim,)
-        assert transition_matrix.shape[-2:] == (hidden_dim, hidden_dim)
-        assert transition_dist.event_shape == (hidden_dim,)
-        assert observation_dist.event_shape == (obs_dim,)
+        _check(_is_mvn(initial_dist) and _is_mvn(transition_dist), "initial_dist / transition_dist must be MultivariateNormal")
+        _check(torch.is_tensor(transition_matrix) and torch.is_tensor(observation_matrix), "matrices must be torch tensors")
+        _check(_is_mvn(observation_dist) or isinstance(observation_dist, torch.distributions.Independent),
+               "observation_dist must be MultivariateNormal or Independent(Normal, 1)")
+        D_, O_ = observation_matrix.shape[-2], observation_matrix.shape[-1]
+        hidden_dim, obs_dim = int(D_), int(O_)
+        _check(2 * obs_dim >= hidden_dim - 1, "obs_dim must be at least half of hidden_dim")
+        _check(tuple(initial_dist.event_shape) == (hidden_dim,) and tuple(transition_dist.event_shape) == (hidden_dim,),
+               "initial_dist / transition_dist must have event_shape (hidden_dim,)")
+        _check(tuple(transition_matrix.shape[-2:]) == (hidden_dim, hidden_dim), "transition_matrix must end in (hidden_dim, hidden_dim)")
+        _check(tuple(observation_dist.event_shape) == (obs_dim,), "observation_dist must have event_shape (obs_dim,)")
         shape = _broadcast_shape(initial_dist.batch_shape + (1,), transition_matrix.shape[:-2], transition_dist.batch_shape,
                                  observation_matrix.shape[:-2], observation_dist.batch_shape)
         self.batch_shape, time_shape = torch.Size(shape[:-1]), shape[-1:]
@@ -213,12 +221,11 @@ class GaussianMRF:
     has_rsample = True
 
     def __init__(self, initial_dist, transition_dist, observation_dist, validate_args=None):
-        assert isinstance(initial_dist, torch.distributions.MultivariateNormal)
-        assert isinstance(transition_dist, torch.distributions.MultivariateNormal)
-        assert isinstance(observation_dist, torch.distributions.MultivariateNormal)
-        hidden_dim = initial_dist.event_shape[0]
-        assert transition_dist.event_shape[0] == hidden_dim + hidden_dim
-        obs_dim = observation_dist.event_shape[0] - hidden_dim
+        _check(_is_mvn(initial_dist) and _is_mvn(transition_dist) and _is_mvn(observation_dist), "all three factors must be MultivariateNormal")
+        hidden_dim = int(initial_dist.event_shape[-1])
+        _check(int(transition_dist.event_shape[-1]) == 2 * hidden_dim, "transition_dist must be over (old; new) states: event size 2 * hidden_dim")
+        obs_dim = int(observation_dist.event_shape[-1]) - hidden_dim
+        _check(obs_dim >= 1, "observation_dist must be over (state; observation)")
         shape = _broadcast_shape(initial_dist.batch_shape + (1,), transition_dist.batch_shape, observation_dist.batch_shape)
         self.batch_shape, time_shape = torch.Size(shape[:-1]), shape[-1:]
         self.event_shape = torch.Size(time_shape + (obs_dim,))
