@@ -95,3 +95,20 @@ def test_chain_distribution_shapes_on_cpu():
     m = GaussianMRF(MVN(torch.zeros(5, D), scale_tril=eye((5,), D)), MVN(torch.zeros(7, 2 * D), scale_tril=eye((7,), 2 * D)),
                     MVN(torch.zeros(5, 7, D + O), scale_tril=eye((5, 7), D + O)))
     assert tuple(m.batch_shape) == (5,) and tuple(m.event_shape) == (7, O) and m.hidden_dim == D and m.obs_dim == O
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on host cores only (no GPU): one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-T", "2"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["workload"] == "c2"
