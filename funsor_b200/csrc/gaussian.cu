@@ -839,6 +839,89 @@ static int homog_chain_run(const float* Lam, const float* eta, const float* c, i
     return FB2_OK;
 }
 
+
+// (Lam, eta, c) -> (w, P, s): a square root of a positive SEMI-definite precision (chain products are rank deficient in general:
+// transition factors carry rank D + O < 2D, gaussian.py:402-406) by diagonally pivoted Cholesky, one warp per element.
+// P[n][n] = rows of the factor in the ORIGINAL row order, columns in pivot order, zero columns beyond the numerical rank; any P with
+// P P' = Lam is a valid prec_sqrt (gaussian.py:419-498; testing.py:149-153 compares Lam and eta only).  w solves P w = eta on the
+// range of Lam, s = c + |w|^2 / 2.  Pivoting makes the dropped remainder small ENTRYWISE (every remaining diagonal is below the
+// threshold, and |m_ij| <= sqrt(m_ii m_jj) for a PSD remainder); without it one small leading pivot would drop sqrt(tol)-sized entries.
+constexpr int I2S_WARPS = 4;
+__global__ void __launch_bounds__(I2S_WARPS * 32) gaussian_info_to_sqrt(const float* __restrict__ Lam, const float* __restrict__ eta,
+                                                                          const float* __restrict__ c, int64_t N, int n, float rel_tol,
+                                                                          float* __restrict__ w, float* __restrict__ P, float* __restrict__ s,
+                                                                          int32_t* __restrict__ rank_out) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ld = n + 1;
+    float* L = sm + (size_t)wid * (n * ld + n);  // L[i][j] (row i, pivot column j), then wv[n]
+    float* wv = L + n * ld;
+    const int64_t e = (int64_t)blockIdx.x * I2S_WARPS + wid;
+    if (e >= N) return;
+    const float* A = Lam + e * (int64_t)n * n;
+    const int r0 = lane, r1 = lane + 32;
+    float d0 = r0 < n ? A[(int64_t)r0 * n + r0] : -1.f, d1 = r1 < n ? A[(int64_t)r1 * n + r1] : -1.f;
+    bool done0 = r0 >= n, done1 = r1 >= n;
+    float e0 = r0 < n ? eta[e * n + r0] : 0.f, e1 = r1 < n ? eta[e * n + r1] : 0.f;  // running right-hand side eta - L[:, :j] w[:j]
+    const float tol = fmaxf(warp_max(fmaxf(d0, d1)), 0.f) * rel_tol;
+    for (int idx = lane; idx < n * ld + n; idx += 32) L[idx] = 0.f;
+    __syncwarp();
+    int rank = 0;
+    float ww = 0.f;
+    for (int j = 0; j < n; ++j) {
+        // pivot = largest remaining diagonal, smallest index on ties
+        float bv = done0 ? -INFINITY : d0;
+        int bi = r0;
+        if (!done1 && d1 > bv) bv = d1, bi = r1;
+        if (done0 && done1) bi = 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+        }
+        if (!(bv > tol)) break;
+        const int p = bi;
+        // column of the remainder through the pivot: v_i = Lam[p][i] - sum_k L[i][k] L[p][k]   (row p of Lam: a coalesced read)
+        float v0 = (r0 < n) ? A[(int64_t)p * n + r0] : 0.f, v1 = (r1 < n) ? A[(int64_t)p * n + r1] : 0.f;
+        for (int k = 0; k < j; ++k) {
+            const float lp = L[p * ld + k];
+            if (r0 < n) v0 = fmaf(-L[r0 * ld + k], lp, v0);
+            if (r1 < n) v1 = fmaf(-L[r1 * ld + k], lp, v1);
+        }
+        const float vp = __shfl_sync(0xffffffffu, (p & 32) ? v1 : v0, p & 31);
+        const float piv = sqrtf(fmaxf(vp, tol * 0.5f));
+        const float inv = 1.f / piv;
+        const float ep = __shfl_sync(0xffffffffu, (p & 32) ? e1 : e0, p & 31);
+        const float wj = ep * inv;
+        ww = fmaf(wj, wj, ww);
+        if (lane == 0) wv[j] = wj;
+        if (r0 < n) {
+            float l = (r0 == p) ? piv : (done0 ? 0.f : v0 * inv);
+            L[r0 * ld + j] = l;
+            d0 -= l * l;
+            e0 -= l * wj;
+            if (r0 == p) done0 = true;
+        }
+        if (r1 < n) {
+            float l = (r1 == p) ? piv : (done1 ? 0.f : v1 * inv);
+            L[r1 * ld + j] = l;
+            d1 -= l * l;
+            e1 -= l * wj;
+            if (r1 == p) done1 = true;
+        }
+        rank = j + 1;
+        __syncwarp();
+    }
+    float* Po = P + e * (int64_t)n * n;
+    for (int idx = lane; idx < n * n; idx += 32) Po[idx] = L[(idx / n) * ld + (idx % n)];
+    for (int k = lane; k < n; k += 32) w[e * n + k] = wv[k];
+    if (lane == 0) {
+        s[e] = c[e] + 0.5f * ww;
+        if (rank_out) rank_out[e] = rank;
+    }
+}
+
 }  // namespace fb2
 
 using namespace fb2;
@@ -854,6 +937,27 @@ extern "C" int fb2_gaussian_sqrt_to_info_f32(const float* w, const float* P, con
     FB2_REQUIRE(N < (1ll << 31), "too many elements for one launch");
     size_t smem = ((size_t)dim * 33 + 32) * sizeof(float);
     gaussian_sqrt_to_info<<<(unsigned)N, 256, smem, static_cast<cudaStream_t>(stream)>>>(w, P, s, dim, rank, Lam, eta, c);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
+extern "C" int fb2_gaussian_info_to_sqrt_f32(const float* Lam, const float* eta, const float* c, int64_t N, int32_t dim, float rel_tol,
+                                             float* w, float* P, float* s, int32_t* rank, void* stream) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(Lam && eta && c && w && P && s, "null pointer");
+    FB2_REQUIRE(N >= 0 && dim >= 1 && dim <= 2 * GMAXD, "bad extents N=%lld dim=%d", (long long)N, dim);
+    if (N == 0) return FB2_OK;
+    if (!(rel_tol > 0.f)) rel_tol = dim * 1.2e-7f;
+    size_t smem = (size_t)I2S_WARPS * ((size_t)dim * (dim + 1) + dim) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        FB2_CUDA(cudaFuncSetAttribute(gaussian_info_to_sqrt, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    int64_t blocks = ceil_div(N, I2S_WARPS);
+    FB2_REQUIRE(blocks < (1ll << 31), "too many elements for one launch");
+    gaussian_info_to_sqrt<<<(unsigned)blocks, I2S_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(Lam, eta, c, N, dim, rel_tol, w, P, s, rank);
     FB2_LAUNCH_CHECK();
     return FB2_OK;
 }

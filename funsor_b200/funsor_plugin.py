@@ -11,6 +11,15 @@ more-specific rules to funsor's `eager` interpretation for the torch backend:
                                                            the Gaussian scan (gaussian.py:841-1132 per level) as ONE
                                                            information-form chain kernel; the result is converted back
                                                            to the reference's (white_vec, prec_sqrt) + Tensor form
+  Contraction[Logaddexp, Add, frozenset, Gaussian | GaussianMixture, Gaussian | GaussianMixture]
+                                                           one level of that scan when sequential_sum_product is called
+                                                           directly (pyro/hmm.py:269): replaces cnf.py:385-389
+                                                           ((x + y).reduce) by sqrt->info, the Schur-complement pair kernel
+                                                           and a pivoted-Cholesky info->sqrt
+
+Gradients: the Tensor rules stay differentiable (ops.semiring_matmul / sequential_sum_product switch to the autograd
+Functions of autograd.py when an operand requires grad, examples/discrete_hmm.py:76-78); the Gaussian rules delegate to
+the reference whenever an operand requires grad.
 
 A rule takes the CUDA path only when its operands are float32 CUDA tensors with scalar output shape and
 the contraction has matrix-product structure; in every other case it calls the handler that was
@@ -30,7 +39,8 @@ from collections import OrderedDict
 import torch
 
 _STATE = {"registered": False, "calls": {"contraction_fast": 0, "contraction_delegated": 0,
-                                         "markov_fast": 0, "markov_delegated": 0, "gaussian_homogeneous": 0}}
+                                         "markov_fast": 0, "markov_delegated": 0, "gaussian_homogeneous": 0,
+                                         "gaussian_contraction_fast": 0, "gaussian_contraction_delegated": 0}}
 
 
 def stats(reset=False):
@@ -130,20 +140,64 @@ def gaussian_markov_named(white_vec, prec_sqrt, scalar, bint_names, real_blocks,
     return Lam.reshape(bshape + (2 * D, 2 * D)), eta.reshape(bshape + (2 * D,)), c.reshape(bshape), batch
 
 
+def gaussian_contract_named(x, y, reduced, bint_sizes, out_bints, out_reals, to_info, combine, to_sqrt):
+    """One Gaussian pair contraction of the scan (cnf.py:385-389: (x + y).reduce(logaddexp, reduced)) on raw tensors.
+
+    x, y: dicts with `w` [bints..., r], `P` [bints..., dim, r], `s` (None or a tensor over `s_bints`), `bints` (names of the
+    leading dims of w / P), `s_bints`, `reals` [(name, size), ...] in row order of P (gaussian.py:133-151).
+    x must be over real inputs {a, b}, y over {b, c} with reduced == {b} and all three of size D; otherwise returns None.
+    bint_sizes: {name: size}; out_bints: batch names of the result in order; out_reals: [a, c] in the order the result lists them.
+    to_info(w[N,r], P[N,2D,r], s[N]) -> (Lam, eta, c); combine(X, Y) -> (Lam, eta, c, flag); to_sqrt(Lam, eta, c) -> (w, P, s).
+    Returns (w[bints..., 2D], P[bints..., 2D, 2D], s[bints...])."""
+    if len(reduced) != 1:
+        return None
+    (b,) = tuple(reduced)
+    xr, yr = dict(x["reals"]), dict(y["reals"])
+    if b not in xr or b not in yr or len(xr) != 2 or len(yr) != 2:
+        return None
+    (a,) = [k for k in xr if k != b]
+    (c,) = [k for k in yr if k != b]
+    D = xr[b]
+    if a == c or not (xr[a] == yr[c] == yr[b] == D) or sorted(out_reals) != sorted([a, c]):
+        return None
+    bshape = tuple(bint_sizes[n] for n in out_bints)
+    N = 1
+    for d in bshape:
+        N *= d
+
+    def aligned(t, names, tail):
+        """t[names..., *tail dims] -> broadcast over out_bints, flattened to [N, *tail]"""
+        names = list(names)
+        perm = [names.index(n) for n in out_bints if n in names]
+        t = t.permute(perm + list(range(len(names), t.dim())))
+        shape = [bint_sizes[n] if n in names else 1 for n in out_bints]
+        t = t.reshape(shape + list(t.shape[len(perm):]))
+        return t.expand(list(bshape) + list(t.shape[len(out_bints):])).reshape((N,) + tuple(tail))
+
+    def info(g, first, second):
+        r = g["w"].shape[-1]
+        P = g["P"]
+        if [k for k, _ in g["reals"]] != [first, second]:  # rows are (second; first): swap the two blocks
+            P = torch.cat([P[..., D:, :], P[..., :D, :]], dim=-2)
+        w = aligned(g["w"], g["bints"], (r,))
+        P = aligned(P, g["bints"], (2 * D, r))
+        sc = w.new_zeros(N) if g["s"] is None else aligned(g["s"], g["s_bints"], ())
+        return to_info(w, P, sc)
+
+    Lo, eo, co, flag = combine(info(x, a, b), info(y, b, c))
+    if flag is not None and bool(flag.any()):
+        raise ValueError("Too little information to marginalize over {}. Consider adding a prior.".format({b}))  # gaussian.py:897-901
+    w, P, sc = to_sqrt(Lo, eo, co)
+    if list(out_reals) != [a, c]:
+        P = torch.cat([P[..., D:, :], P[..., :D, :]], dim=-2)
+    return w.reshape(bshape + (2 * D,)), P.reshape(bshape + (2 * D, 2 * D)), sc.reshape(bshape)
+
+
 def info_to_sqrt(Lam, eta, c):
-    """(Lam, eta, c) -> the reference's (white_vec, prec_sqrt, scalar) triple.  The precision of a chain product is
-    positive SEMI-definite in general (transition factors are rank deficient), so the square root
-    is taken through an eigendecomposition rather than a Cholesky factor: P = V sqrt(l), w = sqrt(l)^-1 V' eta on the
-    range of Lam.  A [B, 2D, 2D] problem once per scan (not T-sized); float64 on whatever device the inputs live on."""
-    lam, V = torch.linalg.eigh(Lam.double())
-    tol = lam.amax(-1, keepdim=True).clamp(min=0) * (Lam.shape[-1] * 1e-7 if Lam.dtype == torch.float32 else 1e-13)
-    keep = lam > tol
-    root = torch.where(keep, lam.clamp(min=0).sqrt(), torch.zeros_like(lam))
-    P = V * root[..., None, :]
-    proj = (V.transpose(-1, -2) @ eta.double()[..., None])[..., 0]
-    w = torch.where(keep, proj / torch.where(keep, root, torch.ones_like(root)), torch.zeros_like(proj))
-    s = c.double() + 0.5 * (w * w).sum(-1)
-    return w.to(Lam.dtype), P.to(Lam.dtype), s.to(Lam.dtype)
+    """(Lam, eta, c) -> the reference's (white_vec, prec_sqrt, scalar) triple with P P' = Lam, P w = eta, s - |w|^2/2 = c.
+    The precision of a chain product is positive SEMI-definite in general (transition factors are rank deficient,
+    SURVEY section 7): diagonally pivoted Cholesky on the GPU (fb2_gaussian_info_to_sqrt_f32), one warp per element."""
+    return _HOOKS["info_to_sqrt"](Lam, eta, c)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -165,17 +219,60 @@ def _kernel_gaussian_chain(w, P, s):
 
     T = w.shape[1]
     # GaussianHMM with fixed dynamics reaches this rule with a dense prec_sqrt[B, T, 2D, r] whose time slices are all equal
-    # (pyro/hmm.py:258-270: only white_vec depends on t; the Gaussian product materialises the broadcast).  One comparison
-    # pass detects it and the scan then runs on per-level operators + eta-only sweeps (gaussian.gaussian_chain_homog).
-    if T >= 8 and bool((P[:, 1:] == P[:, :1]).all()):
-        _STATE["calls"]["gaussian_homogeneous"] += 1
-        return fg.gaussian_chain_homog(w.contiguous(), P[:, 0].contiguous(), s.contiguous())
+    # (pyro/hmm.py:258-270: only white_vec depends on t; the Gaussian product materialises the broadcast).  A probe of four
+    # time slices rules the heterogeneous case out cheaply; only a chain that passes it pays the full comparison pass.  The scan
+    # then runs on per-level operators + eta-only sweeps (gaussian.gaussian_chain_homog).
+    if T >= 8:
+        probe = P[:, [1, T // 2, T - 2, T - 1]]
+        if P.stride(1) == 0 or (bool((probe == P[:, :1]).all()) and bool((P[:, 1:] == P[:, :1]).all())):
+            _STATE["calls"]["gaussian_homogeneous"] += 1
+            return fg.gaussian_chain_homog(w.contiguous(), P[:, 0].contiguous(), s.contiguous())
     Lam, eta, c = fg.sqrt_to_info(w.contiguous(), P.contiguous(), s.contiguous())
     return fg.gaussian_sequential_sum_product(Lam, eta, c)
 
 
+def _kernel_sqrt_to_info(w, P, s):
+    from . import gaussian as fg
+
+    return fg.sqrt_to_info(w, P, s)
+
+
+def _kernel_gaussian_pair(X, Y):
+    from . import gaussian as fg
+
+    return fg.gaussian_pair_combine(X, Y)
+
+
+def _kernel_info_to_sqrt(Lam, eta, c):
+    from . import gaussian as fg
+
+    return fg.info_to_sqrt(Lam, eta, c)
+
+
 def _fast_ok(*datas):
     return all(isinstance(d, torch.Tensor) and d.is_cuda and d.dtype == torch.float32 for d in datas)
+
+
+def _no_grad_needed(*datas):
+    return not (torch.is_grad_enabled() and any(isinstance(d, torch.Tensor) and d.requires_grad for d in datas))
+
+
+# The kernel entry points and the admission test, looked up at call time: the CPU tests replace them with oracle stand-ins to
+# drive the rules' fast branches inside the unmodified reference without a GPU (tests/test_funsor_plugin.py); on the GPU box
+# the defaults below are what runs (tests/test_gpu_funsor.py).
+_HOOKS = {"fast_ok": _fast_ok, "matmul": _kernel_matmul, "chain": _kernel_chain, "gaussian_chain": _kernel_gaussian_chain,
+          "sqrt_to_info": _kernel_sqrt_to_info, "gaussian_pair": _kernel_gaussian_pair, "info_to_sqrt": _kernel_info_to_sqrt}
+_DEFAULT_HOOKS = dict(_HOOKS)
+
+
+def set_hooks(**hooks):
+    """Test aid: override kernel entry points / the admission test; set_hooks() with no arguments restores the defaults."""
+    if not hooks:
+        _HOOKS.update(_DEFAULT_HOOKS)
+    for k, v in hooks.items():
+        if k not in _HOOKS:
+            raise KeyError(k)
+        _HOOKS[k] = v
 
 
 # ------------------------------------------------------------------------------------------------
@@ -215,11 +312,11 @@ def register():
         sname = _semiring(red_op)
         fast = (
             x.dtype == "real" and y.dtype == "real" and not x.shape and not y.shape
-            and _fast_ok(x.data, y.data) and len(reduced_vars) >= 1
+            and _HOOKS["fast_ok"](x.data, y.data) and len(reduced_vars) >= 1
         )
         if fast:
             reduced = {v.name for v in reduced_vars}
-            res = contract_named(x.data, x.inputs, y.data, y.inputs, reduced, sname, _kernel_matmul)
+            res = contract_named(x.data, x.inputs, y.data, y.inputs, reduced, sname, _HOOKS["matmul"])
             if res is not None:
                 data, out_names = res
                 inputs = OrderedDict()
@@ -235,13 +332,13 @@ def register():
 
     def markov_rule(sum_op, prod_op, trans, time, step, step_names):
         fast = (
-            len(step) == 1 and trans.dtype == "real" and not trans.shape and _fast_ok(trans.data)
+            len(step) == 1 and trans.dtype == "real" and not trans.shape and _HOOKS["fast_ok"](trans.data)
             and time.name in trans.inputs
         )
         if fast:
             ((prev, curr),) = tuple(step)
             if prev in trans.inputs and curr in trans.inputs and trans.inputs[prev] == trans.inputs[curr]:
-                data, out_names = markov_named(trans.data, trans.inputs, time.name, prev, curr, _semiring(sum_op), _kernel_chain)
+                data, out_names = markov_named(trans.data, trans.inputs, time.name, prev, curr, _semiring(sum_op), _HOOKS["chain"])
                 result = Tensor(data, OrderedDict((n, trans.inputs[n]) for n in out_names))
                 _STATE["calls"]["markov_fast"] += 1
                 return Subs(result, step_names)  # funsor/sum_product.py:1064
@@ -273,11 +370,12 @@ def register():
             ((prev, curr),) = tuple(step)
             bints = [(k, d) for k, d in g.inputs.items() if d.dtype != "real"]
             reals = [(k, d.num_elements) for k, d in g.inputs.items() if d.dtype == "real"]
-            ok = (_fast_ok(g.white_vec, g.prec_sqrt) and time.name in dict(bints)
+            ok = (_HOOKS["fast_ok"](g.white_vec, g.prec_sqrt) and _no_grad_needed(g.white_vec, g.prec_sqrt, None if t is None else t.data)
+                  and time.name in dict(bints)
                   and all(len(g.inputs[k].shape) == 1 for k, _ in reals) and max(n for _, n in reals) <= 32)
             scalar = None
             if ok and t is not None:
-                ok = _fast_ok(t.data) and set(t.inputs) <= set(k for k, _ in bints)
+                ok = _HOOKS["fast_ok"](t.data) and set(t.inputs) <= set(k for k, _ in bints)
                 if ok:  # broadcast the Tensor half over the Gaussian's bint dims
                     tdims = list(t.inputs)
                     data = t.data.permute([tdims.index(k) for k, _ in bints if k in tdims])
@@ -285,7 +383,7 @@ def register():
                     scalar = data.reshape(shape).expand([d.size for _, d in bints])
             if ok:
                 res = gaussian_markov_named(g.white_vec, g.prec_sqrt, scalar, [k for k, _ in bints], reals, time.name, prev, curr,
-                                            _kernel_gaussian_chain)
+                                            _HOOKS["gaussian_chain"])
                 if res is not None:
                     Lam, eta, c, batch = res
                     w, P, s = info_to_sqrt(Lam, eta, c)
@@ -305,6 +403,62 @@ def register():
     prev_markov_gauss = eager.dispatch(MarkovProduct, fops.logaddexp, fops.add, sg, tv, step, names)
     eager.register(MarkovProduct, fops.LogaddexpOp, fops.AddOp, Gaussian, Variable, frozenset, frozenset)(gaussian_markov_rule)
     eager.register(MarkovProduct, fops.LogaddexpOp, fops.AddOp, GaussianMixture, Variable, frozenset, frozenset)(gaussian_markov_rule)
+
+    # ---- one level of the Gaussian scan: Contraction[Logaddexp, Add, frozenset, Gaussian | GaussianMixture x 2] (cnf.py:385-389)
+    def _parts_dict(t, g):
+        bints = [k for k, d in g.inputs.items() if d.dtype != "real"]
+        reals = [(k, d.num_elements) for k, d in g.inputs.items() if d.dtype == "real"]
+        return dict(w=g.white_vec, P=g.prec_sqrt, s=None if t is None else t.data, bints=bints,
+                    s_bints=[] if t is None else list(t.inputs), reals=reals)
+
+    def gaussian_contraction_rule(red_op, bin_op, reduced_vars, x, y):
+        px, py = _split_gaussian(x), _split_gaussian(y)
+        if px is not None and py is not None and len(reduced_vars) == 1:
+            (tx, gx), (ty, gy) = px, py
+            datas = [gx.white_vec, gx.prec_sqrt, gy.white_vec, gy.prec_sqrt] + [t.data for t in (tx, ty) if t is not None]
+            (rv,) = tuple(reduced_vars)
+            ok = (_HOOKS["fast_ok"](*datas) and _no_grad_needed(*datas) and rv.dtype == "real" and len(rv.output.shape) == 1
+                  and rv.output.num_elements <= 32
+                  and all(len(d.shape) == 1 for g in (gx, gy) for d in g.inputs.values() if d.dtype == "real")
+                  and all(t is None or all(d.dtype != "real" for d in t.inputs.values()) for t in (tx, ty)))
+            if ok:
+                # input order of the reference's result: the Gaussian sum lists the inputs of its left operand first
+                # (gaussian.py:1123-1124), and normalisation of (Tx + Gx) + (Ty + Gy) puts Gy on the left whenever a Tensor part is
+                # present (verified against the reference in tests/test_funsor_plugin.py); the scalar part follows the same batch
+                order = (gx, gy) if (tx is None and ty is None) else (gy, gx)
+                ginputs = OrderedDict()
+                for g in order:
+                    ginputs.update(g.inputs)
+                for t in (tx, ty):
+                    if t is not None:
+                        for k, d in t.inputs.items():
+                            ginputs.setdefault(k, d)
+                ginputs.pop(rv.name, None)
+                binputs = OrderedDict((k, d) for k, d in ginputs.items() if d.dtype != "real")
+                out_reals = [k for k, d in ginputs.items() if d.dtype == "real"]
+                ginputs = OrderedDict(list(binputs.items()) + [(k, ginputs[k]) for k in out_reals])
+                res = gaussian_contract_named(_parts_dict(tx, gx), _parts_dict(ty, gy), {rv.name}, {k: d.size for k, d in binputs.items()},
+                                              list(binputs), out_reals, _HOOKS["sqrt_to_info"], _HOOKS["gaussian_pair"], _HOOKS["info_to_sqrt"])
+                if res is not None:
+                    w, P, sc = res
+                    _STATE["calls"]["gaussian_contraction_fast"] += 1
+                    return Tensor(sc, binputs) + Gaussian(white_vec=w, prec_sqrt=P, inputs=ginputs)
+        _STATE["calls"]["gaussian_contraction_delegated"] += 1
+        return prev_gauss_contract[(type(x) is Gaussian, type(y) is Gaussian)](red_op, bin_op, reduced_vars, x, y)
+
+    sgx = Gaussian(white_vec=torch.zeros(2), prec_sqrt=torch.eye(2), inputs=OrderedDict(a=Reals[1], b=Reals[1]))
+    sgy = Gaussian(white_vec=torch.zeros(2), prec_sqrt=torch.eye(2), inputs=OrderedDict(b=Reals[1], c=Reals[1]))
+    stz = Tensor(torch.zeros(()), OrderedDict())
+    rvb = frozenset({Variable("b", Reals[1])})
+    with funsor.interpretations.lazy:
+        smx, smy = stz + sgx, stz + sgy
+    prev_gauss_contract = {}
+    for fx, sx_ in ((True, sgx), (False, smx)):
+        for fy, sy_ in ((True, sgy), (False, smy)):
+            prev_gauss_contract[(fx, fy)] = eager.dispatch(Contraction, fops.logaddexp, fops.add, rvb, sx_, sy_)
+    for tx_ in (Gaussian, GaussianMixture):
+        for ty_ in (Gaussian, GaussianMixture):
+            eager.register(Contraction, fops.LogaddexpOp, fops.AddOp, frozenset, tx_, ty_)(gaussian_contraction_rule)
 
     _STATE["registered"] = True
 

@@ -38,6 +38,27 @@ def sqrt_to_info(white_vec, prec_sqrt, scalar=None):
     return Lam, eta, c
 
 
+def info_to_sqrt(Lam, eta, c, rel_tol=0.0, return_rank=False):
+    """(Lam[..., n, n], eta[..., n], c[...]) -> (white_vec[..., n], prec_sqrt[..., n, n], scalar[...]) with P P' = Lam, P w = eta,
+    s - |w|^2/2 = c: the inverse of sqrt_to_info, so that results can be handed back as the reference's Gaussian(white_vec,
+    prec_sqrt) + Tensor (gaussian.py:419-498).  Lam may be rank deficient: diagonally pivoted Cholesky, one warp per element."""
+    for t in (Lam, eta, c):
+        _dev_f32(t, "gaussian element")
+    batch = Lam.shape[:-2]
+    n = Lam.shape[-1]
+    Lam, eta, c = Lam.contiguous(), eta.expand(batch + (n,)).contiguous(), c.expand(batch).contiguous()
+    N = int(torch.Size(batch).numel())
+    w = torch.empty(batch + (n,), dtype=torch.float32, device=Lam.device)
+    P = torch.empty(batch + (n, n), dtype=torch.float32, device=Lam.device)
+    s = torch.empty(batch, dtype=torch.float32, device=Lam.device)
+    rank = torch.empty(batch, dtype=torch.int32, device=Lam.device) if return_rank else None
+    lib = _lib.load()
+    with torch.cuda.device(Lam.device):
+        check(lib.fb2_gaussian_info_to_sqrt_f32(Lam.data_ptr(), eta.data_ptr(), c.data_ptr(), N, n, float(rel_tol), w.data_ptr(),
+                                                P.data_ptr(), s.data_ptr(), _ptr(rank), _stream()))
+    return (w, P, s, rank) if return_rank else (w, P, s)
+
+
 def gaussian_pair_combine(x, y):
     """Contraction[logaddexp, add] of two chain elements x over (a;b) and y over (b;c) (cnf.py:385-389).
     x, y: tuples (Lam[..., 2D, 2D], eta[..., 2D], c[...]) with identical batch shapes."""

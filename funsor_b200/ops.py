@@ -85,7 +85,17 @@ def semiring_matmul(sum_op, prod_op, x, y, want_argmax=False):
 
     Mirrors the eager Contraction of two Tensors that one scan level performs (cnf.py:335-379 for
     (logaddexp, add); cnf.py:312-324 for (max, add)).  With want_argmax (max only) also returns the
-    first maximising k as int32 (approximations.py:115-127)."""
+    first maximising k as int32 (approximations.py:115-127).  Differentiable (autograd.SemiringMatmul) when an
+    operand requires grad."""
+    from . import autograd as ag
+
+    if not want_argmax and ag.needs_grad(x, y):
+        semiring_id(sum_op, prod_op)
+        return ag.SemiringMatmul.apply(sum_op, x, y)
+    return _semiring_matmul_raw(sum_op, prod_op, x.detach(), y.detach(), want_argmax)
+
+
+def _semiring_matmul_raw(sum_op, prod_op, x, y, want_argmax=False):
     semi = semiring_id(sum_op, prod_op)
     _dev_f32(x, "x"), _dev_f32(y, "y")
     if x.dim() < 2 or y.dim() < 2 or x.shape[-1] != y.shape[-2]:
@@ -116,13 +126,21 @@ def semiring_matmul(sum_op, prod_op, x, y, want_argmax=False):
 # ----------------------------------------------------------------------------------------- a1 - a4
 def sequential_sum_product(sum_op, prod_op, trans, time=-3):
     """Chain product over the `time` dim of trans[..., T, S, S] (prev = dim -2, curr = dim -1), in the
-    reference's balanced-tree order (sum_product.py:690-701).  Returns [..., S, S]."""
+    reference's balanced-tree order (sum_product.py:690-701).  Returns [..., S, S].  When `trans` requires grad the
+    same tree is evaluated level by level on differentiable semiring matmuls (autograd.chain_tree)."""
     semi = semiring_id(sum_op, prod_op)
     _dev_f32(trans, "trans")
     if trans.dim() < 3 or trans.shape[-1] != trans.shape[-2]:
         raise ValueError("trans must be [..., T, S, S], got {}".format(tuple(trans.shape)))
     if time not in (-3, trans.dim() - 3):
         trans = trans.movedim(time, -3)
+    from . import autograd as ag
+
+    if ag.needs_grad(trans):
+        if trans.shape[-3] < 1:
+            raise ValueError("time dimension must be non-empty")
+        return ag.chain_tree(sum_op, trans)
+    trans = trans.detach()
     batch = trans.shape[:-3]
     T, S = trans.shape[-3], trans.shape[-1]
     if T < 1:
@@ -205,7 +223,17 @@ def _hmm_args(init, A, obs):
 
 def hmm_forward(init, A, obs, sum_op="logaddexp", return_alpha=False):
     """DiscreteHMM.log_prob (hmm.py:129-135) without materialising trans + obs:
-    returns (+)_{paths} init[z0] (x) prod_t (A[z_{t-1}, z_t] (x) obs[t, z_t])  as [B]."""
+    returns (+)_{paths} init[z0] (x) prod_t (A[z_{t-1}, z_t] (x) obs[t, z_t])  as [B].
+    Differentiable in (init, A, obs): the backward pass is one forward-backward pass (autograd.HmmForward)."""
+    from . import autograd as ag
+
+    if not return_alpha and ag.needs_grad(init, A, obs):
+        _hmm_args(init, A, obs)  # argument validation before autograd sees them
+        return ag.HmmForward.apply(sum_op, init, A, obs)
+    return _hmm_forward_raw(None if init is None else init.detach(), A.detach(), obs.detach(), sum_op, return_alpha)
+
+
+def _hmm_forward_raw(init, A, obs, sum_op="logaddexp", return_alpha=False):
     semi = semiring_id(sum_op)
     init_t, init_sb, A, a_sb, a_st, obs, B, T, S = _hmm_args(init, A, obs)
     out = torch.empty((B,), dtype=torch.float32, device=obs.device)

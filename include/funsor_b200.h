@@ -133,6 +133,12 @@ int fb2_chain_adjoint_f32(int semiring, const float* trans, const int64_t trans_
  */
 int fb2_gaussian_sqrt_to_info_f32(const float* w, const float* P, const float* s, int64_t N, int32_t dim,
                                   int32_t rank, float* Lam, float* eta, float* c, void* stream);
+/* info_to_sqrt : the way back, (Lam, eta, c) -> (white_vec w[N,dim], prec_sqrt P[N,dim,dim], scalar s[N]) with P P' = Lam, P w = eta,
+ *                s - |w|^2/2 = c, so that a rule can hand funsor a Gaussian(white_vec, prec_sqrt) (gaussian.py:419-498).  Lam is positive
+ *                SEMI-definite in general: diagonally pivoted Cholesky, columns beyond the numerical rank (remaining diagonal
+ *                <= rel_tol * max diagonal; rel_tol <= 0 selects dim * 1.2e-7) are zero.  rank (nullable) int32 [N]. */
+int fb2_gaussian_info_to_sqrt_f32(const float* Lam, const float* eta, const float* c, int64_t N, int32_t dim, float rel_tol,
+                                  float* w, float* P, float* s, int32_t* rank, void* stream);
 int fb2_gaussian_pair_combine_f32(const float* Lx, const float* ex, const float* cx, int64_t x_stride,
                                   const float* Ly, const float* ey, const float* cy, int64_t y_stride,
                                   int64_t n0, int64_t n1, int64_t x_s0, int64_t y_s0, int32_t D, float* Lo,

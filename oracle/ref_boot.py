@@ -1,7 +1,8 @@
 """Test infrastructure: import the UNMODIFIED reference (funsor 0.4.8) from
 /root/reference in the build container, to pin the oracle and to generate the
 golden fixtures under tests/golden/.  /root/reference does not exist on the GPU
-box, so nothing that runs there may import this module.
+box; there the same unmodified package is found under baseline/_ref (installed with pip --target,
+git-ignored) and is used by the `-m gpu` plugin tests and by `bench.py --impl reference` only.
 
 What is stubbed and why:
   * multipledispatch / makefun / opt_einsum: absent third-party deps -> oracle/shims/.
@@ -14,8 +15,12 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("FUNSOR_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "shims")
+# Where the unmodified reference lives: the source tree in the build container, or the copy that
+# `pip install --no-deps --target baseline/_ref` made of it (git-ignored; it travels to the GPU box).
+_CANDIDATES = [os.environ.get("FUNSOR_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+REFERENCE_ROOT = next((p for p in _CANDIDATES if p and os.path.isdir(os.path.join(p, "funsor"))), "/root/reference")
 
 
 def available():

@@ -186,7 +186,7 @@ def test_gaussian_markov_named_matches_reference_scan(funsor, order, T, D):
     from funsor.terms import Variable
     from funsor.testing import random_gaussian
 
-    from funsor_b200.funsor_plugin import gaussian_markov_named, info_to_sqrt
+    from funsor_b200.funsor_plugin import gaussian_markov_named
 
     torch.manual_seed(3)
     doms = dict(b=Bint[2], time=Bint[T], prev=Reals[D], curr=Reals[D])
@@ -201,14 +201,14 @@ def test_gaussian_markov_named_matches_reference_scan(funsor, order, T, D):
     assert torch.allclose(eta, weta, rtol=1e-8, atol=1e-8)
     assert torch.allclose(c, wc, rtol=1e-8, atol=1e-8)
     # and back to the reference's representation: the (w, P, s) triple must describe the same function
-    w, P, s = info_to_sqrt(Lam, eta, c)
+    w, P, s = _np_info_to_sqrt(Lam, eta, c)  # the oracle's twin of fb2_gaussian_info_to_sqrt_f32
     assert torch.allclose(P @ P.transpose(-1, -2), wLam, rtol=1e-7, atol=1e-7)
     assert torch.allclose((P @ w[..., None])[..., 0], weta, rtol=1e-6, atol=1e-6)
     assert torch.allclose(s - 0.5 * (w * w).sum(-1), wc, rtol=1e-7, atol=1e-7)
 
 
 def test_info_to_sqrt_handles_singular_precision(funsor):
-    from funsor_b200.funsor_plugin import info_to_sqrt
+    info_to_sqrt = _np_info_to_sqrt
 
     torch.manual_seed(4)
     A = torch.randn(3, 6, 2, dtype=torch.float64)  # rank 2 of 6
@@ -272,3 +272,207 @@ def test_plugin_sequential_sum_product_function(funsor):
     got = funsor_plugin.sequential_sum_product(ops.logaddexp, ops.add, g, tv, {"prev": "curr"})
     for x, y in zip(_info_of(funsor, want, ["prev", "curr"], 2), _info_of(funsor, got, ["prev", "curr"], 2)):
         assert torch.allclose(x, y, rtol=1e-9, atol=1e-9)
+
+
+# ------------------------------------------------------------------ the rules' FAST branches inside the unmodified reference
+# The kernels cannot run in the CPU container, so the entry points the rules call are replaced by oracle stand-ins
+# (funsor_plugin.set_hooks); everything else -- pattern matching, named-dimension bookkeeping, input order, Subs, cons-hashing,
+# AdjointTape -- is the code that runs on the GPU box, where tests/test_gpu_funsor.py repeats these cases with the real kernels.
+def _np_sqrt_to_info(w, P, s):
+    from oracle import gaussian_ref as G
+
+    return tuple(torch.from_numpy(np.asarray(a)) for a in G.sqrt_to_info(w.double().numpy(), P.double().numpy(), s.double().numpy()))
+
+
+def _np_pair(X, Y):
+    from oracle import gaussian_ref as G
+
+    D = X[0].shape[-1] // 2
+    out = G.info_pair_combine(tuple(t.numpy() for t in X), tuple(t.numpy() for t in Y), D)
+    return tuple(torch.from_numpy(np.asarray(a)) for a in out) + (None,)
+
+
+def _np_info_to_sqrt(Lam, eta, c):
+    from oracle import gaussian_ref as G
+
+    return tuple(torch.from_numpy(np.asarray(a)) for a in G.info_to_sqrt(Lam.numpy(), eta.numpy(), c.numpy()))
+
+
+import numpy as np  # noqa: E402
+
+
+@pytest.fixture
+def fast(funsor):
+    from funsor_b200 import funsor_plugin
+
+    funsor_plugin.register()
+    funsor_plugin.set_hooks(fast_ok=lambda *d: all(isinstance(t, torch.Tensor) for t in d), matmul=torch_matmul, chain=torch_chain,
+                            gaussian_chain=_oracle_gaussian_chain, sqrt_to_info=_np_sqrt_to_info, gaussian_pair=_np_pair,
+                            info_to_sqrt=_np_info_to_sqrt)
+    funsor_plugin.stats(reset=True)
+    yield funsor_plugin
+    funsor_plugin.set_hooks()
+
+
+def _both(plugin, build):
+    """build() evaluated by the stock rules (hooks off: CPU tensors delegate) and by the fast branches; fresh tensors each time
+    because funsor cons-hashes terms by tensor identity."""
+    saved = dict(plugin._HOOKS)
+    plugin.set_hooks()
+    want = build()
+    plugin.set_hooks(**saved)
+    plugin.stats(reset=True)
+    got = build()
+    return want, got, plugin.stats()
+
+
+@pytest.mark.parametrize("sname", ["logaddexp", "max"])
+def test_fast_tensor_rules_inside_reference(funsor, fast, sname):
+    import funsor.ops as ops
+    from funsor.adjoint import AdjointTape
+    from funsor.cnf import Contraction
+    from funsor.domains import Bint
+    from funsor.einsum import einsum
+    from funsor.sum_product import MarkovProduct, mixed_sequential_sum_product, naive_sequential_sum_product, sequential_sum_product, sum_product
+    from funsor.tensor import Tensor
+    from funsor.terms import Variable
+    from funsor.testing import assert_close
+
+    op = ops.logaddexp if sname == "logaddexp" else ops.max
+    g = torch.Generator().manual_seed(7)
+    B, T, S = 2, 7, 3
+    d_trans, d_init = torch.randn(B, T, S, S, generator=g), torch.randn(B, S, generator=g)
+    d_x, d_y = torch.randn(B, 4, 5, generator=g), torch.randn(5, 3, B, generator=g)
+    tv = Variable("time", Bint[T])
+
+    def tensors():
+        trans = Tensor(d_trans.clone(), OrderedDict(b=Bint[B], time=Bint[T], prev=Bint[S], curr=Bint[S]))
+        init = Tensor(d_init.clone(), OrderedDict(b=Bint[B], prev=Bint[S]))
+        x = Tensor(d_x.clone(), OrderedDict(b=Bint[B], i=Bint[4], k=Bint[5]))
+        y = Tensor(d_y.clone(), OrderedDict(k=Bint[5], j=Bint[3], b=Bint[B]))
+        return trans, init, x, y
+
+    def contraction():
+        _, _, x, y = tensors()
+        return Contraction(op, ops.add, frozenset({Variable("k", Bint[5])}), x, y)
+
+    def markov():
+        trans = tensors()[0]
+        return MarkovProduct(op, ops.add, trans, tv, {"prev": "curr"})
+
+    def seq(fn, **kw):
+        def build():
+            trans = tensors()[0]
+            return fn(op, ops.add, trans, tv, {"prev": "curr"}, **kw)
+        return build
+
+    def hmm_expression():  # pyro/hmm.py:128-137
+        trans, init, _, _ = tensors()
+        r = sequential_sum_product(op, ops.add, trans, tv, {"prev": "curr"})
+        return (init + r.reduce(op, "curr")).reduce(op, "prev")
+
+    def front_door():  # funsor.einsum.einsum routes by backend NAME to the semiring (einsum/__init__.py:13-28)
+        _, _, x, y = tensors()
+        backend = "pyro.ops.einsum.torch_log" if sname == "logaddexp" else "pyro.ops.einsum.torch_map"
+        xs = Tensor(x.data[0], OrderedDict(a=Bint[4], b=Bint[5]))
+        ys = Tensor(y.data[..., 0], OrderedDict(b=Bint[5], c=Bint[3]))
+        return einsum("ab,bc->ac", xs, ys, backend=backend)
+
+    def planner():  # the planner builds the expression lazily; the optimizer turns it into binary Contractions (einsum/__init__.py:126-128)
+        from funsor.interpretations import lazy
+        from funsor.optimizer import apply_optimizer
+
+        _, _, x, y = tensors()
+        z = Tensor(d_init.clone()[:, :3], OrderedDict(b=Bint[B], j=Bint[3]))
+        with lazy:
+            expr = sum_product(op, ops.add, [x, y, z], frozenset({"k", "j", "b"}), frozenset({"b"}))
+        return apply_optimizer(expr)
+
+    def adjoint():
+        trans = tensors()[0]
+        with AdjointTape() as tape:
+            z = sequential_sum_product(op, ops.add, trans, tv, {"prev": "curr"})
+            z = z.reduce(op, frozenset({"prev", "curr"}))
+        return tape.adjoint(op, ops.add, z, (trans,), batch_vars=frozenset({Variable("b", Bint[B])}))[trans]
+
+    cases = {"contraction": (contraction, "contraction_fast"), "markov": (markov, "markov_fast"),
+             "sequential": (seq(sequential_sum_product), "contraction_fast"), "naive": (seq(naive_sequential_sum_product), None),  # Binary + Reduce under eager (sum_product.py:644-648): never a Contraction
+             "mixed": (seq(mixed_sequential_sum_product, num_segments=3), "contraction_fast"), "hmm": (hmm_expression, "contraction_fast"),
+             "einsum": (front_door, "contraction_fast"), "sum_product": (planner, "contraction_fast"), "adjoint": (adjoint, "contraction_fast")}
+    for name, (build, counter) in cases.items():
+        want, got, st = _both(fast, build)
+        assert counter is None or st[counter] > 0, (name, st)
+        assert isinstance(got, Tensor), (name, type(got))
+        assert_close(got, want, atol=1e-9, rtol=1e-9)
+
+
+def _same_gaussian_function(funsor, got, want, names, D, tol):
+    """`Tensor + Gaussian` results describe the same function: same inputs in the same order, same (Lam, eta) and same value at
+    x = 0.  (white_vec / prec_sqrt / the Tensor term are representation dependent: a rank-2D pivoted-Cholesky root here, the
+    uncompressed rank-r root in the reference, whose |w|^2 differs; testing.py:149-153 compares info_vec and precision.)"""
+    assert type(got) is type(want) and list(got.inputs.items()) == list(want.inputs.items()), (got.inputs, want.inputs)
+    assert [type(t) for t in got.terms] == [type(t) for t in want.terms]
+    assert [list(t.inputs.items()) for t in got.terms] == [list(t.inputs.items()) for t in want.terms]
+    for a, b in zip(_info_of(funsor, got, names, D), _info_of(funsor, want, names, D)):
+        assert torch.allclose(a, b, rtol=tol, atol=tol), (a - b).abs().max()
+
+
+@pytest.mark.parametrize("T,D", [(2, 1), (5, 2), (8, 3), (11, 2)])
+def test_fast_gaussian_contraction_rule_inside_reference(funsor, fast, T, D):
+    """sequential_sum_product over Gaussian chain elements, called directly as pyro/hmm.py:269 does: every level reaches the
+    Contraction[.., Gaussian|GaussianMixture x 2] rule; values AND input order must be the reference's (assert_close compares
+    the OrderedDicts, funsor/testing.py:132)."""
+    import funsor.ops as ops
+    from funsor.domains import Bint, Reals
+    from funsor.gaussian import Gaussian
+    from funsor.sum_product import sequential_sum_product
+    from funsor.terms import Variable
+    from funsor.testing import assert_close, random_gaussian
+
+    torch.manual_seed(8)
+    proto = random_gaussian(OrderedDict(b=Bint[2], time=Bint[T], prev=Reals[D], curr=Reals[D]))
+
+    def build():
+        g = Gaussian(white_vec=proto.white_vec.clone(), prec_sqrt=proto.prec_sqrt.clone(), inputs=proto.inputs)
+        return sequential_sum_product(ops.logaddexp, ops.add, g, Variable("time", Bint[T]), {"prev": "curr"})
+
+    want, got, st = _both(fast, build)
+    assert st["gaussian_contraction_fast"] > 0 and st["gaussian_contraction_delegated"] == 0, st
+    _same_gaussian_function(funsor, got, want, ["prev", "curr"], D, 1e-7)
+
+
+def test_fast_gaussian_hmm_expression_inside_reference(funsor, fast):
+    """pyro/hmm.py:258-272 with rank-deficient Kalman elements (rank D + O < 2D) and a Tensor part on the elements."""
+    import importlib.util
+    import os
+
+    import funsor.ops as ops
+    from funsor.domains import Bint
+    from funsor.sum_product import sequential_sum_product
+    from funsor.tensor import Tensor
+    from funsor.terms import Variable
+    from funsor.testing import assert_close
+
+    spec = importlib.util.spec_from_file_location("_ref_convert", os.path.join(ref_boot.REFERENCE_ROOT, "funsor/pyro/convert.py"))
+    conv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(conv)
+    MVN = torch.distributions.MultivariateNormal
+    torch.manual_seed(9)
+    B, T, D, O = 2, 9, 4, 1
+    F = 0.9 * torch.linalg.qr(torch.randn(B, D, D))[0]
+    H = torch.randn(B, D, O)
+    y = torch.randn(B, T, O)
+    ex = lambda t: t.unsqueeze(1).expand((B, T) + t.shape[1:])  # noqa: E731
+
+    def build():
+        trans = conv.matrix_and_mvn_to_funsor(ex(F).clone(), MVN(torch.zeros(B, T, D), scale_tril=torch.eye(D).expand(B, T, D, D).clone()),
+                                              ("time",), "state", "state(time=1)")
+        obs = conv.matrix_and_mvn_to_funsor(ex(H).clone(), MVN(torch.zeros(B, T, O), scale_tril=torch.eye(O).expand(B, T, O, O).clone()),
+                                            ("time",), "state(time=1)", "value")
+        value = Tensor(y.clone(), OrderedDict([("_pyro_dim_-1", Bint[B]), ("time", Bint[T])]))
+        elem = trans + obs(value=value)
+        return sequential_sum_product(ops.logaddexp, ops.add, elem, Variable("time", Bint[T]), {"state": "state(time=1)"})
+
+    want, got, st = _both(fast, build)
+    assert st["gaussian_contraction_fast"] > 0, st
+    _same_gaussian_function(funsor, got, want, ["state", "state(time=1)"], D, 1e-6)
