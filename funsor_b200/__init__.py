@@ -13,6 +13,7 @@ entry point raises.
 """
 from . import _lib  # noqa: F401
 from .ops import (  # noqa: F401
+    async_status,
     chain_adjoint,
     hmm_chunk_summary,
     hmm_chunk_summary_tree,

@@ -7,7 +7,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfunsor_b200.so")
 
-OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_NO_DEVICE, ERR_NUMERIC = range(7)
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_NO_DEVICE, ERR_NUMERIC, ERR_ABORTED = range(8)
 SEMIRING_LOG, SEMIRING_MAX = 0, 1
 
 
@@ -21,6 +21,10 @@ class Fb2Unsupported(Fb2Error, NotImplementedError):
     pass
 
 
+class Fb2Aborted(Fb2Error):
+    """an earlier asynchronous dataflow pass on this device gave up: its outputs are NaN (include/funsor_b200.h, fb2_async_status)"""
+
+
 _fp = c_void_p  # device/host pointers are passed as integers
 _i64p = POINTER(c_int64)
 
@@ -29,6 +33,7 @@ SIGNATURES = {
     "fb2_version": (c_int, []),
     "fb2_status_string": (c_char_p, [c_int]),
     "fb2_last_error": (c_char_p, []),
+    "fb2_async_status": (c_int, [c_int]),
     "fb2_device_query": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
     "fb2_semiring_matmul_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
     "fb2_semiring_matmul_f32": (c_int, [c_int, _fp, _i64p, _fp, _i64p, _fp, _fp, c_int64, c_int64, c_int32, c_int32, c_int32, _fp, c_size_t, c_void_p]),
@@ -91,6 +96,9 @@ def check(status):
         raise Fb2Unsupported(status, msg)
     if status == ERR_NUMERIC:
         raise ValueError("funsor_b200: " + msg)
+    if status == ERR_ABORTED:
+        lib.fb2_async_status(1)  # reported once; the caller decides whether to recompute
+        raise Fb2Aborted(status, msg)
     raise Fb2Error(status, msg)
 
 

@@ -18,6 +18,10 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
                          void* workspace, size_t workspace_bytes, cudaStream_t stream, const unsigned* ready_flags,
                          int64_t rows_per_chunk, int cpo, float* rows_out, double* row_offset);
 
+int hmm_flow_async_status(int clear);
+// hmm_scan.cu
+void hmm_force_cooperative_kernels(int on);
+
 static thread_local char g_err[512] = "";
 static thread_local int64_t g_launches = 0;
 
@@ -91,11 +95,17 @@ extern "C" const char* fb2_status_string(int status) {
         case FB2_ERR_WORKSPACE: return "workspace too small or misaligned";
         case FB2_ERR_NO_DEVICE: return "no sm_100 CUDA device (no CPU fallback)";
         case FB2_ERR_NUMERIC: return "numerical failure (non-positive pivot)";
+        case FB2_ERR_ABORTED: return "an earlier asynchronous dataflow pass aborted (fb2_async_status)";
         default: return "unknown status";
     }
 }
 
 extern "C" const char* fb2_last_error(void) { return g_err; }
+
+extern "C" int fb2_async_status(int clear) {
+    if (check_device() != FB2_OK) return 0;
+    return hmm_flow_async_status(clear);
+}
 
 extern "C" int fb2_device_query(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin_bytes) {
     int count = 0;
@@ -197,18 +207,26 @@ extern "C" int fb2_hmm_forward_f32_host(int semiring, const float* init, int64_t
             FB2_CUDA(cudaMemcpyAsync(logZ, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
             FB2_CUDA(cudaStreamSynchronize(s));
             FB2_CUDA(cudaStreamSynchronize(g_arena.copy_stream));
-            return FB2_OK;
+            if (!hmm_flow_async_status(1)) return FB2_OK;
+            // the pass gave up (a chunk never landed in time, or its CTAs were starved): obs is resident now -> recompute below
+        } else {
+            FB2_CUDA(cudaStreamSynchronize(g_arena.copy_stream));  // declined: obs is resident now, fall through to the plain call
+            if (st != FB2_ERR_UNSUPPORTED) return st;
         }
-        FB2_CUDA(cudaStreamSynchronize(g_arena.copy_stream));  // declined: obs is resident now, fall through to the plain call
-        if (st != FB2_ERR_UNSUPPORTED) return st;
     } else {
         FB2_CUDA(cudaMemcpyAsync(d_obs, obs, n_obs * 4, cudaMemcpyHostToDevice, s));
     }
-    st = fb2_hmm_forward_f32(semiring, d_init, init_sb, d_A, a_sb, a_st, d_obs, B, T, S, d_out, nullptr, d_ws, ws, s);
-    if (st != FB2_OK) return st;
-    FB2_CUDA(cudaMemcpyAsync(logZ, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    FB2_CUDA(cudaStreamSynchronize(s));
-    return FB2_OK;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        hmm_force_cooperative_kernels(attempt);  // second attempt: kernels whose co-residency the driver guarantees
+        st = fb2_hmm_forward_f32(semiring, d_init, init_sb, d_A, a_sb, a_st, d_obs, B, T, S, d_out, nullptr, d_ws, ws, s);
+        hmm_force_cooperative_kernels(0);
+        if (st != FB2_OK) return st;
+        FB2_CUDA(cudaMemcpyAsync(logZ, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+        FB2_CUDA(cudaStreamSynchronize(s));
+        if (!hmm_flow_async_status(1)) return FB2_OK;
+    }
+    set_error("dataflow pass aborted and the cooperative retry did not complete");
+    return FB2_ERR_ABORTED;
 }
 
 extern "C" int fb2_chain_product_f32_host(int semiring, const float* trans, int64_t B, int64_t T, int32_t S, float* out) {

@@ -395,6 +395,14 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
             do {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ready_flags + c) : "memory");
             } while (v == 0 && clock64() - start < 20 * FLOW_SPIN_LIMIT);
+            if (v == 0) {  // the host-to-device copy of this chunk never landed: the rows about to be read are stale -> poison the pass
+                if (atomicCAS(p.abort_flag + 1, 0, 4) == 0) {
+                    p.abort_flag[2] = (int)blockIdx.x;
+                    p.abort_flag[3] = tid;
+                    p.abort_flag[4] = (int)row;
+                }
+                atomicExch(p.abort_flag, 1);
+            }
             chunk_seen = c;
         };
 
@@ -756,6 +764,14 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_direct_forward(FlowArgs p
                 do {
                     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ready_flags + ch) : "memory");
                 } while (v == 0 && clock64() - start < 20 * FLOW_SPIN_LIMIT);
+                if (v == 0) {  // see hmm_flow_forward: a chunk that never landed poisons the pass instead of being read stale
+                    if (atomicCAS(p.abort_flag + 1, 0, 4) == 0) {
+                        p.abort_flag[2] = (int)blockIdx.x;
+                        p.abort_flag[3] = tid;
+                        p.abort_flag[4] = (int)row;
+                    }
+                    atomicExch(p.abort_flag, 1);
+                }
                 chunk_seen = ch;
             };
             auto publish = [&](unsigned t_stamp, float u, int E15, bool zero) {
@@ -1550,9 +1566,10 @@ __global__ void flow_colmax(const float* A, int S, int Sp, float* cA, int transp
 
 // logZ[b] = log sum_j u[b,j] 2^{E[b,j/8]}  (one warp per chain, double accumulation)
 __global__ void flow_finalise(const float* fin_u, const int* fin_e, const int* abort_flag, int64_t B, int S, int Sp,
-                              float* logZ, double* logZ_d) {
+                              float* logZ, double* logZ_d, int* sticky) {
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
+    if (sticky && blockIdx.x == 0 && threadIdx.x == 0 && *abort_flag) atomicExch_system(sticky, abort_flag[1] ? abort_flag[1] : 9);
     if (b >= B) return;
     const int ngrp = Sp / 8;
     int emax = INT_MIN;
@@ -1744,9 +1761,10 @@ int flow_padded_states(int S);
 
 // rows_out[c, j] = log(final message of chain c)[j] - row_offset[c],  row_offset[c] = ln2 * (largest block exponent of chain c)
 __global__ void flow_rows_out(const float* fin_u, const int* fin_e, const int* abort_flag, int64_t C, int S, int Sp, float* rows,
-                              double* row_offset) {
+                              double* row_offset, int* sticky) {
     const int64_t c = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
+    if (sticky && blockIdx.x == 0 && threadIdx.x == 0 && *abort_flag) atomicExch_system(sticky, abort_flag[1] ? abort_flag[1] : 9);
     if (c >= C) return;
     const int ngrp = Sp / 8;
     int emax = INT_MIN;
@@ -1920,6 +1938,58 @@ int hmm_flow_forward_device(const float* init, int64_t init_sb, const float* A, 
 // set by hmm_flow_marginals_device around its two passes: take the two-tiles-per-warp variant (half the clusters) even for a
 // single chain group, so that the forward and the backward pass fit on the GPU side by side
 static thread_local int tl_force_wide = 0;
+// set by hmm_flow_marginals_device while it runs its two passes side by side: the pair is ONE unit of the per-device serialisation
+static thread_local int tl_in_pair = 0;
+
+// Per-device state of the dataflow kernels.
+//  * Every pass needs all of its CTAs co-resident (they spin on each other's packets).  cudaOccupancyMaxActiveClusters proves that
+//    for an otherwise empty GPU only, so two passes launched from different host threads / streams must not overlap: each pass
+//    waits (on the device, cudaStreamWaitEvent -- no host synchronisation) for the completion event of the previous pass on this
+//    device and records its own.  Foreign kernels can still delay residency; they end, and the spin limit (~1 s) is far beyond that.
+//  * A pass that does give up (lost co-residency, a host-to-device chunk that never landed) poisons its outputs with NaN and raises
+//    a sticky word in mapped host memory: fb2_async_status() reports it, the next dataflow call on the device refuses to run until
+//    it has been read, and the host-buffer entry points (which synchronise anyway) retry on the cooperative kernel.
+struct FlowDevice {
+    std::mutex mu;
+    cudaEvent_t last_done = nullptr;
+    bool has_last = false;
+    int* sticky_host = nullptr;
+    int* sticky_dev = nullptr;
+};
+static int flow_device(FlowDevice** out) {
+    static FlowDevice table[64];
+    int dev = 0;
+    FB2_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return FB2_ERR_UNSUPPORTED;
+    FlowDevice& d = table[dev];
+    std::lock_guard<std::mutex> lock(d.mu);
+    if (!d.last_done) {
+        FB2_CUDA(cudaEventCreateWithFlags(&d.last_done, cudaEventDisableTiming));
+        FB2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&d.sticky_host), sizeof(int), cudaHostAllocMapped));
+        *d.sticky_host = 0;
+        FB2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d.sticky_dev), d.sticky_host, 0));
+    }
+    *out = &d;
+    return FB2_OK;
+}
+static void flow_serialise_begin(FlowDevice* d, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(d->mu);
+    if (d->has_last) cudaStreamWaitEvent(stream, d->last_done, 0);
+}
+static void flow_serialise_end(FlowDevice* d, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(d->mu);
+    cudaEventRecord(d->last_done, stream);
+    d->has_last = true;
+}
+// 0 = no dataflow pass on the current device has aborted since the last clear; otherwise the kind of the first wait that gave up
+// (1 packets, 2/3 partials, 4 input chunk, 9 unknown).
+int hmm_flow_async_status(int clear) {
+    FlowDevice* d = nullptr;
+    if (flow_device(&d) != FB2_OK) return 0;
+    const int v = *static_cast<volatile int*>(d->sticky_host);
+    if (clear) *static_cast<volatile int*>(d->sticky_host) = 0;
+    return v;
+}
 
 int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, const float* obs, int64_t obs_T, int64_t B, int64_t T, int S,
                          float* logZ, double* logZ_d, float* hist_u, int* hist_e, int64_t hist_T, int transpose, int reverse,
@@ -1932,6 +2002,16 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
     }
     const int Sp = fs.k16 * 128;
     const int64_t groups = ceil_div(B, FLOW_CHAINS);
+    FlowDevice* dv = nullptr;
+    {
+        const int dst = flow_device(&dv);
+        if (dst != FB2_OK) return dst;
+    }
+    if (const int kind = *static_cast<volatile int*>(dv->sticky_host)) {
+        set_error("an earlier dataflow pass on this device aborted (kind %d: its CTAs lost co-residency or an input chunk never arrived); "
+                  "its outputs are NaN.  Read and clear the condition with fb2_async_status(1) before launching another pass", kind);
+        return FB2_ERR_ABORTED;
+    }
     Arena arena(workspace, workspace_bytes);
     float* cA = arena.take<float>((size_t)Sp);
     unsigned long long* pkt = arena.take<unsigned long long>((size_t)FLOW_MAX_SETS * 2 * FLOW_CHAINS * Sp);
@@ -1944,6 +2024,7 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
         return FB2_ERR_WORKSPACE;
     }
     // stale packets must never carry a valid stamp: 0xFF.. = stamp 0xFFFF, overwritten after two steps
+    if (!tl_in_pair) flow_serialise_begin(dv, stream);
     FB2_CUDA(cudaMemsetAsync(pkt, 0xFF, (size_t)FLOW_MAX_SETS * 2 * FLOW_CHAINS * Sp * 8, stream));
     FB2_CUDA(cudaMemsetAsync(abort_flag, 0, 32, stream));
     flow_colmax<<<(unsigned)ceil_div(Sp, 128), 128, 0, stream>>>(A, S, Sp, cA, transpose);
@@ -1993,14 +2074,18 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
             st = (cl4 && cl4[0] == '1') ? flow_launch<8, 1, 4>(a, stream) : flow_launch<8, 2>(a, stream);
         }
     }
-    if (st != FB2_OK) return st;
+    if (st != FB2_OK) {
+        if (!tl_in_pair) flow_serialise_end(dv, stream);
+        return st;
+    }
     if (rows_out) {  // chunk summary: the final messages themselves, as rows relative to a float64 offset
-        flow_rows_out<<<(unsigned)ceil_div(B, 4), 128, 0, stream>>>(fin_u, fin_e, abort_flag, B, S, Sp, rows_out, row_offset);
+        flow_rows_out<<<(unsigned)ceil_div(B, 4), 128, 0, stream>>>(fin_u, fin_e, abort_flag, B, S, Sp, rows_out, row_offset, dv->sticky_dev);
         FB2_LAUNCH_CHECK();
     } else {
-        flow_finalise<<<(unsigned)ceil_div(B, 4), 128, 0, stream>>>(fin_u, fin_e, abort_flag, B, S, Sp, logZ, logZ_d);
+        flow_finalise<<<(unsigned)ceil_div(B, 4), 128, 0, stream>>>(fin_u, fin_e, abort_flag, B, S, Sp, logZ, logZ_d, dv->sticky_dev);
         FB2_LAUNCH_CHECK();
     }
+    if (!tl_in_pair) flow_serialise_end(dv, stream);
     if (getenv("FB2_DEBUG")) {
         int h[8];
         FB2_CUDA(cudaStreamSynchronize(stream));
@@ -2056,12 +2141,11 @@ struct SideStream {
     cudaEvent_t fork = nullptr, join = nullptr;
 };
 static int side_stream_for_current_device(SideStream** out) {
-    static SideStream table[64];
-    static std::mutex mu;
+    // per host thread: the fork / join events belong to one call at a time (two threads sharing them could wait on each other's fork)
+    static thread_local SideStream table[64];
     int dev = 0;
     FB2_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return FB2_ERR_UNSUPPORTED;
-    std::lock_guard<std::mutex> lock(mu);
     SideStream& s = table[dev];
     if (!s.stream) {
         FB2_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -2110,16 +2194,23 @@ int hmm_flow_marginals_device(const float* init, int64_t init_sb, const float* A
         SideStream* side = nullptr;
         st = side_stream_for_current_device(&side);
         if (st != FB2_OK) return st;
+        FlowDevice* dv = nullptr;
+        st = flow_device(&dv);
+        if (st != FB2_OK) return st;
+        flow_serialise_begin(dv, stream);
         FB2_CUDA(cudaEventRecord(side->fork, stream));
         FB2_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
         tl_force_wide = fs.k16 == 4;
+        tl_in_pair = 1;
         st = hmm_flow_pass_device(obs + (T - 1) * (int64_t)S, T * (int64_t)S, A, obs, T, B, T - 1, S, zb, zb_d, uw, ew, T, 1, 1, rest + per_pass,
                                   rest_bytes - per_pass, side->stream);
         if (st == FB2_OK) st = hmm_flow_pass_device(init, init_sb, A, obs, T, B, T, S, logZ, z_d, ua, ea, T, 0, 0, rest, per_pass, stream);
         tl_force_wide = 0;
+        tl_in_pair = 0;
         // join even on failure so that the caller's stream never runs ahead of the side stream
         cudaEventRecord(side->join, side->stream);
         cudaStreamWaitEvent(stream, side->join, 0);
+        flow_serialise_end(dv, stream);
         if (st != FB2_OK) return st;
     } else {
         st = hmm_flow_pass_device(init, init_sb, A, obs, T, B, T, S, logZ, z_d, ua, ea, T, 0, 0, rest, rest_bytes, stream);

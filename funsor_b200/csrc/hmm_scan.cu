@@ -42,9 +42,12 @@ static bool stream_disabled() {
     const char* e = getenv("FB2_DISABLE_STREAM");
     return e && e[0] == '1';
 }
+static thread_local int tl_force_coop = 0;
+// retry path of the host-buffer entry points after an aborted dataflow pass: only kernels launched cooperatively
+void hmm_force_cooperative_kernels(int on) { tl_force_coop = on; }
 static bool flow_disabled() {
     const char* e = getenv("FB2_DISABLE_FLOW");
-    return e && e[0] == '1';
+    return tl_force_coop || (e && e[0] == '1');
 }
 
 struct HmmArgs {

@@ -147,6 +147,8 @@ def hmm_marginals_time_sharded(init, A, obs_chunk, group=None, summary_fn=None, 
     beta_out = fold_right(torch.zeros_like(init, dtype=torch.float64), allm, rank)
     a_off = alpha_in.amax(-1, keepdim=True)
     b_off = beta_out.amax(-1, keepdim=True)
+    a_off = torch.where(torch.isfinite(a_off), a_off, torch.zeros_like(a_off))  # an all -inf boundary (impossible evidence) stays -inf
+    b_off = torch.where(torch.isfinite(b_off), b_off, torch.zeros_like(b_off))
     obs2 = obs_chunk.clone()
     obs2[:, -1, :] += (beta_out - b_off).to(obs_chunk.dtype)
     logZ_local, gamma = marginals_fn((alpha_in - a_off).to(obs_chunk.dtype), A, obs2)

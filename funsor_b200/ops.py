@@ -310,6 +310,7 @@ def hmm_posterior_sample(init, A, obs, num_samples=1, uniforms=None, generator=N
 def _recentre(M):
     """M[..., S, S] -> (M - max entry, max entry as float64): keeps the fp32 entries O(1)-O(100) whatever the chain length."""
     m = M.amax((-1, -2))
+    m = torch.where(torch.isfinite(m), m, torch.zeros_like(m))  # an all -inf product (impossible observation) stays -inf, not NaN
     return M - m[..., None, None], m.double()
 
 
@@ -410,6 +411,16 @@ def chain_adjoint(sum_op, prod_op, trans, init=None, final=None):
         check(lib.fb2_chain_adjoint_f32(semi, trans.data_ptr(), strides4(trans.stride()), _ptr(init_t), _ptr(final_t), B, T, S,
                                         Z.data_ptr(), adj.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
     return Z, adj
+
+
+def async_status(clear=True, raise_on_abort=True):
+    """After synchronising: did a dataflow pass on the current device give up while running (its outputs are then NaN)?
+    Returns the condition code (0 = none); with raise_on_abort raises _lib.Fb2Aborted instead of returning non-zero."""
+    lib = _lib.load()
+    kind = int(lib.fb2_async_status(1 if clear else 0))
+    if kind and raise_on_abort:
+        raise _lib.Fb2Aborted(_lib.ERR_ABORTED, "a dataflow pass aborted while running (kind {}): its outputs are NaN".format(kind))
+    return kind
 
 
 def launch_count(reset=False):

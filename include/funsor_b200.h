@@ -32,6 +32,7 @@ extern "C" {
 #define FB2_ERR_WORKSPACE 4        /* workspace too small or misaligned                      */
 #define FB2_ERR_NO_DEVICE 5        /* no sm_100 device: the product path fails loudly, no CPU fallback */
 #define FB2_ERR_NUMERIC 6          /* e.g. non-positive pivot: "Too little information to marginalize" (gaussian.py:897-901) */
+#define FB2_ERR_ABORTED 7          /* an earlier asynchronous dataflow pass on this device gave up (see fb2_async_status)      */
 
 /* semirings: (sum_op, prod_op) pairs of funsor/ops/builtin.py:266-292 that the path supports */
 #define FB2_SEMIRING_LOG 0 /* (ops.logaddexp, ops.add) */
@@ -40,6 +41,14 @@ extern "C" {
 int fb2_version(void);
 const char* fb2_status_string(int status);
 const char* fb2_last_error(void);
+/* Asynchronous failures.  The device-pointer entry points never synchronise, so a dataflow pass that gives up while running
+ * (its co-resident CTAs were starved by other work for ~1 s, or a host-to-device chunk of the *_host path never landed) cannot
+ * change the status of the call that launched it.  Such a pass (i) writes NaN to ALL of its outputs and (ii) raises a sticky
+ * per-device condition: fb2_async_status(clear) returns 0 if none is pending on the current device, otherwise a small positive
+ * code (which wait gave up), and clears it when `clear` is non-zero.  While the condition is pending every further dataflow
+ * launch on the device returns FB2_ERR_ABORTED.  Call it after synchronising the stream.  The *_host entry points (which
+ * synchronise themselves) check it and transparently recompute on the cooperative-launch kernel. */
+int fb2_async_status(int clear);
 /* Device facts the host side needs for grid sizing / roofline arithmetic. */
 int fb2_device_query(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin_bytes);
 

@@ -1,5 +1,6 @@
 // One-way latency of a store -> remote-SM load hand-over through L2 on B200, for the instruction variants the
 // dataflow kernel could use.  Block 0 and block `peer` bounce a counter; time per hop = elapsed / (2*iters).
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pingpong pingpong.cu   (the binary is not tracked)
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
