@@ -292,6 +292,33 @@ def register():
     if funsor.get_backend() != "torch":
         raise RuntimeError("funsor_b200 plugs into the torch backend: call funsor.set_backend('torch') first")
 
+    # ---- a12: the torch op registrations that allocate on the DEFAULT device (funsor/torch/ops.py:194, 201, 303-306, 311) break every
+    # CUDA expression that touches them: Slice / arange substitution in the scan (sum_product.py:692-698), AdjointTape.adjoint
+    # (adjoint.py:250), matrix_and_mvn_to_funsor (pyro/convert.py:284).  Same semantics, allocated on the operand's device.
+    @fops.new_arange.register(torch.Tensor)
+    def _new_arange(x, start, stop, step):
+        if step is not None:
+            return torch.arange(start, stop, step, device=x.device)
+        if stop is not None:
+            return torch.arange(start, stop, device=x.device)
+        return torch.arange(start, device=x.device)
+
+    @fops.new_eye.register(torch.Tensor)
+    def _new_eye(x, shape):
+        return torch.eye(shape[-1], dtype=x.dtype, device=x.device).expand(shape + (-1,))
+
+    @fops.triangular_inv.register(torch.Tensor)
+    def _triangular_inv(x, upper=False):
+        if x.size(-1) == 1:
+            return x.reciprocal()
+        return torch.linalg.solve_triangular(x, torch.eye(x.size(-1), dtype=x.dtype, device=x.device), upper=upper)
+
+    @fops.cholesky_inverse.register(torch.Tensor)
+    def _cholesky_inverse(x):
+        if x.dim() == 2:
+            return x.cholesky_inverse()
+        return torch.eye(x.size(-1), dtype=x.dtype, device=x.device).cholesky_solve(x)
+
     # ---- capture the handlers that are in force now, by dispatching on tiny sample terms
     sx = Tensor(torch.zeros(2, 2), OrderedDict(a=Bint[2], b=Bint[2]))
     sy = Tensor(torch.zeros(2, 2), OrderedDict(b=Bint[2], c=Bint[2]))
@@ -390,8 +417,20 @@ def register():
                     D = dict(reals)[prev]
                     binputs = OrderedDict((k, g.inputs[k]) for k in batch)
                     ginputs = binputs.copy()
-                    ginputs[prev] = Reals[D]
-                    ginputs[curr] = Reals[D]
+                    # order of the real inputs as the reference's scan leaves it: untouched for a single step; (prev, curr) after one
+                    # level of bare Gaussians (the Gaussian sum lists its left operand first, gaussian.py:1123-1124); (curr, prev) as
+                    # soon as the last level combined `Tensor + Gaussian` elements (see gaussian_contraction_rule)
+                    T = g.inputs[time.name].size
+                    if T == 1:
+                        real_order = [k for k, _ in reals]
+                    elif T == 2 and t is None:
+                        real_order = [prev, curr]
+                    else:
+                        real_order = [curr, prev]
+                    if real_order[0] == curr:
+                        P = torch.cat([P[..., D:, :], P[..., :D, :]], dim=-2)
+                    for k in real_order:
+                        ginputs[k] = Reals[D]
                     result = Tensor(s, binputs) + Gaussian(white_vec=w, prec_sqrt=P, inputs=ginputs)
                     _STATE["calls"]["markov_fast"] += 1
                     return Subs(result, step_names)

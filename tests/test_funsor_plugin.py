@@ -476,3 +476,36 @@ def test_fast_gaussian_hmm_expression_inside_reference(funsor, fast):
     want, got, st = _both(fast, build)
     assert st["gaussian_contraction_fast"] > 0, st
     _same_gaussian_function(funsor, got, want, ["state", "state(time=1)"], D, 1e-6)
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 8])
+@pytest.mark.parametrize("with_tensor", [False, True])
+@pytest.mark.parametrize("order", [("b", "time", "prev", "curr"), ("time", "b", "curr", "prev")])
+def test_fast_gaussian_markov_rule_inside_reference(funsor, fast, T, with_tensor, order):
+    """MarkovProduct over Gaussian / Tensor + Gaussian elements through the whole-scan rule: same function AND the same input order
+    as the reference's level-by-level evaluation."""
+    import funsor.ops as ops
+    from funsor.domains import Bint, Reals
+    from funsor.gaussian import Gaussian
+    from funsor.sum_product import MarkovProduct
+    from funsor.tensor import Tensor
+    from funsor.terms import Variable
+    from funsor.testing import random_gaussian
+
+    torch.manual_seed(10)
+    D = 2
+    doms = dict(b=Bint[2], time=Bint[T], prev=Reals[D], curr=Reals[D])
+    proto = random_gaussian(OrderedDict((n, doms[n]) for n in order))
+    tdata = torch.randn(T, 2)
+
+    def build():
+        g = Gaussian(white_vec=proto.white_vec.clone(), prec_sqrt=proto.prec_sqrt.clone(), inputs=proto.inputs)
+        elem = g + Tensor(tdata.clone(), OrderedDict(time=Bint[T], b=Bint[2])) if with_tensor else g
+        return MarkovProduct(ops.logaddexp, ops.add, elem, Variable("time", Bint[T]), {"prev": "curr"})
+
+    want, got, st = _both(fast, build)
+    assert st["markov_fast"] > 0, st
+    if T == 1 and not with_tensor:
+        assert list(got.inputs.items()) == list(want.inputs.items())
+        return
+    _same_gaussian_function(funsor, got, want, ["prev", "curr"], D, 1e-7)
