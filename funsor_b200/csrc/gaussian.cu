@@ -751,40 +751,75 @@ static int homog_levels_count(int64_t T) {
     for (int64_t d = T; d > 1; d = (d + 1) / 2) ++nl;
     return nl;
 }
-static size_t homog_workspace_bytes(int64_t B, int64_t T, int D) {
+// Workspace layout of the homogeneous chain.  keep = every level's eta is kept (levels 1 .. NL-1 in their own buffers) so that
+// gaussian_homog_sample can walk the tree back down; otherwise two ping-pong buffers.
+struct HomogLayout {
+    float *Lreg, *Ltail, *opU, *opLinv, *konst, *zeros, *scratch;
+    int32_t* flag;
+    float* be[2];
+    float* bc[2];
+    float* lev_e[48];  // lev_e[l] = eta entering level l (l >= 1); lev_e[0] is the caller's array
+    bool ok;
+};
+static HomogLayout homog_layout(void* workspace, size_t workspace_bytes, int64_t B, int64_t T, int D, int DT, bool keep) {
+    const int n = 2 * D, NL = homog_levels_count(T);
+    const int64_t t1 = (T + 1) / 2, t2 = (t1 + 1) / 2;
+    Arena arena(workspace, workspace_bytes);
+    HomogLayout L{};
+    L.Lreg = arena.take<float>((size_t)B * NL * n * n);
+    L.Ltail = arena.take<float>((size_t)B * NL * n * n);
+    L.opU = arena.take<float>((size_t)B * NL * 2 * DT * 2 * DT);
+    L.opLinv = arena.take<float>((size_t)B * NL * 2 * DT * DT);
+    L.konst = arena.take<float>((size_t)B * NL * 2);
+    L.zeros = arena.take<float>((size_t)n);
+    L.scratch = arena.take<float>((size_t)B * 2 * n);
+    L.flag = arena.take<int32_t>(1);
+    const int64_t tt[2] = {t1, t2};
+    for (int q = 0; q < 2; ++q) {
+        L.be[q] = keep ? nullptr : arena.take<float>((size_t)B * tt[q] * n);
+        L.bc[q] = arena.take<float>((size_t)B * tt[q]);
+    }
+    if (keep) {
+        int64_t d = T;
+        for (int l = 1; l < NL && l < 48; ++l) {
+            d = (d + 1) / 2;
+            L.lev_e[l] = arena.take<float>((size_t)B * d * n);
+        }
+    }
+    L.ok = arena.ok() && NL < 48;
+    return L;
+}
+static size_t homog_workspace_bytes(int64_t B, int64_t T, int D, bool keep = false) {
     const int n = 2 * D, NL = homog_levels_count(T);
     const int DT = D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 32;
     const int64_t t1 = (T + 1) / 2, t2 = (t1 + 1) / 2;
     size_t w = 2 * align_up((size_t)B * NL * n * n * 4) + align_up((size_t)B * NL * 2 * DT * 2 * DT * 4) + align_up((size_t)B * NL * 2 * DT * DT * 4) +
                align_up((size_t)B * NL * 2 * 4) + align_up((size_t)n * 4) + align_up((size_t)B * 2 * n * 4) + align_up(4);
-    for (int64_t tt : {t1, t2}) w += align_up((size_t)B * tt * n * 4) + align_up((size_t)B * tt * 4);
+    for (int64_t tt : {t1, t2}) w += (keep ? 0 : align_up((size_t)B * tt * n * 4)) + align_up((size_t)B * tt * 4);
+    if (keep) {
+        int64_t d = T;
+        for (int l = 1; l < NL; ++l) {
+            d = (d + 1) / 2;
+            w += align_up((size_t)B * d * n * 4);
+        }
+    }
     return w + 256;
 }
 
 template <int DT>
 static int homog_chain_run(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int D, float* Lo, float* eo, float* co,
-                           void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-    const int n = 2 * D, NL = homog_levels_count(T);
-    const int64_t t1 = (T + 1) / 2, t2 = (t1 + 1) / 2;
-    Arena arena(workspace, workspace_bytes);
+                           void* workspace, size_t workspace_bytes, cudaStream_t stream, bool keep = false) {
+    const int NL = homog_levels_count(T);
+    const HomogLayout lay = homog_layout(workspace, workspace_bytes, B, T, D, DT, keep);
+    const int n = 2 * D;
     HomogLevelsArgs la;
     la.Lam = Lam; la.T = T; la.D = D; la.NL = NL; la.Lo = Lo;
-    la.Lreg = arena.take<float>((size_t)B * NL * n * n);
-    la.Ltail = arena.take<float>((size_t)B * NL * n * n);
-    la.opU = arena.take<float>((size_t)B * NL * 2 * DT * 2 * DT);
-    la.opLinv = arena.take<float>((size_t)B * NL * 2 * DT * DT);
-    la.konst = arena.take<float>((size_t)B * NL * 2);
-    float* zeros = arena.take<float>((size_t)n);
+    la.Lreg = lay.Lreg; la.Ltail = lay.Ltail; la.opU = lay.opU; la.opLinv = lay.opLinv; la.konst = lay.konst;
+    float* zeros = lay.zeros;
     la.zeros = zeros;
-    la.scratch = arena.take<float>((size_t)B * 2 * n);
-    la.flag = arena.take<int32_t>(1);
-    float *be[2], *bc[2];
-    const int64_t tt[2] = {t1, t2};
-    for (int q = 0; q < 2; ++q) {
-        be[q] = arena.take<float>((size_t)B * tt[q] * n);
-        bc[q] = arena.take<float>((size_t)B * tt[q]);
-    }
-    if (!arena.ok()) {
+    la.scratch = lay.scratch;
+    la.flag = lay.flag;
+    if (!lay.ok) {
         set_error("gaussian_chain (homogeneous): workspace too small (%zu bytes)", workspace_bytes);
         return FB2_ERR_WORKSPACE;
     }
@@ -802,8 +837,8 @@ static int homog_chain_run(const float* Lam, const float* eta, const float* c, i
         const bool odd = d & 1;
         const bool tail_pair = has_tail && !odd;
         const int64_t reg_pairs = npairs - (tail_pair ? 1 : 0);
-        float* de = nd == 1 ? eo : be[which];
-        float* dc = nd == 1 ? co : bc[which];
+        float* de = nd == 1 ? eo : (keep ? lay.lev_e[l + 1] : lay.be[which]);
+        float* dc = nd == 1 ? co : lay.bc[which];
         HomogEtaArgs ea;
         ea.ein = ce; ea.cin = cc; ea.eout = de; ea.cout = dc; ea.in_T = in_T; ea.out_T = nd; ea.D = D; ea.op_stride = (int64_t)NL * 2;
         ea.leftover_src = -1; ea.leftover_dst = -1;
@@ -836,6 +871,147 @@ static int homog_chain_run(const float* Lam, const float* eta, const float* c, i
     }
     gaussian_poison_if_flag<<<(unsigned)ceil_div(B, 256), 256, 0, stream>>>(la.flag, co, B);
     FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward sampling through the same tree (forward-filter backward-sample for Gaussian chains: recipes.py:16-90 runs the adjoint of
+// the scan under MonteCarlo, montecarlo.py:48-61, and Gaussian._sample gaussian.py:946-1059 draws each eliminated variable given its
+// two neighbours).  The variable eliminated by pair p of level l is the state at time m = (2p+1) 2^l, its neighbours are the states at
+// s = 2p 2^l and e = min((2p+2) 2^l, T).  With M = L L' the pair's shared-block precision, U = L^-1 G', v = L^-1 (eta_x[b] + eta_y[a])
+// (exactly the operators the forward sweep used),   x_m | x_s, x_e  ~  N(M^-1 (z - G'[x_s; x_e]), M^-1),   drawn as
+//     x_m = L^-T (eps_m + v - U [x_s; x_e])
+// with caller-supplied white noise eps: the draw is a deterministic function of (inputs, noise), which is what lets the oracle
+// check the joint law exactly.  Levels are walked top-down, all pairs and samples of a level in parallel; one thread per (pair, sample).
+struct HomogSampleArgs {
+    const float* e_lvl;  // eta entering level l: [B, d_l, n]
+    const float* opU;
+    const float* opLinv;
+    int64_t op_stride;
+    const float* noise;  // [B, N, T+1, D]
+    float* x;            // [B, N, T+1, D]
+    int64_t d_l, T, N, p0, count, span;
+    int D;
+};
+template <int DT>
+__global__ void __launch_bounds__(HE_THREADS) gaussian_homog_sample(HomogSampleArgs a) {
+    __shared__ __align__(16) float sLi[DT * DT];
+    __shared__ __align__(16) float sU[DT * 2 * DT];
+    const int64_t b = blockIdx.y;
+    const int D = a.D, n = 2 * D;
+    {
+        const float* U = a.opU + b * a.op_stride * DT * 2 * DT;
+        const float* Li = a.opLinv + b * a.op_stride * DT * DT;
+        for (int i = threadIdx.x; i < DT * DT; i += HE_THREADS) sLi[i] = __ldg(Li + i);
+        for (int i = threadIdx.x; i < DT * 2 * DT; i += HE_THREADS) sU[i] = __ldg(U + i);
+    }
+    __syncthreads();
+    const float* ein = a.e_lvl + b * a.d_l * n;
+    const int64_t row = (a.T + 1) * (int64_t)D;
+    for (int64_t idx = (int64_t)blockIdx.x * HE_THREADS + threadIdx.x; idx < a.count * a.N; idx += (int64_t)gridDim.x * HE_THREADS) {
+        const int64_t p = a.p0 + idx / a.N, smp = idx % a.N;
+        const int64_t ts = 2 * p * a.span, tm = ts + a.span;
+        int64_t te = ts + 2 * a.span;
+        if (te > a.T) te = a.T;
+        float* xb = a.x + (b * a.N + smp) * row;
+        const float* nb = a.noise + (b * a.N + smp) * row;
+        const float* ex = ein + 2 * p * n;
+        const float* ey = ex + n;
+        float z[DT], xac[2 * DT];
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            z[k] = k < D ? ex[D + k] + ey[k] : 0.f;
+            xac[k] = k < D ? xb[ts * D + k] : 0.f;
+            xac[DT + k] = k < D ? xb[te * D + k] : 0.f;
+        }
+        float w[DT];
+#pragma unroll
+        for (int r = 0; r < DT; ++r) {
+            float v = r < D ? nb[tm * D + r] : 0.f;
+#pragma unroll
+            for (int k = 0; k < DT; k += 4) {
+                if (k <= r) {
+                    const float4 l = *reinterpret_cast<const float4*>(&sLi[r * DT + k]);
+                    v = fmaf(l.x, z[k], fmaf(l.y, z[k + 1], fmaf(l.z, z[k + 2], fmaf(l.w, z[k + 3], v))));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2 * DT; c += 4) {
+                const float4 u = *reinterpret_cast<const float4*>(&sU[r * 2 * DT + c]);
+                v = fmaf(-u.x, xac[c], fmaf(-u.y, xac[c + 1], fmaf(-u.z, xac[c + 2], fmaf(-u.w, xac[c + 3], v))));
+            }
+            w[r] = v;
+        }
+        // x_m = L^-T w:  (L^-T)[i][r] = Linv[r][i], non-zero for r >= i; padded rows (r >= D) carry the identity and w = 0
+        float out[DT];
+#pragma unroll
+        for (int i = 0; i < DT; ++i) out[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < DT; ++r) {
+#pragma unroll
+            for (int i = 0; i < DT; i += 4) {
+                if (i <= r) {
+                    const float4 l = *reinterpret_cast<const float4*>(&sLi[r * DT + i]);
+                    out[i] = fmaf(l.x, w[r], out[i]);
+                    out[i + 1] = fmaf(l.y, w[r], out[i + 1]);
+                    out[i + 2] = fmaf(l.z, w[r], out[i + 2]);
+                    out[i + 3] = fmaf(l.w, w[r], out[i + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DT; ++k)
+            if (k < D) xb[tm * D + k] = out[k];
+    }
+}
+
+template <int DT>
+static int homog_sample_run(const float* eta, int64_t B, int64_t T, int D, int64_t N, const float* noise, float* x, void* workspace,
+                            size_t workspace_bytes, cudaStream_t stream) {
+    const int NL = homog_levels_count(T);
+    const HomogLayout lay = homog_layout(workspace, workspace_bytes, B, T, D, DT, true);
+    if (!lay.ok) {
+        set_error("gaussian_chain sample: workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    // replay the forward bookkeeping: which pairs of each level used the regular / the tail operator
+    struct Lvl { int64_t d, reg_pairs; bool tail_pair; };
+    Lvl lv[48];
+    {
+        int64_t d = T;
+        bool has_tail = false;
+        for (int l = 0; d > 1; ++l) {
+            const int64_t npairs = d / 2;
+            const bool odd = d & 1;
+            const bool tail_pair = has_tail && !odd;
+            lv[l] = {d, npairs - (tail_pair ? 1 : 0), tail_pair};
+            if (!tail_pair && !has_tail && odd) has_tail = true;
+            d = (d + 1) / 2;
+        }
+    }
+    for (int l = NL - 1; l >= 0; --l) {
+        HomogSampleArgs sa;
+        sa.e_lvl = l == 0 ? eta : lay.lev_e[l];
+        sa.op_stride = (int64_t)NL * 2;
+        sa.noise = noise; sa.x = x; sa.d_l = lv[l].d; sa.T = T; sa.N = N; sa.span = (int64_t)1 << l; sa.D = D;
+        if (lv[l].reg_pairs > 0) {
+            sa.opU = lay.opU + (size_t)(l * 2 + 0) * DT * 2 * DT;
+            sa.opLinv = lay.opLinv + (size_t)(l * 2 + 0) * DT * DT;
+            sa.p0 = 0; sa.count = lv[l].reg_pairs;
+            int64_t blocks = ceil_div(sa.count * N, HE_THREADS);
+            if (blocks > 65535) blocks = 65535;
+            gaussian_homog_sample<DT><<<dim3((unsigned)blocks, (unsigned)B), HE_THREADS, 0, stream>>>(sa);
+            FB2_LAUNCH_CHECK();
+        }
+        if (lv[l].tail_pair) {
+            sa.opU = lay.opU + (size_t)(l * 2 + 1) * DT * 2 * DT;
+            sa.opLinv = lay.opLinv + (size_t)(l * 2 + 1) * DT * DT;
+            sa.p0 = lv[l].d / 2 - 1; sa.count = 1;
+            int64_t blocks = ceil_div(N, HE_THREADS);
+            gaussian_homog_sample<DT><<<dim3((unsigned)blocks, (unsigned)B), HE_THREADS, 0, stream>>>(sa);
+            FB2_LAUNCH_CHECK();
+        }
+    }
     return FB2_OK;
 }
 
@@ -1022,6 +1198,38 @@ extern "C" int fb2_gaussian_chain_f32(const float* Lam, const float* eta, const 
                                       float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes,
                                       void* stream_) {
     return gaussian_chain_impl(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream_, false);
+}
+
+extern "C" size_t fb2_gaussian_chain_sample_workspace_bytes(int64_t B, int64_t T, int32_t D) {
+    return homog_workspace_bytes(B, T, D, true);
+}
+
+extern "C" int fb2_gaussian_chain_homog_keep_f32(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D,
+                                                 float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes, void* stream_) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(Lam && eta && c && Lo && eo && co, "null pointer");
+    FB2_REQUIRE(D >= 1 && D <= GMAXD, "state dimension D=%d outside [1, %d]", D, GMAXD);
+    FB2_REQUIRE(B >= 1 && B <= 65535 && T >= 2, "bad extents B=%lld T=%lld (the sampling path needs T >= 2)", (long long)B, (long long)T);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (D <= 4) return homog_chain_run<4>(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream, true);
+    if (D <= 8) return homog_chain_run<8>(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream, true);
+    if (D <= 16) return homog_chain_run<16>(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream, true);
+    return homog_chain_run<32>(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream, true);
+}
+
+extern "C" int fb2_gaussian_chain_homog_backward_sample_f32(const float* eta, int64_t B, int64_t T, int32_t D, int64_t N, const float* noise,
+                                                            float* x, void* workspace, size_t workspace_bytes, void* stream_) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(eta && noise && x && workspace, "null pointer");
+    FB2_REQUIRE(D >= 1 && D <= GMAXD, "state dimension D=%d outside [1, %d]", D, GMAXD);
+    FB2_REQUIRE(B >= 1 && B <= 65535 && T >= 2 && N >= 1, "bad extents");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (D <= 4) return homog_sample_run<4>(eta, B, T, D, N, noise, x, workspace, workspace_bytes, stream);
+    if (D <= 8) return homog_sample_run<8>(eta, B, T, D, N, noise, x, workspace, workspace_bytes, stream);
+    if (D <= 16) return homog_sample_run<16>(eta, B, T, D, N, noise, x, workspace, workspace_bytes, stream);
+    return homog_sample_run<32>(eta, B, T, D, N, noise, x, workspace, workspace_bytes, stream);
 }
 
 extern "C" int fb2_gaussian_chain_homog_f32(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D,

@@ -62,7 +62,23 @@ def contract_named(x, x_names, y, y_names, reduced, semiring, matmul):
     (funsor/cnf.py:348-375).  Returns None when the contraction is not a matrix product
     (a reduced name missing from one side)."""
     x_names, y_names = list(x_names), list(y_names)
-    if not reduced or not all(r in x_names and r in y_names for r in reduced):
+    reduced = set(reduced)
+    if not reduced or not all(r in x_names or r in y_names for r in reduced):
+        return None
+    # a reduced name that only ONE operand carries (sarkka_bilmes_product's block factors, sum_product.py:905-921) is summed out of
+    # that operand first -- a unary reduction over its own elements, exact for max and within rounding for logaddexp
+    for own, other in ((x_names, y_names), (y_names, x_names)):
+        dims = [i for i, n in enumerate(own) if n in reduced and n not in other]
+        if dims:
+            t = x if own is x_names else y
+            t = torch.logsumexp(t, dims) if semiring == "logaddexp" else t.amax(dims)
+            kept = [n for i, n in enumerate(own) if i not in dims]
+            if own is x_names:
+                x, x_names = t, kept
+            else:
+                y, y_names = t, kept
+    reduced = {r for r in reduced if r in x_names and r in y_names}
+    if not reduced:
         return None
     shared = [n for n in x_names if n in y_names and n not in reduced]  # batch dims
     ks = [n for n in x_names if n in reduced]

@@ -225,6 +225,71 @@ def kalman_chain(F, q_loc, q_tril, H, r_loc, r_tril, y, validate=True):
     return gaussian_chain_homog(w, P, s, validate=validate)
 
 
+def kalman_posterior_sample(m0, p0_tril, F, q_loc, q_tril, H, r_loc, r_tril, y, num_samples=1, noise=None, generator=None):
+    """Forward-filter backward-sample for a time-homogeneous linear-Gaussian state-space model: exact joint draws of the state path
+    x_0 .. x_T from p(x | y) (recipes.forward_filter_backward_rsample recipes.py:16-90 specialised to a chain; Gaussian._sample
+    gaussian.py:946-1059 draws every eliminated state given its two neighbours in the scan tree, sum_product.py:690-701).
+
+    The forward sweep is the parallel-scan Kalman filter (kalman_chain) that keeps its levels; the two end states are drawn from the
+    joint of the chain result and N(m0, p0 p0') (a [B, 2D, 2D] problem, torch.linalg in float64), then the tree is walked top-down on
+    the GPU, all pairs and samples of a level in parallel.  `noise[B, N, T+1, D]` standard normal makes the draws a deterministic
+    function of the inputs.  Returns (x[B,N,T+1,D], log_q[B,N] = log p(x | y), log_prob[B] = log p(y))."""
+    B, T, O = y.shape
+    D = F.shape[-1]
+    if T < 2:
+        raise ValueError("kalman_posterior_sample needs at least two time steps")
+    if noise is None:
+        noise = torch.randn((B, num_samples, T + 1, D), dtype=torch.float32, device=y.device, generator=generator)
+    _dev_f32(noise, "noise")
+    if noise.dim() != 4 or noise.shape[0] != B or noise.shape[2:] != (T + 1, D):
+        raise ValueError("noise must be [B, N, T+1, D], got {}".format(tuple(noise.shape)))
+    noise = noise.contiguous()
+    N = noise.shape[1]
+    w, P, s = kalman_elements_homog(F, q_loc, q_tril, H, r_loc, r_tril, y)
+    n, r = 2 * D, w.shape[-1]
+    P = P.contiguous()
+    Lam, _, _ = sqrt_to_info(torch.zeros(B, r, device=P.device), P)
+    eta = torch.empty((B, T, n), dtype=torch.float32, device=P.device)
+    c = torch.empty((B, T), dtype=torch.float32, device=P.device)
+    Lo = torch.empty((B, n, n), dtype=torch.float32, device=P.device)
+    eo = torch.empty((B, n), dtype=torch.float32, device=P.device)
+    co = torch.empty((B,), dtype=torch.float32, device=P.device)
+    x = torch.empty((B, N, T + 1, D), dtype=torch.float32, device=P.device)
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_gaussian_chain_sample_workspace_bytes(B, T, D), P.device)
+    with torch.cuda.device(P.device):
+        check(lib.fb2_gaussian_eta_f32(w.data_ptr(), P.data_ptr(), s.data_ptr(), B, T, n, r, eta.data_ptr(), c.data_ptr(), _stream()))
+        check(lib.fb2_gaussian_chain_homog_keep_f32(Lam.data_ptr(), eta.data_ptr(), c.data_ptr(), B, T, D, Lo.data_ptr(), eo.data_ptr(),
+                                                    co.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    if bool(torch.isnan(co).any()):
+        raise ValueError("Too little information to marginalize over the shared state. Consider adding a prior.")
+    # the two end states: joint of the chain result over (x_0; x_T) and the initial distribution on x_0
+    Lj, ej = Lo.double().clone(), eo.double().clone()
+    eye = torch.eye(D, device=P.device, dtype=torch.float64)
+    Li = torch.linalg.solve_triangular(p0_tril.double(), eye.expand(B, D, D), upper=False)
+    L0 = Li.transpose(-1, -2) @ Li
+    Lj[:, :D, :D] += L0
+    ej[:, :D] += (L0 @ m0.double()[..., None])[..., 0]
+    Lc = torch.linalg.cholesky(Lj)
+    v = torch.linalg.solve_triangular(Lc, ej[..., None], upper=False)[..., 0]  # [B, 2D]
+    eps = torch.cat([noise[:, :, 0], noise[:, :, T]], -1).double()  # [B, N, 2D]
+    ends = torch.linalg.solve_triangular(Lc.transpose(-1, -2)[:, None], (eps + v[:, None])[..., None], upper=True)[..., 0]
+    x[:, :, 0] = ends[..., :D].float()
+    x[:, :, T] = ends[..., D:].float()
+    with torch.cuda.device(P.device):
+        check(lib.fb2_gaussian_chain_homog_backward_sample_f32(eta.data_ptr(), B, T, D, N, noise.data_ptr(), x.data_ptr(), ws.data_ptr(),
+                                                               ws.numel(), _stream()))
+    log_prob = gaussian_hmm_log_prob(m0, p0_tril, (Lo, eo, co))
+    # log density of the draws: sum of the factors at the sample minus the normaliser (recipes.py:80-88)
+    pairs = torch.cat([x[:, :, :-1], x[:, :, 1:]], -1)  # [B, N, T, 2D]
+    resid = pairs.reshape(B, N * T, n) @ P - w[:, None].expand(B, N, T, r).reshape(B, N * T, r)
+    elem = s[:, None] - 0.5 * (resid * resid).sum(-1).reshape(B, N, T)
+    d0 = (x[:, :, 0].double() - m0.double()[:, None]) @ Li.transpose(-1, -2)
+    init_lp = -0.5 * D * math.log(2 * math.pi) - p0_tril.double().diagonal(dim1=-1, dim2=-2).log().sum(-1)[:, None] - 0.5 * (d0 * d0).sum(-1)
+    log_q = elem.double().sum(-1) + init_lp - log_prob[:, None]
+    return x, log_q, log_prob
+
+
 def gaussian_hmm_log_prob(m0, p0_tril, chain):
     """hmm.py:271-272: init + chain.reduce(curr) then reduce(state), for init = N(m0, p0 p0').
     A [B, 2D, 2D] problem once per call (not T-sized): done with torch.linalg in float64."""

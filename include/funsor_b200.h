@@ -161,6 +161,22 @@ int fb2_gaussian_eta_f32(const float* w, const float* P, const float* s, int64_t
                          float* eta, float* c, void* stream);
 int fb2_gaussian_chain_homog_f32(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D,
                                  float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes, void* stream);
+/* Backward sampling of a homogeneous Gaussian chain (forward-filter backward-sample).
+ * Replaces: recipes.forward_filter_backward_rsample funsor/recipes.py:16-90 specialised to a chain = the adjoint of the scan under
+ *           MonteCarlo (montecarlo.py:48-61) with Gaussian._sample (gaussian.py:946-1059) drawing every eliminated state given its two
+ *           neighbours in the scan tree (sum_product.py:690-701).
+ * chain_homog_keep            : fb2_gaussian_chain_homog_f32 that also keeps every level's eta and the per-level operators in `workspace`
+ *                               (sized by fb2_gaussian_chain_sample_workspace_bytes); T >= 2.
+ * chain_homog_backward_sample : walks the tree top-down.  x[B,N,T+1,D]: on entry x[..,0,:] and x[..,T,:] hold draws of the two END states
+ *                               (from the joint of the chain result and the initial distribution, a [B] problem the caller solves); on
+ *                               exit every interior state t = 1..T-1 is filled with  x_m = L^-T (noise_m + v - U [x_s; x_e])  for the pair
+ *                               that eliminated it.  noise[B,N,T+1,D] standard normal (rows 0 and T unused): the result is a deterministic
+ *                               function of (inputs, noise).  `eta` and `workspace` must be the ones the keep call just used. */
+size_t fb2_gaussian_chain_sample_workspace_bytes(int64_t B, int64_t T, int32_t D);
+int fb2_gaussian_chain_homog_keep_f32(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D,
+                                      float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes, void* stream);
+int fb2_gaussian_chain_homog_backward_sample_f32(const float* eta, int64_t B, int64_t T, int32_t D, int64_t N, const float* noise,
+                                                 float* x, void* workspace, size_t workspace_bytes, void* stream);
 size_t fb2_gaussian_chain_workspace_bytes(int64_t B, int64_t T, int32_t D);
 int fb2_gaussian_chain_f32(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D,
                            float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes,

@@ -509,3 +509,48 @@ def test_fast_gaussian_markov_rule_inside_reference(funsor, fast, T, with_tensor
         assert list(got.inputs.items()) == list(want.inputs.items())
         return
     _same_gaussian_function(funsor, got, want, ["prev", "curr"], D, 1e-7)
+
+
+@pytest.mark.parametrize("sname", ["logaddexp", "max"])
+def test_fast_planners_inside_reference(funsor, fast, sname):
+    """(f4) sarkka_bilmes_product (sum_product.py:856-937) and the plated Markov planners (486-600, 344-483) with the rules' fast
+    branches on: several (prev, curr) pairs per step reach contract_named as several reduced names."""
+    from functools import reduce
+
+    import funsor.ops as ops
+    import funsor.sum_product as sp
+    from funsor.domains import Bint
+    from funsor.tensor import Tensor
+    from funsor.terms import Variable
+    from funsor.testing import assert_close
+
+    op = ops.logaddexp if sname == "logaddexp" else ops.max
+    g = torch.Generator().manual_seed(21)
+    sizes = OrderedDict([("a", 4), ("b", 3), ("_PREV_b", 3), ("c", 2), ("_PREV__PREV_c", 2)])
+    for duration in (2, 5, 8):
+        data = torch.randn(duration, *sizes.values(), generator=g)
+        inputs = OrderedDict([("time", Bint[duration])] + [(k, Bint[v]) for k, v in sizes.items()])
+
+        def build():
+            return sp.sarkka_bilmes_product(op, ops.add, Tensor(data.clone(), inputs), Variable("time", Bint[duration]), frozenset())
+
+        want, got, st = _both(fast, build)
+        if duration >= 4:
+            assert st["contraction_fast"] > 0, st
+        assert_close(got.align(tuple(want.inputs)), want, atol=1e-9, rtol=1e-9)
+    x_dim, y_dim, time = 2, 3, 5
+    datas = [torch.randn((), generator=g), torch.randn(x_dim, generator=g), torch.randn(time, x_dim, x_dim, generator=g),
+             torch.randn(x_dim, y_dim, generator=g), torch.randn(time, x_dim, y_dim, generator=g)]
+    names = [OrderedDict(), OrderedDict(x_0=Bint[x_dim]), OrderedDict(time=Bint[time], x_prev=Bint[x_dim], x_curr=Bint[x_dim]),
+             OrderedDict(x_0=Bint[x_dim], y_0=Bint[y_dim]), OrderedDict(time=Bint[time], x_curr=Bint[x_dim], y_curr=Bint[y_dim])]
+    plate_to_step = {"time": frozenset({("x_0", "x_prev", "x_curr")})}
+    for impl in (sp.modified_partial_sum_product, sp.dynamic_partial_sum_product):
+        def build():
+            factors = [Tensor(d.clone(), n) for d, n in zip(datas, names)]
+            f1 = impl(op, ops.add, factors, frozenset({"y_0", "y_curr"}), plate_to_step)
+            f2 = impl(op, ops.add, f1, frozenset({"time", "x_0", "x_prev", "x_curr"}), plate_to_step)
+            return reduce(ops.add, f2)
+
+        want, got, st = _both(fast, build)
+        assert st["contraction_fast"] + st["markov_fast"] > 0, (impl.__name__, st)
+        assert_close(got, want, atol=1e-9, rtol=1e-9)

@@ -423,3 +423,85 @@ def test_torch_backend_ops_allocate_on_the_operand_device(funsor):
     assert f(time=Variable("t2", Bint[7])).data.is_cuda and f(time=6).data.is_cuda
     idx = Tensor(torch.tensor([0, 2], device=DEV), OrderedDict(k=Bint[2]), 7)
     assert f(time=idx).data.is_cuda
+
+
+# ------------------------------------------------------------------------------------------------ (f4) higher-order / plated planners
+SARKKA_BILMES = {  # test_sum_product.py:2658-2760: inputs of `trans`, durations
+    "lag1": (OrderedDict([("a", 3), ("b", 2), ("_PREV_b", 2)]), [2, 3, 6, 33]),
+    "lag1_and_2": (OrderedDict([("a", 4), ("b", 3), ("_PREV_b", 3), ("c", 2), ("_PREV__PREV_c", 2)]), [2, 5, 8, 32]),
+    "lag2": (OrderedDict([("a", 4), ("c", 2), ("_PREV__PREV_c", 2)]), [2, 7, 8, 40]),
+    "lag1_and_3": (OrderedDict([("a", 2), ("_PREV_a", 2), ("_PREV__PREV__PREV_a", 2)]), [3, 6, 9, 30]),
+    "wide": (OrderedDict([("a", 48), ("_PREV_a", 48), ("x", 2)]), [4, 17, 64]),
+}
+
+
+@pytest.mark.parametrize("sname", ["logaddexp", "max"])
+@pytest.mark.parametrize("case", sorted(SARKKA_BILMES))
+def test_sarkka_bilmes_product_through_the_rules(funsor, plugin, sname, case):
+    """sum_product.py:856-937: the higher-order Markov planner re-blocks `trans` into period-sized steps and calls
+    mixed_sequential_sum_product with SEVERAL (prev, curr) pairs per step; every level reaches the Contraction rule with several
+    reduced names (contract_named folds them into one k)."""
+    import funsor.ops as ops
+    from funsor.domains import Bint
+    from funsor.sum_product import sarkka_bilmes_product
+    from funsor.tensor import Tensor
+    from funsor.terms import Variable
+
+    op = _ops(funsor, sname)
+    sizes, durations = SARKKA_BILMES[case]
+    for duration in durations:
+        g = torch.Generator().manual_seed(duration)
+        data = torch.randn(duration, *sizes.values(), generator=g)
+        inputs = OrderedDict([("time", Bint[duration])] + [(k, Bint[v]) for k, v in sizes.items()])
+
+        def build(put):
+            return sarkka_bilmes_product(op, ops.add, Tensor(put(data), inputs), Variable("time", Bint[duration]), frozenset())
+
+        want = build(lambda t: t.double())
+        plugin.stats(reset=True)
+        got = build(lambda t: t.to(DEV))
+        st = plugin.stats()
+        period = max(k.count("_PREV_") for k in sizes)
+        if duration // period >= 2:
+            assert st["contraction_fast"] > 0, (case, duration, st)
+        assert set(got.inputs) == set(want.inputs)
+        got = got.align(tuple(want.inputs))
+        rel_close(got.data.cpu().numpy(), want.data.numpy(), rtol=1e-5, atol=1.0)
+
+
+@pytest.mark.parametrize("sname", ["logaddexp", "max"])
+@pytest.mark.parametrize("impl", ["modified_partial_sum_product", "dynamic_partial_sum_product"])
+@pytest.mark.parametrize("x_dim,y_dim,time", [(2, 3, 5), (48, 3, 37), (33, 40, 16)])
+def test_plated_markov_planners_through_the_rules(funsor, plugin, sname, impl, x_dim, y_dim, time):
+    """sum_product.py:486-600 (modified_partial_sum_product) and 344-483 (dynamic_partial_sum_product) on the factor graph of
+    test_sum_product.py:413-467: a Markov chain in a `time` plate with an emission per step; the time plate is eliminated by
+    sequential_sum_product inside the planner."""
+    from functools import reduce
+
+    import funsor.ops as ops
+    import funsor.sum_product as sp
+    from funsor.domains import Bint
+    from funsor.tensor import Tensor
+
+    op = _ops(funsor, sname)
+    g = torch.Generator().manual_seed(x_dim + time)
+    datas = [torch.randn((), generator=g), torch.randn(x_dim, generator=g), torch.randn(time, x_dim, x_dim, generator=g),
+             torch.randn(x_dim, y_dim, generator=g), torch.randn(time, x_dim, y_dim, generator=g)]
+    names = [OrderedDict(), OrderedDict(x_0=Bint[x_dim]), OrderedDict(time=Bint[time], x_prev=Bint[x_dim], x_curr=Bint[x_dim]),
+             OrderedDict(x_0=Bint[x_dim], y_0=Bint[y_dim]), OrderedDict(time=Bint[time], x_curr=Bint[x_dim], y_curr=Bint[y_dim])]
+    plate_to_step = {"time": frozenset({("x_0", "x_prev", "x_curr")})}
+    vars1, vars2 = frozenset({"y_0", "y_curr"}), frozenset({"time", "x_0", "x_prev", "x_curr"})
+
+    def build(put):
+        factors = [Tensor(put(d), n) for d, n in zip(datas, names)]
+        f1 = getattr(sp, impl)(op, ops.add, factors, vars1, plate_to_step)
+        f2 = getattr(sp, impl)(op, ops.add, f1, vars2, plate_to_step)
+        return reduce(ops.add, f2)
+
+    want = build(lambda t: t.double())
+    plugin.stats(reset=True)
+    got = build(lambda t: t.to(DEV))
+    st = plugin.stats()
+    assert st["contraction_fast"] + st["markov_fast"] > 0, st
+    assert isinstance(got, Tensor) and not got.inputs
+    rel_close(got.data.cpu().numpy(), want.data.numpy(), rtol=1e-5, atol=1.0)

@@ -167,3 +167,76 @@ def test_kalman_homogeneous_operator_path_against_float64_filter(fg, T, D, O):
     m0, p0 = rng.standard_normal((B, D)), spd_tril(D)
     lp = fg.gaussian_hmm_log_prob(dev(m0), dev(p0), chain)
     close_norm(host(lp), G.hmm_logprob_from_chain(G.mvn_info(m0, p0), want, D), 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ (f2) Gaussian backward sampling
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,D,O", [(2, 2, 1, 1), (2, 7, 3, 2), (1, 8, 2, 1), (2, 13, 4, 2), (1, 33, 2, 2)])
+def test_kalman_posterior_sample_has_the_exact_joint_law(B, T, D, O):
+    """Forward-filter backward-sample (recipes.py:16-90; Gaussian._sample gaussian.py:946-1059) on the scan tree.  The sampler is an
+    affine map of its white noise, x = x(0) + A eps, so the joint law is verified EXACTLY against the dense float64 posterior of all
+    states (oracle/gaussian_ref.kalman_posterior_dense, no scan): x(0) must be the posterior mean and A A' the posterior covariance;
+    the reported log density must be the dense Gaussian log density of every draw."""
+    import funsor_b200.gaussian as fg
+    from oracle import gaussian_ref as G
+
+    rng = np.random.default_rng(100 * T + D)
+    n = (T + 1) * D
+
+    def spd_tril(k):
+        a = rng.standard_normal((B, k, k))
+        return np.linalg.cholesky(a @ a.transpose(0, 2, 1) / k + 0.5 * np.eye(k))
+
+    F = 0.9 * np.linalg.qr(rng.standard_normal((B, D, D)))[0]
+    H = rng.standard_normal((B, D, O))
+    args64 = (rng.standard_normal((B, D)), spd_tril(D), F, 0.1 * rng.standard_normal((B, D)), spd_tril(D), H,
+              0.1 * rng.standard_normal((B, O)), spd_tril(O), rng.standard_normal((B, T, O)))
+    mean, cov, logZ = G.kalman_posterior_dense(*args64)
+    args = [torch.tensor(a, dtype=torch.float32, device="cuda") for a in args64]
+    # noise: sample 0 = zeros, samples 1..n = unit vectors, then a few random draws
+    extra = 5
+    noise = np.zeros((B, 1 + n + extra, T + 1, D), np.float32)
+    for k in range(n):
+        noise[:, 1 + k].reshape(B, n)[:, k] = 1.0
+    noise[:, 1 + n:] = rng.standard_normal((B, extra, T + 1, D))
+    x, log_q, log_prob = fg.kalman_posterior_sample(*args, noise=torch.tensor(noise, device="cuda"))
+    x = x.cpu().double().numpy().reshape(B, 1 + n + extra, n)
+    scale = np.abs(mean).max() + np.sqrt(np.abs(cov).max())
+    assert np.abs(x[:, 0] - mean).max() <= 2e-4 * scale, np.abs(x[:, 0] - mean).max()
+    A = (x[:, 1 : 1 + n] - x[:, :1]).transpose(0, 2, 1)  # column k = response to unit noise k
+    assert np.abs(A @ A.transpose(0, 2, 1) - cov).max() <= 5e-4 * np.abs(cov).max(), np.abs(A @ A.transpose(0, 2, 1) - cov).max()
+    np.testing.assert_allclose(log_prob.cpu().numpy(), logZ, rtol=1e-4, atol=1e-3)
+    # affine in the noise, and the density of every draw
+    sign, logdet = np.linalg.slogdet(cov)
+    for k in range(extra):
+        xs = x[:, 1 + n + k]
+        want_x = mean + (A @ noise[:, 1 + n + k].reshape(B, n, 1).astype(np.float64))[..., 0]
+        assert np.abs(xs - want_x).max() <= 1e-3 * scale
+        d = xs - mean
+        want_q = -0.5 * (d * np.linalg.solve(cov, d[..., None])[..., 0]).sum(-1) - 0.5 * logdet - 0.5 * n * np.log(2 * np.pi)
+        np.testing.assert_allclose(log_q[:, 1 + n + k].cpu().numpy(), want_q, rtol=2e-3, atol=2e-2)
+
+
+@pytest.mark.gpu
+def test_kalman_posterior_sample_moments_at_scale():
+    """C4-like shape (D=32, O=16) on a longer chain: sample mean over many draws against the smoothed mean of the dense oracle at a
+    few time points (T small enough for the dense float64 solve)."""
+    import funsor_b200.gaussian as fg
+    from oracle import gaussian_ref as G
+
+    rng = np.random.default_rng(7)
+    B, T, D, O, N = 1, 40, 32, 16, 4096
+    F = 0.9 * np.linalg.qr(rng.standard_normal((B, D, D)))[0]
+    H = rng.standard_normal((B, D, O)) / np.sqrt(D)
+    eye = lambda k: np.broadcast_to(np.eye(k), (B, k, k)).copy()  # noqa: E731
+    args64 = (np.zeros((B, D)), eye(D), F, np.zeros((B, D)), eye(D), H, np.zeros((B, O)), eye(O), rng.standard_normal((B, T, O)))
+    mean, cov, _ = G.kalman_posterior_dense(*args64)
+    args = [torch.tensor(a, dtype=torch.float32, device="cuda") for a in args64]
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x, log_q, _ = fg.kalman_posterior_sample(*args, num_samples=N, generator=g)
+    xm = x.double().mean(1).cpu().numpy().reshape(B, -1)
+    sd = np.sqrt(np.diagonal(cov, axis1=-2, axis2=-1))
+    assert np.abs((xm - mean) / sd).max() < 6.0 / np.sqrt(N) * 1.2  # 6 sigma of the Monte-Carlo error of a mean
+    xv = x.double().var(1).cpu().numpy().reshape(B, -1)
+    assert np.abs(xv / sd ** 2 - 1).max() < 0.2
+    assert bool(torch.isfinite(log_q).all())

@@ -182,3 +182,16 @@ def test_gaussian_mrf_oracle_matches_reference():
     for name, d in cases.items():
         got = mrf_oracle(d)
         rel_close(got, d["log_prob"].reshape(got.shape), rtol=1e-8, atol=1.0)
+
+
+def test_dense_posterior_oracle_agrees_with_the_sequential_filter():
+    """oracle/gaussian_ref.kalman_posterior_dense (the law forward-filter backward-sample draws from) against the textbook
+    sequential Kalman filter and against the golden log-probabilities written by the reference (tests/golden/kalman.npz)."""
+    from oracle import gaussian_ref as G
+
+    for name, d in golden_cases(load_golden("kalman")).items():
+        args = [d[k].astype(np.float64) for k in ("m0", "p0_tril", "F", "q_loc", "q_tril", "H", "r_loc", "r_tril", "y")]
+        mean, cov, logZ = G.kalman_posterior_dense(*args)
+        np.testing.assert_allclose(logZ, d["logprob"], rtol=1e-8, atol=1e-8)
+        np.testing.assert_allclose(logZ, G.kalman_filter_logprob(*args), rtol=1e-9, atol=1e-9)
+        assert np.all(np.linalg.eigvalsh(cov) > 0)
