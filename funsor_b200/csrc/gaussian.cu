@@ -1098,6 +1098,191 @@ __global__ void __launch_bounds__(I2S_WARPS * 32) gaussian_info_to_sqrt(const fl
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Moment matching of a Gaussian mixture (joint.py:102-150: the Contraction[Logaddexp, Add, {discrete}, Tensor, Gaussian] rule of the
+// `moment_matching` interpretation, which is what makes the SwitchingLinearHMM scan tractable, pyro/hmm.py:527-551).
+// For every output element e: K components (logit d_k, Lam_k, eta_k, c_k) over n reals ->
+//     logn_k = c_k + n/2 log 2pi - sum log diag L_k + |L_k^-1 eta_k|^2 / 2          (L_k L_k' = Lam_k: the component's mass)
+//     Z = logsumexp_k (d_k + logn_k),  p_k = exp(d_k + logn_k - Z),  mu_k = Lam_k^-1 eta_k,  Sig_k = Lam_k^-1
+//     mu = sum p_k mu_k,   Sig = sum p_k (Sig_k + (mu_k - mu)(mu_k - mu)')              (an empty mixture gets Sig = I, joint.py:141-143)
+//     Lam' = Sig^-1,  eta' = Lam' mu,  c' = Z - n/2 log 2pi - 1/2 log det Sig - mu' eta' / 2   (a normalised density of mass exp Z)
+// One warp per element; every matrix lives in the warp's shared-memory slot (Cholesky in place, inverse through two triangular
+// solves with one right-hand-side column per lane).  Two passes over the components: the weights need Z first, and the centred form
+// (mu_k - mu) avoids the cancellation of  sum p_k mu_k mu_k' - mu mu'.
+constexpr int MM_WARPS = 2;
+struct MMSlot {  // layout inside the dynamic shared memory of one warp, n <= 64, ld = n + 1
+    float* A;    // [n][ld]  working matrix / Cholesky factor
+    float* S;    // [n][ld]  accumulated covariance
+    float* Y;    // [n][64]  right-hand sides of the inverse, one column per (lane, half)
+    float* vec;  // [4][n]   eta / v / mu_k / mu
+};
+__device__ __forceinline__ bool mm_cholesky(float* A, int n, int ld, int lane, float& half_logdet) {
+    // right-looking Cholesky, lane owns rows lane and lane + 32; returns false on a non-positive pivot
+    half_logdet = 0.f;
+    bool ok = true;
+    for (int j = 0; j < n; ++j) {
+        const float d = A[j * ld + j];
+        if (!(d > 0.f)) ok = false;
+        const float piv = sqrtf(fmaxf(d, 1e-30f));
+        half_logdet += logf(piv);
+        const float inv = 1.f / piv;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            if (i == j) A[j * ld + j] = piv;
+            else if (i > j) A[i * ld + j] *= inv;
+        }
+        __syncwarp();
+        for (int i = j + 1 + lane; i < n; i += 32) {
+            const float lij = A[i * ld + j];
+            for (int c = j + 1; c <= i; ++c) A[i * ld + c] = fmaf(-lij, A[c * ld + j], A[i * ld + c]);
+        }
+    }
+    __syncwarp();
+    return ok;
+}
+// x = L^-1 b (in place in `b`, shared memory), then optionally x = L^-T x
+__device__ __forceinline__ void mm_solve_vec(const float* L, int n, int ld, float* b, int lane, bool back) {
+    for (int j = 0; j < n; ++j) {
+        float part = 0.f;
+        for (int m = lane; m < j; m += 32) part = fmaf(L[j * ld + m], b[m], part);
+        part = warp_sum(part);
+        __syncwarp();
+        if (lane == 0) b[j] = (b[j] - part) / L[j * ld + j];
+        __syncwarp();
+    }
+    if (!back) return;
+    for (int j = n - 1; j >= 0; --j) {
+        float part = 0.f;
+        for (int m = j + 1 + lane; m < n; m += 32) part = fmaf(L[m * ld + j], b[m], part);
+        part = warp_sum(part);
+        __syncwarp();
+        if (lane == 0) b[j] = (b[j] - part) / L[j * ld + j];
+        __syncwarp();
+    }
+}
+// Y[:, col] = (L L')^-1 e_col for the columns this lane owns (col = lane, lane + 32); all lanes walk the same (j, m) so L is a broadcast read
+__device__ __forceinline__ void mm_inverse_columns(const float* L, int n, int ld, float* Y, int lane) {
+    for (int h = 0; h < 2; ++h) {
+        const int col = lane + 32 * h;
+        float* y = Y + col;  // stride 64
+        if (col < n) {
+            for (int j = 0; j < n; ++j) {
+                float acc = j == col ? 1.f : 0.f;
+                for (int m = col; m < j; ++m) acc = fmaf(-L[j * ld + m], y[m * 64], acc);  // y[m] = 0 for m < col
+                y[j * 64] = j < col ? 0.f : acc / L[j * ld + j];
+            }
+            for (int j = n - 1; j >= 0; --j) {
+                float acc = y[j * 64];
+                for (int m = j + 1; m < n; ++m) acc = fmaf(-L[m * ld + j], y[m * 64], acc);
+                y[j * 64] = acc / L[j * ld + j];
+            }
+        }
+    }
+    __syncwarp();
+}
+__global__ void __launch_bounds__(MM_WARPS * 32) gaussian_moment_match(const float* __restrict__ logits, const float* __restrict__ Lam,
+                                                                        const float* __restrict__ eta, const float* __restrict__ c, int64_t N, int K,
+                                                                        int n, float* __restrict__ scratch /*[N,K,n+1]: mu_k, logit_k + logn_k*/,
+                                                                        float* __restrict__ Lo, float* __restrict__ eo, float* __restrict__ co,
+                                                                        int32_t* __restrict__ flag) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ld = n + 1;
+    const size_t per_warp = (size_t)2 * n * ld + (size_t)n * 64 + 4 * n;
+    float* base = sm + wid * per_warp;
+    float *A = base, *S = A + n * ld, *Y = S + n * ld, *vec = Y + n * 64;
+    float *v0 = vec, *mu = vec + n;
+    const int64_t e = (int64_t)blockIdx.x * MM_WARPS + wid;
+    if (e >= N) return;
+    float* sc = scratch + e * (int64_t)K * (n + 1);
+    // ---- pass 1: mass and mean of every component
+    float zmax = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+        const float* Lk = Lam + (e * K + k) * (int64_t)n * n;
+        for (int idx = lane; idx < n * n; idx += 32) A[(idx / n) * ld + idx % n] = Lk[idx];
+        for (int i = lane; i < n; i += 32) v0[i] = eta[(e * K + k) * (int64_t)n + i];
+        __syncwarp();
+        float hl;
+        if (!mm_cholesky(A, n, ld, lane, hl) && lane == 0 && flag) atomicExch(flag, 1);
+        mm_solve_vec(A, n, ld, v0, lane, false);  // v = L^-1 eta
+        float q = 0.f;
+        for (int i = lane; i < n; i += 32) q = fmaf(v0[i], v0[i], q);
+        q = warp_sum(q);
+        const float lg = logits[e * K + k] + c[e * K + k] + n * kHalfLog2Pi - hl + 0.5f * q;
+        // mu_k = L^-T v
+        for (int j = n - 1; j >= 0; --j) {
+            float part = 0.f;
+            for (int m = j + 1 + lane; m < n; m += 32) part = fmaf(A[m * ld + j], v0[m], part);
+            part = warp_sum(part);
+            __syncwarp();
+            if (lane == 0) v0[j] = (v0[j] - part) / A[j * ld + j];
+            __syncwarp();
+        }
+        for (int i = lane; i < n; i += 32) sc[k * (n + 1) + i] = v0[i];
+        if (lane == 0) sc[k * (n + 1) + n] = lg;
+        zmax = fmaxf(zmax, lg);
+        __syncwarp();
+    }
+    float wsum = 0.f;
+    for (int k = 0; k < K; ++k) wsum += zmax == -INFINITY ? 0.f : __expf(sc[k * (n + 1) + n] - zmax);
+    const float Z = zmax == -INFINITY ? -INFINITY : zmax + logf(wsum);
+    for (int i = lane; i < n; i += 32) {
+        float m = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float pk = Z == -INFINITY ? 0.f : __expf(sc[k * (n + 1) + n] - Z);
+            m = fmaf(pk, sc[k * (n + 1) + i], m);
+        }
+        mu[i] = m;
+    }
+    for (int idx = lane; idx < n * ld; idx += 32) S[idx] = 0.f;
+    __syncwarp();
+    // ---- pass 2: Sig = sum p_k (Lam_k^-1 + (mu_k - mu)(mu_k - mu)')
+    for (int k = 0; k < K; ++k) {
+        const float pk = Z == -INFINITY ? 0.f : __expf(sc[k * (n + 1) + n] - Z);
+        if (pk == 0.f) continue;  // warp-uniform
+        const float* Lk = Lam + (e * K + k) * (int64_t)n * n;
+        for (int idx = lane; idx < n * n; idx += 32) A[(idx / n) * ld + idx % n] = Lk[idx];
+        __syncwarp();
+        float hl;
+        mm_cholesky(A, n, ld, lane, hl);
+        mm_inverse_columns(A, n, ld, Y, lane);
+        for (int i = lane; i < n; i += 32) v0[i] = sc[k * (n + 1) + i] - mu[i];
+        __syncwarp();
+        for (int idx = lane; idx < n * n; idx += 32) {
+            const int i = idx / n, j = idx % n;
+            S[i * ld + j] += pk * (Y[i * 64 + j] + v0[i] * v0[j]);
+        }
+        __syncwarp();
+    }
+    if (Z == -INFINITY) {  // empty mixture: bogus unit covariance (joint.py:141-143)
+        for (int i = lane; i < n; i += 32) S[i * ld + i] = 1.f;
+        __syncwarp();
+    }
+    // ---- Lam' = Sig^-1, eta' = Lam' mu, c'
+    for (int idx = lane; idx < n * n; idx += 32) {  // symmetrise against rounding before factorising
+        const int i = idx / n, j = idx % n;
+        A[i * ld + j] = 0.5f * (S[i * ld + j] + S[j * ld + i]);
+    }
+    __syncwarp();
+    float hl;
+    if (!mm_cholesky(A, n, ld, lane, hl) && lane == 0 && flag) atomicExch(flag, 1);
+    mm_inverse_columns(A, n, ld, Y, lane);
+    float quad = 0.f;
+    for (int i = lane; i < n; i += 32) {
+        float acc = 0.f;
+        for (int j = 0; j < n; ++j) acc = fmaf(0.5f * (Y[i * 64 + j] + Y[j * 64 + i]), mu[j], acc);
+        eo[e * n + i] = acc;
+        quad = fmaf(acc, mu[i], quad);
+    }
+    quad = warp_sum(quad);
+    for (int idx = lane; idx < n * n; idx += 32) {
+        const int i = idx / n, j = idx % n;
+        Lo[e * (int64_t)n * n + idx] = 0.5f * (Y[i * 64 + j] + Y[j * 64 + i]);
+    }
+    if (lane == 0) co[e] = Z - n * kHalfLog2Pi - hl - 0.5f * quad;
+}
+
 }  // namespace fb2
 
 using namespace fb2;
@@ -1134,6 +1319,34 @@ extern "C" int fb2_gaussian_info_to_sqrt_f32(const float* Lam, const float* eta,
     int64_t blocks = ceil_div(N, I2S_WARPS);
     FB2_REQUIRE(blocks < (1ll << 31), "too many elements for one launch");
     gaussian_info_to_sqrt<<<(unsigned)blocks, I2S_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(Lam, eta, c, N, dim, rel_tol, w, P, s, rank);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
+extern "C" size_t fb2_gaussian_moment_match_workspace_bytes(int64_t N, int32_t K, int32_t dim) {
+    return align_up((size_t)N * K * (dim + 1) * sizeof(float)) + 256;
+}
+
+extern "C" int fb2_gaussian_moment_match_f32(const float* logits, const float* Lam, const float* eta, const float* c, int64_t N, int32_t K,
+                                             int32_t dim, float* Lo, float* eo, float* co, int32_t* status_flag, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(logits && Lam && eta && c && Lo && eo && co, "null pointer");
+    FB2_REQUIRE(N >= 0 && K >= 1 && dim >= 1 && dim <= 2 * GMAXD, "bad extents N=%lld K=%d dim=%d", (long long)N, K, dim);
+    if (N == 0) return FB2_OK;
+    Arena arena(workspace, workspace_bytes);
+    float* scratch = arena.take<float>((size_t)N * K * (dim + 1));
+    if (!arena.ok()) {
+        set_error("gaussian_moment_match: workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    const size_t smem = (size_t)MM_WARPS * ((size_t)2 * dim * (dim + 1) + (size_t)dim * 64 + 4 * dim) * sizeof(float);
+    FB2_CUDA(cudaFuncSetAttribute(gaussian_moment_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = ceil_div(N, MM_WARPS);
+    FB2_REQUIRE(blocks < (1ll << 31), "too many elements for one launch");
+    gaussian_moment_match<<<(unsigned)blocks, MM_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(logits, Lam, eta, c, N, K, dim, scratch, Lo, eo,
+                                                                                                       co, status_flag);
     FB2_LAUNCH_CHECK();
     return FB2_OK;
 }

@@ -11,6 +11,9 @@ more-specific rules to funsor's `eager` interpretation for the torch backend:
                                                            the Gaussian scan (gaussian.py:841-1132 per level) as ONE
                                                            information-form chain kernel; the result is converted back
                                                            to the reference's (white_vec, prec_sqrt) + Tensor form
+  moment_matching: Contraction[Logaddexp, Add, frozenset, Tensor, Gaussian]
+                                                           the mixture collapse of funsor/joint.py:102-150 (SwitchingLinearHMM,
+                                                           pyro/hmm.py:527-551) as ONE kernel per contraction
   Contraction[Logaddexp, Add, frozenset, Gaussian | GaussianMixture, Gaussian | GaussianMixture]
                                                            one level of that scan when sequential_sum_product is called
                                                            directly (pyro/hmm.py:269): replaces cnf.py:385-389
@@ -40,7 +43,8 @@ import torch
 
 _STATE = {"registered": False, "calls": {"contraction_fast": 0, "contraction_delegated": 0,
                                          "markov_fast": 0, "markov_delegated": 0, "gaussian_homogeneous": 0,
-                                         "gaussian_contraction_fast": 0, "gaussian_contraction_delegated": 0}}
+                                         "gaussian_contraction_fast": 0, "gaussian_contraction_delegated": 0,
+                                         "moment_matching_fast": 0, "moment_matching_delegated": 0}}
 
 
 def stats(reset=False):
@@ -265,6 +269,12 @@ def _kernel_info_to_sqrt(Lam, eta, c):
     return fg.info_to_sqrt(Lam, eta, c)
 
 
+def _kernel_moment_match(logits, Lam, eta, c):
+    from . import gaussian as fg
+
+    return fg.gaussian_moment_match(logits, Lam, eta, c)
+
+
 def _fast_ok(*datas):
     return all(isinstance(d, torch.Tensor) and d.is_cuda and d.dtype == torch.float32 for d in datas)
 
@@ -277,7 +287,8 @@ def _no_grad_needed(*datas):
 # drive the rules' fast branches inside the unmodified reference without a GPU (tests/test_funsor_plugin.py); on the GPU box
 # the defaults below are what runs (tests/test_gpu_funsor.py).
 _HOOKS = {"fast_ok": _fast_ok, "matmul": _kernel_matmul, "chain": _kernel_chain, "gaussian_chain": _kernel_gaussian_chain,
-          "sqrt_to_info": _kernel_sqrt_to_info, "gaussian_pair": _kernel_gaussian_pair, "info_to_sqrt": _kernel_info_to_sqrt}
+          "sqrt_to_info": _kernel_sqrt_to_info, "gaussian_pair": _kernel_gaussian_pair, "info_to_sqrt": _kernel_info_to_sqrt,
+          "moment_match": _kernel_moment_match}
 _DEFAULT_HOOKS = dict(_HOOKS)
 
 
@@ -514,6 +525,59 @@ def register():
     for tx_ in (Gaussian, GaussianMixture):
         for ty_ in (Gaussian, GaussianMixture):
             eager.register(Contraction, fops.LogaddexpOp, fops.AddOp, frozenset, tx_, ty_)(gaussian_contraction_rule)
+
+    # ---- moment matching (joint.py:102-150): collapse the mixture components indexed by the reduced discrete inputs
+    from funsor.interpretations import moment_matching
+
+    def moment_matching_rule(red_op, bin_op, reduced_vars, discrete, gaussian):
+        approx_vars = frozenset(v for v in reduced_vars & gaussian.input_vars if v.dtype != "real")
+        datas = (discrete.data, gaussian.white_vec, gaussian.prec_sqrt)
+        reals = [(k, d) for k, d in gaussian.inputs.items() if d.dtype == "real"]
+        n = sum(d.num_elements for _, d in reals)
+        fast = (approx_vars and approx_vars == reduced_vars and isinstance(discrete, Tensor) and discrete.dtype == "real" and not discrete.shape
+                and all(v.name in discrete.inputs for v in approx_vars) and all(d.dtype != "real" for d in discrete.inputs.values())
+                and _HOOKS["fast_ok"](*datas) and _no_grad_needed(*datas) and 1 <= n <= 64 and gaussian.rank >= n)
+        if fast:
+            approx = [k for k in gaussian.inputs if k in {v.name for v in approx_vars}]
+            all_ints = OrderedDict(discrete.inputs)
+            all_ints.update((k, d) for k, d in gaussian.inputs.items() if d.dtype != "real")
+            binputs = OrderedDict((k, d) for k, d in all_ints.items() if k not in approx)  # order of new_loc.inputs (joint.py:127-128)
+            order = list(binputs) + approx
+            bshape = tuple(d.size for d in binputs.values())
+            K = 1
+            for k in approx:
+                K *= all_ints[k].size
+            N = 1
+            for d_ in bshape:
+                N *= d_
+
+            def aligned(t, names, tail):
+                names = list(names)
+                perm = [names.index(k) for k in order if k in names]
+                t = t.permute(perm + list(range(len(names), t.dim())))
+                t = t.reshape([all_ints[k].size if k in names else 1 for k in order] + list(tail))
+                return t.expand([all_ints[k].size for k in order] + list(tail)).reshape((N * K,) + tuple(tail))
+
+            gints = [k for k, d in gaussian.inputs.items() if d.dtype != "real"]
+            r = gaussian.rank
+            w = aligned(gaussian.white_vec, gints, (r,))
+            P = aligned(gaussian.prec_sqrt, gints, (n, r))
+            logits = aligned(discrete.data, list(discrete.inputs), ())
+            Lam, eta, c = _HOOKS["sqrt_to_info"](w, P, w.new_zeros(N * K))
+            Lo, eo, co = _HOOKS["moment_match"](logits.reshape(N, K), Lam.reshape(N, K, n, n), eta.reshape(N, K, n), c.reshape(N, K))
+            wv, Ps, sc = _HOOKS["info_to_sqrt"](Lo, eo, co)
+            ginputs = binputs.copy()
+            ginputs.update(reals)
+            _STATE["calls"]["moment_matching_fast"] += 1
+            return Tensor(sc.reshape(bshape), binputs) + Gaussian(white_vec=wv.reshape(bshape + (n,)), prec_sqrt=Ps.reshape(bshape + (n, n)),
+                                                                  inputs=ginputs)
+        _STATE["calls"]["moment_matching_delegated"] += 1
+        return prev_mm(red_op, bin_op, reduced_vars, discrete, gaussian)
+
+    smd = Tensor(torch.zeros(2), OrderedDict(k=Bint[2]))
+    smg = Gaussian(white_vec=torch.zeros(2, 1), prec_sqrt=torch.ones(2, 1, 1), inputs=OrderedDict(k=Bint[2], x=Reals[1]))
+    prev_mm = moment_matching.dispatch(Contraction, fops.logaddexp, fops.add, frozenset({Variable("k", Bint[2])}), smd, smg)
+    moment_matching.register(Contraction, fops.LogaddexpOp, fops.AddOp, frozenset, Tensor, Gaussian)(moment_matching_rule)
 
     _STATE["registered"] = True
 

@@ -59,6 +59,36 @@ def info_to_sqrt(Lam, eta, c, rel_tol=0.0, return_rank=False):
     return (w, P, s, rank) if return_rank else (w, P, s)
 
 
+def gaussian_moment_match(logits, Lam, eta, c, validate=True):
+    """Collapse mixtures of K Gaussians into single Gaussians with the mixture's mass, mean and covariance -- the
+    `moment_matching` interpretation's Contraction[Logaddexp, Add, {discrete}, Tensor, Gaussian] (joint.py:102-150), used by the
+    SwitchingLinearHMM scan (pyro/hmm.py:527-551).  logits[..., K], Lam[..., K, n, n], eta[..., K, n], c[..., K]
+    -> (Lam[..., n, n], eta[..., n], c[...])."""
+    for t_ in (logits, Lam, eta, c):
+        _dev_f32(t_, "mixture component")
+    batch = Lam.shape[:-3]
+    K, n = Lam.shape[-3], Lam.shape[-1]
+    if K < 1 or n < 1 or n > 64:
+        raise ValueError("gaussian_moment_match: K >= 1 components over at most 64 real dimensions, got K={} n={}".format(K, n))
+    Lam = Lam.contiguous()
+    eta = eta.expand(batch + (K, n)).contiguous()
+    c = c.expand(batch + (K,)).contiguous()
+    logits = logits.expand(batch + (K,)).contiguous()
+    N = int(torch.Size(batch).numel())
+    Lo = torch.empty(batch + (n, n), dtype=torch.float32, device=Lam.device)
+    eo = torch.empty(batch + (n,), dtype=torch.float32, device=Lam.device)
+    co = torch.empty(batch, dtype=torch.float32, device=Lam.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=Lam.device)
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_gaussian_moment_match_workspace_bytes(N, K, n), Lam.device)
+    with torch.cuda.device(Lam.device):
+        check(lib.fb2_gaussian_moment_match_f32(logits.data_ptr(), Lam.data_ptr(), eta.data_ptr(), c.data_ptr(), N, K, n, Lo.data_ptr(),
+                                                eo.data_ptr(), co.data_ptr(), flag.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    if validate and bool(flag.any()):
+        raise ValueError("gaussian_moment_match: a component precision (or the matched covariance) is not positive definite")
+    return Lo, eo, co
+
+
 def gaussian_pair_combine(x, y):
     """Contraction[logaddexp, add] of two chain elements x over (a;b) and y over (b;c) (cnf.py:385-389).
     x, y: tuples (Lam[..., 2D, 2D], eta[..., 2D], c[...]) with identical batch shapes."""

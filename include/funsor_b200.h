@@ -148,6 +148,17 @@ int fb2_gaussian_sqrt_to_info_f32(const float* w, const float* P, const float* s
  *                <= rel_tol * max diagonal; rel_tol <= 0 selects dim * 1.2e-7) are zero.  rank (nullable) int32 [N]. */
 int fb2_gaussian_info_to_sqrt_f32(const float* Lam, const float* eta, const float* c, int64_t N, int32_t dim, float rel_tol,
                                   float* w, float* P, float* s, int32_t* rank, void* stream);
+/* moment_match : collapse a mixture of K Gaussians per element into ONE Gaussian with the mixture's mass, mean and covariance.
+ *                Replaces: moment_matching_contract_joint funsor/joint.py:102-150 (the Contraction[Logaddexp, Add, {discrete}, Tensor,
+ *                Gaussian] rule of the `moment_matching` interpretation; SwitchingLinearHMM pyro/hmm.py:527-551).
+ *                logits[N,K], Lam[N,K,dim,dim], eta[N,K,dim], c[N,K] (component k is exp(logit_k + c_k - x Lam_k x'/2 + x eta_k)) ->
+ *                Lo[N,dim,dim], eo[N,dim], co[N]: a normalised Gaussian density scaled by the total mass.  An empty mixture (all
+ *                logits -inf) yields co = -inf with unit covariance (joint.py:141-143).  status_flag (nullable) is raised on a
+ *                non-positive pivot. */
+size_t fb2_gaussian_moment_match_workspace_bytes(int64_t N, int32_t K, int32_t dim);
+int fb2_gaussian_moment_match_f32(const float* logits, const float* Lam, const float* eta, const float* c, int64_t N, int32_t K,
+                                  int32_t dim, float* Lo, float* eo, float* co, int32_t* status_flag, void* workspace,
+                                  size_t workspace_bytes, void* stream);
 int fb2_gaussian_pair_combine_f32(const float* Lx, const float* ex, const float* cx, int64_t x_stride,
                                   const float* Ly, const float* ey, const float* cy, int64_t y_stride,
                                   int64_t n0, int64_t n1, int64_t x_s0, int64_t y_s0, int32_t D, float* Lo,

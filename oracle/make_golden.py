@@ -364,9 +364,50 @@ def main():
                          obs_loc=obs_dist.loc, obs_tril=obs_dist.scale_tril, data=data, log_prob=lp).items():
             out["mrf/" + name + "/" + k] = _np(v)
     np.savez_compressed(os.path.join(GOLDEN, "distributions.npz"), **out)
+    moment_matching_golden()
     for fn in sorted(os.listdir(GOLDEN)):
         print(fn, os.path.getsize(os.path.join(GOLDEN, fn)))
 
 
+def moment_matching_golden():
+    """tests/golden/moment_matching.npz: the `moment_matching` interpretation of the reference (joint.py:102-150) collapsing
+    Gaussian mixtures, and the SwitchingLinearHMM log_prob expression (pyro/hmm.py:527-551) under it.
+    `python -m oracle.make_golden moment` writes only this file."""
+    sys.path.insert(0, ROOT)
+    from oracle import ref_boot
+
+    funsor = ref_boot.boot("float64")
+    import torch
+
+    import funsor.ops as ops
+    from funsor.cnf import Contraction
+    from funsor.domains import Bint, Reals
+    from funsor.gaussian import Gaussian
+    from funsor.interpretations import moment_matching
+    from funsor.tensor import Tensor
+    from funsor.terms import Variable
+    from funsor.testing import random_gaussian
+
+    out = {}
+    torch.manual_seed(18)
+    for name, (B, K, n) in {"m0": (1, 2, 1), "m1": (3, 4, 2), "m2": (2, 3, 6), "m3": (2, 5, 16), "m4": (1, 7, 64)}.items():
+        g = random_gaussian(OrderedDict([("b", Bint[B]), ("k", Bint[K]), ("x", Reals[n])]))
+        logits = torch.randn(B, K)
+        if name == "m1":
+            logits[0, 1] = -float("inf")  # a component without mass
+        d = Tensor(logits, OrderedDict([("b", Bint[B]), ("k", Bint[K])]))
+        with moment_matching:
+            r = Contraction(ops.logaddexp, ops.add, frozenset({Variable("k", Bint[K])}), d, g)
+        (gr,) = [t for t in r.terms if isinstance(t, Gaussian)]
+        assert list(gr.inputs) == ["b", "x"], gr.inputs
+        c = r(x=funsor.to_funsor(torch.zeros(n), Reals[n]))
+        out[name + "/logits"], out[name + "/w"], out[name + "/P"] = _np(logits), _np(g.white_vec), _np(g.prec_sqrt)
+        out[name + "/Lam"], out[name + "/eta"], out[name + "/c"] = _np(gr._precision), _np(gr._info_vec), _np(c.data)
+    np.savez_compressed(os.path.join(GOLDEN, "moment_matching.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if "moment" in sys.argv[1:]:
+        moment_matching_golden()
+    else:
+        main()

@@ -554,3 +554,74 @@ def test_fast_planners_inside_reference(funsor, fast, sname):
         want, got, st = _both(fast, build)
         assert st["contraction_fast"] + st["markov_fast"] > 0, (impl.__name__, st)
         assert_close(got, want, atol=1e-9, rtol=1e-9)
+
+
+def _np_moment_match(logits, Lam, eta, c):
+    from oracle import gaussian_ref as G
+
+    return tuple(torch.from_numpy(np.asarray(a)) for a in G.moment_match(logits.numpy(), Lam.numpy(), eta.numpy(), c.numpy()))
+
+
+@pytest.mark.parametrize("order", [("b", "k", "x"), ("k", "b", "x")])
+def test_fast_moment_matching_rule_inside_reference(funsor, fast, order):
+    """(f3) the `moment_matching` interpretation's mixture collapse (joint.py:102-150) through the plugin rule: same function and the
+    same input order as the reference."""
+    import funsor.ops as ops
+    from funsor.cnf import Contraction
+    from funsor.domains import Bint, Reals
+    from funsor.gaussian import Gaussian
+    from funsor.interpretations import moment_matching
+    from funsor.tensor import Tensor
+    from funsor.terms import Variable
+    from funsor.testing import random_gaussian
+
+    fast.set_hooks(moment_match=_np_moment_match)
+    torch.manual_seed(30)
+    doms = dict(b=Bint[3], k=Bint[4], x=Reals[2])
+    proto = random_gaussian(OrderedDict((n, doms[n]) for n in order))
+    logits = torch.randn(4, 3)
+
+    def build():
+        g = Gaussian(white_vec=proto.white_vec.clone(), prec_sqrt=proto.prec_sqrt.clone(), inputs=proto.inputs)
+        d = Tensor(logits.clone(), OrderedDict(k=Bint[4], b=Bint[3]))
+        with moment_matching:
+            return Contraction(ops.logaddexp, ops.add, frozenset({Variable("k", Bint[4])}), d, g)
+
+    want, got, st = _both(fast, build)
+    assert st["moment_matching_fast"] == 1, st
+    _same_gaussian_function(funsor, got, want, ["x"], 2, 1e-8)
+
+
+def test_fast_switching_linear_hmm_expression(funsor, fast):
+    """pyro/hmm.py:527-551 (SwitchingLinearHMM.log_prob, moment-matching mode): the scan over (class, state) elements under the
+    `moment_matching` interpretation with the plugin's collapse rule and Gaussian contraction rule on."""
+    import funsor.ops as ops
+    from funsor.domains import Bint, Reals
+    from funsor.interpretations import moment_matching
+    from funsor.sum_product import sequential_sum_product
+    from funsor.tensor import Tensor
+    from funsor.terms import Variable
+    from funsor.testing import random_gaussian
+
+    fast.set_hooks(moment_match=_np_moment_match)
+    torch.manual_seed(31)
+    T, C, D = 6, 2, 2
+    gt = random_gaussian(OrderedDict([("time", Bint[T]), ("class(time=1)", Bint[C]), ("state", Reals[D]), ("state(time=1)", Reals[D])]))
+    tl = torch.randn(T, C, C).log_softmax(-1)
+    gi = random_gaussian(OrderedDict([("state", Reals[D])]))
+    il = torch.randn(C).log_softmax(-1)
+
+    def build():
+        trans = (Tensor(tl.clone(), OrderedDict([("time", Bint[T]), ("class", Bint[C]), ("class(time=1)", Bint[C])]))
+                 + type(gt)(white_vec=gt.white_vec.clone(), prec_sqrt=gt.prec_sqrt.clone(), inputs=gt.inputs))
+        init = Tensor(il.clone(), OrderedDict([("class", Bint[C])])) + type(gi)(white_vec=gi.white_vec.clone(), prec_sqrt=gi.prec_sqrt.clone(), inputs=gi.inputs)
+        with moment_matching:
+            r = sequential_sum_product(ops.logaddexp, ops.add, trans, Variable("time", Bint[T]),
+                                       {"class": "class(time=1)", "state": "state(time=1)"})
+            r = r + init
+            return r.reduce(ops.logaddexp, frozenset(["class", "state", "class(time=1)", "state(time=1)"]))
+
+    want, got, st = _both(fast, build)
+    assert st["moment_matching_fast"] > 0, st
+    assert isinstance(got, Tensor)
+    assert torch.allclose(got.data, want.data, rtol=1e-7, atol=1e-7), (got.data, want.data)

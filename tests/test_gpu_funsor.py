@@ -505,3 +505,83 @@ def test_plated_markov_planners_through_the_rules(funsor, plugin, sname, impl, x
     assert st["contraction_fast"] + st["markov_fast"] > 0, st
     assert isinstance(got, Tensor) and not got.inputs
     rel_close(got.data.cpu().numpy(), want.data.numpy(), rtol=1e-5, atol=1.0)
+
+
+# ------------------------------------------------------------------------------------------------ (f3) moment matching / SwitchingLinearHMM
+def test_moment_matching_rule_inside_reference(funsor, plugin):
+    import funsor.ops as ops
+    from funsor.cnf import Contraction
+    from funsor.domains import Bint, Reals
+    from funsor.gaussian import Gaussian
+    from funsor.interpretations import moment_matching
+    from funsor.tensor import Tensor
+    from funsor.terms import Variable
+    from funsor.testing import random_gaussian
+
+    torch.manual_seed(30)
+    torch.set_default_dtype(torch.float64)
+    try:
+        proto = random_gaussian(OrderedDict([("b", Bint[3]), ("k", Bint[4]), ("x", Reals[6])]))
+    finally:
+        torch.set_default_dtype(torch.float32)
+    logits = torch.randn(4, 3, dtype=torch.float64)
+
+    def build(put):
+        g = Gaussian(white_vec=put(proto.white_vec), prec_sqrt=put(proto.prec_sqrt), inputs=proto.inputs)
+        d = Tensor(put(logits), OrderedDict(k=Bint[4], b=Bint[3]))
+        with moment_matching:
+            return Contraction(ops.logaddexp, ops.add, frozenset({Variable("k", Bint[4])}), d, g)
+
+    torch.set_default_dtype(torch.float64)
+    try:
+        want = build(lambda t: t.clone())
+    finally:
+        torch.set_default_dtype(torch.float32)
+    plugin.stats(reset=True)
+    got = build(lambda t: t.float().to(DEV))
+    assert plugin.stats()["moment_matching_fast"] == 1, plugin.stats()
+    _same_function(funsor, got, want, ["x"], 6, 2e-4)
+
+
+@pytest.mark.parametrize("T,C,D", [(6, 2, 2), (16, 3, 4), (9, 2, 8)])
+def test_switching_linear_hmm_expression_inside_reference(funsor, plugin, T, C, D):
+    """pyro/hmm.py:527-551 (SwitchingLinearHMM.log_prob, moment-matching mode) evaluated by funsor on CUDA: the scan over
+    (class, state) elements under `moment_matching`, with the mixture collapse and the Gaussian pair contraction on the kernels."""
+    import funsor.ops as ops
+    from funsor.domains import Bint, Reals
+    from funsor.interpretations import moment_matching
+    from funsor.sum_product import sequential_sum_product
+    from funsor.tensor import Tensor
+    from funsor.terms import Variable
+    from funsor.testing import random_gaussian
+
+    torch.manual_seed(31)
+    torch.set_default_dtype(torch.float64)
+    try:
+        gt = random_gaussian(OrderedDict([("time", Bint[T]), ("class(time=1)", Bint[C]), ("state", Reals[D]), ("state(time=1)", Reals[D])]))
+        gi = random_gaussian(OrderedDict([("state", Reals[D])]))
+        tl = torch.randn(T, C, C).log_softmax(-1)
+        il = torch.randn(C).log_softmax(-1)
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+    def build(put):
+        trans = (Tensor(put(tl), OrderedDict([("time", Bint[T]), ("class", Bint[C]), ("class(time=1)", Bint[C])]))
+                 + type(gt)(white_vec=put(gt.white_vec), prec_sqrt=put(gt.prec_sqrt), inputs=gt.inputs))
+        init = Tensor(put(il), OrderedDict([("class", Bint[C])])) + type(gi)(white_vec=put(gi.white_vec), prec_sqrt=put(gi.prec_sqrt), inputs=gi.inputs)
+        with moment_matching:
+            r = sequential_sum_product(ops.logaddexp, ops.add, trans, Variable("time", Bint[T]),
+                                       {"class": "class(time=1)", "state": "state(time=1)"})
+            r = r + init
+            return r.reduce(ops.logaddexp, frozenset(["class", "state", "class(time=1)", "state(time=1)"]))
+
+    torch.set_default_dtype(torch.float64)
+    try:
+        want = build(lambda t: t.clone())
+    finally:
+        torch.set_default_dtype(torch.float32)
+    plugin.stats(reset=True)
+    got = build(lambda t: t.float().to(DEV))
+    assert plugin.stats()["moment_matching_fast"] > 0, plugin.stats()
+    assert isinstance(got, Tensor) and got.data.is_cuda
+    assert abs(float(got.data) - float(want.data)) <= 1e-4 * (1 + abs(float(want.data))), (float(got.data), float(want.data))

@@ -240,3 +240,44 @@ def test_kalman_posterior_sample_moments_at_scale():
     xv = x.double().var(1).cpu().numpy().reshape(B, -1)
     assert np.abs(xv / sd ** 2 - 1).max() < 0.2
     assert bool(torch.isfinite(log_q).all())
+
+
+# ------------------------------------------------------------------------------------------------ (f3) moment matching
+@pytest.mark.gpu
+def test_moment_match_kernel_golden():
+    """fb2_gaussian_moment_match_f32 against tests/golden/moment_matching.npz (the reference's `moment_matching` interpretation,
+    joint.py:102-150, run by oracle/make_golden.py)"""
+    import funsor_b200.gaussian as fg
+
+    for name, d in golden_cases(load_golden("moment_matching")).items():
+        w, P = torch.tensor(d["w"], dtype=torch.float32, device="cuda"), torch.tensor(d["P"], dtype=torch.float32, device="cuda")
+        Lam, eta, c = fg.sqrt_to_info(w, P)
+        Lo, eo, co = fg.gaussian_moment_match(torch.tensor(d["logits"], dtype=torch.float32, device="cuda"), Lam, eta, c)
+        for label, a, b in (("Lam", Lo, d["Lam"]), ("eta", eo, d["eta"]), ("c", co, d["c"])):
+            a = a.cpu().double().numpy()
+            err = np.abs(a - b).max() / max(1.0, np.abs(b).max())
+            assert err <= (5e-4 if name == "m4" else 5e-5), (name, label, err)  # m4: 64 reals, random (ill-conditioned) precisions
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,K,n", [(5, 1, 3), (7, 2, 1), (100, 4, 8), (33, 6, 32), (9, 3, 64), (3, 17, 5)])
+def test_moment_match_kernel_random(N, K, n):
+    import funsor_b200.gaussian as fg
+
+    rng = np.random.default_rng(N + K + n)
+    A = rng.standard_normal((N, K, n, 2 * n))
+    Lam = A @ A.transpose(0, 1, 3, 2) / (2 * n) + 0.5 * np.eye(n)  # well-conditioned component precisions
+    mu = rng.standard_normal((N, K, n))
+    eta = (Lam @ mu[..., None])[..., 0]
+    c = rng.standard_normal((N, K))
+    logits = rng.standard_normal((N, K))
+    if K > 1:
+        logits[0, 0] = -np.inf
+        logits[-1, :] = -np.inf  # an empty mixture: mass -inf, unit covariance (joint.py:141-143)
+    want = G.moment_match(logits, Lam, eta, c)
+    got = fg.gaussian_moment_match(*[torch.tensor(a, dtype=torch.float32, device="cuda") for a in (logits, Lam, eta, c)])
+    for label, a, b in zip(("Lam", "eta", "c"), got, want):
+        a = a.cpu().double().numpy()
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), fin), label
+        assert np.abs(a[fin] - b[fin]).max() <= 2e-5 * max(1.0, np.abs(b[fin]).max()), (label, np.abs(a[fin] - b[fin]).max())

@@ -195,3 +195,16 @@ def test_dense_posterior_oracle_agrees_with_the_sequential_filter():
         np.testing.assert_allclose(logZ, d["logprob"], rtol=1e-8, atol=1e-8)
         np.testing.assert_allclose(logZ, G.kalman_filter_logprob(*args), rtol=1e-9, atol=1e-9)
         assert np.all(np.linalg.eigvalsh(cov) > 0)
+
+
+def test_moment_matching_oracle_matches_reference_fixture():
+    """oracle/gaussian_ref.moment_match (joint.py:102-150 restated) against tests/golden/moment_matching.npz, which
+    oracle/make_golden.py wrote by running the reference's `moment_matching` interpretation."""
+    from oracle import gaussian_ref as G
+
+    for name, d in golden_cases(load_golden("moment_matching")).items():
+        Lam, eta, c = G.sqrt_to_info(d["w"], d["P"], np.zeros(d["w"].shape[:-1]))
+        Lo, eo, co = G.moment_match(d["logits"], Lam, eta, c)
+        np.testing.assert_allclose(Lo, d["Lam"], rtol=1e-9, atol=1e-9, err_msg=name)
+        np.testing.assert_allclose(eo, d["eta"], rtol=1e-9, atol=1e-9, err_msg=name)
+        np.testing.assert_allclose(co, d["c"], rtol=1e-9, atol=1e-9, err_msg=name)
