@@ -45,6 +45,8 @@ SIGNATURES = {
     "fb2_hmm_marginals_f32": (c_int, [_fp, c_int64, _fp, c_int64, c_int64, _fp, c_int64, c_int64, c_int32, _fp, _fp, _fp, _fp, c_size_t, c_void_p]),
     "fb2_hmm_chunk_summary_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "fb2_hmm_chunk_summary_f32": (c_int, [c_int, _fp, c_int64, c_int64, _fp, c_int64, c_int64, c_int32, _fp, _fp, _fp, c_size_t, c_void_p]),
+    "fb2_hmm_chunk_summary_gemm_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int64]),
+    "fb2_hmm_chunk_summary_gemm_f32": (c_int, [_fp, _fp, c_int64, c_int32, c_int64, _fp, _fp, _fp, c_size_t, c_void_p]),
     "fb2_hmm_backward_sample_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int64, c_int64]),
     "fb2_hmm_backward_sample_f32": (c_int, [_fp, c_int64, _fp, c_int64, c_int64, _fp, _fp, _fp, c_int64, c_int64, c_int32, c_int64, _fp, _fp, _fp, c_size_t, c_void_p]),
     "fb2_chain_adjoint_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfunsor_b200.so")
 OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["capi.cu", "semiring_matmul.cu", "log_matmul_tc.cu", "hmm_scan.cu", "hmm_flow.cu", "hmm_small.cu", "hmm_sample.cu", "gaussian.cu"]
+SOURCES = ["capi.cu", "semiring_matmul.cu", "log_matmul_tc.cu", "chain_gemm_tc.cu", "hmm_scan.cu", "hmm_flow.cu", "hmm_small.cu", "hmm_sample.cu", "gaussian.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--use_fast_math=false",

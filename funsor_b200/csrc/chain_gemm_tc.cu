@@ -1,0 +1,703 @@
+// Linear-domain matrix-chain products on the 5th-generation tensor cores: TMA-fed, warp-specialised 3xTF32 GEMM.
+//
+// What it computes.  The chunk summary of a time-sharded HMM (mixed_sequential_sum_product sum_product.py:766-795 with
+// segments = GPUs) and every large dense scan are chains of S x S matrix products in the log semiring (sequential_sum_product
+// sum_product.py:652-701; one level = Contraction[Logaddexp, Add, Tensor, Tensor] cnf.py:335-379).  The reference's own trick
+// (einsum/numpy_log.py:24-47: subtract a shift, exp, multiply, log, add the shift back) is applied ONCE per chain instead of once per
+// level: all elements of the tree are kept in the LINEAR domain as non-negative fp32 values times a power of two per matrix, so that a
+// level is a plain GEMM.  A matrix lives as two planes, hi = the TF32 truncation of the value and lo = value - hi (exact in fp32, its
+// own TF32 truncation carries 21+ mantissa bits together with hi), and a product is hi*hi + lo*hi + hi*lo with fp32 accumulation in
+// tensor memory.  The planes are written by the epilogue of the level below, so the main loop does nothing but move tiles and issue
+// tensor instructions:
+//
+//     warp 0  producer : cp.async.bulk.tensor (TMA, 128-byte swizzle) of the A / B tiles of one K chunk into a 2-stage ring,
+//                        mbarrier complete_tx
+//     warp 1  MMA      : tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 256, K = 8; 12 instructions per chunk; tcgen05.commit
+//                        releases the stage; the last commit hands the accumulators to the epilogue
+//     warps 2-5 epilogue: tcgen05.ld, optional column scaling (the observation of the second step of a leaf pair), exact power-of-two
+//                        renormalisation, hi / lo split, stores in the orientation the NEXT level needs, per-matrix max by atomicMax
+//
+// Orientation.  Both MMA operands are K-major in shared memory, so a matrix that will be a RIGHT operand is stored transposed.  In
+// the reference's tree (pairs (2p, 2p+1), odd leftover appended, sum_product.py:690-701) the role of an element is the parity of its
+// index at the level where it is finally paired; the host walks the carry chain of the last element and tells the kernel.
+//
+// Scaling.  stored = true / 2^E with an integer E per matrix: leaves are <= 1; the epilogue multiplies by 2^-(ea + eb), ea / eb the
+// binary exponents of the operands' largest stored entries (read from the level below), which bounds every stored value by 4 K and
+// keeps E exact.  Entries more than ~2^-126 below the largest entry of their matrix flush to zero (the same statement as for the
+// dataflow kernels).
+//
+// Accumulation bias: as in log_matmul_tc.cu the correction products have their own accumulator and the hi*hi sum is multiplied by
+// 1 + 5.82e-8 * (number of accumulations) (measured one-sided truncation of the tensor-memory accumulator).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace fb2 {
+
+constexpr int CG_BM = 128, CG_BN = 256, CG_KC = 32, CG_STAGES = 2;
+constexpr int CG_A_PLANE = CG_BM * CG_KC * 4;  // 16 KB
+constexpr int CG_B_PLANE = CG_BN * CG_KC * 4;  // 32 KB
+constexpr int CG_STAGE_BYTES = 2 * CG_A_PLANE + 2 * CG_B_PLANE;  // 96 KB
+constexpr int CG_SMEM = CG_STAGES * CG_STAGE_BYTES + 1024;
+constexpr int CG_THREADS = 192;
+
+struct ChainGemmArgs {
+    // outputs of this level
+    float* out;            // planes [n_out][2][S][S] (orientation per element), or [n_out][S][S] fp32 when final_sum
+    unsigned* zmax_out;    // [n_out] bits of the largest stored entry (zeroed before the launch)
+    int* E_out;            // [n_out]
+    // scaling state of the operands
+    const unsigned* zmax_a;  // [n_a] or nullptr (= 1.0)
+    const int* E_a;          // [n_a] or nullptr (= 0)
+    const unsigned* zmax_b;
+    const int* E_b;
+    const float* colscale;   // nullable [pairs][S]: out[:, j] *= colscale[p][j]
+    int S;
+    int a_shared;          // 1: every pair uses element 0 of the A tensor map (the transition matrix P)
+    int a_stride, a_off;   // A element of pair p = a_stride * p + a_off (in the A map's element index)
+    int b_stride, b_off;
+    int last_transposed;   // orientation of the LAST output element (others: parity of the output index)
+    int n_out;
+    int final_sum;         // 1: write hi + lo as one fp32 matrix, row-major (the result of a tree)
+    float comp;
+};
+
+__device__ __forceinline__ uint32_t cg_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t cg_desc(uint32_t addr) {  // K-major, 128-byte swizzle, 8-row groups 1024 B apart
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void cg_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void cg_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cg_tma_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void cg_tmem_ld16(uint32_t taddr, uint32_t (&d)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]),
+          "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// One CTA = one 128 x 256 tile of one product.  grid = (tiles, pairs).
+__global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                               ChainGemmArgs a) {
+    extern __shared__ unsigned char cg_smem_raw[];
+    __shared__ __align__(8) unsigned long long s_full[CG_STAGES], s_empty[CG_STAGES], s_done;
+    __shared__ uint32_t s_tmem;
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cg_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = a.S;
+    const int tiles_n = (S + CG_BN - 1) / CG_BN;
+    const int tile = blockIdx.x;
+    const int i0 = (tile / tiles_n) * CG_BM, j0 = (tile % tiles_n) * CG_BN;
+    const int p = blockIdx.y;
+    const int ia = a.a_shared ? 0 : a.a_stride * p + a.a_off;
+    const int ib = a.b_stride * p + a.b_off;
+    const int nchunks = S / CG_KC;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < CG_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_full[s])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_empty[s])) : "memory");
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_done)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cg_u32(&s_tmem)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    if (warp == 0) {
+        // ---------------- producer
+        if (lane == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % CG_STAGES;
+                if (c >= CG_STAGES) cg_wait(cg_u32(&s_empty[s]), ((c / CG_STAGES) - 1) & 1);
+                const uint32_t bar = cg_u32(&s_full[s]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)CG_STAGE_BYTES) : "memory");
+                const uint32_t st = cg_u32(smem + (size_t)s * CG_STAGE_BYTES);
+                const int k0 = c * CG_KC;
+                cg_tma_3d(st, &map_a, k0, i0, 2 * ia, bar);
+                cg_tma_3d(st + CG_A_PLANE, &map_a, k0, i0, 2 * ia + 1, bar);
+                cg_tma_3d(st + 2 * CG_A_PLANE, &map_b, k0, j0, 2 * ib, bar);
+                cg_tma_3d(st + 2 * CG_A_PLANE + CG_B_PLANE, &map_b, k0, j0, 2 * ib + 1, bar);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer
+        constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CG_BN >> 3) << 17) | ((128u >> 4) << 24);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % CG_STAGES;
+            cg_wait(cg_u32(&s_full[s]), (c / CG_STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t ah = cg_u32(smem + (size_t)s * CG_STAGE_BYTES), al = ah + CG_A_PLANE, bh = ah + 2 * CG_A_PLANE, bl = bh + CG_B_PLANE;
+#pragma unroll
+                for (int ks = 0; ks < CG_KC / 8; ++ks) {
+                    const uint64_t dah = cg_desc(ah + ks * 32), dal = cg_desc(al + ks * 32);
+                    const uint64_t dbh = cg_desc(bh + ks * 32), dbl = cg_desc(bl + ks * 32);
+                    cg_mma(tmem, dah, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                    cg_mma(tmem + CG_BN, dal, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                    cg_mma(tmem + CG_BN, dah, dbl, IDESC, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cg_u32(&s_empty[s])) : "memory");
+                if (c == nchunks - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cg_u32(&s_done)) : "memory");
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- epilogue: warp w owns tensor-memory lanes 32 (w % 4) ..
+        const int q4 = warp & 3;
+        const int row = i0 + q4 * 32 + lane;
+        // scaling state of the operands -> exact power-of-two renormalisation
+        const float za = a.zmax_a ? __uint_as_float(a.zmax_a[ia]) : 1.f;
+        const float zb = a.zmax_b ? __uint_as_float(a.zmax_b[ib]) : 1.f;
+        int ea = 0, eb = 0;
+        if (za > 0.f) frexpf(za, &ea);
+        if (zb > 0.f) frexpf(zb, &eb);
+        const float scale = ldexpf(1.f, -(ea + eb));
+        const bool transposed = a.final_sum ? false : (p == a.n_out - 1 ? a.last_transposed != 0 : (p & 1) != 0);
+        if (tile == 0 && warp == 2 && lane == 0)
+            a.E_out[p] = (a.E_a ? a.E_a[ia] : 0) + (a.E_b ? a.E_b[ib] : 0) + ea + eb;
+        const float fmain = 1.f + a.comp * (float)(nchunks * (CG_KC / 8));
+        const size_t SS = (size_t)S * S;
+        float* out_hi = a.out + (size_t)p * (a.final_sum ? SS : 2 * SS);
+        float* out_lo = out_hi + SS;
+        const float* cs = a.colscale ? a.colscale + (size_t)p * S : nullptr;
+        cg_wait(cg_u32(&s_done), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float vmax = 0.f;
+        const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll 1
+        for (int cc = 0; cc < CG_BN; cc += 16) {
+            if (j0 + cc >= S) break;  // warp-uniform
+            uint32_t r0[16], r1[16];
+            cg_tmem_ld16(lane_base + (uint32_t)cc, r0);
+            cg_tmem_ld16(lane_base + (uint32_t)(CG_BN + cc), r1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                float z = fmaf(__uint_as_float(r0[q]), fmain, __uint_as_float(r1[q])) * scale;
+                if (cs) z *= __ldg(cs + j0 + cc + q);
+                v[q] = fmaxf(z, 0.f);
+                vmax = fmaxf(vmax, v[q]);
+            }
+            if (row < S) {
+                if (a.final_sum) {
+                    float* o = out_hi + (size_t)row * S + j0 + cc;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                } else if (!transposed) {
+                    float h[16], l[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        h[q] = __uint_as_float(__float_as_uint(v[q]) & 0xffffe000u);
+                        l[q] = v[q] - h[q];
+                    }
+                    float* oh = out_hi + (size_t)row * S + j0 + cc;
+                    float* ol = out_lo + (size_t)row * S + j0 + cc;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        *reinterpret_cast<float4*>(oh + 4 * q) = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+                        *reinterpret_cast<float4*>(ol + 4 * q) = make_float4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {  // out^T[col][row]: the lanes of a warp write 32 consecutive rows of one column
+                        const float h = __uint_as_float(__float_as_uint(v[q]) & 0xffffe000u);
+                        const size_t o = (size_t)(j0 + cc + q) * S + row;
+                        out_hi[o] = h;
+                        out_lo[o] = v[q] - h;
+                    }
+                }
+            }
+        }
+        vmax = warp_max(vmax);
+        if (lane == 0 && vmax > 0.f) atomicMax(a.zmax_out + p, __float_as_uint(vmax));
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ leaf preparation and conversions
+// base_hi/lo: planes of a matrix M [S][S]; out[e] planes = M[r][c] * w[e][row_scale ? r : c] split into hi / lo, w = exp(obs - shift).
+// Used for: N_t^T[j][k] = P^T[j][k] e_t[k] (right operand of a leaf pair), single leaves P D_t (either orientation).
+__global__ void cg_scale_planes(const float* __restrict__ base, const float* __restrict__ obs, int64_t obs_stride, int S, int row_scale, float* __restrict__ out,
+                                float* __restrict__ shift_out) {
+    __shared__ float s_w[1024];
+    __shared__ float s_red[32];
+    const int64_t e = blockIdx.y;
+    const float* o = obs + e * obs_stride;
+    float m = -FLT_MAX;
+    for (int k = threadIdx.x; k < S; k += blockDim.x) m = fmaxf(m, o[k]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = -FLT_MAX;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, s_red[q]);
+    if (!(m > -FLT_MAX)) m = 0.f;  // an impossible observation row stays all-zero
+    for (int k = threadIdx.x; k < S; k += blockDim.x) s_w[k] = expf(o[k] - m);
+    if (shift_out && blockIdx.x == 0 && threadIdx.x == 0) shift_out[e] = m;
+    __syncthreads();
+    const size_t SS = (size_t)S * S;
+    float* oh = out + (size_t)e * 2 * SS;
+    float* ol = oh + SS;
+    const int rows_per_block = (S + gridDim.x - 1) / gridDim.x;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(S, r0 + rows_per_block);
+    for (int idx = r0 * S + threadIdx.x * 4; idx < r1 * S; idx += blockDim.x * 4) {
+        const int r = idx / S, c = idx % S;
+        const float4 b = *reinterpret_cast<const float4*>(base + idx);
+        float4 w4;
+        if (row_scale) w4 = make_float4(s_w[r], s_w[r], s_w[r], s_w[r]);
+        else w4 = make_float4(s_w[c], s_w[c + 1], s_w[c + 2], s_w[c + 3]);
+        const float v[4] = {b.x * w4.x, b.y * w4.y, b.z * w4.z, b.w * w4.w};
+        float h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            h[q] = __uint_as_float(__float_as_uint(v[q]) & 0xffffe000u);
+            l[q] = v[q] - h[q];
+        }
+        *reinterpret_cast<float4*>(oh + idx) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(ol + idx) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+// w[e][j] = exp(obs[e][j] - max_j obs[e][j]), shift[e] = that max: the column scaling of a leaf pair's second step
+__global__ void cg_obs_weights(const float* __restrict__ obs, int64_t obs_stride, int S, float* __restrict__ w, float* __restrict__ shift_out) {
+    __shared__ float s_red[32];
+    const int64_t e = blockIdx.x;
+    const float* o = obs + e * obs_stride;
+    float m = -FLT_MAX;
+    for (int k = threadIdx.x; k < S; k += blockDim.x) m = fmaxf(m, o[k]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = -FLT_MAX;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, s_red[q]);
+    if (!(m > -FLT_MAX)) m = 0.f;
+    for (int k = threadIdx.x; k < S; k += blockDim.x) w[e * S + k] = expf(o[k] - m);
+    if (threadIdx.x == 0) shift_out[e] = m;
+}
+// planes of exp(A - colshift) in both orientations: P[i][j] (left operand) and P^T[j][i]; A row-major (prev, curr), entries <= 0 after the shift
+__global__ void cg_exp_planes(const float* __restrict__ A, int S, float* __restrict__ P, float* __restrict__ PT_single) {
+    const size_t SS = (size_t)S * S;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < SS; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / S), j = (int)(idx % S);
+        const float v = expf(A[idx]);
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        P[idx] = h;
+        P[SS + idx] = v - h;
+        PT_single[(size_t)j * S + i] = v;  // one fp32 plane of P^T: the base of the right-operand leaves
+    }
+}
+// fp32 matrix (row-major) -> planes in the requested orientation (tree results re-entering a tree as elements)
+__global__ void cg_split_planes(const float* __restrict__ M, int S, const int* __restrict__ transposed, float* __restrict__ out) {
+    const int64_t e = blockIdx.y;
+    const size_t SS = (size_t)S * S;
+    const float* m = M + (size_t)e * SS;
+    float* oh = out + (size_t)e * 2 * SS;
+    float* ol = oh + SS;
+    const bool tr = transposed[e] != 0;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < SS; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / S), j = (int)(idx % S);
+        const float v = tr ? m[(size_t)j * S + i] : m[idx];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        oh[idx] = h;
+        ol[idx] = v - h;
+    }
+}
+// planes of one element -> planes in the other orientation (a carried leftover whose role changes)
+__global__ void cg_transpose_planes(const float* __restrict__ in, int S, float* __restrict__ out) {
+    const size_t SS = (size_t)S * S;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * SS; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t pl = idx / SS, r = idx % SS;
+        const int i = (int)(r / S), j = (int)(r % S);
+        out[pl * SS + (size_t)j * S + i] = in[idx];
+    }
+}
+// rows[i][j] = log(M[i][j]) - log(zmax),  offset = E ln2 + log(zmax) + extra   (M = the final fp32 matrix of a tree)
+__global__ void cg_finish_rows(const float* __restrict__ M, const unsigned* __restrict__ zmax, const int* __restrict__ E, const double* __restrict__ extra, int S,
+                               float* __restrict__ rows, double* __restrict__ row_offset) {
+    const float zm = __uint_as_float(zmax[0]);
+    const size_t SS = (size_t)S * S;
+    const float lz = zm > 0.f ? logf(zm) : 0.f;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < SS; idx += (size_t)gridDim.x * blockDim.x) {
+        const float v = M[idx];
+        rows[idx] = v > 0.f ? logf(v) - lz : -INFINITY;
+    }
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < S; i += blockDim.x)
+            row_offset[i] = zm > 0.f ? (double)E[0] * 0.69314718055994530942 + (double)lz + extra[0] : -INFINITY;
+}
+__global__ void cg_sum_shifts(const float* __restrict__ shift, int64_t n, double* __restrict__ acc) {
+    __shared__ double s_red[32];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += (double)shift[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += s_red[q];
+        atomicAdd(acc, t);
+    }
+}
+__global__ void cg_fill_u32(unsigned* p, int64_t n, unsigned v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn cg_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// planes buffer [n][2][S][S] fp32 as a 3-D tensor (k, row, 2 n) with a (32, box_rows, 1) box and 128-byte swizzle
+static int cg_make_map(CUtensorMap* map, const float* base, int64_t n_elems, int S, int box_rows) {
+    EncodeTiledFn enc = cg_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return FB2_ERR_UNSUPPORTED;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)(2 * n_elems)};
+    cuuint64_t strides[2] = {(cuuint64_t)S * 4, (cuuint64_t)S * S * 4};
+    cuuint32_t box[3] = {CG_KC, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return FB2_ERR_CUDA;
+    }
+    return FB2_OK;
+}
+
+bool chain_gemm_supported(int S) { return S >= 256 && S <= 1024 && S % 128 == 0 && cg_encode_fn() != nullptr; }
+
+// role (0 = left / row-major, 1 = right / transposed) of the element at index `idx` of a level with `size` elements, following the
+// carry chain of the odd leftover (sum_product.py:696-698); the final result of the tree is row-major
+__host__ __device__ static int cg_role(int64_t idx, int64_t size) {
+    while (size > 1) {
+        if (idx == size - 1 && (size & 1)) {
+            idx = size / 2;
+            size = (size + 1) / 2;
+            continue;
+        }
+        return (int)(idx & 1);
+    }
+    return 0;
+}
+
+__global__ void cg_roles_kernel(int* roles, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) roles[i] = cg_role(i, n);
+}
+
+static int cg_launch(const float* a_planes, int64_t n_a, const float* b_planes, int64_t n_b, const ChainGemmArgs& args, int64_t pairs, cudaStream_t stream) {
+    CUtensorMap ma, mb;
+    int st = cg_make_map(&ma, a_planes, n_a, args.S, CG_BM);
+    if (st != FB2_OK) return st;
+    st = cg_make_map(&mb, b_planes, n_b, args.S, CG_BN);
+    if (st != FB2_OK) return st;
+    FB2_CUDA(cudaFuncSetAttribute(chain_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM));
+    const int tiles = (args.S / CG_BM) * ((args.S + CG_BN - 1) / CG_BN);
+    FB2_REQUIRE(pairs >= 1 && pairs <= 65535, "chain_gemm: %lld products in one level (grid.y limit 65535): use smaller blocks", (long long)pairs);
+    chain_gemm_tc<<<dim3((unsigned)tiles, (unsigned)pairs), CG_THREADS, CG_SMEM, stream>>>(ma, mb, args);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
+// Balanced tree (the reference's order) over `n` elements given as planes in `cur` (roles by cg_role) with scaling state
+// (zmax, E); ping-pongs between two plane buffers; writes the final product as ONE fp32 matrix + its (zmax, E).
+struct CgTreeBuffers {
+    float* planes[2];     // each >= ceil(n/2) elements of 2 S^2 floats
+    unsigned* zmax[2];    // each >= n
+    int* E[2];
+};
+static int cg_tree(const float* first_a, int64_t first_na, int first_a_shared, const float* first_b, int64_t first_nb, const float* first_colscale,
+                   int64_t n_pairs_first, const float* odd_leaf /*planes of a leftover leaf, role-correct, or nullptr*/, int S, const CgTreeBuffers& buf,
+                   float* final_out, unsigned* final_zmax, int* final_E, float comp, cudaStream_t stream) {
+    // level 0 -> 1: n_pairs_first products (A from first_a, B from first_b), optional leftover leaf appended
+    int64_t n = n_pairs_first + (odd_leaf ? 1 : 0);  // elements at the level being produced
+    const size_t SS2 = (size_t)2 * S * S;
+    int which = 0;
+    {
+        ChainGemmArgs a{};
+        a.S = S; a.comp = comp;
+        a.a_shared = first_a_shared; a.a_stride = first_a_shared ? 0 : 1; a.a_off = 0; a.b_stride = 1; a.b_off = 0;
+        a.colscale = first_colscale;
+        a.n_out = (int)n_pairs_first;
+        const bool is_final = n == 1;
+        a.final_sum = is_final;
+        a.out = is_final ? final_out : buf.planes[which];
+        a.zmax_out = is_final ? final_zmax : buf.zmax[which];
+        a.E_out = is_final ? final_E : buf.E[which];
+        a.last_transposed = cg_role(n_pairs_first - 1, n);
+        FB2_CUDA(cudaMemsetAsync(a.zmax_out, 0, (size_t)n * sizeof(unsigned), stream));
+        int st = cg_launch(first_a, first_na, first_b, first_nb, a, n_pairs_first, stream);
+        if (st != FB2_OK) return st;
+        if (odd_leaf) {  // append the leftover leaf (already in its role's orientation; stored <= 1, E = 0)
+            FB2_CUDA(cudaMemcpyAsync(buf.planes[which] + (size_t)n_pairs_first * SS2, odd_leaf, SS2 * 4, cudaMemcpyDeviceToDevice, stream));
+            cg_fill_u32<<<1, 32, 0, stream>>>(buf.zmax[which] + n_pairs_first, 1, 0x3f800000u);  // bits of 1.0f
+            FB2_LAUNCH_CHECK();
+            FB2_CUDA(cudaMemsetAsync(buf.E[which] + n_pairs_first, 0, sizeof(int), stream));
+        }
+        if (is_final) return FB2_OK;
+    }
+    while (n > 1) {
+        const int64_t pairs = n / 2, nd = (n + 1) / 2;
+        const bool odd = n & 1;
+        const int src = which, dst = which ^ 1;
+        ChainGemmArgs a{};
+        a.S = S; a.comp = comp;
+        a.a_shared = 0; a.a_stride = 2; a.a_off = 0; a.b_stride = 2; a.b_off = 1;
+        a.zmax_a = buf.zmax[src]; a.E_a = buf.E[src]; a.zmax_b = buf.zmax[src]; a.E_b = buf.E[src];
+        a.n_out = (int)pairs;
+        const bool is_final = nd == 1;
+        a.final_sum = is_final;
+        a.out = is_final ? final_out : buf.planes[dst];
+        a.zmax_out = is_final ? final_zmax : buf.zmax[dst];
+        a.E_out = is_final ? final_E : buf.E[dst];
+        a.last_transposed = cg_role(pairs - 1, nd);
+        FB2_CUDA(cudaMemsetAsync(a.zmax_out, 0, (size_t)nd * sizeof(unsigned), stream));
+        int st = cg_launch(buf.planes[src], n, buf.planes[src], n, a, pairs, stream);
+        if (st != FB2_OK) return st;
+        if (odd) {  // carry the leftover: it was stored row-major (its index was even); transpose if its eventual role is "right"
+            const float* lsrc = buf.planes[src] + (size_t)(n - 1) * SS2;
+            float* ldst = buf.planes[dst] + (size_t)pairs * SS2;
+            // the leftover's CURRENT orientation is its eventual role as computed when it was written (cg_role follows the whole carry
+            // chain), so a plain copy is correct
+            FB2_CUDA(cudaMemcpyAsync(ldst, lsrc, SS2 * 4, cudaMemcpyDeviceToDevice, stream));
+            FB2_CUDA(cudaMemcpyAsync(buf.zmax[dst] + pairs, buf.zmax[src] + (n - 1), sizeof(unsigned), cudaMemcpyDeviceToDevice, stream));
+            FB2_CUDA(cudaMemcpyAsync(buf.E[dst] + pairs, buf.E[src] + (n - 1), sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        }
+        n = nd;
+        which = dst;
+    }
+    return FB2_OK;
+}
+
+// Blocks of `block_steps` (even) time steps; a single trailing step is absorbed by the last block, so every block has >= 2 steps.
+static int64_t cg_block_count(int64_t T, int64_t bs) {
+    int64_t n = 0;
+    for (int64_t t = 0; t < T;) {
+        int64_t nt = bs < T - t ? bs : T - t;
+        if (T - (t + nt) == 1) nt += 1;
+        t += nt;
+        ++n;
+    }
+    return n;
+}
+
+size_t hmm_chunk_summary_gemm_workspace_bytes(int64_t T, int S, int64_t block_steps) {
+    const size_t SS = (size_t)S * S;
+    int64_t bs = block_steps < T ? block_steps : T;
+    bs += bs & 1;
+    const int64_t pairs = bs / 2 + 2;
+    const int64_t nblocks = cg_block_count(T, bs);
+    size_t w = 0;
+    w += align_up(2 * SS * 4) + align_up(SS * 4);                       // P planes, P^T single plane
+    w += align_up((size_t)pairs * 2 * SS * 4);                           // leaf right operands N (+ leftover leaf slot)
+    w += align_up((size_t)pairs * S * 4);                                // column weights
+    w += 2 * align_up((size_t)(bs + 2) * 4);                             // shifts
+    w += align_up((size_t)pairs * 2 * SS * 4) + align_up((size_t)(pairs / 2 + 1) * 2 * SS * 4);  // tree ping-pong
+    w += 4 * align_up((size_t)(pairs + 1) * 4);                          // zmax / E ping-pong
+    w += align_up((size_t)nblocks * SS * 4) + 3 * align_up((size_t)nblocks * 4);  // block results, zmax, E, roles
+    w += align_up((size_t)nblocks * 2 * SS * 4) + align_up((size_t)(nblocks / 2 + 1) * 2 * SS * 4);  // upper tree
+    w += 4 * align_up((size_t)(nblocks + 1) * 4);
+    w += align_up(SS * 4) + 3 * 256;                                     // final matrix, zmax, E, offset accumulator
+    return w + 4096;
+}
+
+// out rows [S][S] fp32 (largest entry 0) + row_offset [S] float64 of  (x)_{t} (A + obs[t])  for ONE chain; obs [T][S] contiguous
+int hmm_chunk_summary_gemm_device(const float* A, const float* obs, int64_t T, int S, int64_t block_steps, float* rows_out, double* row_offset,
+                                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!chain_gemm_supported(S) || T < 2) return FB2_ERR_UNSUPPORTED;
+    const size_t SS = (size_t)S * S;
+    int64_t bs = block_steps < T ? block_steps : T;
+    bs += bs & 1;
+    FB2_REQUIRE(bs >= 2 && bs <= 131068, "hmm_chunk_summary (gemm): block of %lld steps outside [2, 131068]", (long long)bs);
+    const int64_t max_pairs = bs / 2 + 2;
+    const int64_t nblocks = cg_block_count(T, bs);
+    Arena ar(workspace, workspace_bytes);
+    float* P = ar.take<float>(2 * SS);
+    float* PT = ar.take<float>(SS);
+    float* N = ar.take<float>((size_t)max_pairs * 2 * SS);
+    float* W = ar.take<float>((size_t)max_pairs * S);
+    float* shiftN = ar.take<float>((size_t)bs + 2);
+    float* shiftW = ar.take<float>((size_t)bs + 2);
+    CgTreeBuffers tb{}, ub{};
+    tb.planes[0] = ar.take<float>((size_t)max_pairs * 2 * SS);
+    tb.planes[1] = ar.take<float>((size_t)(max_pairs / 2 + 1) * 2 * SS);
+    for (int q = 0; q < 2; ++q) {
+        tb.zmax[q] = ar.take<unsigned>((size_t)max_pairs + 1);
+        tb.E[q] = ar.take<int>((size_t)max_pairs + 1);
+    }
+    float* blockM = ar.take<float>((size_t)nblocks * SS);
+    unsigned* block_zmax = ar.take<unsigned>((size_t)nblocks);
+    int* block_E = ar.take<int>((size_t)nblocks);
+    int* block_role = ar.take<int>((size_t)nblocks);
+    ub.planes[0] = ar.take<float>((size_t)nblocks * 2 * SS);
+    ub.planes[1] = ar.take<float>((size_t)(nblocks / 2 + 1) * 2 * SS);
+    for (int q = 0; q < 2; ++q) {
+        ub.zmax[q] = ar.take<unsigned>((size_t)nblocks + 1);
+        ub.E[q] = ar.take<int>((size_t)nblocks + 1);
+    }
+    float* finalM = ar.take<float>(SS);
+    unsigned* final_zmax = ar.take<unsigned>(64);
+    int* final_E = ar.take<int>(64);
+    double* shift_acc = ar.take<double>(32);
+    if (!ar.ok()) {
+        set_error("hmm_chunk_summary (gemm): workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    const float comp = 5.82e-8f;
+    FB2_CUDA(cudaMemsetAsync(shift_acc, 0, sizeof(double), stream));
+    cg_exp_planes<<<296, 256, 0, stream>>>(A, S, P, PT);
+    FB2_LAUNCH_CHECK();
+    int64_t t0 = 0;
+    for (int64_t b = 0; b < nblocks; ++b) {
+        int64_t nt = bs < T - t0 ? bs : T - t0;
+        if (T - (t0 + nt) == 1) nt += 1;
+        const int64_t pairs = nt / 2;
+        const bool odd = nt & 1;
+        const float* ob = obs + t0 * S;
+        float* dstM = nblocks == 1 ? finalM : blockM + (size_t)b * SS;
+        unsigned* dstZ = nblocks == 1 ? final_zmax : block_zmax + b;
+        int* dstE = nblocks == 1 ? final_E : block_E + b;
+        // right operands of the leaf pairs: N_p^T[j][k] = P^T[j][k] * e_{2p}[k]  (column scaling of P^T), one element per pair
+        cg_scale_planes<<<dim3(8, (unsigned)pairs), 256, 0, stream>>>(PT, ob, 2 * (int64_t)S, S, 0, N, shiftN);
+        FB2_LAUNCH_CHECK();
+        // column weights of the second step of every pair (applied in the epilogue of the leaf products)
+        cg_obs_weights<<<(unsigned)pairs, 128, 0, stream>>>(ob + S, 2 * (int64_t)S, S, W, shiftW);
+        FB2_LAUNCH_CHECK();
+        cg_sum_shifts<<<32, 256, 0, stream>>>(shiftN, pairs, shift_acc);
+        FB2_LAUNCH_CHECK();
+        cg_sum_shifts<<<32, 256, 0, stream>>>(shiftW, pairs, shift_acc);
+        FB2_LAUNCH_CHECK();
+        const float* odd_leaf = nullptr;
+        if (odd) {
+            // the last step of an odd block is a leaf of its own, M = P D_t, stored in the orientation of its eventual role.
+            // Row scaling of P^T gives M^T (the "right operand" orientation); the "left operand" orientation is its transpose.
+            const int role = cg_role(pairs, pairs + 1);
+            float* leaf = N + (size_t)pairs * 2 * SS;  // spare slot behind the pair operands
+            cg_scale_planes<<<dim3(8, 1), 256, 0, stream>>>(PT, ob + (nt - 1) * S, S, S, 1, leaf, shiftN + pairs);
+            FB2_LAUNCH_CHECK();
+            cg_sum_shifts<<<1, 32, 0, stream>>>(shiftN + pairs, 1, shift_acc);
+            FB2_LAUNCH_CHECK();
+            if (role == 0) {
+                float* tmp = tb.planes[1];  // not in use before the tree starts
+                cg_transpose_planes<<<296, 256, 0, stream>>>(leaf, S, tmp);
+                FB2_LAUNCH_CHECK();
+                FB2_CUDA(cudaMemcpyAsync(leaf, tmp, 2 * SS * 4, cudaMemcpyDeviceToDevice, stream));
+            }
+            odd_leaf = leaf;
+        }
+        int st = cg_tree(P, 1, 1, N, pairs + (odd ? 1 : 0), W, pairs, odd_leaf, S, tb, dstM, dstZ, dstE, comp, stream);
+        if (st != FB2_OK) return st;
+        t0 += nt;
+    }
+    if (nblocks > 1) {
+        // the block results re-enter a tree as elements: split into planes in the orientation of their role
+        cg_roles_kernel<<<1, 256, 0, stream>>>(block_role, nblocks);
+        FB2_LAUNCH_CHECK();
+        cg_split_planes<<<dim3(64, (unsigned)nblocks), 256, 0, stream>>>(blockM, S, block_role, ub.planes[0]);
+        FB2_LAUNCH_CHECK();
+        FB2_CUDA(cudaMemcpyAsync(ub.zmax[0], block_zmax, (size_t)nblocks * sizeof(unsigned), cudaMemcpyDeviceToDevice, stream));
+        FB2_CUDA(cudaMemcpyAsync(ub.E[0], block_E, (size_t)nblocks * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        int64_t n = nblocks;
+        int which = 0;
+        const size_t SS2 = 2 * SS;
+        while (n > 1) {
+            const int64_t pairs = n / 2, nd = (n + 1) / 2;
+            const int src = which, dst = which ^ 1;
+            ChainGemmArgs a{};
+            a.S = S; a.comp = comp;
+            a.a_stride = 2; a.a_off = 0; a.b_stride = 2; a.b_off = 1;
+            a.zmax_a = ub.zmax[src]; a.E_a = ub.E[src]; a.zmax_b = ub.zmax[src]; a.E_b = ub.E[src];
+            a.n_out = (int)pairs;
+            const bool is_final = nd == 1;
+            a.final_sum = is_final;
+            a.out = is_final ? finalM : ub.planes[dst];
+            a.zmax_out = is_final ? final_zmax : ub.zmax[dst];
+            a.E_out = is_final ? final_E : ub.E[dst];
+            a.last_transposed = cg_role(pairs - 1, nd);
+            FB2_CUDA(cudaMemsetAsync(a.zmax_out, 0, (size_t)nd * sizeof(unsigned), stream));
+            int st = cg_launch(ub.planes[src], n, ub.planes[src], n, a, pairs, stream);
+            if (st != FB2_OK) return st;
+            if (n & 1) {
+                FB2_CUDA(cudaMemcpyAsync(ub.planes[dst] + (size_t)pairs * SS2, ub.planes[src] + (size_t)(n - 1) * SS2, SS2 * 4, cudaMemcpyDeviceToDevice, stream));
+                FB2_CUDA(cudaMemcpyAsync(ub.zmax[dst] + pairs, ub.zmax[src] + (n - 1), sizeof(unsigned), cudaMemcpyDeviceToDevice, stream));
+                FB2_CUDA(cudaMemcpyAsync(ub.E[dst] + pairs, ub.E[src] + (n - 1), sizeof(int), cudaMemcpyDeviceToDevice, stream));
+            }
+            n = nd;
+            which = dst;
+        }
+    }
+    cg_finish_rows<<<296, 256, 0, stream>>>(finalM, final_zmax, final_E, shift_acc, S, rows_out, row_offset);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
+}  // namespace fb2
+
+using namespace fb2;
+
+extern "C" size_t fb2_hmm_chunk_summary_gemm_workspace_bytes(int64_t T, int32_t S, int64_t block_steps) {
+    if (T < 2 || S < 1 || block_steps < 2) return 0;
+    return hmm_chunk_summary_gemm_workspace_bytes(T, S, block_steps);
+}
+
+extern "C" int fb2_hmm_chunk_summary_gemm_f32(const float* A, const float* obs, int64_t T, int32_t S, int64_t block_steps, float* rows,
+                                              double* row_offset, void* workspace, size_t workspace_bytes, void* stream) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(A && obs && rows && row_offset && workspace, "null pointer");
+    FB2_REQUIRE(T >= 2 && block_steps >= 2, "bad extents T=%lld block_steps=%lld", (long long)T, (long long)block_steps);
+    if (!chain_gemm_supported(S)) {
+        set_error("hmm_chunk_summary (gemm): S=%d not supported (multiples of 128 in [256, 1024])", S);
+        return FB2_ERR_UNSUPPORTED;
+    }
+    return hmm_chunk_summary_gemm_device(A, obs, T, S, block_steps, rows, row_offset, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}

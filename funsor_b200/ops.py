@@ -367,15 +367,49 @@ def hmm_chunk_summary_tree(A, obs, sum_op="logaddexp", block_bytes=2 << 30, leaf
     return acc.contiguous(), off[:, None].expand(B, S).contiguous()
 
 
+def hmm_chunk_summary_gemm(A, obs, block_steps=4096):
+    """The chunk summary as a linear-domain matrix-chain product on the tensor cores (csrc/chain_gemm_tc.cu: TMA-fed 3xTF32 tcgen05
+    GEMMs, hi / lo planes written by the epilogue of the level below, the reference's tree order sum_product.py:690-701 inside blocks
+    of `block_steps` steps and across blocks).  Shared log-semiring A[S,S], S a multiple of 128 in [256, 1024].
+    Returns (rows[B,S,S] fp32 with max entry 0, row_offset[B,S] float64)."""
+    _dev_f32(obs, "obs"), _dev_f32(A, "A")
+    B, T, S = obs.shape
+    if A.dim() != 2 or A.shape != (S, S):
+        raise ValueError("hmm_chunk_summary_gemm needs a shared transition matrix A[S,S]")
+    A, obs = A.contiguous(), obs.contiguous()
+    rows = torch.empty((B, S, S), dtype=torch.float32, device=obs.device)
+    off = torch.empty((B, S), dtype=torch.float64, device=obs.device)
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_hmm_chunk_summary_gemm_workspace_bytes(T, S, block_steps), obs.device)
+    with torch.cuda.device(obs.device):
+        for b in range(B):
+            check(lib.fb2_hmm_chunk_summary_gemm_f32(A.data_ptr(), obs[b].data_ptr(), T, S, block_steps, rows[b].data_ptr(), off[b].data_ptr(),
+                                                     ws.data_ptr(), ws.numel(), _stream()))
+    return rows, off
+
+
+def _gemm_summary_ok(A, obs, sum_op):
+    S = obs.shape[-1]
+    return (semiring_id(sum_op) == SEMIRING_LOG and A.dim() == 2 and S % 128 == 0 and 256 <= S <= 1024 and obs.shape[1] >= 2
+            and os.environ.get("FB2_SUMMARY_GEMM", "1") != "0")
+
+
 def hmm_chunk_summary(A, obs, sum_op="logaddexp", return_offsets=False, method="auto"):
     """Transfer matrix of a chunk of time: out[b] = (x)_{t in chunk} (A + obs[b,t]) as [B,S,S] -- the summary
     that time-sharded ranks all-gather (mixed_sequential_sum_product sum_product.py:766-795).
     With return_offsets the rows come back relative to a float64 offset [B,S] (true entry = out + offset[..., None]):
     the log-magnitude of a long chunk (~1e5) would otherwise eat the fp32 resolution of the entries.
-    method: "tree" = blocked dense tree on the tensor cores (default with offsets, shared A, S >= 64), "scan" = S chains per
+    method: "gemm" = linear-domain TMA + tcgen05 matrix-chain tree (default with offsets, log semiring, shared A, S a multiple of 128
+    in [256, 1024]), "tree" = blocked dense log-domain tree on the tensor cores (shared A, S >= 64), "scan" = S chains per
     batch entry on the recurrence kernels (dataflow kernel with offsets, generic cooperative kernel without)."""
     if method == "auto":
-        method = "tree" if (return_offsets and A.dim() == 2 and obs.shape[-1] >= 64) else "scan"
+        if return_offsets and _gemm_summary_ok(A, obs, sum_op):
+            method = "gemm"
+        else:
+            method = "tree" if (return_offsets and A.dim() == 2 and obs.shape[-1] >= 64) else "scan"
+    if method == "gemm":
+        rows, off = hmm_chunk_summary_gemm(A, obs)
+        return (rows, off) if return_offsets else (rows.double() + off[..., None]).float()
     if method == "tree":
         rows, off = hmm_chunk_summary_tree(A, obs, sum_op)
         return (rows, off) if return_offsets else (rows.double() + off[..., None]).float()

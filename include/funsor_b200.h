@@ -118,6 +118,15 @@ int fb2_hmm_chunk_summary_f32(int semiring, const float* A, int64_t a_sb, int64_
                               int64_t B, int64_t T, int32_t S, float* out /*[B,S,S]*/, double* row_offset, void* workspace,
                               size_t workspace_bytes, void* stream);
 
+/* chunk_summary_gemm: the same summary for ONE chain with a shared log-semiring transition matrix A[S,S] (S a multiple of 128 in
+ * [256, 1024]) as a blocked balanced tree of S x S products (the reference's own sequential_sum_product order, sum_product.py:690-701)
+ * kept in the LINEAR domain: TMA-fed 3xTF32 tcgen05 GEMMs whose epilogue writes the TF32 hi / lo planes of the next level
+ * (csrc/chain_gemm_tc.cu).  obs[T,S] contiguous, T >= 2; time is processed in blocks of `block_steps` steps (bounds the workspace:
+ * ~ 3 * block_steps * S * S * 4 bytes).  rows[S,S] fp32 with largest entry 0, row_offset[S] float64 (true entry = rows + row_offset). */
+size_t fb2_hmm_chunk_summary_gemm_workspace_bytes(int64_t T, int32_t S, int64_t block_steps);
+int fb2_hmm_chunk_summary_gemm_f32(const float* A, const float* obs, int64_t T, int32_t S, int64_t block_steps, float* rows,
+                                   double* row_offset, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (4) Dense adjoint of the chain (backward pass).
  * Replaces: AdjointTape.adjoint over a scan, funsor/adjoint.py:72-131, 231-294 (+ Scatter tensor.py:639-683).
