@@ -39,8 +39,9 @@ constexpr int CG_BM = 128, CG_BN = 256, CG_KC = 32, CG_STAGES = 2;
 constexpr int CG_A_PLANE = CG_BM * CG_KC * 4;  // 16 KB
 constexpr int CG_B_PLANE = CG_BN * CG_KC * 4;  // 32 KB
 constexpr int CG_STAGE_BYTES = 2 * CG_A_PLANE + 2 * CG_B_PLANE;  // 96 KB
-constexpr int CG_SMEM = CG_STAGES * CG_STAGE_BYTES + 1024;
-constexpr int CG_THREADS = 192;
+
+constexpr int CG_THREADS = 320;  // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (4 lane quarters x 2 column halves)
+
 
 struct ChainGemmArgs {
     // outputs of this level
@@ -61,6 +62,9 @@ struct ChainGemmArgs {
     int n_out;
     int final_sum;         // 1: write hi + lo as one fp32 matrix, row-major (the result of a tree)
     float comp;
+    long long stagger;  // start delay of odd CTAs in cycles (0 = none)
+    long long* prof;  // debugging aid (FB2_CG_PROF=1): clock64 stamps of CTA (0, 0) and of the last CTA
+    int mode;  // FB2_CG_MODE ablations: 1 = no TMA loads after the first two chunks, 2 = no MMAs, 4 = no epilogue stores
 };
 
 __device__ __forceinline__ uint32_t cg_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,6 +95,9 @@ __device__ __forceinline__ void cg_tma_3d(uint32_t dst, const CUtensorMap* map, 
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void cg_tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void cg_tmem_ld16(uint32_t taddr, uint32_t (&d)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -100,22 +107,36 @@ __device__ __forceinline__ void cg_tmem_ld16(uint32_t taddr, uint32_t (&d)[16]) 
         : "memory");
 }
 
-// One CTA = one 128 x 256 tile of one product.  grid = (tiles, pairs).
+// Persistent: grid = min(#tiles, #SMs) CTAs, each walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (t = pair * tiles_per_product +
+// tile, so neighbouring CTAs work on the same product and share its operands in L2).  Measured with clock64 stamps on the first,
+// non-persistent version (S = 512): first TMA load of a CTA 6-12k cycles, main loop 1.7k cycles per K chunk (tensor-bound), epilogue
+// 10-22k cycles of poorly coalesced direct stores -- i.e. half of a CTA's life was not tensor work.  Hence (i) the producer runs ahead
+// into the next tile while the epilogue drains tensor memory, (ii) the epilogue stages 32 x 16 sub-blocks in shared memory and
+// writes them with TMA stores (cp.async.bulk.tensor ... global.shared::cta) in the orientation the next level needs.
+constexpr int CG_EPI_WARPS = 8;
+constexpr int CG_EPI_BYTES = 4096;  // per epilogue warp: hi [32 x 16] + lo [32 x 16] fp32
+constexpr int CG_SMEM_TOTAL = 1024 + CG_STAGES * CG_STAGE_BYTES + CG_EPI_WARPS * CG_EPI_BYTES;
+
+__device__ __forceinline__ void cg_tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                               const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_ot,
                                                                ChainGemmArgs a) {
     extern __shared__ unsigned char cg_smem_raw[];
-    __shared__ __align__(8) unsigned long long s_full[CG_STAGES], s_empty[CG_STAGES], s_done;
+    __shared__ __align__(8) unsigned long long s_full[CG_STAGES], s_empty[CG_STAGES], s_tfull, s_tempty;
     __shared__ uint32_t s_tmem;
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cg_smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = a.S;
     const int tiles_n = (S + CG_BN - 1) / CG_BN;
-    const int tile = blockIdx.x;
-    const int i0 = (tile / tiles_n) * CG_BM, j0 = (tile % tiles_n) * CG_BN;
-    const int p = blockIdx.y;
-    const int ia = a.a_shared ? 0 : a.a_stride * p + a.a_off;
-    const int ib = a.b_stride * p + a.b_off;
+    const int tiles = (S / CG_BM) * tiles_n;
+    const int64_t total = (int64_t)tiles * a.n_out;
     const int nchunks = S / CG_KC;
+    const bool do_prof = a.prof != nullptr && blockIdx.x == 0;
+    if (do_prof && tid == 0) a.prof[0] = clock64();
 
     if (tid == 0) {
 #pragma unroll
@@ -123,10 +144,13 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_full[s])) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_empty[s])) : "memory");
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_done)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_tfull)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cg_u32(&s_tempty)), "n"(CG_EPI_WARPS) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ot) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cg_u32(&s_tmem)), "n"(512) : "memory");
@@ -136,120 +160,196 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
+    if (do_prof && tid == 0) a.prof[1] = clock64();
+    // De-phase the CTAs.  All persistent CTAs start together and would stay in lock step: every SM reading operands during the
+    // main loop, then every SM writing its 256 KB of planes during the epilogue, so that neither the HBM read nor the write
+    // stream is ever shared with tensor work of another SM.  Odd CTAs start half a tile late (a.stagger cycles).
+    if (a.stagger > 0 && (blockIdx.x & 1)) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < a.stagger) __nanosleep(200);
+    }
 
     if (warp == 0) {
-        // ---------------- producer
+        // ---------------- producer: one lane, runs ahead of the MMA warp by the depth of the ring (also across tiles)
         if (lane == 0) {
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c % CG_STAGES;
-                if (c >= CG_STAGES) cg_wait(cg_u32(&s_empty[s]), ((c / CG_STAGES) - 1) & 1);
-                const uint32_t bar = cg_u32(&s_full[s]);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)CG_STAGE_BYTES) : "memory");
-                const uint32_t st = cg_u32(smem + (size_t)s * CG_STAGE_BYTES);
-                const int k0 = c * CG_KC;
-                cg_tma_3d(st, &map_a, k0, i0, 2 * ia, bar);
-                cg_tma_3d(st + CG_A_PLANE, &map_a, k0, i0, 2 * ia + 1, bar);
-                cg_tma_3d(st + 2 * CG_A_PLANE, &map_b, k0, j0, 2 * ib, bar);
-                cg_tma_3d(st + 2 * CG_A_PLANE + CG_B_PLANE, &map_b, k0, j0, 2 * ib + 1, bar);
+            int64_t gc = 0;  // chunks issued by this CTA so far
+            for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+                const int p = (int)(t / tiles), tile = (int)(t % tiles);
+                const int i0 = (tile / tiles_n) * CG_BM, j0 = (tile % tiles_n) * CG_BN;
+                const int ia = a.a_shared ? 0 : a.a_stride * p + a.a_off;
+                const int ib = a.b_stride * p + a.b_off;
+                for (int c = 0; c < nchunks; ++c, ++gc) {
+                    const int s = (int)(gc % CG_STAGES);
+                    if (gc >= CG_STAGES) cg_wait(cg_u32(&s_empty[s]), (uint32_t)(((gc / CG_STAGES) - 1) & 1));
+                    const uint32_t bar = cg_u32(&s_full[s]);
+                    if ((a.mode & 1) && gc >= CG_STAGES) {  // ablation: no data movement, just hand the stage back
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+                        continue;
+                    }
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)CG_STAGE_BYTES) : "memory");
+                    const uint32_t st = cg_u32(smem + (size_t)s * CG_STAGE_BYTES);
+                    const int k0 = c * CG_KC;
+                    cg_tma_3d(st, &map_a, k0, i0, 2 * ia, bar);
+                    cg_tma_3d(st + CG_A_PLANE, &map_a, k0, i0, 2 * ia + 1, bar);
+                    cg_tma_3d(st + 2 * CG_A_PLANE, &map_b, k0, j0, 2 * ib, bar);
+                    cg_tma_3d(st + 2 * CG_A_PLANE + CG_B_PLANE, &map_b, k0, j0, 2 * ib + 1, bar);
+                }
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer
         constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CG_BN >> 3) << 17) | ((128u >> 4) << 24);
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c % CG_STAGES;
-            cg_wait(cg_u32(&s_full[s]), (c / CG_STAGES) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t ah = cg_u32(smem + (size_t)s * CG_STAGE_BYTES), al = ah + CG_A_PLANE, bh = ah + 2 * CG_A_PLANE, bl = bh + CG_B_PLANE;
-#pragma unroll
-                for (int ks = 0; ks < CG_KC / 8; ++ks) {
-                    const uint64_t dah = cg_desc(ah + ks * 32), dal = cg_desc(al + ks * 32);
-                    const uint64_t dbh = cg_desc(bh + ks * 32), dbl = cg_desc(bl + ks * 32);
-                    cg_mma(tmem, dah, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
-                    cg_mma(tmem + CG_BN, dal, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
-                    cg_mma(tmem + CG_BN, dah, dbl, IDESC, 1u);
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cg_u32(&s_empty[s])) : "memory");
-                if (c == nchunks - 1)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cg_u32(&s_done)) : "memory");
+        int64_t gc = 0;
+        int it = 0;
+        for (int64_t t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+            if (it > 0) {  // the epilogue of the previous tile must have read the accumulators out of tensor memory
+                cg_wait(cg_u32(&s_tempty), (uint32_t)((it - 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            __syncwarp();
+            for (int c = 0; c < nchunks; ++c, ++gc) {
+                const int s = (int)(gc % CG_STAGES);
+                cg_wait(cg_u32(&s_full[s]), (uint32_t)((gc / CG_STAGES) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (do_prof && lane == 0 && it < 2 && (c == 0 || c == nchunks - 1)) a.prof[2 + 2 * it + (c ? 1 : 0)] = clock64();
+                if (lane == 0) {
+                    const uint32_t ah = cg_u32(smem + (size_t)s * CG_STAGE_BYTES), al = ah + CG_A_PLANE, bh = ah + 2 * CG_A_PLANE, bl = bh + CG_B_PLANE;
+#pragma unroll
+                    for (int ks = 0; ks < CG_KC / 8; ++ks) {
+                        if ((a.mode & 2) && (c > 0 || ks > 0)) break;  // ablation: one MMA per tile
+                        const uint64_t dah = cg_desc(ah + ks * 32), dal = cg_desc(al + ks * 32);
+                        const uint64_t dbh = cg_desc(bh + ks * 32), dbl = cg_desc(bl + ks * 32);
+                        cg_mma(tmem, dah, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                        cg_mma(tmem + CG_BN, dal, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                        cg_mma(tmem + CG_BN, dah, dbl, IDESC, 1u);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cg_u32(&s_empty[s])) : "memory");
+                    if (c == nchunks - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cg_u32(&s_tfull)) : "memory");
+                }
+                __syncwarp();
+            }
         }
     } else {
-        // ---------------- epilogue: warp w owns tensor-memory lanes 32 (w % 4) ..
+        // ---------------- epilogue: warp w owns tensor-memory lanes 32 (w % 4) .. and one half of the tile's columns
         const int q4 = warp & 3;
-        const int row = i0 + q4 * 32 + lane;
-        // scaling state of the operands -> exact power-of-two renormalisation
-        const float za = a.zmax_a ? __uint_as_float(a.zmax_a[ia]) : 1.f;
-        const float zb = a.zmax_b ? __uint_as_float(a.zmax_b[ib]) : 1.f;
-        int ea = 0, eb = 0;
-        if (za > 0.f) frexpf(za, &ea);
-        if (zb > 0.f) frexpf(zb, &eb);
-        const float scale = ldexpf(1.f, -(ea + eb));
-        const bool transposed = a.final_sum ? false : (p == a.n_out - 1 ? a.last_transposed != 0 : (p & 1) != 0);
-        if (tile == 0 && warp == 2 && lane == 0)
-            a.E_out[p] = (a.E_a ? a.E_a[ia] : 0) + (a.E_b ? a.E_b[ib] : 0) + ea + eb;
+        const int chalf = (warp - 2) >> 2;
+        unsigned char* stg = smem + (size_t)CG_STAGES * CG_STAGE_BYTES + (size_t)(warp - 2) * CG_EPI_BYTES;
+        float* stg_hi = reinterpret_cast<float*>(stg);
+        float* stg_lo = stg_hi + 512;
+        const uint32_t stg_u32 = cg_u32(stg);
         const float fmain = 1.f + a.comp * (float)(nchunks * (CG_KC / 8));
         const size_t SS = (size_t)S * S;
-        float* out_hi = a.out + (size_t)p * (a.final_sum ? SS : 2 * SS);
-        float* out_lo = out_hi + SS;
-        const float* cs = a.colscale ? a.colscale + (size_t)p * S : nullptr;
-        cg_wait(cg_u32(&s_done), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float vmax = 0.f;
         const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
-#pragma unroll 1
-        for (int cc = 0; cc < CG_BN; cc += 16) {
-            if (j0 + cc >= S) break;  // warp-uniform
-            uint32_t r0[16], r1[16];
-            cg_tmem_ld16(lane_base + (uint32_t)cc, r0);
-            cg_tmem_ld16(lane_base + (uint32_t)(CG_BN + cc), r1);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float v[16];
+        int it = 0;
+        for (int64_t t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+            const int p = (int)(t / tiles), tile = (int)(t % tiles);
+            const int i0 = (tile / tiles_n) * CG_BM, j0 = (tile % tiles_n) * CG_BN;
+            const int ia = a.a_shared ? 0 : a.a_stride * p + a.a_off;
+            const int ib = a.b_stride * p + a.b_off;
+            const int row = i0 + q4 * 32 + lane;
+            // scaling state of the operands -> exact power-of-two renormalisation
+            const float za = a.zmax_a ? __uint_as_float(a.zmax_a[ia]) : 1.f;
+            const float zb = a.zmax_b ? __uint_as_float(a.zmax_b[ib]) : 1.f;
+            int ea = 0, eb = 0;
+            if (za > 0.f) frexpf(za, &ea);
+            if (zb > 0.f) frexpf(zb, &eb);
+            const float scale = ldexpf(1.f, -(ea + eb));
+            const bool transposed = a.final_sum ? false : (p == a.n_out - 1 ? a.last_transposed != 0 : (p & 1) != 0);
+            if (tile == 0 && warp == 2 && lane == 0)
+                a.E_out[p] = (a.E_a ? a.E_a[ia] : 0) + (a.E_b ? a.E_b[ib] : 0) + ea + eb;
+            const float* cs = a.colscale ? a.colscale + (size_t)p * S : nullptr;
+            cg_wait(cg_u32(&s_tfull), (uint32_t)(it & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (do_prof && tid == 64 && it < 2) a.prof[8 + 2 * it] = clock64();
+            // Phase A: pull this warp's 32 x 128 block of the accumulators into REGISTERS (128 values per thread) and hand tensor memory
+            // back at once, so that the next tile's MMAs run while phase B writes the planes out.  (With the single 2 x 256-column
+            // accumulator set there is no second buffer in tensor memory; measured before this split: the MMA warp sat idle for the
+            // whole 19-21k-cycle epilogue of every tile.)
+            float vmax = 0.f;
+            float v[128];
+            const int cbase = chalf * (CG_BN / 2);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                float z = fmaf(__uint_as_float(r0[q]), fmain, __uint_as_float(r1[q])) * scale;
-                if (cs) z *= __ldg(cs + j0 + cc + q);
-                v[q] = fmaxf(z, 0.f);
-                vmax = fmaxf(vmax, v[q]);
-            }
-            if (row < S) {
-                if (a.final_sum) {
-                    float* o = out_hi + (size_t)row * S + j0 + cc;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                } else if (!transposed) {
-                    float h[16], l[16];
+            for (int g = 0; g < 8; ++g) {
+                const int cc = cbase + g * 16;
+                if (j0 + cc < S) {  // warp-uniform
+                    uint32_t r0[16], r1[16];
+                    cg_tmem_ld16(lane_base + (uint32_t)cc, r0);
+                    cg_tmem_ld16(lane_base + (uint32_t)(CG_BN + cc), r1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
-                        h[q] = __uint_as_float(__float_as_uint(v[q]) & 0xffffe000u);
-                        l[q] = v[q] - h[q];
-                    }
-                    float* oh = out_hi + (size_t)row * S + j0 + cc;
-                    float* ol = out_lo + (size_t)row * S + j0 + cc;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        *reinterpret_cast<float4*>(oh + 4 * q) = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
-                        *reinterpret_cast<float4*>(ol + 4 * q) = make_float4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3]);
+                        float z = fmaf(__uint_as_float(r0[q]), fmain, __uint_as_float(r1[q])) * scale;
+                        if (cs) z *= __ldg(cs + j0 + cc + q);
+                        v[g * 16 + q] = fmaxf(z, 0.f);
+                        vmax = fmaxf(vmax, v[g * 16 + q]);
                     }
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {  // out^T[col][row]: the lanes of a warp write 32 consecutive rows of one column
-                        const float h = __uint_as_float(__float_as_uint(v[q]) & 0xffffe000u);
-                        const size_t o = (size_t)(j0 + cc + q) * S + row;
-                        out_hi[o] = h;
-                        out_lo[o] = v[q] - h;
-                    }
+                    for (int q = 0; q < 16; ++q) v[g * 16 + q] = 0.f;
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cg_u32(&s_tempty)) : "memory");
+            if (do_prof && tid == 64 && it < 2) a.prof[13 + it] = clock64();
+            // Phase B: hi / lo split and stores, one 32 x 16 sub-block at a time through the warp's staging slot
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const int cc = cbase + g * 16;
+                if (j0 + cc >= S || (a.mode & 4)) continue;  // warp-uniform
+                if (a.final_sum) {
+                    float* o = a.out + (size_t)p * SS + (size_t)row * S + j0 + cc;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[g * 16 + 4 * q], v[g * 16 + 4 * q + 1], v[g * 16 + 4 * q + 2], v[g * 16 + 4 * q + 3]);
+                    continue;
+                }
+                // the staging slot may still be read by the TMA stores of the previous sub-block
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                if (!transposed) {  // [32 rows][16 cols], row = lane
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float h[4], l[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            h[u] = __uint_as_float(__float_as_uint(v[g * 16 + 4 * q + u]) & 0xffffe000u);
+                            l[u] = v[g * 16 + 4 * q + u] - h[u];
+                        }
+                        *reinterpret_cast<float4*>(stg_hi + lane * 16 + 4 * q) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4*>(stg_lo + lane * 16 + 4 * q) = make_float4(l[0], l[1], l[2], l[3]);
+                    }
+                } else {  // out^T: [16 cols][32 rows], the warp writes 32 consecutive floats per column
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const float h = __uint_as_float(__float_as_uint(v[g * 16 + q]) & 0xffffe000u);
+                        stg_hi[q * 32 + lane] = h;
+                        stg_lo[q * 32 + lane] = v[g * 16 + q] - h;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (!transposed) {
+                        cg_tma_store_3d(&map_o, stg_u32, j0 + cc, i0 + q4 * 32, 2 * p);
+                        cg_tma_store_3d(&map_o, stg_u32 + 2048, j0 + cc, i0 + q4 * 32, 2 * p + 1);
+                    } else {
+                        cg_tma_store_3d(&map_ot, stg_u32, i0 + q4 * 32, j0 + cc, 2 * p);
+                        cg_tma_store_3d(&map_ot, stg_u32 + 2048, i0 + q4 * 32, j0 + cc, 2 * p + 1);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            vmax = warp_max(vmax);
+            if (lane == 0 && vmax > 0.f) atomicMax(a.zmax_out + p, __float_as_uint(vmax));
+            if (do_prof && tid == 64 && it < 2) a.prof[9 + 2 * it] = clock64();
         }
-        vmax = warp_max(vmax);
-        if (lane == 0 && vmax > 0.f) atomicMax(a.zmax_out + p, __float_as_uint(vmax));
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    if (do_prof && tid == 32) a.prof[12] = clock64();
 }
 
 // ------------------------------------------------------------------------------------------------ leaf preparation and conversions
@@ -434,17 +534,75 @@ __global__ void cg_roles_kernel(int* roles, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) roles[i] = cg_role(i, n);
 }
 
+// planes buffer [n][2][S][S] as the destination of the epilogue's TMA stores: (inner, rows) box without swizzle
+static int cg_make_store_map(CUtensorMap* map, const float* base, int64_t n_elems, int S, int box_inner, int box_rows) {
+    EncodeTiledFn enc = cg_encode_fn();
+    if (!enc) return FB2_ERR_UNSUPPORTED;
+    cuuint64_t dims[3] = {(cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)(2 * n_elems)};
+    cuuint64_t strides[2] = {(cuuint64_t)S * 4, (cuuint64_t)S * S * 4};
+    cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (store map) failed (%d)", (int)r);
+        return FB2_ERR_CUDA;
+    }
+    return FB2_OK;
+}
+
 static int cg_launch(const float* a_planes, int64_t n_a, const float* b_planes, int64_t n_b, const ChainGemmArgs& args, int64_t pairs, cudaStream_t stream) {
-    CUtensorMap ma, mb;
+    CUtensorMap ma, mb, mo, mot;
     int st = cg_make_map(&ma, a_planes, n_a, args.S, CG_BM);
     if (st != FB2_OK) return st;
     st = cg_make_map(&mb, b_planes, n_b, args.S, CG_BN);
     if (st != FB2_OK) return st;
-    FB2_CUDA(cudaFuncSetAttribute(chain_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM));
+    // final_sum writes one fp32 plane per product with direct stores; the maps then only need to be valid descriptors
+    const float* obase = args.final_sum ? a_planes : args.out;
+    const int64_t on = args.final_sum ? n_a : pairs;
+    st = cg_make_store_map(&mo, obase, on, args.S, 16, 32);
+    if (st != FB2_OK) return st;
+    st = cg_make_store_map(&mot, obase, on, args.S, 32, 16);
+    if (st != FB2_OK) return st;
+    FB2_CUDA(cudaFuncSetAttribute(chain_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL));
+    ChainGemmArgs margs = args;
+    {
+        const char* m = getenv("FB2_CG_MODE");
+        margs.mode = m ? atoi(m) : 0;
+    }
+    static long long* d_prof = nullptr;
+    const char* pe = getenv("FB2_CG_PROF");
+    if (pe && pe[0] == '1') {
+        if (!d_prof) FB2_CUDA(cudaMalloc(&d_prof, 32 * sizeof(long long)));
+        FB2_CUDA(cudaMemsetAsync(d_prof, 0, 32 * sizeof(long long), stream));
+        margs.prof = d_prof;
+    }
     const int tiles = (args.S / CG_BM) * ((args.S + CG_BN - 1) / CG_BN);
-    FB2_REQUIRE(pairs >= 1 && pairs <= 65535, "chain_gemm: %lld products in one level (grid.y limit 65535): use smaller blocks", (long long)pairs);
-    chain_gemm_tc<<<dim3((unsigned)tiles, (unsigned)pairs), CG_THREADS, CG_SMEM, stream>>>(ma, mb, args);
+    FB2_REQUIRE(pairs >= 1 && pairs <= (1 << 24), "chain_gemm: %lld products in one level", (long long)pairs);
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        FB2_CUDA(cudaGetDevice(&dev));
+        FB2_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int64_t total = (int64_t)tiles * pairs;
+    const unsigned grid = (unsigned)(total < sm_count ? total : sm_count);
+    {
+        const char* se = getenv("FB2_CG_STAGGER");
+        const long long cyc = se ? atoll(se) : (long long)(args.S / CG_KC) * 1000;  // ~ half of a tile's main loop
+        margs.stagger = (total >= 4 * (int64_t)grid) ? cyc : 0;
+    }
+    chain_gemm_tc<<<grid, CG_THREADS, CG_SMEM_TOTAL, stream>>>(ma, mb, mo, mot, margs);
     FB2_LAUNCH_CHECK();
+    if (margs.prof) {
+        long long h[32];
+        FB2_CUDA(cudaStreamSynchronize(stream));
+        FB2_CUDA(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[cg prof] pairs %lld cta 0: setup %lld | tile0 first chunk +%lld, last chunk +%lld | tile1 first chunk +%lld, last chunk +%lld | "
+                        "epilogue0 start +%lld, tensor memory released after %lld, len %lld | epilogue1 start +%lld, released after %lld, len %lld | total %lld (cycles)\n",
+                (long long)pairs, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[8] - h[0], h[13] - h[8], h[9] - h[8], h[10] - h[0],
+                h[14] - h[10], h[11] - h[10], h[12] - h[0]);
+    }
     return FB2_OK;
 }
 
