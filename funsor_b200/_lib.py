@@ -38,6 +38,7 @@ SIGNATURES = {
     "fb2_semiring_matmul_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
     "fb2_semiring_matmul_f32": (c_int, [c_int, _fp, _i64p, _fp, _i64p, _fp, _fp, c_int64, c_int64, c_int32, c_int32, c_int32, _fp, c_size_t, c_void_p]),
     "fb2_chain_product_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
+    "fb2_chain_product_gemm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "fb2_chain_product_f32": (c_int, [c_int, _fp, _i64p, c_int64, c_int64, c_int32, _fp, _fp, c_size_t, c_void_p]),
     "fb2_hmm_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64, c_int32]),
     "fb2_hmm_forward_f32": (c_int, [c_int, _fp, c_int64, _fp, c_int64, c_int64, _fp, c_int64, c_int64, c_int32, _fp, _fp, _fp, c_size_t, c_void_p]),

@@ -58,8 +58,10 @@ struct ChainGemmArgs {
     int a_shared;          // 1: every pair uses element 0 of the A tensor map (the transition matrix P)
     int a_stride, a_off;   // A element of pair p = a_stride * p + a_off (in the A map's element index)
     int b_stride, b_off;
-    int last_transposed;   // orientation of the LAST output element (others: parity of the output index)
-    int n_out;
+    int last_transposed;   // orientation of the LAST output element of a chain (others: parity of the output index)
+    int n_out;             // products in this launch (all chains)
+    int ppc;               // products per chain; product p belongs to chain p / ppc and is pair q = p % ppc of it
+    int a_cs, b_cs, o_cs;  // elements per chain in the A / B operand arrays and in the output array
     int final_sum;         // 1: write hi + lo as one fp32 matrix, row-major (the result of a tree)
     float comp;
     long long stagger;  // start delay of odd CTAs in cycles (0 = none)
@@ -176,8 +178,9 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
             for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
                 const int p = (int)(t / tiles), tile = (int)(t % tiles);
                 const int i0 = (tile / tiles_n) * CG_BM, j0 = (tile % tiles_n) * CG_BN;
-                const int ia = a.a_shared ? 0 : a.a_stride * p + a.a_off;
-                const int ib = a.b_stride * p + a.b_off;
+                const int ch = p / a.ppc, q = p % a.ppc;
+                const int ia = a.a_shared ? 0 : ch * a.a_cs + a.a_stride * q + a.a_off;
+                const int ib = ch * a.b_cs + a.b_stride * q + a.b_off;
                 for (int c = 0; c < nchunks; ++c, ++gc) {
                     const int s = (int)(gc % CG_STAGES);
                     if (gc >= CG_STAGES) cg_wait(cg_u32(&s_empty[s]), (uint32_t)(((gc / CG_STAGES) - 1) & 1));
@@ -244,8 +247,10 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
         for (int64_t t = blockIdx.x; t < total; t += gridDim.x, ++it) {
             const int p = (int)(t / tiles), tile = (int)(t % tiles);
             const int i0 = (tile / tiles_n) * CG_BM, j0 = (tile % tiles_n) * CG_BN;
-            const int ia = a.a_shared ? 0 : a.a_stride * p + a.a_off;
-            const int ib = a.b_stride * p + a.b_off;
+            const int ch = p / a.ppc, pq = p % a.ppc;
+            const int ia = a.a_shared ? 0 : ch * a.a_cs + a.a_stride * pq + a.a_off;
+            const int ib = ch * a.b_cs + a.b_stride * pq + a.b_off;
+            const int po = ch * a.o_cs + pq;  // output element
             const int row = i0 + q4 * 32 + lane;
             // scaling state of the operands -> exact power-of-two renormalisation
             const float za = a.zmax_a ? __uint_as_float(a.zmax_a[ia]) : 1.f;
@@ -254,9 +259,9 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
             if (za > 0.f) frexpf(za, &ea);
             if (zb > 0.f) frexpf(zb, &eb);
             const float scale = ldexpf(1.f, -(ea + eb));
-            const bool transposed = a.final_sum ? false : (p == a.n_out - 1 ? a.last_transposed != 0 : (p & 1) != 0);
-            if (tile == 0 && warp == 2 && lane == 0)
-                a.E_out[p] = (a.E_a ? a.E_a[ia] : 0) + (a.E_b ? a.E_b[ib] : 0) + ea + eb;
+            const bool transposed = a.final_sum ? false : (pq == a.ppc - 1 ? a.last_transposed != 0 : (pq & 1) != 0);
+            if (tile == 0 && q4 == 0 && chalf == 0 && lane == 0)
+                a.E_out[po] = (a.E_a ? a.E_a[ia] : 0) + (a.E_b ? a.E_b[ib] : 0) + ea + eb;
             const float* cs = a.colscale ? a.colscale + (size_t)p * S : nullptr;
             cg_wait(cg_u32(&s_tfull), (uint32_t)(it & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -298,7 +303,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
                 const int cc = cbase + g * 16;
                 if (j0 + cc >= S || (a.mode & 4)) continue;  // warp-uniform
                 if (a.final_sum) {
-                    float* o = a.out + (size_t)p * SS + (size_t)row * S + j0 + cc;
+                    float* o = a.out + (size_t)po * SS + (size_t)row * S + j0 + cc;
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[g * 16 + 4 * q], v[g * 16 + 4 * q + 1], v[g * 16 + 4 * q + 2], v[g * 16 + 4 * q + 3]);
@@ -331,17 +336,17 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
                 __syncwarp();
                 if (lane == 0) {
                     if (!transposed) {
-                        cg_tma_store_3d(&map_o, stg_u32, j0 + cc, i0 + q4 * 32, 2 * p);
-                        cg_tma_store_3d(&map_o, stg_u32 + 2048, j0 + cc, i0 + q4 * 32, 2 * p + 1);
+                        cg_tma_store_3d(&map_o, stg_u32, j0 + cc, i0 + q4 * 32, 2 * po);
+                        cg_tma_store_3d(&map_o, stg_u32 + 2048, j0 + cc, i0 + q4 * 32, 2 * po + 1);
                     } else {
-                        cg_tma_store_3d(&map_ot, stg_u32, i0 + q4 * 32, j0 + cc, 2 * p);
-                        cg_tma_store_3d(&map_ot, stg_u32 + 2048, i0 + q4 * 32, j0 + cc, 2 * p + 1);
+                        cg_tma_store_3d(&map_ot, stg_u32, i0 + q4 * 32, j0 + cc, 2 * po);
+                        cg_tma_store_3d(&map_ot, stg_u32 + 2048, i0 + q4 * 32, j0 + cc, 2 * po + 1);
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
             vmax = warp_max(vmax);
-            if (lane == 0 && vmax > 0.f) atomicMax(a.zmax_out + p, __float_as_uint(vmax));
+            if (lane == 0 && vmax > 0.f) atomicMax(a.zmax_out + po, __float_as_uint(vmax));
             if (do_prof && tid == 64 && it < 2) a.prof[9 + 2 * it] = clock64();
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -559,13 +564,17 @@ static int cg_launch(const float* a_planes, int64_t n_a, const float* b_planes, 
     if (st != FB2_OK) return st;
     // final_sum writes one fp32 plane per product with direct stores; the maps then only need to be valid descriptors
     const float* obase = args.final_sum ? a_planes : args.out;
-    const int64_t on = args.final_sum ? n_a : pairs;
+    const int64_t on = args.final_sum ? n_a : (args.ppc > 0 ? (int64_t)(pairs / args.ppc) * args.o_cs : pairs);
     st = cg_make_store_map(&mo, obase, on, args.S, 16, 32);
     if (st != FB2_OK) return st;
     st = cg_make_store_map(&mot, obase, on, args.S, 32, 16);
     if (st != FB2_OK) return st;
     FB2_CUDA(cudaFuncSetAttribute(chain_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL));
     ChainGemmArgs margs = args;
+    if (margs.ppc <= 0) {  // single chain
+        margs.ppc = (int)pairs;
+        margs.a_cs = margs.b_cs = margs.o_cs = 0;
+    }
     {
         const char* m = getenv("FB2_CG_MODE");
         margs.mode = m ? atoi(m) : 0;
@@ -834,6 +843,158 @@ int hmm_chunk_summary_gemm_device(const float* A, const float* obs, int64_t T, i
         }
     }
     cg_finish_rows<<<296, 256, 0, stream>>>(finalM, final_zmax, final_E, shift_acc, S, rows_out, row_offset);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ dense chains: sequential_sum_product
+// trans[B][T][S][S] (log domain, contiguous) -> out[B][S][S] = trans[b,0] (x) ... (x) trans[b,T-1] in the reference's tree order
+// (sum_product.py:690-701).  Every element is shifted by its largest entry and exponentiated ONCE (the shift trick of
+// einsum/numpy_log.py:24-47 hoisted out of the levels), the tree runs in the linear domain on the GEMM kernel above, the result is
+// taken back to the log domain with all shifts and binary exponents added in double precision.
+__global__ void cg_elem_max(const float* __restrict__ x, int64_t SS, float* __restrict__ shift) {
+    __shared__ float s_red[32];
+    const float* xe = x + (int64_t)blockIdx.x * SS;
+    float m = -FLT_MAX;
+    for (int64_t i = threadIdx.x * 4; i < SS; i += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xe + i);
+        m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = -FLT_MAX;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t = fmaxf(t, s_red[q]);
+        shift[blockIdx.x] = t > -FLT_MAX ? t : 0.f;  // an all -inf element stays all zero
+    }
+}
+// planes[e] = hi / lo split of exp(x[e] - shift[e]) in the orientation of element e's role in its chain of T elements
+__global__ void cg_exp_split_tiles(const float* __restrict__ x, const float* __restrict__ shift, int S, int64_t T, float* __restrict__ planes) {
+    __shared__ float tile[32][33];
+    const int64_t e = blockIdx.z;
+    const size_t SS = (size_t)S * S;
+    const bool tr = cg_role(e % T, T) != 0;
+    const float sh = shift[e];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const float* xe = x + e * SS;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) tile[rr][threadIdx.x] = expf(xe[(size_t)(r0 + rr) * S + c0 + threadIdx.x] - sh);
+    __syncthreads();
+    float* oh = planes + e * 2 * SS;
+    float* ol = oh + SS;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const float v = tr ? tile[threadIdx.x][rr] : tile[rr][threadIdx.x];
+        const size_t o = tr ? (size_t)(c0 + rr) * S + r0 + threadIdx.x : (size_t)(r0 + rr) * S + c0 + threadIdx.x;
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        oh[o] = h;
+        ol[o] = v - h;
+    }
+}
+__global__ void cg_copy_leftover(const float* __restrict__ src, const unsigned* __restrict__ zsrc, const int* __restrict__ esrc, int64_t n, int64_t nd, size_t SS2,
+                                 float* __restrict__ dst, unsigned* __restrict__ zdst, int* __restrict__ edst, int first_level) {
+    const int64_t ch = blockIdx.y;
+    const float* s_ = src + (size_t)(ch * n + n - 1) * SS2;
+    float* d_ = dst + (size_t)(ch * nd + nd - 1) * SS2;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < SS2; i += (size_t)gridDim.x * blockDim.x * 4)
+        *reinterpret_cast<float4*>(d_ + i) = *reinterpret_cast<const float4*>(s_ + i);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        zdst[ch * nd + nd - 1] = first_level ? 0x3f800000u : zsrc[ch * n + n - 1];
+        edst[ch * nd + nd - 1] = first_level ? 0 : esrc[ch * n + n - 1];
+    }
+}
+// out[b] = log(M[b]) + E[b] ln2 + sum_t shift[b,t]
+__global__ void cg_finish_dense(const float* __restrict__ M, const int* __restrict__ E, const float* __restrict__ shift, int64_t T, size_t SS, float* __restrict__ out) {
+    __shared__ double s_off;
+    const int64_t b = blockIdx.y;
+    if (threadIdx.x == 0) {
+        double acc = (double)E[b] * 0.69314718055994530942;
+        for (int64_t t = 0; t < T; ++t) acc += (double)shift[b * T + t];
+        s_off = acc;
+    }
+    __syncthreads();
+    const double off = s_off;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < SS; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = M[b * SS + i];
+        out[b * SS + i] = v > 0.f ? (float)((double)logf(v) + off) : -INFINITY;
+    }
+}
+
+size_t chain_product_gemm_workspace_bytes(int64_t B, int64_t T, int S) {
+    const size_t SS = (size_t)S * S;
+    const int64_t t1 = (T + 1) / 2, t2 = (t1 + 1) / 2;
+    return align_up((size_t)B * T * 2 * SS * 4) + align_up((size_t)B * t1 * 2 * SS * 4) + align_up((size_t)B * t2 * 2 * SS * 4) + align_up((size_t)B * SS * 4) +
+           align_up((size_t)B * T * 4) + 4 * align_up((size_t)B * (t1 + 1) * 4) + 4096;
+}
+
+int chain_product_gemm_device(const float* trans, int64_t B, int64_t T, int S, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!chain_gemm_supported(S) || T < 2 || B < 1) return FB2_ERR_UNSUPPORTED;
+    const size_t SS = (size_t)S * S, SS2 = 2 * SS;
+    const int64_t t1 = (T + 1) / 2, t2 = (t1 + 1) / 2;
+    if (B * T > (1 << 22)) return FB2_ERR_UNSUPPORTED;
+    Arena ar(workspace, workspace_bytes);
+    float* leaves = ar.take<float>((size_t)B * T * SS2);
+    float* buf[2] = {ar.take<float>((size_t)B * t1 * SS2), ar.take<float>((size_t)B * t2 * SS2)};
+    float* finalM = ar.take<float>((size_t)B * SS);
+    float* shift = ar.take<float>((size_t)B * T);
+    unsigned* zm[2];
+    int* Ex[2];
+    for (int q = 0; q < 2; ++q) {
+        zm[q] = ar.take<unsigned>((size_t)B * (t1 + 1));
+        Ex[q] = ar.take<int>((size_t)B * (t1 + 1));
+    }
+    if (!ar.ok()) return FB2_ERR_UNSUPPORTED;  // the caller falls back to the level-by-level log-domain kernels
+    cg_elem_max<<<(unsigned)(B * T), 256, 0, stream>>>(trans, (int64_t)SS, shift);
+    FB2_LAUNCH_CHECK();
+    {
+        int64_t done = 0;
+        while (done < B * T) {  // grid.z limit
+            const int64_t nz = B * T - done < 65535 ? B * T - done : 65535;
+            FB2_REQUIRE(done % T == 0 || nz == B * T - done || true, "unreachable");
+            // roles depend on e % T, so offsetting the element pointer by `done` needs the same offset inside the kernel: pass via pointer arithmetic
+            // only when `done` is a multiple of T; otherwise launch per chain
+            if (done % T != 0) return FB2_ERR_UNSUPPORTED;
+            int64_t take = nz - nz % T;
+            if (take == 0) return FB2_ERR_UNSUPPORTED;  // one chain longer than 65535 elements
+            cg_exp_split_tiles<<<dim3((unsigned)(S / 32), (unsigned)(S / 32), (unsigned)take), dim3(32, 8), 0, stream>>>(trans + done * SS, shift + done, S, T,
+                                                                                                                  leaves + done * SS2);
+            FB2_LAUNCH_CHECK();
+            done += take;
+        }
+    }
+    const float comp = 5.82e-8f;
+    const float* src = leaves;
+    const unsigned* zsrc = nullptr;
+    const int* esrc = nullptr;
+    int64_t n = T;
+    int which = 0;
+    bool first = true;
+    while (n > 1) {
+        const int64_t pairs = n / 2, nd = (n + 1) / 2;
+        const bool is_final = nd == 1;
+        ChainGemmArgs a{};
+        a.S = S; a.comp = comp;
+        a.a_stride = 2; a.a_off = 0; a.b_stride = 2; a.b_off = 1;
+        a.zmax_a = zsrc; a.E_a = esrc; a.zmax_b = zsrc; a.E_b = esrc;
+        a.ppc = (int)pairs; a.a_cs = (int)n; a.b_cs = (int)n; a.o_cs = (int)nd;
+        a.n_out = (int)(B * pairs);
+        a.final_sum = is_final;
+        a.out = is_final ? finalM : buf[which];
+        a.zmax_out = zm[which];
+        a.E_out = Ex[which];
+        a.last_transposed = cg_role(pairs - 1, nd);
+        FB2_CUDA(cudaMemsetAsync(a.zmax_out, 0, (size_t)B * nd * sizeof(unsigned), stream));
+        int st = cg_launch(src, B * n, src, B * n, a, B * pairs, stream);
+        if (st != FB2_OK) return st;
+        if (n & 1) {
+            cg_copy_leftover<<<dim3(32, (unsigned)B), 256, 0, stream>>>(src, zsrc, esrc, n, nd, SS2, buf[which], zm[which], Ex[which], first ? 1 : 0);
+            FB2_LAUNCH_CHECK();
+        }
+        src = buf[which]; zsrc = zm[which]; esrc = Ex[which];
+        n = nd;
+        which ^= 1;
+        first = false;
+    }
+    cg_finish_dense<<<dim3(64, (unsigned)B), 256, 0, stream>>>(finalM, esrc, shift, T, SS, out);
     FB2_LAUNCH_CHECK();
     return FB2_OK;
 }

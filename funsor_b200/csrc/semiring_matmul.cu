@@ -432,6 +432,21 @@ static void level_sizes(int64_t T, int64_t* t1, int64_t* t2) {
     *t2 = (*t1 + 1) / 2;
 }
 
+namespace fb2 {  // chain_gemm_tc.cu
+bool chain_gemm_supported(int S);
+size_t chain_product_gemm_workspace_bytes(int64_t B, int64_t T, int S);
+int chain_product_gemm_device(const float* trans, int64_t B, int64_t T, int S, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+}  // namespace fb2
+static bool chain_gemm_enabled() {
+    const char* e = getenv("FB2_CHAIN_GEMM");
+    return !(e && e[0] == '0');
+}
+
+extern "C" size_t fb2_chain_product_gemm_workspace_bytes(int64_t B, int64_t T, int32_t S) {
+    if (B < 1 || T < 4 || !chain_gemm_supported(S) || !chain_gemm_enabled()) return 0;
+    return chain_product_gemm_workspace_bytes(B, T, S);
+}
+
 extern "C" size_t fb2_chain_product_workspace_bytes(int64_t B, int64_t T, int32_t S) {
     int64_t t1, t2;
     level_sizes(T, &t1, &t2);
@@ -451,6 +466,13 @@ extern "C" int fb2_chain_product_f32(int semiring, const float* trans, const int
     if (B == 0) return FB2_OK;
     int64_t per = (int64_t)S * S;
     if (T == 1) return launch_copy_matrices(trans, ts[0], ts[2], ts[3], out, per, B, S, stream);
+    // Large state spaces, log semiring, contiguous input, a workspace that holds the TF32 planes of every level: the whole tree runs in
+    // the linear domain on the TMA + tcgen05 GEMM kernel (chain_gemm_tc.cu); exp / log are applied once per chain instead of per level.
+    if (semiring == FB2_SEMIRING_LOG && T >= 4 && chain_gemm_enabled() && chain_gemm_supported(S) && ts[3] == 1 && ts[2] == S && ts[1] == per &&
+        ts[0] == T * per && workspace_bytes >= chain_product_gemm_workspace_bytes(B, T, S)) {
+        st = chain_product_gemm_device(trans, B, T, S, out, workspace, workspace_bytes, stream);
+        if (st != FB2_ERR_UNSUPPORTED) return st;
+    }
     int64_t t1, t2;
     level_sizes(T, &t1, &t2);
     Arena arena(workspace, workspace_bytes);

@@ -152,6 +152,11 @@ def sequential_sum_product(sum_op, prod_op, trans, time=-3):
         return out.reshape(batch + (S, S))
     lib = _lib.load()
     nbytes = lib.fb2_chain_product_workspace_bytes(B, T, S)
+    if semi == SEMIRING_LOG and t4.is_contiguous():
+        # the linear-domain GEMM tree (csrc/chain_gemm_tc.cu) needs room for the TF32 planes of every level: take it when it is there
+        big = lib.fb2_chain_product_gemm_workspace_bytes(B, T, S)
+        if big and big < 0.8 * torch.cuda.mem_get_info(trans.device)[0]:
+            nbytes = max(nbytes, big)
     ws = _workspace(nbytes, trans.device)
     with torch.cuda.device(trans.device):
         check(lib.fb2_chain_product_f32(semi, t4.data_ptr(), strides4(t4.stride()), B, T, S, out.data_ptr(),

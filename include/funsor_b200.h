@@ -78,6 +78,11 @@ int fb2_semiring_matmul_f32(int semiring, const float* x, const int64_t x_stride
  * out is contiguous [B,S,S].
  */
 size_t fb2_chain_product_workspace_bytes(int64_t B, int64_t T, int32_t S);
+/* Optional larger workspace: when the caller provides at least this many bytes (0 = not applicable), a contiguous LOG-semiring chain
+ * with S a multiple of 128 in [256, 1024] and T >= 4 runs as a linear-domain GEMM tree (TMA + tcgen05, csrc/chain_gemm_tc.cu): the
+ * shift / exp / log of einsum/numpy_log.py:24-47 are applied once per chain instead of once per level.  Entries more than ~87 nats
+ * below the largest entry of their matrix flush to -inf on this path. */
+size_t fb2_chain_product_gemm_workspace_bytes(int64_t B, int64_t T, int32_t S);
 int fb2_chain_product_f32(int semiring, const float* trans, const int64_t trans_strides[4], int64_t B,
                           int64_t T, int32_t S, float* out, void* workspace, size_t workspace_bytes,
                           void* stream);

@@ -81,3 +81,25 @@ def test_chunk_summary_gemm_sparse_transitions(fb):
     fin = torch.isfinite(want)
     assert bool((torch.isfinite(got) == fin).all())
     assert (got[fin] - want[fin]).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("B,T,S", [(1, 4, 256), (2, 5, 256), (3, 16, 256), (2, 37, 384), (1, 8, 1024), (4, 7, 512)])
+def test_dense_chain_on_the_gemm_engine(fb, B, T, S):
+    """sequential_sum_product (sum_product.py:652-701) of a dense log-semiring chain at large S: linear-domain GEMM tree against a
+    float64 evaluation of the same products, and against the level-by-level log-domain kernels (FB2_CHAIN_GEMM=0 path)."""
+    import os
+
+    g = torch.Generator(device=DEV).manual_seed(B * 100 + T)
+    trans = torch.randn(B, T, S, S, device=DEV, generator=g) * 3.0 - 5.0
+    got = fb.sequential_sum_product("logaddexp", "add", trans)
+    want = trans[:, 0].double()
+    for t in range(1, T):
+        want = torch.logsumexp(want.unsqueeze(-1) + trans[:, t].double().unsqueeze(-3), -2)
+    err = ((got.double() - want).abs() / (1.0 + want.abs())).max().item()
+    assert err <= 1e-5, err
+    os.environ["FB2_CHAIN_GEMM"] = "0"
+    try:
+        old = fb.sequential_sum_product("logaddexp", "add", trans)
+    finally:
+        del os.environ["FB2_CHAIN_GEMM"]
+    assert ((got - old).abs() / (1.0 + old.abs())).max().item() <= 2e-5
