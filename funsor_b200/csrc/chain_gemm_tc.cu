@@ -1,25 +1,35 @@
-// Linear-domain matrix-chain products on the 5th-generation tensor cores: TMA-fed, warp-specialised 3xTF32 GEMM.
+// Linear-domain matrix-chain products on the 5th-generation tensor cores: TMA-fed, warp-specialised, persistent 3xTF32 GEMM.
 //
 // What it computes.  The chunk summary of a time-sharded HMM (mixed_sequential_sum_product sum_product.py:766-795 with
 // segments = GPUs) and every large dense scan are chains of S x S matrix products in the log semiring (sequential_sum_product
 // sum_product.py:652-701; one level = Contraction[Logaddexp, Add, Tensor, Tensor] cnf.py:335-379).  The reference's own trick
 // (einsum/numpy_log.py:24-47: subtract a shift, exp, multiply, log, add the shift back) is applied ONCE per chain instead of once per
 // level: all elements of the tree are kept in the LINEAR domain as non-negative fp32 values times a power of two per matrix, so that a
-// level is a plain GEMM.  A matrix lives as two planes, hi = the TF32 truncation of the value and lo = value - hi (exact in fp32, its
-// own TF32 truncation carries 21+ mantissa bits together with hi), and a product is hi*hi + lo*hi + hi*lo with fp32 accumulation in
-// tensor memory.  The planes are written by the epilogue of the level below, so the main loop does nothing but move tiles and issue
-// tensor instructions:
+// level is a plain GEMM, computed as 3xTF32 (hi*hi + lo*hi + hi*lo, fp32 accumulation in tensor memory) for fp32-class accuracy.
 //
-//     warp 0  producer : cp.async.bulk.tensor (TMA, 128-byte swizzle) of the A / B tiles of one K chunk into a 2-stage ring,
-//                        mbarrier complete_tx
-//     warp 1  MMA      : tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 256, K = 8; 12 instructions per chunk; tcgen05.commit
-//                        releases the stage; the last commit hands the accumulators to the epilogue
-//     warps 2-5 epilogue: tcgen05.ld, optional column scaling (the observation of the second step of a leaf pair), exact power-of-two
-//                        renormalisation, hi / lo split, stores in the orientation the NEXT level needs, per-matrix max by atomicMax
+// Data movement.  A matrix is ONE fp32 plane in HBM.  The tensor core reads an fp32 container as TF32 by ignoring the low 13
+// mantissa bits, so the plane as loaded by TMA already is the "hi" operand; the "lo" operand, v - trunc_tf32(v), is computed in
+// shared memory by transform warps (one LOP + one FSUB per element, same swizzled offset in the neighbouring buffer).  Measured on
+// the first version of this kernel, which kept hi / lo planes in HBM: at S = 512 a product moved 6 MB for 0.8 GFLOP of issued tensor
+// work and the kernel ran at 76 % of HBM bandwidth -- memory-bound; computing lo on chip halves every stream (and lets the leaf
+// level scale its left operand by the observation weights on the fly instead of materialising scaled copies).
+//
+//     warp 0     producer : cp.async.bulk.tensor (TMA, 128-byte swizzle) of the raw A / B tiles of a K chunk into a 2-stage ring,
+//                           mbarrier complete_tx; runs ahead of the MMA warp across tiles
+//     warps 2-7  transform: lo = v - trunc(v) (optionally v *= w[k] first: the leaf level's diag(exp(obs))), fence.proxy.async,
+//                           arrive on the stage's `ready` barrier
+//     warp 1     MMA      : tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 256, K = 8; 12 instructions per chunk; tcgen05.commit
+//                           releases the stage; the last commit of a tile hands the accumulators to the epilogue
+//     warps 8-15 epilogue : tcgen05.ld of the warp's 32 x 128 block into REGISTERS, tensor memory handed back at once (the next
+//                           tile's MMAs overlap the stores), optional column scaling, exact power-of-two renormalisation, 32 x 16
+//                           sub-blocks staged in shared memory and written by TMA stores in the orientation the NEXT level needs,
+//                           per-matrix max by atomicMax.  setmaxnreg moves registers from the other warpgroups to these two.
+//
+// Persistent: grid = min(#tiles, #SMs); tile t = product * tiles_per_product + tile, so neighbouring CTAs share a product's operands in L2.
 //
 // Orientation.  Both MMA operands are K-major in shared memory, so a matrix that will be a RIGHT operand is stored transposed.  In
 // the reference's tree (pairs (2p, 2p+1), odd leftover appended, sum_product.py:690-701) the role of an element is the parity of its
-// index at the level where it is finally paired; the host walks the carry chain of the last element and tells the kernel.
+// index at the level where it is finally paired; cg_role walks the carry chain of the last element.
 //
 // Scaling.  stored = true / 2^E with an integer E per matrix: leaves are <= 1; the epilogue multiplies by 2^-(ea + eb), ea / eb the
 // binary exponents of the operands' largest stored entries (read from the level below), which bounds every stored value by 4 K and
@@ -38,35 +48,36 @@ namespace fb2 {
 constexpr int CG_BM = 128, CG_BN = 256, CG_KC = 32, CG_STAGES = 2;
 constexpr int CG_A_PLANE = CG_BM * CG_KC * 4;  // 16 KB
 constexpr int CG_B_PLANE = CG_BN * CG_KC * 4;  // 32 KB
-constexpr int CG_STAGE_BYTES = 2 * CG_A_PLANE + 2 * CG_B_PLANE;  // 96 KB
-
-constexpr int CG_THREADS = 320;  // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (4 lane quarters x 2 column halves)
-
+constexpr int CG_STAGE_BYTES = 2 * CG_A_PLANE + 2 * CG_B_PLANE;  // 96 KB: [A hi | A lo | B hi | B lo]
+constexpr int CG_TX_BYTES = CG_A_PLANE + CG_B_PLANE;             // what TMA brings per stage: the two raw tiles
+constexpr int CG_THREADS = 512;                                  // 4 warpgroups
+constexpr int CG_XF_WARPS = 6;                                   // transform warps 2..7
+constexpr int CG_EPI_WARPS = 8;                                  // epilogue warps 8..15
+constexpr int CG_EPI_BYTES = 4096;                               // per epilogue warp: two [32 x 16] fp32 staging slots
+constexpr int CG_SMEM_TOTAL = 1024 + CG_STAGES * CG_STAGE_BYTES + CG_EPI_WARPS * CG_EPI_BYTES;
 
 struct ChainGemmArgs {
-    // outputs of this level
-    float* out;            // planes [n_out][2][S][S] (orientation per element), or [n_out][S][S] fp32 when final_sum
-    unsigned* zmax_out;    // [n_out] bits of the largest stored entry (zeroed before the launch)
-    int* E_out;            // [n_out]
-    // scaling state of the operands
-    const unsigned* zmax_a;  // [n_a] or nullptr (= 1.0)
-    const int* E_a;          // [n_a] or nullptr (= 0)
+    float* out;              // [n_out_elems][S][S] fp32, orientation per element
+    unsigned* zmax_out;      // [n_out_elems] bits of the largest stored entry (zeroed before the launch)
+    int* E_out;              // [n_out_elems]
+    const unsigned* zmax_a;  // scaling state of the operands: nullptr = (1.0, 0)
+    const int* E_a;
     const unsigned* zmax_b;
     const int* E_b;
-    const float* colscale;   // nullable [pairs][S]: out[:, j] *= colscale[p][j]
+    const float* kscale;     // nullable: A[:, k] *= kscale[p * scale_stride + k]   (leaf level: diag(exp(obs_t0)) between the two P)
+    const float* colscale;   // nullable: out[:, j] *= colscale[p * scale_stride + j] (leaf level: diag(exp(obs_t1)))
+    int64_t scale_stride;
     int S;
-    int a_shared;          // 1: every pair uses element 0 of the A tensor map (the transition matrix P)
-    int a_stride, a_off;   // A element of pair p = a_stride * p + a_off (in the A map's element index)
+    int a_shared;            // 1: every product uses element 0 of the A tensor map
+    int a_stride, a_off;     // A element of pair q of chain ch = ch * a_cs + a_stride * q + a_off
     int b_stride, b_off;
-    int last_transposed;   // orientation of the LAST output element of a chain (others: parity of the output index)
-    int n_out;             // products in this launch (all chains)
-    int ppc;               // products per chain; product p belongs to chain p / ppc and is pair q = p % ppc of it
-    int a_cs, b_cs, o_cs;  // elements per chain in the A / B operand arrays and in the output array
-    int final_sum;         // 1: write hi + lo as one fp32 matrix, row-major (the result of a tree)
+    int last_transposed;     // orientation of the LAST output element of a chain (others: parity of the output index)
+    int n_out;               // products in this launch (all chains)
+    int ppc;                 // products per chain
+    int a_cs, b_cs, o_cs;    // elements per chain in the A / B operand arrays and in the output array
     float comp;
-    long long stagger;  // start delay of odd CTAs in cycles (0 = none)
-    long long* prof;  // debugging aid (FB2_CG_PROF=1): clock64 stamps of CTA (0, 0) and of the last CTA
-    int mode;  // FB2_CG_MODE ablations: 1 = no TMA loads after the first two chunks, 2 = no MMAs, 4 = no epilogue stores
+    long long* prof;         // debugging aid (FB2_CG_PROF=1): clock64 stamps of CTA 0
+    int mode;                // FB2_CG_MODE ablations: 1 = no TMA loads after the first two chunks, 2 = one MMA per tile, 4 = no stores
 };
 
 __device__ __forceinline__ uint32_t cg_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,8 +108,9 @@ __device__ __forceinline__ void cg_tma_3d(uint32_t dst, const CUtensorMap* map, 
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void cg_tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+__device__ __forceinline__ void cg_tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
 }
 __device__ __forceinline__ void cg_tmem_ld16(uint32_t taddr, uint32_t (&d)[16]) {
     asm volatile(
@@ -108,27 +120,16 @@ __device__ __forceinline__ void cg_tmem_ld16(uint32_t taddr, uint32_t (&d)[16]) 
         : "r"(taddr)
         : "memory");
 }
-
-// Persistent: grid = min(#tiles, #SMs) CTAs, each walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (t = pair * tiles_per_product +
-// tile, so neighbouring CTAs work on the same product and share its operands in L2).  Measured with clock64 stamps on the first,
-// non-persistent version (S = 512): first TMA load of a CTA 6-12k cycles, main loop 1.7k cycles per K chunk (tensor-bound), epilogue
-// 10-22k cycles of poorly coalesced direct stores -- i.e. half of a CTA's life was not tensor work.  Hence (i) the producer runs ahead
-// into the next tile while the epilogue drains tensor memory, (ii) the epilogue stages 32 x 16 sub-blocks in shared memory and
-// writes them with TMA stores (cp.async.bulk.tensor ... global.shared::cta) in the orientation the next level needs.
-constexpr int CG_EPI_WARPS = 8;
-constexpr int CG_EPI_BYTES = 4096;  // per epilogue warp: hi [32 x 16] + lo [32 x 16] fp32
-constexpr int CG_SMEM_TOTAL = 1024 + CG_STAGES * CG_STAGE_BYTES + CG_EPI_WARPS * CG_EPI_BYTES;
-
-__device__ __forceinline__ void cg_tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
+__device__ __forceinline__ float cg_trunc_tf32(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+__device__ __forceinline__ float4 cg_lo4(const float4 v) {
+    return make_float4(v.x - cg_trunc_tf32(v.x), v.y - cg_trunc_tf32(v.y), v.z - cg_trunc_tf32(v.z), v.w - cg_trunc_tf32(v.w));
 }
 
 __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                                const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_ot,
                                                                ChainGemmArgs a) {
     extern __shared__ unsigned char cg_smem_raw[];
-    __shared__ __align__(8) unsigned long long s_full[CG_STAGES], s_empty[CG_STAGES], s_tfull, s_tempty;
+    __shared__ __align__(8) unsigned long long s_full[CG_STAGES], s_ready[CG_STAGES], s_empty[CG_STAGES], s_tfull, s_tempty;
     __shared__ uint32_t s_tmem;
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cg_smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
 #pragma unroll
         for (int s = 0; s < CG_STAGES; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_full[s])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cg_u32(&s_ready[s])), "n"(CG_XF_WARPS) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_empty[s])) : "memory");
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_tfull)) : "memory");
@@ -163,87 +165,128 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
     if (do_prof && tid == 0) a.prof[1] = clock64();
-    // De-phase the CTAs.  All persistent CTAs start together and would stay in lock step: every SM reading operands during the
-    // main loop, then every SM writing its 256 KB of planes during the epilogue, so that neither the HBM read nor the write
-    // stream is ever shared with tensor work of another SM.  Odd CTAs start half a tile late (a.stagger cycles).
-    if (a.stagger > 0 && (blockIdx.x & 1)) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < a.stagger) __nanosleep(200);
-    }
 
-    if (warp == 0) {
-        // ---------------- producer: one lane, runs ahead of the MMA warp by the depth of the ring (also across tiles)
-        if (lane == 0) {
-            int64_t gc = 0;  // chunks issued by this CTA so far
-            for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
-                const int p = (int)(t / tiles), tile = (int)(t % tiles);
-                const int i0 = (tile / tiles_n) * CG_BM, j0 = (tile % tiles_n) * CG_BN;
-                const int ch = p / a.ppc, q = p % a.ppc;
-                const int ia = a.a_shared ? 0 : ch * a.a_cs + a.a_stride * q + a.a_off;
-                const int ib = ch * a.b_cs + a.b_stride * q + a.b_off;
+    if (warp < 8) {
+        // warpgroups 0 and 1 (producer, MMA issuer, transform) need few registers: give the rest to the epilogue warpgroups
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;" ::: "memory");
+        if (warp == 0) {
+            // ---------------- producer: one lane, runs ahead of the MMA warp by the depth of the ring (also across tiles)
+            if (lane == 0) {
+                int64_t gc = 0;  // chunks issued by this CTA so far
+                for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+                    const int p = (int)(t / tiles), tile = (int)(t % tiles);
+                    const int i0 = (tile / tiles_n) * CG_BM, j0 = (tile % tiles_n) * CG_BN;
+                    const int ch = p / a.ppc, q = p % a.ppc;
+                    const int ia = a.a_shared ? 0 : ch * a.a_cs + a.a_stride * q + a.a_off;
+                    const int ib = ch * a.b_cs + a.b_stride * q + a.b_off;
+                    for (int c = 0; c < nchunks; ++c, ++gc) {
+                        const int s = (int)(gc % CG_STAGES);
+                        if (gc >= CG_STAGES) cg_wait(cg_u32(&s_empty[s]), (uint32_t)(((gc / CG_STAGES) - 1) & 1));
+                        const uint32_t bar = cg_u32(&s_full[s]);
+                        if ((a.mode & 1) && gc >= CG_STAGES) {  // ablation: no data movement, just hand the stage on
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+                            continue;
+                        }
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)CG_TX_BYTES) : "memory");
+                        const uint32_t st = cg_u32(smem + (size_t)s * CG_STAGE_BYTES);
+                        cg_tma_3d(st, &map_a, c * CG_KC, i0, ia, bar);
+                        cg_tma_3d(st + 2 * CG_A_PLANE, &map_b, c * CG_KC, j0, ib, bar);
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ---------------- MMA issuer
+            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CG_BN >> 3) << 17) | ((128u >> 4) << 24);
+            int64_t gc = 0;
+            int it = 0;
+            for (int64_t t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+                if (it > 0) {  // the epilogue of the previous tile must have read the accumulators out of tensor memory
+                    cg_wait(cg_u32(&s_tempty), (uint32_t)((it - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
                 for (int c = 0; c < nchunks; ++c, ++gc) {
                     const int s = (int)(gc % CG_STAGES);
-                    if (gc >= CG_STAGES) cg_wait(cg_u32(&s_empty[s]), (uint32_t)(((gc / CG_STAGES) - 1) & 1));
-                    const uint32_t bar = cg_u32(&s_full[s]);
-                    if ((a.mode & 1) && gc >= CG_STAGES) {  // ablation: no data movement, just hand the stage back
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-                        continue;
-                    }
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)CG_STAGE_BYTES) : "memory");
-                    const uint32_t st = cg_u32(smem + (size_t)s * CG_STAGE_BYTES);
-                    const int k0 = c * CG_KC;
-                    cg_tma_3d(st, &map_a, k0, i0, 2 * ia, bar);
-                    cg_tma_3d(st + CG_A_PLANE, &map_a, k0, i0, 2 * ia + 1, bar);
-                    cg_tma_3d(st + 2 * CG_A_PLANE, &map_b, k0, j0, 2 * ib, bar);
-                    cg_tma_3d(st + 2 * CG_A_PLANE + CG_B_PLANE, &map_b, k0, j0, 2 * ib + 1, bar);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer
-        constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CG_BN >> 3) << 17) | ((128u >> 4) << 24);
-        int64_t gc = 0;
-        int it = 0;
-        for (int64_t t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-            if (it > 0) {  // the epilogue of the previous tile must have read the accumulators out of tensor memory
-                cg_wait(cg_u32(&s_tempty), (uint32_t)((it - 1) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            for (int c = 0; c < nchunks; ++c, ++gc) {
-                const int s = (int)(gc % CG_STAGES);
-                cg_wait(cg_u32(&s_full[s]), (uint32_t)((gc / CG_STAGES) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (do_prof && lane == 0 && it < 2 && (c == 0 || c == nchunks - 1)) a.prof[2 + 2 * it + (c ? 1 : 0)] = clock64();
-                if (lane == 0) {
-                    const uint32_t ah = cg_u32(smem + (size_t)s * CG_STAGE_BYTES), al = ah + CG_A_PLANE, bh = ah + 2 * CG_A_PLANE, bl = bh + CG_B_PLANE;
+                    cg_wait(cg_u32(&s_ready[s]), (uint32_t)((gc / CG_STAGES) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (do_prof && lane == 0 && it < 2 && (c == 0 || c == nchunks - 1)) a.prof[2 + 2 * it + (c ? 1 : 0)] = clock64();
+                    if (lane == 0) {
+                        const uint32_t ah = cg_u32(smem + (size_t)s * CG_STAGE_BYTES), al = ah + CG_A_PLANE, bh = ah + 2 * CG_A_PLANE, bl = bh + CG_B_PLANE;
 #pragma unroll
-                    for (int ks = 0; ks < CG_KC / 8; ++ks) {
-                        if ((a.mode & 2) && (c > 0 || ks > 0)) break;  // ablation: one MMA per tile
-                        const uint64_t dah = cg_desc(ah + ks * 32), dal = cg_desc(al + ks * 32);
-                        const uint64_t dbh = cg_desc(bh + ks * 32), dbl = cg_desc(bl + ks * 32);
-                        cg_mma(tmem, dah, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
-                        cg_mma(tmem + CG_BN, dal, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
-                        cg_mma(tmem + CG_BN, dah, dbl, IDESC, 1u);
+                        for (int ks = 0; ks < CG_KC / 8; ++ks) {
+                            if ((a.mode & 2) && (c > 0 || ks > 0)) break;  // ablation: one MMA per tile
+                            const uint64_t dah = cg_desc(ah + ks * 32), dal = cg_desc(al + ks * 32);
+                            const uint64_t dbh = cg_desc(bh + ks * 32), dbl = cg_desc(bl + ks * 32);
+                            cg_mma(tmem, dah, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                            cg_mma(tmem + CG_BN, dal, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                            cg_mma(tmem + CG_BN, dah, dbl, IDESC, 1u);
+                        }
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cg_u32(&s_empty[s])) : "memory");
+                        if (c == nchunks - 1)
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cg_u32(&s_tfull)) : "memory");
                     }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cg_u32(&s_empty[s])) : "memory");
-                    if (c == nchunks - 1)
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cg_u32(&s_tfull)) : "memory");
+                    __syncwarp();
                 }
-                __syncwarp();
+            }
+        } else {
+            // ---------------- transform: lo = v - trunc_tf32(v) for the stage's raw tiles (A: 1024 16-byte pieces, B: 2048)
+            const int xt = tid - 64;  // 0 .. 191
+            int64_t gc = 0;
+            for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+                const int p = (int)(t / tiles);
+                const float* ksc = a.kscale ? a.kscale + (size_t)p * a.scale_stride : nullptr;
+                for (int c = 0; c < nchunks; ++c, ++gc) {
+                    const int s = (int)(gc % CG_STAGES);
+                    cg_wait(cg_u32(&s_full[s]), (uint32_t)((gc / CG_STAGES) & 1));
+                    unsigned char* st = smem + (size_t)s * CG_STAGE_BYTES;
+                    if (ksc) {
+                        // leaf level: the left operand is P diag(w): scale column k of the A tile.  The 16-byte piece at position j' of
+                        // row r holds the logical k-chunk j' ^ (r % 8) of the 128-byte swizzle.
+                        for (int ci = xt; ci < CG_A_PLANE / 16; ci += CG_XF_WARPS * 32) {
+                            const int r = ci >> 3, jl = (ci & 7) ^ (r & 7);
+                            const float4 w = __ldg(reinterpret_cast<const float4*>(ksc + c * CG_KC + 4 * jl));
+                            float4 v = *reinterpret_cast<float4*>(st + ci * 16);
+                            v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w;
+                            *reinterpret_cast<float4*>(st + ci * 16) = v;
+                            *reinterpret_cast<float4*>(st + CG_A_PLANE + ci * 16) = cg_lo4(v);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {  // 1024 pieces over 192 threads: 5.33 rounds, all loads of the unrolled body issue first
+                            const int ci = xt + i * CG_XF_WARPS * 32;
+                            if (ci < CG_A_PLANE / 16) *reinterpret_cast<float4*>(st + CG_A_PLANE + ci * 16) = cg_lo4(*reinterpret_cast<const float4*>(st + ci * 16));
+                        }
+                    }
+                    unsigned char* sb = st + 2 * CG_A_PLANE;
+                    {
+                        float4 vb[11];
+#pragma unroll
+                        for (int i = 0; i < 11; ++i) {  // 2048 pieces over 192 threads: 10.67 rounds
+                            const int ci = xt + i * CG_XF_WARPS * 32;
+                            if (ci < CG_B_PLANE / 16) vb[i] = *reinterpret_cast<const float4*>(sb + ci * 16);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 11; ++i) {
+                            const int ci = xt + i * CG_XF_WARPS * 32;
+                            if (ci < CG_B_PLANE / 16) *reinterpret_cast<float4*>(sb + CG_B_PLANE + ci * 16) = cg_lo4(vb[i]);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core's reads
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cg_u32(&s_ready[s])) : "memory");
+                }
             }
         }
     } else {
         // ---------------- epilogue: warp w owns tensor-memory lanes 32 (w % 4) .. and one half of the tile's columns
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;" ::: "memory");
         const int q4 = warp & 3;
-        const int chalf = (warp - 2) >> 2;
-        unsigned char* stg = smem + (size_t)CG_STAGES * CG_STAGE_BYTES + (size_t)(warp - 2) * CG_EPI_BYTES;
-        float* stg_hi = reinterpret_cast<float*>(stg);
-        float* stg_lo = stg_hi + 512;
+        const int chalf = (warp - 8) >> 2;
+        unsigned char* stg = smem + (size_t)CG_STAGES * CG_STAGE_BYTES + (size_t)(warp - 8) * CG_EPI_BYTES;
         const uint32_t stg_u32 = cg_u32(stg);
         const float fmain = 1.f + a.comp * (float)(nchunks * (CG_KC / 8));
-        const size_t SS = (size_t)S * S;
         const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
         int it = 0;
+        int slot = 0;
         for (int64_t t = blockIdx.x; t < total; t += gridDim.x, ++it) {
             const int p = (int)(t / tiles), tile = (int)(t % tiles);
             const int i0 = (tile / tiles_n) * CG_BM, j0 = (tile % tiles_n) * CG_BN;
@@ -251,7 +294,6 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
             const int ia = a.a_shared ? 0 : ch * a.a_cs + a.a_stride * pq + a.a_off;
             const int ib = ch * a.b_cs + a.b_stride * pq + a.b_off;
             const int po = ch * a.o_cs + pq;  // output element
-            const int row = i0 + q4 * 32 + lane;
             // scaling state of the operands -> exact power-of-two renormalisation
             const float za = a.zmax_a ? __uint_as_float(a.zmax_a[ia]) : 1.f;
             const float zb = a.zmax_b ? __uint_as_float(a.zmax_b[ib]) : 1.f;
@@ -259,17 +301,14 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
             if (za > 0.f) frexpf(za, &ea);
             if (zb > 0.f) frexpf(zb, &eb);
             const float scale = ldexpf(1.f, -(ea + eb));
-            const bool transposed = a.final_sum ? false : (pq == a.ppc - 1 ? a.last_transposed != 0 : (pq & 1) != 0);
+            const bool transposed = pq == a.ppc - 1 ? a.last_transposed != 0 : (pq & 1) != 0;
             if (tile == 0 && q4 == 0 && chalf == 0 && lane == 0)
                 a.E_out[po] = (a.E_a ? a.E_a[ia] : 0) + (a.E_b ? a.E_b[ib] : 0) + ea + eb;
-            const float* cs = a.colscale ? a.colscale + (size_t)p * S : nullptr;
+            const float* cs = a.colscale ? a.colscale + (size_t)p * a.scale_stride : nullptr;
             cg_wait(cg_u32(&s_tfull), (uint32_t)(it & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (do_prof && tid == 64 && it < 2) a.prof[8 + 2 * it] = clock64();
-            // Phase A: pull this warp's 32 x 128 block of the accumulators into REGISTERS (128 values per thread) and hand tensor memory
-            // back at once, so that the next tile's MMAs run while phase B writes the planes out.  (With the single 2 x 256-column
-            // accumulator set there is no second buffer in tensor memory; measured before this split: the MMA warp sat idle for the
-            // whole 19-21k-cycle epilogue of every tile.)
+            if (do_prof && tid == 256 && it < 2) a.prof[8 + 2 * it] = clock64();
+            // Phase A: this warp's 32 x 128 block of the accumulators -> registers; tensor memory goes back to the MMA warp at once
             float vmax = 0.f;
             float v[128];
             const int cbase = chalf * (CG_BN / 2);
@@ -296,58 +335,36 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cg_u32(&s_tempty)) : "memory");
-            if (do_prof && tid == 64 && it < 2) a.prof[13 + it] = clock64();
-            // Phase B: hi / lo split and stores, one 32 x 16 sub-block at a time through the warp's staging slot
+            if (do_prof && tid == 256 && it < 2) a.prof[13 + it] = clock64();
+            // Phase B: stores, one 32 x 16 sub-block at a time through the warp's two staging slots
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const int cc = cbase + g * 16;
                 if (j0 + cc >= S || (a.mode & 4)) continue;  // warp-uniform
-                if (a.final_sum) {
-                    float* o = a.out + (size_t)po * SS + (size_t)row * S + j0 + cc;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[g * 16 + 4 * q], v[g * 16 + 4 * q + 1], v[g * 16 + 4 * q + 2], v[g * 16 + 4 * q + 3]);
-                    continue;
-                }
-                // the staging slot may still be read by the TMA stores of the previous sub-block
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                // the slot written two sub-blocks ago may still be read by its TMA store
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 __syncwarp();
+                float* sg = reinterpret_cast<float*>(stg + slot * 2048);
                 if (!transposed) {  // [32 rows][16 cols], row = lane
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float h[4], l[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            h[u] = __uint_as_float(__float_as_uint(v[g * 16 + 4 * q + u]) & 0xffffe000u);
-                            l[u] = v[g * 16 + 4 * q + u] - h[u];
-                        }
-                        *reinterpret_cast<float4*>(stg_hi + lane * 16 + 4 * q) = make_float4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<float4*>(stg_lo + lane * 16 + 4 * q) = make_float4(l[0], l[1], l[2], l[3]);
-                    }
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4*>(sg + lane * 16 + 4 * q) = make_float4(v[g * 16 + 4 * q], v[g * 16 + 4 * q + 1], v[g * 16 + 4 * q + 2], v[g * 16 + 4 * q + 3]);
                 } else {  // out^T: [16 cols][32 rows], the warp writes 32 consecutive floats per column
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const float h = __uint_as_float(__float_as_uint(v[g * 16 + q]) & 0xffffe000u);
-                        stg_hi[q * 32 + lane] = h;
-                        stg_lo[q * 32 + lane] = v[g * 16 + q] - h;
-                    }
+                    for (int q = 0; q < 16; ++q) sg[q * 32 + lane] = v[g * 16 + q];
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
-                    if (!transposed) {
-                        cg_tma_store_3d(&map_o, stg_u32, j0 + cc, i0 + q4 * 32, 2 * po);
-                        cg_tma_store_3d(&map_o, stg_u32 + 2048, j0 + cc, i0 + q4 * 32, 2 * po + 1);
-                    } else {
-                        cg_tma_store_3d(&map_ot, stg_u32, i0 + q4 * 32, j0 + cc, 2 * po);
-                        cg_tma_store_3d(&map_ot, stg_u32 + 2048, i0 + q4 * 32, j0 + cc, 2 * po + 1);
-                    }
+                    if (!transposed) cg_tma_store_3d(&map_o, stg_u32 + slot * 2048, j0 + cc, i0 + q4 * 32, po);
+                    else cg_tma_store_3d(&map_ot, stg_u32 + slot * 2048, i0 + q4 * 32, j0 + cc, po);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+                slot ^= 1;
             }
             vmax = warp_max(vmax);
             if (lane == 0 && vmax > 0.f) atomicMax(a.zmax_out + po, __float_as_uint(vmax));
-            if (do_prof && tid == 64 && it < 2) a.prof[9 + 2 * it] = clock64();
+            if (do_prof && tid == 256 && it < 2) a.prof[9 + 2 * it] = clock64();
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -358,52 +375,25 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------ leaf preparation and conversions
-// base_hi/lo: planes of a matrix M [S][S]; out[e] planes = M[r][c] * w[e][row_scale ? r : c] split into hi / lo, w = exp(obs - shift).
-// Used for: N_t^T[j][k] = P^T[j][k] e_t[k] (right operand of a leaf pair), single leaves P D_t (either orientation).
-__global__ void cg_scale_planes(const float* __restrict__ base, const float* __restrict__ obs, int64_t obs_stride, int S, int row_scale, float* __restrict__ out,
-                                float* __restrict__ shift_out) {
-    __shared__ float s_w[1024];
-    __shared__ float s_red[32];
-    const int64_t e = blockIdx.y;
-    const float* o = obs + e * obs_stride;
-    float m = -FLT_MAX;
-    for (int k = threadIdx.x; k < S; k += blockDim.x) m = fmaxf(m, o[k]);
-    m = warp_max(m);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
-    __syncthreads();
-    m = -FLT_MAX;
-    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m = fmaxf(m, s_red[q]);
-    if (!(m > -FLT_MAX)) m = 0.f;  // an impossible observation row stays all-zero
-    for (int k = threadIdx.x; k < S; k += blockDim.x) s_w[k] = expf(o[k] - m);
-    if (shift_out && blockIdx.x == 0 && threadIdx.x == 0) shift_out[e] = m;
-    __syncthreads();
-    const size_t SS = (size_t)S * S;
-    float* oh = out + (size_t)e * 2 * SS;
-    float* ol = oh + SS;
-    const int rows_per_block = (S + gridDim.x - 1) / gridDim.x;
-    const int r0 = blockIdx.x * rows_per_block, r1 = min(S, r0 + rows_per_block);
-    for (int idx = r0 * S + threadIdx.x * 4; idx < r1 * S; idx += blockDim.x * 4) {
-        const int r = idx / S, c = idx % S;
-        const float4 b = *reinterpret_cast<const float4*>(base + idx);
-        float4 w4;
-        if (row_scale) w4 = make_float4(s_w[r], s_w[r], s_w[r], s_w[r]);
-        else w4 = make_float4(s_w[c], s_w[c + 1], s_w[c + 2], s_w[c + 3]);
-        const float v[4] = {b.x * w4.x, b.y * w4.y, b.z * w4.z, b.w * w4.w};
-        float h[4], l[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            h[q] = __uint_as_float(__float_as_uint(v[q]) & 0xffffe000u);
-            l[q] = v[q] - h[q];
+// role (0 = left / row-major, 1 = right / transposed) of the element at index `idx` of a level with `size` elements, following the
+// carry chain of the odd leftover (sum_product.py:696-698); the final result of the tree is row-major
+__host__ __device__ static int cg_role(int64_t idx, int64_t size) {
+    while (size > 1) {
+        if (idx == size - 1 && (size & 1)) {
+            idx = size / 2;
+            size = (size + 1) / 2;
+            continue;
         }
-        *reinterpret_cast<float4*>(oh + idx) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4*>(ol + idx) = make_float4(l[0], l[1], l[2], l[3]);
+        return (int)(idx & 1);
     }
+    return 0;
 }
-// w[e][j] = exp(obs[e][j] - max_j obs[e][j]), shift[e] = that max: the column scaling of a leaf pair's second step
-__global__ void cg_obs_weights(const float* __restrict__ obs, int64_t obs_stride, int S, float* __restrict__ w, float* __restrict__ shift_out) {
+
+// w[e][j] = exp(obs[e][j] - max_j obs[e][j]), shift[e] = that max (an impossible observation row, all -inf, gives w = 0, shift = 0)
+__global__ void cg_obs_weights(const float* __restrict__ obs, int S, float* __restrict__ w, float* __restrict__ shift_out) {
     __shared__ float s_red[32];
     const int64_t e = blockIdx.x;
-    const float* o = obs + e * obs_stride;
+    const float* o = obs + e * S;
     float m = -FLT_MAX;
     for (int k = threadIdx.x; k < S; k += blockDim.x) m = fmaxf(m, o[k]);
     m = warp_max(m);
@@ -415,44 +405,49 @@ __global__ void cg_obs_weights(const float* __restrict__ obs, int64_t obs_stride
     for (int k = threadIdx.x; k < S; k += blockDim.x) w[e * S + k] = expf(o[k] - m);
     if (threadIdx.x == 0) shift_out[e] = m;
 }
-// planes of exp(A - colshift) in both orientations: P[i][j] (left operand) and P^T[j][i]; A row-major (prev, curr), entries <= 0 after the shift
-__global__ void cg_exp_planes(const float* __restrict__ A, int S, float* __restrict__ P, float* __restrict__ PT_single) {
+// P = exp(A) row-major and P^T (the shared operands of every leaf product); A row-major (prev, curr)
+__global__ void cg_exp_both(const float* __restrict__ A, int S, float* __restrict__ P, float* __restrict__ PT) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const float v = expf(A[(size_t)(r0 + rr) * S + c0 + threadIdx.x]);
+        tile[rr][threadIdx.x] = v;
+        P[(size_t)(r0 + rr) * S + c0 + threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) PT[(size_t)(c0 + rr) * S + r0 + threadIdx.x] = tile[threadIdx.x][rr];
+}
+// a single leaf M = P diag(w) in the orientation `transposed` (0: M[i][j] = P[i][j] w[j]; 1: M^T[j][i] = P^T[j][i] w[j]); state (1.0, 0)
+__global__ void cg_single_leaf(const float* __restrict__ P, const float* __restrict__ PT, const float* __restrict__ w, int S, int transposed, float* __restrict__ out,
+                               unsigned* __restrict__ zmax, int* __restrict__ E) {
     const size_t SS = (size_t)S * S;
+    const float* base = transposed ? PT : P;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < SS; idx += (size_t)gridDim.x * blockDim.x) {
-        const int i = (int)(idx / S), j = (int)(idx % S);
-        const float v = expf(A[idx]);
-        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-        P[idx] = h;
-        P[SS + idx] = v - h;
-        PT_single[(size_t)j * S + i] = v;  // one fp32 plane of P^T: the base of the right-operand leaves
+        const int r = (int)(idx / S), c = (int)(idx % S);
+        out[idx] = base[idx] * (transposed ? w[r] : w[c]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *zmax = 0x3f800000u;
+        *E = 0;
     }
 }
-// fp32 matrix (row-major) -> planes in the requested orientation (tree results re-entering a tree as elements)
-__global__ void cg_split_planes(const float* __restrict__ M, int S, const int* __restrict__ transposed, float* __restrict__ out) {
-    const int64_t e = blockIdx.y;
+// fp32 matrices (row-major) -> the orientation of their role among n elements (tree results re-entering a tree as elements)
+__global__ void cg_orient(const float* __restrict__ M, int S, int64_t n, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int64_t e = blockIdx.z;
     const size_t SS = (size_t)S * S;
+    const bool tr = cg_role(e, n) != 0;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
     const float* m = M + (size_t)e * SS;
-    float* oh = out + (size_t)e * 2 * SS;
-    float* ol = oh + SS;
-    const bool tr = transposed[e] != 0;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < SS; idx += (size_t)gridDim.x * blockDim.x) {
-        const int i = (int)(idx / S), j = (int)(idx % S);
-        const float v = tr ? m[(size_t)j * S + i] : m[idx];
-        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-        oh[idx] = h;
-        ol[idx] = v - h;
+    float* o = out + (size_t)e * SS;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) tile[rr][threadIdx.x] = m[(size_t)(r0 + rr) * S + c0 + threadIdx.x];
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        if (tr) o[(size_t)(c0 + rr) * S + r0 + threadIdx.x] = tile[threadIdx.x][rr];
+        else o[(size_t)(r0 + rr) * S + c0 + threadIdx.x] = tile[rr][threadIdx.x];
     }
 }
-// planes of one element -> planes in the other orientation (a carried leftover whose role changes)
-__global__ void cg_transpose_planes(const float* __restrict__ in, int S, float* __restrict__ out) {
-    const size_t SS = (size_t)S * S;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * SS; idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t pl = idx / SS, r = idx % SS;
-        const int i = (int)(r / S), j = (int)(r % S);
-        out[pl * SS + (size_t)j * S + i] = in[idx];
-    }
-}
-// rows[i][j] = log(M[i][j]) - log(zmax),  offset = E ln2 + log(zmax) + extra   (M = the final fp32 matrix of a tree)
+// rows[i][j] = log(M[i][j]) - log(zmax),  offset = E ln2 + log(zmax) + extra   (M = the final matrix of a tree, row-major)
 __global__ void cg_finish_rows(const float* __restrict__ M, const unsigned* __restrict__ zmax, const int* __restrict__ E, const double* __restrict__ extra, int S,
                                float* __restrict__ rows, double* __restrict__ row_offset) {
     const float zm = __uint_as_float(zmax[0]);
@@ -480,8 +475,18 @@ __global__ void cg_sum_shifts(const float* __restrict__ shift, int64_t n, double
         atomicAdd(acc, t);
     }
 }
-__global__ void cg_fill_u32(unsigned* p, int64_t n, unsigned v) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+// carry the odd leftover of every chain to the end of the next level (already in the orientation of its eventual role)
+__global__ void cg_copy_leftover(const float* __restrict__ src, const unsigned* __restrict__ zsrc, const int* __restrict__ esrc, int64_t n, int64_t nd, size_t SS,
+                                 float* __restrict__ dst, unsigned* __restrict__ zdst, int* __restrict__ edst) {
+    const int64_t ch = blockIdx.y;
+    const float* s_ = src + (size_t)(ch * n + n - 1) * SS;
+    float* d_ = dst + (size_t)(ch * nd + nd - 1) * SS;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < SS; i += (size_t)gridDim.x * blockDim.x * 4)
+        *reinterpret_cast<float4*>(d_ + i) = *reinterpret_cast<const float4*>(s_ + i);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        zdst[ch * nd + nd - 1] = zsrc ? zsrc[ch * n + n - 1] : 0x3f800000u;  // leaves: largest stored entry 1.0, E = 0
+        edst[ch * nd + nd - 1] = esrc ? esrc[ch * n + n - 1] : 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -499,19 +504,20 @@ static EncodeTiledFn cg_encode_fn() {
     }
     return fn;
 }
-// planes buffer [n][2][S][S] fp32 as a 3-D tensor (k, row, 2 n) with a (32, box_rows, 1) box and 128-byte swizzle
-static int cg_make_map(CUtensorMap* map, const float* base, int64_t n_elems, int S, int box_rows) {
+// [n][S][S] fp32 as a 3-D tensor (inner, row, element) with an (inner_box, row_box, 1) box
+static int cg_make_map(CUtensorMap* map, const float* base, int64_t n_elems, int S, int box_inner, int box_rows, bool swizzle128) {
     EncodeTiledFn enc = cg_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");
         return FB2_ERR_UNSUPPORTED;
     }
-    cuuint64_t dims[3] = {(cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)(2 * n_elems)};
+    cuuint64_t dims[3] = {(cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)n_elems};
     cuuint64_t strides[2] = {(cuuint64_t)S * 4, (cuuint64_t)S * S * 4};
-    cuuint32_t box[3] = {CG_KC, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     swizzle128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
         return FB2_ERR_CUDA;
@@ -521,60 +527,19 @@ static int cg_make_map(CUtensorMap* map, const float* base, int64_t n_elems, int
 
 bool chain_gemm_supported(int S) { return S >= 256 && S <= 1024 && S % 128 == 0 && cg_encode_fn() != nullptr; }
 
-// role (0 = left / row-major, 1 = right / transposed) of the element at index `idx` of a level with `size` elements, following the
-// carry chain of the odd leftover (sum_product.py:696-698); the final result of the tree is row-major
-__host__ __device__ static int cg_role(int64_t idx, int64_t size) {
-    while (size > 1) {
-        if (idx == size - 1 && (size & 1)) {
-            idx = size / 2;
-            size = (size + 1) / 2;
-            continue;
-        }
-        return (int)(idx & 1);
-    }
-    return 0;
-}
-
-__global__ void cg_roles_kernel(int* roles, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) roles[i] = cg_role(i, n);
-}
-
-// planes buffer [n][2][S][S] as the destination of the epilogue's TMA stores: (inner, rows) box without swizzle
-static int cg_make_store_map(CUtensorMap* map, const float* base, int64_t n_elems, int S, int box_inner, int box_rows) {
-    EncodeTiledFn enc = cg_encode_fn();
-    if (!enc) return FB2_ERR_UNSUPPORTED;
-    cuuint64_t dims[3] = {(cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)(2 * n_elems)};
-    cuuint64_t strides[2] = {(cuuint64_t)S * 4, (cuuint64_t)S * S * 4};
-    cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled (store map) failed (%d)", (int)r);
-        return FB2_ERR_CUDA;
-    }
-    return FB2_OK;
-}
-
-static int cg_launch(const float* a_planes, int64_t n_a, const float* b_planes, int64_t n_b, const ChainGemmArgs& args, int64_t pairs, cudaStream_t stream) {
+// One level.  n_a / n_b / n_o = elements behind the A / B / output base pointers.
+static int cg_launch(const float* a_base, int64_t n_a, const float* b_base, int64_t n_b, int64_t n_o, const ChainGemmArgs& args, cudaStream_t stream) {
     CUtensorMap ma, mb, mo, mot;
-    int st = cg_make_map(&ma, a_planes, n_a, args.S, CG_BM);
+    int st = cg_make_map(&ma, a_base, n_a, args.S, CG_KC, CG_BM, true);
     if (st != FB2_OK) return st;
-    st = cg_make_map(&mb, b_planes, n_b, args.S, CG_BN);
+    st = cg_make_map(&mb, b_base, n_b, args.S, CG_KC, CG_BN, true);
     if (st != FB2_OK) return st;
-    // final_sum writes one fp32 plane per product with direct stores; the maps then only need to be valid descriptors
-    const float* obase = args.final_sum ? a_planes : args.out;
-    const int64_t on = args.final_sum ? n_a : (args.ppc > 0 ? (int64_t)(pairs / args.ppc) * args.o_cs : pairs);
-    st = cg_make_store_map(&mo, obase, on, args.S, 16, 32);
+    st = cg_make_map(&mo, args.out, n_o, args.S, 16, 32, false);
     if (st != FB2_OK) return st;
-    st = cg_make_store_map(&mot, obase, on, args.S, 32, 16);
+    st = cg_make_map(&mot, args.out, n_o, args.S, 32, 16, false);
     if (st != FB2_OK) return st;
     FB2_CUDA(cudaFuncSetAttribute(chain_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_TOTAL));
     ChainGemmArgs margs = args;
-    if (margs.ppc <= 0) {  // single chain
-        margs.ppc = (int)pairs;
-        margs.a_cs = margs.b_cs = margs.o_cs = 0;
-    }
     {
         const char* m = getenv("FB2_CG_MODE");
         margs.mode = m ? atoi(m) : 0;
@@ -587,100 +552,64 @@ static int cg_launch(const float* a_planes, int64_t n_a, const float* b_planes, 
         margs.prof = d_prof;
     }
     const int tiles = (args.S / CG_BM) * ((args.S + CG_BN - 1) / CG_BN);
-    FB2_REQUIRE(pairs >= 1 && pairs <= (1 << 24), "chain_gemm: %lld products in one level", (long long)pairs);
+    FB2_REQUIRE(args.n_out >= 1 && args.ppc >= 1, "chain_gemm: empty level");
     static int sm_count = 0;
     if (!sm_count) {
         int dev = 0;
         FB2_CUDA(cudaGetDevice(&dev));
         FB2_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    const int64_t total = (int64_t)tiles * pairs;
+    const int64_t total = (int64_t)tiles * args.n_out;
     const unsigned grid = (unsigned)(total < sm_count ? total : sm_count);
-    {
-        const char* se = getenv("FB2_CG_STAGGER");
-        const long long cyc = se ? atoll(se) : (long long)(args.S / CG_KC) * 1000;  // ~ half of a tile's main loop
-        margs.stagger = (total >= 4 * (int64_t)grid) ? cyc : 0;
-    }
     chain_gemm_tc<<<grid, CG_THREADS, CG_SMEM_TOTAL, stream>>>(ma, mb, mo, mot, margs);
     FB2_LAUNCH_CHECK();
     if (margs.prof) {
         long long h[32];
         FB2_CUDA(cudaStreamSynchronize(stream));
         FB2_CUDA(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[cg prof] pairs %lld cta 0: setup %lld | tile0 first chunk +%lld, last chunk +%lld | tile1 first chunk +%lld, last chunk +%lld | "
+        fprintf(stderr, "[cg prof] products %d cta 0: setup %lld | tile0 first chunk +%lld, last chunk +%lld | tile1 first chunk +%lld, last chunk +%lld | "
                         "epilogue0 start +%lld, tensor memory released after %lld, len %lld | epilogue1 start +%lld, released after %lld, len %lld | total %lld (cycles)\n",
-                (long long)pairs, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[8] - h[0], h[13] - h[8], h[9] - h[8], h[10] - h[0],
+                args.n_out, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[8] - h[0], h[13] - h[8], h[9] - h[8], h[10] - h[0],
                 h[14] - h[10], h[11] - h[10], h[12] - h[0]);
     }
     return FB2_OK;
 }
 
-// Balanced tree (the reference's order) over `n` elements given as planes in `cur` (roles by cg_role) with scaling state
-// (zmax, E); ping-pongs between two plane buffers; writes the final product as ONE fp32 matrix + its (zmax, E).
+// Balanced tree (the reference's order) over `chains` independent chains of `n` elements each, laid out [chains][n][S][S] in `src`
+// (element roles by cg_role), scaling state (zsrc, esrc) or nullptr for leaves.  Ping-pongs between buf[0] / buf[1]
+// (>= chains * ceil(n/2) and chains * ceil(n/4) elements); the final products land row-major in final_out[chains][S][S].
 struct CgTreeBuffers {
-    float* planes[2];     // each >= ceil(n/2) elements of 2 S^2 floats
-    unsigned* zmax[2];    // each >= n
+    float* buf[2];
+    unsigned* zmax[2];  // each >= chains * ceil(n/2)
     int* E[2];
 };
-static int cg_tree(const float* first_a, int64_t first_na, int first_a_shared, const float* first_b, int64_t first_nb, const float* first_colscale,
-                   int64_t n_pairs_first, const float* odd_leaf /*planes of a leftover leaf, role-correct, or nullptr*/, int S, const CgTreeBuffers& buf,
-                   float* final_out, unsigned* final_zmax, int* final_E, float comp, cudaStream_t stream) {
-    // level 0 -> 1: n_pairs_first products (A from first_a, B from first_b), optional leftover leaf appended
-    int64_t n = n_pairs_first + (odd_leaf ? 1 : 0);  // elements at the level being produced
-    const size_t SS2 = (size_t)2 * S * S;
+static int cg_tree(const float* src, const unsigned* zsrc, const int* esrc, int64_t chains, int64_t n, int S, const CgTreeBuffers& tb, float* final_out,
+                   unsigned* final_zmax, int* final_E, float comp, cudaStream_t stream) {
+    const size_t SS = (size_t)S * S;
     int which = 0;
-    {
-        ChainGemmArgs a{};
-        a.S = S; a.comp = comp;
-        a.a_shared = first_a_shared; a.a_stride = first_a_shared ? 0 : 1; a.a_off = 0; a.b_stride = 1; a.b_off = 0;
-        a.colscale = first_colscale;
-        a.n_out = (int)n_pairs_first;
-        const bool is_final = n == 1;
-        a.final_sum = is_final;
-        a.out = is_final ? final_out : buf.planes[which];
-        a.zmax_out = is_final ? final_zmax : buf.zmax[which];
-        a.E_out = is_final ? final_E : buf.E[which];
-        a.last_transposed = cg_role(n_pairs_first - 1, n);
-        FB2_CUDA(cudaMemsetAsync(a.zmax_out, 0, (size_t)n * sizeof(unsigned), stream));
-        int st = cg_launch(first_a, first_na, first_b, first_nb, a, n_pairs_first, stream);
-        if (st != FB2_OK) return st;
-        if (odd_leaf) {  // append the leftover leaf (already in its role's orientation; stored <= 1, E = 0)
-            FB2_CUDA(cudaMemcpyAsync(buf.planes[which] + (size_t)n_pairs_first * SS2, odd_leaf, SS2 * 4, cudaMemcpyDeviceToDevice, stream));
-            cg_fill_u32<<<1, 32, 0, stream>>>(buf.zmax[which] + n_pairs_first, 1, 0x3f800000u);  // bits of 1.0f
-            FB2_LAUNCH_CHECK();
-            FB2_CUDA(cudaMemsetAsync(buf.E[which] + n_pairs_first, 0, sizeof(int), stream));
-        }
-        if (is_final) return FB2_OK;
-    }
     while (n > 1) {
         const int64_t pairs = n / 2, nd = (n + 1) / 2;
-        const bool odd = n & 1;
-        const int src = which, dst = which ^ 1;
+        const bool is_final = nd == 1;
         ChainGemmArgs a{};
         a.S = S; a.comp = comp;
-        a.a_shared = 0; a.a_stride = 2; a.a_off = 0; a.b_stride = 2; a.b_off = 1;
-        a.zmax_a = buf.zmax[src]; a.E_a = buf.E[src]; a.zmax_b = buf.zmax[src]; a.E_b = buf.E[src];
-        a.n_out = (int)pairs;
-        const bool is_final = nd == 1;
-        a.final_sum = is_final;
-        a.out = is_final ? final_out : buf.planes[dst];
-        a.zmax_out = is_final ? final_zmax : buf.zmax[dst];
-        a.E_out = is_final ? final_E : buf.E[dst];
+        a.a_stride = 2; a.a_off = 0; a.b_stride = 2; a.b_off = 1;
+        a.zmax_a = zsrc; a.E_a = esrc; a.zmax_b = zsrc; a.E_b = esrc;
+        a.ppc = (int)pairs; a.a_cs = (int)n; a.b_cs = (int)n; a.o_cs = (int)nd;
+        a.n_out = (int)(chains * pairs);
+        a.out = is_final ? final_out : tb.buf[which];
+        a.zmax_out = is_final ? final_zmax : tb.zmax[which];
+        a.E_out = is_final ? final_E : tb.E[which];
         a.last_transposed = cg_role(pairs - 1, nd);
-        FB2_CUDA(cudaMemsetAsync(a.zmax_out, 0, (size_t)nd * sizeof(unsigned), stream));
-        int st = cg_launch(buf.planes[src], n, buf.planes[src], n, a, pairs, stream);
+        FB2_CUDA(cudaMemsetAsync(a.zmax_out, 0, (size_t)chains * nd * sizeof(unsigned), stream));
+        int st = cg_launch(src, chains * n, src, chains * n, chains * nd, a, stream);
         if (st != FB2_OK) return st;
-        if (odd) {  // carry the leftover: it was stored row-major (its index was even); transpose if its eventual role is "right"
-            const float* lsrc = buf.planes[src] + (size_t)(n - 1) * SS2;
-            float* ldst = buf.planes[dst] + (size_t)pairs * SS2;
-            // the leftover's CURRENT orientation is its eventual role as computed when it was written (cg_role follows the whole carry
-            // chain), so a plain copy is correct
-            FB2_CUDA(cudaMemcpyAsync(ldst, lsrc, SS2 * 4, cudaMemcpyDeviceToDevice, stream));
-            FB2_CUDA(cudaMemcpyAsync(buf.zmax[dst] + pairs, buf.zmax[src] + (n - 1), sizeof(unsigned), cudaMemcpyDeviceToDevice, stream));
-            FB2_CUDA(cudaMemcpyAsync(buf.E[dst] + pairs, buf.E[src] + (n - 1), sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        if (n & 1) {
+            cg_copy_leftover<<<dim3(32, (unsigned)chains), 256, 0, stream>>>(src, zsrc, esrc, n, nd, SS, a.out, a.zmax_out, a.E_out);
+            FB2_LAUNCH_CHECK();
         }
+        src = a.out; zsrc = a.zmax_out; esrc = a.E_out;
         n = nd;
-        which = dst;
+        which ^= 1;
     }
     return FB2_OK;
 }
@@ -701,19 +630,15 @@ size_t hmm_chunk_summary_gemm_workspace_bytes(int64_t T, int S, int64_t block_st
     const size_t SS = (size_t)S * S;
     int64_t bs = block_steps < T ? block_steps : T;
     bs += bs & 1;
-    const int64_t pairs = bs / 2 + 2;
+    const int64_t l1 = bs / 2 + 2;  // elements after the leaf level (+ leftover leaf)
     const int64_t nblocks = cg_block_count(T, bs);
-    size_t w = 0;
-    w += align_up(2 * SS * 4) + align_up(SS * 4);                       // P planes, P^T single plane
-    w += align_up((size_t)pairs * 2 * SS * 4);                           // leaf right operands N (+ leftover leaf slot)
-    w += align_up((size_t)pairs * S * 4);                                // column weights
-    w += 2 * align_up((size_t)(bs + 2) * 4);                             // shifts
-    w += align_up((size_t)pairs * 2 * SS * 4) + align_up((size_t)(pairs / 2 + 1) * 2 * SS * 4);  // tree ping-pong
-    w += 4 * align_up((size_t)(pairs + 1) * 4);                          // zmax / E ping-pong
-    w += align_up((size_t)nblocks * SS * 4) + 3 * align_up((size_t)nblocks * 4);  // block results, zmax, E, roles
-    w += align_up((size_t)nblocks * 2 * SS * 4) + align_up((size_t)(nblocks / 2 + 1) * 2 * SS * 4);  // upper tree
-    w += 4 * align_up((size_t)(nblocks + 1) * 4);
-    w += align_up(SS * 4) + 3 * 256;                                     // final matrix, zmax, E, offset accumulator
+    size_t w = 2 * align_up(SS * 4);                                                 // P, P^T
+    w += align_up((size_t)(bs + 2) * S * 4) + align_up((size_t)(bs + 2) * 4);        // observation weights, shifts
+    w += align_up((size_t)l1 * SS * 4) + align_up((size_t)(l1 / 2 + 1) * SS * 4) + align_up((size_t)(l1 / 4 + 2) * SS * 4);  // leaf outputs + ping-pong
+    w += 6 * align_up((size_t)(l1 + 1) * 4);
+    w += 2 * align_up((size_t)nblocks * SS * 4) + align_up((size_t)(nblocks / 2 + 1) * SS * 4) + align_up((size_t)(nblocks / 4 + 2) * SS * 4);
+    w += 6 * align_up((size_t)(nblocks + 1) * 4);
+    w += align_up(SS * 4) + 3 * 256;
     return w + 4096;
 }
 
@@ -724,29 +649,30 @@ int hmm_chunk_summary_gemm_device(const float* A, const float* obs, int64_t T, i
     const size_t SS = (size_t)S * S;
     int64_t bs = block_steps < T ? block_steps : T;
     bs += bs & 1;
-    FB2_REQUIRE(bs >= 2 && bs <= 131068, "hmm_chunk_summary (gemm): block of %lld steps outside [2, 131068]", (long long)bs);
-    const int64_t max_pairs = bs / 2 + 2;
+    FB2_REQUIRE(bs >= 2 && bs <= (1 << 22), "hmm_chunk_summary (gemm): block of %lld steps out of range", (long long)bs);
+    const int64_t l1 = bs / 2 + 2;
     const int64_t nblocks = cg_block_count(T, bs);
     Arena ar(workspace, workspace_bytes);
-    float* P = ar.take<float>(2 * SS);
+    float* P = ar.take<float>(SS);
     float* PT = ar.take<float>(SS);
-    float* N = ar.take<float>((size_t)max_pairs * 2 * SS);
-    float* W = ar.take<float>((size_t)max_pairs * S);
-    float* shiftN = ar.take<float>((size_t)bs + 2);
-    float* shiftW = ar.take<float>((size_t)bs + 2);
+    float* W = ar.take<float>((size_t)(bs + 2) * S);
+    float* shift = ar.take<float>((size_t)bs + 2);
+    float* L1 = ar.take<float>((size_t)l1 * SS);
     CgTreeBuffers tb{}, ub{};
-    tb.planes[0] = ar.take<float>((size_t)max_pairs * 2 * SS);
-    tb.planes[1] = ar.take<float>((size_t)(max_pairs / 2 + 1) * 2 * SS);
+    tb.buf[0] = ar.take<float>((size_t)(l1 / 2 + 1) * SS);
+    tb.buf[1] = ar.take<float>((size_t)(l1 / 4 + 2) * SS);
+    unsigned* z1 = ar.take<unsigned>((size_t)l1 + 1);
+    int* e1 = ar.take<int>((size_t)l1 + 1);
     for (int q = 0; q < 2; ++q) {
-        tb.zmax[q] = ar.take<unsigned>((size_t)max_pairs + 1);
-        tb.E[q] = ar.take<int>((size_t)max_pairs + 1);
+        tb.zmax[q] = ar.take<unsigned>((size_t)l1 + 1);
+        tb.E[q] = ar.take<int>((size_t)l1 + 1);
     }
     float* blockM = ar.take<float>((size_t)nblocks * SS);
-    unsigned* block_zmax = ar.take<unsigned>((size_t)nblocks);
-    int* block_E = ar.take<int>((size_t)nblocks);
-    int* block_role = ar.take<int>((size_t)nblocks);
-    ub.planes[0] = ar.take<float>((size_t)nblocks * 2 * SS);
-    ub.planes[1] = ar.take<float>((size_t)(nblocks / 2 + 1) * 2 * SS);
+    float* blockO = ar.take<float>((size_t)nblocks * SS);
+    ub.buf[0] = ar.take<float>((size_t)(nblocks / 2 + 1) * SS);
+    ub.buf[1] = ar.take<float>((size_t)(nblocks / 4 + 2) * SS);
+    unsigned* block_zmax = ar.take<unsigned>((size_t)nblocks + 1);
+    int* block_E = ar.take<int>((size_t)nblocks + 1);
     for (int q = 0; q < 2; ++q) {
         ub.zmax[q] = ar.take<unsigned>((size_t)nblocks + 1);
         ub.E[q] = ar.take<int>((size_t)nblocks + 1);
@@ -761,7 +687,7 @@ int hmm_chunk_summary_gemm_device(const float* A, const float* obs, int64_t T, i
     }
     const float comp = 5.82e-8f;
     FB2_CUDA(cudaMemsetAsync(shift_acc, 0, sizeof(double), stream));
-    cg_exp_planes<<<296, 256, 0, stream>>>(A, S, P, PT);
+    cg_exp_both<<<dim3((unsigned)(S / 32), (unsigned)(S / 32)), dim3(32, 8), 0, stream>>>(A, S, P, PT);
     FB2_LAUNCH_CHECK();
     int64_t t0 = 0;
     for (int64_t b = 0; b < nblocks; ++b) {
@@ -769,78 +695,49 @@ int hmm_chunk_summary_gemm_device(const float* A, const float* obs, int64_t T, i
         if (T - (t0 + nt) == 1) nt += 1;
         const int64_t pairs = nt / 2;
         const bool odd = nt & 1;
-        const float* ob = obs + t0 * S;
         float* dstM = nblocks == 1 ? finalM : blockM + (size_t)b * SS;
         unsigned* dstZ = nblocks == 1 ? final_zmax : block_zmax + b;
         int* dstE = nblocks == 1 ? final_E : block_E + b;
-        // right operands of the leaf pairs: N_p^T[j][k] = P^T[j][k] * e_{2p}[k]  (column scaling of P^T), one element per pair
-        cg_scale_planes<<<dim3(8, (unsigned)pairs), 256, 0, stream>>>(PT, ob, 2 * (int64_t)S, S, 0, N, shiftN);
+        // observation weights of every step of the block: w_t = exp(obs_t - max obs_t)
+        cg_obs_weights<<<(unsigned)nt, 128, 0, stream>>>(obs + t0 * S, S, W, shift);
         FB2_LAUNCH_CHECK();
-        // column weights of the second step of every pair (applied in the epilogue of the leaf products)
-        cg_obs_weights<<<(unsigned)pairs, 128, 0, stream>>>(ob + S, 2 * (int64_t)S, S, W, shiftW);
+        cg_sum_shifts<<<32, 256, 0, stream>>>(shift, nt, shift_acc);
         FB2_LAUNCH_CHECK();
-        cg_sum_shifts<<<32, 256, 0, stream>>>(shiftN, pairs, shift_acc);
-        FB2_LAUNCH_CHECK();
-        cg_sum_shifts<<<32, 256, 0, stream>>>(shiftW, pairs, shift_acc);
-        FB2_LAUNCH_CHECK();
-        const float* odd_leaf = nullptr;
-        if (odd) {
-            // the last step of an odd block is a leaf of its own, M = P D_t, stored in the orientation of its eventual role.
-            // Row scaling of P^T gives M^T (the "right operand" orientation); the "left operand" orientation is its transpose.
-            const int role = cg_role(pairs, pairs + 1);
-            float* leaf = N + (size_t)pairs * 2 * SS;  // spare slot behind the pair operands
-            cg_scale_planes<<<dim3(8, 1), 256, 0, stream>>>(PT, ob + (nt - 1) * S, S, S, 1, leaf, shiftN + pairs);
-            FB2_LAUNCH_CHECK();
-            cg_sum_shifts<<<1, 32, 0, stream>>>(shiftN + pairs, 1, shift_acc);
-            FB2_LAUNCH_CHECK();
-            if (role == 0) {
-                float* tmp = tb.planes[1];  // not in use before the tree starts
-                cg_transpose_planes<<<296, 256, 0, stream>>>(leaf, S, tmp);
-                FB2_LAUNCH_CHECK();
-                FB2_CUDA(cudaMemcpyAsync(leaf, tmp, 2 * SS * 4, cudaMemcpyDeviceToDevice, stream));
-            }
-            odd_leaf = leaf;
+        // leaf level: product p = P diag(w_{2p}) P diag(w_{2p+1}): A = P scaled along K in shared memory, B = P^T, columns scaled in the epilogue
+        const int64_t n1 = pairs + (odd ? 1 : 0);
+        const bool leaf_final = n1 == 1;
+        {
+            ChainGemmArgs a{};
+            a.S = S; a.comp = comp;
+            a.a_shared = 1; a.b_stride = 0; a.b_off = 0;  // A = P, B = P^T for every product
+            a.kscale = W; a.colscale = W + S; a.scale_stride = 2 * (int64_t)S;  // rows 2p and 2p + 1 of W
+            a.ppc = (int)pairs; a.a_cs = 0; a.b_cs = 0; a.o_cs = (int)n1;
+            a.n_out = (int)pairs;
+            a.out = leaf_final ? dstM : L1;
+            a.zmax_out = leaf_final ? dstZ : z1;
+            a.E_out = leaf_final ? dstE : e1;
+            a.last_transposed = cg_role(pairs - 1, n1);
+            FB2_CUDA(cudaMemsetAsync(a.zmax_out, 0, (size_t)n1 * sizeof(unsigned), stream));
+            int st = cg_launch(P, 1, PT, 1, n1, a, stream);
+            if (st != FB2_OK) return st;
         }
-        int st = cg_tree(P, 1, 1, N, pairs + (odd ? 1 : 0), W, pairs, odd_leaf, S, tb, dstM, dstZ, dstE, comp, stream);
-        if (st != FB2_OK) return st;
+        if (odd) {
+            // the last step of an odd block is a leaf of its own, M = P D_t, in the orientation of its eventual role
+            cg_single_leaf<<<296, 256, 0, stream>>>(P, PT, W + (size_t)(nt - 1) * S, S, cg_role(pairs, n1), L1 + (size_t)pairs * SS, z1 + pairs, e1 + pairs);
+            FB2_LAUNCH_CHECK();
+        }
+        if (!leaf_final) {
+            int st = cg_tree(L1, z1, e1, 1, n1, S, tb, dstM, dstZ, dstE, comp, stream);
+            if (st != FB2_OK) return st;
+        }
         t0 += nt;
     }
     if (nblocks > 1) {
-        // the block results re-enter a tree as elements: split into planes in the orientation of their role
-        cg_roles_kernel<<<1, 256, 0, stream>>>(block_role, nblocks);
+        // the block results re-enter a tree as elements, in the orientation of their role
+        cg_orient<<<dim3((unsigned)(S / 32), (unsigned)(S / 32), (unsigned)nblocks), dim3(32, 8), 0, stream>>>(blockM, S, nblocks, blockO);
         FB2_LAUNCH_CHECK();
-        cg_split_planes<<<dim3(64, (unsigned)nblocks), 256, 0, stream>>>(blockM, S, block_role, ub.planes[0]);
-        FB2_LAUNCH_CHECK();
-        FB2_CUDA(cudaMemcpyAsync(ub.zmax[0], block_zmax, (size_t)nblocks * sizeof(unsigned), cudaMemcpyDeviceToDevice, stream));
-        FB2_CUDA(cudaMemcpyAsync(ub.E[0], block_E, (size_t)nblocks * sizeof(int), cudaMemcpyDeviceToDevice, stream));
-        int64_t n = nblocks;
-        int which = 0;
-        const size_t SS2 = 2 * SS;
-        while (n > 1) {
-            const int64_t pairs = n / 2, nd = (n + 1) / 2;
-            const int src = which, dst = which ^ 1;
-            ChainGemmArgs a{};
-            a.S = S; a.comp = comp;
-            a.a_stride = 2; a.a_off = 0; a.b_stride = 2; a.b_off = 1;
-            a.zmax_a = ub.zmax[src]; a.E_a = ub.E[src]; a.zmax_b = ub.zmax[src]; a.E_b = ub.E[src];
-            a.n_out = (int)pairs;
-            const bool is_final = nd == 1;
-            a.final_sum = is_final;
-            a.out = is_final ? finalM : ub.planes[dst];
-            a.zmax_out = is_final ? final_zmax : ub.zmax[dst];
-            a.E_out = is_final ? final_E : ub.E[dst];
-            a.last_transposed = cg_role(pairs - 1, nd);
-            FB2_CUDA(cudaMemsetAsync(a.zmax_out, 0, (size_t)nd * sizeof(unsigned), stream));
-            int st = cg_launch(ub.planes[src], n, ub.planes[src], n, a, pairs, stream);
-            if (st != FB2_OK) return st;
-            if (n & 1) {
-                FB2_CUDA(cudaMemcpyAsync(ub.planes[dst] + (size_t)pairs * SS2, ub.planes[src] + (size_t)(n - 1) * SS2, SS2 * 4, cudaMemcpyDeviceToDevice, stream));
-                FB2_CUDA(cudaMemcpyAsync(ub.zmax[dst] + pairs, ub.zmax[src] + (n - 1), sizeof(unsigned), cudaMemcpyDeviceToDevice, stream));
-                FB2_CUDA(cudaMemcpyAsync(ub.E[dst] + pairs, ub.E[src] + (n - 1), sizeof(int), cudaMemcpyDeviceToDevice, stream));
-            }
-            n = nd;
-            which = dst;
-        }
+        int st = cg_tree(blockO, block_zmax, block_E, 1, nblocks, S, ub, finalM, final_zmax, final_E, comp, stream);
+        if (st != FB2_OK) return st;
     }
     cg_finish_rows<<<296, 256, 0, stream>>>(finalM, final_zmax, final_E, shift_acc, S, rows_out, row_offset);
     FB2_LAUNCH_CHECK();
@@ -869,8 +766,8 @@ __global__ void cg_elem_max(const float* __restrict__ x, int64_t SS, float* __re
         shift[blockIdx.x] = t > -FLT_MAX ? t : 0.f;  // an all -inf element stays all zero
     }
 }
-// planes[e] = hi / lo split of exp(x[e] - shift[e]) in the orientation of element e's role in its chain of T elements
-__global__ void cg_exp_split_tiles(const float* __restrict__ x, const float* __restrict__ shift, int S, int64_t T, float* __restrict__ planes) {
+// leaves[e] = exp(x[e] - shift[e]) in the orientation of element e's role in its chain of T elements
+__global__ void cg_exp_orient(const float* __restrict__ x, const float* __restrict__ shift, int S, int64_t T, float* __restrict__ leaves) {
     __shared__ float tile[32][33];
     const int64_t e = blockIdx.z;
     const size_t SS = (size_t)S * S;
@@ -878,28 +775,12 @@ __global__ void cg_exp_split_tiles(const float* __restrict__ x, const float* __r
     const float sh = shift[e];
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
     const float* xe = x + e * SS;
+    float* o = leaves + e * SS;
     for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) tile[rr][threadIdx.x] = expf(xe[(size_t)(r0 + rr) * S + c0 + threadIdx.x] - sh);
     __syncthreads();
-    float* oh = planes + e * 2 * SS;
-    float* ol = oh + SS;
     for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
-        const float v = tr ? tile[threadIdx.x][rr] : tile[rr][threadIdx.x];
-        const size_t o = tr ? (size_t)(c0 + rr) * S + r0 + threadIdx.x : (size_t)(r0 + rr) * S + c0 + threadIdx.x;
-        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-        oh[o] = h;
-        ol[o] = v - h;
-    }
-}
-__global__ void cg_copy_leftover(const float* __restrict__ src, const unsigned* __restrict__ zsrc, const int* __restrict__ esrc, int64_t n, int64_t nd, size_t SS2,
-                                 float* __restrict__ dst, unsigned* __restrict__ zdst, int* __restrict__ edst, int first_level) {
-    const int64_t ch = blockIdx.y;
-    const float* s_ = src + (size_t)(ch * n + n - 1) * SS2;
-    float* d_ = dst + (size_t)(ch * nd + nd - 1) * SS2;
-    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < SS2; i += (size_t)gridDim.x * blockDim.x * 4)
-        *reinterpret_cast<float4*>(d_ + i) = *reinterpret_cast<const float4*>(s_ + i);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        zdst[ch * nd + nd - 1] = first_level ? 0x3f800000u : zsrc[ch * n + n - 1];
-        edst[ch * nd + nd - 1] = first_level ? 0 : esrc[ch * n + n - 1];
+        if (tr) o[(size_t)(c0 + rr) * S + r0 + threadIdx.x] = tile[threadIdx.x][rr];
+        else o[(size_t)(r0 + rr) * S + c0 + threadIdx.x] = tile[rr][threadIdx.x];
     }
 }
 // out[b] = log(M[b]) + E[b] ln2 + sum_t shift[b,t]
@@ -922,79 +803,42 @@ __global__ void cg_finish_dense(const float* __restrict__ M, const int* __restri
 size_t chain_product_gemm_workspace_bytes(int64_t B, int64_t T, int S) {
     const size_t SS = (size_t)S * S;
     const int64_t t1 = (T + 1) / 2, t2 = (t1 + 1) / 2;
-    return align_up((size_t)B * T * 2 * SS * 4) + align_up((size_t)B * t1 * 2 * SS * 4) + align_up((size_t)B * t2 * 2 * SS * 4) + align_up((size_t)B * SS * 4) +
-           align_up((size_t)B * T * 4) + 4 * align_up((size_t)B * (t1 + 1) * 4) + 4096;
+    return align_up((size_t)B * T * SS * 4) + align_up((size_t)B * t1 * SS * 4) + align_up((size_t)B * t2 * SS * 4) + align_up((size_t)B * SS * 4) +
+           align_up((size_t)B * T * 4) + 4 * align_up((size_t)B * (t1 + 1) * 4) + 2 * align_up((size_t)B * 4) + 4096;
 }
 
 int chain_product_gemm_device(const float* trans, int64_t B, int64_t T, int S, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (!chain_gemm_supported(S) || T < 2 || B < 1) return FB2_ERR_UNSUPPORTED;
-    const size_t SS = (size_t)S * S, SS2 = 2 * SS;
+    const size_t SS = (size_t)S * S;
     const int64_t t1 = (T + 1) / 2, t2 = (t1 + 1) / 2;
-    if (B * T > (1 << 22)) return FB2_ERR_UNSUPPORTED;
+    if (B * T > (1 << 22) || T > 65535) return FB2_ERR_UNSUPPORTED;
     Arena ar(workspace, workspace_bytes);
-    float* leaves = ar.take<float>((size_t)B * T * SS2);
-    float* buf[2] = {ar.take<float>((size_t)B * t1 * SS2), ar.take<float>((size_t)B * t2 * SS2)};
+    float* leaves = ar.take<float>((size_t)B * T * SS);
+    CgTreeBuffers tb{};
+    tb.buf[0] = ar.take<float>((size_t)B * t1 * SS);
+    tb.buf[1] = ar.take<float>((size_t)B * t2 * SS);
     float* finalM = ar.take<float>((size_t)B * SS);
     float* shift = ar.take<float>((size_t)B * T);
-    unsigned* zm[2];
-    int* Ex[2];
     for (int q = 0; q < 2; ++q) {
-        zm[q] = ar.take<unsigned>((size_t)B * (t1 + 1));
-        Ex[q] = ar.take<int>((size_t)B * (t1 + 1));
+        tb.zmax[q] = ar.take<unsigned>((size_t)B * (t1 + 1));
+        tb.E[q] = ar.take<int>((size_t)B * (t1 + 1));
     }
+    unsigned* final_zmax = ar.take<unsigned>((size_t)B);
+    int* final_E = ar.take<int>((size_t)B);
     if (!ar.ok()) return FB2_ERR_UNSUPPORTED;  // the caller falls back to the level-by-level log-domain kernels
     cg_elem_max<<<(unsigned)(B * T), 256, 0, stream>>>(trans, (int64_t)SS, shift);
     FB2_LAUNCH_CHECK();
-    {
-        int64_t done = 0;
-        while (done < B * T) {  // grid.z limit
-            const int64_t nz = B * T - done < 65535 ? B * T - done : 65535;
-            FB2_REQUIRE(done % T == 0 || nz == B * T - done || true, "unreachable");
-            // roles depend on e % T, so offsetting the element pointer by `done` needs the same offset inside the kernel: pass via pointer arithmetic
-            // only when `done` is a multiple of T; otherwise launch per chain
-            if (done % T != 0) return FB2_ERR_UNSUPPORTED;
-            int64_t take = nz - nz % T;
-            if (take == 0) return FB2_ERR_UNSUPPORTED;  // one chain longer than 65535 elements
-            cg_exp_split_tiles<<<dim3((unsigned)(S / 32), (unsigned)(S / 32), (unsigned)take), dim3(32, 8), 0, stream>>>(trans + done * SS, shift + done, S, T,
-                                                                                                                  leaves + done * SS2);
-            FB2_LAUNCH_CHECK();
-            done += take;
-        }
+    for (int64_t b0 = 0; b0 < B;) {  // grid.z limit: whole chains per launch
+        int64_t nb = 65535 / T;
+        if (nb > B - b0) nb = B - b0;
+        cg_exp_orient<<<dim3((unsigned)(S / 32), (unsigned)(S / 32), (unsigned)(nb * T)), dim3(32, 8), 0, stream>>>(trans + b0 * T * SS, shift + b0 * T, S, T,
+                                                                                                                  leaves + b0 * T * SS);
+        FB2_LAUNCH_CHECK();
+        b0 += nb;
     }
-    const float comp = 5.82e-8f;
-    const float* src = leaves;
-    const unsigned* zsrc = nullptr;
-    const int* esrc = nullptr;
-    int64_t n = T;
-    int which = 0;
-    bool first = true;
-    while (n > 1) {
-        const int64_t pairs = n / 2, nd = (n + 1) / 2;
-        const bool is_final = nd == 1;
-        ChainGemmArgs a{};
-        a.S = S; a.comp = comp;
-        a.a_stride = 2; a.a_off = 0; a.b_stride = 2; a.b_off = 1;
-        a.zmax_a = zsrc; a.E_a = esrc; a.zmax_b = zsrc; a.E_b = esrc;
-        a.ppc = (int)pairs; a.a_cs = (int)n; a.b_cs = (int)n; a.o_cs = (int)nd;
-        a.n_out = (int)(B * pairs);
-        a.final_sum = is_final;
-        a.out = is_final ? finalM : buf[which];
-        a.zmax_out = zm[which];
-        a.E_out = Ex[which];
-        a.last_transposed = cg_role(pairs - 1, nd);
-        FB2_CUDA(cudaMemsetAsync(a.zmax_out, 0, (size_t)B * nd * sizeof(unsigned), stream));
-        int st = cg_launch(src, B * n, src, B * n, a, B * pairs, stream);
-        if (st != FB2_OK) return st;
-        if (n & 1) {
-            cg_copy_leftover<<<dim3(32, (unsigned)B), 256, 0, stream>>>(src, zsrc, esrc, n, nd, SS2, buf[which], zm[which], Ex[which], first ? 1 : 0);
-            FB2_LAUNCH_CHECK();
-        }
-        src = buf[which]; zsrc = zm[which]; esrc = Ex[which];
-        n = nd;
-        which ^= 1;
-        first = false;
-    }
-    cg_finish_dense<<<dim3(64, (unsigned)B), 256, 0, stream>>>(finalM, esrc, shift, T, SS, out);
+    int st = cg_tree(leaves, nullptr, nullptr, B, T, S, tb, finalM, final_zmax, final_E, 5.82e-8f, stream);
+    if (st != FB2_OK) return st;
+    cg_finish_dense<<<dim3(64, (unsigned)B), 256, 0, stream>>>(finalM, final_E, shift, T, SS, out);
     FB2_LAUNCH_CHECK();
     return FB2_OK;
 }
