@@ -1283,6 +1283,101 @@ __global__ void __launch_bounds__(MM_WARPS * 32) gaussian_moment_match(const flo
     if (lane == 0) co[e] = Z - n * kHalfLog2Pi - hl - 0.5f * quad;
 }
 
+
+// Chain elements of a time-homogeneous linear-Gaussian state-space model straight from the observations (GaussianHMM, pyro/hmm.py:258-270:
+// element_t = trans + obs(value = y_t); matrix_and_mvn_to_funsor pyro/convert.py:278-298; gaussian.py:723-744 for the substitution).
+// Only white_vec depends on t: w_t = [w_trans ; w_o + y_t Pr], so with u_t = w_o + y_t Pr (O values)
+//     eta_t = P w_t = a0 + Po u_t        (a0 = P[:, :D] w_trans, Po = P[:, D:], both per chain)
+//     c_t   = s - |w_t|^2 / 2 = c0 - |u_t|^2 / 2
+// One warp per time step (strided over the chain): lane o < O owns u[o], lane i owns eta[i] and eta[i + 32]; y is read once (64 B per
+// step at O = 16) and eta / c are written once, coalesced -- the [B, T, D + O] white_vec array of the reference's data flow (and the
+// torch cat / matmul / expand that built it: 6 of the 10.3 ms of BASELINE config 4) never exists.
+// One THREAD per time step for the arithmetic (Pr / Po sit in shared memory and are read as broadcast LDS.128: every lane of a warp
+// multiplies by the same matrix entry), one WARP per tile of 32 consecutive steps for the memory traffic: the tile's observations are
+// loaded coalesced into shared memory, the 32 x 2D block of results goes back through shared memory so that every global store is a
+// full 128-byte line.  (A warp-per-step version with shuffles was measured first: 6.7 ms at C4 -- a chain of ~50 dependent
+// shuffle / FMA pairs per step; this one is bound by the 1280 FMAs per step and the 330 bytes per step of traffic.)
+template <int OT, int KE_WARPS>
+__global__ void __launch_bounds__(KE_WARPS * 32) gaussian_kalman_eta(const float* __restrict__ y, const float* __restrict__ Pr, const float* __restrict__ wo,
+                                                                      const float* __restrict__ a0, const float* __restrict__ Po, const float* __restrict__ c0,
+                                                                      int64_t T, int D, int O, float* __restrict__ eta, float* __restrict__ c) {
+    __shared__ __align__(16) float sPr[OT * OT];     // [o_in][o_out]
+    __shared__ __align__(16) float sPo[64 * OT];     // [i][o], rows beyond 2D are zero
+    __shared__ float sa0[64], swo[OT];
+    __shared__ __align__(16) float sy[KE_WARPS][32 * OT];
+    __shared__ float se[KE_WARPS][32 * 65];
+    const int64_t b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = 2 * D;
+    for (int i = threadIdx.x; i < OT * OT; i += blockDim.x) {
+        const int oi = i / OT, oo = i % OT;
+        sPr[i] = (oi < O && oo < O) ? Pr[(b * O + oi) * O + oo] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 64 * OT; i += blockDim.x) {
+        const int r = i / OT, o = i % OT;
+        sPo[i] = (r < n && o < O) ? Po[(b * n + r) * O + o] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) sa0[i] = i < n ? a0[b * n + i] : 0.f;
+    for (int i = threadIdx.x; i < OT; i += blockDim.x) swo[i] = i < O ? wo[b * O + i] : 0.f;
+    __syncthreads();
+    const float cc = c0[b];
+    const float* yb = y + b * T * O;
+    float* eb = eta + b * T * n;
+    float* cb = c + b * T;
+    float* myy = sy[warp];
+    float* mye = se[warp];
+    const int64_t ntiles = (T + 31) / 32;
+    for (int64_t tile = (int64_t)blockIdx.x * KE_WARPS + warp; tile < ntiles; tile += (int64_t)gridDim.x * KE_WARPS) {
+        const int64_t t0 = tile * 32;
+        const int nt = (int)(T - t0 < 32 ? T - t0 : 32);
+        // observations of the tile: nt * O contiguous floats
+        for (int i = lane; i < 32 * OT; i += 32) {
+            const int st = i / OT, o = i % OT;
+            myy[i] = (st < nt && o < O) ? __ldg(yb + (t0 + st) * O + o) : 0.f;
+        }
+        __syncwarp();
+        float u[OT];
+#pragma unroll
+        for (int o = 0; o < OT; ++o) u[o] = swo[o];
+#pragma unroll
+        for (int oi = 0; oi < OT; ++oi) {
+            const float yv = myy[lane * OT + oi];
+#pragma unroll
+            for (int o4 = 0; o4 < OT; o4 += 4) {
+                const float4 p = *reinterpret_cast<const float4*>(&sPr[oi * OT + o4]);
+                u[o4] = fmaf(yv, p.x, u[o4]);
+                u[o4 + 1] = fmaf(yv, p.y, u[o4 + 1]);
+                u[o4 + 2] = fmaf(yv, p.z, u[o4 + 2]);
+                u[o4 + 3] = fmaf(yv, p.w, u[o4 + 3]);
+            }
+        }
+        float uu = 0.f;
+#pragma unroll
+        for (int o = 0; o < OT; ++o) uu = fmaf(u[o], u[o], uu);
+        if (lane < nt) cb[t0 + lane] = cc - 0.5f * uu;
+#pragma unroll 1
+        for (int i0 = 0; i0 < n; i0 += 8) {
+            float e[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float acc = sa0[i0 + q];
+#pragma unroll
+                for (int o4 = 0; o4 < OT; o4 += 4) {
+                    const float4 p = *reinterpret_cast<const float4*>(&sPo[(i0 + q) * OT + o4]);
+                    acc = fmaf(u[o4], p.x, fmaf(u[o4 + 1], p.y, fmaf(u[o4 + 2], p.z, fmaf(u[o4 + 3], p.w, acc))));
+                }
+                e[q] = acc;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) mye[lane * 65 + i0 + q] = e[q];
+        }
+        __syncwarp();
+        // coalesced stores: the tile's nt * n results are contiguous in global memory
+        for (int i = lane; i < nt * n; i += 32) eb[t0 * n + i] = mye[(i / n) * 65 + i % n];
+        __syncwarp();
+    }
+}
+
 }  // namespace fb2
 
 using namespace fb2;
@@ -1347,6 +1442,24 @@ extern "C" int fb2_gaussian_moment_match_f32(const float* logits, const float* L
     FB2_REQUIRE(blocks < (1ll << 31), "too many elements for one launch");
     gaussian_moment_match<<<(unsigned)blocks, MM_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(logits, Lam, eta, c, N, K, dim, scratch, Lo, eo,
                                                                                                        co, status_flag);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
+extern "C" int fb2_gaussian_kalman_eta_f32(const float* y, const float* Pr, const float* wo, const float* a0, const float* Po, const float* c0, int64_t B,
+                                           int64_t T, int32_t D, int32_t O, float* eta, float* c, void* stream) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(y && Pr && wo && a0 && Po && c0 && eta && c, "null pointer");
+    FB2_REQUIRE(D >= 1 && D <= GMAXD && O >= 1 && O <= 32, "dimensions D=%d O=%d outside [1, 32]", D, O);
+    FB2_REQUIRE(B >= 0 && B <= 65535 && T >= 1, "bad extents");
+    if (B == 0) return FB2_OK;
+    const int warps = O <= 16 ? 4 : 2;
+    int64_t blocks = ceil_div(T, (int64_t)warps * 32 * 4);  // ~4 tiles of 32 steps per warp
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    if (O <= 16) gaussian_kalman_eta<16, 4><<<dim3((unsigned)blocks, (unsigned)B), 128, 0, static_cast<cudaStream_t>(stream)>>>(y, Pr, wo, a0, Po, c0, T, D, O, eta, c);
+    else gaussian_kalman_eta<32, 2><<<dim3((unsigned)blocks, (unsigned)B), 64, 0, static_cast<cudaStream_t>(stream)>>>(y, Pr, wo, a0, Po, c0, T, D, O, eta, c);
     FB2_LAUNCH_CHECK();
     return FB2_OK;
 }

@@ -133,50 +133,22 @@ def gaussian_sequential_sum_product(Lam, eta, c, validate=True):
     return Lo, eo, co
 
 
-def kalman_elements_sqrt(F, q_loc, q_tril, H, r_loc, r_tril, y):
-    """GaussianHMM chain elements (pyro/hmm.py:258-270): trans + obs(value=y_t) in the reference's sqrt
-    form over rows (state; state'), built from time-homogeneous parameters
-    F[B,D,D], q_loc[B,D], q_tril[B,D,D], H[B,D,O], r_loc[B,O], r_tril[B,O,O], y[B,T,O]
-    following matrix_and_mvn_to_funsor (pyro/convert.py:278-298) and the observed-value substitution
-    (gaussian.py:723-744).  Small per-batch linear algebra (triangular inverses) uses torch; the T-sized
-    work is one broadcasted matmul.  Returns w[B,T,D+O], P[B,T,2D,D+O], s[B,T]."""
-    B, T, O = y.shape
-    D = F.shape[-1]
-    eyeD = torch.eye(D, device=F.device, dtype=F.dtype)
-    eyeO = torch.eye(O, device=F.device, dtype=F.dtype)
-    Pq = torch.linalg.solve_triangular(q_tril, eyeD.expand(B, D, D), upper=False).transpose(-1, -2)
-    Pr = torch.linalg.solve_triangular(r_tril, eyeO.expand(B, O, O), upper=False).transpose(-1, -2)
-    P = torch.zeros(B, T, 2 * D, D + O, device=F.device, dtype=F.dtype)
-    P[:, :, :D, :D] = (F @ Pq)[:, None]
-    P[:, :, D:, :D] = (-Pq)[:, None]
-    P[:, :, D:, D:] = (H @ Pr)[:, None]
-    w_t = -(q_loc[:, None, :] @ Pq)[:, 0]  # [B,D]
-    w_o = -(r_loc[:, None, :] @ Pr)[:, 0]  # [B,O]
-    w = torch.cat([w_t[:, None, :].expand(B, T, D), w_o[:, None, :] + y @ Pr], dim=-1)
-    s = (-0.5 * (D + O) * math.log(2 * math.pi) - q_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1)
-         - r_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1))
-    return w.contiguous(), P, s[:, None].expand(B, T).contiguous()
-
-
 def kalman_elements_homog(F, q_loc, q_tril, H, r_loc, r_tril, y):
-    """The same chain elements for time-homogeneous parameters without the T-sized prec_sqrt: only white_vec depends on
-    t (pyro/hmm.py:258-270), so P is built once per chain.  Returns w[B,T,D+O], P[B,2D,D+O], s[B,T]."""
+    """GaussianHMM chain elements (pyro/hmm.py:258-270: trans + obs(value=y_t)) in the reference's sqrt form for time-homogeneous
+    parameters, without the T-sized prec_sqrt: only white_vec depends on t, so P is built once per chain (_kalman_constants).
+    Returns w[B,T,D+O], P[B,2D,D+O], s[B,T].  (kalman_eta goes one step further and never forms w either.)"""
     B, T, O = y.shape
     D = F.shape[-1]
-    eyeD = torch.eye(D, device=F.device, dtype=F.dtype)
-    eyeO = torch.eye(O, device=F.device, dtype=F.dtype)
-    Pq = torch.linalg.solve_triangular(q_tril, eyeD.expand(B, D, D), upper=False).transpose(-1, -2)
-    Pr = torch.linalg.solve_triangular(r_tril, eyeO.expand(B, O, O), upper=False).transpose(-1, -2)
-    P = torch.zeros(B, 2 * D, D + O, device=F.device, dtype=F.dtype)
-    P[:, :D, :D] = F @ Pq
-    P[:, D:, :D] = -Pq
-    P[:, D:, D:] = H @ Pr
-    w_t = -(q_loc[:, None, :] @ Pq)[:, 0]
-    w_o = -(r_loc[:, None, :] @ Pr)[:, 0]
+    P, Pr, w_t, w_o, s = _kalman_constants(F, q_loc, q_tril, H, r_loc, r_tril)
     w = torch.cat([w_t[:, None, :].expand(B, T, D), w_o[:, None, :] + y @ Pr], dim=-1)
-    s = (-0.5 * (D + O) * math.log(2 * math.pi) - q_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1)
-         - r_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1))
     return w.contiguous(), P, s[:, None].expand(B, T).contiguous()
+
+
+def kalman_elements_sqrt(F, q_loc, q_tril, H, r_loc, r_tril, y):
+    """The same elements with the prec_sqrt materialised per step, P[B,T,2D,D+O] -- the reference's own data flow (the Gaussian sum
+    broadcasts over `time`); used by the tests of the general (time-varying) scan."""
+    w, P, s = kalman_elements_homog(F, q_loc, q_tril, H, r_loc, r_tril, y)
+    return w, P[:, None].expand(P.shape[0], y.shape[1], P.shape[1], P.shape[2]).contiguous(), s
 
 
 def kalman_elements_timevarying(F, q_loc, q_tril, H, r_loc, r_tril, y):
@@ -247,10 +219,56 @@ def gaussian_chain_homog(white_vec, prec_sqrt, scalar, validate=True):
     return Lo, eo, co
 
 
+def _kalman_constants(F, q_loc, q_tril, H, r_loc, r_tril):
+    """Per-chain constants of the GaussianHMM chain element (pyro/hmm.py:258-270; matrix_and_mvn_to_funsor pyro/convert.py:278-298):
+    prec_sqrt P[B,2D,D+O] over rows (state; state'), the observation's Pr[B,O,O] and white_vec offset wo[B,O], w_trans[B,D] and the
+    scalar s[B].  [B]-sized linear algebra in torch; nothing here depends on T."""
+    B, D = F.shape[0], F.shape[-1]
+    O = H.shape[-1]
+    eyeD = torch.eye(D, device=F.device, dtype=F.dtype)
+    eyeO = torch.eye(O, device=F.device, dtype=F.dtype)
+    Pq = torch.linalg.solve_triangular(q_tril, eyeD.expand(B, D, D), upper=False).transpose(-1, -2)
+    Pr = torch.linalg.solve_triangular(r_tril, eyeO.expand(B, O, O), upper=False).transpose(-1, -2)
+    P = torch.zeros(B, 2 * D, D + O, device=F.device, dtype=F.dtype)
+    P[:, :D, :D] = F @ Pq
+    P[:, D:, :D] = -Pq
+    P[:, D:, D:] = H @ Pr
+    w_t = -(q_loc[:, None, :] @ Pq)[:, 0]
+    w_o = -(r_loc[:, None, :] @ Pr)[:, 0]
+    s = (-0.5 * (D + O) * math.log(2 * math.pi) - q_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1)
+         - r_tril.diagonal(dim1=-1, dim2=-2).log().sum(-1))
+    return P, Pr.contiguous(), w_t, w_o.contiguous(), s
+
+
+def kalman_eta(F, q_loc, q_tril, H, r_loc, r_tril, y):
+    """Information-form chain elements of a GaussianHMM with fixed dynamics straight from the observations: (Lam[B,2D,2D] shared by all
+    steps of a chain, eta[B,T,2D], c[B,T]).  One kernel reads y once and writes eta / c once (fb2_gaussian_kalman_eta_f32)."""
+    _dev_f32(y, "y")
+    B, T, O = y.shape
+    D = F.shape[-1]
+    P, Pr, w_t, w_o, s = _kalman_constants(F, q_loc, q_tril, H, r_loc, r_tril)
+    P = P.contiguous()
+    Lam, _, _ = sqrt_to_info(torch.zeros(B, D + O, device=P.device), P)
+    a0 = (P[:, :, :D] @ w_t[:, :, None])[:, :, 0].contiguous()
+    Po = P[:, :, D:].contiguous()
+    c0 = (s - 0.5 * (w_t * w_t).sum(-1)).contiguous()
+    y = y.contiguous()
+    eta = torch.empty((B, T, 2 * D), dtype=torch.float32, device=P.device)
+    c = torch.empty((B, T), dtype=torch.float32, device=P.device)
+    lib = _lib.load()
+    with torch.cuda.device(P.device):
+        check(lib.fb2_gaussian_kalman_eta_f32(y.data_ptr(), Pr.data_ptr(), w_o.data_ptr(), a0.data_ptr(), Po.data_ptr(), c0.data_ptr(), B, T, D, O,
+                                              eta.data_ptr(), c.data_ptr(), _stream()))
+    return Lam, eta, c
+
+
 def kalman_chain(F, q_loc, q_tril, H, r_loc, r_tril, y, validate=True):
     """Parallel-scan Kalman filter for time-homogeneous parameters (examples/kalman_filter.py, GaussianHMM pyro/hmm.py:258-274):
     Returns (Lam[B,2D,2D], eta[B,2D], c[B]) over (state_{-1}; state_{T-1}), the value of the reference's MarkovProduct
     (pyro/hmm.py:269).  Time-varying elements go through kalman_elements_sqrt + sqrt_to_info + gaussian_sequential_sum_product."""
+    if F.shape[-1] <= 32 and y.shape[-1] <= 32:
+        Lam, eta, c = kalman_eta(F, q_loc, q_tril, H, r_loc, r_tril, y)
+        return gaussian_chain_info_homog(Lam, eta, c, validate=validate)
     w, P, s = kalman_elements_homog(F, q_loc, q_tril, H, r_loc, r_tril, y)
     return gaussian_chain_homog(w, P, s, validate=validate)
 

@@ -182,6 +182,12 @@ int fb2_gaussian_pair_combine_f32(const float* Lx, const float* ex, const float*
  * chain_homog  : the same scan for Lam[B,2D,2D] shared by all time steps of a chain (eta[B,T,2D], c[B,T] per step): the
  *                T-sized precision array is never materialised and level 1 reads Lam[b] for both operands.
  */
+/* kalman_eta   : the same per-step (eta, c) for a GaussianHMM with fixed dynamics, computed straight from the observations y[B,T,O]
+ *                (pyro/hmm.py:258-270 with matrix_and_mvn_to_funsor pyro/convert.py:278-298 and the value substitution gaussian.py:723-744):
+ *                u_t = wo + y_t Pr, eta_t = a0 + Po u_t, c_t = c0 - |u_t|^2 / 2, with the per-chain constants Pr[B,O,O] (obs prec_sqrt),
+ *                wo[B,O], a0[B,2D] = P[:, :D] w_trans, Po[B,2D,O] = P[:, D:], c0[B].  No [B,T,D+O] white_vec array is materialised. */
+int fb2_gaussian_kalman_eta_f32(const float* y, const float* Pr, const float* wo, const float* a0, const float* Po, const float* c0, int64_t B,
+                                int64_t T, int32_t D, int32_t O, float* eta, float* c, void* stream);
 int fb2_gaussian_eta_f32(const float* w, const float* P, const float* s, int64_t B, int64_t T, int32_t dim, int32_t rank,
                          float* eta, float* c, void* stream);
 int fb2_gaussian_chain_homog_f32(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D,
