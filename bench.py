@@ -349,6 +349,9 @@ def main():
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops"],
                 "traffic": traffic, "kernel": "hmm_flow_forward<8,2>", "kernel_ms": kernel_ms, "peak_source": peaks["src"],
                 "algorithmic_flops_per_launch": flops, "us_per_time_step": kernel_ms * 1e3 / T,
+                "latency_floor_us": 1.7, "latency_floor_source": "scripts/microbench/pingpong.cu: one store -> remote-SM load hand-over through L2 = 936 cycles "
+                "(0.48 us), DSMEM hop ~215 cycles + 17-21 B/cycle; a step of this decomposition needs one L2 hop + one DSMEM reduce + the contraction + two short "
+                "ALU chains (DESIGN.md section 3)", "achieved_over_floor": kernel_ms * 1e3 / T / 1.7,
                 "note": "T dependent steps of a [16x1024]x[1024x1024] product: latency-bound (one L2 hand-over is 936 cycles "
                         "measured, plus a DSMEM reduce per step), DESIGN.md section 3; dram traffic = algorithmic (profiles/)",
                 "hbm": {"achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
@@ -512,7 +515,7 @@ def extra_measurements(device):
     sec = timeit(lambda: fg.kalman_chain(*kargs, validate=False))
     kalman_bytes = (y.numel() + Bk * (2 * D) * (2 * D + 1) + Bk) * 4.0  # read y once, write one (Lam, eta, c) per chain
     out["kalman_scan"] = {"steps_per_s": Bk * Tk / sec, "D": D, "O": O, "B": Bk, "T": Tk, "ms": sec * 1e3,
-                          "kernel": "gaussian_homog_levels<32> (precision operators per tree level) + gaussian_homog_eta<32> (eta-only sweeps) + gaussian_eta_c<64>",
+                          "kernel": "gaussian_kalman_eta<16,4> (eta, c straight from y) + gaussian_homog_levels<32> (precision operators per tree level) + gaussian_homog_eta<32> (eta-only sweeps)",
                           "roofline": {"bound": "hbm", "achieved": kalman_bytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                        "frac": kalman_bytes / sec / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": kalman_bytes,
                                        "note": "algorithmic bytes = the observations y[B,T,O] read once + the [B] results; every intermediate "
@@ -528,12 +531,25 @@ def extra_measurements(device):
     dense_bytes = 4.0 * Bd * Td * Sd * Sd
     out["dense_chain_log"] = {"pair_products_per_s": Bd * (Td - 1) / sec, "useful_tflops": tf, "B": Bd, "T": Td, "S": Sd, "ms": sec * 1e3,
                               "units_per_s": Bd * Td * Sd * Sd / sec,
-                              "kernel": "log_matmul_tc (tcgen05 kind::tf32, 3 products per useful flop)",
+                              "kernel": "chain_gemm_tc (linear-domain tree: TMA + tcgen05 kind::tf32, 3 tensor products per useful flop, lo operand "
+                                        "formed in shared memory) + cg_elem_max / cg_exp_orient / cg_finish_dense",
                               "roofline": {"bound": "tensor", "achieved": 3 * tf, "peak": peaks_tf32(), "unit": "TFLOP/s (tf32 issued)",
                                            "frac": 3 * tf / peaks_tf32(), "peak_source": _TF32.get("how"),
                                            "hbm": {"achieved_gbs": dense_bytes / sec / 1e9, "peak_gbs": peaks["hbm_gbs"],
                                                    "frac": dense_bytes / sec / 1e9 / peaks["hbm_gbs"],
-                                                   "note": "dense input read once; the matrix-chain product is tensor-bound at S=1024 (S/2 flop per byte)"}}}
+                                                   "note": "dense input read once (algorithmic bytes); the matrix-chain product is tensor-bound at S=1024 (S/2 flop per byte)"}}}
+    # chunk summary of a time-sharded chain (the cost of breaking the dependency chain): S x S matrix-chain product of
+    # T steps of A + obs[t], linear-domain GEMM tree; this is what bounds the multi-GPU speed-up of BASELINE config 5
+    Sc, Tc = 512, 32768
+    Ac = torch.randn(Sc, Sc, device=device, generator=g).log_softmax(-1)
+    oc = torch.randn(1, Tc, Sc, device=device, generator=g)
+    sec_c = timeit(lambda: fb.hmm_chunk_summary(Ac, oc, return_offsets=True), n=2)
+    tfc = 2.0 * Sc ** 3 * (Tc - 1) / sec_c / 1e12
+    out["chunk_summary_S512"] = {"us_per_step": sec_c * 1e6 / Tc, "useful_tflops": tfc, "S": Sc, "T": Tc, "ms": sec_c * 1e3,
+                                 "kernel": "chain_gemm_tc (leaf level scales P by exp(obs) in shared memory; nothing T x S x S is materialised)",
+                                 "roofline": {"bound": "tensor", "achieved": 3 * tfc, "peak": peaks_tf32(), "unit": "TFLOP/s (tf32 issued)",
+                                              "frac": 3 * tfc / peaks_tf32(), "peak_source": _TF32.get("how")}}
+    del Ac, oc
     trans_small = trans[:4, :64].contiguous()
     del trans
     sec = timeit(lambda: fb.sequential_sum_product("max", "add", trans_small), n=1)
