@@ -5,7 +5,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfunsor_b200.so")
+LIB_PATH = os.environ.get("FB2_LIB_PATH") or os.path.join(_HERE, "lib", "libfunsor_b200.so")  # FB2_LIB_PATH: A/B builds of the same ABI
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_NO_DEVICE, ERR_NUMERIC, ERR_ABORTED = range(8)
 SEMIRING_LOG, SEMIRING_MAX = 0, 1

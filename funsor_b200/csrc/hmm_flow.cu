@@ -44,6 +44,9 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr int FLOW_PROF_CTAS = 160;
 constexpr int FLOW_OBS_DEPTH = 8;     // observation prefetch distance in steps (HBM latency << 7 steps)
 constexpr long long FLOW_SPIN_LIMIT = 2000000000ll;  // cycles (~1 s) before a wait gives up and aborts the pass
+#ifndef FLOW_EXPO_FIRST_KW
+#define FLOW_EXPO_FIRST_KW 8  // single-hop kernel: from this many fragments per warp on, spin on the exponent words first (see the fetch loop)
+#endif
 
 struct FlowArgs {
     const float* init;  // [B,S] log domain, nullable (= 0)
@@ -829,7 +832,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_direct_forward(FlowArgs p
                     // 1.58 us/step at S = 128).
                     for (;;) {
                         bool ok = true;
-                        if constexpr (KW >= 8) {
+                        if constexpr (KW >= FLOW_EXPO_FIRST_KW) {
 #pragma unroll
                             for (int ks = 0; ks < KW; ++ks)
                                 asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ew[ks]) : "l"(esrc + ks * 16) : "memory");
@@ -2027,6 +2030,9 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
     if (!tl_in_pair) flow_serialise_begin(dv, stream);
     FB2_CUDA(cudaMemsetAsync(pkt, 0xFF, (size_t)FLOW_MAX_SETS * 2 * FLOW_CHAINS * Sp * 8, stream));
     FB2_CUDA(cudaMemsetAsync(abort_flag, 0, 32, stream));
+    if (const char* fa = getenv("FB2_FLOW_FORCE_ABORT")) {  // test hook: behave as if a wait had given up (outputs NaN, sticky status raised)
+        if (fa[0] == '1') FB2_CUDA(cudaMemsetAsync(abort_flag, 1, 1, stream));
+    }
     flow_colmax<<<(unsigned)ceil_div(Sp, 128), 128, 0, stream>>>(A, S, Sp, cA, transpose);
     FB2_LAUNCH_CHECK();
     FlowArgs a{};

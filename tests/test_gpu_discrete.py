@@ -981,3 +981,64 @@ def test_generic_kernel_many_groups_wide_slices(fb, B, T, S, amode):
         zm, gamma, _ = fb.hmm_marginals(init.cuda(), A.cuda(), obs.cuda(), want_xi=False)
         rel_close(host(zm), want, rtol=RTOL, atol=1.0)
         assert np.abs(np.exp(host(gamma)).sum(-1) - 1).max() < 1e-3
+
+
+@pytest.mark.gpu
+def test_aborted_dataflow_pass_is_loud_and_recoverable(fb):
+    """A dataflow pass that gives up while running (lost co-residency, an input chunk that never landed) poisons its outputs with NaN
+    AND raises a sticky per-device status (fb2_async_status): the next dataflow launch refuses to run until the condition has been
+    read; the host-buffer entry point, which synchronises anyway, retries on the cooperative kernel.  FB2_FLOW_FORCE_ABORT=1 is the
+    test hook that makes a pass behave as if a wait had timed out."""
+    import os
+
+    from funsor_b200 import _lib
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, T, S = 2, 4096, 128
+    A = torch.randn(S, S, device="cuda", generator=g).log_softmax(-1)
+    init = torch.randn(B, S, device="cuda", generator=g).log_softmax(-1)
+    obs = torch.randn(B, T, S, device="cuda", generator=g)
+    good = fb.hmm_forward(init, A, obs)
+    torch.cuda.synchronize()
+    assert fb.async_status(raise_on_abort=False) == 0
+    os.environ["FB2_FLOW_FORCE_ABORT"] = "1"
+    try:
+        bad = fb.hmm_forward(init, A, obs)
+        torch.cuda.synchronize()
+        assert bool(torch.isnan(bad).all())
+        with pytest.raises(_lib.Fb2Aborted):  # the next dataflow launch on this device reports the pending condition ...
+            fb.hmm_forward(init, A, obs)
+        assert fb.async_status(raise_on_abort=False) == 0  # ... once; reading it cleared it
+        bad = fb.hmm_forward(init, A, obs)
+        torch.cuda.synchronize()
+        with pytest.raises(_lib.Fb2Aborted):
+            fb.async_status()
+        # host-buffer entry point: synchronises, sees the abort, recomputes on the cooperative kernel
+        lib = _lib.load()
+        h_init, h_A, h_obs = init.cpu().contiguous(), A.cpu().contiguous(), obs.cpu().contiguous()
+        h_out = torch.empty(B, dtype=torch.float32)
+        _lib.check(lib.fb2_hmm_forward_f32_host(0, h_init.data_ptr(), S, h_A.data_ptr(), 0, 0, h_obs.data_ptr(), B, T, S, h_out.data_ptr()))
+        assert torch.allclose(h_out, good.cpu(), rtol=1e-5, atol=1e-2), (h_out, good)
+    finally:
+        del os.environ["FB2_FLOW_FORCE_ABORT"]
+        fb.async_status(raise_on_abort=False)
+    again = fb.hmm_forward(init, A, obs)
+    assert torch.allclose(again, good)
+
+
+@pytest.mark.gpu
+def test_time_sharded_with_impossible_observation(fb):
+    """a step at which every state is impossible (all -inf): the reference's scan returns -inf, the re-centring of the time-sharded
+    path must not turn it into NaN (summary tree, folds, boundary offsets)"""
+    from funsor_b200 import distributed as fd
+
+    g = torch.Generator(device="cuda").manual_seed(4)
+    T, S = 64, 128
+    A = torch.randn(S, S, device="cuda", generator=g).log_softmax(-1)
+    init = torch.randn(1, S, device="cuda", generator=g).log_softmax(-1)
+    obs = torch.randn(1, T, S, device="cuda", generator=g)
+    obs[0, 17, :] = -float("inf")
+    for method in ("tree", "scan"):
+        summ = fb.hmm_chunk_summary(A, obs, return_offsets=True, method=method)
+        val, _ = fd.hmm_forward_time_sharded(init, A, obs, summary_fn=lambda a, o: summ)
+        assert float(val) == -float("inf"), (method, float(val))
