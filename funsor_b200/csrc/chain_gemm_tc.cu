@@ -45,10 +45,20 @@
 
 namespace fb2 {
 
-constexpr int CG_BM = 128, CG_BN = 256, CG_KC = 32, CG_STAGES = 2;
-constexpr int CG_A_PLANE = CG_BM * CG_KC * 4;  // 16 KB
-constexpr int CG_B_PLANE = CG_BN * CG_KC * 4;  // 32 KB
-constexpr int CG_STAGE_BYTES = 2 * CG_A_PLANE + 2 * CG_B_PLANE;  // 96 KB: [A hi | A lo | B hi | B lo]
+// K chunk per stage: 32 fp32 (one 128-byte swizzle row, 2 stages of 96 KB; default) or 16 (64-byte swizzle rows, 4 stages of 48 KB;
+// -DCG_KC_VALUE=16).  The deeper ring was built to test whether the main loop (2.3k cycles per 32-wide chunk against 1.57k of tensor
+// work) was waiting for loads: it measured the same (1.60 vs 1.55 us/step), so it is not.  What the numbers add up to is SHARED-MEMORY
+// BANDWIDTH: per chunk the tensor core reads 144 KB of operands (A 4 KB + B 8 KB per instruction, 12 instructions), the transform warps
+// read and write 48 KB each and TMA writes 48 KB: 288 KB at 128 B/cycle = 2.25k cycles.
+#ifndef CG_KC_VALUE
+#define CG_KC_VALUE 32
+#endif
+constexpr int CG_BM = 128, CG_BN = 256, CG_KC = CG_KC_VALUE, CG_STAGES = CG_KC == 32 ? 2 : 4;
+constexpr int CG_ROW_BYTES = CG_KC * 4;                        // 128 or 64: the swizzle span
+constexpr int CG_PIECES = CG_ROW_BYTES / 16;                   // 16-byte pieces per row: 8 or 4
+constexpr int CG_A_PLANE = CG_BM * CG_KC * 4;  // 16 / 8 KB
+constexpr int CG_B_PLANE = CG_BN * CG_KC * 4;  // 32 / 16 KB
+constexpr int CG_STAGE_BYTES = 2 * CG_A_PLANE + 2 * CG_B_PLANE;  // 96 / 48 KB: [A hi | A lo | B hi | B lo]
 constexpr int CG_TX_BYTES = CG_A_PLANE + CG_B_PLANE;             // what TMA brings per stage: the two raw tiles
 constexpr int CG_THREADS = 512;                                  // 4 warpgroups
 constexpr int CG_XF_WARPS = 6;                                   // transform warps 2..7
@@ -81,8 +91,9 @@ struct ChainGemmArgs {
 };
 
 __device__ __forceinline__ uint32_t cg_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t cg_desc(uint32_t addr) {  // K-major, 128-byte swizzle, 8-row groups 1024 B apart
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+__device__ __forceinline__ uint64_t cg_desc(uint32_t addr) {  // K-major; 128-byte (64-byte) swizzle, 8-row groups 1024 (512) B apart
+    constexpr uint64_t layout = CG_KC == 32 ? 2ull : 4ull;  // cute::UMMA::LayoutType SWIZZLE_128B / SWIZZLE_64B
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)((8u * CG_ROW_BYTES) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 __device__ __forceinline__ void cg_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -242,7 +253,9 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
                         // leaf level: the left operand is P diag(w): scale column k of the A tile.  The 16-byte piece at position j' of
                         // row r holds the logical k-chunk j' ^ (r % 8) of the 128-byte swizzle.
                         for (int ci = xt; ci < CG_A_PLANE / 16; ci += CG_XF_WARPS * 32) {
-                            const int r = ci >> 3, jl = (ci & 7) ^ (r & 7);
+                            // logical k-piece of the physical piece: 128-byte swizzle XORs with (row % 8), 64-byte swizzle with ((row / 2) % 4)
+                            const int r = ci / CG_PIECES;
+                            const int jl = (ci % CG_PIECES) ^ (CG_KC == 32 ? (r & 7) : ((r >> 1) & 3));
                             const float4 w = __ldg(reinterpret_cast<const float4*>(ksc + c * CG_KC + 4 * jl));
                             float4 v = *reinterpret_cast<float4*>(st + ci * 16);
                             v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w;
@@ -251,21 +264,22 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) {  // 1024 pieces over 192 threads: 5.33 rounds, all loads of the unrolled body issue first
+                        for (int i = 0; i < (CG_A_PLANE / 16 + CG_XF_WARPS * 32 - 1) / (CG_XF_WARPS * 32); ++i) {  // all loads of the unrolled body issue first
                             const int ci = xt + i * CG_XF_WARPS * 32;
                             if (ci < CG_A_PLANE / 16) *reinterpret_cast<float4*>(st + CG_A_PLANE + ci * 16) = cg_lo4(*reinterpret_cast<const float4*>(st + ci * 16));
                         }
                     }
                     unsigned char* sb = st + 2 * CG_A_PLANE;
                     {
-                        float4 vb[11];
+                        constexpr int NB = (CG_B_PLANE / 16 + CG_XF_WARPS * 32 - 1) / (CG_XF_WARPS * 32);
+                        float4 vb[NB];
 #pragma unroll
-                        for (int i = 0; i < 11; ++i) {  // 2048 pieces over 192 threads: 10.67 rounds
+                        for (int i = 0; i < NB; ++i) {
                             const int ci = xt + i * CG_XF_WARPS * 32;
                             if (ci < CG_B_PLANE / 16) vb[i] = *reinterpret_cast<const float4*>(sb + ci * 16);
                         }
 #pragma unroll
-                        for (int i = 0; i < 11; ++i) {
+                        for (int i = 0; i < NB; ++i) {
                             const int ci = xt + i * CG_XF_WARPS * 32;
                             if (ci < CG_B_PLANE / 16) *reinterpret_cast<float4*>(sb + CG_B_PLANE + ci * 16) = cg_lo4(vb[i]);
                         }
@@ -516,7 +530,7 @@ static int cg_make_map(CUtensorMap* map, const float* base, int64_t n_elems, int
     cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     swizzle128 ? (CG_KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B) : CU_TENSOR_MAP_SWIZZLE_NONE,
                      swizzle128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
