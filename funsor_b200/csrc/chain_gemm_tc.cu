@@ -388,6 +388,278 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chain_gemm_tc(const __grid_cons
     if (do_prof && tid == 32) a.prof[12] = clock64();
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// Same pipeline on a pair of CTAs (one thread-block cluster of 2 = the two SMs of a TPC) computing a 256 x 256 tile with
+// tcgen05.mma.cta_group::2: each CTA stages its 128 rows of A and HALF of B (128 of the tile's 256 columns), the leader CTA issues the
+// M = 256 instructions, each tensor core reads its own A and both halves of B, each CTA's tensor memory receives its 128 rows of the
+// result.  What it buys: the 1-CTA kernel is bound by shared-memory bandwidth (288 KB per 32-wide K chunk: see above); here a CTA moves
+// 32 KB by TMA, 64 KB through the transform warps and 96 KB into the tensor core per chunk (192 KB), and the stage shrinks to 64 KB,
+// so three stages fit.
+constexpr int CG2_STAGES = 3;
+constexpr int CG2_KC = 32;
+constexpr int CG2_A_PLANE = 128 * CG2_KC * 4;                 // 16 KB
+constexpr int CG2_B_PLANE = 128 * CG2_KC * 4;                 // 16 KB: this CTA's half of the B tile
+constexpr int CG2_STAGE_BYTES = 2 * CG2_A_PLANE + 2 * CG2_B_PLANE;  // 64 KB: [A hi | A lo | B hi | B lo]
+constexpr int CG2_TX_BYTES = CG2_A_PLANE + CG2_B_PLANE;
+constexpr int CG2_SMEM_TOTAL = 1024 + CG2_STAGES * CG2_STAGE_BYTES + CG_EPI_WARPS * CG_EPI_BYTES;
+
+__device__ __forceinline__ uint64_t cg2_desc(uint32_t addr) {  // K-major, 128-byte swizzle, 8-row groups 1024 B apart
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void cg2_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void cg2_wait_cluster(uint32_t bar, uint32_t parity) {  // arrivals may come from the peer CTA
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cg2_arrive_on_leader(uint32_t local_bar) {  // arrive on the barrier at the same offset in CTA 0 of the pair
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(local_bar));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void cg2_commit_both(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void cg2_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS, 1)
+    chain_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o,
+                   const __grid_constant__ CUtensorMap map_ot, ChainGemmArgs a) {
+    extern __shared__ unsigned char cg_smem_raw[];
+    __shared__ __align__(8) unsigned long long s_full[CG2_STAGES], s_ready[CG2_STAGES], s_empty[CG2_STAGES], s_tfull, s_tempty;
+    __shared__ uint32_t s_tmem;
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cg_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t cta_rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const bool leader = cta_rank == 0;
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int S = a.S;
+    const int tiles_n = S / 256;
+    const int tiles = (S / 256) * tiles_n;  // 256 x 256 pair-tiles per product
+    const int64_t total = (int64_t)tiles * a.n_out;
+    const int nchunks = S / CG2_KC;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < CG2_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_full[s])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cg_u32(&s_ready[s])), "n"(2 * CG_XF_WARPS) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_empty[s])) : "memory");
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cg_u32(&s_tfull)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cg_u32(&s_tempty)), "n"(2 * CG_EPI_WARPS) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ot) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cg_u32(&s_tmem)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cg2_cluster_sync();  // the peer's barriers are initialised before anybody arrives on them remotely
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    if (warp < 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;" ::: "memory");
+        if (warp == 0) {
+            // ---------------- producer (both CTAs): this CTA's 128 rows of A and its 128-column half of B
+            if (lane == 0) {
+                int64_t gc = 0;
+                for (int64_t t = cluster_id; t < total; t += nclusters) {
+                    const int p = (int)(t / tiles), tile = (int)(t % tiles);
+                    const int i0 = (tile / tiles_n) * 256 + 128 * (int)cta_rank, jb = (tile % tiles_n) * 256 + 128 * (int)cta_rank;
+                    const int ch = p / a.ppc, q = p % a.ppc;
+                    const int ia = a.a_shared ? 0 : ch * a.a_cs + a.a_stride * q + a.a_off;
+                    const int ib = ch * a.b_cs + a.b_stride * q + a.b_off;
+                    for (int c = 0; c < nchunks; ++c, ++gc) {
+                        const int s = (int)(gc % CG2_STAGES);
+                        if (gc >= CG2_STAGES) cg_wait(cg_u32(&s_empty[s]), (uint32_t)(((gc / CG2_STAGES) - 1) & 1));
+                        const uint32_t bar = cg_u32(&s_full[s]);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)CG2_TX_BYTES) : "memory");
+                        const uint32_t st = cg_u32(smem + (size_t)s * CG2_STAGE_BYTES);
+                        cg_tma_3d(st, &map_a, c * CG2_KC, i0, ia, bar);
+                        cg_tma_3d(st + 2 * CG2_A_PLANE, &map_b, c * CG2_KC, jb, ib, bar);
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ---------------- MMA issuer: the leader CTA only
+            if (leader) {
+                constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((256u >> 4) << 24);  // M = 256, N = 256
+                int64_t gc = 0;
+                int it = 0;
+                for (int64_t t = cluster_id; t < total; t += nclusters, ++it) {
+                    if (it > 0) {  // both CTAs' epilogues have read the previous tile's accumulators
+                        cg2_wait_cluster(cg_u32(&s_tempty), (uint32_t)((it - 1) & 1));
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    for (int c = 0; c < nchunks; ++c, ++gc) {
+                        const int s = (int)(gc % CG2_STAGES);
+                        cg2_wait_cluster(cg_u32(&s_ready[s]), (uint32_t)((gc / CG2_STAGES) & 1));
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (lane == 0) {
+                            const uint32_t ah = cg_u32(smem + (size_t)s * CG2_STAGE_BYTES), al = ah + CG2_A_PLANE, bh = ah + 2 * CG2_A_PLANE, bl = bh + CG2_B_PLANE;
+#pragma unroll
+                            for (int ks = 0; ks < CG2_KC / 8; ++ks) {
+                                const uint64_t dah = cg2_desc(ah + ks * 32), dal = cg2_desc(al + ks * 32);
+                                const uint64_t dbh = cg2_desc(bh + ks * 32), dbl = cg2_desc(bl + ks * 32);
+                                cg2_mma(tmem, dah, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                                cg2_mma(tmem + CG_BN, dal, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                                cg2_mma(tmem + CG_BN, dah, dbl, IDESC, 1u);
+                            }
+                            cg2_commit_both(cg_u32(&s_empty[s]));
+                            if (c == nchunks - 1) cg2_commit_both(cg_u32(&s_tfull));
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        } else {
+            // ---------------- transform (both CTAs): lo = v - trunc_tf32(v); arrive on the LEADER's ready barrier
+            const int xt = tid - 64;
+            int64_t gc = 0;
+            for (int64_t t = cluster_id; t < total; t += nclusters) {
+                const int p = (int)(t / tiles);
+                const float* ksc = a.kscale ? a.kscale + (size_t)p * a.scale_stride : nullptr;
+                for (int c = 0; c < nchunks; ++c, ++gc) {
+                    const int s = (int)(gc % CG2_STAGES);
+                    cg_wait(cg_u32(&s_full[s]), (uint32_t)((gc / CG2_STAGES) & 1));
+                    unsigned char* st = smem + (size_t)s * CG2_STAGE_BYTES;
+                    if (ksc) {
+                        for (int ci = xt; ci < CG2_A_PLANE / 16; ci += CG_XF_WARPS * 32) {
+                            const int r = ci >> 3, jl = (ci & 7) ^ (r & 7);
+                            const float4 w = __ldg(reinterpret_cast<const float4*>(ksc + c * CG2_KC + 4 * jl));
+                            float4 v = *reinterpret_cast<float4*>(st + ci * 16);
+                            v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w;
+                            *reinterpret_cast<float4*>(st + ci * 16) = v;
+                            *reinterpret_cast<float4*>(st + CG2_A_PLANE + ci * 16) = cg_lo4(v);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < (CG2_A_PLANE / 16 + CG_XF_WARPS * 32 - 1) / (CG_XF_WARPS * 32); ++i) {
+                            const int ci = xt + i * CG_XF_WARPS * 32;
+                            if (ci < CG2_A_PLANE / 16) *reinterpret_cast<float4*>(st + CG2_A_PLANE + ci * 16) = cg_lo4(*reinterpret_cast<const float4*>(st + ci * 16));
+                        }
+                    }
+                    unsigned char* sb = st + 2 * CG2_A_PLANE;
+#pragma unroll
+                    for (int i = 0; i < (CG2_B_PLANE / 16 + CG_XF_WARPS * 32 - 1) / (CG_XF_WARPS * 32); ++i) {
+                        const int ci = xt + i * CG_XF_WARPS * 32;
+                        if (ci < CG2_B_PLANE / 16) *reinterpret_cast<float4*>(sb + CG2_B_PLANE + ci * 16) = cg_lo4(*reinterpret_cast<const float4*>(sb + ci * 16));
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) cg2_arrive_on_leader(cg_u32(&s_ready[s]));
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue (both CTAs): this CTA's 128 rows x 256 columns of the pair-tile
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;" ::: "memory");
+        const int q4 = warp & 3;
+        const int chalf = (warp - 8) >> 2;
+        unsigned char* stg = smem + (size_t)CG2_STAGES * CG2_STAGE_BYTES + (size_t)(warp - 8) * CG_EPI_BYTES;
+        const uint32_t stg_u32 = cg_u32(stg);
+        const float fmain = 1.f + a.comp * (float)(nchunks * (CG2_KC / 8));
+        const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
+        int it = 0;
+        int slot = 0;
+        for (int64_t t = cluster_id; t < total; t += nclusters, ++it) {
+            const int p = (int)(t / tiles), tile = (int)(t % tiles);
+            const int i0 = (tile / tiles_n) * 256 + 128 * (int)cta_rank, j0 = (tile % tiles_n) * 256;
+            const int ch = p / a.ppc, pq = p % a.ppc;
+            const int ia = a.a_shared ? 0 : ch * a.a_cs + a.a_stride * pq + a.a_off;
+            const int ib = ch * a.b_cs + a.b_stride * pq + a.b_off;
+            const int po = ch * a.o_cs + pq;
+            const float za = a.zmax_a ? __uint_as_float(a.zmax_a[ia]) : 1.f;
+            const float zb = a.zmax_b ? __uint_as_float(a.zmax_b[ib]) : 1.f;
+            int ea = 0, eb = 0;
+            if (za > 0.f) frexpf(za, &ea);
+            if (zb > 0.f) frexpf(zb, &eb);
+            const float scale = ldexpf(1.f, -(ea + eb));
+            const bool transposed = pq == a.ppc - 1 ? a.last_transposed != 0 : (pq & 1) != 0;
+            if (tile == 0 && leader && q4 == 0 && chalf == 0 && lane == 0)
+                a.E_out[po] = (a.E_a ? a.E_a[ia] : 0) + (a.E_b ? a.E_b[ib] : 0) + ea + eb;
+            const float* cs = a.colscale ? a.colscale + (size_t)p * a.scale_stride : nullptr;
+            cg_wait(cg_u32(&s_tfull), (uint32_t)(it & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float vmax = 0.f;
+            float v[128];
+            const int cbase = chalf * 128;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const int cc = cbase + g * 16;
+                uint32_t r0[16], r1[16];
+                cg_tmem_ld16(lane_base + (uint32_t)cc, r0);
+                cg_tmem_ld16(lane_base + (uint32_t)(CG_BN + cc), r1);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    float z = fmaf(__uint_as_float(r0[q]), fmain, __uint_as_float(r1[q])) * scale;
+                    if (cs) z *= __ldg(cs + j0 + cc + q);
+                    v[g * 16 + q] = fmaxf(z, 0.f);
+                    vmax = fmaxf(vmax, v[g * 16 + q]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) cg2_arrive_on_leader(cg_u32(&s_tempty));
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const int cc = cbase + g * 16;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                float* sg = reinterpret_cast<float*>(stg + slot * 2048);
+                if (!transposed) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4*>(sg + lane * 16 + 4 * q) = make_float4(v[g * 16 + 4 * q], v[g * 16 + 4 * q + 1], v[g * 16 + 4 * q + 2], v[g * 16 + 4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) sg[q * 32 + lane] = v[g * 16 + q];
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (!transposed) cg_tma_store_3d(&map_o, stg_u32 + slot * 2048, j0 + cc, i0 + q4 * 32, po);
+                    else cg_tma_store_3d(&map_ot, stg_u32 + slot * 2048, i0 + q4 * 32, j0 + cc, po);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                slot ^= 1;
+            }
+            vmax = warp_max(vmax);
+            if (lane == 0 && vmax > 0.f) atomicMax(a.zmax_out + po, __float_as_uint(vmax));
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cg2_cluster_sync();  // neither CTA may free tensor memory or exit while the pair's instructions can still touch it
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ leaf preparation and conversions
 // role (0 = left / row-major, 1 = right / transposed) of the element at index `idx` of a level with `size` elements, following the
 // carry chain of the odd leftover (sum_product.py:696-698); the final result of the tree is row-major
@@ -574,6 +846,19 @@ static int cg_launch(const float* a_base, int64_t n_a, const float* b_base, int6
         FB2_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     const int64_t total = (int64_t)tiles * args.n_out;
+    const char* two_env = getenv("FB2_CG_2CTA");
+    const bool two = CG_KC == 32 && args.S % 256 == 0 && !(two_env && two_env[0] == '0') && margs.prof == nullptr && margs.mode == 0;
+    if (two) {
+        // CTA pairs on 256 x 256 tiles (tcgen05 cta_group::2): the B operand needs a 128-row box
+        st = cg_make_map(&mb, b_base, n_b, args.S, CG_KC, 128, true);
+        if (st != FB2_OK) return st;
+        FB2_CUDA(cudaFuncSetAttribute(chain_gemm_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, CG2_SMEM_TOTAL));
+        const int64_t total2 = (int64_t)(args.S / 256) * (args.S / 256) * args.n_out;
+        const int64_t clusters = total2 < sm_count / 2 ? total2 : sm_count / 2;
+        chain_gemm_tc2<<<(unsigned)(2 * clusters), CG_THREADS, CG2_SMEM_TOTAL, stream>>>(ma, mb, mo, mot, margs);
+        FB2_LAUNCH_CHECK();
+        return FB2_OK;
+    }
     const unsigned grid = (unsigned)(total < sm_count ? total : sm_count);
     chain_gemm_tc<<<grid, CG_THREADS, CG_SMEM_TOTAL, stream>>>(ma, mb, mo, mot, margs);
     FB2_LAUNCH_CHECK();
