@@ -372,7 +372,7 @@ def hmm_chunk_summary_tree(A, obs, sum_op="logaddexp", block_bytes=2 << 30, leaf
     return acc.contiguous(), off[:, None].expand(B, S).contiguous()
 
 
-def hmm_chunk_summary_gemm(A, obs, block_steps=4096):
+def hmm_chunk_summary_gemm(A, obs, block_steps=16384):
     """The chunk summary as a linear-domain matrix-chain product on the tensor cores (csrc/chain_gemm_tc.cu: TMA-fed 3xTF32 tcgen05
     GEMMs, hi / lo planes written by the epilogue of the level below, the reference's tree order sum_product.py:690-701 inside blocks
     of `block_steps` steps and across blocks).  Shared log-semiring A[S,S], S a multiple of 128 in [256, 1024].
