@@ -531,7 +531,7 @@ def extra_measurements(device):
     dense_bytes = 4.0 * Bd * Td * Sd * Sd
     out["dense_chain_log"] = {"pair_products_per_s": Bd * (Td - 1) / sec, "useful_tflops": tf, "B": Bd, "T": Td, "S": Sd, "ms": sec * 1e3,
                               "units_per_s": Bd * Td * Sd * Sd / sec,
-                              "kernel": "chain_gemm_tc (linear-domain tree: TMA + tcgen05 kind::tf32, 3 tensor products per useful flop, lo operand "
+                              "kernel": "chain_gemm_tc2 (linear-domain tree: TMA + tcgen05.mma cta_group::2 kind::tf32 on CTA pairs, 3 tensor products per useful flop, lo operand "
                                         "formed in shared memory) + cg_elem_max / cg_exp_orient / cg_finish_dense",
                               "roofline": {"bound": "tensor", "achieved": 3 * tf, "peak": peaks_tf32(), "unit": "TFLOP/s (tf32 issued)",
                                            "frac": 3 * tf / peaks_tf32(), "peak_source": _TF32.get("how"),
@@ -546,7 +546,7 @@ def extra_measurements(device):
     sec_c = timeit(lambda: fb.hmm_chunk_summary(Ac, oc, return_offsets=True), n=2)
     tfc = 2.0 * Sc ** 3 * (Tc - 1) / sec_c / 1e12
     out["chunk_summary_S512"] = {"us_per_step": sec_c * 1e6 / Tc, "useful_tflops": tfc, "S": Sc, "T": Tc, "ms": sec_c * 1e3,
-                                 "kernel": "chain_gemm_tc (leaf level scales P by exp(obs) in shared memory; nothing T x S x S is materialised)",
+                                 "kernel": "chain_gemm_tc2 (CTA pairs, tcgen05.mma cta_group::2; the leaf level scales P by exp(obs) in shared memory; nothing T x S x S is materialised)",
                                  "roofline": {"bound": "tensor", "achieved": 3 * tfc, "peak": peaks_tf32(), "unit": "TFLOP/s (tf32 issued)",
                                               "frac": 3 * tfc / peaks_tf32(), "peak_source": _TF32.get("how")}}
     del Ac, oc
