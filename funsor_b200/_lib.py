@@ -58,6 +58,9 @@ SIGNATURES = {
     "fb2_gaussian_moment_match_f32": (c_int, [_fp, _fp, _fp, _fp, c_int64, c_int32, c_int32, _fp, _fp, _fp, _fp, _fp, c_size_t, c_void_p]),
     "fb2_gaussian_pair_combine_f32": (c_int, [_fp, _fp, _fp, c_int64, _fp, _fp, _fp, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, _fp, _fp, _fp, _fp, c_void_p]),
     "fb2_gaussian_kalman_eta_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, c_int64, c_int64, c_int32, c_int32, _fp, _fp, c_void_p]),
+    "fb2_gaussian_kalman_constants_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, c_int64, c_int32, c_int32, _fp, _fp, _fp, _fp, _fp, _fp, c_void_p]),
+    "fb2_gaussian_kalman_chain_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
+    "fb2_gaussian_kalman_chain_f32": (c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, c_int64, c_int64, c_int32, c_int32, _fp, _fp, _fp, _fp, c_size_t, c_void_p]),
     "fb2_gaussian_eta_f32": (c_int, [_fp, _fp, _fp, c_int64, c_int64, c_int32, c_int32, _fp, _fp, c_void_p]),
     "fb2_gaussian_chain_homog_f32": (c_int, [_fp, _fp, _fp, c_int64, c_int64, c_int32, _fp, _fp, _fp, _fp, c_size_t, c_void_p]),
     "fb2_gaussian_chain_sample_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),

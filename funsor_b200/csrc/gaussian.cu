@@ -641,6 +641,7 @@ struct HomogEtaArgs {
     int64_t op_stride;  // operators per chain (= 2 NL)
     int64_t in_T, out_T, p0, count;
     int64_t leftover_src, leftover_dst;  // -1: none
+    int64_t out_p_off;  // pair p of the input range is written to output slot p + out_p_off (0 except for the remainder tile of the fused Kalman path)
     int D;
 };
 constexpr int HE_THREADS = 128;
@@ -719,7 +720,7 @@ __global__ void __launch_bounds__(HE_THREADS) gaussian_homog_eta(HomogEtaArgs a)
                 out[c + 3] = fmaf(-u.w, v, out[c + 3]);
             }
         }
-        float* eo = eout + p * n;
+        float* eo = eout + (p + a.out_p_off) * n;
         if (vec) {
 #pragma unroll
             for (int k = 0; k < DT; k += 4) {
@@ -737,7 +738,7 @@ __global__ void __launch_bounds__(HE_THREADS) gaussian_homog_eta(HomogEtaArgs a)
                 }
             }
         }
-        cout[p] = cxy + konst + 0.5f * vv;
+        cout[p + a.out_p_off] = cxy + konst + 0.5f * vv;
     }
     if (a.leftover_src >= 0 && blockIdx.x == 0 && threadIdx.x < 32) {
         const int lane = threadIdx.x;
@@ -841,7 +842,7 @@ static int homog_chain_run(const float* Lam, const float* eta, const float* c, i
         float* dc = nd == 1 ? co : lay.bc[which];
         HomogEtaArgs ea;
         ea.ein = ce; ea.cin = cc; ea.eout = de; ea.cout = dc; ea.in_T = in_T; ea.out_T = nd; ea.D = D; ea.op_stride = (int64_t)NL * 2;
-        ea.leftover_src = -1; ea.leftover_dst = -1;
+        ea.leftover_src = -1; ea.leftover_dst = -1; ea.out_p_off = 0;
         if (reg_pairs > 0) {
             ea.opU = la.opU + (size_t)(l * 2 + 0) * DT * 2 * DT;
             ea.opLinv = la.opLinv + (size_t)(l * 2 + 0) * DT * DT;
@@ -1300,7 +1301,9 @@ __global__ void __launch_bounds__(MM_WARPS * 32) gaussian_moment_match(const flo
 template <int OT, int KE_WARPS>
 __global__ void __launch_bounds__(KE_WARPS * 32) gaussian_kalman_eta(const float* __restrict__ y, const float* __restrict__ Pr, const float* __restrict__ wo,
                                                                       const float* __restrict__ a0, const float* __restrict__ Po, const float* __restrict__ c0,
-                                                                      int64_t T, int D, int O, float* __restrict__ eta, float* __restrict__ c) {
+                                                                      int64_t T, int D, int O, float* __restrict__ eta, float* __restrict__ c,
+                                                                      int64_t y_T, int64_t t_begin) {
+    // y_T = time extent of y per chain, t_begin = first step of the range; the T steps [t_begin, t_begin + T) are written to eta[B,T,2D], c[B,T]
     __shared__ __align__(16) float sPr[OT * OT];     // [o_in][o_out]
     __shared__ __align__(16) float sPo[64 * OT];     // [i][o], rows beyond 2D are zero
     __shared__ float sa0[64], swo[OT];
@@ -1321,7 +1324,7 @@ __global__ void __launch_bounds__(KE_WARPS * 32) gaussian_kalman_eta(const float
     for (int i = threadIdx.x; i < OT; i += blockDim.x) swo[i] = i < O ? wo[b * O + i] : 0.f;
     __syncthreads();
     const float cc = c0[b];
-    const float* yb = y + b * T * O;
+    const float* yb = y + (b * y_T + t_begin) * O;
     float* eb = eta + b * T * n;
     float* cb = c + b * T;
     float* myy = sy[warp];
@@ -1376,6 +1379,438 @@ __global__ void __launch_bounds__(KE_WARPS * 32) gaussian_kalman_eta(const float
         for (int i = lane; i < nt * n; i += 32) eb[t0 * n + i] = mye[(i / n) * 65 + i % n];
         __syncwarp();
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// BASELINE config 4 in one library call: GaussianHMM with fixed dynamics, from the model parameters and the observations to the chain
+// result.  Three pieces replace the [B]-sized torch linear algebra, the level-0 eta array and the first K tree levels of the eta sweep:
+//
+// gaussian_kalman_constants: one CTA per chain.  Everything of the chain element that does not depend on t (pyro/hmm.py:258-270,
+//   matrix_and_mvn_to_funsor pyro/convert.py:278-298): Pq = (q_tril^-1)', Pr = (r_tril^-1)', the prec_sqrt P = [[F Pq, 0], [-Pq, H Pr]],
+//   Lam = P P', w_trans = -q_loc Pq, wo = -r_loc Pr, a0 = P[:, :D] w_trans, Po = P[:, D:], c0 = s - |w_trans|^2 / 2.
+struct KalmanConstArgs {
+    const float *F, *q_loc, *q_tril, *H, *r_loc, *r_tril;  // [B,D,D] [B,D] [B,D,D] [B,D,O] [B,O] [B,O,O]
+    float *Lam, *Pr, *wo, *a0, *Po, *c0;                   // [B,2D,2D] [B,O,O] [B,O] [B,2D] [B,2D,O] [B]
+    int D, O;
+};
+__global__ void __launch_bounds__(256) gaussian_kalman_constants(KalmanConstArgs a) {
+    __shared__ float Xq[32][33], Xr[32][33];  // inverses of q_tril / r_tril (lower triangular)
+    __shared__ float sP[64][65];              // prec_sqrt, rows (state; state'), columns (transition noise; observation noise)
+    __shared__ float swt[32], slog[64];
+    const int64_t b = blockIdx.x;
+    const int D = a.D, O = a.O, n = 2 * D, r = D + O, tid = threadIdx.x;
+    const float* qt = a.q_tril + b * D * D;
+    const float* rt = a.r_tril + b * O * O;
+    // column j of the inverse of a lower-triangular matrix by forward substitution; thread j < D: q_tril, thread 32 + j, j < O: r_tril
+    if (tid < 64) {
+        const bool isq = tid < 32;
+        const int j = tid & 31, m = isq ? D : O;
+        const float* L = isq ? qt : rt;
+        float(*X)[33] = isq ? Xq : Xr;
+        if (j < m) {
+            for (int i = 0; i < j; ++i) X[i][j] = 0.f;
+            const float dj = L[j * m + j];
+            X[j][j] = 1.f / dj;
+            slog[tid] = logf(dj);
+            for (int i = j + 1; i < m; ++i) {
+                float acc = 0.f;
+                for (int k = j; k < i; ++k) acc = fmaf(L[i * m + k], X[k][j], acc);
+                X[i][j] = -acc / L[i * m + i];
+            }
+        } else {
+            slog[tid] = 0.f;
+        }
+    }
+    __syncthreads();
+    // P[i][j];  Pq[k][j] = Xq[j][k],  Pr[o][j] = Xr[j][o]
+    const float* F = a.F + b * D * D;
+    const float* H = a.H + b * D * O;
+    for (int idx = tid; idx < n * r; idx += blockDim.x) {
+        const int i = idx / r, j = idx % r;
+        float v = 0.f;
+        if (j < D) {
+            if (i < D) {
+                for (int k = 0; k < D; ++k) v = fmaf(F[i * D + k], Xq[j][k], v);
+            } else {
+                v = -Xq[j][i - D];
+            }
+        } else if (i >= D) {
+            const int jo = j - D;
+            for (int o = 0; o < O; ++o) v = fmaf(H[(i - D) * O + o], Xr[jo][o], v);
+        }
+        sP[i][j] = v;
+    }
+    if (tid < D) {  // w_trans[j] = -sum_k q_loc[k] Pq[k][j]
+        float v = 0.f;
+        for (int k = 0; k < D; ++k) v = fmaf(a.q_loc[b * D + k], Xq[tid][k], v);
+        swt[tid] = -v;
+    }
+    if (tid >= 32 && tid < 32 + O) {  // wo[j] = -sum_k r_loc[k] Pr[k][j]
+        const int j = tid - 32;
+        float v = 0.f;
+        for (int k = 0; k < O; ++k) v = fmaf(a.r_loc[b * O + k], Xr[j][k], v);
+        a.wo[b * O + j] = -v;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+        const int i = idx / n, j = idx % n;
+        float v = 0.f;
+        for (int k = 0; k < r; ++k) v = fmaf(sP[i][k], sP[j][k], v);
+        a.Lam[b * n * n + idx] = v;
+    }
+    for (int idx = tid; idx < n * O; idx += blockDim.x) a.Po[b * n * O + idx] = sP[idx / O][D + idx % O];
+    for (int idx = tid; idx < O * O; idx += blockDim.x) a.Pr[b * O * O + idx] = Xr[idx % O][idx / O];
+    if (tid < n) {
+        float v = 0.f;
+        for (int k = 0; k < D; ++k) v = fmaf(sP[tid][k], swt[k], v);
+        a.a0[b * n + tid] = v;
+    }
+    if (tid == 0) {
+        float sl = 0.f, ww = 0.f;
+        for (int k = 0; k < 64; ++k) sl += slog[k];
+        for (int k = 0; k < D; ++k) ww = fmaf(swt[k], swt[k], ww);
+        a.c0[b] = -(float)(D + O) * kHalfLog2Pi - sl - 0.5f * ww;
+    }
+}
+
+// gaussian_kalman_tile: the per-step elements AND the first K levels of the reference's tree (sum_product.py:690-701) for the full
+//   tiles of 2^K consecutive steps, one THREAD per tile.  Level-l element j of the tree covers the steps [j 2^l, (j+1) 2^l) (clipped
+//   at T), so an aligned tile is a complete subtree whose pairs all use the level's regular operator: the thread walks its 2^K steps
+//   in order (eta_t, c_t straight from y_t as in gaussian_kalman_eta), and folds finished subtrees like a binary counter -- after step
+//   i it combines once per trailing one-bit of i; the pending left operands (at most K) sit in a per-thread stack.  Same arithmetic,
+//   same order as gaussian_kalman_eta + gaussian_homog_eta, so the results are bit-identical to the level-by-level path, but the
+//   level-0 .. level-(K-1) eta arrays (1.6 GB + 0.8 GB + ... at BASELINE config 4) never exist: per tile y is read once (2^K O floats)
+//   and one element (2D + 1 floats) is written.  The operators of the K levels sit in shared memory as broadcast LDS.128 operands.
+struct KalmanTileArgs {
+    const float *y, *Pr, *wo, *a0, *Po, *c0;
+    const float *opU, *opLinv, *konst;  // per-level operators of gaussian_homog_levels: regular operator of level l at ((b NL + l) 2)
+    float *eout, *cout;                 // level-K arrays [B, out_T, 2D], [B, out_T]
+    int64_t T, ntiles, out_T;
+    int D, O, K, NL;
+};
+constexpr int KT_THREADS = 128;
+constexpr int KT_KMAX = 6;
+template <int DT, int OT>
+__host__ __device__ constexpr int kt_const_floats() { return OT * OT + 2 * DT * OT + 2 * DT + OT + 8; }
+template <int DT>
+__host__ __device__ constexpr int kt_level_floats() { return DT * DT + DT * 2 * DT; }
+
+template <int DT, int OT>
+__global__ void __launch_bounds__(KT_THREADS, 2) gaussian_kalman_tile(KalmanTileArgs a) {
+    extern __shared__ __align__(16) float kt_smem[];
+    float* sPr = kt_smem;                 // [o_in][o_out]
+    float* sPo = sPr + OT * OT;           // [blk * DT + k][o]: padded rows are zero
+    float* sa0 = sPo + 2 * DT * OT;
+    float* swo = sa0 + 2 * DT;
+    float* sk = swo + OT;                 // konst per level
+    float* sops = kt_smem + kt_const_floats<DT, OT>();  // per level: L^-1 [DT][DT], U [DT][2 DT]
+    const int64_t b = blockIdx.y;
+    const int D = a.D, O = a.O, n = 2 * D, K = a.K;
+    for (int i = threadIdx.x; i < OT * OT; i += KT_THREADS) {
+        const int oi = i / OT, oo = i % OT;
+        sPr[i] = (oi < O && oo < O) ? a.Pr[(b * O + oi) * O + oo] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 2 * DT * OT; i += KT_THREADS) {
+        const int row = i / OT, o = i % OT, blk = row / DT, k = row % DT;
+        sPo[i] = (k < D && o < O) ? a.Po[(b * n + blk * D + k) * O + o] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 2 * DT; i += KT_THREADS) sa0[i] = (i % DT) < D ? a.a0[b * n + (i / DT) * D + i % DT] : 0.f;
+    for (int i = threadIdx.x; i < OT; i += KT_THREADS) swo[i] = i < O ? a.wo[b * O + i] : 0.f;
+    for (int l = 0; l < K; ++l) {
+        const size_t op = ((size_t)b * a.NL + l) * 2;
+        const float4* Li = reinterpret_cast<const float4*>(a.opLinv + op * DT * DT);
+        const float4* U = reinterpret_cast<const float4*>(a.opU + op * DT * 2 * DT);
+        float4* dLi = reinterpret_cast<float4*>(sops + (size_t)l * kt_level_floats<DT>());
+        float4* dU = dLi + DT * DT / 4;
+        for (int i = threadIdx.x; i < DT * DT / 4; i += KT_THREADS) dLi[i] = __ldg(Li + i);
+        for (int i = threadIdx.x; i < DT * 2 * DT / 4; i += KT_THREADS) dU[i] = __ldg(U + i);
+        if (threadIdx.x == 0) sk[l] = a.konst[op];
+    }
+    __syncthreads();
+    const int64_t tile = (int64_t)blockIdx.x * KT_THREADS + threadIdx.x;
+    if (tile >= a.ntiles) return;
+    const float c0 = a.c0[b];
+    const float* yp = a.y + (b * a.T + (tile << K)) * O;
+    const bool yvec = (O == OT) && (reinterpret_cast<uintptr_t>(a.y) % 16 == 0);
+    float4 stk[KT_KMAX][2 * DT / 4];  // pending left operands, one per level (local memory: indexed by the run-time level)
+    float stc[KT_KMAX];
+    float cur[2 * DT], cc = 0.f;
+    float yv[OT];
+    auto load_y = [&](const float* src) {
+        if (yvec) {
+#pragma unroll
+            for (int o = 0; o < OT; o += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + o));
+                yv[o] = v.x; yv[o + 1] = v.y; yv[o + 2] = v.z; yv[o + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int o = 0; o < OT; ++o) yv[o] = o < O ? __ldg(src + o) : 0.f;
+        }
+    };
+    load_y(yp);
+    const int nsteps = 1 << K;
+#pragma unroll 1
+    for (int i = 0; i < nsteps; ++i) {
+        // ---- element of step i: u = wo + y Pr, eta = a0 + Po u, c = c0 - |u|^2 / 2
+        float u[OT];
+#pragma unroll
+        for (int o = 0; o < OT; ++o) u[o] = swo[o];
+#pragma unroll
+        for (int oi = 0; oi < OT; ++oi) {
+#pragma unroll
+            for (int o4 = 0; o4 < OT; o4 += 4) {
+                const float4 p = *reinterpret_cast<const float4*>(&sPr[oi * OT + o4]);
+                u[o4] = fmaf(yv[oi], p.x, u[o4]);
+                u[o4 + 1] = fmaf(yv[oi], p.y, u[o4 + 1]);
+                u[o4 + 2] = fmaf(yv[oi], p.z, u[o4 + 2]);
+                u[o4 + 3] = fmaf(yv[oi], p.w, u[o4 + 3]);
+            }
+        }
+        if (i + 1 < nsteps) load_y(yp + (size_t)(i + 1) * O);  // next step's observations travel while this step computes
+        float uu = 0.f;
+#pragma unroll
+        for (int o = 0; o < OT; ++o) uu = fmaf(u[o], u[o], uu);
+        cc = c0 - 0.5f * uu;
+#pragma unroll
+        for (int q = 0; q < 2 * DT; ++q) {
+            float acc = sa0[q];
+#pragma unroll
+            for (int o4 = 0; o4 < OT; o4 += 4) {
+                const float4 p = *reinterpret_cast<const float4*>(&sPo[q * OT + o4]);
+                acc = fmaf(u[o4], p.x, fmaf(u[o4 + 1], p.y, fmaf(u[o4 + 2], p.z, fmaf(u[o4 + 3], p.w, acc))));
+            }
+            cur[q] = acc;
+        }
+        // ---- fold the finished subtrees: one combine per trailing one-bit of i
+        int lvl = 0;
+#pragma unroll 1
+        for (int m = i; m & 1; m >>= 1, ++lvl) {
+            const float* sLi = sops + (size_t)lvl * kt_level_floats<DT>();
+            const float* sU = sLi + DT * DT;
+            float z[DT];
+#pragma unroll
+            for (int k4 = 0; k4 < DT / 4; ++k4) {
+                const float4 xa = stk[lvl][k4], xb = stk[lvl][DT / 4 + k4];
+                z[4 * k4] = xb.x + cur[4 * k4];
+                z[4 * k4 + 1] = xb.y + cur[4 * k4 + 1];
+                z[4 * k4 + 2] = xb.z + cur[4 * k4 + 2];
+                z[4 * k4 + 3] = xb.w + cur[4 * k4 + 3];
+                cur[4 * k4] = xa.x; cur[4 * k4 + 1] = xa.y; cur[4 * k4 + 2] = xa.z; cur[4 * k4 + 3] = xa.w;
+            }
+            const float cxy = stc[lvl] + cc;
+            float vv = 0.f;
+#pragma unroll
+            for (int r = 0; r < DT; ++r) {
+                float v = 0.f;
+#pragma unroll
+                for (int k = 0; k < DT; k += 4) {
+                    if (k <= r) {
+                        const float4 l = *reinterpret_cast<const float4*>(&sLi[r * DT + k]);
+                        v = fmaf(l.x, z[k], fmaf(l.y, z[k + 1], fmaf(l.z, z[k + 2], fmaf(l.w, z[k + 3], v))));
+                    }
+                }
+                vv = fmaf(v, v, vv);
+#pragma unroll
+                for (int c = 0; c < 2 * DT; c += 4) {
+                    const float4 uo = *reinterpret_cast<const float4*>(&sU[r * 2 * DT + c]);
+                    cur[c] = fmaf(-uo.x, v, cur[c]);
+                    cur[c + 1] = fmaf(-uo.y, v, cur[c + 1]);
+                    cur[c + 2] = fmaf(-uo.z, v, cur[c + 2]);
+                    cur[c + 3] = fmaf(-uo.w, v, cur[c + 3]);
+                }
+            }
+            cc = cxy + sk[lvl] + 0.5f * vv;
+        }
+        if (i + 1 < nsteps) {
+#pragma unroll
+            for (int k4 = 0; k4 < 2 * DT / 4; ++k4) stk[lvl][k4] = make_float4(cur[4 * k4], cur[4 * k4 + 1], cur[4 * k4 + 2], cur[4 * k4 + 3]);
+            stc[lvl] = cc;
+        }
+    }
+    float* eo = a.eout + (b * a.out_T + tile) * n;
+    if (D == DT && reinterpret_cast<uintptr_t>(a.eout) % 16 == 0) {
+#pragma unroll
+        for (int k4 = 0; k4 < 2 * DT / 4; ++k4)
+            reinterpret_cast<float4*>(eo)[k4] = make_float4(cur[4 * k4], cur[4 * k4 + 1], cur[4 * k4 + 2], cur[4 * k4 + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            if (k < D) {
+                eo[k] = cur[k];
+                eo[D + k] = cur[DT + k];
+            }
+        }
+    }
+    a.cout[b * a.out_T + tile] = cc;
+}
+
+
+static int kalman_pref_levels() {
+    const char* e = getenv("FB2_KALMAN_K");  // tree levels fused into gaussian_kalman_tile (tile = 2^K steps per thread)
+    int k = e ? atoi(e) : 4;
+    return k < 1 ? 1 : (k > KT_KMAX ? KT_KMAX : k);
+}
+static int kalman_levels_for(int64_t T) {
+    int k = kalman_pref_levels();
+    while (k > 1 && (T >> k) < 1) --k;
+    return k;
+}
+struct KalmanLayout {
+    float *Lreg, *Ltail, *opU, *opLinv, *konst, *zeros, *scratch;
+    int32_t* flag;
+    float *lkE[2], *lkC[2], *remE[2], *remC[2];
+    bool ok;
+};
+static KalmanLayout kalman_layout(void* workspace, size_t workspace_bytes, int64_t B, int64_t T, int D, int DT, bool count_only, size_t* used) {
+    const int n = 2 * D, NL = homog_levels_count(T), K = KT_KMAX;
+    // sized for the largest tile the environment can select, so that the size query does not depend on FB2_KALMAN_K
+    const int64_t dK = (T >> 1) + 1, dK1 = (dK + 1) / 2, rem = (int64_t)1 << K;
+    static char dummy;
+    Arena arena(count_only ? static_cast<void*>(&dummy) : workspace, count_only ? ~(size_t)0 >> 1 : workspace_bytes);
+    KalmanLayout L{};
+    L.Lreg = arena.take<float>((size_t)B * NL * n * n);
+    L.Ltail = arena.take<float>((size_t)B * NL * n * n);
+    L.opU = arena.take<float>((size_t)B * NL * 2 * DT * 2 * DT);
+    L.opLinv = arena.take<float>((size_t)B * NL * 2 * DT * DT);
+    L.konst = arena.take<float>((size_t)B * NL * 2);
+    L.zeros = arena.take<float>((size_t)n);
+    L.scratch = arena.take<float>((size_t)B * 2 * n);
+    L.flag = arena.take<int32_t>(1);
+    const int64_t tt[2] = {dK, dK1};
+    for (int q = 0; q < 2; ++q) {
+        L.lkE[q] = arena.take<float>((size_t)B * tt[q] * n);
+        L.lkC[q] = arena.take<float>((size_t)B * tt[q]);
+        L.remE[q] = arena.take<float>((size_t)B * rem * n);
+        L.remC[q] = arena.take<float>((size_t)B * rem);
+    }
+    L.ok = arena.ok() && NL < 48;
+    if (used) *used = arena.used;
+    return L;
+}
+
+template <int DT>
+static int kalman_chain_run(const float* y, const float* Lam, const float* Pr, const float* wo, const float* a0, const float* Po, const float* c0,
+                            int64_t B, int64_t T, int D, int O, float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes,
+                            cudaStream_t stream) {
+    const int NL = homog_levels_count(T), n = 2 * D;
+    const int K = kalman_levels_for(T);
+    const int64_t nfull = T >> K, rem = T - (nfull << K), dK = nfull + (rem > 0 ? 1 : 0);
+    const KalmanLayout lay = kalman_layout(workspace, workspace_bytes, B, T, D, DT, false, nullptr);
+    if (!lay.ok) {
+        set_error("gaussian_kalman_chain: workspace too small (%zu bytes)", workspace_bytes);
+        return FB2_ERR_WORKSPACE;
+    }
+    HomogLevelsArgs la;
+    la.Lam = Lam; la.T = T; la.D = D; la.NL = NL; la.Lo = Lo;
+    la.Lreg = lay.Lreg; la.Ltail = lay.Ltail; la.opU = lay.opU; la.opLinv = lay.opLinv; la.konst = lay.konst;
+    la.zeros = lay.zeros; la.scratch = lay.scratch; la.flag = lay.flag;
+    FB2_CUDA(cudaMemsetAsync(la.flag, 0, sizeof(int32_t), stream));
+    FB2_CUDA(cudaMemsetAsync(lay.zeros, 0, (size_t)n * 4, stream));
+    gaussian_homog_levels<DT><<<(unsigned)B, 64, 0, stream>>>(la);
+    FB2_LAUNCH_CHECK();
+
+    // level-K arrays: [B, dK, n] / [B, dK] (the chain result itself when dK == 1)
+    float* kE = dK == 1 ? eo : lay.lkE[0];
+    float* kC = dK == 1 ? co : lay.lkC[0];
+    {
+        KalmanTileArgs ta;
+        ta.y = y; ta.Pr = Pr; ta.wo = wo; ta.a0 = a0; ta.Po = Po; ta.c0 = c0;
+        ta.opU = la.opU; ta.opLinv = la.opLinv; ta.konst = la.konst;
+        ta.eout = kE; ta.cout = kC; ta.T = T; ta.ntiles = nfull; ta.out_T = dK; ta.D = D; ta.O = O; ta.K = K; ta.NL = NL;
+        const size_t smem = ((size_t)kt_const_floats<DT, 16>() + (size_t)K * kt_level_floats<DT>()) * sizeof(float);
+        FB2_CUDA(cudaFuncSetAttribute(gaussian_kalman_tile<DT, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gaussian_kalman_tile<DT, 16><<<dim3((unsigned)ceil_div(nfull, KT_THREADS), (unsigned)B), KT_THREADS, smem, stream>>>(ta);
+        FB2_LAUNCH_CHECK();
+    }
+    HomogEtaArgs ea;
+    ea.D = D; ea.op_stride = (int64_t)NL * 2;
+    auto op_at = [&](int l, int which) {
+        ea.opU = la.opU + (size_t)(l * 2 + which) * DT * 2 * DT;
+        ea.opLinv = la.opLinv + (size_t)(l * 2 + which) * DT * DT;
+        ea.konst = la.konst + (size_t)(l * 2 + which);
+    };
+    bool has_tail = false;
+    // ---- the remainder tile (the last rem < 2^K steps): level by level with the operators of the whole chain; its parities are those of
+    //      the whole chain (d_l = nfull 2^(K-l) + dl_l), its single level-K element lands in slot nfull
+    if (rem > 0) {
+        gaussian_kalman_eta<16, 4><<<dim3((unsigned)ceil_div(rem, 128), (unsigned)B), 128, 0, stream>>>(y, Pr, wo, a0, Po, c0, rem, D, O, lay.remE[0],
+                                                                                                    lay.remC[0], T, nfull << K);
+        FB2_LAUNCH_CHECK();
+        int64_t dl = rem;
+        int which = 0;
+        for (int l = 0; l < K; ++l) {
+            const bool odd = dl & 1;
+            const int64_t lp = dl / 2, ndl = (dl + 1) / 2;
+            const bool tail_pair = has_tail && !odd && lp >= 1;
+            const int64_t lreg = lp - (tail_pair ? 1 : 0);
+            const bool last = l == K - 1;
+            ea.ein = lay.remE[which]; ea.cin = lay.remC[which]; ea.in_T = dl;
+            ea.eout = last ? kE : lay.remE[which ^ 1];
+            ea.cout = last ? kC : lay.remC[which ^ 1];
+            ea.out_T = last ? dK : ndl;
+            ea.out_p_off = last ? nfull : 0;
+            if (lreg > 0 || odd) {
+                op_at(l, 0);
+                ea.p0 = 0; ea.count = lreg;
+                ea.leftover_src = odd ? dl - 1 : -1;
+                ea.leftover_dst = odd ? ndl - 1 + ea.out_p_off : -1;
+                int64_t blocks = ceil_div(lreg > 0 ? lreg : 1, HE_THREADS);
+                gaussian_homog_eta<DT><<<dim3((unsigned)blocks, (unsigned)B), HE_THREADS, 0, stream>>>(ea);
+                FB2_LAUNCH_CHECK();
+            }
+            if (tail_pair) {
+                op_at(l, 1);
+                ea.p0 = lp - 1; ea.count = 1;
+                ea.leftover_src = -1; ea.leftover_dst = -1;
+                gaussian_homog_eta<DT><<<dim3(1, (unsigned)B), HE_THREADS, 0, stream>>>(ea);
+                FB2_LAUNCH_CHECK();
+            }
+            if (!tail_pair && !has_tail && odd) has_tail = true;
+            dl = ndl;
+            which ^= 1;
+        }
+    }
+    // ---- levels K .. NL-1 over the level-K array, as in homog_chain_run
+    const float *ce = kE, *cc = kC;
+    int64_t d = dK, in_T = dK;
+    int which = 1;
+    for (int l = K; d > 1; ++l) {
+        const int64_t npairs = d / 2, nd = (d + 1) / 2;
+        const bool odd = d & 1;
+        const bool tail_pair = has_tail && !odd;
+        const int64_t reg_pairs = npairs - (tail_pair ? 1 : 0);
+        float* de = nd == 1 ? eo : lay.lkE[which];
+        float* dc = nd == 1 ? co : lay.lkC[which];
+        ea.ein = ce; ea.cin = cc; ea.eout = de; ea.cout = dc; ea.in_T = in_T; ea.out_T = nd;
+        ea.leftover_src = -1; ea.leftover_dst = -1; ea.out_p_off = 0;
+        if (reg_pairs > 0) {
+            op_at(l, 0);
+            ea.p0 = 0; ea.count = reg_pairs;
+            if (odd) {
+                ea.leftover_src = d - 1;
+                ea.leftover_dst = nd - 1;
+            }
+            int64_t blocks = ceil_div(reg_pairs, HE_THREADS);
+            if (blocks > 65535) blocks = 65535;
+            gaussian_homog_eta<DT><<<dim3((unsigned)blocks, (unsigned)B), HE_THREADS, 0, stream>>>(ea);
+            FB2_LAUNCH_CHECK();
+        }
+        if (tail_pair) {
+            op_at(l, 1);
+            ea.p0 = npairs - 1; ea.count = 1;
+            ea.leftover_src = -1; ea.leftover_dst = -1;
+            gaussian_homog_eta<DT><<<dim3(1, (unsigned)B), HE_THREADS, 0, stream>>>(ea);
+            FB2_LAUNCH_CHECK();
+        }
+        if (!tail_pair && !has_tail && odd) has_tail = true;
+        ce = de; cc = dc; in_T = nd; d = nd;
+        which ^= 1;
+    }
+    gaussian_poison_if_flag<<<(unsigned)ceil_div(B, 256), 256, 0, stream>>>(la.flag, co, B);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
 }
 
 }  // namespace fb2
@@ -1458,10 +1893,51 @@ extern "C" int fb2_gaussian_kalman_eta_f32(const float* y, const float* Pr, cons
     int64_t blocks = ceil_div(T, (int64_t)warps * 32 * 4);  // ~4 tiles of 32 steps per warp
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    if (O <= 16) gaussian_kalman_eta<16, 4><<<dim3((unsigned)blocks, (unsigned)B), 128, 0, static_cast<cudaStream_t>(stream)>>>(y, Pr, wo, a0, Po, c0, T, D, O, eta, c);
-    else gaussian_kalman_eta<32, 2><<<dim3((unsigned)blocks, (unsigned)B), 64, 0, static_cast<cudaStream_t>(stream)>>>(y, Pr, wo, a0, Po, c0, T, D, O, eta, c);
+    if (O <= 16) gaussian_kalman_eta<16, 4><<<dim3((unsigned)blocks, (unsigned)B), 128, 0, static_cast<cudaStream_t>(stream)>>>(y, Pr, wo, a0, Po, c0, T, D, O, eta, c, T, 0);
+    else gaussian_kalman_eta<32, 2><<<dim3((unsigned)blocks, (unsigned)B), 64, 0, static_cast<cudaStream_t>(stream)>>>(y, Pr, wo, a0, Po, c0, T, D, O, eta, c, T, 0);
     FB2_LAUNCH_CHECK();
     return FB2_OK;
+}
+
+extern "C" int fb2_gaussian_kalman_constants_f32(const float* F, const float* q_loc, const float* q_tril, const float* H, const float* r_loc,
+                                                 const float* r_tril, int64_t B, int32_t D, int32_t O, float* Lam, float* Pr, float* wo, float* a0,
+                                                 float* Po, float* c0, void* stream) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(F && q_loc && q_tril && H && r_loc && r_tril && Lam && Pr && wo && a0 && Po && c0, "null pointer");
+    FB2_REQUIRE(D >= 1 && D <= GMAXD && O >= 1 && O <= 32, "dimensions D=%d O=%d outside [1, 32]", D, O);
+    FB2_REQUIRE(B >= 0 && B < (1ll << 31), "bad extents");
+    if (B == 0) return FB2_OK;
+    KalmanConstArgs a;
+    a.F = F; a.q_loc = q_loc; a.q_tril = q_tril; a.H = H; a.r_loc = r_loc; a.r_tril = r_tril;
+    a.Lam = Lam; a.Pr = Pr; a.wo = wo; a.a0 = a0; a.Po = Po; a.c0 = c0; a.D = D; a.O = O;
+    gaussian_kalman_constants<<<(unsigned)B, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
+extern "C" size_t fb2_gaussian_kalman_chain_workspace_bytes(int64_t B, int64_t T, int32_t D) {
+    if (B < 1 || T < 2 || D < 1 || D > GMAXD) return 0;
+    const int DT = D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 32;
+    size_t used = 0;
+    kalman_layout(nullptr, 0, B, T, D, DT, true, &used);
+    return used + 256;
+}
+
+extern "C" int fb2_gaussian_kalman_chain_f32(const float* y, const float* Lam, const float* Pr, const float* wo, const float* a0, const float* Po,
+                                             const float* c0, int64_t B, int64_t T, int32_t D, int32_t O, float* Lo, float* eo, float* co,
+                                             void* workspace, size_t workspace_bytes, void* stream_) {
+    int st = check_device();
+    if (st != FB2_OK) return st;
+    FB2_REQUIRE(y && Lam && Pr && wo && a0 && Po && c0 && Lo && eo && co, "null pointer");
+    FB2_REQUIRE(D >= 1 && D <= GMAXD && O >= 1 && O <= 16, "dimensions D=%d (1..32) O=%d (1..16) out of range", D, O);
+    FB2_REQUIRE(B >= 0 && B <= 65535 && T >= 2, "bad extents B=%lld T=%lld (T >= 2)", (long long)B, (long long)T);
+    if (B == 0) return FB2_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (D <= 4) return kalman_chain_run<4>(y, Lam, Pr, wo, a0, Po, c0, B, T, D, O, Lo, eo, co, workspace, workspace_bytes, stream);
+    if (D <= 8) return kalman_chain_run<8>(y, Lam, Pr, wo, a0, Po, c0, B, T, D, O, Lo, eo, co, workspace, workspace_bytes, stream);
+    if (D <= 16) return kalman_chain_run<16>(y, Lam, Pr, wo, a0, Po, c0, B, T, D, O, Lo, eo, co, workspace, workspace_bytes, stream);
+    return kalman_chain_run<32>(y, Lam, Pr, wo, a0, Po, c0, B, T, D, O, Lo, eo, co, workspace, workspace_bytes, stream);
 }
 
 extern "C" int fb2_gaussian_pair_combine_f32(const float* Lx, const float* ex, const float* cx, int64_t x_stride,

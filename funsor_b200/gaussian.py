@@ -11,6 +11,7 @@ sequential_sum_product sum_product.py:652-701, matrix_and_mvn_to_funsor pyro/con
 GaussianHMM pyro/hmm.py:258-274.
 """
 import math
+import os
 
 import torch
 
@@ -262,10 +263,67 @@ def kalman_eta(F, q_loc, q_tril, H, r_loc, r_tril, y):
     return Lam, eta, c
 
 
+def kalman_constants(F, q_loc, q_tril, H, r_loc, r_tril):
+    """The t-independent part of the GaussianHMM chain element in one launch (fb2_gaussian_kalman_constants_f32; the same quantities as
+    _kalman_constants + sqrt_to_info, which remain as the torch statement of them): (Lam[B,2D,2D], Pr[B,O,O], wo[B,O], a0[B,2D],
+    Po[B,2D,O], c0[B])."""
+    B, D = F.shape[0], F.shape[-1]
+    O = H.shape[-1]
+    args = [_dev_f32(t, "kalman parameter").expand(shape).contiguous() for t, shape in (
+        (F, (B, D, D)), (q_loc, (B, D)), (q_tril, (B, D, D)), (H, (B, D, O)), (r_loc, (B, O)), (r_tril, (B, O, O)))]
+    dev = F.device
+    out = [torch.empty(shape, dtype=torch.float32, device=dev) for shape in ((B, 2 * D, 2 * D), (B, O, O), (B, O), (B, 2 * D), (B, 2 * D, O), (B,))]
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        check(lib.fb2_gaussian_kalman_constants_f32(*[t.data_ptr() for t in args], B, D, O, *[t.data_ptr() for t in out], _stream()))
+    return tuple(out)
+
+
+def kalman_eta_from_constants(constants, y):
+    """Per-step chain elements (Lam[B,2D,2D], eta[B,T,2D], c[B,T]) from kalman_constants and the observations (the level-by-level
+    counterpart of kalman_chain_fused)."""
+    Lam, Pr, wo, a0, Po, c0 = constants
+    B, T, O = y.shape
+    n = Lam.shape[-1]
+    y = _dev_f32(y, "y").contiguous()
+    eta = torch.empty((B, T, n), dtype=torch.float32, device=y.device)
+    c = torch.empty((B, T), dtype=torch.float32, device=y.device)
+    lib = _lib.load()
+    with torch.cuda.device(y.device):
+        check(lib.fb2_gaussian_kalman_eta_f32(y.data_ptr(), Pr.data_ptr(), wo.data_ptr(), a0.data_ptr(), Po.data_ptr(), c0.data_ptr(), B, T, n // 2, O,
+                                              eta.data_ptr(), c.data_ptr(), _stream()))
+    return Lam, eta, c
+
+
+def kalman_chain_fused(constants, y, validate=True):
+    """kalman_eta + gaussian_chain_info_homog in one library call (fb2_gaussian_kalman_chain_f32): per tile of 2^K steps the elements
+    and the first K tree levels are evaluated in registers, bit-identical to the level-by-level path."""
+    Lam, Pr, wo, a0, Po, c0 = constants
+    _dev_f32(y, "y")
+    B, T, O = y.shape
+    n = Lam.shape[-1]
+    D = n // 2
+    y = y.contiguous()
+    Lo = torch.empty((B, n, n), dtype=torch.float32, device=y.device)
+    eo = torch.empty((B, n), dtype=torch.float32, device=y.device)
+    co = torch.empty((B,), dtype=torch.float32, device=y.device)
+    lib = _lib.load()
+    ws = _workspace(lib.fb2_gaussian_kalman_chain_workspace_bytes(B, T, D), y.device)
+    with torch.cuda.device(y.device):
+        check(lib.fb2_gaussian_kalman_chain_f32(y.data_ptr(), Lam.data_ptr(), Pr.data_ptr(), wo.data_ptr(), a0.data_ptr(), Po.data_ptr(),
+                                                c0.data_ptr(), B, T, D, O, Lo.data_ptr(), eo.data_ptr(), co.data_ptr(), ws.data_ptr(),
+                                                ws.numel(), _stream()))
+    if validate and bool(torch.isnan(co).any()):
+        raise ValueError("Too little information to marginalize over the shared state. Consider adding a prior.")
+    return Lo, eo, co
+
+
 def kalman_chain(F, q_loc, q_tril, H, r_loc, r_tril, y, validate=True):
     """Parallel-scan Kalman filter for time-homogeneous parameters (examples/kalman_filter.py, GaussianHMM pyro/hmm.py:258-274):
     Returns (Lam[B,2D,2D], eta[B,2D], c[B]) over (state_{-1}; state_{T-1}), the value of the reference's MarkovProduct
     (pyro/hmm.py:269).  Time-varying elements go through kalman_elements_sqrt + sqrt_to_info + gaussian_sequential_sum_product."""
+    if F.shape[-1] <= 32 and y.shape[-1] <= 16 and y.shape[1] >= 2 and os.environ.get("FB2_KALMAN_FUSED", "1") != "0":
+        return kalman_chain_fused(kalman_constants(F, q_loc, q_tril, H, r_loc, r_tril), y, validate=validate)
     if F.shape[-1] <= 32 and y.shape[-1] <= 32:
         Lam, eta, c = kalman_eta(F, q_loc, q_tril, H, r_loc, r_tril, y)
         return gaussian_chain_info_homog(Lam, eta, c, validate=validate)

@@ -195,6 +195,20 @@ int fb2_gaussian_pair_combine_f32(const float* Lx, const float* ex, const float*
  *                wo[B,O], a0[B,2D] = P[:, :D] w_trans, Po[B,2D,O] = P[:, D:], c0[B].  No [B,T,D+O] white_vec array is materialised. */
 int fb2_gaussian_kalman_eta_f32(const float* y, const float* Pr, const float* wo, const float* a0, const float* Po, const float* c0, int64_t B,
                                 int64_t T, int32_t D, int32_t O, float* eta, float* c, void* stream);
+/* kalman_constants : everything of the GaussianHMM chain element that does not depend on t, one CTA per chain (pyro/hmm.py:258-270,
+ *                     matrix_and_mvn_to_funsor pyro/convert.py:278-298): F[B,D,D], q_loc[B,D], q_tril[B,D,D], H[B,D,O], r_loc[B,O],
+ *                     r_tril[B,O,O] -> Lam[B,2D,2D] = P P' (the precision shared by all steps), Pr, wo, a0, Po, c0 as kalman_eta takes them.
+ * kalman_chain     : the whole scan of pyro/hmm.py:269 (sequential_sum_product over the T chain elements, sum_product.py:652-701) from the
+ *                     observations y[B,T,O] and those constants to (Lam[B,2D,2D], eta[B,2D], c[B]) over (state_-1; state_T-1).  The per-step
+ *                     elements and the first K levels of the reference's tree (K = 4, FB2_KALMAN_K) are evaluated per tile of 2^K steps
+ *                     without touching memory; results are bit-identical to kalman_eta + chain_homog.  O <= 16, T >= 2. */
+int fb2_gaussian_kalman_constants_f32(const float* F, const float* q_loc, const float* q_tril, const float* H, const float* r_loc,
+                                      const float* r_tril, int64_t B, int32_t D, int32_t O, float* Lam, float* Pr, float* wo, float* a0,
+                                      float* Po, float* c0, void* stream);
+size_t fb2_gaussian_kalman_chain_workspace_bytes(int64_t B, int64_t T, int32_t D);
+int fb2_gaussian_kalman_chain_f32(const float* y, const float* Lam, const float* Pr, const float* wo, const float* a0, const float* Po,
+                                  const float* c0, int64_t B, int64_t T, int32_t D, int32_t O, float* Lo, float* eo, float* co,
+                                  void* workspace, size_t workspace_bytes, void* stream);
 int fb2_gaussian_eta_f32(const float* w, const float* P, const float* s, int64_t B, int64_t T, int32_t dim, int32_t rank,
                          float* eta, float* c, void* stream);
 int fb2_gaussian_chain_homog_f32(const float* Lam, const float* eta, const float* c, int64_t B, int64_t T, int32_t D,

@@ -169,6 +169,55 @@ def test_kalman_homogeneous_operator_path_against_float64_filter(fg, T, D, O):
     close_norm(host(lp), G.hmm_logprob_from_chain(G.mvn_info(m0, p0), want, D), 1e-5)
 
 
+def _kalman_args(B, T, D, O, seed):
+    g = torch.Generator().manual_seed(seed)
+    F = 0.9 * torch.linalg.qr(torch.randn(B, D, D, generator=g))[0]
+    H = torch.randn(B, D, O, generator=g) / D ** 0.5
+
+    def tril(n):
+        a = torch.randn(B, n, n, generator=g) * 0.2
+        return torch.tril(a, -1) + torch.diag_embed(0.5 + torch.rand(B, n, generator=g))
+
+    args = [F, torch.randn(B, D, generator=g) * 0.1, tril(D), H, torch.randn(B, O, generator=g) * 0.1, tril(O), torch.randn(B, T, O, generator=g)]
+    return [a.cuda() for a in args]
+
+
+@pytest.mark.parametrize("B,D,O", [(3, 4, 2), (2, 32, 16), (5, 3, 1), (1, 8, 8), (2, 17, 5), (64, 32, 16)])
+def test_kalman_constants_kernel_matches_the_torch_statement(fg, B, D, O):
+    """fb2_gaussian_kalman_constants_f32 against _kalman_constants + sqrt_to_info evaluated in float64 by torch."""
+    args = _kalman_args(B, 4, D, O, 7 + D)
+    got = fg.kalman_constants(*args[:6])
+    a64 = [a.double() for a in args[:6]]
+    P, Pr, w_t, w_o, s = fg._kalman_constants(*a64)
+    want = (P @ P.transpose(-1, -2), Pr, w_o, (P[:, :, :D] @ w_t[:, :, None])[:, :, 0], P[:, :, D:], s - 0.5 * (w_t * w_t).sum(-1))
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        close_norm(host(a), host(b), 1e-5)
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("D,O", [(3, 2), (32, 16), (8, 5)])
+def test_kalman_fused_tiles_are_bit_identical_to_the_level_by_level_path(fg, monkeypatch, K, D, O):
+    """gaussian_kalman_tile (elements + the first K tree levels per tile of 2^K steps in registers, remainder tile level by level) must
+    walk the reference's tree (sum_product.py:690-701) exactly: every T from 2 to 70 plus a few long ones, against kalman_eta +
+    gaussian_homog_eta on the same constants, compared with torch.equal."""
+    monkeypatch.setenv("FB2_KALMAN_K", str(K))
+    B = 2
+    lengths = list(range(2, 71)) + [127, 128, 129, 1000, 1023, 4097] if D <= 8 else [2, 3, 5, 16, 17, 31, 33, 47, 64, 65, 100, 1023, 4097]
+    for T in lengths:
+        args = _kalman_args(B, T, D, O, 100 * T + D)
+        consts = fg.kalman_constants(*args[:6])
+        got = fg.kalman_chain_fused(consts, args[6])
+        if T >= 4:
+            want = fg.gaussian_chain_info_homog(*fg.kalman_eta_from_constants(consts, args[6]))
+            for a, b in zip(got, want):
+                assert torch.equal(a, b), "T={} K={}: max diff {}".format(T, K, (a - b).abs().max().item())
+        w, P, s = fg.kalman_elements_sqrt(*args)
+        ref = fg.gaussian_sequential_sum_product(*fg.sqrt_to_info(w, P, s))
+        for a, b in zip(got, ref):
+            close_norm(host(a), host(b), 2e-5)
+
+
 # ------------------------------------------------------------------------------------------------ (f2) Gaussian backward sampling
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,T,D,O", [(2, 2, 1, 1), (2, 7, 3, 2), (1, 8, 2, 1), (2, 13, 4, 2), (1, 33, 2, 2)])
