@@ -89,6 +89,17 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_bf16_k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {  // {upper half: hi, lower half: lo}, round to nearest
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -288,9 +299,17 @@ constexpr float kScalePl = 16777216.f, kUnscalePl = 1.f / 16777216.f;
 // CL = CTAs per cluster: 8 (each warp contracts the whole K-slice for its n-tile(s)) or 4 ("half-K": the K-slice is twice as
 // long, a cluster owns 32 columns, warp w contracts n-tile w & 3 over K-half w >> 2, so a warp issues half the MMAs and a CTA
 // ships 1.5 KB instead of 7 KB of partials per step; 2 x 4 = 8 partial sources per column group either way).
-template <int K16, int NT, int CL = 8>
+//
+// PK4 (single chain group, S in (512, 1024]): the message travels as 4-byte self-validating words in mma A-fragment order instead
+// of 8-byte packets -- the format of the single-hop kernel below: every fp32 mantissa carries a 1-bit step stamp in its LSB (rounded
+// to even at bit 1 first, cleared by the consumer: <= 1 ulp, unbiased), block exponents travel as {stamp16 | zero | E15} words.  A
+// consumer CTA's K-slice is one contiguous 8 KB block [k8-step][lane][4] + 1 KB of exponent words, fetched by all 256 threads with
+// fully coalesced 16-byte loads (2 per thread and round): 272 L2 sectors per CTA and poll round instead of 2048 (the 8-byte packets
+// were read as 16-byte pieces 64 bytes apart, every sector twice).
+template <int K16, int NT, int CL = 8, bool PK4 = false>
 __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) {
     constexpr bool HALFK = CL == 4;
+    static_assert(!PK4 || (CL == 8 && K16 == 8), "4-byte words: clusters of 8, 16 k8-steps per K-slice");
     constexpr int SP = K16 * 128;         // padded state count
     constexpr int KS = SP / CL;           // rows of P (= message entries) per CTA
     constexpr int NG = KS / 8;            // producer groups (8 columns each) in this CTA's K-slice
@@ -313,6 +332,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ int s_abort;
     __shared__ float s_obs[FLOW_OBS_DEPTH][FLOW_THREADS];  // cp.async ring of obs[b, t, colC], private per thread
+    __shared__ __align__(16) int s_ex[PK4 ? FLOW_CHAINS : 1][20];  // PK4: {zero | E15} of the slice's 16 column groups, per chain
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
     const int rank = (int)cluster_ctarank();
@@ -353,8 +373,12 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 Ph[nt][ks][h] = hi;
                 lo2[h] = (v - __uint_as_float(hi)) * kScalePl;
             }
-            const __half2 l = __floats2half2_rn(lo2[0], lo2[1]);
-            Pl[nt][ks] = *reinterpret_cast<const uint32_t*>(&l);
+            if constexpr (PK4) {
+                Pl[nt][ks] = pack_bf16(lo2[0] * kUnscalePl, lo2[1] * kUnscalePl);  // plain bf16 pair: B fragment half of the k16 side products
+            } else {
+                const __half2 l = __floats2half2_rn(lo2[0], lo2[1]);
+                Pl[nt][ks] = *reinterpret_cast<const uint32_t*>(&l);
+            }
         }
     }
 
@@ -375,6 +399,26 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
     cluster_sync_all();  // barriers initialised cluster-wide before any remote arrive
 
     unsigned long long* const pkt_set = p.pkt + (size_t)set * 2 * FLOW_CHAINS * SP;
+    // PK4 layout inside the same allocation: data [parity][K-slice][k8-step][32 lanes][4] fp32, then exponents [parity][K-slice][k8-step][16 chains]
+    uint32_t* const data_set = reinterpret_cast<uint32_t*>(pkt_set);
+    uint32_t* const expo_set = data_set + 2 * FLOW_CLUSTER * NG * 128;
+    // where the value of (chain bc, column colC) goes: K-slice colC / KS, k8-step (colC % KS) / 8, lane (bc & 7, jc >> 1), word (bc >> 3) + 2 (jc & 1)
+    const int pub_grp = tc >= 0 ? (colC / KS) * NG + (colC % KS) / 8 : 0;
+    const int pub_word = (((bc & 7) * 4 + (jc >> 1)) * 4) + (bc >> 3) + 2 * (jc & 1);
+    auto publish4 = [&](unsigned t_stamp, float u, int E15, bool zero) {
+        uint32_t bits = __float_as_uint(u);
+        bits = ((bits & 3u) == 3u) ? bits + 1u : (bits & ~1u);  // round to even at bit 1: bit 0 is free for the stamp
+        bits |= (t_stamp >> 1) & 1u;
+        uint32_t* dst = data_set + ((size_t)(t_stamp & 1) * FLOW_CLUSTER * NG + pub_grp) * 128 + pub_word;
+        if (p.mode & 1) atomicExch(dst, bits);
+        else asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(dst), "r"(bits) : "memory");
+        if (jc == 0) {
+            const uint32_t w = ((t_stamp & 0xFFFFu) << 16) | (zero ? 0x8000u : 0u) | (unsigned)E15;
+            uint32_t* de = expo_set + ((size_t)(t_stamp & 1) * FLOW_CLUSTER * NG + pub_grp) * 16 + bc;
+            if (p.mode & 1) atomicExch(de, w);
+            else asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(de), "r"(w) : "memory");
+        }
+    };
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned nstep = 0;  // steps executed by this CTA (drives barrier parity and smem buffer choice)
     unsigned tau = 0;    // packet stamp counter (monotone across chain groups)
@@ -423,8 +467,10 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
             u_last = u;
             zero_last = zero;
             const unsigned stamp = ((tau & 0xFFFFu) << 16) | (zero ? 0x8000u : 0u) | (unsigned)E15;
-            st_pkt(pkt_set + ((size_t)(tau & 1) * FLOW_CHAINS + bc) * SP + colC,
-                   ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(u));
+            if constexpr (PK4) publish4(tau, u, E15, zero);
+            else
+                st_pkt(pkt_set + ((size_t)(tau & 1) * FLOW_CHAINS + bc) * SP + colC,
+                       ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(u));
         }
         // obs prefetch ring: one cp.async group per step, FLOW_OBS_DEPTH-1 steps ahead
         const uint32_t obs_ring = smem_u32(&s_obs[0][tid]);
@@ -445,7 +491,116 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
             long long c_pkt = c_top;
 
             // ================= phase A: fetch this CTA's K-slice of the message =================
-            if (tid < NA) {
+            if constexpr (PK4) {
+                // thread tid holds lane `lane` of the A fragments of k8-steps warp and warp + 8, and exponent word tid = (k8-step tid >> 4, chain tid & 15)
+                const uint32_t* dsl = data_set + ((size_t)(tau & 1) * FLOW_CLUSTER + rank) * NG * 128;
+                const uint32_t* esl = expo_set + ((size_t)(tau & 1) * FLOW_CLUSTER + rank) * NG * 16;
+                const uint32_t want_bit = (tau >> 1) & 1u, want16 = tau & 0xFFFFu;
+                uint4 f0, f1;
+                uint32_t ew;
+                const long long start = clock64();
+                auto fetch = [&](uint4& a0, uint4& a1, uint32_t& e) {
+                    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a0.x), "=r"(a0.y), "=r"(a0.z), "=r"(a0.w) : "l"(dsl + tid * 4) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w) : "l"(dsl + (tid + 256) * 4) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(esl + tid) : "memory");
+                };
+                auto valid = [&](const uint4& a0, const uint4& a1, uint32_t e) {
+                    const uint32_t all_and = a0.x & a0.y & a0.z & a0.w & a1.x & a1.y & a1.z & a1.w;
+                    const uint32_t all_or = a0.x | a0.y | a0.z | a0.w | a1.x | a1.y | a1.z | a1.w;
+                    return ((want_bit ? all_and : ~all_or) & 1u) && (e >> 16) == want16;
+                };
+                if (p.mode & 32) {
+                    // two probe sets in flight, half a round trip apart: a word that lands right after one probe was served is seen by the
+                    // other ~350 cycles later instead of a full round trip later (the step is a chip-wide maximum over all polling threads)
+                    uint4 g0, g1;
+                    uint32_t gw;
+                    fetch(f0, f1, ew);
+                    spin_cycles(330);
+                    fetch(g0, g1, gw);
+                    for (;;) {
+                        if (valid(f0, f1, ew)) break;
+                        fetch(f0, f1, ew);
+                        if (valid(g0, g1, gw)) {
+                            f0 = g0; f1 = g1; ew = gw;
+                            break;
+                        }
+                        fetch(g0, g1, gw);
+                        if (clock64() - start > FLOW_SPIN_LIMIT) {
+                            timed_out = 1;
+                            break;
+                        }
+                    }
+                } else
+                for (;;) {
+                    fetch(f0, f1, ew);
+                    if (valid(f0, f1, ew)) break;
+                    if (clock64() - start > FLOW_SPIN_LIMIT) {
+                        timed_out = 1;
+                        if (atomicCAS(p.abort_flag + 1, 0, 1) == 0) {  // first timeout wins: leave a post-mortem record
+                            p.abort_flag[2] = (int)blockIdx.x;
+                            p.abort_flag[3] = tid;
+                            p.abort_flag[4] = (int)t;
+                            p.abort_flag[5] = (int)want16;
+                            p.abort_flag[6] = (int)f0.x;
+                            p.abort_flag[7] = (int)ew;
+                        }
+                        break;
+                    }
+                }
+                if (p.prof) c_pkt = clock64();
+                s_ex[tid & 15][tid >> 4] = (int)(ew & 0xFFFFu);
+                __syncthreads();
+                // align the block exponents of the slice's 16 column groups, per chain (g and g + 8 of this lane's fragments)
+                float sc[2][2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int ch = g + 8 * h;
+                    int e[16];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int4 v = *reinterpret_cast<const int4*>(&s_ex[ch][4 * q4]);
+                        e[4 * q4] = v.x; e[4 * q4 + 1] = v.y; e[4 * q4 + 2] = v.z; e[4 * q4 + 3] = v.w;
+                    }
+                    const int ref = e[0] & 0x7FFF;
+                    int m = -40000;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) m = max(m, (e[q] & 0x8000) ? -40000 : sext15(e[q] - ref));
+                    const int ea = s_ex[ch][warp], eb = s_ex[ch][warp + 8];
+                    sc[h][0] = (ea & 0x8000) ? 0.f : pow2i(sext15(ea - ref) - m);
+                    sc[h][1] = (eb & 0x8000) ? 0.f : pow2i(sext15(eb - ref) - m);
+                    if (warp == 0 && tig == 0) s_erefloc[buf][ch] = (m == -40000) ? (0x8000 | ref) : ((ref + m) & 0x7FFF);
+                }
+                // Staged per lane: the TF32 hi fragments of k8-steps warp and warp + 8, and for the k16 unit made of these two k8-steps
+                // the bf16 A fragments of lo = v - hi and of v (rows g / g + 8, k slots (2 tig, 2 tig + 1) of either k8-step):
+                //   v P = vh Ph (TF32, 2 mma.k8) + [vl Ph + vh Pl] (bf16, 2 mma.k16): 4 tensor instructions per 16 k instead of 6; the
+                //   side products are 2^-11 of the result, so bf16's 2^-9 keeps them at 2^-20.
+                const int swz = (g & 1) * 16;
+                float v[2][4], lo[2][4];
+                uint32_t hi[2][4];
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    const uint4 q = f ? f1 : f0;
+                    v[f][0] = __uint_as_float(q.x & ~1u) * sc[0][f];
+                    v[f][1] = __uint_as_float(q.y & ~1u) * sc[1][f];
+                    v[f][2] = __uint_as_float(q.z & ~1u) * sc[0][f];
+                    v[f][3] = __uint_as_float(q.w & ~1u) * sc[1][f];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        hi[f][c] = cvt_tf32(v[f][c]);
+                        lo[f][c] = v[f][c] - __uint_as_float(hi[f][c]);
+                    }
+                }
+                const uint4 bl = make_uint4(pack_bf16(lo[0][0], lo[0][2]), pack_bf16(lo[0][1], lo[0][3]), pack_bf16(lo[1][0], lo[1][2]),
+                                            pack_bf16(lo[1][1], lo[1][3]));
+                const uint4 bh = make_uint4(pack_bf16(v[0][0], v[0][2]), pack_bf16(v[0][1], v[0][3]), pack_bf16(v[1][0], v[1][2]),
+                                            pack_bf16(v[1][1], v[1][3]));
+                unsigned char* d0 = &s_frag[buf][warp][0] + lane * 32;
+                unsigned char* d1 = &s_frag[buf][warp + 8][0] + lane * 32;
+                *reinterpret_cast<uint4*>(d0 + swz) = make_uint4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
+                *reinterpret_cast<uint4*>(d0 + (16 ^ swz)) = bl;
+                *reinterpret_cast<uint4*>(d1 + swz) = make_uint4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
+                *reinterpret_cast<uint4*>(d1 + (16 ^ swz)) = bh;
+            } else if (tid < NA) {
                 constexpr unsigned amask = NA >= 32 ? 0xffffffffu : ((1u << (NA & 31)) - 1u);
                 const unsigned long long* src0 = pkt_set + ((size_t)(tau & 1) * FLOW_CHAINS + ga) * SP + rank * KS + pa * 8;
                 const unsigned long long* src1 = src0 + (size_t)8 * SP;
@@ -537,6 +692,31 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
 #pragma unroll
                         for (int c = 0; c < 4; ++c) acc[nt][q][c] = 0.f;
                 const int swz = ((lane >> 2) & 1) * 16;
+                if constexpr (PK4) {
+#pragma unroll
+                    for (int j = 0; j < NKS / 2; ++j) {
+                        const unsigned char* r0 = &s_frag[buf][j][0] + lane * 32;
+                        const unsigned char* r1 = &s_frag[buf][j + NKS / 2][0] + lane * 32;
+                        const uint4 h0 = *reinterpret_cast<const uint4*>(r0 + swz), bl = *reinterpret_cast<const uint4*>(r0 + (16 ^ swz));
+                        const uint4 h1 = *reinterpret_cast<const uint4*>(r1 + swz), bh = *reinterpret_cast<const uint4*>(r1 + (16 ^ swz));
+                        const uint32_t ah0[4] = {h0.x, h0.y, h0.z, h0.w}, ah1[4] = {h1.x, h1.y, h1.z, h1.w};
+                        const uint32_t abl[4] = {bl.x, bl.y, bl.z, bl.w}, abh[4] = {bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[nt][0], ah0, Ph[nt][j][0], Ph[nt][j][1]);
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)  // bf16 B fragment of Ph: the upper halves of the TF32 registers (slots h = 0, 1 of either k8-step)
+                            mma_bf16_k16(acc[nt][2], abl, __byte_perm(Ph[nt][j][0], Ph[nt][j][1], 0x7632),
+                                         __byte_perm(Ph[nt][j + NKS / 2][0], Ph[nt][j + NKS / 2][1], 0x7632));
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[nt][1], ah1, Ph[nt][j + NKS / 2][0], Ph[nt][j + NKS / 2][1]);
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) mma_bf16_k16(acc[nt][2], abh, Pl[nt][j], Pl[nt][j + NKS / 2]);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[nt][2][c] *= kScalePl;  // the common epilogue below multiplies by 2^-24
+                } else
 #pragma unroll
                 for (int ks = 0; ks < NKS; ++ks) {
                     const unsigned char* rowp = &s_frag[buf][khalf * NKS + ks][0] + lane * 32;
@@ -623,7 +803,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 zero_last = zero;
                 const unsigned tn = tau + 1;
                 const unsigned stamp = ((tn & 0xFFFFu) << 16) | (zero ? 0x8000u : 0u) | (unsigned)E15;
-                if (p.mode & 1)
+                if constexpr (PK4)
+                    publish4(tn, u, E15, zero);
+                else if (p.mode & 1)
                     atomicExch(pkt_set + ((size_t)(tn & 1) * FLOW_CHAINS + bc) * SP + colC,
                                ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(u));
                 else
@@ -1814,9 +1996,9 @@ size_t hmm_flow_workspace_bytes(int64_t B, int S) {
            align_up(groups * FLOW_CHAINS * (Sp / 8) * 4) + align_up(32) + align_up((size_t)FLOW_PROF_CTAS * 64) + 256;
 }
 
-template <int K16, int NT, int CL = 8>
+template <int K16, int NT, int CL = 8, bool PK4 = false>
 static int flow_launch(FlowArgs& a, cudaStream_t stream) {
-    auto kernel = hmm_flow_forward<K16, NT, CL>;
+    auto kernel = hmm_flow_forward<K16, NT, CL, PK4>;
     constexpr int NCC = K16 * 128 / (CL * 8 * NT);
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(FLOW_THREADS);
@@ -2077,7 +2259,10 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
         else if (fs.k16 == 4) st = wide ? flow_launch<4, 2>(a, stream) : flow_launch<4, 1>(a, stream);
         else {
             const char* cl4 = getenv("FB2_FLOW_CL4");  // experiment: clusters of 4 with half-K warps
-            st = (cl4 && cl4[0] == '1') ? flow_launch<8, 1, 4>(a, stream) : flow_launch<8, 2>(a, stream);
+            const char* pk4 = getenv("FB2_FLOW_PK4");  // 0: 8-byte packets also for a single chain group
+            if (cl4 && cl4[0] == '1') st = flow_launch<8, 1, 4>(a, stream);
+            else if (groups == 1 && !(pk4 && pk4[0] == '0')) st = flow_launch<8, 2, 8, true>(a, stream);
+            else st = flow_launch<8, 2>(a, stream);
         }
     }
     if (st != FB2_OK) {
