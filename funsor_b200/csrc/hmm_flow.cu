@@ -332,7 +332,10 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ int s_abort;
     __shared__ float s_obs[FLOW_OBS_DEPTH][FLOW_THREADS];  // cp.async ring of obs[b, t, colC], private per thread
-    __shared__ __align__(16) int s_ex[PK4 ? FLOW_CHAINS : 1][20];  // PK4: {zero | E15} of the slice's 16 column groups, per chain
+    // PK4: the slice's 16 block exponents per chain, as E15 << 17 (wrapping differences are then plain int subtractions), bit 0 set = zero
+    // group (no value of E15 << 17 is free to serve as a marker: 0x4000 << 17 is INT_MIN); column 16 = E15 << 17 of group 0 whatever its
+    // zero flag (the reference)
+    __shared__ __align__(16) int s_ex[PK4 ? FLOW_CHAINS : 1][20];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
     const int rank = (int)cluster_ctarank();
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
             const unsigned ph = (nstep >> 1) & 1;
             int timed_out = 0;
             const long long c_top = p.prof ? clock64() : 0;
-            long long c_pkt = c_top;
+            long long c_pkt = c_top, c_bar1 = 0;
 
             // ================= phase A: fetch this CTA's K-slice of the message =================
             if constexpr (PK4) {
@@ -548,27 +551,35 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                     }
                 }
                 if (p.prof) c_pkt = clock64();
-                s_ex[tid & 15][tid >> 4] = (int)(ew & 0xFFFFu);
+                s_ex[tid & 15][tid >> 4] = (int)(ew << 17) | (int)((ew >> 15) & 1u);
+                if (tid < 16) s_ex[tid][16] = (int)(ew << 17);
                 __syncthreads();
-                // align the block exponents of the slice's 16 column groups, per chain (g and g + 8 of this lane's fragments)
+                if (p.prof) c_bar1 = clock64();
+                // align the block exponents of the slice's 16 column groups, per chain.  Every warp: lane -> (chain lane & 15, half lane >> 4)
+                // takes the maximum over 8 groups relative to group 0, the halves are merged by one shuffle, and a lane fetches (ref, max) of
+                // the chains g and g + 8 of its fragments by shuffle (the first version let every thread scan all 16 words of both chains:
+                // ~190 ALU instructions per thread, ~770 cycles of ALU issue per step).
                 float sc[2][2];
+                {
+                    const int chn = lane & 15, hf = lane >> 4;
+                    const int ref_l = s_ex[chn][16];
+                    const int4 ea4 = *reinterpret_cast<const int4*>(&s_ex[chn][8 * hf]), eb4 = *reinterpret_cast<const int4*>(&s_ex[chn][8 * hf + 4]);
+                    const int own[2][2] = {{s_ex[g][warp], s_ex[g][warp + 8]}, {s_ex[g + 8][warp], s_ex[g + 8][warp + 8]}};
+                    const int e8[8] = {ea4.x, ea4.y, ea4.z, ea4.w, eb4.x, eb4.y, eb4.z, eb4.w};
+                    int d8[8];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int ch = g + 8 * h;
-                    int e[16];
+                    for (int q = 0; q < 8; ++q) d8[q] = (e8[q] & 1) ? INT_MIN : e8[q] - ref_l;  // = sext15(E - ref) << 17
+                    int m_l = max(max(max(d8[0], d8[1]), max(d8[2], d8[3])), max(max(d8[4], d8[5]), max(d8[6], d8[7])));
+                    m_l = max(m_l, __shfl_xor_sync(0xffffffffu, m_l, 16));
+                    if (warp == 0 && lane < 16)
+                        s_erefloc[buf][lane] = (m_l == INT_MIN) ? (0x8000 | (int)((unsigned)ref_l >> 17)) : (int)((unsigned)(ref_l + m_l) >> 17);
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const int4 v = *reinterpret_cast<const int4*>(&s_ex[ch][4 * q4]);
-                        e[4 * q4] = v.x; e[4 * q4 + 1] = v.y; e[4 * q4 + 2] = v.z; e[4 * q4 + 3] = v.w;
+                    for (int h = 0; h < 2; ++h) {
+                        const int ch = g + 8 * h;
+                        const int ref = __shfl_sync(0xffffffffu, ref_l, ch), m = __shfl_sync(0xffffffffu, m_l, ch) >> 17;
+                        sc[h][0] = (own[h][0] & 1) ? 0.f : pow2i(((own[h][0] - ref) >> 17) - m);
+                        sc[h][1] = (own[h][1] & 1) ? 0.f : pow2i(((own[h][1] - ref) >> 17) - m);
                     }
-                    const int ref = e[0] & 0x7FFF;
-                    int m = -40000;
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) m = max(m, (e[q] & 0x8000) ? -40000 : sext15(e[q] - ref));
-                    const int ea = s_ex[ch][warp], eb = s_ex[ch][warp + 8];
-                    sc[h][0] = (ea & 0x8000) ? 0.f : pow2i(sext15(ea - ref) - m);
-                    sc[h][1] = (eb & 0x8000) ? 0.f : pow2i(sext15(eb - ref) - m);
-                    if (warp == 0 && tig == 0) s_erefloc[buf][ch] = (m == -40000) ? (0x8000 | ref) : ((ref + m) & 0x7FFF);
                 }
                 // Staged per lane: the TF32 hi fragments of k8-steps warp and warp + 8, and for the k16 unit made of these two k8-steps
                 // the bf16 A fragments of lo = v - hi and of v (rows g / g + 8, k slots (2 tig, 2 tig + 1) of either k8-step):
@@ -753,6 +764,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 prof_acc[0] += c_pkt - c_top;    // waiting for / loading packets
                 prof_acc[1] += c_sync - c_pkt;   // exponent alignment, split, STS, bar.sync
                 prof_acc[2] += c_sent - c_sync;  // LDS + mma + DSMEM stores + arrive
+                if (c_bar1) prof_acc[6] += c_bar1 - c_pkt;  // PK4: own words valid -> every thread's words valid (barrier 1)
             }
 
             // ================= phase C: final owners finish their columns and publish =================
@@ -762,33 +774,42 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 const float ob = obs_c ? s_obs[t % FLOW_OBS_DEPTH][tid] : 0.f;
                 const FlowObs1 oterm = flow_obs1(chain_ok ? (ob + caC) * kLog2e : -INFINITY, true);
                 const long long start = clock64();
-                while (!mbar_try_wait(bar_addr0 + (uint32_t)par * 8, ph)) {
-                    if (clock64() - start > FLOW_SPIN_LIMIT) {
-                        s_abort = 1;
-                        if (atomicCAS(p.abort_flag + 1, 0, 2) == 0) {
-                            p.abort_flag[2] = (int)blockIdx.x;
-                            p.abort_flag[3] = tid;
-                            p.abort_flag[4] = (int)t;
+                auto wait_bar = [&](uint32_t addr, int kind) {
+                    while (!mbar_try_wait(addr, ph)) {
+                        if (clock64() - start > FLOW_SPIN_LIMIT) {
+                            s_abort = 1;
+                            if (atomicCAS(p.abort_flag + 1, 0, kind) == 0) {
+                                p.abort_flag[2] = (int)blockIdx.x;
+                                p.abort_flag[3] = tid;
+                                p.abort_flag[4] = (int)t;
+                            }
+                            break;
                         }
-                        break;
                     }
-                }
+                };
+                // The 8 lanes (jc = 0..7) that share a chain split the 8 sources between them: lane jc aligns source jc, the maximum is an
+                // 8-lane butterfly and the weights are handed round by shuffle (every thread scanning all 8 exponent words cost ~110 ALU
+                // instructions per thread: ~450 cycles of ALU issue per step).  (Sending the exponents ahead of the contraction under their own
+                // mbarrier, so that the weights are ready when the partial sums land, was measured: no change in the step time.)
+                wait_bar(bar_addr0 + (uint32_t)par * 8, 2);
                 const long long c_got = p.prof ? clock64() : 0;
-                const int e0 = s_eref[par][0][bc] & 0x7FFF;
-                int dr[FLOW_CLUSTER], dmax = -40000;
+                const int e_mine = s_eref[par][jc][bc];
+                const int e0 = __shfl_sync(0xffffffffu, e_mine, lane & ~7) & 0x7FFF;
+                const int d_mine = (e_mine & 0x8000) ? -40000 : sext15(e_mine - e0);
+                int dmax = d_mine;
+                dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, 4));
+                dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, 2));
+                dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, 1));
+                const float w_mine = (d_mine == -40000) ? 0.f : pow2i(d_mine - dmax);
+                float wr[FLOW_CLUSTER];
 #pragma unroll
-                for (int r = 0; r < FLOW_CLUSTER; ++r) {
-                    const int e = s_eref[par][r][bc];
-                    dr[r] = (e & 0x8000) ? -40000 : sext15(e - e0);
-                    dmax = max(dmax, dr[r]);
-                }
+                for (int r = 0; r < FLOW_CLUSTER; ++r) wr[r] = __shfl_sync(0xffffffffu, w_mine, (lane & ~7) + r);
+                const int emax = (dmax == -40000) ? e0 : ((e0 + dmax) & 0x7FFF);
                 float s = 0.f;
 #pragma unroll
-                for (int r = 0; r < FLOW_CLUSTER; ++r)
-                    s += (dr[r] == -40000) ? 0.f : s_part[par][r][ntc][bc][jc] * pow2i(dr[r] - dmax);
-                const int emax = (dmax == -40000) ? e0 : ((e0 + dmax) & 0x7FFF);
+                for (int r = 0; r < FLOW_CLUSTER; ++r) s += s_part[par][r][ntc][bc][jc] * wr[r];
                 // this phase is complete (all threads of the CTA that wait on it see the same parity); arm the
-                // barrier for the step after next.  No sender can be two steps ahead of this CTA.
+                // barriers for the step after next.  No sender can be two steps ahead of this CTA.
                 if (tc == 0) mbar_arm(bar_addr0 + (uint32_t)par * 8, TX_BYTES);
                 const long long c_red = p.prof ? clock64() : 0;
                 int E15;
@@ -847,14 +868,16 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
         tau += 2;
     }
     if (p.prof) {
-        if (tid == 0)
+        if (tid == 0) {
             for (int q = 0; q < 3; ++q) p.prof[(size_t)blockIdx.x * 8 + q] = prof_acc[q];
+            if (PK4) p.prof[(size_t)blockIdx.x * 8 + 7] = prof_acc[6];  // PK4: the "obs" column of the report is the wait at barrier 1
+        }
         if (tid == FLOW_THREADS - 1) {
             p.prof[(size_t)blockIdx.x * 8 + 3] = prof_acc[3];
             p.prof[(size_t)blockIdx.x * 8 + 4] = prof_acc[4];
             p.prof[(size_t)blockIdx.x * 8 + 5] = (long long)nstep;
             p.prof[(size_t)blockIdx.x * 8 + 6] = prof_acc[5];
-            p.prof[(size_t)blockIdx.x * 8 + 7] = prof_acc[6];
+            if (!PK4) p.prof[(size_t)blockIdx.x * 8 + 7] = prof_acc[6];
             p.prof[(size_t)blockIdx.x * 8 + 2] += 0;
             p.prof[(size_t)(FLOW_PROF_CTAS / 2 + blockIdx.x / 2) * 8 + (blockIdx.x & 1)] = prof_acc[7];
         }
@@ -2304,7 +2327,7 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
         for (int c = 0; c < FLOW_PROF_CTAS / 2; c += 9) {
             const double n = h[c * 8 + 5] > 0 ? (double)h[c * 8 + 5] : 1.0;
             if (h[c * 8 + 5] > 0)
-                fprintf(stderr, "[fb2 flow prof] cta %3d steps %lld | pkt-wait %.0f  A-proc+sync %.0f  B(mma+send) %.0f | C-wait %.0f  C-proc %.0f (reduce %.0f obs %.0f normalise %.0f) cycles/step\n",
+                fprintf(stderr, "[fb2 flow prof] cta %3d steps %lld | pkt-wait %.0f  A-proc+sync %.0f  B(mma+send) %.0f | C-wait %.0f  C-proc %.0f (reduce %.0f obs|bar1 %.0f normalise %.0f) cycles/step\n",
                         c, h[c * 8 + 5], h[c * 8 + 0] / n, h[c * 8 + 1] / n, h[c * 8 + 2] / n, h[c * 8 + 3] / n, h[c * 8 + 4] / n,
                         h[c * 8 + 6] / n, h[c * 8 + 7] / n, h[(FLOW_PROF_CTAS / 2 + c / 2) * 8 + (c & 1)] / n);
         }

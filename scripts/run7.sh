@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+timeout 300 python scripts/flowtime.py > gpurun_out/flowtime_e.log 2>&1
+timeout 300 python scripts/flowprof.py > gpurun_out/flowprof_e.log 2>&1
+cat gpurun_out/flowtime_e.log gpurun_out/flowprof_e.log | head -5
+timeout 1500 python -m pytest tests/test_gpu_discrete.py tests/test_gpu_fuzz.py -x -q > gpurun_out/t_discrete.log 2>&1; tail -4 gpurun_out/t_discrete.log

@@ -432,6 +432,97 @@ def test_hmm_forward_flow_unaligned_state_count(fb):
     rel_close(got, want, rtol=RTOL, atol=1.0)
 
 
+# ------------------------------------------------------------------ two-hop kernel, one chain group, 512 < S <= 1024 (BASELINE config 2's shape):
+# 4-byte self-validating words in fragment order + TF32 main product with bf16 side products (hmm_flow_forward<8,2,8,true>)
+def _flow4_scenario(name):
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    if name == "extreme_observations":
+        return _flow_case(4, 60, 640, seed=24, obs_scale=150.0, obs_shift=-900.0)
+    if name == "neg_inf":
+        B, T, S = 4, 20, 1001
+        init = torch.randn(B, S, generator=g)
+        A = torch.randn(S, S, generator=g)
+        A[0, 1] = -float("inf")
+        A[:, 4] = -float("inf")  # unreachable state
+        A[:, 64:72] = -float("inf")  # a whole column group unreachable
+        A[:, 512:640] = -float("inf")  # a whole K-slice of the message stays zero
+        obs = torch.randn(B, T, S, generator=g)
+        obs[1, 3, 2] = -float("inf")
+        obs[2, 5, :] = -float("inf")  # impossible observation -> logZ = -inf, not NaN
+        init[3, :] = -float("inf")
+        init[3, 7] = 0.0  # deterministic start
+        return init, A, obs
+    if name == "sparse_left_to_right":
+        B, T, S = 3, 90, 800
+        A = torch.full((S, S), -float("inf"))
+        for i in range(S):
+            A[i, i] = np.log(0.6)
+            A[i, (i + 1) % S] = np.log(0.4)
+        init = torch.full((B, S), -float("inf"))
+        init[:, 0] = 0.0
+        return init, A, torch.randn(B, T, S, generator=g) * 3
+    if name == "large_magnitude_init":
+        init, A, obs = _flow_case(5, 40, 520, seed=28)
+        return init - 65000.0 + torch.arange(5)[:, None] * 30000.0, A, obs
+    if name == "unaligned_state_count":
+        return _flow_case(3, 30, 901, seed=29)
+    if name == "peaked_messages":  # near-deterministic emissions: one or two states carry the message, no averaging over the side products
+        init, A, obs = _flow_case(16, 50, 1024, seed=30)
+        obs = obs * 0.1
+        hot = torch.randint(0, 1024, (16, 50), generator=g)
+        obs.scatter_(2, hot[..., None], 40.0)
+        return init, A, obs
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["extreme_observations", "neg_inf", "sparse_left_to_right", "large_magnitude_init", "unaligned_state_count",
+                                  "peaked_messages"])
+def test_hmm_forward_flow_four_byte_words(fb, name):
+    import os
+
+    init, A, obs = _flow4_scenario(name)
+    n0 = fb.launch_count(reset=True)
+    got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    assert fb.launch_count() == 3, "expected colmax + flow + finalise launches, i.e. the dataflow path"
+    want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    assert not np.isnan(got).any()
+    rel_close(got, want, rtol=RTOL, atol=1.0)
+    os.environ["FB2_FLOW_PK4"] = "0"  # the 8-byte packet / 3xTF32 form of the same kernel
+    try:
+        old = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    finally:
+        os.environ.pop("FB2_FLOW_PK4")
+    rel_close(got, old, rtol=RTOL, atol=1.0)
+
+
+def test_hmm_forward_flow_four_byte_words_tight_short_chain(fb):
+    """Short chains have small |logZ|: TF32 main product + bf16 side products must hold fp32-class accuracy (2e-5 of 1 + |logZ|
+    is the bound the 3xTF32 kernels are held to; measured here per step through the filtered messages as well)."""
+    init, A, obs = _flow_case(16, 8, 1024, seed=32)
+    got, alpha = fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda(), return_alpha=True)
+    want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    assert np.max(np.abs(host(got) - want)) < 2e-5 * (1 + np.max(np.abs(want)))
+    # filtered messages against a float64 recurrence: every entry within 60 nats of its row maximum to 2e-5 absolute in the log
+    a = init.double()
+    for t in range(8):
+        a = torch.logsumexp(a[:, :, None] + A.double()[None], 1) + obs[:, t].double()
+        d = (alpha[:, t].double().cpu() - a).abs()
+        live = a > a.max(-1, keepdim=True).values - 60.0
+        assert d[live].max().item() < 2e-5, (t, d[live].max().item())
+
+
+def test_hmm_forward_flow_four_byte_words_stamp_wrap(fb):
+    """T > 65536 wraps the 16-bit stamp of the exponent words (the data words carry one stamp bit); closed form for uniform transitions."""
+    B, T, S = 2, 70001, 640
+    g = torch.Generator(device="cuda").manual_seed(37)
+    obs = torch.randn(B, T, S, device="cuda", generator=g)
+    init = torch.randn(B, S, device="cuda", generator=g).log_softmax(-1)
+    A = torch.full((S, S), -float(np.log(S)), device="cuda")
+    got = fb.hmm_forward(init, A, obs)
+    want = torch.logsumexp(init.double(), -1) + (torch.logsumexp(obs.double(), -1) - np.log(S)).sum(-1)
+    rel_close(host(got), host(want), rtol=RTOL)
+
+
 # ------------------------------------------------------------------ streaming max-plus kernel (Viterbi, S >= 256, shared A)
 @pytest.mark.parametrize("B,T,S", [(1, 60, 4096), (5, 40, 1000), (4, 25, 257), (2, 33, 300), (9, 7, 512)])
 def test_viterbi_stream_bit_exact(fb, B, T, S):
