@@ -588,6 +588,7 @@ struct HomogLevelsArgs {
     int32_t* flag;
     int64_t T;
     int D, NL;
+    int l_begin, l_end;  // levels [l_begin, l_end) are computed by this launch (earlier ones are replayed for their bookkeeping only)
 };
 
 template <int DT>
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(64) gaussian_homog_levels(HomogLevelsArgs a) {
     const float* cur_tail = nullptr;
     bool has_tail = false;
     int64_t d = a.T;
-    for (int l = 0; d > 1; ++l) {
+    for (int l = 0; d > 1 && l < a.l_end; ++l) {
         const int64_t npairs = d / 2;
         const bool odd = d & 1;
         const bool tail_pair = has_tail && !odd;
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(64) gaussian_homog_levels(HomogLevelsArgs a) {
         float* next_reg = a.Lreg + (b * a.NL + l) * nn;
         float* next_tail = a.Ltail + (b * a.NL + l) * nn;
         const size_t op = ((size_t)b * a.NL + l) * 2 + warp;
-        if ((warp == 0 && reg_pairs > 0) || (warp == 1 && tail_pair)) {
+        if (l >= a.l_begin && ((warp == 0 && reg_pairs > 0) || (warp == 1 && tail_pair))) {
             gauss_pair_body<DT, false, true>(cur_reg, warp == 0 ? cur_reg : cur_tail, a.zeros, a.zeros, 0.f, 0.f, D, warp == 0 ? next_reg : next_tail,
                                              a.scratch + (b * 2 + warp) * n, a.konst + op, a.flag, sm2[warp], lane, a.opU + op * DT * 2 * DT,
                                              a.opLinv + op * DT * DT);
@@ -624,6 +625,7 @@ __global__ void __launch_bounds__(64) gaussian_homog_levels(HomogLevelsArgs a) {
         cur_reg = next_reg;
         d = (d + 1) / 2;
     }
+    if (d > 1) return;  // the launch that reaches the top of the tree writes the result
     const float* res = has_tail ? cur_tail : cur_reg;
     for (size_t i = threadIdx.x; i < nn; i += blockDim.x) a.Lo[b * nn + i] = res[i];
 }
@@ -814,7 +816,7 @@ static int homog_chain_run(const float* Lam, const float* eta, const float* c, i
     const HomogLayout lay = homog_layout(workspace, workspace_bytes, B, T, D, DT, keep);
     const int n = 2 * D;
     HomogLevelsArgs la;
-    la.Lam = Lam; la.T = T; la.D = D; la.NL = NL; la.Lo = Lo;
+    la.Lam = Lam; la.T = T; la.D = D; la.NL = NL; la.Lo = Lo; la.l_begin = 0; la.l_end = NL + 1;
     la.Lreg = lay.Lreg; la.Ltail = lay.Ltail; la.opU = lay.opU; la.opLinv = lay.opLinv; la.konst = lay.konst;
     float* zeros = lay.zeros;
     la.zeros = zeros;
@@ -1496,7 +1498,9 @@ __host__ __device__ constexpr int kt_const_floats() { return OT * OT + 2 * DT * 
 template <int DT>
 __host__ __device__ constexpr int kt_level_floats() { return DT * DT + DT * 2 * DT; }
 
-template <int DT, int OT>
+// NTL = tiles per thread (consecutive tiles, processed in lock step): every broadcast LDS.128 of operator entries then feeds 4 NTL FMAs.
+// With one tile per thread the kernel is bound by shared-memory operand bandwidth (one LDS.128 per 4 FMAs: ~35 % of the FMA rate measured).
+template <int DT, int OT, int NTL>
 __global__ void __launch_bounds__(KT_THREADS, 2) gaussian_kalman_tile(KalmanTileArgs a) {
     extern __shared__ __align__(16) float kt_smem[];
     float* sPr = kt_smem;                 // [o_in][o_out]
@@ -1528,60 +1532,83 @@ __global__ void __launch_bounds__(KT_THREADS, 2) gaussian_kalman_tile(KalmanTile
         if (threadIdx.x == 0) sk[l] = a.konst[op];
     }
     __syncthreads();
-    const int64_t tile = (int64_t)blockIdx.x * KT_THREADS + threadIdx.x;
-    if (tile >= a.ntiles) return;
+    const int64_t tile0 = ((int64_t)blockIdx.x * KT_THREADS + threadIdx.x) * NTL;
+    if (tile0 >= a.ntiles) return;
     const float c0 = a.c0[b];
-    const float* yp = a.y + (b * a.T + (tile << K)) * O;
+    const float* yp[NTL];
+    bool live[NTL];
+#pragma unroll
+    for (int q = 0; q < NTL; ++q) {
+        live[q] = tile0 + q < a.ntiles;
+        yp[q] = a.y + (b * a.T + ((live[q] ? tile0 + q : tile0) << K)) * O;  // a missing last tile repeats its neighbour (not stored)
+    }
     const bool yvec = (O == OT) && (reinterpret_cast<uintptr_t>(a.y) % 16 == 0);
-    float4 stk[KT_KMAX][2 * DT / 4];  // pending left operands, one per level (local memory: indexed by the run-time level)
-    float stc[KT_KMAX];
-    float cur[2 * DT], cc = 0.f;
-    float yv[OT];
-    auto load_y = [&](const float* src) {
-        if (yvec) {
+    float4 stk[NTL][KT_KMAX][2 * DT / 4];  // pending left operands, one per level (local memory: indexed by the run-time level)
+    float stc[NTL][KT_KMAX];
+    float cur[NTL][2 * DT], cc[NTL];
+    float yv[NTL][OT];
+    auto load_y = [&](int step) {
 #pragma unroll
-            for (int o = 0; o < OT; o += 4) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(src + o));
-                yv[o] = v.x; yv[o + 1] = v.y; yv[o + 2] = v.z; yv[o + 3] = v.w;
+        for (int q = 0; q < NTL; ++q) {
+            const float* src = yp[q] + (size_t)step * O;
+            if (yvec) {
+#pragma unroll
+                for (int o = 0; o < OT; o += 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + o));
+                    yv[q][o] = v.x; yv[q][o + 1] = v.y; yv[q][o + 2] = v.z; yv[q][o + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int o = 0; o < OT; ++o) yv[q][o] = o < O ? __ldg(src + o) : 0.f;
             }
-        } else {
-#pragma unroll
-            for (int o = 0; o < OT; ++o) yv[o] = o < O ? __ldg(src + o) : 0.f;
         }
     };
-    load_y(yp);
+    load_y(0);
     const int nsteps = 1 << K;
 #pragma unroll 1
     for (int i = 0; i < nsteps; ++i) {
         // ---- element of step i: u = wo + y Pr, eta = a0 + Po u, c = c0 - |u|^2 / 2
-        float u[OT];
+        float u[NTL][OT];
 #pragma unroll
-        for (int o = 0; o < OT; ++o) u[o] = swo[o];
+        for (int q = 0; q < NTL; ++q)
+#pragma unroll
+            for (int o = 0; o < OT; ++o) u[q][o] = swo[o];
 #pragma unroll
         for (int oi = 0; oi < OT; ++oi) {
 #pragma unroll
             for (int o4 = 0; o4 < OT; o4 += 4) {
                 const float4 p = *reinterpret_cast<const float4*>(&sPr[oi * OT + o4]);
-                u[o4] = fmaf(yv[oi], p.x, u[o4]);
-                u[o4 + 1] = fmaf(yv[oi], p.y, u[o4 + 1]);
-                u[o4 + 2] = fmaf(yv[oi], p.z, u[o4 + 2]);
-                u[o4 + 3] = fmaf(yv[oi], p.w, u[o4 + 3]);
+#pragma unroll
+                for (int q = 0; q < NTL; ++q) {
+                    u[q][o4] = fmaf(yv[q][oi], p.x, u[q][o4]);
+                    u[q][o4 + 1] = fmaf(yv[q][oi], p.y, u[q][o4 + 1]);
+                    u[q][o4 + 2] = fmaf(yv[q][oi], p.z, u[q][o4 + 2]);
+                    u[q][o4 + 3] = fmaf(yv[q][oi], p.w, u[q][o4 + 3]);
+                }
             }
         }
-        if (i + 1 < nsteps) load_y(yp + (size_t)(i + 1) * O);  // next step's observations travel while this step computes
-        float uu = 0.f;
+        if (i + 1 < nsteps) load_y(i + 1);  // next step's observations travel while this step computes
 #pragma unroll
-        for (int o = 0; o < OT; ++o) uu = fmaf(u[o], u[o], uu);
-        cc = c0 - 0.5f * uu;
+        for (int q = 0; q < NTL; ++q) {
+            float uu = 0.f;
 #pragma unroll
-        for (int q = 0; q < 2 * DT; ++q) {
-            float acc = sa0[q];
+            for (int o = 0; o < OT; ++o) uu = fmaf(u[q][o], u[q][o], uu);
+            cc[q] = c0 - 0.5f * uu;
+        }
+#pragma unroll
+        for (int r = 0; r < 2 * DT; ++r) {
+            float acc[NTL];
+#pragma unroll
+            for (int q = 0; q < NTL; ++q) acc[q] = sa0[r];
 #pragma unroll
             for (int o4 = 0; o4 < OT; o4 += 4) {
-                const float4 p = *reinterpret_cast<const float4*>(&sPo[q * OT + o4]);
-                acc = fmaf(u[o4], p.x, fmaf(u[o4 + 1], p.y, fmaf(u[o4 + 2], p.z, fmaf(u[o4 + 3], p.w, acc))));
+                const float4 p = *reinterpret_cast<const float4*>(&sPo[r * OT + o4]);
+#pragma unroll
+                for (int q = 0; q < NTL; ++q)
+                    acc[q] = fmaf(u[q][o4], p.x, fmaf(u[q][o4 + 1], p.y, fmaf(u[q][o4 + 2], p.z, fmaf(u[q][o4 + 3], p.w, acc[q]))));
             }
-            cur[q] = acc;
+#pragma unroll
+            for (int q = 0; q < NTL; ++q) cur[q][r] = acc[q];
         }
         // ---- fold the finished subtrees: one combine per trailing one-bit of i
         int lvl = 0;
@@ -1589,63 +1616,103 @@ __global__ void __launch_bounds__(KT_THREADS, 2) gaussian_kalman_tile(KalmanTile
         for (int m = i; m & 1; m >>= 1, ++lvl) {
             const float* sLi = sops + (size_t)lvl * kt_level_floats<DT>();
             const float* sU = sLi + DT * DT;
-            float z[DT];
+            float z[NTL][DT];
+            float cxy[NTL], vv[NTL];
 #pragma unroll
-            for (int k4 = 0; k4 < DT / 4; ++k4) {
-                const float4 xa = stk[lvl][k4], xb = stk[lvl][DT / 4 + k4];
-                z[4 * k4] = xb.x + cur[4 * k4];
-                z[4 * k4 + 1] = xb.y + cur[4 * k4 + 1];
-                z[4 * k4 + 2] = xb.z + cur[4 * k4 + 2];
-                z[4 * k4 + 3] = xb.w + cur[4 * k4 + 3];
-                cur[4 * k4] = xa.x; cur[4 * k4 + 1] = xa.y; cur[4 * k4 + 2] = xa.z; cur[4 * k4 + 3] = xa.w;
+            for (int q = 0; q < NTL; ++q) {
+#pragma unroll
+                for (int k4 = 0; k4 < DT / 4; ++k4) {
+                    const float4 xa = stk[q][lvl][k4], xb = stk[q][lvl][DT / 4 + k4];
+                    z[q][4 * k4] = xb.x + cur[q][4 * k4];
+                    z[q][4 * k4 + 1] = xb.y + cur[q][4 * k4 + 1];
+                    z[q][4 * k4 + 2] = xb.z + cur[q][4 * k4 + 2];
+                    z[q][4 * k4 + 3] = xb.w + cur[q][4 * k4 + 3];
+                    cur[q][4 * k4] = xa.x; cur[q][4 * k4 + 1] = xa.y; cur[q][4 * k4 + 2] = xa.z; cur[q][4 * k4 + 3] = xa.w;
+                }
+                cxy[q] = stc[q][lvl] + cc[q];
+                vv[q] = 0.f;
             }
-            const float cxy = stc[lvl] + cc;
-            float vv = 0.f;
 #pragma unroll
             for (int r = 0; r < DT; ++r) {
-                float v = 0.f;
+                float v[NTL];
+#pragma unroll
+                for (int q = 0; q < NTL; ++q) v[q] = 0.f;
 #pragma unroll
                 for (int k = 0; k < DT; k += 4) {
                     if (k <= r) {
                         const float4 l = *reinterpret_cast<const float4*>(&sLi[r * DT + k]);
-                        v = fmaf(l.x, z[k], fmaf(l.y, z[k + 1], fmaf(l.z, z[k + 2], fmaf(l.w, z[k + 3], v))));
+#pragma unroll
+                        for (int q = 0; q < NTL; ++q)
+                            v[q] = fmaf(l.x, z[q][k], fmaf(l.y, z[q][k + 1], fmaf(l.z, z[q][k + 2], fmaf(l.w, z[q][k + 3], v[q]))));
                     }
                 }
-                vv = fmaf(v, v, vv);
+#pragma unroll
+                for (int q = 0; q < NTL; ++q) vv[q] = fmaf(v[q], v[q], vv[q]);
 #pragma unroll
                 for (int c = 0; c < 2 * DT; c += 4) {
                     const float4 uo = *reinterpret_cast<const float4*>(&sU[r * 2 * DT + c]);
-                    cur[c] = fmaf(-uo.x, v, cur[c]);
-                    cur[c + 1] = fmaf(-uo.y, v, cur[c + 1]);
-                    cur[c + 2] = fmaf(-uo.z, v, cur[c + 2]);
-                    cur[c + 3] = fmaf(-uo.w, v, cur[c + 3]);
+#pragma unroll
+                    for (int q = 0; q < NTL; ++q) {
+                        cur[q][c] = fmaf(-uo.x, v[q], cur[q][c]);
+                        cur[q][c + 1] = fmaf(-uo.y, v[q], cur[q][c + 1]);
+                        cur[q][c + 2] = fmaf(-uo.z, v[q], cur[q][c + 2]);
+                        cur[q][c + 3] = fmaf(-uo.w, v[q], cur[q][c + 3]);
+                    }
                 }
             }
-            cc = cxy + sk[lvl] + 0.5f * vv;
+#pragma unroll
+            for (int q = 0; q < NTL; ++q) cc[q] = cxy[q] + sk[lvl] + 0.5f * vv[q];
         }
         if (i + 1 < nsteps) {
 #pragma unroll
-            for (int k4 = 0; k4 < 2 * DT / 4; ++k4) stk[lvl][k4] = make_float4(cur[4 * k4], cur[4 * k4 + 1], cur[4 * k4 + 2], cur[4 * k4 + 3]);
-            stc[lvl] = cc;
-        }
-    }
-    float* eo = a.eout + (b * a.out_T + tile) * n;
-    if (D == DT && reinterpret_cast<uintptr_t>(a.eout) % 16 == 0) {
+            for (int q = 0; q < NTL; ++q) {
 #pragma unroll
-        for (int k4 = 0; k4 < 2 * DT / 4; ++k4)
-            reinterpret_cast<float4*>(eo)[k4] = make_float4(cur[4 * k4], cur[4 * k4 + 1], cur[4 * k4 + 2], cur[4 * k4 + 3]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < DT; ++k) {
-            if (k < D) {
-                eo[k] = cur[k];
-                eo[D + k] = cur[DT + k];
+                for (int k4 = 0; k4 < 2 * DT / 4; ++k4)
+                    stk[q][lvl][k4] = make_float4(cur[q][4 * k4], cur[q][4 * k4 + 1], cur[q][4 * k4 + 2], cur[q][4 * k4 + 3]);
+                stc[q][lvl] = cc[q];
             }
         }
     }
-    a.cout[b * a.out_T + tile] = cc;
+#pragma unroll
+    for (int q = 0; q < NTL; ++q) {
+        if (!live[q]) continue;
+        float* eo = a.eout + (b * a.out_T + tile0 + q) * n;
+        if (D == DT && reinterpret_cast<uintptr_t>(a.eout) % 16 == 0) {
+#pragma unroll
+            for (int k4 = 0; k4 < 2 * DT / 4; ++k4)
+                reinterpret_cast<float4*>(eo)[k4] = make_float4(cur[q][4 * k4], cur[q][4 * k4 + 1], cur[q][4 * k4 + 2], cur[q][4 * k4 + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < DT; ++k) {
+                if (k < D) {
+                    eo[k] = cur[q][k];
+                    eo[D + k] = cur[q][DT + k];
+                }
+            }
+        }
+        a.cout[b * a.out_T + tile0 + q] = cc[q];
+    }
 }
 
+// A side stream per device and host thread (the fork / join events belong to one call at a time).
+struct GaussSide {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int gauss_side_for_current_device(GaussSide** out) {
+    static thread_local GaussSide table[64];
+    int dev = 0;
+    FB2_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return FB2_ERR_UNSUPPORTED;
+    GaussSide& s = table[dev];
+    if (!s.stream) {
+        FB2_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        FB2_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+        FB2_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    }
+    *out = &s;
+    return FB2_OK;
+}
 
 static int kalman_pref_levels() {
     const char* e = getenv("FB2_KALMAN_K");  // tree levels fused into gaussian_kalman_tile (tile = 2^K steps per thread)
@@ -1708,8 +1775,27 @@ static int kalman_chain_run(const float* y, const float* Lam, const float* Pr, c
     la.zeros = lay.zeros; la.scratch = lay.scratch; la.flag = lay.flag;
     FB2_CUDA(cudaMemsetAsync(la.flag, 0, sizeof(int32_t), stream));
     FB2_CUDA(cudaMemsetAsync(lay.zeros, 0, (size_t)n * 4, stream));
+    // The precision operators are a serial chain of NL small factorisations per chain (one CTA each): the first K levels are all the tile
+    // kernel needs, the rest runs on a side stream next to it and is joined before the level-K sweeps.
+    GaussSide* side = nullptr;
+    const char* side_env = getenv("FB2_KALMAN_SIDE");  // off by default: measured 2.92 -> 2.91 ms at C4 (the tile kernel fills the SMs either way)
+    const bool use_side = NL > K && side_env && side_env[0] == '1' && gauss_side_for_current_device(&side) == FB2_OK;
+    la.l_begin = 0; la.l_end = use_side ? K : NL + 1;
     gaussian_homog_levels<DT><<<(unsigned)B, 64, 0, stream>>>(la);
     FB2_LAUNCH_CHECK();
+    if (use_side) {
+        FB2_CUDA(cudaEventRecord(side->fork, stream));
+        FB2_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        la.l_begin = K; la.l_end = NL + 1;
+        gaussian_homog_levels<DT><<<(unsigned)B, 64, 0, side->stream>>>(la);
+        cudaError_t le = cudaGetLastError();
+        cudaEventRecord(side->join, side->stream);  // joined below even on failure: the caller's stream never runs ahead of the side stream
+        if (le != cudaSuccess) {
+            cudaStreamWaitEvent(stream, side->join, 0);
+            set_error("gaussian_kalman_chain: side-stream launch failed: %s", cudaGetErrorString(le));
+            return FB2_ERR_CUDA;
+        }
+    }
 
     // level-K arrays: [B, dK, n] / [B, dK] (the chain result itself when dK == 1)
     float* kE = dK == 1 ? eo : lay.lkE[0];
@@ -1720,9 +1806,17 @@ static int kalman_chain_run(const float* y, const float* Lam, const float* Pr, c
         ta.opU = la.opU; ta.opLinv = la.opLinv; ta.konst = la.konst;
         ta.eout = kE; ta.cout = kC; ta.T = T; ta.ntiles = nfull; ta.out_T = dK; ta.D = D; ta.O = O; ta.K = K; ta.NL = NL;
         const size_t smem = ((size_t)kt_const_floats<DT, 16>() + (size_t)K * kt_level_floats<DT>()) * sizeof(float);
-        FB2_CUDA(cudaFuncSetAttribute(gaussian_kalman_tile<DT, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gaussian_kalman_tile<DT, 16><<<dim3((unsigned)ceil_div(nfull, KT_THREADS), (unsigned)B), KT_THREADS, smem, stream>>>(ta);
-        FB2_LAUNCH_CHECK();
+        // One tile per thread.  Two tiles per thread (NTL = 2: every operator load feeds 8 FMAs) was measured at C4: 4.1 ms against 2.9 ms --
+        // 255 registers with spills and half as many threads cost more than the halved shared-memory traffic gains.
+        FB2_CUDA(cudaFuncSetAttribute(gaussian_kalman_tile<DT, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gaussian_kalman_tile<DT, 16, 1><<<dim3((unsigned)ceil_div(nfull, KT_THREADS), (unsigned)B), KT_THREADS, smem, stream>>>(ta);
+        const cudaError_t le = cudaGetLastError();
+        // join here: everything enqueued from now on waits for the side stream, the tile kernel above runs next to it
+        if (use_side) cudaStreamWaitEvent(stream, side->join, 0);
+        if (le != cudaSuccess) {
+            set_error("gaussian_kalman_chain: tile kernel launch failed: %s", cudaGetErrorString(le));
+            return FB2_ERR_CUDA;
+        }
     }
     HomogEtaArgs ea;
     ea.D = D; ea.op_stride = (int64_t)NL * 2;

@@ -1,4 +1,4 @@
-"""C4 (Kalman, D=32, O=16, B=64, T=100000): fused tile path for K = 1..6 against the level-by-level path."""
+"""C4 (Kalman, D=32, O=16, B=64, T=100000): fused tile path for K / tiles-per-thread / side stream against the level-by-level path."""
 import os, sys, time
 sys.path.insert(0, "/root/repo")
 import torch
@@ -31,9 +31,14 @@ print("level-by-level: %.3f ms" % timeit(lambda: fg.kalman_chain(*args, validate
 os.environ["FB2_KALMAN_FUSED"] = "1"
 consts = fg.kalman_constants(*args[:6])
 print("constants kernel: %.3f ms" % timeit(lambda: fg.kalman_constants(*args[:6])))
-for K in (1, 2, 3, 4, 5, 6):
-    os.environ["FB2_KALMAN_K"] = str(K)
-    got = fg.kalman_chain(*args)
-    err = max((a - b).abs().max().item() / max(b.abs().max().item(), 1.0) for a, b in zip(got, ref))
-    print("K=%d fused total: %.3f ms   chain only: %.3f ms   rel err vs level path %.2e" % (
-        K, timeit(lambda: fg.kalman_chain(*args, validate=False)), timeit(lambda: fg.kalman_chain_fused(consts, args[6], validate=False)), err))
+for ntl in ("1", "2"):
+    for side in ("0", "1"):
+        for K in (3, 4, 5):
+            os.environ["FB2_KALMAN_K"] = str(K)
+            os.environ["FB2_KALMAN_NTL"] = ntl
+            os.environ["FB2_KALMAN_SIDE"] = side
+            got = fg.kalman_chain(*args)
+            exact = all(torch.equal(a, b) for a, b in zip(got, fg.gaussian_chain_info_homog(*fg.kalman_eta_from_constants(consts, args[6]))))
+            err = max((a - b).abs().max().item() / max(b.abs().max().item(), 1.0) for a, b in zip(got, ref))
+            print("tiles/thread=%s side=%s K=%d total: %.3f ms   chain only: %.3f ms   bit-identical to the level path: %s   rel err vs torch-constants path %.2e" % (
+                ntl, side, K, timeit(lambda: fg.kalman_chain(*args, validate=False)), timeit(lambda: fg.kalman_chain_fused(consts, args[6], validate=False)), exact, err))
