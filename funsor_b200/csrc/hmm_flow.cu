@@ -78,11 +78,9 @@ struct FlowArgs {
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t cvt_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// fp32 -> TF32, round to nearest, ties away from zero (= cvt.rna.tf32.f32 for every finite input; inf / NaN stay non-finite).  Two integer
+// instructions: ptxas expands cvt.rna.tf32 into ~6 (the staging phase of the dataflow kernels is ALU-issue bound).
+__device__ __forceinline__ uint32_t cvt_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
