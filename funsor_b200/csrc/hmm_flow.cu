@@ -307,7 +307,7 @@ constexpr float kScalePl = 16777216.f, kUnscalePl = 1.f / 16777216.f;
 template <int K16, int NT, int CL = 8, bool PK4 = false>
 __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) {
     constexpr bool HALFK = CL == 4;
-    static_assert(!PK4 || (CL == 8 && K16 == 8), "4-byte words: clusters of 8, 16 k8-steps per K-slice");
+    static_assert(!PK4 || (CL == 8 && (K16 == 8 || K16 == 4)), "4-byte words: clusters of 8, 16 or 8 k8-steps per K-slice");
     constexpr int SP = K16 * 128;         // padded state count
     constexpr int KS = SP / CL;           // rows of P (= message entries) per CTA
     constexpr int NG = KS / 8;            // producer groups (8 columns each) in this CTA's K-slice
@@ -493,16 +493,18 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
 
             // ================= phase A: fetch this CTA's K-slice of the message =================
             if constexpr (PK4) {
-                // thread tid holds lane `lane` of the A fragments of k8-steps warp and warp + 8, and exponent word tid = (k8-step tid >> 4, chain tid & 15)
+                // thread tid < 16 NG holds lane `lane` of the A fragments of k8-steps warp and warp + NG / 2, and exponent word tid = (k8-step
+                // tid >> 4, chain tid & 15); with 8 k8-steps per slice (S <= 512) warps 4-7 only take part in the barriers
                 const uint32_t* dsl = data_set + ((size_t)(tau & 1) * FLOW_CLUSTER + rank) * NG * 128;
                 const uint32_t* esl = expo_set + ((size_t)(tau & 1) * FLOW_CLUSTER + rank) * NG * 16;
                 const uint32_t want_bit = (tau >> 1) & 1u, want16 = tau & 0xFFFFu;
-                uint4 f0, f1;
-                uint32_t ew;
+                uint4 f0 = make_uint4(0, 0, 0, 0), f1 = f0;
+                uint32_t ew = 0;
                 const long long start = clock64();
+                const bool stager = tid < NG * 16;
                 auto fetch = [&](uint4& a0, uint4& a1, uint32_t& e) {
                     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a0.x), "=r"(a0.y), "=r"(a0.z), "=r"(a0.w) : "l"(dsl + tid * 4) : "memory");
-                    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w) : "l"(dsl + (tid + 256) * 4) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w) : "l"(dsl + (tid + NG * 16) * 4) : "memory");
                     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(esl + tid) : "memory");
                 };
                 auto valid = [&](const uint4& a0, const uint4& a1, uint32_t e) {
@@ -510,28 +512,8 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                     const uint32_t all_or = a0.x | a0.y | a0.z | a0.w | a1.x | a1.y | a1.z | a1.w;
                     return ((want_bit ? all_and : ~all_or) & 1u) && (e >> 16) == want16;
                 };
-                if (p.mode & 32) {
-                    // two probe sets in flight, half a round trip apart: a word that lands right after one probe was served is seen by the
-                    // other ~350 cycles later instead of a full round trip later (the step is a chip-wide maximum over all polling threads)
-                    uint4 g0, g1;
-                    uint32_t gw;
-                    fetch(f0, f1, ew);
-                    spin_cycles(330);
-                    fetch(g0, g1, gw);
-                    for (;;) {
-                        if (valid(f0, f1, ew)) break;
-                        fetch(f0, f1, ew);
-                        if (valid(g0, g1, gw)) {
-                            f0 = g0; f1 = g1; ew = gw;
-                            break;
-                        }
-                        fetch(g0, g1, gw);
-                        if (clock64() - start > FLOW_SPIN_LIMIT) {
-                            timed_out = 1;
-                            break;
-                        }
-                    }
-                } else
+                // (Two probe sets kept in flight half a round trip apart were measured with this format too: no change, 3.26 vs 3.25 us/step.)
+                if (stager)
                 for (;;) {
                     fetch(f0, f1, ew);
                     if (valid(f0, f1, ew)) break;
@@ -549,25 +531,29 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                     }
                 }
                 if (p.prof) c_pkt = clock64();
-                s_ex[tid & 15][tid >> 4] = (int)(ew << 17) | (int)((ew >> 15) & 1u);
+                if (stager) s_ex[tid & 15][tid >> 4] = (int)(ew << 17) | (int)((ew >> 15) & 1u);
                 if (tid < 16) s_ex[tid][16] = (int)(ew << 17);
                 __syncthreads();
                 if (p.prof) c_bar1 = clock64();
+                if (stager) {
                 // align the block exponents of the slice's 16 column groups, per chain.  Every warp: lane -> (chain lane & 15, half lane >> 4)
                 // takes the maximum over 8 groups relative to group 0, the halves are merged by one shuffle, and a lane fetches (ref, max) of
                 // the chains g and g + 8 of its fragments by shuffle (the first version let every thread scan all 16 words of both chains:
                 // ~190 ALU instructions per thread, ~770 cycles of ALU issue per step).
                 float sc[2][2];
                 {
+                    constexpr int GH = NG / 2;  // column groups per half-warp
                     const int chn = lane & 15, hf = lane >> 4;
                     const int ref_l = s_ex[chn][16];
-                    const int4 ea4 = *reinterpret_cast<const int4*>(&s_ex[chn][8 * hf]), eb4 = *reinterpret_cast<const int4*>(&s_ex[chn][8 * hf + 4]);
-                    const int own[2][2] = {{s_ex[g][warp], s_ex[g][warp + 8]}, {s_ex[g + 8][warp], s_ex[g + 8][warp + 8]}};
-                    const int e8[8] = {ea4.x, ea4.y, ea4.z, ea4.w, eb4.x, eb4.y, eb4.z, eb4.w};
-                    int d8[8];
+                    const int own[2][2] = {{s_ex[g][warp], s_ex[g][warp + GH]}, {s_ex[g + 8][warp], s_ex[g + 8][warp + GH]}};
+                    int m_l = INT_MIN;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) d8[q] = (e8[q] & 1) ? INT_MIN : e8[q] - ref_l;  // = sext15(E - ref) << 17
-                    int m_l = max(max(max(d8[0], d8[1]), max(d8[2], d8[3])), max(max(d8[4], d8[5]), max(d8[6], d8[7])));
+                    for (int q4 = 0; q4 < GH / 4; ++q4) {
+                        const int4 e4 = *reinterpret_cast<const int4*>(&s_ex[chn][GH * hf + 4 * q4]);
+                        const int d0 = (e4.x & 1) ? INT_MIN : e4.x - ref_l, d1 = (e4.y & 1) ? INT_MIN : e4.y - ref_l;  // = sext15(E - ref) << 17
+                        const int d2 = (e4.z & 1) ? INT_MIN : e4.z - ref_l, d3 = (e4.w & 1) ? INT_MIN : e4.w - ref_l;
+                        m_l = max(m_l, max(max(d0, d1), max(d2, d3)));
+                    }
                     m_l = max(m_l, __shfl_xor_sync(0xffffffffu, m_l, 16));
                     if (warp == 0 && lane < 16)
                         s_erefloc[buf][lane] = (m_l == INT_MIN) ? (0x8000 | (int)((unsigned)ref_l >> 17)) : (int)((unsigned)(ref_l + m_l) >> 17);
@@ -604,11 +590,12 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 const uint4 bh = make_uint4(pack_bf16(v[0][0], v[0][2]), pack_bf16(v[0][1], v[0][3]), pack_bf16(v[1][0], v[1][2]),
                                             pack_bf16(v[1][1], v[1][3]));
                 unsigned char* d0 = &s_frag[buf][warp][0] + lane * 32;
-                unsigned char* d1 = &s_frag[buf][warp + 8][0] + lane * 32;
+                unsigned char* d1 = &s_frag[buf][warp + NG / 2][0] + lane * 32;
                 *reinterpret_cast<uint4*>(d0 + swz) = make_uint4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
                 *reinterpret_cast<uint4*>(d0 + (16 ^ swz)) = bl;
                 *reinterpret_cast<uint4*>(d1 + swz) = make_uint4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
                 *reinterpret_cast<uint4*>(d1 + (16 ^ swz)) = bh;
+                }
             } else if (tid < NA) {
                 constexpr unsigned amask = NA >= 32 ? 0xffffffffu : ((1u << (NA & 31)) - 1u);
                 const unsigned long long* src0 = pkt_set + ((size_t)(tau & 1) * FLOW_CHAINS + ga) * SP + rank * KS + pa * 8;
@@ -2257,8 +2244,13 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
     const bool legacy = !(tc_env && tc_env[0] == '1') || hist_u != nullptr || transpose || reverse || ready_flags != nullptr || cpo > 1;
     // single-hop variant (hmm_direct_forward): measured faster than the two-hop kernel for S <= 512 (1.32 / 1.86 / 2.35 vs 2.08 / 2.42 /
     // 2.66 us per step at S = 128 / 256 / 512) and slower at S = 1024 (3.68 vs 3.37: 8 MB of L2 reads per step).  FB2_FLOW_DIRECT=0|1 forces.
+    // Round 2: with 4-byte words, bf16 side products and the shared alignment work the two-hop kernel overtakes it for a single chain group
+    // at 256 < S <= 512 when a pass runs alone (2.05 vs 2.28 us per step, forward); side by side (forward-backward, two passes of 4 wide
+    // clusters each) the single-hop kernel stays ahead (2.35 vs 2.29 / 2.46 us at B = 1 / 16).
     const char* direct_env = getenv("FB2_FLOW_DIRECT");
-    const bool direct = direct_env ? direct_env[0] == '1' : fs.k16 <= 4;
+    const char* pk4_off = getenv("FB2_FLOW_PK4");
+    const bool two_hop_512 = fs.k16 == 4 && groups == 1 && !tl_in_pair && !(pk4_off && pk4_off[0] == '0');
+    const bool direct = direct_env ? direct_env[0] == '1' : (fs.k16 <= 4 && !two_hop_512);
     if (direct) {
         if (fs.k16 == 1) st = direct_launch<2>(a, stream);
         else if (fs.k16 == 2) st = direct_launch<4>(a, stream);
@@ -2275,14 +2267,17 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
         // three times as many groups run side by side (at most 15 clusters of 8 are co-resident); a single group is
         // faster with one tile per warp (less tensor work on its critical path).
         const bool wide = groups > 1 || tl_force_wide;
+        const char* pk4_env = getenv("FB2_FLOW_PK4");  // 0: 8-byte packets also for a single chain group
+        const bool pk4 = groups == 1 && !(pk4_env && pk4_env[0] == '0');
         if (fs.k16 == 1) st = wide ? flow_launch<1, 2>(a, stream) : flow_launch<1, 1>(a, stream);
         else if (fs.k16 == 2) st = wide ? flow_launch<2, 2>(a, stream) : flow_launch<2, 1>(a, stream);
-        else if (fs.k16 == 4) st = wide ? flow_launch<4, 2>(a, stream) : flow_launch<4, 1>(a, stream);
-        else {
+        else if (fs.k16 == 4) {
+            if (pk4) st = wide ? flow_launch<4, 2, 8, true>(a, stream) : flow_launch<4, 1, 8, true>(a, stream);
+            else st = wide ? flow_launch<4, 2>(a, stream) : flow_launch<4, 1>(a, stream);
+        } else {
             const char* cl4 = getenv("FB2_FLOW_CL4");  // experiment: clusters of 4 with half-K warps
-            const char* pk4 = getenv("FB2_FLOW_PK4");  // 0: 8-byte packets also for a single chain group
             if (cl4 && cl4[0] == '1') st = flow_launch<8, 1, 4>(a, stream);
-            else if (groups == 1 && !(pk4 && pk4[0] == '0')) st = flow_launch<8, 2, 8, true>(a, stream);
+            else if (pk4) st = flow_launch<8, 2, 8, true>(a, stream);
             else st = flow_launch<8, 2>(a, stream);
         }
     }
