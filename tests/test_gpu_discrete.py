@@ -524,7 +524,7 @@ def test_hmm_forward_flow_four_byte_words_stamp_wrap(fb):
 
 
 # ------------------------------------------------------------------ streaming max-plus kernel (Viterbi, S >= 256, shared A)
-@pytest.mark.parametrize("B,T,S", [(1, 60, 4096), (5, 40, 1000), (4, 25, 257), (2, 33, 300), (9, 7, 512)])
+@pytest.mark.parametrize("B,T,S", [(1, 60, 4096), (5, 40, 1000), (4, 25, 257), (2, 33, 300), (9, 7, 512), (1, 30, 2500), (2, 20, 3000), (3, 9, 2401)])
 def test_viterbi_stream_bit_exact(fb, B, T, S):
     g = torch.Generator().manual_seed(22)
     init = torch.randn(B, S, generator=g)
