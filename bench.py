@@ -320,6 +320,20 @@ def main():
         e2e = {"value": world * units_per_step_rank * n_e2e / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": int(h_obs.numel() * 4 + h_A.numel() * 4 + h_init.numel() * 4), "d2h_bytes_per_step": int(B * 4),
                "ms_per_step": e2e_s / n_e2e * 1e3, "steps": n_e2e}
+        try:  # the same bytes as one plain pinned -> device copy: when this is close to ms_per_step the end-to-end number is the PCIe link, not the kernel
+            d_tmp = torch.empty_like(obs)
+            d_tmp.copy_(h_obs, non_blocking=True)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            d_tmp.copy_(h_obs, non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize()
+            e2e["h2d_copy_alone_ms"] = c0.elapsed_time(c1)
+            e2e["h2d_copy_alone_gbs"] = h_obs.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+            del d_tmp
+        except Exception as e:
+            e2e["h2d_copy_alone_ms"] = repr(e)
         lib.fb2_host_arena_release()
         del h_obs
 

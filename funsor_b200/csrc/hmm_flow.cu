@@ -98,6 +98,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {  // {upper h
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// upper halves of two fp32 registers as one bf16 pair {hi: b, lo: a}; volatile: recomputed where it is used (ptxas otherwise hoists the 32
+// loop-invariant results of the contraction loop out of the time loop and holds them in registers for the whole pass)
+__device__ __forceinline__ uint32_t upper_halves(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm volatile("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -421,6 +428,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
         }
     };
     long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long c_prev_top = 0;
     unsigned nstep = 0;  // steps executed by this CTA (drives barrier parity and smem buffer choice)
     unsigned tau = 0;    // packet stamp counter (monotone across chain groups)
     bool aborted = false;
@@ -489,6 +497,10 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
             const unsigned ph = (nstep >> 1) & 1;
             int timed_out = 0;
             const long long c_top = p.prof ? clock64() : 0;
+            if (PK4 && p.prof && tid == FLOW_THREADS - 1) {  // PK4 report: the step period (top of this step - top of the previous one)
+                if (t > 0) prof_acc[7] += c_top - c_prev_top;
+                c_prev_top = c_top;
+            }
             long long c_pkt = c_top, c_bar1 = 0;
 
             // ================= phase A: fetch this CTA's K-slice of the message =================
@@ -689,20 +701,30 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                         for (int c = 0; c < 4; ++c) acc[nt][q][c] = 0.f;
                 const int swz = ((lane >> 2) & 1) * 16;
                 if constexpr (PK4) {
+                    uint4 nh0, nbl, nh1, nbh;  // fragments of the next k16 unit travel while this one is contracted
+                    {
+                        const unsigned char* r0 = &s_frag[buf][0][0] + lane * 32;
+                        const unsigned char* r1 = &s_frag[buf][NKS / 2][0] + lane * 32;
+                        nh0 = *reinterpret_cast<const uint4*>(r0 + swz), nbl = *reinterpret_cast<const uint4*>(r0 + (16 ^ swz));
+                        nh1 = *reinterpret_cast<const uint4*>(r1 + swz), nbh = *reinterpret_cast<const uint4*>(r1 + (16 ^ swz));
+                    }
 #pragma unroll
                     for (int j = 0; j < NKS / 2; ++j) {
-                        const unsigned char* r0 = &s_frag[buf][j][0] + lane * 32;
-                        const unsigned char* r1 = &s_frag[buf][j + NKS / 2][0] + lane * 32;
-                        const uint4 h0 = *reinterpret_cast<const uint4*>(r0 + swz), bl = *reinterpret_cast<const uint4*>(r0 + (16 ^ swz));
-                        const uint4 h1 = *reinterpret_cast<const uint4*>(r1 + swz), bh = *reinterpret_cast<const uint4*>(r1 + (16 ^ swz));
+                        const uint4 h0 = nh0, bl = nbl, h1 = nh1, bh = nbh;
+                        if (j + 1 < NKS / 2) {
+                            const unsigned char* r0 = &s_frag[buf][j + 1][0] + lane * 32;
+                            const unsigned char* r1 = &s_frag[buf][j + 1 + NKS / 2][0] + lane * 32;
+                            nh0 = *reinterpret_cast<const uint4*>(r0 + swz), nbl = *reinterpret_cast<const uint4*>(r0 + (16 ^ swz));
+                            nh1 = *reinterpret_cast<const uint4*>(r1 + swz), nbh = *reinterpret_cast<const uint4*>(r1 + (16 ^ swz));
+                        }
                         const uint32_t ah0[4] = {h0.x, h0.y, h0.z, h0.w}, ah1[4] = {h1.x, h1.y, h1.z, h1.w};
                         const uint32_t abl[4] = {bl.x, bl.y, bl.z, bl.w}, abh[4] = {bh.x, bh.y, bh.z, bh.w};
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[nt][0], ah0, Ph[nt][j][0], Ph[nt][j][1]);
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt)  // bf16 B fragment of Ph: the upper halves of the TF32 registers (slots h = 0, 1 of either k8-step)
-                            mma_bf16_k16(acc[nt][2], abl, __byte_perm(Ph[nt][j][0], Ph[nt][j][1], 0x7632),
-                                         __byte_perm(Ph[nt][j + NKS / 2][0], Ph[nt][j + NKS / 2][1], 0x7632));
+                            mma_bf16_k16(acc[nt][2], abl, upper_halves(Ph[nt][j][0], Ph[nt][j][1]),
+                                         upper_halves(Ph[nt][j + NKS / 2][0], Ph[nt][j + NKS / 2][1]));
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[nt][1], ah1, Ph[nt][j + NKS / 2][0], Ph[nt][j + NKS / 2][1]);
 #pragma unroll
@@ -834,9 +856,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 if (p.prof && tid == FLOW_THREADS - 1) {
                     prof_acc[3] += c_got - c_sent;       // waiting for the 8 partials of my columns
                     prof_acc[4] += clock64() - c_got;    // reduce, exp2, normalise, publish
-                    prof_acc[5] += c_red - c_got;
+                    prof_acc[5] += PK4 ? c_sent - c_sync : c_red - c_got;  // PK4 report: contraction + send of the LAST warp
                     prof_acc[6] += c_obs - c_red;
-                    prof_acc[7] += c_nrm - c_obs;
+                    if (!PK4) prof_acc[7] += c_nrm - c_obs;
                 }
             }
             ++nstep;
@@ -2320,7 +2342,7 @@ int hmm_flow_pass_device(const float* init, int64_t init_sb, const float* A, con
         for (int c = 0; c < FLOW_PROF_CTAS / 2; c += 9) {
             const double n = h[c * 8 + 5] > 0 ? (double)h[c * 8 + 5] : 1.0;
             if (h[c * 8 + 5] > 0)
-                fprintf(stderr, "[fb2 flow prof] cta %3d steps %lld | pkt-wait %.0f  A-proc+sync %.0f  B(mma+send) %.0f | C-wait %.0f  C-proc %.0f (reduce %.0f obs|bar1 %.0f normalise %.0f) cycles/step\n",
+                fprintf(stderr, "[fb2 flow prof] cta %3d steps %lld | pkt-wait %.0f  A-proc+sync %.0f  B(mma+send) %.0f | C-wait %.0f  C-proc %.0f (reduce|B-last-warp %.0f obs|bar1 %.0f normalise|step %.0f) cycles/step\n",
                         c, h[c * 8 + 5], h[c * 8 + 0] / n, h[c * 8 + 1] / n, h[c * 8 + 2] / n, h[c * 8 + 3] / n, h[c * 8 + 4] / n,
                         h[c * 8 + 6] / n, h[c * 8 + 7] / n, h[(FLOW_PROF_CTAS / 2 + c / 2) * 8 + (c & 1)] / n);
         }
