@@ -1694,6 +1694,241 @@ __global__ void __launch_bounds__(KT_THREADS, 2) gaussian_kalman_tile(KalmanTile
     }
 }
 
+// gaussian_kalman_tile_tc (D = 17..32, O <= 16): the same tile walk with the arithmetic on the tensor pipe.  The FFMA form above is bound
+// by shared-memory operand bandwidth (one broadcast LDS.128 per 4 FMAs).  Here a WARP owns 16 tiles = the 16 rows of mma.sync.m16n8k8
+// tiles; every per-tile vector lives in C-fragment layout (rows g / g + 8 of a lane quad, columns 2 tig, 2 tig + 1 of each 8-column block),
+// and every product of the step is a small GEMM against an operator that all tiles share:
+//     U_t = wo + Y Pr          [16 x 16] [16 x 16]      eta = a0 + U_t Po'     [16 x 16] [16 x 64]
+//     V   = Z Linv'            [16 x 32] [32 x 32] (upper-triangular blocks only)      cur -= V U     [16 x 32] [32 x 64]
+// A C fragment becomes the A fragment of the next product without moving data: with the k slots of a k8-step permuted as (tig <-> column
+// 2 tig, tig + 4 <-> column 2 tig + 1) a thread already holds exactly its A entries; the operators are stored once per CTA in shared
+// memory as B fragments in that slot order, split into TF32 hi and lo (one LDS.128 per (k8, n8) block and lane).  3xTF32
+// (Ah Bh + Al Bh + Ah Bl) keeps fp32-class accuracy.  Not bit-identical to the level-by-level path (different summation order); the
+// tests hold it to the same 1e-5 against the float64 oracle.
+constexpr int KTC_CONST_BLOCKS = 2 * 2 + 2 * 8;   // Pr: 2 x 2 blocks, Po': 2 x 8
+constexpr int KTC_LEVEL_BLOCKS = 4 * 4 + 4 * 8;   // Linv': 4 x 4, -U: 4 x 8
+__host__ __device__ constexpr size_t ktc_smem_bytes(int K) {
+    return (size_t)(KTC_CONST_BLOCKS + K * KTC_LEVEL_BLOCKS) * 512 + (64 + 16 + 8) * 4;
+}
+__device__ __forceinline__ void ktc_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+struct KtcFrag {
+    uint32_t hi[4], lo[4];
+};
+// C fragment (rows g, g + 8; columns 2 tig, 2 tig + 1) -> split A fragment in the permuted slot order
+__device__ __forceinline__ KtcFrag ktc_split(float c0, float c1, float c2, float c3) {
+    KtcFrag f;
+    const float v[4] = {c0, c2, c1, c3};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f.hi[i] = (__float_as_uint(v[i]) + 0x1000u) & 0xFFFFE000u;  // round to nearest TF32 (ties away), see hmm_flow.cu
+        f.lo[i] = __float_as_uint(v[i] - __uint_as_float(f.hi[i]));
+    }
+    return f;
+}
+__device__ __forceinline__ void ktc_mma3(float (&d)[4], const KtcFrag& a, const float4& b) {
+    ktc_mma(d, a.lo, __float_as_uint(b.x), __float_as_uint(b.y));
+    ktc_mma(d, a.hi, __float_as_uint(b.z), __float_as_uint(b.w));
+    ktc_mma(d, a.hi, __float_as_uint(b.x), __float_as_uint(b.y));
+}
+__device__ __forceinline__ float ktc_quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+template <int KTC_WARPS>
+__global__ void __launch_bounds__(KTC_WARPS * 32, KTC_WARPS <= 6 ? 2 : 1) gaussian_kalman_tile_tc(KalmanTileArgs a) {
+    constexpr int DT = 32, OT = 16, KTC_THREADS = KTC_WARPS * 32;
+    extern __shared__ __align__(16) unsigned char ktc_smem[];
+    float4* sB = reinterpret_cast<float4*>(ktc_smem);  // [block][lane] {hi(k0), hi(k0 + 1), lo(k0), lo(k0 + 1)}: B fragments
+    const int K = a.K;
+    float* sa0 = reinterpret_cast<float*>(ktc_smem + (size_t)(KTC_CONST_BLOCKS + K * KTC_LEVEL_BLOCKS) * 512);  // [64] padded
+    float* swo = sa0 + 64;                                                                                      // [16]
+    float* sk = swo + 16;                                                                                       // konst per level
+    const int64_t b = blockIdx.y;
+    const int D = a.D, O = a.O, n = 2 * D;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+    // ---- operators -> B fragments.  Block order: Pr (kb, nb) 2 x 2 | Po' 2 x 8 | per level: Linv' 4 x 4 | -U 4 x 8
+    const int nblocks = KTC_CONST_BLOCKS + K * KTC_LEVEL_BLOCKS;
+    for (int idx = tid; idx < nblocks * 32; idx += KTC_THREADS) {
+        const int blk = idx >> 5, ln = idx & 31, gg = ln >> 2, tt = ln & 3;
+        float v0 = 0.f, v1 = 0.f;
+        auto fetch = [&](auto elem, int kb, int nb) {
+            const int k0 = 8 * kb + 2 * tt, col = 8 * nb + gg;
+            v0 = elem(k0, col);
+            v1 = elem(k0 + 1, col);
+        };
+        if (blk < 4) {  // B[k = o_in][n = o_out] = Pr[o_in][o_out]
+            fetch([&](int k, int c) { return (k < O && c < O) ? a.Pr[(b * O + k) * O + c] : 0.f; }, blk >> 1, blk & 1);
+        } else if (blk < KTC_CONST_BLOCKS) {  // B[k = o][n = padded row i] = Po[i][o]
+            const int q = blk - 4;
+            fetch([&](int k, int c) {
+                const int half = c / DT, kk = c % DT;
+                return (kk < D && k < O) ? a.Po[(b * n + half * D + kk) * O + k] : 0.f;
+            }, q >> 3, q & 7);
+        } else {
+            const int q = blk - KTC_CONST_BLOCKS, l = q / KTC_LEVEL_BLOCKS, r = q % KTC_LEVEL_BLOCKS;
+            const size_t op = ((size_t)b * a.NL + l) * 2;
+            if (r < 16) {  // B[k][n = r] = Linv[r][k]
+                const float* Li = a.opLinv + op * DT * DT;
+                fetch([&](int k, int c) { return __ldg(Li + c * DT + k); }, r >> 2, r & 3);
+            } else {  // B[k = r][n = c] = -U[r][c]
+                const float* U = a.opU + op * DT * 2 * DT;
+                fetch([&](int k, int c) { return -__ldg(U + k * 2 * DT + c); }, (r - 16) >> 3, (r - 16) & 7);
+            }
+        }
+        const float h0 = __uint_as_float((__float_as_uint(v0) + 0x1000u) & 0xFFFFE000u), h1 = __uint_as_float((__float_as_uint(v1) + 0x1000u) & 0xFFFFE000u);
+        sB[idx] = make_float4(h0, h1, v0 - h0, v1 - h1);
+    }
+    for (int i = tid; i < 64; i += KTC_THREADS) sa0[i] = (i % DT) < D ? a.a0[b * n + (i / DT) * D + i % DT] : 0.f;
+    for (int i = tid; i < 16; i += KTC_THREADS) swo[i] = i < O ? a.wo[b * O + i] : 0.f;
+    if (tid < K) sk[tid] = a.konst[((size_t)b * a.NL + tid) * 2];
+    __syncthreads();
+
+    const int64_t tile_base = ((int64_t)blockIdx.x * KTC_WARPS + warp) * 16;
+    if (tile_base >= a.ntiles) return;
+    const int64_t tile_r[2] = {tile_base + g, tile_base + g + 8};
+    const bool live[2] = {tile_r[0] < a.ntiles, tile_r[1] < a.ntiles};
+    const float* yp[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) yp[h] = a.y + (b * a.T + ((live[h] ? tile_r[h] : tile_base) << K)) * O;  // a missing tile repeats tile 0 of the warp (not stored)
+    const float c0 = a.c0[b];
+    const bool yvec = (O == OT) && (reinterpret_cast<uintptr_t>(a.y) % 8 == 0);
+    const float4* sPr = sB;
+    const float4* sPo = sB + 4 * 32;
+    float stk[KT_KMAX][34];  // pending left operands per level: 8 C fragments + the two scalars (local memory, run-time level index)
+    float cur[8][4], cc[2];
+    float yv[2][2][2];  // [row half][k8-step][column 2 tig, 2 tig + 1]
+    auto load_y = [&](int step) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const float* src = yp[h] + (size_t)step * O + 8 * s + 2 * tig;
+                if (yvec) {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(src));
+                    yv[h][s][0] = v.x;
+                    yv[h][s][1] = v.y;
+                } else {
+                    yv[h][s][0] = (8 * s + 2 * tig) < O ? __ldg(src) : 0.f;
+                    yv[h][s][1] = (8 * s + 2 * tig + 1) < O ? __ldg(src + 1) : 0.f;
+                }
+            }
+    };
+    load_y(0);
+    const int nsteps = 1 << K;
+#pragma unroll 1
+    for (int i = 0; i < nsteps; ++i) {
+        // ---- u = wo + y Pr  (C fragments of two 8-column blocks)
+        float u[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            u[j][0] = u[j][2] = swo[8 * j + 2 * tig];
+            u[j][1] = u[j][3] = swo[8 * j + 2 * tig + 1];
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const KtcFrag ya = ktc_split(yv[0][s][0], yv[0][s][1], yv[1][s][0], yv[1][s][1]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) ktc_mma3(u[j], ya, sPr[(s * 2 + j) * 32 + lane]);
+        }
+        if (i + 1 < nsteps) load_y(i + 1);  // next step's observations travel while this step computes
+        {
+            float uu0 = 0.f, uu1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uu0 = fmaf(u[j][0], u[j][0], fmaf(u[j][1], u[j][1], uu0));
+                uu1 = fmaf(u[j][2], u[j][2], fmaf(u[j][3], u[j][3], uu1));
+            }
+            cc[0] = c0 - 0.5f * ktc_quad_sum(uu0);
+            cc[1] = c0 - 0.5f * ktc_quad_sum(uu1);
+        }
+        // ---- eta = a0 + u Po'
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            cur[j][0] = cur[j][2] = sa0[8 * j + 2 * tig];
+            cur[j][1] = cur[j][3] = sa0[8 * j + 2 * tig + 1];
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const KtcFrag ua = ktc_split(u[s][0], u[s][1], u[s][2], u[s][3]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ktc_mma3(cur[j], ua, sPo[(s * 8 + j) * 32 + lane]);
+        }
+        // ---- fold the finished subtrees: one combine per trailing one-bit of i
+        int lvl = 0;
+#pragma unroll 1
+        for (int m = i; m & 1; m >>= 1, ++lvl) {
+            const float4* sLi = sB + (size_t)(KTC_CONST_BLOCKS + lvl * KTC_LEVEL_BLOCKS) * 32;
+            const float4* sU = sLi + 16 * 32;
+            // z = x_b + y_a: blocks 4..7 of the stacked element + blocks 0..3 of cur; blocks 0..3 of the result start as x_a
+            KtcFrag za[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float z[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    z[e] = stk[lvl][(4 + j) * 4 + e] + cur[j][e];
+                    cur[j][e] = stk[lvl][j * 4 + e];
+                }
+                za[j] = ktc_split(z[0], z[1], z[2], z[3]);
+            }
+            const float cxy0 = stk[lvl][32] + cc[0], cxy1 = stk[lvl][33] + cc[1];
+            // v = z Linv' (Linv lower triangular: k-block <= r-block)
+            float v[4][4];
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[rb][e] = 0.f;
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                for (int rb = kb; rb < 4; ++rb) ktc_mma3(v[rb], za[kb], sLi[(kb * 4 + rb) * 32 + lane]);
+            float vv0 = 0.f, vv1 = 0.f;
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb) {
+                vv0 = fmaf(v[rb][0], v[rb][0], fmaf(v[rb][1], v[rb][1], vv0));
+                vv1 = fmaf(v[rb][2], v[rb][2], fmaf(v[rb][3], v[rb][3], vv1));
+            }
+            // cur -= v U
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb) {
+                const KtcFrag va = ktc_split(v[rb][0], v[rb][1], v[rb][2], v[rb][3]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ktc_mma3(cur[j], va, sU[(rb * 8 + j) * 32 + lane]);
+            }
+            cc[0] = cxy0 + sk[lvl] + 0.5f * ktc_quad_sum(vv0);
+            cc[1] = cxy1 + sk[lvl] + 0.5f * ktc_quad_sum(vv1);
+        }
+        if (i + 1 < nsteps) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) stk[lvl][j * 4 + e] = cur[j][e];
+            stk[lvl][32] = cc[0];
+            stk[lvl][33] = cc[1];
+        }
+    }
+    // ---- one level-K element per tile: row g / g + 8, columns 8 j + 2 tig, + 1 (padded column 32 half + k <-> 2D-layout column half D + k)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (!live[h]) continue;
+        float* eo = a.eout + (b * a.out_T + tile_r[h]) * n;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int pc = 8 * j + 2 * tig, half = pc / DT, kk = pc % DT;
+            if (kk < D) eo[half * D + kk] = cur[j][2 * h];
+            if (kk + 1 < D) eo[half * D + kk + 1] = cur[j][2 * h + 1];
+        }
+        if (tig == 0) a.cout[b * a.out_T + tile_r[h]] = cc[h];
+    }
+}
+
 // A side stream per device and host thread (the fork / join events belong to one call at a time).
 struct GaussSide {
     cudaStream_t stream = nullptr;
@@ -1714,13 +1949,17 @@ static int gauss_side_for_current_device(GaussSide** out) {
     return FB2_OK;
 }
 
-static int kalman_pref_levels() {
-    const char* e = getenv("FB2_KALMAN_K");  // tree levels fused into gaussian_kalman_tile (tile = 2^K steps per thread)
-    int k = e ? atoi(e) : 4;
+static bool kalman_tc_tiles(int D) {
+    const char* tc_env = getenv("FB2_KALMAN_TC");  // 0: the FFMA tile kernel also for D > 16
+    return D > 16 && !(tc_env && tc_env[0] == '0');
+}
+static int kalman_pref_levels(int D) {
+    const char* e = getenv("FB2_KALMAN_K");  // tree levels fused into the tile kernel (tile = 2^K steps); measured best: 4 (FFMA tiles), 5 (tensor-core tiles)
+    int k = e ? atoi(e) : (kalman_tc_tiles(D) ? 5 : 4);
     return k < 1 ? 1 : (k > KT_KMAX ? KT_KMAX : k);
 }
-static int kalman_levels_for(int64_t T) {
-    int k = kalman_pref_levels();
+static int kalman_levels_for(int64_t T, int D) {
+    int k = kalman_pref_levels(D);
     while (k > 1 && (T >> k) < 1) --k;
     return k;
 }
@@ -1762,7 +2001,7 @@ static int kalman_chain_run(const float* y, const float* Lam, const float* Pr, c
                             int64_t B, int64_t T, int D, int O, float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes,
                             cudaStream_t stream) {
     const int NL = homog_levels_count(T), n = 2 * D;
-    const int K = kalman_levels_for(T);
+    const int K = kalman_levels_for(T, D);
     const int64_t nfull = T >> K, rem = T - (nfull << K), dK = nfull + (rem > 0 ? 1 : 0);
     const KalmanLayout lay = kalman_layout(workspace, workspace_bytes, B, T, D, DT, false, nullptr);
     if (!lay.ok) {
@@ -1806,10 +2045,26 @@ static int kalman_chain_run(const float* y, const float* Lam, const float* Pr, c
         ta.opU = la.opU; ta.opLinv = la.opLinv; ta.konst = la.konst;
         ta.eout = kE; ta.cout = kC; ta.T = T; ta.ntiles = nfull; ta.out_T = dK; ta.D = D; ta.O = O; ta.K = K; ta.NL = NL;
         const size_t smem = ((size_t)kt_const_floats<DT, 16>() + (size_t)K * kt_level_floats<DT>()) * sizeof(float);
-        // One tile per thread.  Two tiles per thread (NTL = 2: every operator load feeds 8 FMAs) was measured at C4: 4.1 ms against 2.9 ms --
-        // 255 registers with spills and half as many threads cost more than the halved shared-memory traffic gains.
-        FB2_CUDA(cudaFuncSetAttribute(gaussian_kalman_tile<DT, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gaussian_kalman_tile<DT, 16, 1><<<dim3((unsigned)ceil_div(nfull, KT_THREADS), (unsigned)B), KT_THREADS, smem, stream>>>(ta);
+        if (DT == 32 && kalman_tc_tiles(D)) {
+            const size_t smem_tc = ktc_smem_bytes(K);
+            const char* w_env = getenv("FB2_KALMAN_TC_WARPS");
+            const int nw = w_env ? atoi(w_env) : 12;  // C4: 4 warps 2.06 ms, 6: 1.88, 8: 1.85 (K = 5), 12: 1.75 (K = 5)
+#define FB2_KTC_LAUNCH(NWv)                                                                                                              \
+    do {                                                                                                                                 \
+        FB2_CUDA(cudaFuncSetAttribute(gaussian_kalman_tile_tc<NWv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));         \
+        gaussian_kalman_tile_tc<NWv><<<dim3((unsigned)ceil_div(nfull, NWv * 16), (unsigned)B), NWv * 32, smem_tc, stream>>>(ta);         \
+    } while (0)
+            if (nw == 6) FB2_KTC_LAUNCH(6);
+            else if (nw == 8) FB2_KTC_LAUNCH(8);
+            else if (nw == 12) FB2_KTC_LAUNCH(12);
+            else FB2_KTC_LAUNCH(4);
+#undef FB2_KTC_LAUNCH
+        } else {
+            // One tile per thread.  Two tiles per thread (NTL = 2: every operator load feeds 8 FMAs) was measured at C4: 4.1 ms against 2.9 ms --
+            // 255 registers with spills and half as many threads cost more than the halved shared-memory traffic gains.
+            FB2_CUDA(cudaFuncSetAttribute(gaussian_kalman_tile<DT, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gaussian_kalman_tile<DT, 16, 1><<<dim3((unsigned)ceil_div(nfull, KT_THREADS), (unsigned)B), KT_THREADS, smem, stream>>>(ta);
+        }
         const cudaError_t le = cudaGetLastError();
         // join here: everything enqueued from now on waits for the side stream, the tile kernel above runs next to it
         if (use_side) cudaStreamWaitEvent(stream, side->join, 0);

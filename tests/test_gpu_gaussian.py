@@ -202,6 +202,7 @@ def test_kalman_fused_tiles_are_bit_identical_to_the_level_by_level_path(fg, mon
     walk the reference's tree (sum_product.py:690-701) exactly: every T from 2 to 70 plus a few long ones, against kalman_eta +
     gaussian_homog_eta on the same constants, compared with torch.equal."""
     monkeypatch.setenv("FB2_KALMAN_K", str(K))
+    monkeypatch.setenv("FB2_KALMAN_TC", "0")  # the FFMA tile kernel (the tensor-core one is not bit-identical: next test)
     B = 2
     lengths = list(range(2, 71)) + [127, 128, 129, 1000, 1023, 4097] if D <= 8 else [2, 3, 5, 16, 17, 31, 33, 47, 64, 65, 100, 1023, 4097]
     for T in lengths:
@@ -212,6 +213,27 @@ def test_kalman_fused_tiles_are_bit_identical_to_the_level_by_level_path(fg, mon
             want = fg.gaussian_chain_info_homog(*fg.kalman_eta_from_constants(consts, args[6]))
             for a, b in zip(got, want):
                 assert torch.equal(a, b), "T={} K={}: max diff {}".format(T, K, (a - b).abs().max().item())
+        w, P, s = fg.kalman_elements_sqrt(*args)
+        ref = fg.gaussian_sequential_sum_product(*fg.sqrt_to_info(w, P, s))
+        for a, b in zip(got, ref):
+            close_norm(host(a), host(b), 2e-5)
+
+
+@pytest.mark.parametrize("K", [1, 3, 4, 6])
+@pytest.mark.parametrize("D,O", [(32, 16), (20, 7), (17, 16)])
+def test_kalman_tensor_core_tiles_match_the_level_by_level_path(fg, monkeypatch, K, D, O):
+    """gaussian_kalman_tile_tc (D > 16: the tile walk as 3xTF32 mma.sync GEMMs against the shared operators, 16 tiles per warp) against
+    the level-by-level path on the same constants (5e-6 of each tensor's largest entry) and against the general scan."""
+    monkeypatch.setenv("FB2_KALMAN_K", str(K))
+    monkeypatch.setenv("FB2_KALMAN_TC", "1")
+    for B, T in [(2, 2), (1, 3), (2, 17), (3, 64), (2, 65), (1, 100), (2, 1023), (1, 1024), (2, 1040), (1, 4097), (5, 1087)]:
+        args = _kalman_args(B, T, D, O, 200 * T + D)
+        consts = fg.kalman_constants(*args[:6])
+        got = fg.kalman_chain_fused(consts, args[6])
+        if T >= 4:
+            want = fg.gaussian_chain_info_homog(*fg.kalman_eta_from_constants(consts, args[6]))
+            for a, b in zip(got, want):
+                close_norm(host(a), host(b), 5e-6)
         w, P, s = fg.kalman_elements_sqrt(*args)
         ref = fg.gaussian_sequential_sum_product(*fg.sqrt_to_info(w, P, s))
         for a, b in zip(got, ref):
