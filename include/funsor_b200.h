@@ -200,8 +200,10 @@ int fb2_gaussian_kalman_eta_f32(const float* y, const float* Pr, const float* wo
  *                     r_tril[B,O,O] -> Lam[B,2D,2D] = P P' (the precision shared by all steps), Pr, wo, a0, Po, c0 as kalman_eta takes them.
  * kalman_chain     : the whole scan of pyro/hmm.py:269 (sequential_sum_product over the T chain elements, sum_product.py:652-701) from the
  *                     observations y[B,T,O] and those constants to (Lam[B,2D,2D], eta[B,2D], c[B]) over (state_-1; state_T-1).  The per-step
- *                     elements and the first K levels of the reference's tree (K = 4, FB2_KALMAN_K) are evaluated per tile of 2^K steps
- *                     without touching memory; results are bit-identical to kalman_eta + chain_homog.  O <= 16, T >= 2. */
+ *                     elements and the first K levels of the reference's tree (FB2_KALMAN_K) are evaluated per tile of 2^K steps
+ *                     without touching memory.  D <= 16: one thread per tile, fp32 FMA, bit-identical to kalman_eta + chain_homog (K = 4);
+ *                     D > 16: 16 tiles per warp as 3xTF32 mma.sync GEMMs against the shared operators (K = 5; within 5e-6 of that path,
+ *                     FB2_KALMAN_TC=0 selects the FMA form).  O <= 16, T >= 2. */
 int fb2_gaussian_kalman_constants_f32(const float* F, const float* q_loc, const float* q_tril, const float* H, const float* r_loc,
                                       const float* r_tril, int64_t B, int32_t D, int32_t O, float* Lam, float* Pr, float* wo, float* a0,
                                       float* Po, float* c0, void* stream);
