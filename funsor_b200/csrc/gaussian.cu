@@ -630,6 +630,164 @@ __global__ void __launch_bounds__(64) gaussian_homog_levels(HomogLevelsArgs a) {
     for (size_t i = threadIdx.x; i < nn; i += blockDim.x) a.Lo[b * nn + i] = res[i];
 }
 
+// gaussian_homog_levels_cta: the same chain of per-level pair contractions with a whole CTA (256 threads) per chain and the level
+// precisions resident in shared memory.  The warp-wide version above spends ~25 us per level (one warp walks the O(D^3) work of a pair,
+// and every level goes through global memory): 0.43 ms of BASELINE config 4, a quarter of the whole scan once the eta work moved to the
+// tensor pipe.  Here warp 0 factorises M (the same shuffle Cholesky, so the operators stay bit-identical), warps 0-1 run the forward
+// substitution for the 2 DT right-hand-side columns while warp 2 inverts L, and all 8 warps share Lam' = base - U'U (16 outputs per
+// thread, U broadcast from shared memory).  Same operation order per output as gauss_pair_body.
+template <int DT>
+struct HomogLevelsSmem {
+    float Lam[4][2 * DT][2 * DT + 1];  // padded layout (a-block rows/cols [0, DT), c-block [DT, 2 DT)): cur regular, cur tail, next regular, next tail
+    float L[DT][DT + 1];               // Cholesky factor, diagonal holds 1 / L[k][k]
+    float U[DT][2 * DT + 4];           // U = L^-1 G'
+    float logdet;
+    int bad;
+};
+template <int DT>
+__device__ void homog_pair_cta(const float (*X)[2 * DT + 1], const float (*Y)[2 * DT + 1], float (*Z)[2 * DT + 1], HomogLevelsSmem<DT>& sm, int D,
+                               float* opU, float* opLinv, float* konst, int32_t* flag) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- phase 1 (warp 0): Cholesky of M = X_cc + Y_aa, lane = row
+    if (warp == 0) {
+        float m[DT];
+#pragma unroll
+        for (int k = 0; k < DT; ++k) m[k] = (lane < D && k < D) ? X[DT + k][DT + lane] + Y[k][lane] : (k == lane ? 1.f : 0.f);
+        float logdet = 0.f, dinv = 1.f;
+        int bad = 0;
+#pragma unroll
+        for (int j = 0; j < DT; ++j) {
+            float d = __shfl_sync(0xffffffffu, m[j], j);
+            if (!(d > 0.f)) {
+                bad = 1;
+                d = 1.f;
+            }
+            float inv = rsqrtf(d);
+            inv = inv * fmaf(-0.5f * d * inv, inv, 1.5f);
+            const float ljj = d * inv;
+            logdet += __logf(ljj);
+            if (lane == j) dinv = inv;
+            const float lij = lane > j ? m[j] * inv : (lane == j ? ljj : 0.f);
+            m[j] = lij;
+#pragma unroll
+            for (int k = j + 1; k < DT; ++k) m[k] = fmaf(-lij, __shfl_sync(0xffffffffu, lij, k), m[k]);
+        }
+        if (lane < DT) {
+#pragma unroll
+            for (int k = 0; k < DT; ++k) sm.L[lane][k] = m[k];
+            sm.L[lane][lane] = dinv;
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            sm.logdet = logdet;
+            if (bad && flag) atomicExch(flag, 1);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: threads 0 .. 2 DT - 1: forward substitution for column c of G' (a-block column cc: X_ca[k][cc], c-block: Y_ac[k][cc]);
+    //      the next warp: L^-1 by forward substitution on the identity (lane = column)
+    if (tid < 2 * DT) {
+        const int c = tid, blk = c / DT, cc = c % DT;
+        float u[DT];
+#pragma unroll
+        for (int k = 0; k < DT; ++k) u[k] = (cc < D && k < D) ? (blk == 0 ? X[DT + k][cc] : Y[k][DT + cc]) : 0.f;
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            float acc = u[k];
+#pragma unroll
+            for (int mm = 0; mm < k; ++mm) acc = fmaf(-sm.L[k][mm], u[mm], acc);
+            u[k] = acc * sm.L[k][k];
+            sm.U[k][c] = u[k];
+            opU[k * 2 * DT + c] = u[k];
+        }
+    } else if (warp == (2 * DT + 31) / 32) {
+        const int col = lane;
+        float x[DT];
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            float acc = k == col ? 1.f : 0.f;
+#pragma unroll
+            for (int mm = 0; mm < k; ++mm) acc = fmaf(-sm.L[k][mm], x[mm], acc);
+            x[k] = acc * sm.L[k][k];
+        }
+        if (col < DT) {
+#pragma unroll
+            for (int k = 0; k < DT; ++k) opLinv[k * DT + col] = x[k];
+        }
+        if (col == 0) *konst = __fsub_rn(__fmul_rn((float)D, kHalfLog2Pi), sm.logdet);  // two roundings, as gauss_pair_body evaluates it (no fused multiply-add)
+    }
+    __syncthreads();
+    // ---- phase 3: Z = diag(X_aa, Y_cc) - U'U over the padded layout, 16 entries of one row per thread (rows of 2 DT = 64: 4 threads each)
+    constexpr int PER = (2 * DT) * (2 * DT) / 256 < 1 ? 1 : (2 * DT) * (2 * DT) / 256;  // entries per thread
+    constexpr int TPR = 2 * DT / PER;                                                       // threads per row
+    if (tid < 2 * DT * TPR) {
+        const int r = tid / TPR, s0 = (tid % TPR) * PER;
+        const int rblk = r / DT, rc = r % DT;
+        float acc[PER];
+#pragma unroll
+        for (int t = 0; t < PER; ++t) {
+            const int sp = s0 + t, sblk = sp / DT, sc = sp % DT;
+            acc[t] = (rc < D && sc < D && rblk == sblk) ? (rblk == 0 ? X[sc][rc] : Y[DT + sc][DT + rc]) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            const float ur = sm.U[k][r];
+#pragma unroll
+            for (int t = 0; t < PER; ++t) acc[t] = fmaf(-ur, sm.U[k][s0 + t], acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < PER; ++t) Z[s0 + t][r] = acc[t];  // written through the transpose like gauss_pair_body (the result is symmetric up to rounding)
+    }
+    __syncthreads();
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) gaussian_homog_levels_cta(HomogLevelsArgs a) {
+    extern __shared__ __align__(16) unsigned char hl_raw[];
+    HomogLevelsSmem<DT>& sm = *reinterpret_cast<HomogLevelsSmem<DT>*>(hl_raw);
+    const int64_t b = blockIdx.x;
+    const int D = a.D, n = 2 * D, tid = threadIdx.x;
+    // Lam[b] -> padded layout, slot 0
+    for (int idx = tid; idx < 2 * DT * 2 * DT; idx += blockDim.x) {
+        const int r = idx / (2 * DT), c = idx % (2 * DT);
+        const int rb = r / DT, rc = r % DT, cb = c / DT, cc = c % DT;
+        sm.Lam[0][r][c] = (rc < D && cc < D) ? a.Lam[b * n * n + (rb * D + rc) * n + cb * D + cc] : 0.f;
+    }
+    __syncthreads();
+    int reg = 0, tail = -1;  // slots of the current regular / tail precision
+    bool has_tail = false;
+    int64_t d = a.T;
+    for (int l = 0; d > 1; ++l) {
+        const int64_t npairs = d / 2;
+        const bool odd = d & 1;
+        const bool tail_pair = has_tail && !odd;
+        const int64_t reg_pairs = npairs - (tail_pair ? 1 : 0);
+        // two free slots for this level's results
+        int free_slots[2], nf = 0;
+        for (int q = 0; q < 4 && nf < 2; ++q)
+            if (q != reg && q != tail) free_slots[nf++] = q;
+        const size_t op = ((size_t)b * a.NL + l) * 2;
+        if (reg_pairs > 0)
+            homog_pair_cta<DT>(sm.Lam[reg], sm.Lam[reg], sm.Lam[free_slots[0]], sm, D, a.opU + op * DT * 2 * DT, a.opLinv + op * DT * DT, a.konst + op, a.flag);
+        if (tail_pair)
+            homog_pair_cta<DT>(sm.Lam[reg], sm.Lam[tail], sm.Lam[free_slots[1]], sm, D, a.opU + (op + 1) * DT * 2 * DT, a.opLinv + (op + 1) * DT * DT,
+                               a.konst + op + 1, a.flag);
+        if (tail_pair) {
+            tail = free_slots[1];
+        } else if (!has_tail && odd) {
+            tail = reg;
+            has_tail = true;
+        }
+        if (reg_pairs > 0) reg = free_slots[0];
+        d = (d + 1) / 2;
+    }
+    const int res = has_tail ? tail : reg;
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+        const int r = idx / n, c = idx % n;
+        a.Lo[b * n * n + idx] = sm.Lam[res][(r / D) * DT + r % D][(c / D) * DT + c % D];
+    }
+}
+
 // eta / c update of `count` pairs per chain starting at pair index p0, all with the operator (opU, opLinv, konst) of their
 // chain; one warp per pair, the operator lives in registers.  `leftover`: also copy input element d-1 to output slot `lslot`.
 struct HomogEtaArgs {
@@ -749,6 +907,20 @@ __global__ void __launch_bounds__(HE_THREADS) gaussian_homog_eta(HomogEtaArgs a)
     }
 }
 
+template <int DT>
+static int launch_homog_levels(HomogLevelsArgs& la, int64_t B, cudaStream_t stream) {
+    const char* warp_env = getenv("FB2_GAUSS_LEVELS_WARP");  // 1: the warp-per-pair form (one warp walks a level's pair contraction)
+    if ((warp_env && warp_env[0] == '1') || la.l_begin > 0 || la.l_end <= la.NL) {
+        gaussian_homog_levels<DT><<<(unsigned)B, 64, 0, stream>>>(la);
+    } else {
+        const size_t smem = sizeof(HomogLevelsSmem<DT>);
+        FB2_CUDA(cudaFuncSetAttribute(gaussian_homog_levels_cta<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gaussian_homog_levels_cta<DT><<<(unsigned)B, 256, smem, stream>>>(la);
+    }
+    FB2_LAUNCH_CHECK();
+    return FB2_OK;
+}
+
 static int homog_levels_count(int64_t T) {
     int nl = 0;
     for (int64_t d = T; d > 1; d = (d + 1) / 2) ++nl;
@@ -829,8 +1001,10 @@ static int homog_chain_run(const float* Lam, const float* eta, const float* c, i
     FB2_REQUIRE(B <= 65535, "gaussian_chain (homogeneous): at most 65535 chains per call");
     FB2_CUDA(cudaMemsetAsync(la.flag, 0, sizeof(int32_t), stream));
     FB2_CUDA(cudaMemsetAsync(zeros, 0, (size_t)n * 4, stream));
-    gaussian_homog_levels<DT><<<(unsigned)B, 64, 0, stream>>>(la);
-    FB2_LAUNCH_CHECK();
+    {
+        const int lst = launch_homog_levels<DT>(la, B, stream);
+        if (lst != FB2_OK) return lst;
+    }
     const float *ce = eta, *cc = c;
     int64_t d = T, in_T = T;
     bool has_tail = false;
@@ -2020,8 +2194,10 @@ static int kalman_chain_run(const float* y, const float* Lam, const float* Pr, c
     const char* side_env = getenv("FB2_KALMAN_SIDE");  // off by default: measured 2.92 -> 2.91 ms at C4 (the tile kernel fills the SMs either way)
     const bool use_side = NL > K && side_env && side_env[0] == '1' && gauss_side_for_current_device(&side) == FB2_OK;
     la.l_begin = 0; la.l_end = use_side ? K : NL + 1;
-    gaussian_homog_levels<DT><<<(unsigned)B, 64, 0, stream>>>(la);
-    FB2_LAUNCH_CHECK();
+    {
+        const int lst = launch_homog_levels<DT>(la, B, stream);
+        if (lst != FB2_OK) return lst;
+    }
     if (use_side) {
         FB2_CUDA(cudaEventRecord(side->fork, stream));
         FB2_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));

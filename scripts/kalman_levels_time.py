@@ -1,0 +1,30 @@
+"""C4: warp-wide vs CTA-wide level-operator kernel, tile depth K (tensor-core tiles)."""
+import os, sys
+sys.path.insert(0, "/root/repo")
+import torch
+import funsor_b200.gaussian as fg
+B, T, D, O = 64, 100000, 32, 16
+g = torch.Generator().manual_seed(0)
+F = 0.9 * torch.linalg.qr(torch.randn(B, D, D, generator=g))[0]
+H = torch.randn(B, D, O, generator=g) / D ** 0.5
+def tril(n):
+    a = torch.randn(B, n, n, generator=g) * 0.2
+    return torch.tril(a, -1) + torch.diag_embed(0.5 + torch.rand(B, n, generator=g))
+args = [a.cuda() for a in [F, torch.randn(B, D, generator=g) * 0.1, tril(D), H, torch.randn(B, O, generator=g) * 0.1, tril(O), torch.randn(B, T, O, generator=g)]]
+def timeit(fn, reps=20):
+    for _ in range(5): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+ref = None
+for rep in range(2):
+    for lw in ("1", "0"):
+        for K in (4, 5, 6):
+            os.environ.update({"FB2_GAUSS_LEVELS_WARP": lw, "FB2_KALMAN_K": str(K)})
+            out = fg.kalman_chain(*args)
+            if ref is None: ref = out
+            err = max((a - b).abs().max().item() / max(b.abs().max().item(), 1.0) for a, b in zip(out, ref))
+            print("pass %d  warp-wide levels=%s K=%d: %.3f ms   rel diff vs first %.2e" % (rep, lw, K, timeit(lambda: fg.kalman_chain(*args, validate=False)), err), flush=True)

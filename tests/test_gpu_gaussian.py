@@ -240,6 +240,25 @@ def test_kalman_tensor_core_tiles_match_the_level_by_level_path(fg, monkeypatch,
             close_norm(host(a), host(b), 2e-5)
 
 
+@pytest.mark.parametrize("D,O", [(3, 2), (8, 5), (16, 16), (32, 16), (21, 9)])
+def test_cta_wide_level_operators_are_bit_identical_to_the_warp_version(fg, monkeypatch, D, O):
+    """gaussian_homog_levels_cta (256 threads per chain, level precisions in shared memory) against gaussian_homog_levels (one warp per
+    pair contraction): same operation order per output, so the whole scan must agree bit for bit -- every tail / leftover combination."""
+    monkeypatch.setenv("FB2_KALMAN_TC", "0")
+    for T in list(range(4, 40)) + [64, 65, 127, 1000, 1023, 4097]:
+        args = _kalman_args(2, T, D, O, 300 * T + D)
+        consts = fg.kalman_constants(*args[:6])
+        elems = fg.kalman_eta_from_constants(consts, args[6])
+        monkeypatch.setenv("FB2_GAUSS_LEVELS_WARP", "1")
+        want = fg.gaussian_chain_info_homog(*elems)
+        want_fused = fg.kalman_chain_fused(consts, args[6])
+        monkeypatch.setenv("FB2_GAUSS_LEVELS_WARP", "0")
+        got = fg.gaussian_chain_info_homog(*elems)
+        got_fused = fg.kalman_chain_fused(consts, args[6])
+        for a, b in zip(got + got_fused, want + want_fused):
+            assert torch.equal(a, b), "T={}: max diff {}".format(T, (a - b).abs().max().item())
+
+
 # ------------------------------------------------------------------------------------------------ (f2) Gaussian backward sampling
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,T,D,O", [(2, 2, 1, 1), (2, 7, 3, 2), (1, 8, 2, 1), (2, 13, 4, 2), (1, 33, 2, 2)])
