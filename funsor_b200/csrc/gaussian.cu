@@ -810,6 +810,81 @@ constexpr int HE_THREADS = 128;
 // LDS.128; z, v and the 2 DT outputs live in registers.  3 DT^2 FMAs and 3 DT^2 / 4 shared loads per pair, no shuffles (a
 // warp-per-pair version with the operator in registers spent 64 shuffles per pair and took 6.7 ms over the levels of C4).
 // A thread reads the 2 n contiguous floats of its pair; neighbouring threads are 2 n floats apart, the lines are shared through L1.
+// eta / c update of one pair (elements 2p, 2p + 1 of `ein` -> element `po` of `eout`) with the operator in shared memory
+// NC: the inputs are read-only for the whole kernel (non-coherent loads); otherwise they were written earlier by this kernel (L2 loads).
+template <int DT, bool NC>
+__device__ __forceinline__ void homog_eta_pair(const float* ex, float cxy, float* eo, float* co, const float* sLi, const float* sU, float konst, int D,
+                                               bool vec) {
+    auto ld4 = [](const float* p) { return NC ? __ldg(reinterpret_cast<const float4*>(p)) : __ldcg(reinterpret_cast<const float4*>(p)); };
+    auto ld1 = [](const float* p) { return NC ? __ldg(p) : __ldcg(p); };
+    const int n = 2 * D;
+    const float* ey = ex + n;
+    float z[DT], out[2 * DT];
+    if (vec) {
+#pragma unroll
+        for (int k = 0; k < DT; k += 4) {
+            if (k < D) {
+                const float4 xa = ld4(ex + k), xb = ld4(ex + D + k);
+                const float4 ya = ld4(ey + k), yc = ld4(ey + D + k);
+                z[k] = xb.x + ya.x; z[k + 1] = xb.y + ya.y; z[k + 2] = xb.z + ya.z; z[k + 3] = xb.w + ya.w;
+                out[k] = xa.x; out[k + 1] = xa.y; out[k + 2] = xa.z; out[k + 3] = xa.w;
+                out[DT + k] = yc.x; out[DT + k + 1] = yc.y; out[DT + k + 2] = yc.z; out[DT + k + 3] = yc.w;
+            } else {
+                z[k] = z[k + 1] = z[k + 2] = z[k + 3] = 0.f;
+                out[k] = out[k + 1] = out[k + 2] = out[k + 3] = 0.f;
+                out[DT + k] = out[DT + k + 1] = out[DT + k + 2] = out[DT + k + 3] = 0.f;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            z[k] = k < D ? ld1(ex + D + k) + ld1(ey + k) : 0.f;
+            out[k] = k < D ? ld1(ex + k) : 0.f;
+            out[DT + k] = k < D ? ld1(ey + D + k) : 0.f;
+        }
+    }
+    float vv = 0.f;
+#pragma unroll
+    for (int r = 0; r < DT; ++r) {
+        // v_r = (L^-1 z)_r; L^-1 is lower triangular: columns beyond r are zero (and beyond D the padding is the identity)
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < DT; k += 4) {
+            if (k <= r) {
+                const float4 l = *reinterpret_cast<const float4*>(&sLi[r * DT + k]);
+                v = fmaf(l.x, z[k], fmaf(l.y, z[k + 1], fmaf(l.z, z[k + 2], fmaf(l.w, z[k + 3], v))));
+            }
+        }
+        vv = fmaf(v, v, vv);
+#pragma unroll
+        for (int c = 0; c < 2 * DT; c += 4) {
+            const float4 u = *reinterpret_cast<const float4*>(&sU[r * 2 * DT + c]);
+            out[c] = fmaf(-u.x, v, out[c]);
+            out[c + 1] = fmaf(-u.y, v, out[c + 1]);
+            out[c + 2] = fmaf(-u.z, v, out[c + 2]);
+            out[c + 3] = fmaf(-u.w, v, out[c + 3]);
+        }
+    }
+    if (vec) {
+#pragma unroll
+        for (int k = 0; k < DT; k += 4) {
+            if (k < D) {
+                *reinterpret_cast<float4*>(eo + k) = make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]);
+                *reinterpret_cast<float4*>(eo + D + k) = make_float4(out[DT + k], out[DT + k + 1], out[DT + k + 2], out[DT + k + 3]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            if (k < D) {
+                eo[k] = out[k];
+                eo[D + k] = out[DT + k];
+            }
+        }
+    }
+    *co = cxy + konst + 0.5f * vv;
+}
+
 template <int DT>
 __global__ void __launch_bounds__(HE_THREADS) gaussian_homog_eta(HomogEtaArgs a) {
     __shared__ __align__(16) float sLi[DT * DT];
@@ -831,79 +906,75 @@ __global__ void __launch_bounds__(HE_THREADS) gaussian_homog_eta(HomogEtaArgs a)
     const bool vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(a.ein) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.eout) % 16 == 0);
     for (int64_t i = (int64_t)blockIdx.x * HE_THREADS + threadIdx.x; i < a.count; i += (int64_t)gridDim.x * HE_THREADS) {
         const int64_t p = a.p0 + i;
-        const float* ex = ein + 2 * p * n;
-        const float* ey = ex + n;
-        float z[DT], out[2 * DT];
-        if (vec) {
-#pragma unroll
-            for (int k = 0; k < DT; k += 4) {
-                if (k < D) {
-                    const float4 xa = __ldg(reinterpret_cast<const float4*>(ex + k)), xb = __ldg(reinterpret_cast<const float4*>(ex + D + k));
-                    const float4 ya = __ldg(reinterpret_cast<const float4*>(ey + k)), yc = __ldg(reinterpret_cast<const float4*>(ey + D + k));
-                    z[k] = xb.x + ya.x; z[k + 1] = xb.y + ya.y; z[k + 2] = xb.z + ya.z; z[k + 3] = xb.w + ya.w;
-                    out[k] = xa.x; out[k + 1] = xa.y; out[k + 2] = xa.z; out[k + 3] = xa.w;
-                    out[DT + k] = yc.x; out[DT + k + 1] = yc.y; out[DT + k + 2] = yc.z; out[DT + k + 3] = yc.w;
-                } else {
-                    z[k] = z[k + 1] = z[k + 2] = z[k + 3] = 0.f;
-                    out[k] = out[k + 1] = out[k + 2] = out[k + 3] = 0.f;
-                    out[DT + k] = out[DT + k + 1] = out[DT + k + 2] = out[DT + k + 3] = 0.f;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < DT; ++k) {
-                z[k] = k < D ? __ldg(ex + D + k) + __ldg(ey + k) : 0.f;
-                out[k] = k < D ? __ldg(ex + k) : 0.f;
-                out[DT + k] = k < D ? __ldg(ey + D + k) : 0.f;
-            }
-        }
-        const float cxy = cin[2 * p] + cin[2 * p + 1];
-        float vv = 0.f;
-#pragma unroll
-        for (int r = 0; r < DT; ++r) {
-            // v_r = (L^-1 z)_r; L^-1 is lower triangular: columns beyond r are zero (and beyond D the padding is the identity)
-            float v = 0.f;
-#pragma unroll
-            for (int k = 0; k < DT; k += 4) {
-                if (k <= r) {
-                    const float4 l = *reinterpret_cast<const float4*>(&sLi[r * DT + k]);
-                    v = fmaf(l.x, z[k], fmaf(l.y, z[k + 1], fmaf(l.z, z[k + 2], fmaf(l.w, z[k + 3], v))));
-                }
-            }
-            vv = fmaf(v, v, vv);
-#pragma unroll
-            for (int c = 0; c < 2 * DT; c += 4) {
-                const float4 u = *reinterpret_cast<const float4*>(&sU[r * 2 * DT + c]);
-                out[c] = fmaf(-u.x, v, out[c]);
-                out[c + 1] = fmaf(-u.y, v, out[c + 1]);
-                out[c + 2] = fmaf(-u.z, v, out[c + 2]);
-                out[c + 3] = fmaf(-u.w, v, out[c + 3]);
-            }
-        }
-        float* eo = eout + (p + a.out_p_off) * n;
-        if (vec) {
-#pragma unroll
-            for (int k = 0; k < DT; k += 4) {
-                if (k < D) {
-                    *reinterpret_cast<float4*>(eo + k) = make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]);
-                    *reinterpret_cast<float4*>(eo + D + k) = make_float4(out[DT + k], out[DT + k + 1], out[DT + k + 2], out[DT + k + 3]);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < DT; ++k) {
-                if (k < D) {
-                    eo[k] = out[k];
-                    eo[D + k] = out[DT + k];
-                }
-            }
-        }
-        cout[p + a.out_p_off] = cxy + konst + 0.5f * vv;
+        homog_eta_pair<DT, true>(ein + 2 * p * n, cin[2 * p] + cin[2 * p + 1], eout + (p + a.out_p_off) * n, cout + p + a.out_p_off, sLi, sU, konst, D, vec);
     }
     if (a.leftover_src >= 0 && blockIdx.x == 0 && threadIdx.x < 32) {
         const int lane = threadIdx.x;
         for (int i = lane; i < n; i += 32) eout[a.leftover_dst * n + i] = ein[a.leftover_src * n + i];
         if (lane == 0) cout[a.leftover_dst] = cin[a.leftover_src];
+    }
+}
+
+// gaussian_homog_upper: every level from `l0` to the top of the tree in ONE launch, one CTA per chain (the levels above the tile depth
+// hold a few thousand elements per chain and shrink by two each time: as 16 separate launches they were launch-latency bound, ~0.3 ms of
+// BASELINE config 4).  Same per-pair arithmetic (homog_eta_pair) and the same regular / tail / leftover bookkeeping as the host loop of
+// homog_chain_run; the elements ping-pong between two global buffers (L2 resident), the level's operator is reloaded into shared memory.
+struct HomogUpperArgs {
+    const float* e0;  // level-l0 elements [B, d0, n], [B, d0]
+    const float* c0;
+    float *eb[2], *cb[2];  // ping-pong buffers: capacity (d0 + 1) / 2 and ((d0 + 1) / 2 + 1) / 2 elements per chain
+    float *eo, *co;        // chain result [B, n], [B]
+    const float *opU, *opLinv, *konst;
+    int64_t d0, cap[2];
+    int l0, NL, D, has_tail;
+};
+constexpr int HU_THREADS = 256;
+template <int DT>
+__global__ void __launch_bounds__(HU_THREADS) gaussian_homog_upper(HomogUpperArgs a) {
+    __shared__ __align__(16) float sLi[2][DT * DT];
+    __shared__ __align__(16) float sU[2][DT * 2 * DT];
+    __shared__ float sk[2];
+    const int64_t b = blockIdx.x;
+    const int D = a.D, n = 2 * D, tid = threadIdx.x;
+    const float* ein = a.e0 + b * a.d0 * n;
+    const float* cin = a.c0 + b * a.d0;
+    int64_t d = a.d0;
+    bool has_tail = a.has_tail != 0;
+    int which = 0;
+    for (int l = a.l0; d > 1; ++l) {
+        const int64_t npairs = d / 2, nd = (d + 1) / 2;
+        const bool odd = d & 1;
+        const bool tail_pair = has_tail && !odd;
+        const int64_t reg_pairs = npairs - (tail_pair ? 1 : 0);
+        float* eout = nd == 1 ? a.eo + b * n : a.eb[which] + b * a.cap[which] * n;
+        float* cout = nd == 1 ? a.co + b : a.cb[which] + b * a.cap[which];
+        __syncthreads();  // the previous level's operator and results are no longer in use / are complete
+        for (int w = 0; w < 2; ++w) {
+            if ((w == 0 && reg_pairs > 0) || (w == 1 && tail_pair)) {
+                const size_t op = ((size_t)b * a.NL + l) * 2 + w;
+                const float4* Li = reinterpret_cast<const float4*>(a.opLinv + op * DT * DT);
+                const float4* U = reinterpret_cast<const float4*>(a.opU + op * DT * 2 * DT);
+                for (int i = tid; i < DT * DT / 4; i += HU_THREADS) reinterpret_cast<float4*>(sLi[w])[i] = __ldg(Li + i);
+                for (int i = tid; i < DT * 2 * DT / 4; i += HU_THREADS) reinterpret_cast<float4*>(sU[w])[i] = __ldg(U + i);
+                if (tid == 0) sk[w] = a.konst[op];
+            }
+        }
+        __syncthreads();
+        const bool vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(ein) % 16 == 0) && (reinterpret_cast<uintptr_t>(eout) % 16 == 0);
+        for (int64_t p = tid; p < reg_pairs; p += HU_THREADS)
+            homog_eta_pair<DT, false>(ein + 2 * p * n, __ldcg(cin + 2 * p) + __ldcg(cin + 2 * p + 1), eout + p * n, cout + p, sLi[0], sU[0], sk[0], D, vec);
+        if (tail_pair && tid == HU_THREADS - 1) {
+            const int64_t p = npairs - 1;
+            homog_eta_pair<DT, false>(ein + 2 * p * n, __ldcg(cin + 2 * p) + __ldcg(cin + 2 * p + 1), eout + p * n, cout + p, sLi[1], sU[1], sk[1], D, vec);
+        }
+        if (odd && tid < 32) {  // the leftover passes through
+            for (int i = tid; i < n; i += 32) eout[(nd - 1) * n + i] = __ldcg(ein + (d - 1) * n + i);
+            if (tid == 0) cout[nd - 1] = __ldcg(cin + d - 1);
+        }
+        if (!tail_pair && !has_tail && odd) has_tail = true;
+        __threadfence_block();
+        ein = eout; cin = cout; d = nd;
+        which ^= 1;
     }
 }
 
@@ -2297,7 +2368,25 @@ static int kalman_chain_run(const float* y, const float* Lam, const float* Pr, c
             which ^= 1;
         }
     }
-    // ---- levels K .. NL-1 over the level-K array, as in homog_chain_run
+    // ---- levels K .. NL-1 over the level-K array: one launch (gaussian_homog_upper) or, with FB2_KALMAN_UPPER=0, level by level as in homog_chain_run
+    {
+        const char* up_env = getenv("FB2_KALMAN_UPPER");
+        if (dK > 1 && !(up_env && up_env[0] == '0')) {
+            HomogUpperArgs ua;
+            ua.e0 = kE; ua.c0 = kC; ua.d0 = dK;
+            // per-chain strides: a chain only ever touches its own regions (the CTAs of different chains are at different levels): the level-K
+            // input sits in lkE[0] with stride dK, odd levels above it go to lkE[1] (stride (dK + 1) / 2), even ones back over the chain's own input
+            ua.eb[0] = lay.lkE[1]; ua.cb[0] = lay.lkC[1]; ua.cap[0] = (dK + 1) / 2;
+            ua.eb[1] = lay.lkE[0]; ua.cb[1] = lay.lkC[0]; ua.cap[1] = dK;
+            ua.eo = eo; ua.co = co; ua.opU = la.opU; ua.opLinv = la.opLinv; ua.konst = la.konst;
+            ua.l0 = K; ua.NL = NL; ua.D = D; ua.has_tail = has_tail ? 1 : 0;
+            gaussian_homog_upper<DT><<<(unsigned)B, HU_THREADS, 0, stream>>>(ua);
+            FB2_LAUNCH_CHECK();
+            gaussian_poison_if_flag<<<(unsigned)ceil_div(B, 256), 256, 0, stream>>>(la.flag, co, B);
+            FB2_LAUNCH_CHECK();
+            return FB2_OK;
+        }
+    }
     const float *ce = kE, *cc = kC;
     int64_t d = dK, in_T = dK;
     int which = 1;
