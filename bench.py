@@ -529,14 +529,14 @@ def extra_measurements(device):
     sec = timeit(lambda: fg.kalman_chain(*kargs, validate=False))
     kalman_bytes = (y.numel() + Bk * (2 * D) * (2 * D + 1) + Bk) * 4.0  # read y once, write one (Lam, eta, c) per chain
     out["kalman_scan"] = {"steps_per_s": Bk * Tk / sec, "D": D, "O": O, "B": Bk, "T": Tk, "ms": sec * 1e3,
-                          "kernel": "gaussian_kalman_constants + gaussian_homog_levels<32> (precision operators per tree level) + gaussian_kalman_tile_tc<12> "
+                          "kernel": "gaussian_kalman_constants + gaussian_homog_levels_cta<32> (precision operators per tree level) + gaussian_kalman_tile_tc<12> "
                                     "(per tile of 32 steps: elements from y and the first 5 tree levels as 3xTF32 mma.sync GEMMs against the shared operators, "
-                                    "16 tiles per warp) + gaussian_homog_eta<32> (levels 5..16)",
+                                    "16 tiles per warp) + gaussian_homog_upper<32> (levels 5..16 in one launch)",
                           "roofline": {"bound": "hbm", "achieved": kalman_bytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                        "frac": kalman_bytes / sec / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": kalman_bytes,
                                        "note": "algorithmic bytes = the observations y[B,T,O] read once + the [B] results; the tile kernel (half of the time) "
                                                "runs on the tensor pipe (ncu: tensor pipe 69 % active, DRAM read = y), the rest is the serial chain of per-level "
-                                               "precision operators (0.43 ms, one CTA per chain) and 16 small sweeps of the upper levels"},
+                                               "precision operators (0.29 ms, one CTA per chain) and the upper levels of the tree (one launch)"},
                           "fp32": {"mac_per_step": 1280 + 2600, "useful_tflops": 2.0 * (1280 + 2600) * Bk * Tk / sec / 1e12,
                                    "note": "1280 multiply-adds per element (u = wo + y Pr, eta = a0 + Po u) + ~2600 per pair contraction (triangular L^-1 z, U'v), "
                                            "issued as 3xTF32 mma.sync (three tensor instructions per useful product)"},
