@@ -1080,7 +1080,23 @@ static int homog_chain_run(const float* Lam, const float* eta, const float* c, i
     int64_t d = T, in_T = T;
     bool has_tail = false;
     int which = 0;
+    const char* up_env = getenv("FB2_KALMAN_UPPER");
+    const bool upper_ok = !keep && !(up_env && up_env[0] == '0');
     for (int l = 0; d > 1; ++l) {
+        // once a level is small, the rest of the tree runs in one launch (gaussian_homog_upper, one CTA per chain).  The current elements
+        // sit in the caller's array (l = 0) or in be[which ^ 1] with stride d; odd levels from here go to be[which], even ones back over
+        // the chain's own region of be[which ^ 1]
+        if (upper_ok && d <= 1024) {
+            HomogUpperArgs ua;
+            ua.e0 = ce; ua.c0 = cc; ua.d0 = d;
+            ua.eb[0] = lay.be[which]; ua.cb[0] = lay.bc[which]; ua.cap[0] = (d + 1) / 2;
+            ua.eb[1] = lay.be[which ^ 1]; ua.cb[1] = lay.bc[which ^ 1]; ua.cap[1] = l == 0 ? ((d + 1) / 2 + 1) / 2 : d;
+            ua.eo = eo; ua.co = co; ua.opU = la.opU; ua.opLinv = la.opLinv; ua.konst = la.konst;
+            ua.l0 = l; ua.NL = NL; ua.D = D; ua.has_tail = has_tail ? 1 : 0;
+            gaussian_homog_upper<DT><<<(unsigned)B, HU_THREADS, 0, stream>>>(ua);
+            FB2_LAUNCH_CHECK();
+            break;
+        }
         const int64_t npairs = d / 2, nd = (d + 1) / 2;
         const bool odd = d & 1;
         const bool tail_pair = has_tail && !odd;
@@ -2368,29 +2384,29 @@ static int kalman_chain_run(const float* y, const float* Lam, const float* Pr, c
             which ^= 1;
         }
     }
-    // ---- levels K .. NL-1 over the level-K array: one launch (gaussian_homog_upper) or, with FB2_KALMAN_UPPER=0, level by level as in homog_chain_run
-    {
-        const char* up_env = getenv("FB2_KALMAN_UPPER");
-        if (dK > 1 && !(up_env && up_env[0] == '0')) {
-            HomogUpperArgs ua;
-            ua.e0 = kE; ua.c0 = kC; ua.d0 = dK;
-            // per-chain strides: a chain only ever touches its own regions (the CTAs of different chains are at different levels): the level-K
-            // input sits in lkE[0] with stride dK, odd levels above it go to lkE[1] (stride (dK + 1) / 2), even ones back over the chain's own input
-            ua.eb[0] = lay.lkE[1]; ua.cb[0] = lay.lkC[1]; ua.cap[0] = (dK + 1) / 2;
-            ua.eb[1] = lay.lkE[0]; ua.cb[1] = lay.lkC[0]; ua.cap[1] = dK;
-            ua.eo = eo; ua.co = co; ua.opU = la.opU; ua.opLinv = la.opLinv; ua.konst = la.konst;
-            ua.l0 = K; ua.NL = NL; ua.D = D; ua.has_tail = has_tail ? 1 : 0;
-            gaussian_homog_upper<DT><<<(unsigned)B, HU_THREADS, 0, stream>>>(ua);
-            FB2_LAUNCH_CHECK();
-            gaussian_poison_if_flag<<<(unsigned)ceil_div(B, 256), 256, 0, stream>>>(la.flag, co, B);
-            FB2_LAUNCH_CHECK();
-            return FB2_OK;
-        }
-    }
+    // ---- levels K .. NL-1 over the level-K array: level by level while a level is large (many CTAs per chain), then the rest of the tree in
+    //      one launch (gaussian_homog_upper, one CTA per chain; FB2_KALMAN_UPPER=0: off, FB2_KALMAN_UPPER_MAX: largest level it takes)
+    const char* up_env = getenv("FB2_KALMAN_UPPER");
+    const char* upmax_env = getenv("FB2_KALMAN_UPPER_MAX");
+    const bool upper_ok = !(up_env && up_env[0] == '0');
+    const int64_t upper_max = upmax_env ? atoll(upmax_env) : 1024;
     const float *ce = kE, *cc = kC;
     int64_t d = dK, in_T = dK;
     int which = 1;
     for (int l = K; d > 1; ++l) {
+        if (upper_ok && d <= upper_max) {
+            // per-chain strides: a chain only ever touches its own regions (the CTAs of different chains are at different levels): the input
+            // sits in lkE[which ^ 1] with stride d, odd levels above it go to lkE[which] (stride (d + 1) / 2), even ones back over the chain's own input
+            HomogUpperArgs ua;
+            ua.e0 = ce; ua.c0 = cc; ua.d0 = d;
+            ua.eb[0] = lay.lkE[which]; ua.cb[0] = lay.lkC[which]; ua.cap[0] = (d + 1) / 2;
+            ua.eb[1] = lay.lkE[which ^ 1]; ua.cb[1] = lay.lkC[which ^ 1]; ua.cap[1] = d;
+            ua.eo = eo; ua.co = co; ua.opU = la.opU; ua.opLinv = la.opLinv; ua.konst = la.konst;
+            ua.l0 = l; ua.NL = NL; ua.D = D; ua.has_tail = has_tail ? 1 : 0;
+            gaussian_homog_upper<DT><<<(unsigned)B, HU_THREADS, 0, stream>>>(ua);
+            FB2_LAUNCH_CHECK();
+            break;
+        }
         const int64_t npairs = d / 2, nd = (d + 1) / 2;
         const bool odd = d & 1;
         const bool tail_pair = has_tail && !odd;
