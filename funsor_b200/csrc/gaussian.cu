@@ -732,8 +732,19 @@ __device__ void homog_pair_cta(const float (*X)[2 * DT + 1], const float (*Y)[2 
 #pragma unroll
         for (int k = 0; k < DT; ++k) {
             const float ur = sm.U[k][r];
+            if constexpr (PER % 4 == 0) {  // rows of U are 16-byte aligned (2 DT + 4 floats) and s0 is a multiple of PER
 #pragma unroll
-            for (int t = 0; t < PER; ++t) acc[t] = fmaf(-ur, sm.U[k][s0 + t], acc[t]);
+                for (int t = 0; t < PER; t += 4) {
+                    const float4 uv = *reinterpret_cast<const float4*>(&sm.U[k][s0 + t]);
+                    acc[t] = fmaf(-ur, uv.x, acc[t]);
+                    acc[t + 1] = fmaf(-ur, uv.y, acc[t + 1]);
+                    acc[t + 2] = fmaf(-ur, uv.z, acc[t + 2]);
+                    acc[t + 3] = fmaf(-ur, uv.w, acc[t + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < PER; ++t) acc[t] = fmaf(-ur, sm.U[k][s0 + t], acc[t]);
+            }
         }
 #pragma unroll
         for (int t = 0; t < PER; ++t) Z[s0 + t][r] = acc[t];  // written through the transpose like gauss_pair_body (the result is symmetric up to rounding)
