@@ -1757,6 +1757,7 @@ __global__ void __launch_bounds__(256) gaussian_kalman_constants(KalmanConstArgs
 //   level-0 .. level-(K-1) eta arrays (1.6 GB + 0.8 GB + ... at BASELINE config 4) never exist: per tile y is read once (2^K O floats)
 //   and one element (2D + 1 floats) is written.  The operators of the K levels sit in shared memory as broadcast LDS.128 operands.
 struct KalmanTileArgs {
+    const float *eta_in, *c_in;  // non-null: the per-step elements are given (eta[B,T,2D], c[B,T]) instead of being formed from y
     const float *y, *Pr, *wo, *a0, *Po, *c0;
     const float *opU, *opLinv, *konst;  // per-level operators of gaussian_homog_levels: regular operator of level l at ((b NL + l) 2)
     float *eout, *cout;                 // level-K arrays [B, out_T, 2D], [B, out_T]
@@ -1783,16 +1784,19 @@ __global__ void __launch_bounds__(KT_THREADS, 2) gaussian_kalman_tile(KalmanTile
     float* sops = kt_smem + kt_const_floats<DT, OT>();  // per level: L^-1 [DT][DT], U [DT][2 DT]
     const int64_t b = blockIdx.y;
     const int D = a.D, O = a.O, n = 2 * D, K = a.K;
-    for (int i = threadIdx.x; i < OT * OT; i += KT_THREADS) {
-        const int oi = i / OT, oo = i % OT;
-        sPr[i] = (oi < O && oo < O) ? a.Pr[(b * O + oi) * O + oo] : 0.f;
+    const bool given = a.eta_in != nullptr;
+    if (!given) {
+        for (int i = threadIdx.x; i < OT * OT; i += KT_THREADS) {
+            const int oi = i / OT, oo = i % OT;
+            sPr[i] = (oi < O && oo < O) ? a.Pr[(b * O + oi) * O + oo] : 0.f;
+        }
+        for (int i = threadIdx.x; i < 2 * DT * OT; i += KT_THREADS) {
+            const int row = i / OT, o = i % OT, blk = row / DT, k = row % DT;
+            sPo[i] = (k < D && o < O) ? a.Po[(b * n + blk * D + k) * O + o] : 0.f;
+        }
+        for (int i = threadIdx.x; i < 2 * DT; i += KT_THREADS) sa0[i] = (i % DT) < D ? a.a0[b * n + (i / DT) * D + i % DT] : 0.f;
+        for (int i = threadIdx.x; i < OT; i += KT_THREADS) swo[i] = i < O ? a.wo[b * O + i] : 0.f;
     }
-    for (int i = threadIdx.x; i < 2 * DT * OT; i += KT_THREADS) {
-        const int row = i / OT, o = i % OT, blk = row / DT, k = row % DT;
-        sPo[i] = (k < D && o < O) ? a.Po[(b * n + blk * D + k) * O + o] : 0.f;
-    }
-    for (int i = threadIdx.x; i < 2 * DT; i += KT_THREADS) sa0[i] = (i % DT) < D ? a.a0[b * n + (i / DT) * D + i % DT] : 0.f;
-    for (int i = threadIdx.x; i < OT; i += KT_THREADS) swo[i] = i < O ? a.wo[b * O + i] : 0.f;
     for (int l = 0; l < K; ++l) {
         const size_t op = ((size_t)b * a.NL + l) * 2;
         const float4* Li = reinterpret_cast<const float4*>(a.opLinv + op * DT * DT);
@@ -1806,15 +1810,21 @@ __global__ void __launch_bounds__(KT_THREADS, 2) gaussian_kalman_tile(KalmanTile
     __syncthreads();
     const int64_t tile0 = ((int64_t)blockIdx.x * KT_THREADS + threadIdx.x) * NTL;
     if (tile0 >= a.ntiles) return;
-    const float c0 = a.c0[b];
+    const float c0 = given ? 0.f : a.c0[b];
     const float* yp[NTL];
+    const float* ep[NTL];  // given elements: eta / c of the tile's first step
+    const float* cp[NTL];
     bool live[NTL];
 #pragma unroll
     for (int q = 0; q < NTL; ++q) {
         live[q] = tile0 + q < a.ntiles;
-        yp[q] = a.y + (b * a.T + ((live[q] ? tile0 + q : tile0) << K)) * O;  // a missing last tile repeats its neighbour (not stored)
+        const int64_t t_first = b * a.T + ((live[q] ? tile0 + q : tile0) << K);  // a missing last tile repeats its neighbour (not stored)
+        yp[q] = given ? nullptr : a.y + t_first * O;
+        ep[q] = given ? a.eta_in + t_first * n : nullptr;
+        cp[q] = given ? a.c_in + t_first : nullptr;
     }
-    const bool yvec = (O == OT) && (reinterpret_cast<uintptr_t>(a.y) % 16 == 0);
+    const bool yvec = !given && (O == OT) && (reinterpret_cast<uintptr_t>(a.y) % 16 == 0);
+    const bool evec = given && (D % 4 == 0) && (reinterpret_cast<uintptr_t>(a.eta_in) % 16 == 0);
     float4 stk[NTL][KT_KMAX][2 * DT / 4];  // pending left operands, one per level (local memory: indexed by the run-time level)
     float stc[NTL][KT_KMAX];
     float cur[NTL][2 * DT], cc[NTL];
@@ -1835,10 +1845,37 @@ __global__ void __launch_bounds__(KT_THREADS, 2) gaussian_kalman_tile(KalmanTile
             }
         }
     };
-    load_y(0);
+    if (!given) load_y(0);
     const int nsteps = 1 << K;
 #pragma unroll 1
     for (int i = 0; i < nsteps; ++i) {
+      if (given) {
+        // ---- element of step i as given: eta in the padded register layout, c
+#pragma unroll
+        for (int q = 0; q < NTL; ++q) {
+            const float* e = ep[q] + (size_t)i * n;
+            if (evec) {
+#pragma unroll
+                for (int k = 0; k < DT; k += 4) {
+                    if (k < D) {
+                        const float4 ea = __ldg(reinterpret_cast<const float4*>(e + k)), ec = __ldg(reinterpret_cast<const float4*>(e + D + k));
+                        cur[q][k] = ea.x; cur[q][k + 1] = ea.y; cur[q][k + 2] = ea.z; cur[q][k + 3] = ea.w;
+                        cur[q][DT + k] = ec.x; cur[q][DT + k + 1] = ec.y; cur[q][DT + k + 2] = ec.z; cur[q][DT + k + 3] = ec.w;
+                    } else {
+                        cur[q][k] = cur[q][k + 1] = cur[q][k + 2] = cur[q][k + 3] = 0.f;
+                        cur[q][DT + k] = cur[q][DT + k + 1] = cur[q][DT + k + 2] = cur[q][DT + k + 3] = 0.f;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < DT; ++k) {
+                    cur[q][k] = k < D ? __ldg(e + k) : 0.f;
+                    cur[q][DT + k] = k < D ? __ldg(e + D + k) : 0.f;
+                }
+            }
+            cc[q] = __ldg(cp[q] + i);
+        }
+      } else {
         // ---- element of step i: u = wo + y Pr, eta = a0 + Po u, c = c0 - |u|^2 / 2
         float u[NTL][OT];
 #pragma unroll
@@ -1882,6 +1919,7 @@ __global__ void __launch_bounds__(KT_THREADS, 2) gaussian_kalman_tile(KalmanTile
 #pragma unroll
             for (int q = 0; q < NTL; ++q) cur[q][r] = acc[q];
         }
+      }
         // ---- fold the finished subtrees: one combine per trailing one-bit of i
         int lvl = 0;
 #pragma unroll 1
@@ -2035,7 +2073,8 @@ __global__ void __launch_bounds__(KTC_WARPS * 32, KTC_WARPS <= 6 ? 2 : 1) gaussi
             v0 = elem(k0, col);
             v1 = elem(k0 + 1, col);
         };
-        if (blk < 4) {  // B[k = o_in][n = o_out] = Pr[o_in][o_out]
+        if (blk < KTC_CONST_BLOCKS && a.eta_in) {  // given elements: the observation operators are not used
+        } else if (blk < 4) {  // B[k = o_in][n = o_out] = Pr[o_in][o_out]
             fetch([&](int k, int c) { return (k < O && c < O) ? a.Pr[(b * O + k) * O + c] : 0.f; }, blk >> 1, blk & 1);
         } else if (blk < KTC_CONST_BLOCKS) {  // B[k = o][n = padded row i] = Po[i][o]
             const int q = blk - 4;
@@ -2057,8 +2096,11 @@ __global__ void __launch_bounds__(KTC_WARPS * 32, KTC_WARPS <= 6 ? 2 : 1) gaussi
         const float h0 = __uint_as_float((__float_as_uint(v0) + 0x1000u) & 0xFFFFE000u), h1 = __uint_as_float((__float_as_uint(v1) + 0x1000u) & 0xFFFFE000u);
         sB[idx] = make_float4(h0, h1, v0 - h0, v1 - h1);
     }
-    for (int i = tid; i < 64; i += KTC_THREADS) sa0[i] = (i % DT) < D ? a.a0[b * n + (i / DT) * D + i % DT] : 0.f;
-    for (int i = tid; i < 16; i += KTC_THREADS) swo[i] = i < O ? a.wo[b * O + i] : 0.f;
+    const bool given = a.eta_in != nullptr;
+    if (!given) {
+        for (int i = tid; i < 64; i += KTC_THREADS) sa0[i] = (i % DT) < D ? a.a0[b * n + (i / DT) * D + i % DT] : 0.f;
+        for (int i = tid; i < 16; i += KTC_THREADS) swo[i] = i < O ? a.wo[b * O + i] : 0.f;
+    }
     if (tid < K) sk[tid] = a.konst[((size_t)b * a.NL + tid) * 2];
     __syncthreads();
 
@@ -2067,10 +2109,18 @@ __global__ void __launch_bounds__(KTC_WARPS * 32, KTC_WARPS <= 6 ? 2 : 1) gaussi
     const int64_t tile_r[2] = {tile_base + g, tile_base + g + 8};
     const bool live[2] = {tile_r[0] < a.ntiles, tile_r[1] < a.ntiles};
     const float* yp[2];
+    const float* ep[2];
+    const float* cp[2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) yp[h] = a.y + (b * a.T + ((live[h] ? tile_r[h] : tile_base) << K)) * O;  // a missing tile repeats tile 0 of the warp (not stored)
-    const float c0 = a.c0[b];
-    const bool yvec = (O == OT) && (reinterpret_cast<uintptr_t>(a.y) % 8 == 0);
+    for (int h = 0; h < 2; ++h) {
+        const int64_t t_first = b * a.T + ((live[h] ? tile_r[h] : tile_base) << K);  // a missing tile repeats tile 0 of the warp (not stored)
+        yp[h] = given ? nullptr : a.y + t_first * O;
+        ep[h] = given ? a.eta_in + t_first * n : nullptr;
+        cp[h] = given ? a.c_in + t_first : nullptr;
+    }
+    const float c0 = given ? 0.f : a.c0[b];
+    const bool yvec = !given && (O == OT) && (reinterpret_cast<uintptr_t>(a.y) % 8 == 0);
+    const bool evec = given && (D % 2 == 0) && (reinterpret_cast<uintptr_t>(a.eta_in) % 8 == 0);
     const float4* sPr = sB;
     const float4* sPo = sB + 4 * 32;
     float stk[KT_KMAX][34];  // pending left operands per level: 8 C fragments + the two scalars (local memory, run-time level index)
@@ -2092,10 +2142,35 @@ __global__ void __launch_bounds__(KTC_WARPS * 32, KTC_WARPS <= 6 ? 2 : 1) gaussi
                 }
             }
     };
-    load_y(0);
+    if (!given) load_y(0);
     const int nsteps = 1 << K;
 #pragma unroll 1
     for (int i = 0; i < nsteps; ++i) {
+      if (given) {
+        // ---- element of step i as given: rows g / g + 8 of the C fragments straight from eta (padded column 32 half + kk <-> half D + kk)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float* e = ep[h] + (size_t)i * n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int pc = 8 * j + 2 * tig, half = pc / DT, kk = pc % DT;
+                float x0 = 0.f, x1 = 0.f;
+                if (evec) {
+                    if (kk < D) {
+                        const float2 v = __ldg(reinterpret_cast<const float2*>(e + half * D + kk));
+                        x0 = v.x;
+                        x1 = v.y;
+                    }
+                } else {
+                    if (kk < D) x0 = __ldg(e + half * D + kk);
+                    if (kk + 1 < D) x1 = __ldg(e + half * D + kk + 1);
+                }
+                cur[j][2 * h] = x0;
+                cur[j][2 * h + 1] = x1;
+            }
+            cc[h] = __ldg(cp[h] + i);
+        }
+      } else {
         // ---- u = wo + y Pr  (C fragments of two 8-column blocks)
         float u[2][4];
 #pragma unroll
@@ -2132,6 +2207,7 @@ __global__ void __launch_bounds__(KTC_WARPS * 32, KTC_WARPS <= 6 ? 2 : 1) gaussi
 #pragma unroll
             for (int j = 0; j < 8; ++j) ktc_mma3(cur[j], ua, sPo[(s * 8 + j) * 32 + lane]);
         }
+      }
         // ---- fold the finished subtrees: one combine per trailing one-bit of i
         int lvl = 0;
 #pragma unroll 1
@@ -2268,10 +2344,12 @@ static KalmanLayout kalman_layout(void* workspace, size_t workspace_bytes, int64
     return L;
 }
 
+// Source of the per-step elements: the observations + per-chain constants (GaussianHMM, eta_in == nullptr) or the elements themselves
+// (eta_in[B,T,2D], c_in[B,T]: any time-homogeneous chain, e.g. the funsor rule for a Gaussian MarkovProduct).
 template <int DT>
 static int kalman_chain_run(const float* y, const float* Lam, const float* Pr, const float* wo, const float* a0, const float* Po, const float* c0,
                             int64_t B, int64_t T, int D, int O, float* Lo, float* eo, float* co, void* workspace, size_t workspace_bytes,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const float* eta_in = nullptr, const float* c_in = nullptr) {
     const int NL = homog_levels_count(T), n = 2 * D;
     const int K = kalman_levels_for(T, D);
     const int64_t nfull = T >> K, rem = T - (nfull << K), dK = nfull + (rem > 0 ? 1 : 0);
@@ -2315,7 +2393,7 @@ static int kalman_chain_run(const float* y, const float* Lam, const float* Pr, c
     float* kC = dK == 1 ? co : lay.lkC[0];
     {
         KalmanTileArgs ta;
-        ta.y = y; ta.Pr = Pr; ta.wo = wo; ta.a0 = a0; ta.Po = Po; ta.c0 = c0;
+        ta.y = y; ta.Pr = Pr; ta.wo = wo; ta.a0 = a0; ta.Po = Po; ta.c0 = c0; ta.eta_in = eta_in; ta.c_in = c_in;
         ta.opU = la.opU; ta.opLinv = la.opLinv; ta.konst = la.konst;
         ta.eout = kE; ta.cout = kC; ta.T = T; ta.ntiles = nfull; ta.out_T = dK; ta.D = D; ta.O = O; ta.K = K; ta.NL = NL;
         const size_t smem = ((size_t)kt_const_floats<DT, 16>() + (size_t)K * kt_level_floats<DT>()) * sizeof(float);
@@ -2358,9 +2436,11 @@ static int kalman_chain_run(const float* y, const float* Lam, const float* Pr, c
     // ---- the remainder tile (the last rem < 2^K steps): level by level with the operators of the whole chain; its parities are those of
     //      the whole chain (d_l = nfull 2^(K-l) + dl_l), its single level-K element lands in slot nfull
     if (rem > 0) {
-        gaussian_kalman_eta<16, 4><<<dim3((unsigned)ceil_div(rem, 128), (unsigned)B), 128, 0, stream>>>(y, Pr, wo, a0, Po, c0, rem, D, O, lay.remE[0],
-                                                                                                    lay.remC[0], T, nfull << K);
-        FB2_LAUNCH_CHECK();
+        if (!eta_in) {
+            gaussian_kalman_eta<16, 4><<<dim3((unsigned)ceil_div(rem, 128), (unsigned)B), 128, 0, stream>>>(y, Pr, wo, a0, Po, c0, rem, D, O, lay.remE[0],
+                                                                                                        lay.remC[0], T, nfull << K);
+            FB2_LAUNCH_CHECK();
+        }
         int64_t dl = rem;
         int which = 0;
         for (int l = 0; l < K; ++l) {
@@ -2370,6 +2450,9 @@ static int kalman_chain_run(const float* y, const float* Lam, const float* Pr, c
             const int64_t lreg = lp - (tail_pair ? 1 : 0);
             const bool last = l == K - 1;
             ea.ein = lay.remE[which]; ea.cin = lay.remC[which]; ea.in_T = dl;
+            if (l == 0 && eta_in) {  // given elements: the remainder's level-0 elements are the tail of the caller's arrays (chain stride T)
+                ea.ein = eta_in + (nfull << K) * n; ea.cin = c_in + (nfull << K); ea.in_T = T;
+            }
             ea.eout = last ? kE : lay.remE[which ^ 1];
             ea.cout = last ? kC : lay.remC[which ^ 1];
             ea.out_T = last ? dK : ndl;
@@ -2630,7 +2713,13 @@ extern "C" size_t fb2_gaussian_chain_workspace_bytes(int64_t B, int64_t T, int32
         per += align_up((size_t)B * tt * n * n * 4) + align_up((size_t)B * tt * n * 4) + align_up((size_t)B * tt * 4);
     (void)gauss_elem_floats;
     const size_t tree = per + align_up(4) + 256;
-    const size_t homog = T >= 2 ? homog_workspace_bytes(B, T, D) : 0;
+    size_t homog = T >= 2 ? homog_workspace_bytes(B, T, D) : 0;
+    if (T >= 2 && B >= 1) {  // the tile walk of the homogeneous chain (kalman_chain_run with given elements)
+        const int DT = D <= 4 ? 4 : D <= 8 ? 8 : D <= 16 ? 16 : 32;
+        size_t used = 0;
+        kalman_layout(nullptr, 0, B, T, D, DT, true, &used);
+        if (used + 256 > homog) homog = used + 256;
+    }
     return tree > homog ? tree : homog;
 }
 
@@ -2701,6 +2790,14 @@ static int gaussian_chain_impl(const float* Lam, const float* eta, const float* 
     {
         const char* tree_env = getenv("FB2_GAUSS_HOMOG_TREE");
         if (homog && T >= 4 && B <= 65535 && !(tree_env && tree_env[0] == '1')) {
+            // the tile walk (elements read from eta / c): first K levels per tile without touching memory (FB2_GAUSS_HOMOG_TILES=0: level by level)
+            const char* tiles_env = getenv("FB2_GAUSS_HOMOG_TILES");
+            if (T >= 64 && !(tiles_env && tiles_env[0] == '0')) {
+                if (D <= 4) return kalman_chain_run<4>(nullptr, Lam, nullptr, nullptr, nullptr, nullptr, nullptr, B, T, D, 1, Lo, eo, co, workspace, workspace_bytes, stream, eta, c);
+                if (D <= 8) return kalman_chain_run<8>(nullptr, Lam, nullptr, nullptr, nullptr, nullptr, nullptr, B, T, D, 1, Lo, eo, co, workspace, workspace_bytes, stream, eta, c);
+                if (D <= 16) return kalman_chain_run<16>(nullptr, Lam, nullptr, nullptr, nullptr, nullptr, nullptr, B, T, D, 1, Lo, eo, co, workspace, workspace_bytes, stream, eta, c);
+                return kalman_chain_run<32>(nullptr, Lam, nullptr, nullptr, nullptr, nullptr, nullptr, B, T, D, 1, Lo, eo, co, workspace, workspace_bytes, stream, eta, c);
+            }
             if (D <= 4) return homog_chain_run<4>(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream);
             if (D <= 8) return homog_chain_run<8>(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream);
             if (D <= 16) return homog_chain_run<16>(Lam, eta, c, B, T, D, Lo, eo, co, workspace, workspace_bytes, stream);

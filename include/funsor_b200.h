@@ -187,7 +187,8 @@ int fb2_gaussian_pair_combine_f32(const float* Lx, const float* ex, const float*
 /* eta          : eta[b,t] = P[b] w[b,t], c[b,t] = s[b,t] - |w[b,t]|^2/2 for a TIME-INVARIANT prec_sqrt P[b] (GaussianHMM with
  *                homogeneous dynamics, pyro/hmm.py:258-270: only white_vec depends on t).
  * chain_homog  : the same scan for Lam[B,2D,2D] shared by all time steps of a chain (eta[B,T,2D], c[B,T] per step): the
- *                T-sized precision array is never materialised and level 1 reads Lam[b] for both operands.
+ *                T-sized precision array is never materialised; per-level precision operators once per chain, then the tile walk of
+ *                kalman_chain below with the elements read from eta / c (T >= 64; FB2_GAUSS_HOMOG_TILES=0: level-by-level sweeps).
  */
 /* kalman_eta   : the same per-step (eta, c) for a GaussianHMM with fixed dynamics, computed straight from the observations y[B,T,O]
  *                (pyro/hmm.py:258-270 with matrix_and_mvn_to_funsor pyro/convert.py:278-298 and the value substitution gaussian.py:723-744):

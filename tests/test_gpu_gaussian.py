@@ -210,9 +210,14 @@ def test_kalman_fused_tiles_are_bit_identical_to_the_level_by_level_path(fg, mon
         consts = fg.kalman_constants(*args[:6])
         got = fg.kalman_chain_fused(consts, args[6])
         if T >= 4:
-            want = fg.gaussian_chain_info_homog(*fg.kalman_eta_from_constants(consts, args[6]))
-            for a, b in zip(got, want):
+            elems = fg.kalman_eta_from_constants(consts, args[6])
+            monkeypatch.setenv("FB2_GAUSS_HOMOG_TILES", "0")  # the level-by-level path
+            want = fg.gaussian_chain_info_homog(*elems)
+            monkeypatch.setenv("FB2_GAUSS_HOMOG_TILES", "1")  # the tile walk over given elements (what the funsor rule reaches)
+            given = fg.gaussian_chain_info_homog(*elems)
+            for a, b, c in zip(got, want, given):
                 assert torch.equal(a, b), "T={} K={}: max diff {}".format(T, K, (a - b).abs().max().item())
+                assert torch.equal(c, b), "given elements, T={} K={}: max diff {}".format(T, K, (c - b).abs().max().item())
         w, P, s = fg.kalman_elements_sqrt(*args)
         ref = fg.gaussian_sequential_sum_product(*fg.sqrt_to_info(w, P, s))
         for a, b in zip(got, ref):
@@ -231,9 +236,14 @@ def test_kalman_tensor_core_tiles_match_the_level_by_level_path(fg, monkeypatch,
         consts = fg.kalman_constants(*args[:6])
         got = fg.kalman_chain_fused(consts, args[6])
         if T >= 4:
-            want = fg.gaussian_chain_info_homog(*fg.kalman_eta_from_constants(consts, args[6]))
-            for a, b in zip(got, want):
+            elems = fg.kalman_eta_from_constants(consts, args[6])
+            monkeypatch.setenv("FB2_GAUSS_HOMOG_TILES", "0")  # the level-by-level path
+            want = fg.gaussian_chain_info_homog(*elems)
+            monkeypatch.setenv("FB2_GAUSS_HOMOG_TILES", "1")  # the tensor-core tile walk over given elements
+            given = fg.gaussian_chain_info_homog(*elems)
+            for a, b, c in zip(got, want, given):
                 close_norm(host(a), host(b), 5e-6)
+                close_norm(host(c), host(b), 5e-6)
         w, P, s = fg.kalman_elements_sqrt(*args)
         ref = fg.gaussian_sequential_sum_product(*fg.sqrt_to_info(w, P, s))
         for a, b in zip(got, ref):
