@@ -2277,6 +2277,89 @@ __global__ void __launch_bounds__(KTC_WARPS * 32, KTC_WARPS <= 6 ? 2 : 1) gaussi
     }
 }
 
+// gaussian_eta_tc: eta[b,t] = P[b] w[b,t], c[b,t] = s[b,t] - |w[b,t]|^2 / 2 for dim, rank <= 64 as a batched [T x rank] [rank x dim] GEMM on
+// the tensor pipe (3xTF32, same fragment conventions as gaussian_kalman_tile_tc): a warp owns 16 steps, P' sits in shared memory as split B
+// fragments, the A fragments come straight from w (float2 per k8-step and row).  The thread-per-step FFMA kernel (gaussian_eta_c) is bound
+// by its broadcast operand loads: 4.0 ms at BASELINE config 4's size.
+constexpr int ETC_WARPS = 8;
+constexpr int ETC_REPS = 8;
+__global__ void __launch_bounds__(ETC_WARPS * 32) gaussian_eta_tc(const float* __restrict__ w, const float* __restrict__ P, const float* __restrict__ sc, int64_t T,
+                                                                  int n, int r, float* __restrict__ eta, float* __restrict__ c) {
+    __shared__ float4 sB[8 * 8 * 32];  // [kb][nb][lane] {hi(k0), hi(k0 + 1), lo(k0), lo(k0 + 1)}, B[k = rank index][col = row of P] = P[col][k]
+    const int64_t b = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+    const int KB = (r + 7) / 8, NB = (n + 7) / 8;
+    const float* Pb = P + b * (int64_t)n * r;
+    for (int idx = tid; idx < KB * NB * 32; idx += ETC_WARPS * 32) {
+        const int blk = idx >> 5, ln = idx & 31, kb = blk / NB, nb = blk % NB;
+        const int k0 = 8 * kb + 2 * (ln & 3), col = 8 * nb + (ln >> 2);
+        const float v0 = (col < n && k0 < r) ? Pb[(int64_t)col * r + k0] : 0.f, v1 = (col < n && k0 + 1 < r) ? Pb[(int64_t)col * r + k0 + 1] : 0.f;
+        const float h0 = __uint_as_float((__float_as_uint(v0) + 0x1000u) & 0xFFFFE000u), h1 = __uint_as_float((__float_as_uint(v1) + 0x1000u) & 0xFFFFE000u);
+        sB[(kb * 8 + nb) * 32 + ln] = make_float4(h0, h1, v0 - h0, v1 - h1);
+    }
+    __syncthreads();
+    // ETC_REPS tiles of 16 steps per warp: the operator fragments above are formed once per CTA
+#pragma unroll 1
+    for (int rep = 0; rep < ETC_REPS; ++rep) {
+    const int64_t t0 = (((int64_t)blockIdx.x * ETC_REPS + rep) * ETC_WARPS + warp) * 16;
+    if (t0 >= T) return;
+    const int64_t tr[2] = {t0 + g, t0 + g + 8};
+    const bool live[2] = {tr[0] < T, tr[1] < T};
+    const float* wp[2] = {w + (b * T + (live[0] ? tr[0] : t0)) * r, w + (b * T + (live[1] ? tr[1] : t0)) * r};
+    const bool wvec = (r % 2 == 0) && (reinterpret_cast<uintptr_t>(w) % 8 == 0);
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    float ww0 = 0.f, ww1 = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+        if (kb < KB) {
+            float x[2][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k0 = 8 * kb + 2 * tig;
+                if (wvec && k0 + 1 < r) {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(wp[h] + k0));
+                    x[h][0] = v.x;
+                    x[h][1] = v.y;
+                } else {
+                    x[h][0] = k0 < r ? __ldg(wp[h] + k0) : 0.f;
+                    x[h][1] = k0 + 1 < r ? __ldg(wp[h] + k0 + 1) : 0.f;
+                }
+            }
+            ww0 = fmaf(x[0][0], x[0][0], fmaf(x[0][1], x[0][1], ww0));
+            ww1 = fmaf(x[1][0], x[1][0], fmaf(x[1][1], x[1][1], ww1));
+            const KtcFrag a = ktc_split(x[0][0], x[0][1], x[1][0], x[1][1]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < NB) ktc_mma3(acc[j], a, sB[(kb * 8 + j) * 32 + lane]);
+        }
+    }
+    ww0 = ktc_quad_sum(ww0);
+    ww1 = ktc_quad_sum(ww1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (!live[h]) continue;
+        const int64_t e = b * T + tr[h];
+        float* eo = eta + e * n;
+        const bool st2 = (n % 2 == 0) && (reinterpret_cast<uintptr_t>(eta) % 8 == 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = 8 * j + 2 * tig;
+            if (st2 && col + 1 < n) {
+                *reinterpret_cast<float2*>(eo + col) = make_float2(acc[j][2 * h], acc[j][2 * h + 1]);  // a quad writes one 32-byte sector
+            } else {
+                if (col < n) eo[col] = acc[j][2 * h];
+                if (col + 1 < n) eo[col + 1] = acc[j][2 * h + 1];
+            }
+        }
+        if (tig == 0) c[e] = (sc ? sc[e] : 0.f) - 0.5f * (h ? ww1 : ww0);
+    }
+    }
+}
+
 // A side stream per device and host thread (the fork / join events belong to one call at a time).
 struct GaussSide {
     cudaStream_t stream = nullptr;
@@ -2687,6 +2770,15 @@ extern "C" int fb2_gaussian_eta_f32(const float* w, const float* P, const float*
     FB2_REQUIRE(B >= 0 && T >= 0 && dim >= 1 && rank >= 0, "bad extents");
     if (B * T == 0) return FB2_OK;
     FB2_REQUIRE(dim <= 2 * GMAXD && B <= 65535, "gaussian_eta: dim=%d or B=%lld out of range", dim, (long long)B);
+    {
+        const char* tc_env = getenv("FB2_GAUSS_ETA_TC");  // 0: the thread-per-step FFMA kernel
+        if (dim <= 64 && rank <= 64 && T >= 64 && !(tc_env && tc_env[0] == '0')) {
+            gaussian_eta_tc<<<dim3((unsigned)ceil_div(T, ETC_WARPS * 16 * ETC_REPS), (unsigned)B), ETC_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(w, P, s, T, dim,
+                                                                                                                                 rank, eta, c);
+            FB2_LAUNCH_CHECK();
+            return FB2_OK;
+        }
+    }
     const size_t smem = (size_t)dim * ((rank + 3) / 4 * 4) * sizeof(float);
     FB2_REQUIRE(smem <= 200 * 1024, "gaussian_eta: prec_sqrt of %d x %d does not fit in shared memory", dim, rank);
     const dim3 grid((unsigned)ceil_div(T, ETA_THREADS), (unsigned)B);
