@@ -414,6 +414,31 @@ __device__ __forceinline__ void cg2_mma(uint32_t d_tmem, uint64_t a_desc, uint64
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// bf16 side planes: K-major rows of 32 bf16 = 64 bytes, 64-byte swizzle, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t cg2_desc16(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ void cg2_mma16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cg_pack_bf16(float lo, float hi) {  // {upper half: hi, lower half: lo}, round to nearest
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// One 16-byte piece (4 fp32 = k 4 jl .. 4 jl + 3 of row r) of a raw tile -> 8 bytes in each bf16 side plane (v and lo = v - trunc_tf32(v)):
+// rows of 64 bytes, 16-byte pieces xor-swizzled with (r >> 1) & 3.
+__device__ __forceinline__ void cg2_side16(unsigned char* plane_v, unsigned char* plane_lo, int r, int jl, const float4 v) {
+    const float4 lo = cg_lo4(v);
+    const int off = r * 64 + (((jl >> 1) ^ ((r >> 1) & 3)) << 4) + ((jl & 1) << 3);
+    *reinterpret_cast<uint2*>(plane_v + off) = make_uint2(cg_pack_bf16(v.x, v.y), cg_pack_bf16(v.z, v.w));
+    *reinterpret_cast<uint2*>(plane_lo + off) = make_uint2(cg_pack_bf16(lo.x, lo.y), cg_pack_bf16(lo.z, lo.w));
+}
 __device__ __forceinline__ void cg2_wait_cluster(uint32_t bar, uint32_t parity) {  // arrivals may come from the peer CTA
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -521,13 +546,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS, 1)
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (lane == 0) {
                             const uint32_t ah = cg_u32(smem + (size_t)s * CG2_STAGE_BYTES), al = ah + CG2_A_PLANE, bh = ah + 2 * CG2_A_PLANE, bl = bh + CG2_B_PLANE;
+                            if (!(a.mode & 8)) {  // default: 3xTF32 (lo planes in fp32)
 #pragma unroll
-                            for (int ks = 0; ks < CG2_KC / 8; ++ks) {
-                                const uint64_t dah = cg2_desc(ah + ks * 32), dal = cg2_desc(al + ks * 32);
-                                const uint64_t dbh = cg2_desc(bh + ks * 32), dbl = cg2_desc(bl + ks * 32);
-                                cg2_mma(tmem, dah, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
-                                cg2_mma(tmem + CG_BN, dal, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
-                                cg2_mma(tmem + CG_BN, dah, dbl, IDESC, 1u);
+                                for (int ks = 0; ks < CG2_KC / 8; ++ks) {
+                                    const uint64_t dah = cg2_desc(ah + ks * 32), dal = cg2_desc(al + ks * 32);
+                                    const uint64_t dbh = cg2_desc(bh + ks * 32), dbl = cg2_desc(bl + ks * 32);
+                                    cg2_mma(tmem, dah, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                                    cg2_mma(tmem + CG_BN, dal, dbh, IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+                                    cg2_mma(tmem + CG_BN, dah, dbl, IDESC, 1u);
+                                }
+                            } else {
+                                // FB2_CG_MODE=8 (measured, not the default): hi x hi in TF32 (4 instructions per chunk of 32 k), the two side
+                                // products (2^-10 of the result) in bf16 with K = 16 per instruction: [A lo16 x B v16] + [A v16 x B lo16] -- 8 tensor
+                                // instructions per chunk instead of 12.  Parity-green, but 1.52-1.57 vs 1.48 us per step at S = 512: the loop is bound
+                                // by the transform warps and shared-memory traffic, not by tensor issue, and the bf16 packing adds transform work.
+                                constexpr uint32_t IDESC16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((256u >> 4) << 24);
+                                const uint32_t av16 = al, al16 = al + CG2_A_PLANE / 2, bv16 = bl, bl16 = bl + CG2_B_PLANE / 2;
+#pragma unroll
+                                for (int ks = 0; ks < CG2_KC / 8; ++ks)
+                                    cg2_mma(tmem, cg2_desc(ah + ks * 32), cg2_desc(bh + ks * 32), IDESC, (c > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+                                for (int ks = 0; ks < CG2_KC / 16; ++ks) {
+                                    cg2_mma16(tmem + CG_BN, cg2_desc16(al16 + ks * 32), cg2_desc16(bv16 + ks * 32), IDESC16, (c > 0 || ks > 0) ? 1u : 0u);
+                                    cg2_mma16(tmem + CG_BN, cg2_desc16(av16 + ks * 32), cg2_desc16(bl16 + ks * 32), IDESC16, 1u);
+                                }
                             }
                             cg2_commit_both(cg_u32(&s_empty[s]));
                             if (c == nchunks - 1) cg2_commit_both(cg_u32(&s_tfull));
@@ -547,6 +589,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS, 1)
                     const int s = (int)(gc % CG2_STAGES);
                     cg_wait(cg_u32(&s_full[s]), (uint32_t)((gc / CG2_STAGES) & 1));
                     unsigned char* st = smem + (size_t)s * CG2_STAGE_BYTES;
+                    const bool side16 = (a.mode & 8) != 0;
                     if (ksc) {
                         for (int ci = xt; ci < CG2_A_PLANE / 16; ci += CG_XF_WARPS * 32) {
                             const int r = ci >> 3, jl = (ci & 7) ^ (r & 7);
@@ -554,7 +597,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS, 1)
                             float4 v = *reinterpret_cast<float4*>(st + ci * 16);
                             v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w;
                             *reinterpret_cast<float4*>(st + ci * 16) = v;
-                            *reinterpret_cast<float4*>(st + CG2_A_PLANE + ci * 16) = cg_lo4(v);
+                            if (side16) cg2_side16(st + CG2_A_PLANE, st + CG2_A_PLANE + CG2_A_PLANE / 2, r, jl, v);
+                            else *reinterpret_cast<float4*>(st + CG2_A_PLANE + ci * 16) = cg_lo4(v);
+                        }
+                    } else if (side16) {
+#pragma unroll
+                        for (int i = 0; i < (CG2_A_PLANE / 16 + CG_XF_WARPS * 32 - 1) / (CG_XF_WARPS * 32); ++i) {
+                            const int ci = xt + i * CG_XF_WARPS * 32;
+                            if (ci < CG2_A_PLANE / 16) {
+                                const int r = ci >> 3, jl = (ci & 7) ^ (r & 7);
+                                cg2_side16(st + CG2_A_PLANE, st + CG2_A_PLANE + CG2_A_PLANE / 2, r, jl, *reinterpret_cast<const float4*>(st + ci * 16));
+                            }
                         }
                     } else {
 #pragma unroll
@@ -567,7 +620,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS, 1)
 #pragma unroll
                     for (int i = 0; i < (CG2_B_PLANE / 16 + CG_XF_WARPS * 32 - 1) / (CG_XF_WARPS * 32); ++i) {
                         const int ci = xt + i * CG_XF_WARPS * 32;
-                        if (ci < CG2_B_PLANE / 16) *reinterpret_cast<float4*>(sb + CG2_B_PLANE + ci * 16) = cg_lo4(*reinterpret_cast<const float4*>(sb + ci * 16));
+                        if (ci < CG2_B_PLANE / 16) {
+                            if (side16) {
+                                const int r = ci >> 3, jl = (ci & 7) ^ (r & 7);
+                                cg2_side16(sb + CG2_B_PLANE, sb + CG2_B_PLANE + CG2_B_PLANE / 2, r, jl, *reinterpret_cast<const float4*>(sb + ci * 16));
+                            } else {
+                                *reinterpret_cast<float4*>(sb + CG2_B_PLANE + ci * 16) = cg_lo4(*reinterpret_cast<const float4*>(sb + ci * 16));
+                            }
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -847,7 +907,7 @@ static int cg_launch(const float* a_base, int64_t n_a, const float* b_base, int6
     }
     const int64_t total = (int64_t)tiles * args.n_out;
     const char* two_env = getenv("FB2_CG_2CTA");
-    const bool two = CG_KC == 32 && args.S % 256 == 0 && !(two_env && two_env[0] == '0') && margs.prof == nullptr && margs.mode == 0;
+    const bool two = CG_KC == 32 && args.S % 256 == 0 && !(two_env && two_env[0] == '0') && margs.prof == nullptr && (margs.mode & ~8) == 0;
     if (two) {
         // CTA pairs on 256 x 256 tiles (tcgen05 cta_group::2): the B operand needs a 128-row box
         st = cg_make_map(&mb, b_base, n_b, args.S, CG_KC, 128, true);
