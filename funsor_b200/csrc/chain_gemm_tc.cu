@@ -558,8 +558,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CG_THREADS, 1)
                             } else {
                                 // FB2_CG_MODE=8 (measured, not the default): hi x hi in TF32 (4 instructions per chunk of 32 k), the two side
                                 // products (2^-10 of the result) in bf16 with K = 16 per instruction: [A lo16 x B v16] + [A v16 x B lo16] -- 8 tensor
-                                // instructions per chunk instead of 12.  Parity-green, but 1.52-1.57 vs 1.48 us per step at S = 512: the loop is bound
-                                // by the transform warps and shared-memory traffic, not by tensor issue, and the bf16 packing adds transform work.
+                                // instructions per chunk instead of 12.  Parity-green; alternating A/B: 1.58 vs 1.59 us per step at S = 512, 11.79 vs 12.07 at
+                                // S = 1024: the loop is bound by the transform warps and shared-memory traffic, not by tensor issue.
                                 constexpr uint32_t IDESC16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((256u >> 4) << 24);
                                 const uint32_t av16 = al, al16 = al + CG2_A_PLANE / 2, bv16 = bl, bl16 = bl + CG2_B_PLANE / 2;
 #pragma unroll
