@@ -195,6 +195,215 @@ __global__ void __launch_bounds__(SM_WARPS * 32) hmm_small_forward(SmallArgs p) 
     }
 }
 
+// hmm_small_forward_tc: the same recurrence for MANY chains with a shared transition matrix and only log Z wanted (the batched
+// DiscreteHMM.log_prob of the reference's examples): a warp owns 16 chains = the 16 rows of mma.sync.m16n8k8 tiles, the messages live in
+// C-fragment layout and a step is the small GEMM  V' = V P  [16 x S] [S x S]  in 3xTF32 against P held in shared memory as split B
+// fragments; the C fragments of one step are the A fragments of the next without moving data (k slots permuted: slot tig <-> column
+// 2 tig, slot tig + 4 <-> column 2 tig + 1).  The warp-per-chain kernel above spends one shuffle, one shared-memory load and one FMA
+// per (i, j) pair; here 16 chains share each operand load and the products run on the tensor pipe.
+struct SmallFrag {
+    uint32_t hi[4], lo[4];
+};
+__device__ __forceinline__ SmallFrag small_split(float c0, float c1, float c2, float c3) {  // C fragment -> split A fragment (permuted slots)
+    SmallFrag f;
+    const float v[4] = {c0, c2, c1, c3};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f.hi[i] = (__float_as_uint(v[i]) + 0x1000u) & 0xFFFFE000u;  // round to nearest TF32
+        f.lo[i] = __float_as_uint(v[i] - __uint_as_float(f.hi[i]));
+    }
+    return f;
+}
+__device__ __forceinline__ void small_mma(float (&d)[4], const uint32_t (&a)[4], float b0, float b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+constexpr int SMT_WARPS = 4;
+// NB = padded state count / 8 (1, 2, 4 or 8)
+template <int NB>
+__global__ void __launch_bounds__(SMT_WARPS * 32) hmm_small_forward_tc(SmallArgs p) {
+    extern __shared__ __align__(16) float sm_raw[];
+    constexpr int SP = NB * 8;
+    float4* sB = reinterpret_cast<float4*>(sm_raw);   // [kb][nb][lane] {hi(k0), hi(k0 + 1), lo(k0), lo(k0 + 1)}, B[k = prev][col = curr] = P[k][col]
+    float* sCA = sm_raw + NB * NB * 32 * 4;           // [SP] clamped column maxima
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+    const int S = p.S;
+    for (int j = tid; j < SP; j += SMT_WARPS * 32) {
+        float m = -FLT_MAX;
+        if (j < S)
+            for (int i = 0; i < S; ++i) m = fmaxf(m, p.transpose ? p.A[(int64_t)j * S + i] : p.A[(int64_t)i * S + j]);
+        sCA[j] = j < S ? m : 0.f;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NB * NB * 32; idx += SMT_WARPS * 32) {
+        const int blk = idx >> 5, ln = idx & 31, kb = blk / NB, nb = blk % NB;
+        const int k0 = 8 * kb + 2 * (ln & 3), col = 8 * nb + (ln >> 2);
+        float v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = k0 + h;
+            v[h] = (k < S && col < S) ? expf((p.transpose ? p.A[(int64_t)col * S + k] : p.A[(int64_t)k * S + col]) - sCA[col]) : 0.f;
+        }
+        const float h0 = __uint_as_float((__float_as_uint(v[0]) + 0x1000u) & 0xFFFFE000u), h1 = __uint_as_float((__float_as_uint(v[1]) + 0x1000u) & 0xFFFFE000u);
+        sB[idx] = make_float4(h0, h1, v[0] - h0, v[1] - h1);
+    }
+    __syncthreads();
+    const int64_t b_base = ((int64_t)blockIdx.x * SMT_WARPS + warp) * 16;
+    if (b_base >= p.B) return;
+    const int64_t br[2] = {b_base + g, b_base + g + 8};
+    const bool live[2] = {br[0] < p.B, br[1] < p.B};
+    const int64_t OT = p.obs_T ? p.obs_T : p.T;
+    const float* obs_r[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) obs_r[h] = p.obs ? p.obs + (live[h] ? br[h] : b_base) * OT * S : nullptr;  // a missing chain repeats chain 0 of the warp (not stored)
+    auto row_of = [&](int64_t t) { return p.reverse ? (p.T - 1 - t) : t; };
+    float ca[NB][2];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+        ca[nb][0] = sCA[8 * nb + 2 * tig];
+        ca[nb][1] = sCA[8 * nb + 2 * tig + 1];
+    }
+    // x (log2 domain, rows g / g + 8 of every column block) -> v = w * 2^(x - n), n = ceil(row max); E += n + renormalisation exponent
+    float v[NB][4];
+    long long E[2] = {0, 0};
+    auto apply = [&](const float (&w)[NB][4], const float (&x)[NB][4]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float xm = -INFINITY;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) xm = fmaxf(xm, fmaxf(x[nb][2 * h], x[nb][2 * h + 1]));
+            xm = quad_max(xm);
+            const bool any = xm > -1e30f;
+            const float nf = any ? ceilf(xm) : 0.f;
+            float m = 0.f;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float val = w[nb][2 * h + e] * (any ? exp2f(x[nb][2 * h + e] - nf) : 0.f);
+                    v[nb][2 * h + e] = val;
+                    m = fmaxf(m, val);
+                }
+            }
+            // NaN / inf anywhere in the row must not be hidden by fmaxf: test the sum as well
+            float chk = 0.f;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) chk += v[nb][2 * h] + v[nb][2 * h + 1];
+            chk = quad_sum(chk);
+            m = quad_max(m);
+            int q = 0;
+            if (m > 0.f && chk <= FLT_MAX) {
+                int extra = 0;
+                float pre = 1.f;
+                if (m < 1e-20f) {
+                    pre = 0x1p64f;
+                    m *= 0x1p64f;
+                    extra = -64;
+                }
+                const int qq = ((__float_as_int(m) >> 23) & 0xFF) - 127;
+                const float sc = __int_as_float((127 - qq) << 23);
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    v[nb][2 * h] = (v[nb][2 * h] * pre) * sc;
+                    v[nb][2 * h + 1] = (v[nb][2 * h + 1] * pre) * sc;
+                }
+                q = qq + extra;
+            }
+            E[h] += (long long)nf + q;
+        }
+    };
+    {
+        float ones[NB][4], x[NB][4];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int h = e >> 1, col = 8 * nb + 2 * tig + (e & 1);
+                ones[nb][e] = 1.f;
+                x[nb][e] = col < S ? (p.init ? p.init[(live[h] ? br[h] : b_base) * p.init_sb + col] : 0.f) * kLog2eS : -INFINITY;
+            }
+        apply(ones, x);
+    }
+    const bool ovec = (S % 2 == 0) && p.obs && (reinterpret_cast<uintptr_t>(p.obs) % 8 == 0);
+    float ob_next[NB][4];
+    auto load_obs = [&](int64_t t) {
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = 8 * nb + 2 * tig;
+                float o0 = 0.f, o1 = 0.f;
+                if (obs_r[h] && t < p.T) {
+                    const float* src = obs_r[h] + row_of(t) * S + col;
+                    if (ovec) {
+                        if (col < S) {
+                            const float2 o = __ldg(reinterpret_cast<const float2*>(src));
+                            o0 = o.x;
+                            o1 = o.y;
+                        }
+                    } else {
+                        if (col < S) o0 = __ldg(src);
+                        if (col + 1 < S) o1 = __ldg(src + 1);
+                    }
+                }
+                ob_next[nb][2 * h] = o0;
+                ob_next[nb][2 * h + 1] = o1;
+            }
+    };
+    load_obs(0);
+#pragma unroll 1
+    for (int64_t t = 0; t < p.T; ++t) {
+        float x[NB][4];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = 8 * nb + 2 * tig + (e & 1);
+                x[nb][e] = col < S ? (ob_next[nb][e] + ca[nb][e & 1]) * kLog2eS : -INFINITY;
+            }
+        load_obs(t + 1);  // the next row travels while this step computes
+        float acc[NB][4];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[nb][e] = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < NB; ++kb) {
+            const SmallFrag a = small_split(v[kb][0], v[kb][1], v[kb][2], v[kb][3]);
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const float4 bf = sB[(kb * NB + nb) * 32 + lane];
+                small_mma(acc[nb], a.lo, bf.x, bf.y);
+                small_mma(acc[nb], a.hi, bf.z, bf.w);
+                small_mma(acc[nb], a.hi, bf.x, bf.y);
+            }
+        }
+        apply(acc, x);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float tot = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) tot += v[nb][2 * h] + v[nb][2 * h + 1];
+        tot = quad_sum(tot);
+        if (live[h] && tig == 0) {
+            const double z = tot > 0.f ? (double)E[h] * 0.69314718055994530942 + log((double)tot) : (tot == tot ? -INFINITY : (double)tot);
+            if (p.logZ) p.logZ[br[h]] = (float)z;
+            if (p.logZ_d) p.logZ_d[br[h]] = z;
+        }
+    }
+}
+
 // Max-plus twin (Viterbi for small state spaces): lane j scans the predecessors i in ascending order with a strict '>' on
 //   delta[i] + (A[i,j] + obs[t,j])      (the reference's evaluation order, hmm.py:130; first maximiser wins)
 // so values and back-pointers are bit-identical to the serial fp32 recurrence.  A is kept in shared memory untransformed.
@@ -314,6 +523,22 @@ int hmm_small_forward_device(int semiring, const float* init, int64_t init_sb, c
         FB2_CUDA(cudaFuncSetAttribute(hmm_small_maxplus<NJv, NLv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         hmm_small_maxplus<NJv, NLv><<<grid, SM_WARPS * 32, smem, stream>>>(a, backptr, last);                                   \
     } while (0)
+    // 16 chains per warp on the tensor pipe: a win once there are far more chains than the GPU holds warps (measured, T = 1000: S = 16,
+    // B = 16384: 2.27 -> 0.72 ms; S = 8, B = 65536: 1.52 -> 0.24 ms; but S = 16, B = 1024: 0.37 -> 0.61 ms and S >= 32 at B = 4096 no gain: a
+    // step of a 16-chain warp is a longer dependent chain than a step of a one-chain warp).  FB2_SMALL_TC=1 forces it, 0 switches it off.
+    const char* tc_env = getenv("FB2_SMALL_TC");
+    const bool tc_forced = tc_env && tc_env[0] == '1', tc_off = tc_env && tc_env[0] == '0';
+    if (semiring == FB2_SEMIRING_LOG && a_sb == 0 && !alpha_all && !ell_all && !tc_off && (tc_forced || (S <= 16 && B >= 8192))) {
+        const int NB = S <= 8 ? 1 : S <= 16 ? 2 : S <= 32 ? 4 : 8;
+        const size_t smem_tc = ((size_t)NB * NB * 32 * 4 + NB * 8) * sizeof(float);
+        const unsigned grid_tc = (unsigned)ceil_div(B, SMT_WARPS * 16);
+        if (NB == 1) hmm_small_forward_tc<1><<<grid_tc, SMT_WARPS * 32, smem_tc, stream>>>(a);
+        else if (NB == 2) hmm_small_forward_tc<2><<<grid_tc, SMT_WARPS * 32, smem_tc, stream>>>(a);
+        else if (NB == 4) hmm_small_forward_tc<4><<<grid_tc, SMT_WARPS * 32, smem_tc, stream>>>(a);
+        else hmm_small_forward_tc<8><<<grid_tc, SMT_WARPS * 32, smem_tc, stream>>>(a);
+        FB2_LAUNCH_CHECK();
+        return FB2_OK;
+    }
     if (semiring == FB2_SEMIRING_MAX) {
         if (S <= 8) FB2_SMALLMAX(1, 8);
         else if (S <= 16) FB2_SMALLMAX(1, 16);

@@ -523,6 +523,32 @@ def test_hmm_forward_flow_four_byte_words_stamp_wrap(fb):
     rel_close(host(got), host(want), rtol=RTOL)
 
 
+@pytest.mark.parametrize("B,T,S", [(1, 7, 5), (16, 40, 16), (33, 25, 8), (100, 60, 33), (70, 30, 64), (17, 5, 50), (8200, 12, 16)])
+def test_hmm_forward_small_state_space_tensor_core_batches(fb, monkeypatch, B, T, S):
+    """hmm_small_forward_tc (16 chains per warp as mma.sync rows, P as split-TF32 B fragments; the default for S <= 16 and B >= 8192,
+    forced here): log Z against the float64 oracle incl. -inf transitions, a dead chain and an impossible observation."""
+    monkeypatch.setenv("FB2_SMALL_TC", "1")
+    g = torch.Generator().manual_seed(B * 1000 + S)
+    init = torch.randn(B, S, generator=g).log_softmax(-1)
+    A = torch.randn(S, S, generator=g)
+    if S > 2:
+        A[0, 1] = -float("inf")
+        A[:, 2] = -float("inf")  # unreachable state
+    A = A.log_softmax(-1)
+    obs = torch.randn(B, T, S, generator=g) * 3 - 20.0
+    if B > 2 and T > 3:
+        obs[1, 3, :] = -float("inf")  # impossible observation -> logZ = -inf, not NaN
+        init[2, :] = -float("inf")
+        init[2, S - 1] = 0.0  # deterministic start
+    n0 = fb.launch_count(reset=True)
+    got = host(fb.hmm_forward(init.cuda(), A.cuda(), obs.cuda()))
+    want = R.hmm_forward(R.LOG, init.double().numpy(), A.double().numpy(), obs.double().numpy())
+    assert not np.isnan(got).any()
+    if B > 2 and T > 3:
+        assert np.isneginf(got[1])
+    rel_close(got, want, rtol=RTOL, atol=1.0)
+
+
 # ------------------------------------------------------------------ streaming max-plus kernel (Viterbi, S >= 256, shared A)
 @pytest.mark.parametrize("B,T,S", [(1, 60, 4096), (5, 40, 1000), (4, 25, 257), (2, 33, 300), (9, 7, 512), (1, 30, 2500), (2, 20, 3000), (3, 9, 2401)])
 def test_viterbi_stream_bit_exact(fb, B, T, S):
