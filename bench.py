@@ -603,7 +603,21 @@ def extra_measurements(device):
     out["marginals"] = {"units_per_s": 3.0 * Tm * Sm * Sm / sec, "us_per_step": sec * 1e6 / Tm, "S": Sm, "B": 1, "T": Tm, "ms": sec * 1e3,
                         "note": "forward + backward dataflow passes + gamma + xi_sum (outer-product GEMM over time); 3 T S^2 units"}
     sec = timeit(lambda: fb.hmm_forward(im, Am, om), n=2)
-    out["forward_S512_B1"] = {"units_per_s": Tm * Sm * Sm / sec, "us_per_step": sec * 1e6 / Tm, "ms": sec * 1e3, "kernel": "hmm_direct_forward<8> (single-hop dataflow kernel)"}
+    out["forward_S512_B1"] = {"units_per_s": Tm * Sm * Sm / sec, "us_per_step": sec * 1e6 / Tm, "ms": sec * 1e3,
+                              "kernel": "hmm_flow_forward<4,1,8,true> (two-hop dataflow kernel, 4-byte words; the single-hop kernel serves forward-backward)"}
+    # many short chains with a small state space (the batched DiscreteHMM.log_prob of the reference's examples: hidden_dim 16)
+    Bs, Ts, Ss = 16384, 1000, 16
+    As = torch.randn(Ss, Ss, device=device, generator=g).log_softmax(-1)
+    os_ = torch.randn(Bs, Ts, Ss, device=device, generator=g)
+    is_ = torch.randn(Bs, Ss, device=device, generator=g).log_softmax(-1)
+    sec = timeit(lambda: fb.hmm_forward(is_, As, os_), n=3)
+    small_bytes = 4.0 * Bs * Ts * Ss
+    out["forward_S16_B16384"] = {"units_per_s": Bs * Ts * Ss * Ss / sec, "chain_steps_per_s": Bs * Ts / sec, "ms": sec * 1e3, "S": Ss, "B": Bs, "T": Ts,
+                                 "kernel": "hmm_small_forward_tc<2> (16 chains per warp as mma.sync rows, 3xTF32 against P in shared memory)",
+                                 "roofline": {"bound": "hbm", "achieved": small_bytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                              "frac": small_bytes / sec / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": small_bytes,
+                                              "note": "the observations are read once; a step of a 16-chain warp is a dependent chain of ~0.3 us"}}
+    del As, os_, is_
     # forward-filter backward-sample on the same chain: 64 posterior paths
     Ns = 64
     us = torch.rand(1, Ns, Tm + 1, device=device, generator=g)
