@@ -1,4 +1,6 @@
-"""C3 shape (Viterbi, S = 4096, B = 1): lines in flight per thread in the streaming kernel (8 / 16 / 32); paths must be identical."""
+"""C3 shape (Viterbi, S = 4096, B = 1): lines in flight per thread in the streaming kernel (8 / 16 / 32); paths must be identical.
+The template variants behind FB2_VITERBI_DEEP were removed from the library after this measurement (DESIGN.md section 4.2 records
+the numbers); with the current library the three columns time the same kernel."""
 import os, sys
 sys.path.insert(0, "/root/repo")
 import torch
