@@ -648,8 +648,9 @@ template <int DT>
 __device__ void homog_pair_cta(const float (*X)[2 * DT + 1], const float (*Y)[2 * DT + 1], float (*Z)[2 * DT + 1], HomogLevelsSmem<DT>& sm, int D,
                                float* opU, float* opLinv, float* konst, int32_t* flag) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // ---- phase 1 (warp 0): Cholesky of M = X_cc + Y_aa, lane = row
-    if (warp == 0) {
+    // ---- phase 1: Cholesky of M = X_cc + Y_aa, lane = row.  Every warp runs it (the others would only wait) and warp 0 stores: inside an
+    //      `if (warp == 0)` region ptxas wraps each of the ~530 shuffles in a WARPSYNC.COLLECTIVE sequence (measured: 7.8-13k cycles per pair).
+    {
         float m[DT];
 #pragma unroll
         for (int k = 0; k < DT; ++k) m[k] = (lane < D && k < D) ? X[DT + k][DT + lane] + Y[k][lane] : (k == lane ? 1.f : 0.f);
@@ -672,15 +673,17 @@ __device__ void homog_pair_cta(const float (*X)[2 * DT + 1], const float (*Y)[2 
 #pragma unroll
             for (int k = j + 1; k < DT; ++k) m[k] = fmaf(-lij, __shfl_sync(0xffffffffu, lij, k), m[k]);
         }
-        if (lane < DT) {
-#pragma unroll
-            for (int k = 0; k < DT; ++k) sm.L[lane][k] = m[k];
-            sm.L[lane][lane] = dinv;
-        }
         bad = __any_sync(0xffffffffu, bad);
-        if (lane == 0) {
-            sm.logdet = logdet;
-            if (bad && flag) atomicExch(flag, 1);
+        if (warp == 0) {
+            if (lane < DT) {
+#pragma unroll
+                for (int k = 0; k < DT; ++k) sm.L[lane][k] = m[k];
+                sm.L[lane][lane] = dinv;
+            }
+            if (lane == 0) {
+                sm.logdet = logdet;
+                if (bad && flag) atomicExch(flag, 1);
+            }
         }
     }
     __syncthreads();
@@ -720,7 +723,32 @@ __device__ void homog_pair_cta(const float (*X)[2 * DT + 1], const float (*Y)[2 
     // ---- phase 3: Z = diag(X_aa, Y_cc) - U'U over the padded layout, 16 entries of one row per thread (rows of 2 DT = 64: 4 threads each)
     constexpr int PER = (2 * DT) * (2 * DT) / 256 < 1 ? 1 : (2 * DT) * (2 * DT) / 256;  // entries per thread
     constexpr int TPR = 2 * DT / PER;                                                       // threads per row
-    if (tid < 2 * DT * TPR) {
+    if constexpr (DT == 32) {
+        // 4 x 4 register tile per thread: two LDS.128 of U feed 16 FMAs per k (a 1 x 16 strip needed five loads); same k order per output
+        const int r0 = (tid >> 4) * 4, s0 = (tid & 15) * 4;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int r = r0 + i, sp = s0 + t, rblk = r / DT, rc = r % DT, sblk = sp / DT, sc = sp % DT;
+                acc[i][t] = (rc < D && sc < D && rblk == sblk) ? (rblk == 0 ? X[sc][rc] : Y[DT + sc][DT + rc]) : 0.f;
+            }
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            const float4 ur = *reinterpret_cast<const float4*>(&sm.U[k][r0]);
+            const float4 us = *reinterpret_cast<const float4*>(&sm.U[k][s0]);
+            const float ura[4] = {ur.x, ur.y, ur.z, ur.w}, usa[4] = {us.x, us.y, us.z, us.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) acc[i][t] = fmaf(-ura[i], usa[t], acc[i][t]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) Z[s0 + t][r0 + i] = acc[i][t];
+    } else if (tid < 2 * DT * TPR) {
         const int r = tid / TPR, s0 = (tid % TPR) * PER;
         const int rblk = r / DT, rc = r % DT;
         float acc[PER];
