@@ -536,7 +536,7 @@ def extra_measurements(device):
                                        "frac": kalman_bytes / sec / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": kalman_bytes,
                                        "note": "algorithmic bytes = the observations y[B,T,O] read once + the [B] results; the tile kernel (half of the time) "
                                                "runs on the tensor pipe (ncu: tensor pipe 69 % active, DRAM read = y), the rest is the serial chain of per-level "
-                                               "precision operators (0.29 ms, one CTA per chain) and the upper levels of the tree (one launch)"},
+                                               "precision operators (0.18 ms, one CTA per chain) and the upper levels of the tree (one launch)"},
                           "fp32": {"mac_per_step": 1280 + 2600, "useful_tflops": 2.0 * (1280 + 2600) * Bk * Tk / sec / 1e12,
                                    "note": "1280 multiply-adds per element (u = wo + y Pr, eta = a0 + Po u) + ~2600 per pair contraction (triangular L^-1 z, U'v), "
                                            "issued as 3xTF32 mma.sync (three tensor instructions per useful product)"},

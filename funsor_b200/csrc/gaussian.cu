@@ -641,6 +641,7 @@ struct HomogLevelsSmem {
     float Lam[4][2 * DT][2 * DT + 1];  // padded layout (a-block rows/cols [0, DT), c-block [DT, 2 DT)): cur regular, cur tail, next regular, next tail
     float L[DT][DT + 1];               // Cholesky factor, diagonal holds 1 / L[k][k]
     float U[DT][2 * DT + 4];           // U = L^-1 G'
+    float col[2][DT < 4 ? 4 : DT];     // column j of L as the warp computes it (broadcast through shared memory instead of 31 - j shuffles)
     float logdet;
     int bad;
 };
@@ -648,9 +649,10 @@ template <int DT>
 __device__ void homog_pair_cta(const float (*X)[2 * DT + 1], const float (*Y)[2 * DT + 1], float (*Z)[2 * DT + 1], HomogLevelsSmem<DT>& sm, int D,
                                float* opU, float* opLinv, float* konst, int32_t* flag) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // ---- phase 1: Cholesky of M = X_cc + Y_aa, lane = row.  Every warp runs it (the others would only wait) and warp 0 stores: inside an
-    //      `if (warp == 0)` region ptxas wraps each of the ~530 shuffles in a WARPSYNC.COLLECTIVE sequence (measured: 7.8-13k cycles per pair).
-    {
+    // ---- phase 1 (warp 0): Cholesky of M = X_cc + Y_aa, lane = row.  Column j of L goes to the other lanes through shared memory: the
+    //      31 - j shuffles per column of the warp-wide kernel are shuffle-throughput bound (8.4k cycles per pair when every warp ran them,
+    //      7.8-13k inside a divergent region, where ptxas wraps each shuffle in a WARPSYNC.COLLECTIVE sequence); same arithmetic.
+    if (warp == 0) {
         float m[DT];
 #pragma unroll
         for (int k = 0; k < DT; ++k) m[k] = (lane < D && k < D) ? X[DT + k][DT + lane] + Y[k][lane] : (k == lane ? 1.f : 0.f);
@@ -658,7 +660,11 @@ __device__ void homog_pair_cta(const float (*X)[2 * DT + 1], const float (*Y)[2 
         int bad = 0;
 #pragma unroll
         for (int j = 0; j < DT; ++j) {
-            float d = __shfl_sync(0xffffffffu, m[j], j);
+            float* colj = sm.col[j & 1];
+            if (lane == j) colj[0] = m[j];  // slot 0 first carries the pivot
+            __syncwarp();
+            float d = colj[0];
+            __syncwarp();
             if (!(d > 0.f)) {
                 bad = 1;
                 d = 1.f;
@@ -670,20 +676,20 @@ __device__ void homog_pair_cta(const float (*X)[2 * DT + 1], const float (*Y)[2 
             if (lane == j) dinv = inv;
             const float lij = lane > j ? m[j] * inv : (lane == j ? ljj : 0.f);
             m[j] = lij;
+            if (lane < DT) colj[lane] = lij;
+            __syncwarp();
 #pragma unroll
-            for (int k = j + 1; k < DT; ++k) m[k] = fmaf(-lij, __shfl_sync(0xffffffffu, lij, k), m[k]);
+            for (int k = j + 1; k < DT; ++k) m[k] = fmaf(-lij, colj[k], m[k]);
         }
         bad = __any_sync(0xffffffffu, bad);
-        if (warp == 0) {
-            if (lane < DT) {
+        if (lane < DT) {
 #pragma unroll
-                for (int k = 0; k < DT; ++k) sm.L[lane][k] = m[k];
-                sm.L[lane][lane] = dinv;
-            }
-            if (lane == 0) {
-                sm.logdet = logdet;
-                if (bad && flag) atomicExch(flag, 1);
-            }
+            for (int k = 0; k < DT; ++k) sm.L[lane][k] = m[k];
+            sm.L[lane][lane] = dinv;
+        }
+        if (lane == 0) {
+            sm.logdet = logdet;
+            if (bad && flag) atomicExch(flag, 1);
         }
     }
     __syncthreads();
@@ -694,24 +700,26 @@ __device__ void homog_pair_cta(const float (*X)[2 * DT + 1], const float (*Y)[2 
         float u[DT];
 #pragma unroll
         for (int k = 0; k < DT; ++k) u[k] = (cc < D && k < D) ? (blk == 0 ? X[DT + k][cc] : Y[k][DT + cc]) : 0.f;
+        // right-looking order: once u[k] is final it is subtracted from every later entry -- per entry the same operations in the same
+        // order as the row-by-row form of gauss_pair_body (u[i] - L[i][0] u[0] - L[i][1] u[1] - ...), but independent across i
 #pragma unroll
         for (int k = 0; k < DT; ++k) {
-            float acc = u[k];
-#pragma unroll
-            for (int mm = 0; mm < k; ++mm) acc = fmaf(-sm.L[k][mm], u[mm], acc);
-            u[k] = acc * sm.L[k][k];
+            u[k] = u[k] * sm.L[k][k];
             sm.U[k][c] = u[k];
             opU[k * 2 * DT + c] = u[k];
+#pragma unroll
+            for (int i = k + 1; i < DT; ++i) u[i] = fmaf(-sm.L[i][k], u[k], u[i]);
         }
     } else if (warp == (2 * DT + 31) / 32) {
         const int col = lane;
         float x[DT];
 #pragma unroll
-        for (int k = 0; k < DT; ++k) {
-            float acc = k == col ? 1.f : 0.f;
+        for (int k = 0; k < DT; ++k) x[k] = k == col ? 1.f : 0.f;
 #pragma unroll
-            for (int mm = 0; mm < k; ++mm) acc = fmaf(-sm.L[k][mm], x[mm], acc);
-            x[k] = acc * sm.L[k][k];
+        for (int k = 0; k < DT; ++k) {
+            x[k] = x[k] * sm.L[k][k];
+#pragma unroll
+            for (int i = k + 1; i < DT; ++i) x[i] = fmaf(-sm.L[i][k], x[k], x[i]);
         }
         if (col < DT) {
 #pragma unroll
