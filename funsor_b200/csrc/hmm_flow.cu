@@ -441,11 +441,11 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
         const bool chain_ok = tc >= 0 && (b0 + bc) < p.B && colC < S;
         const float* obs_c = (chain_ok && p.obs) ? p.obs + (((b0 + bc) / p.cpo) * p.obs_T) * S + colC : nullptr;
         auto obs_row = [&](int64_t step) { return p.reverse ? (p.T - 1 - step) : step; };
-        int64_t chunk_seen = -1;
+        int64_t chunk_lo = 0, chunk_hi = 0;  // rows [chunk_lo, chunk_hi) are known to have landed (no 64-bit division on the per-step path)
         auto wait_rows = [&](int64_t row) {  // overlapped H2D: block until the chunk holding `row` has landed
             if (!p.ready_flags) return;
+            if (row >= chunk_lo && row < chunk_hi) return;
             const int64_t c = row / p.rows_per_chunk;
-            if (c == chunk_seen) return;
             const long long start = clock64();
             unsigned v;
             do {
@@ -459,7 +459,8 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_flow_forward(FlowArgs p) 
                 }
                 atomicExch(p.abort_flag, 1);
             }
-            chunk_seen = c;
+            chunk_lo = c * p.rows_per_chunk;
+            chunk_hi = chunk_lo + p.rows_per_chunk;
         };
 
         // ---- message before the first step: alpha_{-1} = init
@@ -969,11 +970,11 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_direct_forward(FlowArgs p
             const bool chain_ok = owner && (b0 + bc) < p.B && colC < S;
             const float* obs_c = (chain_ok && p.obs) ? p.obs + (((b0 + bc) / p.cpo) * p.obs_T) * S + colC : nullptr;
             auto obs_row = [&](int64_t step) { return p.reverse ? (p.T - 1 - step) : step; };
-            int64_t chunk_seen = -1;
+            int64_t chunk_lo = 0, chunk_hi = 0;  // rows [chunk_lo, chunk_hi) are known to have landed
             auto wait_rows = [&](int64_t row) {
                 if (!p.ready_flags) return;
+                if (row >= chunk_lo && row < chunk_hi) return;
                 const int64_t ch = row / p.rows_per_chunk;
-                if (ch == chunk_seen) return;
                 const long long start = clock64();
                 unsigned v;
                 do {
@@ -987,7 +988,8 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) hmm_direct_forward(FlowArgs p
                     }
                     atomicExch(p.abort_flag, 1);
                 }
-                chunk_seen = ch;
+                chunk_lo = ch * p.rows_per_chunk;
+                chunk_hi = chunk_lo + p.rows_per_chunk;
             };
             auto publish = [&](unsigned t_stamp, float u, int E15, bool zero) {
                 uint32_t bits = __float_as_uint(u);
